@@ -1,0 +1,27 @@
+// host_caps.hpp -- workspace capacities of the two kernel tiers (see DESIGN.md "workspace tiers").
+// tier 0: sized for the common case (filterfreq 2, a handful of unitigs) so that a warp's slab stays
+//         cache resident; tier 1: sized for anything the 16-bit indices of the kernel can address.
+// A window that overflows tier 0 is re-run in tier 1; one that overflows tier 1 is reported as an error.
+#pragma once
+#include "window_core.cuh"
+namespace dcu_host {
+inline int ceil_pow2_log(int v) { int l = 4; while ((1 << l) < v) ++l; return l; }
+inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
+  dcu::Caps c;
+  c.S = maxS < 4 ? 4 : maxS;
+  c.B = maxB < 64 ? 64 : maxB;
+  c.NI = c.B;
+  c.EX = tier == 0 ? 256 : 4096;
+  c.LOGH = ceil_pow2_log(2 * (c.NI + c.EX));
+  c.H = 1 << c.LOGH;
+  c.BL = w + 8;
+  if (tier == 0) {
+    c.NN = 512; c.ST = 256; c.SL = 2048; c.SF = 4096; c.RL = 512; c.RP = 1024; c.FP = 1024; c.SI = 1024;
+  } else {
+    c.NN = c.NI + c.EX; if (c.NN > 65000) c.NN = 65000;
+    c.ST = 8192; c.SL = 65000; c.SF = 65000; c.RL = 32768; c.RP = 32768; c.FP = 32768; c.SI = 32768;
+  }
+  if (c.NN > c.NI + c.EX) c.NN = c.NI + c.EX;
+  return c;
+}
+}  // namespace dcu_host

@@ -1,0 +1,1146 @@
+// window_core.cuh -- per-window local de Bruijn consensus, one warp per window (sm_100a).
+//
+// Re-design (not a translation) of the per-window body of daccord's HandleContext::operator()
+// (reference src/HandleContext.hpp:2051-2494) and of DebruijnGraph<k> (reference
+// src/DebruijnGraph.hpp:671-5483).  What changed relative to the reference's data structures:
+//   * k-mers live in a warp-cooperative open-addressing hash (atomicCAS insert) instead of a
+//     radix-sorted prenode array + 4^k direct-address table (DebruijnGraph.hpp:2018-2304, :856-858);
+//     node order is never materialised, every tie-break that the reference derives from node
+//     order is taken from the k-mer value instead;
+//   * per-node position histograms PF/RPF (:1930-2009) are plain per-node instance lists; the
+//     positional weight (:3826-3904) is an integer sum over instances of a dense zero-padded
+//     fixed-point table, evaluated on demand (no Afeaspos arrays, :3117-3174);
+//   * the edge-activation heap (:1818-1897) is replaced by a "next frequency class" max-reduction;
+//   * stretches (unitigs, :2844-2986) are (offset,len) views into one link array, split pieces
+//     (:2772-2841) are sub-views; paths are parent-pointer trees instead of copied id lists
+//     (:3934-4105); RMQ + wavelet tree (:3499-3534) are interval scans over <=108 entries;
+//   * candidate scoring and the placement alignment use Myers bit-vector edit distance with a
+//     bit-vector traceback that reproduces the DP tie rule (diagonal, then DEL, then INS).
+// Arithmetic that decides results is kept identical: u64 fixed-point sums, IEEE double adds in
+// the reference's order (compile with -fmad=false), the same thresholds, the same bounded-heap
+// procedure for every weight heap.
+//
+// The file is compiled twice: by nvcc for sm_100a (32 lanes, product) and, for tests only, by
+// g++ with -DDCU_EMU as a single-lane host emulation (tests/emu) so that parity against the
+// oracle can be debugged without a GPU.  The product library contains only the CUDA build.
+#pragma once
+#include <stdint.h>
+#include <float.h>
+#include <stddef.h>
+
+#ifdef DCU_EMU
+#define DCU_FN static inline
+#define DCU_BIG static
+#define DCU_NL 1
+namespace dcu {
+static inline void wsync() {}
+static inline uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
+static inline uint32_t a_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t ballot(bool p) { return p ? 1u : 0u; }
+static inline uint32_t lanemask_lt(int) { return 0; }
+static inline int popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int popcll(uint64_t x) { return __builtin_popcountll(x); }
+template <class T> static inline T bcast(T v, int) { return v; }
+static inline uint32_t red_max_u32(uint32_t v) { return v; }
+static inline uint32_t red_sum_u32(uint32_t v) { return v; }
+static inline uint32_t red_min_u32(uint32_t v) { return v; }
+static inline void red_argmax_d(double&, int&) {}
+template <class T> static inline T ldg(const T* p) { return *p; }
+}
+#else
+#define DCU_FN __device__ __forceinline__
+#define DCU_BIG __device__ __noinline__
+#define DCU_NL 32
+namespace dcu {
+__device__ __forceinline__ void wsync() { __syncwarp(); }
+__device__ __forceinline__ uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { return atomicCAS(p, c, v); }
+__device__ __forceinline__ uint32_t a_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+__device__ __forceinline__ uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+__device__ __forceinline__ int popc(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int popcll(uint64_t x) { return __popcll(x); }
+template <class T> __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ uint32_t red_max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t red_min_u32(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t red_sum_u32(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+// (value, index) arg-max: larger value wins, ties -> smaller index
+__device__ __forceinline__ void red_argmax_d(double& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+}
+#endif
+
+namespace dcu {
+
+enum { W_EMPTY = 0xFFFFFFFFu, NID_NONE = 0xFFFF, IDX_NONE = 0xFFFFFFFFu };
+enum { ST_SKIPPED = 0, ST_OK = 1, ST_FAILED = 2, ST_OVERFLOW = 250 };
+enum { HEAPK = 12, CDH_N = 16, MAXCAND = 64 };
+
+// read-only tables built on the host (daccord_b200/csrc/tables_host.hpp), resident in HBM
+struct Tables {
+  const double* DPn;               // [NP][MS] DPnorm, zero padded           (OffsetLikely.hpp:75-79)
+  const double* DPsq;              // [NP][MS] DPnormSquare.V, zero padded   (OffsetLikely.hpp:96-98)
+  const unsigned long long* VSq;   // [NP][MS] floor(2^32 * DPnormSquare.V)  (DotProduct.hpp:54-60)
+  const uint16_t* suplo;           // [MS] Vsupport[i].first
+  const uint16_t* suphi;           // [MS] Vsupport[i].second
+  const unsigned long long* klim;  // [nk][KLIMN] KmerLimit::Vlim per k     (DebruijnGraph.hpp:28-75)
+  int NP, MS, KLIMN;
+};
+struct Params {
+  int w, k_lo, k_hi, minff, maxff, mincov, check;   // check = (est_cor != 0)  (DebruijnGraph.hpp:1832-1837)
+  unsigned long long eminrate;
+};
+// capacities of one warp's workspace (two tiers: small for the common case, large for the rest)
+struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, SL, SF, RL, RP, FP, SI, BL; };
+
+struct Slice { uint32_t gpos; uint16_t len; uint16_t flags; };
+struct Window { uint32_t slice_begin; uint16_t slice_cnt; uint16_t reserved; uint32_t aread; uint32_t astart; };
+struct Result { uint8_t status, k; int8_t ff; uint8_t clen; uint32_t err; uint16_t nops, ncand; int32_t elength; };
+
+// one warp's workspace: pointers into its slab (all arrays SoA)
+struct WS {
+  uint8_t* bases; uint16_t* soff; uint16_t* lenhist;
+  uint32_t* hkey; uint32_t* hcnt; uint16_t* hnid;
+  uint32_t* n_kmer; uint16_t* n_freq; uint32_t* n_ioff; uint32_t* n_fill;
+  uint8_t *n_plow, *n_phigh, *n_cplow, *n_cphigh, *n_nsucc, *n_nact, *n_npred;
+  uint16_t* n_sfreq; uint16_t* n_snid; uint16_t* n_mark;
+  uint8_t *ipos, *irpos;
+  uint32_t* ex_kmer; uint8_t *ex_pos, *ex_rpos;
+  uint32_t* ll_kmer; uint16_t* ll_cnt; uint32_t* fl_kmer; uint16_t* fl_cnt; uint16_t* fl_nid;
+  uint16_t* slinks; uint16_t *rs_off, *rs_len;
+  uint16_t *ds_off, *ds_len, *ds_fO, *ds_fL, *ds_cO, *ds_cL, *dt_off, *dt_len;
+  uint8_t* sf_p; double *sf_w, *sf_wf, *sf_wl;      // forward stretch objects
+  uint8_t* sc_p; double *sc_w, *sc_wf, *sc_wl;      // reverse stretch objects
+  uint32_t* rl;
+  double* rp_w; uint32_t* rp_parent; uint32_t* rp_front; uint16_t *rp_stretch, *rp_pos, *rp_len, *rp_baselen;
+  double* rq_w; uint32_t* rq_id;                    // RPST heap
+  uint32_t* arp;                                    // accepted reverse paths, then sorted
+  double* arph_w; uint8_t* arph_n;
+  double* fp_w; uint32_t* fp_parent; uint16_t *fp_stretch, *fp_pos, *fp_len, *fp_baselen;
+  double* apq_w; uint32_t* apq_id; uint8_t* apq_n;
+  double* si_w; uint16_t *si_left, *si_right, *si_cur; uint32_t* si_path;
+  double* sq_w; uint32_t* sq_id;                    // SIQ heap
+  uint8_t* cand; uint8_t* candlen;                  // [CDH_N+1][MAXCAND]
+  double* cdh_w; uint32_t* cdh_id; double* ch_w; uint32_t* ch_id;
+  double* acc_w; uint32_t* acc_err; uint8_t* acc_slot;
+  uint8_t *prevs, *tmps, *best;
+  unsigned long long *m_pv, *m_mv, *m_ph, *m_mh;
+};
+
+// byte layout of a workspace slab, computed once on the host for a Caps
+struct Layout { uint32_t off[96]; uint32_t bytes; };
+
+#define DCU_WS_FIELDS(X)                                                                                  \
+  X(bases, uint8_t, c.B) X(soff, uint16_t, c.S + 1) X(lenhist, uint16_t, 256)                              \
+  X(hkey, uint32_t, c.H) X(hcnt, uint32_t, c.H) X(hnid, uint16_t, c.H)                                     \
+  X(n_kmer, uint32_t, c.NN) X(n_freq, uint16_t, c.NN) X(n_ioff, uint32_t, c.NN) X(n_fill, uint32_t, c.NN)  \
+  X(n_plow, uint8_t, c.NN) X(n_phigh, uint8_t, c.NN) X(n_cplow, uint8_t, c.NN) X(n_cphigh, uint8_t, c.NN)  \
+  X(n_nsucc, uint8_t, c.NN) X(n_nact, uint8_t, c.NN) X(n_npred, uint8_t, c.NN)                             \
+  X(n_sfreq, uint16_t, 4 * c.NN) X(n_snid, uint16_t, 4 * c.NN) X(n_mark, uint16_t, c.NN)                   \
+  X(ipos, uint8_t, c.NI) X(irpos, uint8_t, c.NI)                                                           \
+  X(ex_kmer, uint32_t, c.EX) X(ex_pos, uint8_t, c.EX) X(ex_rpos, uint8_t, c.EX)                            \
+  X(ll_kmer, uint32_t, c.S) X(ll_cnt, uint16_t, c.S) X(fl_kmer, uint32_t, c.S) X(fl_cnt, uint16_t, c.S)    \
+  X(fl_nid, uint16_t, c.S)                                                                                 \
+  X(slinks, uint16_t, c.SL) X(rs_off, uint16_t, c.ST) X(rs_len, uint16_t, c.ST)                            \
+  X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint16_t, c.ST) X(ds_fL, uint16_t, c.ST)    \
+  X(ds_cO, uint16_t, c.ST) X(ds_cL, uint16_t, c.ST) X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST)    \
+  X(sf_p, uint8_t, c.SF) X(sf_w, double, c.SF) X(sf_wf, double, c.SF) X(sf_wl, double, c.SF)               \
+  X(sc_p, uint8_t, c.SF) X(sc_w, double, c.SF) X(sc_wf, double, c.SF) X(sc_wl, double, c.SF)               \
+  X(rl, uint32_t, c.RL)                                                                                    \
+  X(rp_w, double, c.RP) X(rp_parent, uint32_t, c.RP) X(rp_front, uint32_t, c.RP)                           \
+  X(rp_stretch, uint16_t, c.RP) X(rp_pos, uint16_t, c.RP) X(rp_len, uint16_t, c.RP)                        \
+  X(rp_baselen, uint16_t, c.RP) X(rq_w, double, c.RP) X(rq_id, uint32_t, c.RP) X(arp, uint32_t, c.RP)      \
+  X(arph_w, double, c.BL* HEAPK) X(arph_n, uint8_t, c.BL)                                                  \
+  X(fp_w, double, c.FP) X(fp_parent, uint32_t, c.FP) X(fp_stretch, uint16_t, c.FP)                         \
+  X(fp_pos, uint16_t, c.FP) X(fp_len, uint16_t, c.FP) X(fp_baselen, uint16_t, c.FP)                        \
+  X(apq_w, double, c.BL* HEAPK) X(apq_id, uint32_t, c.BL* HEAPK) X(apq_n, uint8_t, c.BL)                   \
+  X(si_w, double, c.SI) X(si_left, uint16_t, c.SI) X(si_right, uint16_t, c.SI) X(si_cur, uint16_t, c.SI)   \
+  X(si_path, uint32_t, c.SI) X(sq_w, double, c.SI) X(sq_id, uint32_t, c.SI)                                \
+  X(cand, uint8_t, (CDH_N + 1) * MAXCAND) X(candlen, uint8_t, CDH_N + 1)                                   \
+  X(cdh_w, double, CDH_N) X(cdh_id, uint32_t, CDH_N) X(ch_w, double, CDH_N) X(ch_id, uint32_t, CDH_N)      \
+  X(acc_w, double, CDH_N) X(acc_err, uint32_t, CDH_N) X(acc_slot, uint8_t, CDH_N)                          \
+  X(prevs, uint8_t, MAXCAND) X(tmps, uint8_t, MAXCAND) X(best, uint8_t, MAXCAND)                           \
+  X(m_pv, unsigned long long, 65) X(m_mv, unsigned long long, 65) X(m_ph, unsigned long long, 65)          \
+  X(m_mh, unsigned long long, 65)
+
+static inline void make_layout(const Caps& c, Layout& L) {
+  uint32_t o = 0; int i = 0;
+#define X(name, type, n) { o = (o + 15u) & ~15u; L.off[i++] = o; o += (uint32_t)(sizeof(type) * (size_t)(n)); }
+  DCU_WS_FIELDS(X)
+#undef X
+  L.bytes = (o + 255u) & ~255u;
+}
+#ifdef DCU_EMU
+static inline
+#else
+__host__ __device__ inline
+#endif
+void bind_ws(WS& w, uint8_t* base, const Layout& L) {
+  int i = 0;
+#define X(name, type, n) w.name = (type*)(base + L.off[i++]);
+  // note: 'c' is unused in this expansion
+  DCU_WS_FIELDS(X)
+#undef X
+}
+
+// per-window state that all lanes hold identically
+struct Ctx {
+  WS ws; Caps cap; Tables T; Params P;
+  const uint8_t* packed; const Slice* sl;
+  int MAo, nbases;
+  int k; uint32_t kmask; int kidx;
+  int nn, ni, nex, nlast, nfirst;
+  int nrs, slO, nds, nsf, nsc, nrl;
+  int overflow;
+};
+
+// ------------------------------------------------------------------ small helpers
+DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - c.cap.LOGH); }
+DCU_FN int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
+  uint32_t h = hslot(c, v), mask = (uint32_t)c.cap.H - 1;
+  for (;;) {
+    uint32_t key = c.ws.hkey[h];
+    if (key == v) return c.ws.hnid[h];
+    if (key == W_EMPTY) return NID_NONE;
+    h = (h + 1) & mask;
+  }
+}
+DCU_FN int sup_lo(const Ctx& c, int pos) { return pos < c.T.MS ? (int)ldg(c.T.suplo + pos) : c.T.NP; }   // OffsetLikely.hpp:34-37
+DCU_FN int sup_hi(const Ctx& c, int pos) { return pos < c.T.MS ? (int)ldg(c.T.suphi + pos) : c.T.NP; }   // OffsetLikely.hpp:39-43
+
+// positional weight of node n at true position p (DebruijnGraph.hpp:3826-3904, fixed point per SURVEY D7)
+DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
+  const uint8_t* ip = (rev ? c.ws.irpos : c.ws.ipos) + c.ws.n_ioff[n];
+  const unsigned long long* row = c.T.VSq + (size_t)p * c.T.MS;
+  int f = c.ws.n_freq[n];
+  unsigned long long u = 0;
+  for (int t = 0; t < f; ++t) { int pos = ip[t]; if (pos < c.T.MS) u += ldg(row + pos); }
+  return (double)u / 4294967296.0;
+}
+
+// bounded binary heap on (weight,id) pairs; convention C2 of oracle/README.md.  MAXH: top = largest weight.
+template <bool MAXH> DCU_FN bool hless(double a, double b) { return MAXH ? (a > b) : (a < b); }
+template <bool MAXH> DCU_FN void heap_push(double* hw, uint32_t* hi, int& n, double w, uint32_t id) {
+  int i = n++;
+  hw[i] = w; hi[i] = id;
+  while (i > 0) {
+    int p = (i - 1) >> 1;
+    if (hless<MAXH>(hw[i], hw[p])) { double tw = hw[i]; hw[i] = hw[p]; hw[p] = tw; uint32_t ti = hi[i]; hi[i] = hi[p]; hi[p] = ti; i = p; } else break;
+  }
+}
+template <bool MAXH> DCU_FN void heap_pop(double* hw, uint32_t* hi, int& n) {
+  --n; hw[0] = hw[n]; hi[0] = hi[n];
+  int p = 0;
+  for (;;) {
+    int l = 2 * p + 1, r = l + 1;
+    if (l >= n) break;
+    int m = (r < n && hless<MAXH>(hw[r], hw[l])) ? r : l;
+    if (hless<MAXH>(hw[m], hw[p])) { double tw = hw[m]; hw[m] = hw[p]; hw[p] = tw; uint32_t ti = hi[m]; hi[m] = hi[p]; hi[p] = ti; p = m; } else break;
+  }
+}
+
+// ------------------------------------------------------------------ load: slices -> base codes
+// replaces DecodedReadContainer + the MA array (HandleContext.hpp:2032-2043); bases as codes 0..3
+DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
+  WS& w = c.ws;
+  c.MAo = win.slice_cnt; c.overflow = 0;
+  if (c.MAo > c.cap.S) { c.overflow = 1; return; }
+  const Slice* sl = c.sl + win.slice_begin;
+  if (lane == 0) {
+    uint32_t o = 0;
+    for (int j = 0; j < c.MAo; ++j) { w.soff[j] = (uint16_t)o; o += sl[j].len; if (sl[j].len > 255) o = 0x10000000u; }
+    w.soff[c.MAo] = (uint16_t)(o > 65535u ? 65535u : o);
+    c.nbases = (int)(o > 0x0fffffffu ? 0x0fffffff : o);
+  }
+  c.nbases = bcast(c.nbases, 0);
+  wsync();
+  if (c.nbases > c.cap.B || c.nbases > 65000) { c.overflow = 2; return; }
+  for (int j = lane; j < c.MAo; j += DCU_NL) {
+    Slice s = sl[j];
+    uint8_t* out = w.bases + w.soff[j];
+    if (!(s.flags & 1)) {
+      for (int i = 0; i < s.len; ++i) { uint32_t g = s.gpos + i; out[i] = (ldg(c.packed + (g >> 2)) >> (6 - 2 * (g & 3))) & 3; }
+    } else {
+      for (int i = 0; i < s.len; ++i) { uint32_t g = s.gpos + (s.len - 1 - i); out[i] = 3 - ((ldg(c.packed + (g >> 2)) >> (6 - 2 * (g & 3))) & 3); }
+    }
+  }
+  wsync();
+}
+DCU_FN int seqlen(const Ctx& c, int j) { return c.ws.soff[j + 1] - c.ws.soff[j]; }
+
+// ------------------------------------------------------------------ expected length (HandleContext.hpp:2051-2155)
+DCU_BIG int estimate_length(Ctx& c, int lane) {
+  WS& w = c.ws;
+  int maxv = -1;
+  if (c.MAo) {
+    int mn = 0x7fffffff, mx = -0x7fffffff;
+    for (int j = 0; j < c.MAo; ++j) { int lp = seqlen(c, j) - 1; mn = lp < mn ? lp : mn; mx = lp > mx ? lp : mx; }
+    if (mn < 0) mn = 0;
+    if (mx < 0) mx = 0;
+    int s0 = sup_lo(c, mn), s1 = sup_hi(c, mx);
+    double best = DBL_MIN; int bi = 0x7fffffff;
+    for (int i = s0 + lane; i < s1; i += DCU_NL) {
+      const double* row = c.T.DPn + (size_t)i * c.T.MS;
+      double vprod = 1.0;
+      for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len) { int lp = len - 1; vprod *= (lp < c.T.MS ? ldg(row + lp) : 0.0); } }
+      if (vprod > best) { best = vprod; bi = i; }
+    }
+    red_argmax_d(best, bi);
+    if (bi != 0x7fffffff && best > DBL_MIN) maxv = bi;
+  }
+  if (maxv == -1) {            // density fallback (:2103-2155), rare -> lane 0
+    if (lane == 0) {
+      int Os = 0;
+      for (int i = 0; i < 256; ++i) w.lenhist[i] = 0;
+      for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len + 1 > Os) Os = len + 1; if (len < 256) w.lenhist[len]++; }
+      int maxoff = -1; double maxoffv = DBL_MIN;
+      for (int i = 0; i < c.T.NP; ++i) {
+        const double* row = c.T.DPsq + (size_t)i * c.T.MS;
+        double s = 0;
+        int lim = Os < c.T.MS ? Os : c.T.MS;
+        for (int j = 0; j < lim; ++j) { double o = (j < 256 && w.lenhist[j]) ? (double)(w.lenhist[j] - 1) : 0.0; s += ldg(row + j) * o; }
+        if (s > maxoffv) { maxoff = i; maxoffv = s; }
+      }
+      if (maxoff != -1 && maxoffv >= 1e-3) maxv = maxoff;
+    }
+    maxv = bcast(maxv, 0);
+  }
+  return maxv + 1;
+}
+
+// ------------------------------------------------------------------ k-mer hash build (replaces setupPreNodes :2018-2304)
+DCU_BIG void build_hash(Ctx& c, int lane) {
+  WS& w = c.ws;
+  for (int i = lane; i < c.cap.H; i += DCU_NL) { w.hkey[i] = W_EMPTY; w.hcnt[i] = 0; }
+  wsync();
+  uint32_t mask = (uint32_t)c.cap.H - 1;
+  uint32_t ni = 0;
+  for (int j = lane; j < c.MAo; j += DCU_NL) {
+    int len = seqlen(c, j);
+    if (len < c.k) continue;
+    const uint8_t* u = w.bases + w.soff[j];
+    uint32_t v = 0;
+    for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i];
+    for (int i = 0; i + c.k <= len; ++i) {
+      v = ((v << 2) & c.kmask) | u[i + c.k - 1];
+      uint32_t h = hslot(c, v);
+      for (;;) {
+        uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
+        if (old == W_EMPTY || old == v) { a_add(&w.hcnt[h], 1); break; }
+        h = (h + 1) & mask;
+      }
+      ++ni;
+    }
+  }
+  c.ni = (int)red_sum_u32(ni);
+  wsync();
+  // last k-mer of every sequence (the `last` array, :2108, :1360-1391): (count, kmer) sorted descending
+  if (lane == 0) {
+    int nl = 0;
+    for (int j = 0; j < c.MAo; ++j) {
+      int len = seqlen(c, j);
+      if (len < c.k) continue;
+      const uint8_t* u = w.bases + w.soff[j] + (len - c.k);
+      uint32_t v = 0;
+      for (int i = 0; i < c.k; ++i) v = (v << 2) | u[i];
+      int t = 0;
+      while (t < nl && w.ll_kmer[t] != v) ++t;
+      if (t == nl) { w.ll_kmer[nl] = v; w.ll_cnt[nl] = 1; ++nl; } else w.ll_cnt[t]++;
+    }
+    for (int a = 1; a < nl; ++a) {          // insertion sort by (cnt, kmer) descending
+      uint32_t kv = w.ll_kmer[a]; uint16_t cv = w.ll_cnt[a]; int b = a;
+      while (b > 0 && (w.ll_cnt[b - 1] < cv || (w.ll_cnt[b - 1] == cv && w.ll_kmer[b - 1] < kv))) { w.ll_kmer[b] = w.ll_kmer[b - 1]; w.ll_cnt[b] = w.ll_cnt[b - 1]; --b; }
+      w.ll_kmer[b] = kv; w.ll_cnt[b] = cv;
+    }
+    c.nlast = nl;
+  }
+  c.nlast = bcast(c.nlast, 0);
+  wsync();
+}
+
+// nodes = k-mers with count >= f (filterFreq :1181-1197), instance lists (setupNodes :1918-2014)
+DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
+  WS& w = c.ws;
+  int nn = 0;
+  for (int base = 0; base < c.cap.H; base += DCU_NL) {
+    int i = base + lane;
+    bool keep = (w.hkey[i] != W_EMPTY) && ((int)w.hcnt[i] >= f);
+    uint32_t b = ballot(keep);
+    int idx = nn + popc(b & lanemask_lt(lane));
+    if (keep) {
+      if (idx < c.cap.NN) { w.n_kmer[idx] = w.hkey[i]; w.n_freq[idx] = (uint16_t)w.hcnt[i]; w.hnid[i] = (uint16_t)idx; w.n_fill[idx] = 0; }
+    } else w.hnid[i] = NID_NONE;
+    nn += popc(b);
+  }
+  if (nn > c.cap.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
+  c.nn = nn;
+  wsync();
+  if (lane == 0) { uint32_t o = 0; for (int n = 0; n < nn; ++n) { w.n_ioff[n] = o; o += w.n_freq[n]; } c.ni = (int)o; }
+  c.ni = bcast(c.ni, 0);
+  wsync();
+  if (c.ni > c.cap.NI) { c.overflow = 4; return; }
+  for (int j = lane; j < c.MAo; j += DCU_NL) {
+    int len = seqlen(c, j);
+    if (len < c.k) continue;
+    const uint8_t* u = w.bases + w.soff[j];
+    uint32_t v = 0;
+    for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i];
+    for (int i = 0; i + c.k <= len; ++i) {
+      v = ((v << 2) & c.kmask) | u[i + c.k - 1];
+      int n = lookup(c, v);
+      if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = (uint8_t)i; w.irpos[w.n_ioff[n] + t] = (uint8_t)(len - i - c.k); }
+    }
+  }
+  for (int e = lane; e < c.nex; e += DCU_NL) {       // synthesised k-mers of the gap filler (:1148-1157)
+    int n = lookup(c, w.ex_kmer[e]);
+    if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = w.ex_pos[e]; w.irpos[w.n_ioff[n] + t] = w.ex_rpos[e]; }
+  }
+  wsync();
+  uint32_t nf = 0;
+  for (int base = 0; base < nn; base += DCU_NL) {
+    int n = base + lane;
+    int c0 = 0;
+    if (n < nn) {
+      int f0 = w.n_freq[n]; const uint8_t* ip = w.ipos + w.n_ioff[n]; const uint8_t* irp = w.irpos + w.n_ioff[n];
+      int lo = 255, hi = 0, clo = 255, chi = 0;
+      for (int t = 0; t < f0; ++t) { int a = ip[t], b = irp[t]; lo = a < lo ? a : lo; hi = a > hi ? a : hi; clo = b < clo ? b : clo; chi = b > chi ? b : chi; c0 += (a == 0); }
+      w.n_plow[n] = (uint8_t)lo; w.n_phigh[n] = (uint8_t)hi; w.n_cplow[n] = (uint8_t)clo; w.n_cphigh[n] = (uint8_t)chi;
+    }
+    uint32_t b = ballot(c0 > 0);               // k-mers seen at position 0 (maxForPosList :1280-1304)
+    int idx = (int)nf + popc(b & lanemask_lt(lane));
+    if (c0 > 0 && idx < c.cap.S) { w.fl_kmer[idx] = w.n_kmer[n]; w.fl_cnt[idx] = (uint16_t)c0; w.fl_nid[idx] = (uint16_t)n; }
+    nf += popc(b);
+  }
+  wsync();
+  if ((int)nf > c.cap.S) { c.overflow = 5; return; }
+  if (lane == 0) {
+    for (int a = 1; a < (int)nf; ++a) {         // (count, kmer) descending
+      uint32_t kv = w.fl_kmer[a]; uint16_t cv = w.fl_cnt[a], nv = w.fl_nid[a]; int b = a;
+      while (b > 0 && (w.fl_cnt[b - 1] < cv || (w.fl_cnt[b - 1] == cv && w.fl_kmer[b - 1] < kv))) { w.fl_kmer[b] = w.fl_kmer[b - 1]; w.fl_cnt[b] = w.fl_cnt[b - 1]; w.fl_nid[b] = w.fl_nid[b - 1]; --b; }
+      w.fl_kmer[b] = kv; w.fl_cnt[b] = cv; w.fl_nid[b] = nv;
+    }
+  }
+  c.nfirst = (int)nf;
+  wsync();
+}
+
+// active predecessors (:2552-2597): p->v is active iff v is among p's first nact successors
+DCU_BIG void compute_npred(Ctx& c, int lane) {
+  WS& w = c.ws;
+  int shift = 2 * (c.k - 1);
+  for (int n = lane; n < c.nn; n += DCU_NL) {
+    uint32_t v = w.n_kmer[n];
+    int cnt = 0;
+    for (uint32_t s = 0; s < 4; ++s) {
+      uint32_t pv = ((v >> 2) & c.kmask) | (s << shift);
+      int p = lookup(c, pv);
+      if (p == NID_NONE) continue;
+      int na = w.n_nact[p];
+      for (int e = 0; e < na; ++e) if (w.n_snid[4 * p + e] == n) { ++cnt; break; }
+    }
+    w.n_npred[n] = (uint8_t)cnt;
+  }
+  wsync();
+}
+// successor lists + primary activation (setNodesActive :1770-1814 / setupAddHeap :1818-1859)
+DCU_BIG void build_edges(Ctx& c, int lane) {
+  WS& w = c.ws;
+  int no = c.MAo < c.T.KLIMN ? c.MAo : c.T.KLIMN - 1;
+  unsigned long long lim = c.P.check ? ldg(c.T.klim + (size_t)c.kidx * c.T.KLIMN + no) : 0;
+  for (int n = lane; n < c.nn; n += DCU_NL) {
+    uint32_t v = w.n_kmer[n];
+    uint32_t key[4]; uint16_t nid[4]; int ns = 0;
+    for (uint32_t s = 0; s < 4; ++s) {
+      int t = lookup(c, ((v << 2) & c.kmask) | s);
+      if (t != NID_NONE) { key[ns] = ((uint32_t)w.n_freq[t] << 8) | s; nid[ns] = (uint16_t)t; ++ns; }
+    }
+    for (int a = 1; a < ns; ++a) {              // Links::sort, descending (Links.hpp:35-57)
+      uint32_t kv = key[a]; uint16_t nv = nid[a]; int b = a;
+      while (b > 0 && key[b - 1] < kv) { key[b] = key[b - 1]; nid[b] = nid[b - 1]; --b; }
+      key[b] = kv; nid[b] = nv;
+    }
+    int na = 0;
+    if (ns) {
+      na = 1;
+      while (na < ns && (((key[na] >> 8) >= (key[0] >> 8) / 2) || (c.P.check && (unsigned long long)(key[na] >> 8) >= lim))) ++na;
+    }
+    for (int e = 0; e < 4; ++e) { w.n_sfreq[4 * n + e] = e < ns ? (uint16_t)(key[e] >> 8) : 0; w.n_snid[4 * n + e] = e < ns ? nid[e] : (uint16_t)NID_NONE; }
+    w.n_nsucc[n] = (uint8_t)ns; w.n_nact[n] = (uint8_t)na; w.n_mark[n] = 0;
+  }
+  wsync();
+  compute_npred(c, lane);
+}
+// addNextFromHeap (:1861-1897): activate every pending edge of the highest pending frequency
+DCU_BIG bool add_next(Ctx& c, int lane) {
+  WS& w = c.ws;
+  uint32_t top = 0;
+  for (int n = lane; n < c.nn; n += DCU_NL) { int na = w.n_nact[n]; if (na < w.n_nsucc[n]) { uint32_t f = w.n_sfreq[4 * n + na]; top = f > top ? f : top; } }
+  top = red_max_u32(top);
+  if (!top) return false;
+  for (int n = lane; n < c.nn; n += DCU_NL) {
+    int na = w.n_nact[n], ns = w.n_nsucc[n];
+    while (na < ns && w.n_sfreq[4 * n + na] == top) ++na;
+    w.n_nact[n] = (uint8_t)na;
+  }
+  wsync();
+  compute_npred(c, lane);
+  return true;
+}
+
+// ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
+DCU_BIG void gap_fill(Ctx& c, int lane) {
+  WS& w = c.ws;
+  uint32_t* nexp = &w.n_fill[0];      // n_fill[0] doubles as the append counter here (rebuilt afterwards)
+  if (lane == 0) *nexp = 0;
+  wsync();
+  for (int a = lane; a < c.nn; a += DCU_NL) {
+    uint32_t v = w.n_kmer[a];
+    int pfa = sup_lo(c, w.n_plow[a]), pta = sup_hi(c, w.n_phigh[a]);
+    for (uint32_t x = 0; x < 16; ++x) {
+      uint32_t nv = ((v << 4) & c.kmask) | x;
+      int b = lookup(c, nv);
+      if (b == NID_NONE) continue;
+      uint32_t cv = ((v << 2) & c.kmask) | (nv >> 2);
+      if (lookup(c, cv) != NID_NONE) continue;
+      int pfb = sup_lo(c, w.n_plow[b]), ptb = sup_hi(c, w.n_phigh[b]);
+      double mweight = DBL_MIN; int mp = 0;
+      for (int p = pfa; p < pta; ++p) {
+        int q = p + 2;
+        if (q < pfb || q >= ptb) continue;
+        double wa = kweight(c, a, p, false);
+        if (!(wa >= 1e-3)) continue;
+        double wb = kweight(c, b, q, false);
+        if (!(wb >= 1e-3)) continue;
+        double lo = wa < wb ? wa : wb, hi = wa < wb ? wb : wa;
+        double weight = lo + hi;
+        if (weight > mweight) { mweight = weight; mp = p + 1; }
+      }
+      if (mweight != DBL_MIN) {
+        int seqid = -1;
+        for (int j = 0; j < c.MAo && seqid < 0; ++j) if (mp + c.k <= seqlen(c, j)) seqid = j;
+        if (seqid >= 0) {
+          uint32_t e = a_add(nexp, 1);
+          if ((int)e < c.cap.EX) { w.ex_kmer[e] = cv; w.ex_pos[e] = (uint8_t)mp; w.ex_rpos[e] = (uint8_t)(seqlen(c, seqid) - mp - c.k); }
+        }
+      }
+    }
+  }
+  wsync();
+  int nex = (int)bcast(*nexp, 0);
+  wsync();
+  if (nex > c.cap.EX) { c.overflow = 6; c.nex = 0; return; }
+  c.nex = nex;
+  uint32_t mask = (uint32_t)c.cap.H - 1;
+  for (int e = lane; e < nex; e += DCU_NL) {
+    uint32_t v = w.ex_kmer[e], h = hslot(c, v);
+    for (;;) {
+      uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
+      if (old == W_EMPTY || old == v) { a_add(&w.hcnt[h], 1); break; }
+      h = (h + 1) & mask;
+    }
+  }
+  wsync();
+}
+
+// ------------------------------------------------------------------ stretches (unitigs)
+// computeStretches(checkpredecessors=true) (:2844-2986); serial walk over the precomputed successor ids
+DCU_BIG void raw_stretches(Ctx& c, int lane) {
+  WS& w = c.ws;
+  if (lane == 0) {
+    int nrs = 0, slO = 0; uint16_t stamp = 0; bool ovf = false;
+    for (int n = 0; n < c.nn; ++n) w.n_mark[n] = 0;
+    for (int z = 0; z < c.nn && !ovf; ++z) {
+      int numsucc = w.n_nact[z], numpred = w.n_npred[z];
+      if (!(numsucc && (numpred != 1 || numsucc > 1))) continue;
+      for (int i = 0; i < numsucc; ++i) {
+        if (nrs >= c.cap.ST || slO + 2 > c.cap.SL) { ovf = true; break; }
+        int start = slO;
+        int ext = w.n_snid[4 * z + i];
+        ++stamp;
+        w.slinks[slO++] = (uint16_t)z; w.n_mark[z] = stamp;
+        w.slinks[slO++] = (uint16_t)ext; w.n_mark[ext] = stamp;
+        int len = 2; bool loop = (z == ext); int cur = ext;
+        while (!loop && w.n_nact[cur] == 1 && w.n_npred[cur] == 1) {
+          cur = w.n_snid[4 * cur];
+          if (slO >= c.cap.SL) { ovf = true; break; }
+          w.slinks[slO++] = (uint16_t)cur; ++len;
+          if (w.n_mark[cur] == stamp) loop = true; else w.n_mark[cur] = stamp;
+        }
+        if (ovf) break;
+        int last = cur;
+        if (loop && z != last) {
+          int j = 0;
+          while (w.slinks[start + j] != last) ++j;
+          j += 1;
+          int retract = len - j;
+          len -= retract; slO -= retract;
+        }
+        w.rs_off[nrs] = (uint16_t)start; w.rs_len[nrs] = (uint16_t)len; ++nrs;
+      }
+    }
+    c.nrs = nrs; c.slO = slO;
+    if (ovf) c.overflow = 7;
+  }
+  c.nrs = bcast(c.nrs, 0); c.slO = bcast(c.slO, 0); c.overflow = bcast(c.overflow, 0);
+  wsync();
+}
+
+// splitStretches(first), splitStretches(last), stretchesUnique (:2772-2841, :3087-3114) on views
+DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
+  WS& w = c.ws;
+  if (lane == 0) {
+    int n = c.nrs; bool ovf = false;
+    for (int i = 0; i < n; ++i) { w.ds_off[i] = w.rs_off[i]; w.ds_len[i] = w.rs_len[i]; }
+    for (int pass = 0; pass < 2 && !ovf; ++pass) {
+      int v = pass == 0 ? F : L;
+      int n0 = n, o = 0, na = 0;
+      // pieces are appended after the surviving originals (the reference appends, then removes)
+      for (int z = 0; z < n0; ++z) {
+        int off = w.ds_off[z], len = w.ds_len[z], split = -1;
+        for (int i = 1; i + 1 < len; ++i) if (w.slinks[off + i] == v) { split = i; break; }
+        if (split < 0) { w.ds_off[o] = (uint16_t)off; w.ds_len[o] = (uint16_t)len; ++o; }
+        else {
+          if (na + 2 > c.cap.ST) { ovf = true; break; }
+          w.dt_off[na] = (uint16_t)off; w.dt_len[na] = (uint16_t)(split + 1); ++na;
+          w.dt_off[na] = (uint16_t)(off + split); w.dt_len[na] = (uint16_t)(len - split); ++na;
+        }
+      }
+      if (ovf || o + na > c.cap.ST) { ovf = true; break; }
+      for (int i = 0; i < na; ++i) { w.ds_off[o + i] = w.dt_off[i]; w.ds_len[o + i] = w.dt_len[i]; }
+      n = o + na;
+    }
+    // sort by (first kmer, ext sym, len desc, last kmer); then keep the first per (first, ext)
+    for (int a = 1; a < n && !ovf; ++a) {
+      int off = w.ds_off[a], len = w.ds_len[a];
+      uint64_t k1 = ((uint64_t)w.n_kmer[w.slinks[off]] << 2) | (w.n_kmer[w.slinks[off + 1]] & 3);
+      uint32_t lk = w.n_kmer[w.slinks[off + len - 1]];
+      int b = a;
+      while (b > 0) {
+        int poff = w.ds_off[b - 1], plen = w.ds_len[b - 1];
+        uint64_t pk1 = ((uint64_t)w.n_kmer[w.slinks[poff]] << 2) | (w.n_kmer[w.slinks[poff + 1]] & 3);
+        bool greater;    // is prev > cur ?
+        if (pk1 != k1) greater = pk1 > k1;
+        else if (plen != len) greater = plen < len;
+        else greater = w.n_kmer[w.slinks[poff + plen - 1]] > lk;
+        if (!greater) break;
+        w.ds_off[b] = (uint16_t)poff; w.ds_len[b] = (uint16_t)plen; --b;
+      }
+      w.ds_off[b] = (uint16_t)off; w.ds_len[b] = (uint16_t)len;
+    }
+    int o = 0;
+    for (int i = 0; i < n; ++i) {
+      if (o > 0) {
+        int poff = w.ds_off[o - 1], off = w.ds_off[i];
+        if (w.slinks[poff] == w.slinks[off] && w.slinks[poff + 1] == w.slinks[off + 1]) continue;
+      }
+      w.ds_off[o] = w.ds_off[i]; w.ds_len[o] = w.ds_len[i]; ++o;
+    }
+    c.nds = o;
+    if (ovf) c.overflow = 8;
+  }
+  c.nds = bcast(c.nds, 0); c.overflow = bcast(c.overflow, 0);
+  wsync();
+}
+DCU_FN int ds_first(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s]]; }
+DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s] + c.ws.ds_len[s] - 1]; }
+
+// computeFeasibleStretchPositions (:3176-3330), weights evaluated on demand, lanes over positions
+DCU_BIG void stretch_positions(Ctx& c, int lane) {
+  WS& w = c.ws;
+  int nsf = 0, nsc = 0;
+  for (int s = 0; s < c.nds; ++s) {
+    int off = w.ds_off[s], L = w.ds_len[s];
+    for (int dir = 0; dir < 2; ++dir) {
+      int anchor = dir == 0 ? w.slinks[off] : w.slinks[off + L - 1];
+      int r0 = dir == 0 ? sup_lo(c, w.n_plow[anchor]) : sup_lo(c, w.n_cplow[anchor]);
+      int r1 = dir == 0 ? sup_hi(c, w.n_phigh[anchor]) : sup_hi(c, w.n_cphigh[anchor]);
+      int startO = dir == 0 ? nsf : nsc, cntO = 0;
+      for (int base = r0; base < r1; base += DCU_NL) {
+        int s0 = base + lane;
+        bool ok = s0 < r1;
+        double sum = 0.0, wfirst = 0.0, wlast = 0.0;
+        if (ok) {
+          for (int jj = 0; jj < L; ++jj) {
+            int nj = dir == 0 ? w.slinks[off + jj] : w.slinks[off + L - 1 - jj];
+            int p = s0 + jj;
+            int lo = dir == 0 ? sup_lo(c, w.n_plow[nj]) : sup_lo(c, w.n_cplow[nj]);
+            int hi = dir == 0 ? sup_hi(c, w.n_phigh[nj]) : sup_hi(c, w.n_cphigh[nj]);
+            if (p < lo || p >= hi) { ok = false; break; }
+            double wt = kweight(c, nj, p, dir == 1);
+            if (!(wt >= 1e-3)) { ok = false; break; }
+            sum += wt;
+            if (jj == 0) wfirst = wt;
+            wlast = wt;
+          }
+        }
+        uint32_t b = ballot(ok);
+        int idx = startO + cntO + popc(b & lanemask_lt(lane));
+        if (ok && idx < c.cap.SF) {
+          if (dir == 0) { w.sf_p[idx] = (uint8_t)s0; w.sf_w[idx] = sum; w.sf_wf[idx] = wfirst; w.sf_wl[idx] = wlast; }
+          else { w.sc_p[idx] = (uint8_t)s0; w.sc_w[idx] = sum; w.sc_wf[idx] = wfirst; w.sc_wl[idx] = wlast; }
+        }
+        cntO += popc(b);
+      }
+#ifdef DCU_EMU_DEBUG
+      if (startO + cntO > c.cap.SF) fprintf(stderr, "SF overflow: s=%d/%d L=%d dir=%d r0=%d r1=%d cnt=%d start=%d nn=%d\n", s, c.nds, L, dir, r0, r1, cntO, startO, c.nn);
+#endif
+      if (startO + cntO > c.cap.SF || startO + cntO > 65535) { c.overflow = 9; wsync(); return; }
+      if (lane == 0) {
+        if (dir == 0) { w.ds_fO[s] = (uint16_t)startO; w.ds_fL[s] = (uint16_t)cntO; } else { w.ds_cO[s] = (uint16_t)startO; w.ds_cL[s] = (uint16_t)cntO; }
+      }
+      if (dir == 0) nsf += cntO; else nsc += cntO;
+    }
+  }
+  c.nsf = nsf; c.nsc = nsc;
+  wsync();
+}
+DCU_FN int sfo_fwd(const Ctx& c, int s, int p) {     // getCachedStretchPositionWeight (:3906-3918)
+  const WS& w = c.ws; int o = w.ds_fO[s], n = w.ds_fL[s];
+  for (int i = 0; i < n; ++i) { int q = w.sf_p[o + i]; if (q == p) return o + i; if (q > p) break; }
+  return -1;
+}
+DCU_FN int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchReversePositionWeight (:3920-3932)
+  const WS& w = c.ws; int o = w.ds_cO[s], n = w.ds_cL[s];
+  for (int i = 0; i < n; ++i) { int q = w.sc_p[o + i]; if (q == p) return o + i; if (q > p) break; }
+  return -1;
+}
+
+// computeStretchLinks / getReverseStretchLinkWeight (:3388-3480); serial, output sorted by (to, from)
+DCU_BIG void stretch_links(Ctx& c, int lane) {
+  WS& w = c.ws;
+  if (lane == 0) {
+    int nrl = 0; bool ovf = false;
+    for (int B = 0; B < c.nds && !ovf; ++B) {
+      int bfirst = ds_first(c, B), shift = w.ds_len[B] - 1;
+      for (int A = 0; A < c.nds; ++A) {
+        if (ds_last(c, A) != bfirst) continue;
+        double weight = 0.0;
+        for (int ib = 0; ib < w.ds_cL[B]; ++ib) {
+          int ob = w.ds_cO[B] + ib, tp = w.sc_p[ob] + shift;
+          for (int ia = 0; ia < w.ds_cL[A]; ++ia) {
+            int oa = w.ds_cO[A] + ia;
+            if (w.sc_p[oa] == tp) { double lw = w.sc_w[ob] + (w.sc_w[oa] - w.sc_wf[oa]); weight = lw > weight ? lw : weight; }
+          }
+        }
+        if (weight >= 1e-1) { if (nrl >= c.cap.RL) { ovf = true; break; } w.rl[nrl++] = ((uint32_t)B << 16) | (uint32_t)A; }
+      }
+    }
+    c.nrl = nrl;
+    if (ovf) c.overflow = 10;
+  }
+  c.nrl = bcast(c.nrl, 0); c.overflow = bcast(c.overflow, 0);
+  wsync();
+}
+
+// ------------------------------------------------------------------ Myers bit-vector edit distance
+// global unit-cost distance of pattern (<=64, Peq masks) against text t[0,n)
+DCU_FN int myers_dist(const unsigned long long* peq, int m, const uint8_t* t, int n) {
+  if (m == 0) return n;
+  unsigned long long pv = ~0ull, mv = 0, top = 1ull << (m - 1);
+  int score = m;
+  for (int j = 0; j < n; ++j) {
+    unsigned long long eq = peq[t[j]];
+    unsigned long long xv = eq | mv;
+    unsigned long long xh = (((eq & pv) + pv) ^ pv) | eq;
+    unsigned long long ph = mv | ~(xh | pv);
+    unsigned long long mh = pv & xh;
+    if (ph & top) ++score; else if (mh & top) --score;
+    ph = (ph << 1) | 1ull; mh <<= 1;
+    pv = mh | ~(xv | ph); mv = ph & xv;
+  }
+  return score;
+}
+DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool ascii) {
+  peq[0] = peq[1] = peq[2] = peq[3] = 0;
+  for (int i = 0; i < m; ++i) {
+    int cde = pat[i];
+    if (ascii) cde = (cde == 'A') ? 0 : (cde == 'C') ? 1 : (cde == 'G') ? 2 : 3;
+    peq[cde] |= 1ull << i;
+  }
+}
+
+// ------------------------------------------------------------------ traverse (:4496-5170)
+struct TravOut { int nacc; };
+
+DCU_FN int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front, int stretch, int pos, int len, int baselen) {
+  WS& w = c.ws;
+  if (nrp >= c.cap.RP) { c.overflow = 11; return -1; }
+  int id = nrp++;
+  w.rp_w[id] = wgt; w.rp_parent[id] = parent; w.rp_front[id] = front; w.rp_stretch[id] = (uint16_t)stretch;
+  w.rp_pos[id] = (uint16_t)pos; w.rp_len[id] = (uint16_t)len; w.rp_baselen[id] = (uint16_t)baselen;
+  return id;
+}
+
+// reverse half-paths (prepareTraverse :3576-3757); lane 0
+DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
+  WS& w = c.ws;
+  int nrp = 0, nq = 0; narp = 0;
+  for (int i = 0; i < c.cap.BL; ++i) w.arph_n[i] = 0;
+  int seed = rp_new(c, nrp, 0.0, IDX_NONE, w.n_kmer[Lnode], NID_NONE, 0, 0, c.k);
+  if (seed < 0) return;
+  heap_push<true>(w.rq_w, w.rq_id, nq, 0.0, (uint32_t)seed);
+  while (nq > 0 && !c.overflow) {
+    double wt = w.rq_w[0]; int id = (int)w.rq_id[0];
+    heap_pop<true>(w.rq_w, w.rq_id, nq);
+    int bl = w.rp_baselen[id];
+    if (bl >= c.cap.BL) continue;                       // longer than any admissible pairing, inert
+    double* hw = w.arph_w + bl * HEAPK; int hn = w.arph_n[bl];
+    if (hn == HEAPK) {                                  // bounded per-length heap (:3626-3665); only weights matter
+      int mi = 0;
+      for (int t = 1; t < HEAPK; ++t) if (hw[t] < hw[mi]) mi = t;
+      if (wt <= hw[mi]) continue;
+      hw[mi] = wt;
+    } else { hw[hn] = wt; w.arph_n[bl] = (uint8_t)(hn + 1); }
+    w.arp[narp++] = (uint32_t)id;
+    int rlen = w.rp_len[id], rpos = w.rp_pos[id];
+    if (rlen == 0) {
+      for (int s = 0; s < c.nds; ++s) if (ds_last(c, s) == Lnode) {
+        int o = sfo_rev(c, s, rpos);                    // extendReversePath (:4058-4105) + feasibility (:4130-4159)
+        if (o >= 0 && w.sc_w[o] >= 0.5) {
+          int L = w.ds_len[s];
+          int nid = rp_new(c, nrp, w.sc_w[o], (uint32_t)id, w.n_kmer[ds_first(c, s)], s, rpos + L - 1, 1, L + c.k - 1);
+          if (nid < 0) return;
+          if (nq >= c.cap.RP) { c.overflow = 12; return; }
+          heap_push<true>(w.rq_w, w.rq_id, nq, w.sc_w[o], (uint32_t)nid);
+        }
+      }
+    } else if (bl < (lmax + 1) / 2) {
+      int ls = w.rp_stretch[id];
+      for (int t = 0; t < c.nrl; ++t) {
+        if ((int)(w.rl[t] >> 16) != ls) continue;
+        int s = (int)(w.rl[t] & 0xFFFF);
+        int o = sfo_rev(c, s, rpos);
+        if (o >= 0 && w.sc_w[o] >= 0.5) {
+          int L = w.ds_len[s];
+          double nw = wt + (w.sc_w[o] - w.sc_wf[o]);
+          int nid = rp_new(c, nrp, nw, (uint32_t)id, w.n_kmer[ds_first(c, s)], s, rpos + L - 1, rlen + 1, bl + L - 1);
+          if (nid < 0) return;
+          if (nq >= c.cap.RP) { c.overflow = 13; return; }
+          heap_push<true>(w.rq_w, w.rq_id, nq, nw, (uint32_t)nid);
+        }
+      }
+    }
+  }
+  // sort accepted paths by (front, baselen), ties in acceptance order (:3742, convention C7)
+  for (int a = 1; a < narp; ++a) {
+    uint32_t id = w.arp[a]; uint32_t fr = w.rp_front[id]; int bl = w.rp_baselen[id]; int b = a;
+    while (b > 0) {
+      uint32_t pid = w.arp[b - 1];
+      bool greater = w.rp_front[pid] != fr ? (w.rp_front[pid] > fr) : (w.rp_baselen[pid] > bl);
+      if (!greater) break;
+      w.arp[b] = pid; --b;
+    }
+    w.arp[b] = id;
+  }
+}
+
+DCU_FN double pair_score(const Ctx& c, int P, int rpid) {      // getPairScore (:3482-3497)
+  const WS& w = c.ws;
+  int ls = w.fp_stretch[P];
+  int lpos = w.fp_pos[P] - (w.ds_len[ls] - 1);
+  int o = sfo_fwd(c, ls, lpos);
+  double s = w.fp_w[P] + w.rp_w[rpid];
+  return o >= 0 ? (s - w.sf_wl[o]) : s;
+}
+// best / next-best reverse path of an interval in (weight, sorted index) order (:3499-3534)
+DCU_FN int interval_next(const Ctx& c, int left, int right, int cur) {
+  const WS& w = c.ws;
+  int best = -1; double bw = 0;
+  double cw = cur >= 0 ? w.rp_w[w.arp[cur]] : 0;
+  for (int i = left; i < right; ++i) {
+    double wi = w.rp_w[w.arp[i]];
+    if (cur >= 0 && !(wi < cw || (wi == cw && i < cur))) continue;
+    if (best < 0 || wi > bw || (wi == bw && i > best)) { best = i; bw = wi; }
+  }
+  return best;
+}
+DCU_FN void apq_push(Ctx& c, int pid) {                        // :4843-4862, :4997-5017
+  WS& w = c.ws;
+  int bl = w.fp_baselen[pid];
+  if (bl >= c.cap.BL) return;                                  // longer than lmax: never pairs, never extends
+  double* hw = w.apq_w + bl * HEAPK; uint32_t* hi = w.apq_id + bl * HEAPK; int n = w.apq_n[bl];
+  double wt = w.fp_w[pid];
+  if (n == HEAPK) { if (wt > hw[0]) { heap_pop<false>(hw, hi, n); heap_push<false>(hw, hi, n, wt, (uint32_t)pid); } }
+  else heap_push<false>(hw, hi, n, wt, (uint32_t)pid);
+  w.apq_n[bl] = (uint8_t)n;
+}
+DCU_FN int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath (:3989-4056); P == -1 -> empty path
+  WS& w = c.ws;
+  int ppos = P < 0 ? 0 : w.fp_pos[P], plen = P < 0 ? 0 : w.fp_len[P];
+  int o = sfo_fwd(c, s, ppos);
+  int L = w.ds_len[s];
+  double wt; int bl;
+  if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sf_w[o] : 0.0; }
+  else { bl = w.fp_baselen[P] + L - 1; wt = w.fp_w[P]; if (o >= 0) wt += w.sf_w[o] - w.sf_wf[o]; }
+  if (nfp >= c.cap.FP) { c.overflow = 14; return -1; }
+  int id = nfp++;
+  w.fp_w[id] = wt; w.fp_parent[id] = P < 0 ? IDX_NONE : (uint32_t)P; w.fp_stretch[id] = (uint16_t)s;
+  w.fp_pos[id] = (uint16_t)(ppos + L - 1); w.fp_len[id] = (uint16_t)(plen + 1); w.fp_baselen[id] = (uint16_t)bl;
+  return id;
+}
+// decodePathPair (:4267-4300) into ASCII; returns length or -1
+DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
+  const WS& w = c.ws;
+  int stack[MAXCAND]; int sp = 0;
+  for (int q = P; q >= 0; q = (w.fp_parent[q] == IDX_NONE ? -1 : (int)w.fp_parent[q])) { if (sp >= MAXCAND) return -1; stack[sp++] = w.fp_stretch[q]; }
+  int o = 0;
+  uint32_t fk = w.n_kmer[ds_first(c, stack[sp - 1])];
+  for (int i = 0; i < c.k; ++i) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[(fk >> (2 * (c.k - 1 - i))) & 3]; }
+  for (int t = sp - 1; t >= 0; --t) {
+    int s = stack[t], off = w.ds_off[s], L = w.ds_len[s];
+    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.n_kmer[w.slinks[off + j]] & 3]; }
+  }
+  for (int q = rpid; w.rp_len[q] > 0; q = (int)w.rp_parent[q]) {
+    int s = w.rp_stretch[q], off = w.ds_off[s], L = w.ds_len[s];
+    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.n_kmer[w.slinks[off + j]] & 3]; }
+  }
+  return o;
+}
+
+// forward search + pair enumeration for one (first,last) pair (:4826-5092); lane 0
+DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& ncdh, uint32_t& freeslots) {
+  WS& w = c.ws;
+  int nfp = 0, nsi = 0, nsq = 0;
+  const int K = c.k;
+  for (int i = 0; i < c.cap.BL; ++i) w.apq_n[i] = 0;
+  for (int s = 0; s < c.nds; ++s) if (ds_first(c, s) == Fnode) { int id = fp_extend(c, nfp, -1, s); if (id < 0) return; apq_push(c, id); }
+  for (int zz = 0; zz < c.cap.BL && !c.overflow; ++zz) {
+    while (w.apq_n[zz] > 0) {
+      double* hw = w.apq_w + zz * HEAPK; uint32_t* hi = w.apq_id + zz * HEAPK; int n = w.apq_n[zz];
+      int P = (int)hi[0];
+      heap_pop<false>(hw, hi, n); w.apq_n[zz] = (uint8_t)n;
+      int candlen = w.fp_pos[P] + K;
+      int pls = w.fp_stretch[P];
+      int plast = ds_last(c, pls); uint32_t plk = w.n_kmer[plast];
+      int blo = lmin + K - candlen; if (blo < 0) blo = 0;
+      int bhi = lmax + K - candlen; if (bhi < 0) bhi = 0;
+      int left = -1, right = -1;
+      for (int i = 0; i < narp; ++i) {
+        uint32_t id = w.arp[i];
+        if (w.rp_front[id] == plk && (int)w.rp_baselen[id] >= blo && (int)w.rp_baselen[id] <= bhi) { if (left < 0) left = i; right = i + 1; }
+      }
+      if (left >= 0) {
+        int cur = interval_next(c, left, right, -1);
+        if (nsi >= c.cap.SI || nsq >= c.cap.SI) { c.overflow = 15; return; }
+        int rec = nsi++;
+        w.si_left[rec] = (uint16_t)left; w.si_right[rec] = (uint16_t)right; w.si_cur[rec] = (uint16_t)cur; w.si_path[rec] = (uint32_t)P;
+        w.si_w[rec] = pair_score(c, P, (int)w.arp[cur]);
+        heap_push<true>(w.sq_w, w.sq_id, nsq, w.si_w[rec], (uint32_t)rec);
+      }
+      int pbl = w.fp_baselen[P];
+      if (pbl < K || (pbl - K) < ((lmax + 1) / 2)) {
+        for (int s = 0; s < c.nds; ++s) {
+          if (ds_first(c, s) != plast) continue;
+          int o = sfo_fwd(c, s, w.fp_pos[P]);
+          double ew = o >= 0 ? w.sf_w[o] : 0.0;
+          if (ew > 0.1) {
+            int L = w.ds_len[s];
+            double nwt = w.fp_w[P] + (w.sf_w[o] - w.sf_wf[o]);
+            if (nwt > 0.1 && (w.fp_pos[P] + L - 1 + K) <= lmax) {
+              int id = fp_extend(c, nfp, P, s);
+              if (id < 0) return;
+              apq_push(c, id);
+            }
+          }
+        }
+      }
+    }
+  }
+  int prevlen = -1;
+  for (int nfull = 0; nsq > 0 && nfull < 16 && !c.overflow; ++nfull) {        // :5049-5092
+    int rec = (int)w.sq_id[0]; double weight = w.sq_w[0];
+    heap_pop<true>(w.sq_w, w.sq_id, nsq);
+    int P = (int)w.si_path[rec], cur = w.si_cur[rec];
+    int nxt = interval_next(c, w.si_left[rec], w.si_right[rec], cur);
+    if (nxt >= 0) {
+      if (nsi >= c.cap.SI) { c.overflow = 16; return; }
+      int r2 = nsi++;
+      w.si_left[r2] = w.si_left[rec]; w.si_right[r2] = w.si_right[rec]; w.si_cur[r2] = (uint16_t)nxt; w.si_path[r2] = (uint32_t)P;
+      w.si_w[r2] = pair_score(c, P, (int)w.arp[nxt]);
+      heap_push<true>(w.sq_w, w.sq_id, nsq, w.si_w[r2], (uint32_t)r2);
+    }
+    if (ncdh == CDH_N) {
+      if (weight <= w.cdh_w[0]) continue;
+      freeslots |= 1u << w.cdh_id[0];
+      heap_pop<false>(w.cdh_w, w.cdh_id, ncdh);
+    }
+    int len = decode_pair(c, P, (int)w.arp[cur], w.tmps);
+    if (len < 0) { c.overflow = 17; return; }
+    if (len == prevlen) { bool eq = true; for (int i = 0; i < len; ++i) if (w.tmps[i] != w.prevs[i]) { eq = false; break; } if (eq) continue; }
+    prevlen = len;
+    int slot = 0; while (!((freeslots >> slot) & 1u)) ++slot;
+    freeslots &= ~(1u << slot);
+    for (int i = 0; i < len; ++i) { w.prevs[i] = w.tmps[i]; w.cand[slot * MAXCAND + i] = w.tmps[i]; }
+    w.candlen[slot] = (uint8_t)len;
+    heap_push<false>(w.cdh_w, w.cdh_id, ncdh, weight, (uint32_t)slot);
+  }
+}
+
+// returns number of candidates, ordered as ACC after the error sort (:5101-5156)
+DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
+  WS& w = c.ws;
+  raw_stretches(c, lane);
+  if (c.overflow) return 0;
+  int ncdh = 0; uint32_t freeslots = (1u << (CDH_N + 1)) - 1;
+  int firstthres = c.nfirst ? (w.fl_cnt[0] * 3) / 4 : 0;
+  int lastthres = c.nlast ? (w.ll_cnt[0] * 3) / 4 : 0;
+  for (int fi = 0; fi < c.nfirst && w.fl_cnt[fi] >= firstthres; ++fi)
+    for (int li = 0; li < c.nlast && w.ll_cnt[li] >= lastthres; ++li) {
+      int F = w.fl_nid[fi];
+      int L = lookup(c, w.ll_kmer[li]);
+      if (L == NID_NONE) continue;        // no reverse seed (:3582) => no pairs; forward search has no side effects
+      derive_stretches(c, F, L, lane);
+      if (c.overflow) return 0;
+      stretch_positions(c, lane);
+      if (c.overflow) return 0;
+      stretch_links(c, lane);
+      if (c.overflow) return 0;
+      if (lane == 0) {
+        int narp = 0;
+        reverse_paths(c, L, lmax, narp);
+        if (!c.overflow) search_pair(c, F, lmin, lmax, narp, ncdh, freeslots);
+      }
+      c.overflow = bcast(c.overflow, 0);
+      wsync();
+      if (c.overflow) return 0;
+    }
+  // CDH -> CH -> ACC (descending weight, heap tie order) (:5101-5136)
+  int nacc = 0;
+  if (lane == 0) {
+    int nch = 0;
+    while (ncdh > 0) { double wt = w.cdh_w[0]; uint32_t id = w.cdh_id[0]; heap_pop<false>(w.cdh_w, w.cdh_id, ncdh); heap_push<true>(w.ch_w, w.ch_id, nch, wt, id); }
+    while (nch > 0) { w.acc_w[nacc] = w.ch_w[0]; w.acc_slot[nacc] = (uint8_t)w.ch_id[0]; ++nacc; heap_pop<true>(w.ch_w, w.ch_id, nch); }
+  }
+  nacc = bcast(nacc, 0);
+  wsync();
+  // getSimpleCandidateError (:5355-5363): lanes over sequences
+  for (int a = 0; a < nacc; ++a) {
+    int slot = w.acc_slot[a], m = w.candlen[slot];
+    unsigned long long peq[4];
+    make_peq(peq, w.cand + slot * MAXCAND, m, true);
+    uint32_t e = 0;
+    for (int j = lane; j < c.MAo; j += DCU_NL) e += (uint32_t)myers_dist(peq, m, w.bases + w.soff[j], seqlen(c, j));
+    e = red_sum_u32(e);
+    if (lane == 0) w.acc_err[a] = e;
+  }
+  wsync();
+  if (lane == 0) {                       // std::sort by error, n <= 16 => stable insertion sort (:5156)
+    for (int a = 1; a < nacc; ++a) {
+      double tw = w.acc_w[a]; uint32_t te = w.acc_err[a]; uint8_t ts = w.acc_slot[a]; int b = a;
+      while (b > 0 && w.acc_err[b - 1] > te) { w.acc_w[b] = w.acc_w[b - 1]; w.acc_err[b] = w.acc_err[b - 1]; w.acc_slot[b] = w.acc_slot[b - 1]; --b; }
+      w.acc_w[b] = tw; w.acc_err[b] = te; w.acc_slot[b] = ts;
+    }
+  }
+  wsync();
+  return nacc;
+}
+
+// ------------------------------------------------------------------ placement: align(A window, consensus) with traceback
+// (HandleContext.hpp:2434-2493); convention C1 via bit-vector deltas.  lane 0.  Returns number of ops.
+DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int lb, uint8_t* ops) {
+  WS& w = c.ws;
+  unsigned long long peq[4];
+  make_peq(peq, a, la, false);            // a = base codes
+  unsigned long long pv = ~0ull, mv = 0;
+  for (int j = 1; j <= lb; ++j) {
+    int ch = cons[j - 1]; ch = (ch == 'A') ? 0 : (ch == 'C') ? 1 : (ch == 'G') ? 2 : 3;
+    unsigned long long eq = peq[ch];
+    unsigned long long xv = eq | mv;
+    unsigned long long xh = (((eq & pv) + pv) ^ pv) | eq;
+    unsigned long long ph = mv | ~(xh | pv);
+    unsigned long long mh = pv & xh;
+    w.m_ph[j] = ph; w.m_mh[j] = mh;       // horizontal deltas of rows 1..m (bit i-1), before the shift
+    ph = (ph << 1) | 1ull; mh <<= 1;
+    pv = mh | ~(xv | ph); mv = ph & xv;
+    w.m_pv[j] = pv; w.m_mv[j] = mv;       // vertical deltas in column j
+  }
+  int i = la, j = lb, n = 0;
+  // ops are produced backwards, then reversed in place
+  while (i > 0 || j > 0) {
+    int op;
+    if (i > 0 && j > 0) {
+      int dv = ((w.m_pv[j] >> (i - 1)) & 1ull) ? 1 : (((w.m_mv[j] >> (i - 1)) & 1ull) ? -1 : 0);
+      int dhup = (i == 1) ? 1 : (((w.m_ph[j] >> (i - 2)) & 1ull) ? 1 : (((w.m_mh[j] >> (i - 2)) & 1ull) ? -1 : 0));
+      int ca = a[i - 1]; int cb = cons[j - 1]; cb = (cb == 'A') ? 0 : (cb == 'C') ? 1 : (cb == 'G') ? 2 : 3;
+      int cost = ca != cb;
+      if (dv + dhup == cost) { op = cost ? 1 : 0; --i; --j; }
+      else if (dv == 1) { op = 3; --i; }
+      else { op = 2; --j; }
+    } else if (i > 0) { op = 3; --i; }
+    else { op = 2; --j; }
+    if (n < 128) ops[n] = (uint8_t)op;
+    ++n;
+  }
+  if (n > 128) return -1;
+  for (int x = 0, y = n - 1; x < y; ++x, --y) { uint8_t t = ops[x]; ops[x] = ops[y]; ops[y] = t; }
+  return n;
+}
+
+// ------------------------------------------------------------------ one window (HandleContext.hpp:2164-2494)
+DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons_out, uint8_t* ops_out, int lane) {
+  WS& w = c.ws;
+  res.status = ST_SKIPPED; res.k = 0; res.ff = -1; res.clen = 0; res.err = 0; res.nops = 0; res.ncand = 0; res.elength = 0;
+  load_window(c, win, lane);
+  if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+  int elength = estimate_length(c, lane);
+  res.elength = elength;
+  if (c.MAo < c.P.mincov) return;
+  if (seqlen(c, 0) != c.P.w) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+  int lmin = elength - 4, lmax = elength + 4;
+  bool pathfailed = true, have = false;
+  unsigned long long minrate = c.P.eminrate;
+  int bestlen = 0, bestk = 0, bestff = -1, bestn = 0;
+  for (int k = c.P.k_lo; k <= c.P.k_hi; ++k) {
+    c.k = k; c.kidx = k - c.P.k_lo; c.kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    c.nex = 0;
+    build_hash(c, lane);
+    for (int ff = c.P.maxff; ff >= c.P.minff; --ff) {
+      int f = ff > 1 ? ff : 1;
+      if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
+      build_nodes(c, f, lane);
+      if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+      if (ff == 0) {
+        gap_fill(c, lane);
+        if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+        build_nodes(c, 1, lane);                         // setupNodes over all prenodes (:2248)
+        if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+      }
+      build_edges(c, lane);
+      int mintry = 0; bool lconsok = false;
+      for (;;) {
+        int nacc = traverse(c, lmin, lmax, lane);
+        if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+        if (nacc > 0) {
+          unsigned long long e0 = bcast(w.acc_err[0], 0);    // checkCandidatesU == error of candidate 0 (:5476-5482)
+          if (e0 < minrate) {
+            lconsok = true; minrate = e0; have = true;
+            int slot = w.acc_slot[0]; bestlen = w.candlen[slot]; bestk = k; bestff = ff; bestn = nacc;
+            for (int i = lane; i < bestlen; i += DCU_NL) w.best[i] = w.cand[slot * MAXCAND + i];
+            wsync();
+          } else if (have) lconsok = true;
+          break;
+        } else if (++mintry >= 3) break;
+        if (!add_next(c, lane)) break;
+      }
+      if (lconsok) { pathfailed = false; break; }
+    }
+  }
+  if (pathfailed) { res.status = ST_FAILED; return; }
+  int nops = 0;
+  if (lane == 0) {
+    for (int i = 0; i < bestlen; ++i) cons_out[i] = w.best[i];
+    nops = placement(c, w.bases, c.P.w, w.best, bestlen, ops_out);
+  }
+  nops = bcast(nops, 0);
+  if (nops < 0) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+  res.status = ST_OK; res.k = (uint8_t)bestk; res.ff = (int8_t)bestff; res.clen = (uint8_t)bestlen;
+  res.err = (uint32_t)minrate; res.nops = (uint16_t)nops; res.ncand = (uint16_t)bestn;
+}
+
+}  // namespace dcu

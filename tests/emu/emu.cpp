@@ -1,0 +1,58 @@
+// TEST-ONLY build of the kernel source (daccord_b200/csrc/window_core.cuh) as a single-lane host
+// emulation (-DDCU_EMU): lets the parity tests exercise the product's per-window logic against the
+// oracle in a container without a GPU.  Never linked into the product library.
+#define DCU_EMU 1
+#include "../../daccord_b200/csrc/window_core.cuh"
+#include "../../daccord_b200/csrc/host_tables.hpp"
+#include "../../daccord_b200/csrc/host_caps.hpp"
+#include "../../include/daccord_b200.h"
+#include <vector>
+#include <cstring>
+#include <cstdlib>
+
+extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
+                             dcu_result* res, uint8_t* cons, uint8_t* ops, int tier, uint64_t* noverflow) {
+  dcu_host::HostTables HT;
+  int maxS = 4, maxB = 64;
+  for (uint64_t i = 0; i < nwin; ++i) {
+    int b = 0;
+    for (uint32_t j = 0; j < win[i].slice_cnt; ++j) b += sl[win[i].slice_begin + j].len;
+    maxS = std::max<int>(maxS, win[i].slice_cnt); maxB = std::max(maxB, b);
+  }
+  dcu_host::build_tables((int)prm->w, prm->p_i, prm->p_d, prm->est_cor, (int)prm->k_lo, (int)prm->k_hi, maxS + 2, HT);
+  dcu::Caps caps = dcu_host::make_caps(tier, (int)prm->w, maxS, maxB);
+  dcu::Layout L; dcu::make_layout(caps, L);
+  std::vector<uint8_t> slab(L.bytes + 64);
+  dcu::Ctx c;
+  dcu::bind_ws(c.ws, slab.data(), L);
+  c.cap = caps;
+  c.T.DPn = HT.DPn.data(); c.T.DPsq = HT.DPsq.data(); c.T.VSq = HT.VSq.data(); c.T.suplo = HT.suplo.data(); c.T.suphi = HT.suphi.data();
+  c.T.klim = HT.klim.data(); c.T.NP = HT.NP; c.T.MS = HT.MS; c.T.KLIMN = HT.KLIMN;
+  c.P.w = (int)prm->w; c.P.k_lo = (int)prm->k_lo; c.P.k_hi = (int)prm->k_hi; c.P.minff = prm->min_ff; c.P.maxff = prm->max_ff;
+  c.P.mincov = (int)prm->min_cov; c.P.check = prm->est_cor != 0.0; c.P.eminrate = prm->max_err;
+  c.packed = packed; c.sl = (const dcu::Slice*)sl;
+  uint64_t nov = 0;
+  for (uint64_t i = 0; i < nwin; ++i) {
+    dcu::Result r;
+    dcu::Window W; memcpy(&W, &win[i], sizeof(W));
+    memset(cons + i * DCU_CONS_STRIDE, 0, DCU_CONS_STRIDE); memset(ops + i * DCU_OPS_STRIDE, 0, DCU_OPS_STRIDE);
+    dcu::process_window(c, W, r, cons + i * DCU_CONS_STRIDE, ops + i * DCU_OPS_STRIDE, 0);
+    memcpy(&res[i], &r, sizeof(r));
+    if (r.status == dcu::ST_OVERFLOW) ++nov;
+  }
+  if (noverflow) *noverflow = nov;
+  return 0;
+}
+// product table builder exposed for the table-parity test
+extern "C" int64_t emu_get_tables(const dcu_params* prm, int which, double* out, int64_t cap, int klimn) {
+  dcu_host::HostTables HT;
+  dcu_host::build_tables((int)prm->w, prm->p_i, prm->p_d, prm->est_cor, (int)prm->k_lo, (int)prm->k_hi, klimn, HT);
+  std::vector<double> v;
+  if (which == 0) v = HT.DPn; else if (which == 1) v = HT.DPsq;
+  else if (which == 2) for (auto x : HT.VSq) v.push_back((double)x);
+  else if (which == 3) for (int i = 0; i < HT.MS; ++i) { v.push_back(HT.suplo[i]); v.push_back(HT.suphi[i]); }
+  else if (which == 4) for (auto x : HT.klim) v.push_back((double)x);
+  else if (which == 5) { v.push_back(HT.NP); v.push_back(HT.MS); }
+  if ((int64_t)v.size() <= cap) memcpy(out, v.data(), v.size() * sizeof(double));
+  return (int64_t)v.size();
+}
