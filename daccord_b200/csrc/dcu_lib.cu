@@ -1,0 +1,304 @@
+// dcu_lib.cu -- sm_100a kernel wrapper and C-ABI (include/daccord_b200.h) of the window-consensus engine.
+// One persistent launch per batch: every warp pulls window indices from a global ticket counter and runs
+// dcu::process_window (window_core.cuh) on its private workspace slab.  Windows whose graph does not fit
+// the small (tier 0) slab are queued and re-run by a second launch on large (tier 1) slabs -- still on the
+// GPU; there is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <new>
+#include "window_core.cuh"
+#include "host_tables.hpp"
+#include "host_caps.hpp"
+#include "../../include/daccord_b200.h"
+
+static_assert(sizeof(dcu::Slice) == sizeof(dcu_slice) && sizeof(dcu::Window) == sizeof(dcu_window) && sizeof(dcu::Result) == sizeof(dcu_result), "ABI structs");
+
+namespace {
+
+constexpr int WPB = 4;                 // warps per block
+
+struct KArgs {
+  dcu::Layout L; dcu::Caps cap; dcu::Tables T; dcu::Params P;
+  const uint8_t* packed; const dcu::Slice* sl; const dcu::Window* win;
+  dcu::Result* res; uint8_t* cons; uint8_t* ops;
+  uint8_t* slabs;                      // [total warps][L.bytes]
+  const uint32_t* todo;                // window indices to run (nullptr: 0..n-1)
+  uint32_t n;
+  unsigned int* ticket;                // work counter
+  unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this tier
+};
+
+__global__ void __launch_bounds__(WPB * 32) dcu_window_kernel(const __grid_constant__ KArgs a) {
+  __shared__ dcu::WS s_ws[WPB];
+  __shared__ dcu::Caps s_cap; __shared__ dcu::Tables s_T; __shared__ dcu::Params s_P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_cap = a.cap; s_T = a.T; s_P = a.P; }
+  if (lane == 0) {
+    size_t gw = (size_t)blockIdx.x * WPB + warp;
+    dcu::bind_ws(s_ws[warp], a.slabs + gw * (size_t)a.L.bytes, a.L);
+  }
+  __syncthreads();
+  dcu::Ctx c(s_ws[warp], s_cap, s_T, s_P);
+  c.packed = a.packed; c.sl = a.sl;
+  for (;;) {
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.n) break;
+    uint32_t wi = a.todo ? a.todo[t] : t;
+    dcu::Window W = a.win[wi];
+    dcu::Result r;
+    dcu::process_window(c, W, r, a.cons + (size_t)wi * DCU_CONS_STRIDE, a.ops + (size_t)wi * DCU_OPS_STRIDE, lane);
+    if (lane == 0) {
+      a.res[wi] = r;
+      if (r.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
+    }
+    __syncwarp();
+  }
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DCU_ERR_CUDA; } } while (0)
+
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct dcu_ctx {
+  int device = 0;
+  dcu_params prm{};
+  dcu_host::HostTables HT;
+  dcu::Tables T{}; dcu::Params P{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0, blocks_per_sm[2] = {4, 1};
+  // tables
+  DevBuf<double> dDPn, dDPsq; DevBuf<unsigned long long> dVSq, dklim; DevBuf<uint16_t> dsuplo, dsuphi;
+  // database
+  DevBuf<uint8_t> dpacked_own; const uint8_t* dpacked = nullptr; uint64_t packed_bytes = 0;
+  // batch
+  DevBuf<dcu::Window> dwin; DevBuf<dcu::Slice> dsl; DevBuf<dcu::Result> dres; DevBuf<uint8_t> dcons, dops;
+  DevBuf<uint32_t> dovf[2]; DevBuf<unsigned int> dcnt;     // dcnt: [ticket0, ovf0, ticket1, ovf1]
+  DevBuf<uint8_t> dslab[2];
+  dcu::Caps caps[2]; dcu::Layout lay[2]; int grid[2] = {0, 0};
+  uint64_t nwin = 0, nsl = 0; int maxS = 0, maxB = 0;
+  uint64_t launches = 0, hard = 0;
+  std::string err;
+};
+
+extern "C" {
+
+const char* dcu_strerror(int code) {
+  switch (code) {
+    case DCU_OK: return "ok";
+    case DCU_ERR_PARAM: return "invalid parameter";
+    case DCU_ERR_CUDA: return "CUDA error";
+    case DCU_ERR_UNSUPPORTED: return "parameter outside the range this build supports";
+    case DCU_ERR_OVERFLOW: return "a window exceeded the large-workspace capacities";
+    case DCU_ERR_STATE: return "call out of order";
+    default: return "unknown";
+  }
+}
+const char* dcu_last_error(dcu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
+  if (!p || !out) return DCU_ERR_PARAM;
+  *out = nullptr;
+  if (p->w < 8 || p->w > 59) return DCU_ERR_UNSUPPORTED;               // consensus / A window must fit 64-bit Myers words
+  if (p->k_lo < 3 || p->k_hi > 14 || p->k_lo > p->k_hi) return DCU_ERR_UNSUPPORTED;
+  if (p->max_ff < p->min_ff || p->min_ff < 0) return DCU_ERR_PARAM;
+  if (!(p->p_i >= 0 && p->p_i < 1 && p->p_d >= 0 && p->p_d < 1)) return DCU_ERR_PARAM;
+  dcu_ctx* ctx = new (std::nothrow) dcu_ctx();
+  if (!ctx) return DCU_ERR_PARAM;
+  ctx->device = device; ctx->prm = *p;
+  *out = ctx;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
+  dcu_host::build_tables((int)p->w, p->p_i, p->p_d, p->est_cor, (int)p->k_lo, (int)p->k_hi, 2048, ctx->HT);
+  auto& H = ctx->HT;
+  CK(ctx->dDPn.ensure(H.DPn.size())); CK(ctx->dDPsq.ensure(H.DPsq.size())); CK(ctx->dVSq.ensure(H.VSq.size()));
+  CK(ctx->dklim.ensure(H.klim.size())); CK(ctx->dsuplo.ensure(H.suplo.size())); CK(ctx->dsuphi.ensure(H.suphi.size()));
+  CK(cudaMemcpy(ctx->dDPn.p, H.DPn.data(), H.DPn.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dDPsq.p, H.DPsq.data(), H.DPsq.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dVSq.p, H.VSq.data(), H.VSq.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dklim.p, H.klim.data(), H.klim.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dsuplo.p, H.suplo.data(), H.suplo.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dsuphi.p, H.suphi.data(), H.suphi.size() * 2, cudaMemcpyHostToDevice));
+  ctx->T.DPn = ctx->dDPn.p; ctx->T.DPsq = ctx->dDPsq.p; ctx->T.VSq = ctx->dVSq.p; ctx->T.klim = ctx->dklim.p;
+  ctx->T.suplo = ctx->dsuplo.p; ctx->T.suphi = ctx->dsuphi.p; ctx->T.NP = H.NP; ctx->T.MS = H.MS; ctx->T.KLIMN = H.KLIMN;
+  ctx->P.w = (int)p->w; ctx->P.k_lo = (int)p->k_lo; ctx->P.k_hi = (int)p->k_hi; ctx->P.minff = p->min_ff; ctx->P.maxff = p->max_ff;
+  ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err;
+  CK(ctx->dcnt.ensure(4));
+  const char* e = getenv("DCU_BLOCKS_PER_SM");
+  if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);
+  return DCU_OK;
+}
+
+void dcu_destroy(dcu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->dDPn.release(); ctx->dDPsq.release(); ctx->dVSq.release(); ctx->dklim.release(); ctx->dsuplo.release(); ctx->dsuphi.release();
+  ctx->dpacked_own.release(); ctx->dwin.release(); ctx->dsl.release(); ctx->dres.release(); ctx->dcons.release(); ctx->dops.release();
+  ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int dcu_set_reads(dcu_ctx* ctx, const uint8_t* packed, uint64_t nbytes) {
+  if (!ctx || !packed) return DCU_ERR_PARAM;
+  if (nbytes >= (1ull << 30)) { ctx->err = "database larger than 2^32 bases"; return DCU_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->dpacked_own.ensure(nbytes + 16));
+  CK(cudaMemcpyAsync(ctx->dpacked_own.p, packed, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->dpacked_own.p + nbytes, 0, 16, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->dpacked = ctx->dpacked_own.p; ctx->packed_bytes = nbytes;
+  return DCU_OK;
+}
+int dcu_set_reads_device(dcu_ctx* ctx, const void* dpacked, uint64_t nbytes) {
+  if (!ctx || !dpacked) return DCU_ERR_PARAM;
+  if (nbytes >= (1ull << 30)) { ctx->err = "database larger than 2^32 bases"; return DCU_ERR_UNSUPPORTED; }
+  ctx->dpacked = (const uint8_t*)dpacked; ctx->packed_bytes = nbytes;
+  return DCU_OK;
+}
+
+int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_slice* sl, uint64_t nsl) {
+  if (!ctx || (!win && nwin) || (!sl && nsl)) return DCU_ERR_PARAM;
+  if (!ctx->dpacked) { ctx->err = "dcu_set_reads not called"; return DCU_ERR_STATE; }
+  if (nwin >= 0xFFFFFFF0ull || nsl >= 0xFFFFFFF0ull) return DCU_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(ctx->device));
+  // validate and size the workspaces for this batch
+  int maxS = 4, maxB = 64;
+  const uint64_t nbases = ctx->packed_bytes * 4;
+  for (uint64_t i = 0; i < nwin; ++i) {
+    const dcu_window& W = win[i];
+    if ((uint64_t)W.slice_begin + W.slice_cnt > nsl) { ctx->err = "window slice range out of bounds"; return DCU_ERR_PARAM; }
+    int b = 0;
+    for (uint32_t j = 0; j < W.slice_cnt; ++j) {
+      const dcu_slice& s = sl[W.slice_begin + j];
+      if (s.len > 255) { ctx->err = "slice longer than 255 bases"; return DCU_ERR_UNSUPPORTED; }
+      if ((uint64_t)s.gpos + s.len > nbases) { ctx->err = "slice outside the read database"; return DCU_ERR_PARAM; }
+      b += s.len;
+    }
+    if (W.slice_cnt && sl[W.slice_begin].len != ctx->prm.w && W.slice_cnt >= ctx->prm.min_cov) { ctx->err = "slice 0 of a window must be the A window of length w"; return DCU_ERR_PARAM; }
+    maxS = std::max<int>(maxS, W.slice_cnt); maxB = std::max(maxB, b);
+  }
+  if (maxS >= ctx->HT.KLIMN || maxB > 65000) { ctx->err = "pile deeper than this build supports"; return DCU_ERR_UNSUPPORTED; }
+  ctx->maxS = maxS; ctx->maxB = maxB;
+  for (int t = 0; t < 2; ++t) { ctx->caps[t] = dcu_host::make_caps(t, (int)ctx->prm.w, maxS, maxB); dcu::make_layout(ctx->caps[t], ctx->lay[t]); }
+  CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
+  CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));
+  CK(ctx->dovf[0].ensure(nwin + 1)); CK(ctx->dovf[1].ensure(nwin + 1));
+  if (nwin) CK(cudaMemcpyAsync(ctx->dwin.p, win, nwin * sizeof(dcu_window), cudaMemcpyHostToDevice, ctx->stream));
+  if (nsl) CK(cudaMemcpyAsync(ctx->dsl.p, sl, nsl * sizeof(dcu_slice), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->nwin = nwin; ctx->nsl = nsl;
+  return DCU_OK;
+}
+
+static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n) {
+  int bps = ctx->blocks_per_sm[tier];
+  int grid = ctx->num_sms * bps;
+  size_t need_blocks = ((size_t)n + WPB - 1) / WPB;
+  if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
+  CK(ctx->dslab[tier].ensure((size_t)grid * WPB * ctx->lay[tier].bytes));
+  KArgs a;
+  a.L = ctx->lay[tier]; a.cap = ctx->caps[tier]; a.T = ctx->T; a.P = ctx->P;
+  a.packed = ctx->dpacked; a.sl = ctx->dsl.p; a.win = ctx->dwin.p; a.res = ctx->dres.p; a.cons = ctx->dcons.p; a.ops = ctx->dops.p;
+  a.slabs = ctx->dslab[tier].p; a.todo = todo; a.n = n;
+  a.ticket = ctx->dcnt.p + 2 * tier; a.ovf_cnt = ctx->dcnt.p + 2 * tier + 1; a.ovf_list = ctx->dovf[tier].p;
+  dcu_window_kernel<<<grid, WPB * 32, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return DCU_OK;
+}
+
+int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
+  if (!ctx) return DCU_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  ctx->launches = 0; ctx->hard = 0;
+  if (kernel_ms) *kernel_ms = 0.f;
+  if (!ctx->nwin) return DCU_OK;
+  CK(cudaMemsetAsync(ctx->dcnt.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = launch_tier(ctx, 0, nullptr, (uint32_t)ctx->nwin);
+  if (rc) return rc;
+  unsigned int cnt[4];
+  CK(cudaMemcpyAsync(cnt, ctx->dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int ret = DCU_OK;
+  if (cnt[1]) {
+    ctx->hard = cnt[1];
+    rc = launch_tier(ctx, 1, ctx->dovf[0].p, cnt[1]);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(cnt, ctx->dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (cnt[3]) { char b[128]; snprintf(b, sizeof b, "%u windows exceeded the large-workspace capacities", cnt[3]); ctx->err = b; ret = DCU_ERR_OVERFLOW; }
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+  return ret;
+}
+
+int dcu_download(dcu_ctx* ctx, dcu_result* res, uint8_t* cons, uint8_t* ops) {
+  if (!ctx) return DCU_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->nwin) return DCU_OK;
+  if (res) CK(cudaMemcpyAsync(res, ctx->dres.p, ctx->nwin * sizeof(dcu_result), cudaMemcpyDeviceToHost, ctx->stream));
+  if (cons) CK(cudaMemcpyAsync(cons, ctx->dcons.p, ctx->nwin * DCU_CONS_STRIDE, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ops) CK(cudaMemcpyAsync(ops, ctx->dops.p, ctx->nwin * DCU_OPS_STRIDE, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return DCU_OK;
+}
+
+int dcu_run(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_slice* sl, uint64_t nsl, dcu_result* res, uint8_t* cons, uint8_t* ops) {
+  int rc = dcu_upload(ctx, win, nwin, sl, nsl);
+  if (rc) return rc;
+  int rl = dcu_launch(ctx, nullptr);
+  if (rl && rl != DCU_ERR_OVERFLOW) return rl;
+  rc = dcu_download(ctx, res, cons, ops);
+  return rc ? rc : rl;
+}
+
+int dcu_last_stats(dcu_ctx* ctx, uint64_t* launches, uint64_t* hard_windows) {
+  if (!ctx) return DCU_ERR_PARAM;
+  if (launches) *launches = ctx->launches;
+  if (hard_windows) *hard_windows = ctx->hard;
+  return DCU_OK;
+}
+
+int64_t dcu_get_tables(dcu_ctx* ctx, int which, double* out, int64_t cap) {
+  if (!ctx) return -1;
+  std::vector<double> v; auto& H = ctx->HT;
+  if (which == 0) v = H.DPn; else if (which == 1) v = H.DPsq;
+  else if (which == 2) for (auto x : H.VSq) v.push_back((double)x);
+  else if (which == 3) for (int i = 0; i < H.MS; ++i) { v.push_back(H.suplo[i]); v.push_back(H.suphi[i]); }
+  else if (which == 4) for (auto x : H.klim) v.push_back((double)x);
+  else if (which == 5) { v.push_back(H.NP); v.push_back(H.MS); v.push_back(H.KLIMN); }
+  if (out && (int64_t)v.size() <= cap) memcpy(out, v.data(), v.size() * sizeof(double));
+  return (int64_t)v.size();
+}
+
+}  // extern "C"

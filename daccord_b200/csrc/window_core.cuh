@@ -31,6 +31,7 @@
 #ifdef DCU_EMU
 #define DCU_FN static inline
 #define DCU_BIG static
+#define DCU_CTOR
 #define DCU_NL 1
 namespace dcu {
 static inline void wsync() {}
@@ -50,6 +51,7 @@ template <class T> static inline T ldg(const T* p) { return *p; }
 #else
 #define DCU_FN __device__ __forceinline__
 #define DCU_BIG __device__ __noinline__
+#define DCU_CTOR __device__
 #define DCU_NL 32
 namespace dcu {
 __device__ __forceinline__ void wsync() { __syncwarp(); }
@@ -179,7 +181,7 @@ static inline void make_layout(const Caps& c, Layout& L) {
 #ifdef DCU_EMU
 static inline
 #else
-__host__ __device__ inline
+__device__ inline
 #endif
 void bind_ws(WS& w, uint8_t* base, const Layout& L) {
   int i = 0;
@@ -191,7 +193,8 @@ void bind_ws(WS& w, uint8_t* base, const Layout& L) {
 
 // per-window state that all lanes hold identically
 struct Ctx {
-  WS ws; Caps cap; Tables T; Params P;
+  const WS& ws; const Caps& cap; const Tables& T; const Params& P;   // read-only, shared by the warp's lanes
+  DCU_CTOR Ctx(const WS& rws, const Caps& rcap, const Tables& rT, const Params& rP) : ws(rws), cap(rcap), T(rT), P(rP) {}
   const uint8_t* packed; const Slice* sl;
   int MAo, nbases;
   int k; uint32_t kmask; int kidx;
@@ -248,7 +251,7 @@ template <bool MAXH> DCU_FN void heap_pop(double* hw, uint32_t* hi, int& n) {
 // ------------------------------------------------------------------ load: slices -> base codes
 // replaces DecodedReadContainer + the MA array (HandleContext.hpp:2032-2043); bases as codes 0..3
 DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   c.MAo = win.slice_cnt; c.overflow = 0;
   if (c.MAo > c.cap.S) { c.overflow = 1; return; }
   const Slice* sl = c.sl + win.slice_begin;
@@ -276,7 +279,7 @@ DCU_FN int seqlen(const Ctx& c, int j) { return c.ws.soff[j + 1] - c.ws.soff[j];
 
 // ------------------------------------------------------------------ expected length (HandleContext.hpp:2051-2155)
 DCU_BIG int estimate_length(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int maxv = -1;
   if (c.MAo) {
     int mn = 0x7fffffff, mx = -0x7fffffff;
@@ -316,7 +319,7 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
 
 // ------------------------------------------------------------------ k-mer hash build (replaces setupPreNodes :2018-2304)
 DCU_BIG void build_hash(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   for (int i = lane; i < c.cap.H; i += DCU_NL) { w.hkey[i] = W_EMPTY; w.hcnt[i] = 0; }
   wsync();
   uint32_t mask = (uint32_t)c.cap.H - 1;
@@ -366,7 +369,7 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
 
 // nodes = k-mers with count >= f (filterFreq :1181-1197), instance lists (setupNodes :1918-2014)
 DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int nn = 0;
   for (int base = 0; base < c.cap.H; base += DCU_NL) {
     int i = base + lane;
@@ -432,7 +435,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
 
 // active predecessors (:2552-2597): p->v is active iff v is among p's first nact successors
 DCU_BIG void compute_npred(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int shift = 2 * (c.k - 1);
   for (int n = lane; n < c.nn; n += DCU_NL) {
     uint32_t v = w.n_kmer[n];
@@ -450,7 +453,7 @@ DCU_BIG void compute_npred(Ctx& c, int lane) {
 }
 // successor lists + primary activation (setNodesActive :1770-1814 / setupAddHeap :1818-1859)
 DCU_BIG void build_edges(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int no = c.MAo < c.T.KLIMN ? c.MAo : c.T.KLIMN - 1;
   unsigned long long lim = c.P.check ? ldg(c.T.klim + (size_t)c.kidx * c.T.KLIMN + no) : 0;
   for (int n = lane; n < c.nn; n += DCU_NL) {
@@ -478,7 +481,7 @@ DCU_BIG void build_edges(Ctx& c, int lane) {
 }
 // addNextFromHeap (:1861-1897): activate every pending edge of the highest pending frequency
 DCU_BIG bool add_next(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   uint32_t top = 0;
   for (int n = lane; n < c.nn; n += DCU_NL) { int na = w.n_nact[n]; if (na < w.n_nsucc[n]) { uint32_t f = w.n_sfreq[4 * n + na]; top = f > top ? f : top; } }
   top = red_max_u32(top);
@@ -495,7 +498,7 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
 
 // ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
 DCU_BIG void gap_fill(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   uint32_t* nexp = &w.n_fill[0];      // n_fill[0] doubles as the append counter here (rebuilt afterwards)
   if (lane == 0) *nexp = 0;
   wsync();
@@ -551,7 +554,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
 // ------------------------------------------------------------------ stretches (unitigs)
 // computeStretches(checkpredecessors=true) (:2844-2986); serial walk over the precomputed successor ids
 DCU_BIG void raw_stretches(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   if (lane == 0) {
     int nrs = 0, slO = 0; uint16_t stamp = 0; bool ovf = false;
     for (int n = 0; n < c.nn; ++n) w.n_mark[n] = 0;
@@ -593,7 +596,7 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
 
 // splitStretches(first), splitStretches(last), stretchesUnique (:2772-2841, :3087-3114) on views
 DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   if (lane == 0) {
     int n = c.nrs; bool ovf = false;
     for (int i = 0; i < n; ++i) { w.ds_off[i] = w.rs_off[i]; w.ds_len[i] = w.rs_len[i]; }
@@ -652,7 +655,7 @@ DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s] + c.
 
 // computeFeasibleStretchPositions (:3176-3330), weights evaluated on demand, lanes over positions
 DCU_BIG void stretch_positions(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int nsf = 0, nsc = 0;
   for (int s = 0; s < c.nds; ++s) {
     int off = w.ds_off[s], L = w.ds_len[s];
@@ -713,7 +716,7 @@ DCU_FN int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchReverseP
 
 // computeStretchLinks / getReverseStretchLinkWeight (:3388-3480); serial, output sorted by (to, from)
 DCU_BIG void stretch_links(Ctx& c, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   if (lane == 0) {
     int nrl = 0; bool ovf = false;
     for (int B = 0; B < c.nds && !ovf; ++B) {
@@ -769,7 +772,7 @@ DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool as
 struct TravOut { int nacc; };
 
 DCU_FN int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front, int stretch, int pos, int len, int baselen) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   if (nrp >= c.cap.RP) { c.overflow = 11; return -1; }
   int id = nrp++;
   w.rp_w[id] = wgt; w.rp_parent[id] = parent; w.rp_front[id] = front; w.rp_stretch[id] = (uint16_t)stretch;
@@ -779,7 +782,7 @@ DCU_FN int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front,
 
 // reverse half-paths (prepareTraverse :3576-3757); lane 0
 DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int nrp = 0, nq = 0; narp = 0;
   for (int i = 0; i < c.cap.BL; ++i) w.arph_n[i] = 0;
   int seed = rp_new(c, nrp, 0.0, IDX_NONE, w.n_kmer[Lnode], NID_NONE, 0, 0, c.k);
@@ -861,7 +864,7 @@ DCU_FN int interval_next(const Ctx& c, int left, int right, int cur) {
   return best;
 }
 DCU_FN void apq_push(Ctx& c, int pid) {                        // :4843-4862, :4997-5017
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int bl = w.fp_baselen[pid];
   if (bl >= c.cap.BL) return;                                  // longer than lmax: never pairs, never extends
   double* hw = w.apq_w + bl * HEAPK; uint32_t* hi = w.apq_id + bl * HEAPK; int n = w.apq_n[bl];
@@ -871,7 +874,7 @@ DCU_FN void apq_push(Ctx& c, int pid) {                        // :4843-4862, :4
   w.apq_n[bl] = (uint8_t)n;
 }
 DCU_FN int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath (:3989-4056); P == -1 -> empty path
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int ppos = P < 0 ? 0 : w.fp_pos[P], plen = P < 0 ? 0 : w.fp_len[P];
   int o = sfo_fwd(c, s, ppos);
   int L = w.ds_len[s];
@@ -905,7 +908,7 @@ DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
 
 // forward search + pair enumeration for one (first,last) pair (:4826-5092); lane 0
 DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& ncdh, uint32_t& freeslots) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   int nfp = 0, nsi = 0, nsq = 0;
   const int K = c.k;
   for (int i = 0; i < c.cap.BL; ++i) w.apq_n[i] = 0;
@@ -984,7 +987,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
 
 // returns number of candidates, ordered as ACC after the error sort (:5101-5156)
 DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   raw_stretches(c, lane);
   if (c.overflow) return 0;
   int ncdh = 0; uint32_t freeslots = (1u << (CDH_N + 1)) - 1;
@@ -1044,7 +1047,7 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
 // ------------------------------------------------------------------ placement: align(A window, consensus) with traceback
 // (HandleContext.hpp:2434-2493); convention C1 via bit-vector deltas.  lane 0.  Returns number of ops.
 DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int lb, uint8_t* ops) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   unsigned long long peq[4];
   make_peq(peq, a, la, false);            // a = base codes
   unsigned long long pv = ~0ull, mv = 0;
@@ -1084,7 +1087,7 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
 
 // ------------------------------------------------------------------ one window (HandleContext.hpp:2164-2494)
 DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons_out, uint8_t* ops_out, int lane) {
-  WS& w = c.ws;
+  const WS& w = c.ws;
   res.status = ST_SKIPPED; res.k = 0; res.ff = -1; res.clen = 0; res.err = 0; res.nops = 0; res.ncand = 0; res.elength = 0;
   load_window(c, win, lane);
   if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }

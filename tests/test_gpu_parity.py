@@ -1,0 +1,88 @@
+"""GPU parity tests (-m gpu): the CUDA library, called through its C ABI, against the oracle on the same
+seeded batches; bit-exact on status, k, filterfreq, error, consensus bytes and placement trace."""
+import numpy as np
+import pytest
+from common import default_params, synth_batch, run_oracle, compare_results, get_tables, oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(p):
+    import daccord_b200 as d
+    pp = d.Params.default(w=p.w, k_lo=p.k_lo, k_hi=p.k_hi, min_cov=p.min_cov, min_ff=p.min_ff, max_ff=p.max_ff, max_err=p.max_err,
+                          p_i=p.p_i, p_d=p.p_d, est_cor=p.est_cor)
+    return d.Engine(pp, 0)
+
+
+def test_tables_match_oracle():
+    p = default_params()
+    e = _engine(p)
+    for which in range(4):
+        a = get_tables(oracle_lib(), "oracle_get_tables", p, which)
+        b = e.tables(which)
+        assert a.shape == b.shape and (a.view(np.uint64) == b.view(np.uint64)).all(), which
+    e.close()
+
+
+CASES = [
+    ("d40", dict(depth=40, n=1500, seed=103, rf=0.0), {}),
+    ("d10", dict(depth=10, n=800, seed=104, rf=0.0), {}),
+    ("d3", dict(depth=3, n=400, seed=105, rf=0.0), {}),
+    ("repeats", dict(depth=12, n=800, seed=106, rf=0.6), {}),
+    ("repeats40", dict(depth=40, n=800, seed=116, rf=0.6), {}),
+    ("gapfill", dict(depth=8, n=400, seed=107, rf=0.3), dict(min_ff=0, max_ff=0)),
+    ("multik", dict(depth=12, n=300, seed=108, rf=0.3), dict(k_lo=6, k_hi=10)),
+    ("k12", dict(depth=30, n=300, seed=109, rf=0.2), dict(k_lo=12, k_hi=12)),
+    ("k14", dict(depth=30, n=200, seed=110, rf=0.2), dict(k_lo=14, k_hi=14)),
+    ("ebound", dict(depth=20, n=400, seed=111, rf=0.2), dict(max_err=120)),
+    ("w32", dict(depth=25, n=300, seed=112, rf=0.2), dict(w=32)),
+    ("w56", dict(depth=25, n=300, seed=113, rf=0.2), dict(w=56)),
+    ("deep200", dict(depth=200, n=100, seed=115, rf=0.3), {}),
+]
+
+
+@pytest.mark.parametrize("name,gen,kw", CASES, ids=[c[0] for c in CASES])
+def test_cuda_matches_oracle(name, gen, kw):
+    p = default_params(**kw)
+    packed, win, sl, _ = synth_batch(gen["n"], gen["depth"], seed=gen["seed"], repeat_frac=gen["rf"], depth_jitter=min(gen["depth"], 3), w=p.w)
+    ro = run_oracle(p, packed, win, sl, 8)
+    e = _engine(p)
+    e.set_reads(packed)
+    rg = e.run(win, sl)
+    bad = compare_results(ro, rg)
+    st = e.stats()
+    e.close()
+    assert not bad, (name, len(bad), bad[:5], [(ro[0][i], rg[0][i]) for i in bad[:3]])
+    assert st["launches"] >= 1
+
+
+def test_repeatable_and_order_independent():
+    p = default_params()
+    packed, win, sl, _ = synth_batch(600, 20, seed=120, repeat_frac=0.3)
+    e = _engine(p)
+    e.set_reads(packed)
+    a = e.run(win, sl)
+    b = e.run(win, sl)
+    assert not compare_results(a, b)
+    perm = np.random.default_rng(1).permutation(len(win))
+    c = e.run(win[perm].copy(), sl)
+    inv = np.argsort(perm)
+    c2 = (c[0][inv], c[1].reshape(-1, 64)[inv].reshape(-1), c[2].reshape(-1, 128)[inv].reshape(-1))
+    assert not compare_results(a, c2)
+    e.close()
+
+
+def test_errors_are_loud():
+    import daccord_b200 as d
+    p = default_params()
+    e = _engine(p)
+    packed, win, sl, _ = synth_batch(4, 5, seed=1)
+    with pytest.raises(d.DcuError):
+        e.run(win, sl)                 # no database set
+    e.set_reads(packed)
+    bad = sl.copy(); bad[3]["gpos"] = 2**31
+    with pytest.raises(d.DcuError):
+        e.run(win, bad)                # slice outside the database
+    with pytest.raises(d.DcuError):
+        d.Engine(d.Params.default(w=100), 0)   # unsupported window size
+    e.close()
