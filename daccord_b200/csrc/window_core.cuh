@@ -31,6 +31,7 @@
 #ifdef DCU_EMU
 #define DCU_FN static inline
 #define DCU_BIG static
+#define DCU_NOINL static inline
 #define DCU_CTOR
 #define DCU_NL 1
 namespace dcu {
@@ -46,11 +47,13 @@ static inline uint32_t red_max_u32(uint32_t v) { return v; }
 static inline uint32_t red_sum_u32(uint32_t v) { return v; }
 static inline uint32_t red_min_u32(uint32_t v) { return v; }
 static inline void red_argmax_d(double&, int&) {}
+static inline uint32_t scan_incl(uint32_t v, int) { return v; }
 template <class T> static inline T ldg(const T* p) { return *p; }
 }
 #else
 #define DCU_FN __device__ __forceinline__
 #define DCU_BIG __device__ __noinline__
+#define DCU_NOINL __device__ __noinline__
 #define DCU_CTOR __device__
 #define DCU_NL 32
 namespace dcu {
@@ -75,6 +78,11 @@ __device__ __forceinline__ void red_argmax_d(double& v, int& i) {
   }
 }
 template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t scan_incl(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+  return v;
+}
 }
 #endif
 
@@ -99,7 +107,7 @@ struct Params {
   unsigned long long eminrate;
 };
 // capacities of one warp's workspace (two tiers: small for the common case, large for the rest)
-struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, SL, SF, RL, RP, FP, SI, BL; };
+struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, STP, SL, SF, RL, RLP, RP, FP, SI, BL, KW; };
 
 struct Slice { uint32_t gpos; uint16_t len; uint16_t flags; };
 struct Window { uint32_t slice_begin; uint16_t slice_cnt; uint16_t reserved; uint32_t aread; uint32_t astart; };
@@ -116,9 +124,13 @@ struct WS {
   uint32_t* ex_kmer; uint8_t *ex_pos, *ex_rpos;
   uint32_t* ll_kmer; uint16_t* ll_cnt; uint32_t* fl_kmer; uint16_t* fl_cnt; uint16_t* fl_nid;
   uint16_t* slinks; uint16_t *rs_off, *rs_len;
-  uint16_t *ds_off, *ds_len, *ds_fO, *ds_fL, *ds_cO, *ds_cL, *dt_off, *dt_len;
-  uint8_t* sf_p; double *sf_w, *sf_wf, *sf_wl;      // forward stretch objects
-  uint8_t* sc_p; double *sc_w, *sc_wf, *sc_wl;      // reverse stretch objects
+  uint16_t *ds_off, *ds_len, *ds_fO, *ds_cO, *dt_off, *dt_len, *du_off, *du_len, *ds_rlO, *ds_rlN;
+  uint8_t *ds_fB, *ds_fN, *ds_cB, *ds_cN;           // slot range of a stretch: positions [B, B+N)
+  double *sf_w, *sf_wf, *sf_wl;                      // forward stretch objects, slot = ds_fO[s] + (p - ds_fB[s]); w < 0: infeasible
+  double *sc_w, *sc_wf, *sc_wl;                      // reverse stretch objects
+  uint8_t *n_pf, *n_pt, *n_cpf, *n_cpt; uint32_t *n_kwo, *n_ckwo; double *kwF, *kwR;   // dense per-node position weights
+  uint16_t* n_dsf; uint8_t* n_dsn;                   // node -> derived stretches starting there
+  unsigned long long* skey;
   uint32_t* rl;
   double* rp_w; uint32_t* rp_parent; uint32_t* rp_front; uint16_t *rp_stretch, *rp_pos, *rp_len, *rp_baselen;
   double* rq_w; uint32_t* rq_id;                    // RPST heap
@@ -136,7 +148,7 @@ struct WS {
 };
 
 // byte layout of a workspace slab, computed once on the host for a Caps
-struct Layout { uint32_t off[96]; uint32_t bytes; };
+struct Layout { uint32_t off[128]; uint32_t bytes; };
 
 #define DCU_WS_FIELDS(X)                                                                                  \
   X(bases, uint8_t, c.B) X(soff, uint16_t, c.S + 1) X(lenhist, uint16_t, 256)                              \
@@ -150,11 +162,16 @@ struct Layout { uint32_t off[96]; uint32_t bytes; };
   X(ll_kmer, uint32_t, c.S) X(ll_cnt, uint16_t, c.S) X(fl_kmer, uint32_t, c.S) X(fl_cnt, uint16_t, c.S)    \
   X(fl_nid, uint16_t, c.S)                                                                                 \
   X(slinks, uint16_t, c.SL) X(rs_off, uint16_t, c.ST) X(rs_len, uint16_t, c.ST)                            \
-  X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint16_t, c.ST) X(ds_fL, uint16_t, c.ST)    \
-  X(ds_cO, uint16_t, c.ST) X(ds_cL, uint16_t, c.ST) X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST)    \
-  X(sf_p, uint8_t, c.SF) X(sf_w, double, c.SF) X(sf_wf, double, c.SF) X(sf_wl, double, c.SF)               \
-  X(sc_p, uint8_t, c.SF) X(sc_w, double, c.SF) X(sc_wf, double, c.SF) X(sc_wl, double, c.SF)               \
-  X(rl, uint32_t, c.RL)                                                                                    \
+  X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint16_t, c.ST) X(ds_cO, uint16_t, c.ST)    \
+  X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST) X(du_off, uint16_t, c.ST) X(du_len, uint16_t, c.ST)  \
+  X(ds_rlO, uint16_t, c.ST) X(ds_rlN, uint16_t, c.ST)                                                      \
+  X(ds_fB, uint8_t, c.ST) X(ds_fN, uint8_t, c.ST) X(ds_cB, uint8_t, c.ST) X(ds_cN, uint8_t, c.ST)          \
+  X(sf_w, double, c.SF) X(sf_wf, double, c.SF) X(sf_wl, double, c.SF)                                      \
+  X(sc_w, double, c.SF) X(sc_wf, double, c.SF) X(sc_wl, double, c.SF)                                      \
+  X(n_pf, uint8_t, c.NN) X(n_pt, uint8_t, c.NN) X(n_cpf, uint8_t, c.NN) X(n_cpt, uint8_t, c.NN)            \
+  X(n_kwo, uint32_t, c.NN) X(n_ckwo, uint32_t, c.NN) X(kwF, double, c.KW) X(kwR, double, c.KW)             \
+  X(n_dsf, uint16_t, c.NN) X(n_dsn, uint8_t, c.NN) X(skey, unsigned long long, c.STP)                      \
+  X(rl, uint32_t, c.RLP)                                                                                   \
   X(rp_w, double, c.RP) X(rp_parent, uint32_t, c.RP) X(rp_front, uint32_t, c.RP)                           \
   X(rp_stretch, uint16_t, c.RP) X(rp_pos, uint16_t, c.RP) X(rp_len, uint16_t, c.RP)                        \
   X(rp_baselen, uint16_t, c.RP) X(rq_w, double, c.RP) X(rq_id, uint32_t, c.RP) X(arp, uint32_t, c.RP)      \
@@ -199,13 +216,13 @@ struct Ctx {
   int MAo, nbases;
   int k; uint32_t kmask; int kidx;
   int nn, ni, nex, nlast, nfirst;
-  int nrs, slO, nds, nsf, nsc, nrl;
+  int nrs, slO, nds, nrl, kwtot;
   int overflow;
 };
 
 // ------------------------------------------------------------------ small helpers
 DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - c.cap.LOGH); }
-DCU_FN int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
+DCU_NOINL int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
   uint32_t h = hslot(c, v), mask = (uint32_t)c.cap.H - 1;
   for (;;) {
     uint32_t key = c.ws.hkey[h];
@@ -228,23 +245,23 @@ DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
 }
 
 // bounded binary heap on (weight,id) pairs; convention C2 of oracle/README.md.  MAXH: top = largest weight.
-template <bool MAXH> DCU_FN bool hless(double a, double b) { return MAXH ? (a > b) : (a < b); }
-template <bool MAXH> DCU_FN void heap_push(double* hw, uint32_t* hi, int& n, double w, uint32_t id) {
+DCU_FN bool hless(bool maxh, double a, double b) { return maxh ? (a > b) : (a < b); }
+DCU_NOINL void heap_push(bool MAXH, double* hw, uint32_t* hi, int& n, double w, uint32_t id) {
   int i = n++;
   hw[i] = w; hi[i] = id;
   while (i > 0) {
     int p = (i - 1) >> 1;
-    if (hless<MAXH>(hw[i], hw[p])) { double tw = hw[i]; hw[i] = hw[p]; hw[p] = tw; uint32_t ti = hi[i]; hi[i] = hi[p]; hi[p] = ti; i = p; } else break;
+    if (hless(MAXH, hw[i], hw[p])) { double tw = hw[i]; hw[i] = hw[p]; hw[p] = tw; uint32_t ti = hi[i]; hi[i] = hi[p]; hi[p] = ti; i = p; } else break;
   }
 }
-template <bool MAXH> DCU_FN void heap_pop(double* hw, uint32_t* hi, int& n) {
+DCU_NOINL void heap_pop(bool MAXH, double* hw, uint32_t* hi, int& n) {
   --n; hw[0] = hw[n]; hi[0] = hi[n];
   int p = 0;
   for (;;) {
     int l = 2 * p + 1, r = l + 1;
     if (l >= n) break;
-    int m = (r < n && hless<MAXH>(hw[r], hw[l])) ? r : l;
-    if (hless<MAXH>(hw[m], hw[p])) { double tw = hw[m]; hw[m] = hw[p]; hw[p] = tw; uint32_t ti = hi[m]; hi[m] = hi[p]; hi[p] = ti; p = m; } else break;
+    int m = (r < n && hless(MAXH, hw[r], hw[l])) ? r : l;
+    if (hless(MAXH, hw[m], hw[p])) { double tw = hw[m]; hw[m] = hw[p]; hw[p] = tw; uint32_t ti = hi[m]; hi[m] = hi[p]; hi[p] = ti; p = m; } else break;
   }
 }
 
@@ -496,6 +513,45 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
   return true;
 }
 
+// ------------------------------------------------------------------ dense per-node position weights
+// computeFeasibleKmerPositions (:3117-3174): weight of every node at every true position of its support
+// range, forward (PF) and reverse (RPF); a value below 1e-3 means "not feasible".  Lanes over (node,position).
+DCU_BIG void node_weights(Ctx& c, int lane) {
+  const WS& w = c.ws;
+  uint32_t run0 = 0, run1 = 0;
+  for (int base = 0; base < c.nn; base += DCU_NL) {
+    int n = base + lane;
+    uint32_t a = 0, b = 0;
+    if (n < c.nn) {
+      int pf = sup_lo(c, w.n_plow[n]), pt = sup_hi(c, w.n_phigh[n]);
+      int cf = sup_lo(c, w.n_cplow[n]), ct = sup_hi(c, w.n_cphigh[n]);
+      if (pt < pf) pt = pf;
+      if (ct < cf) ct = cf;
+      w.n_pf[n] = (uint8_t)pf; w.n_pt[n] = (uint8_t)pt; w.n_cpf[n] = (uint8_t)cf; w.n_cpt[n] = (uint8_t)ct;
+      a = (uint32_t)(pt - pf); b = (uint32_t)(ct - cf);
+    }
+    uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
+    if (n < c.nn) { w.n_kwo[n] = run0 + ia - a; w.n_ckwo[n] = run1 + ib - b; }
+    run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
+  }
+  wsync();
+  if ((int)run0 > c.cap.KW || (int)run1 > c.cap.KW) { c.overflow = 18; return; }
+  for (int dir = 0; dir < 2; ++dir) {
+    const uint32_t* off = dir ? w.n_ckwo : w.n_kwo;
+    const uint8_t* lo = dir ? w.n_cpf : w.n_pf;
+    double* out = dir ? w.kwR : w.kwF;
+    uint32_t tot = dir ? run1 : run0;
+    for (uint32_t q = (uint32_t)lane; q < tot; q += DCU_NL) {
+      int a = 0, b = c.nn;                 // last node with off[n] <= q
+      while (b - a > 1) { int mid = (a + b) >> 1; if (off[mid] <= q) a = mid; else b = mid; }
+      out[q] = kweight(c, a, (int)lo[a] + (int)(q - off[a]), dir == 1);
+    }
+  }
+  wsync();
+}
+DCU_FN double kw_fwd(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_pf[n] && p < w.n_pt[n]) ? w.kwF[w.n_kwo[n] + (uint32_t)(p - w.n_pf[n])] : 0.0; }
+DCU_FN double kw_rev(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_cpf[n] && p < w.n_cpt[n]) ? w.kwR[w.n_ckwo[n] + (uint32_t)(p - w.n_cpf[n])] : 0.0; }
+
 // ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
 DCU_BIG void gap_fill(Ctx& c, int lane) {
   const WS& w = c.ws;
@@ -504,21 +560,17 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   wsync();
   for (int a = lane; a < c.nn; a += DCU_NL) {
     uint32_t v = w.n_kmer[a];
-    int pfa = sup_lo(c, w.n_plow[a]), pta = sup_hi(c, w.n_phigh[a]);
     for (uint32_t x = 0; x < 16; ++x) {
       uint32_t nv = ((v << 4) & c.kmask) | x;
       int b = lookup(c, nv);
       if (b == NID_NONE) continue;
       uint32_t cv = ((v << 2) & c.kmask) | (nv >> 2);
       if (lookup(c, cv) != NID_NONE) continue;
-      int pfb = sup_lo(c, w.n_plow[b]), ptb = sup_hi(c, w.n_phigh[b]);
       double mweight = DBL_MIN; int mp = 0;
-      for (int p = pfa; p < pta; ++p) {
-        int q = p + 2;
-        if (q < pfb || q >= ptb) continue;
-        double wa = kweight(c, a, p, false);
+      for (int p = w.n_pf[a]; p < w.n_pt[a]; ++p) {
+        double wa = kw_fwd(c, a, p);
         if (!(wa >= 1e-3)) continue;
-        double wb = kweight(c, b, q, false);
+        double wb = kw_fwd(c, b, p + 2);
         if (!(wb >= 1e-3)) continue;
         double lo = wa < wb ? wa : wb, hi = wa < wb ? wb : wa;
         double weight = lo + hi;
@@ -594,156 +646,209 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
   wsync();
 }
 
-// splitStretches(first), splitStretches(last), stretchesUnique (:2772-2841, :3087-3114) on views
-DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
-  const WS& w = c.ws;
-  if (lane == 0) {
-    int n = c.nrs; bool ovf = false;
-    for (int i = 0; i < n; ++i) { w.ds_off[i] = w.rs_off[i]; w.ds_len[i] = w.rs_len[i]; }
-    for (int pass = 0; pass < 2 && !ovf; ++pass) {
-      int v = pass == 0 ? F : L;
-      int n0 = n, o = 0, na = 0;
-      // pieces are appended after the surviving originals (the reference appends, then removes)
-      for (int z = 0; z < n0; ++z) {
-        int off = w.ds_off[z], len = w.ds_len[z], split = -1;
-        for (int i = 1; i + 1 < len; ++i) if (w.slinks[off + i] == v) { split = i; break; }
-        if (split < 0) { w.ds_off[o] = (uint16_t)off; w.ds_len[o] = (uint16_t)len; ++o; }
-        else {
-          if (na + 2 > c.cap.ST) { ovf = true; break; }
-          w.dt_off[na] = (uint16_t)off; w.dt_len[na] = (uint16_t)(split + 1); ++na;
-          w.dt_off[na] = (uint16_t)(off + split); w.dt_len[na] = (uint16_t)(len - split); ++na;
+// ascending bitonic sort of P (power of two) 64-bit keys, lanes strided over compare-exchange pairs
+DCU_BIG void warp_sort_u64(unsigned long long* a, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += DCU_NL) {
+        int x = i ^ j;
+        if (x > i) {
+          unsigned long long u = a[i], v = a[x];
+          bool up = ((i & k) == 0);
+          if ((u > v) == up) { a[i] = v; a[x] = u; }
         }
       }
-      if (ovf || o + na > c.cap.ST) { ovf = true; break; }
-      for (int i = 0; i < na; ++i) { w.ds_off[o + i] = w.dt_off[i]; w.ds_len[o + i] = w.dt_len[i]; }
-      n = o + na;
+      wsync();
     }
-    // sort by (first kmer, ext sym, len desc, last kmer); then keep the first per (first, ext)
-    for (int a = 1; a < n && !ovf; ++a) {
-      int off = w.ds_off[a], len = w.ds_len[a];
-      uint64_t k1 = ((uint64_t)w.n_kmer[w.slinks[off]] << 2) | (w.n_kmer[w.slinks[off + 1]] & 3);
-      uint32_t lk = w.n_kmer[w.slinks[off + len - 1]];
-      int b = a;
-      while (b > 0) {
-        int poff = w.ds_off[b - 1], plen = w.ds_len[b - 1];
-        uint64_t pk1 = ((uint64_t)w.n_kmer[w.slinks[poff]] << 2) | (w.n_kmer[w.slinks[poff + 1]] & 3);
-        bool greater;    // is prev > cur ?
-        if (pk1 != k1) greater = pk1 > k1;
-        else if (plen != len) greater = plen < len;
-        else greater = w.n_kmer[w.slinks[poff + plen - 1]] > lk;
-        if (!greater) break;
-        w.ds_off[b] = (uint16_t)poff; w.ds_len[b] = (uint16_t)plen; --b;
+}
+DCU_BIG void warp_sort_u32(uint32_t* a, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += DCU_NL) {
+        int x = i ^ j;
+        if (x > i) {
+          uint32_t u = a[i], v = a[x];
+          bool up = ((i & k) == 0);
+          if ((u > v) == up) { a[i] = v; a[x] = u; }
+        }
       }
-      w.ds_off[b] = (uint16_t)off; w.ds_len[b] = (uint16_t)len;
+      wsync();
     }
-    int o = 0;
-    for (int i = 0; i < n; ++i) {
-      if (o > 0) {
-        int poff = w.ds_off[o - 1], off = w.ds_off[i];
-        if (w.slinks[poff] == w.slinks[off] && w.slinks[poff + 1] == w.slinks[off + 1]) continue;
-      }
-      w.ds_off[o] = w.ds_off[i]; w.ds_len[o] = w.ds_len[i]; ++o;
+}
+
+// one splitStretches pass (:2772-2841) on views: in (n views) -> out; every view with an interior occurrence of
+// node v becomes two views.  Returns the new count (order is irrelevant, the result is sorted afterwards).
+DCU_BIG int split_pass(Ctx& c, const uint16_t* ioff, const uint16_t* ilen, int n, uint16_t* ooff, uint16_t* olen, int v, int lane) {
+  const WS& w = c.ws;
+  int base = 0;
+  for (int b0 = 0; b0 < n; b0 += DCU_NL) {
+    int z = b0 + lane;
+    int off = 0, len = 0, split = -1;
+    if (z < n) {
+      off = ioff[z]; len = ilen[z];
+      for (int i = 1; i + 1 < len; ++i) if (w.slinks[off + i] == v) { split = i; break; }
     }
-    c.nds = o;
-    if (ovf) c.overflow = 8;
+    uint32_t act = ballot(z < n), sp = ballot(split >= 0);
+    int idx = base + popc(act & lanemask_lt(lane)) + popc(sp & lanemask_lt(lane));
+    if (z < n && idx + 2 <= c.cap.ST) {
+      if (split < 0) { ooff[idx] = (uint16_t)off; olen[idx] = (uint16_t)len; }
+      else { ooff[idx] = (uint16_t)off; olen[idx] = (uint16_t)(split + 1); ooff[idx + 1] = (uint16_t)(off + split); olen[idx + 1] = (uint16_t)(len - split); }
+    }
+    base += popc(act) + popc(sp);
   }
-  c.nds = bcast(c.nds, 0); c.overflow = bcast(c.overflow, 0);
+  wsync();
+  return base;
+}
+// splitStretches(first), splitStretches(last), stretchesUnique (:3087-3114): sort by (first, ext, len desc) and keep
+// the first view per (first, ext); equal (first, ext, len) implies identical content, so `last` never decides.
+DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
+  const WS& w = c.ws;
+  int n = split_pass(c, w.rs_off, w.rs_len, c.nrs, w.dt_off, w.dt_len, F, lane);
+  if (n > c.cap.ST) { c.overflow = 8; return; }
+  n = split_pass(c, w.dt_off, w.dt_len, n, w.du_off, w.du_len, L, lane);
+  if (n > c.cap.ST) { c.overflow = 8; return; }
+  int P = 32; while (P < n) P <<= 1;
+  for (int i = lane; i < P; i += DCU_NL) {
+    unsigned long long key = ~0ull;
+    if (i < n) {
+      int off = w.du_off[i], len = w.du_len[i];
+      unsigned long long fe = ((unsigned long long)w.n_kmer[w.slinks[off]] << 2) | (w.n_kmer[w.slinks[off + 1]] & 3);
+      key = (fe << 32) | ((unsigned long long)(0xFFFF - len) << 16) | (unsigned long long)i;
+    }
+    w.skey[i] = key;
+  }
+  wsync();
+  warp_sort_u64(w.skey, P, lane);
+  for (int i = lane; i < c.nn; i += DCU_NL) { w.n_dsf[i] = NID_NONE; w.n_dsn[i] = 0; }
+  wsync();
+  int o = 0;
+  for (int b0 = 0; b0 < n; b0 += DCU_NL) {
+    int i = b0 + lane;
+    bool keep = false; unsigned long long key = 0;
+    if (i < n) { key = w.skey[i]; keep = (i == 0) || ((w.skey[i - 1] >> 32) != (key >> 32)); }
+    uint32_t b = ballot(keep);
+    int idx = o + popc(b & lanemask_lt(lane));
+    if (keep) {
+      int src = (int)(key & 0xFFFF);
+      w.ds_off[idx] = w.du_off[src]; w.ds_len[idx] = w.du_len[src];
+      int fn = w.slinks[w.du_off[src]];
+      bool firstOfNode = (i == 0) || ((w.skey[i - 1] >> 34) != (key >> 34));
+      if (firstOfNode) w.n_dsf[fn] = (uint16_t)idx;
+    }
+    o += popc(b);
+  }
+  c.nds = o;
+  wsync();
+  for (int s = lane; s < o; s += DCU_NL) {          // count per first node (<= 4, distinct ext symbols)
+    int fn = w.slinks[w.ds_off[s]];
+    if (w.n_dsf[fn] == s) { int cnt = 1; while (s + cnt < o && w.slinks[w.ds_off[s + cnt]] == fn) ++cnt; w.n_dsn[fn] = (uint8_t)cnt; }
+  }
   wsync();
 }
 DCU_FN int ds_first(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s]]; }
 DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s] + c.ws.ds_len[s] - 1]; }
 
-// computeFeasibleStretchPositions (:3176-3330), weights evaluated on demand, lanes over positions
+// computeFeasibleStretchPositions (:3176-3330).  Every stretch owns one slot per position of its anchor's
+// support range (forward: first k-mer, object p = start position; reverse: last k-mer, object p = its reverse
+// position); slot weight < 0 marks "not feasible".  Lanes over all slots of all stretches.
 DCU_BIG void stretch_positions(Ctx& c, int lane) {
   const WS& w = c.ws;
-  int nsf = 0, nsc = 0;
-  for (int s = 0; s < c.nds; ++s) {
-    int off = w.ds_off[s], L = w.ds_len[s];
-    for (int dir = 0; dir < 2; ++dir) {
-      int anchor = dir == 0 ? w.slinks[off] : w.slinks[off + L - 1];
-      int r0 = dir == 0 ? sup_lo(c, w.n_plow[anchor]) : sup_lo(c, w.n_cplow[anchor]);
-      int r1 = dir == 0 ? sup_hi(c, w.n_phigh[anchor]) : sup_hi(c, w.n_cphigh[anchor]);
-      int startO = dir == 0 ? nsf : nsc, cntO = 0;
-      for (int base = r0; base < r1; base += DCU_NL) {
-        int s0 = base + lane;
-        bool ok = s0 < r1;
-        double sum = 0.0, wfirst = 0.0, wlast = 0.0;
-        if (ok) {
-          for (int jj = 0; jj < L; ++jj) {
-            int nj = dir == 0 ? w.slinks[off + jj] : w.slinks[off + L - 1 - jj];
-            int p = s0 + jj;
-            int lo = dir == 0 ? sup_lo(c, w.n_plow[nj]) : sup_lo(c, w.n_cplow[nj]);
-            int hi = dir == 0 ? sup_hi(c, w.n_phigh[nj]) : sup_hi(c, w.n_cphigh[nj]);
-            if (p < lo || p >= hi) { ok = false; break; }
-            double wt = kweight(c, nj, p, dir == 1);
-            if (!(wt >= 1e-3)) { ok = false; break; }
-            sum += wt;
-            if (jj == 0) wfirst = wt;
-            wlast = wt;
-          }
-        }
-        uint32_t b = ballot(ok);
-        int idx = startO + cntO + popc(b & lanemask_lt(lane));
-        if (ok && idx < c.cap.SF) {
-          if (dir == 0) { w.sf_p[idx] = (uint8_t)s0; w.sf_w[idx] = sum; w.sf_wf[idx] = wfirst; w.sf_wl[idx] = wlast; }
-          else { w.sc_p[idx] = (uint8_t)s0; w.sc_w[idx] = sum; w.sc_wf[idx] = wfirst; w.sc_wl[idx] = wlast; }
-        }
-        cntO += popc(b);
+  uint32_t run0 = 0, run1 = 0;
+  for (int base = 0; base < c.nds; base += DCU_NL) {
+    int s = base + lane;
+    uint32_t a = 0, b = 0;
+    if (s < c.nds) {
+      int n0 = ds_first(c, s), n1 = ds_last(c, s);
+      a = (uint32_t)(w.n_pt[n0] - w.n_pf[n0]); b = (uint32_t)(w.n_cpt[n1] - w.n_cpf[n1]);
+      w.ds_fB[s] = w.n_pf[n0]; w.ds_fN[s] = (uint8_t)a; w.ds_cB[s] = w.n_cpf[n1]; w.ds_cN[s] = (uint8_t)b;
+    }
+    uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
+    if (s < c.nds) { uint32_t oa = run0 + ia - a, ob = run1 + ib - b; w.ds_fO[s] = (uint16_t)(oa > 65535u ? 65535u : oa); w.ds_cO[s] = (uint16_t)(ob > 65535u ? 65535u : ob); }
+    run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
+  }
+  wsync();
+  if ((int)run0 > c.cap.SF || (int)run1 > c.cap.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
+  for (int dir = 0; dir < 2; ++dir) {
+    const uint16_t* so = dir ? w.ds_cO : w.ds_fO;
+    const uint8_t* sb = dir ? w.ds_cB : w.ds_fB;
+    double* ow = dir ? w.sc_w : w.sf_w; double* owf = dir ? w.sc_wf : w.sf_wf; double* owl = dir ? w.sc_wl : w.sf_wl;
+    uint32_t tot = dir ? run1 : run0;
+    for (uint32_t q = (uint32_t)lane; q < tot; q += DCU_NL) {
+      int a = 0, b = c.nds;                // last stretch with so[s] <= q
+      while (b - a > 1) { int mid = (a + b) >> 1; if (so[mid] <= q) a = mid; else b = mid; }
+      int off = w.ds_off[a], L = w.ds_len[a];
+      int p0 = (int)sb[a] + (int)(q - so[a]);
+      double sum = 0.0, wfirst = 0.0, wlast = 0.0; bool ok = true;
+      for (int jj = 0; jj < L; ++jj) {
+        int nj = dir == 0 ? w.slinks[off + jj] : w.slinks[off + L - 1 - jj];
+        double wt = dir == 0 ? kw_fwd(c, nj, p0 + jj) : kw_rev(c, nj, p0 + jj);
+        if (!(wt >= 1e-3)) { ok = false; break; }
+        sum += wt;
+        if (jj == 0) wfirst = wt;
+        wlast = wt;
       }
-#ifdef DCU_EMU_DEBUG
-      if (startO + cntO > c.cap.SF) fprintf(stderr, "SF overflow: s=%d/%d L=%d dir=%d r0=%d r1=%d cnt=%d start=%d nn=%d\n", s, c.nds, L, dir, r0, r1, cntO, startO, c.nn);
-#endif
-      if (startO + cntO > c.cap.SF || startO + cntO > 65535) { c.overflow = 9; wsync(); return; }
-      if (lane == 0) {
-        if (dir == 0) { w.ds_fO[s] = (uint16_t)startO; w.ds_fL[s] = (uint16_t)cntO; } else { w.ds_cO[s] = (uint16_t)startO; w.ds_cL[s] = (uint16_t)cntO; }
-      }
-      if (dir == 0) nsf += cntO; else nsc += cntO;
+      ow[q] = ok ? sum : -1.0; owf[q] = wfirst; owl[q] = wlast;
     }
   }
-  c.nsf = nsf; c.nsc = nsc;
   wsync();
 }
-DCU_FN int sfo_fwd(const Ctx& c, int s, int p) {     // getCachedStretchPositionWeight (:3906-3918)
-  const WS& w = c.ws; int o = w.ds_fO[s], n = w.ds_fL[s];
-  for (int i = 0; i < n; ++i) { int q = w.sf_p[o + i]; if (q == p) return o + i; if (q > p) break; }
-  return -1;
+DCU_NOINL int sfo_fwd(const Ctx& c, int s, int p) {     // getCachedStretchPositionWeight (:3906-3918)
+  const WS& w = c.ws; int d = p - (int)w.ds_fB[s];
+  if (d < 0 || d >= (int)w.ds_fN[s]) return -1;
+  int o = w.ds_fO[s] + d;
+  return w.sf_w[o] >= 0.0 ? o : -1;
 }
-DCU_FN int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchReversePositionWeight (:3920-3932)
-  const WS& w = c.ws; int o = w.ds_cO[s], n = w.ds_cL[s];
-  for (int i = 0; i < n; ++i) { int q = w.sc_p[o + i]; if (q == p) return o + i; if (q > p) break; }
-  return -1;
+DCU_NOINL int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchReversePositionWeight (:3920-3932)
+  const WS& w = c.ws; int d = p - (int)w.ds_cB[s];
+  if (d < 0 || d >= (int)w.ds_cN[s]) return -1;
+  int o = w.ds_cO[s] + d;
+  return w.sc_w[o] >= 0.0 ? o : -1;
 }
 
-// computeStretchLinks / getReverseStretchLinkWeight (:3388-3480); serial, output sorted by (to, from)
+// computeStretchLinks / getReverseStretchLinkWeight (:3388-3480): link A -> B (B.first == A.last) kept iff
+// max over common reverse positions of w_B + (w_A - wf_A) >= 0.1; stored as (B,A), sorted; lanes over A
 DCU_BIG void stretch_links(Ctx& c, int lane) {
   const WS& w = c.ws;
-  if (lane == 0) {
-    int nrl = 0; bool ovf = false;
-    for (int B = 0; B < c.nds && !ovf; ++B) {
-      int bfirst = ds_first(c, B), shift = w.ds_len[B] - 1;
-      for (int A = 0; A < c.nds; ++A) {
-        if (ds_last(c, A) != bfirst) continue;
-        double weight = 0.0;
-        for (int ib = 0; ib < w.ds_cL[B]; ++ib) {
-          int ob = w.ds_cO[B] + ib, tp = w.sc_p[ob] + shift;
-          for (int ia = 0; ia < w.ds_cL[A]; ++ia) {
-            int oa = w.ds_cO[A] + ia;
-            if (w.sc_p[oa] == tp) { double lw = w.sc_w[ob] + (w.sc_w[oa] - w.sc_wf[oa]); weight = lw > weight ? lw : weight; }
-          }
-        }
-        if (weight >= 1e-1) { if (nrl >= c.cap.RL) { ovf = true; break; } w.rl[nrl++] = ((uint32_t)B << 16) | (uint32_t)A; }
+  uint32_t* cnt = &w.n_fill[0];
+  if (lane == 0) *cnt = 0;
+  wsync();
+  for (int A = lane; A < c.nds; A += DCU_NL) {
+    int ln = ds_last(c, A);
+    int b0 = w.n_dsf[ln], bn = w.n_dsn[ln];
+    if (b0 == NID_NONE) continue;
+    for (int B = b0; B < b0 + bn; ++B) {
+      int shift = w.ds_len[B] - 1;
+      double weight = 0.0;
+      int cb = w.ds_cB[B], cn = w.ds_cN[B], co = w.ds_cO[B];
+      for (int d = 0; d < cn; ++d) {
+        double wb = w.sc_w[co + d];
+        if (!(wb >= 0.0)) continue;
+        int oa = sfo_rev(c, A, cb + d + shift);
+        if (oa >= 0) { double lw = wb + (w.sc_w[oa] - w.sc_wf[oa]); weight = lw > weight ? lw : weight; }
       }
+      if (weight >= 1e-1) { uint32_t t = a_add(cnt, 1); if ((int)t < c.cap.RL) w.rl[t] = ((uint32_t)B << 16) | (uint32_t)A; }
     }
-    c.nrl = nrl;
-    if (ovf) c.overflow = 10;
   }
-  c.nrl = bcast(c.nrl, 0); c.overflow = bcast(c.overflow, 0);
+  wsync();
+  int nrl = (int)bcast(*cnt, 0);
+  wsync();
+  if (nrl > c.cap.RL) { c.overflow = 10; return; }
+  c.nrl = nrl;
+  int P = 32; while (P < nrl) P <<= 1;
+  for (int i = nrl + lane; i < P; i += DCU_NL) w.rl[i] = 0xFFFFFFFFu;
+  for (int s = lane; s < c.nds; s += DCU_NL) { w.ds_rlO[s] = 0; w.ds_rlN[s] = 0; }
+  wsync();
+  warp_sort_u32(w.rl, P, lane);
+  for (int t = lane; t < nrl; t += DCU_NL) {
+    int B = (int)(w.rl[t] >> 16);
+    if (t == 0 || (int)(w.rl[t - 1] >> 16) != B) { int e = t + 1; while (e < nrl && (int)(w.rl[e] >> 16) == B) ++e; w.ds_rlO[B] = (uint16_t)t; w.ds_rlN[B] = (uint16_t)(e - t); }
+  }
   wsync();
 }
 
 // ------------------------------------------------------------------ Myers bit-vector edit distance
 // global unit-cost distance of pattern (<=64, Peq masks) against text t[0,n)
-DCU_FN int myers_dist(const unsigned long long* peq, int m, const uint8_t* t, int n) {
+DCU_NOINL int myers_dist(const unsigned long long* peq, int m, const uint8_t* t, int n) {
   if (m == 0) return n;
   unsigned long long pv = ~0ull, mv = 0, top = 1ull << (m - 1);
   int score = m;
@@ -771,7 +876,7 @@ DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool as
 // ------------------------------------------------------------------ traverse (:4496-5170)
 struct TravOut { int nacc; };
 
-DCU_FN int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front, int stretch, int pos, int len, int baselen) {
+DCU_NOINL int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front, int stretch, int pos, int len, int baselen) {
   const WS& w = c.ws;
   if (nrp >= c.cap.RP) { c.overflow = 11; return -1; }
   int id = nrp++;
@@ -787,10 +892,10 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
   for (int i = 0; i < c.cap.BL; ++i) w.arph_n[i] = 0;
   int seed = rp_new(c, nrp, 0.0, IDX_NONE, w.n_kmer[Lnode], NID_NONE, 0, 0, c.k);
   if (seed < 0) return;
-  heap_push<true>(w.rq_w, w.rq_id, nq, 0.0, (uint32_t)seed);
+  heap_push(true, w.rq_w, w.rq_id, nq, 0.0, (uint32_t)seed);
   while (nq > 0 && !c.overflow) {
     double wt = w.rq_w[0]; int id = (int)w.rq_id[0];
-    heap_pop<true>(w.rq_w, w.rq_id, nq);
+    heap_pop(true, w.rq_w, w.rq_id, nq);
     int bl = w.rp_baselen[id];
     if (bl >= c.cap.BL) continue;                       // longer than any admissible pairing, inert
     double* hw = w.arph_w + bl * HEAPK; int hn = w.arph_n[bl];
@@ -810,13 +915,12 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
           int nid = rp_new(c, nrp, w.sc_w[o], (uint32_t)id, w.n_kmer[ds_first(c, s)], s, rpos + L - 1, 1, L + c.k - 1);
           if (nid < 0) return;
           if (nq >= c.cap.RP) { c.overflow = 12; return; }
-          heap_push<true>(w.rq_w, w.rq_id, nq, w.sc_w[o], (uint32_t)nid);
+          heap_push(true, w.rq_w, w.rq_id, nq, w.sc_w[o], (uint32_t)nid);
         }
       }
     } else if (bl < (lmax + 1) / 2) {
       int ls = w.rp_stretch[id];
-      for (int t = 0; t < c.nrl; ++t) {
-        if ((int)(w.rl[t] >> 16) != ls) continue;
+      for (int t = w.ds_rlO[ls], te = w.ds_rlO[ls] + w.ds_rlN[ls]; t < te; ++t) {
         int s = (int)(w.rl[t] & 0xFFFF);
         int o = sfo_rev(c, s, rpos);
         if (o >= 0 && w.sc_w[o] >= 0.5) {
@@ -825,7 +929,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
           int nid = rp_new(c, nrp, nw, (uint32_t)id, w.n_kmer[ds_first(c, s)], s, rpos + L - 1, rlen + 1, bl + L - 1);
           if (nid < 0) return;
           if (nq >= c.cap.RP) { c.overflow = 13; return; }
-          heap_push<true>(w.rq_w, w.rq_id, nq, nw, (uint32_t)nid);
+          heap_push(true, w.rq_w, w.rq_id, nq, nw, (uint32_t)nid);
         }
       }
     }
@@ -843,7 +947,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
   }
 }
 
-DCU_FN double pair_score(const Ctx& c, int P, int rpid) {      // getPairScore (:3482-3497)
+DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScore (:3482-3497)
   const WS& w = c.ws;
   int ls = w.fp_stretch[P];
   int lpos = w.fp_pos[P] - (w.ds_len[ls] - 1);
@@ -852,7 +956,7 @@ DCU_FN double pair_score(const Ctx& c, int P, int rpid) {      // getPairScore (
   return o >= 0 ? (s - w.sf_wl[o]) : s;
 }
 // best / next-best reverse path of an interval in (weight, sorted index) order (:3499-3534)
-DCU_FN int interval_next(const Ctx& c, int left, int right, int cur) {
+DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
   const WS& w = c.ws;
   int best = -1; double bw = 0;
   double cw = cur >= 0 ? w.rp_w[w.arp[cur]] : 0;
@@ -863,17 +967,17 @@ DCU_FN int interval_next(const Ctx& c, int left, int right, int cur) {
   }
   return best;
 }
-DCU_FN void apq_push(Ctx& c, int pid) {                        // :4843-4862, :4997-5017
+DCU_NOINL void apq_push(Ctx& c, int pid) {                        // :4843-4862, :4997-5017
   const WS& w = c.ws;
   int bl = w.fp_baselen[pid];
   if (bl >= c.cap.BL) return;                                  // longer than lmax: never pairs, never extends
   double* hw = w.apq_w + bl * HEAPK; uint32_t* hi = w.apq_id + bl * HEAPK; int n = w.apq_n[bl];
   double wt = w.fp_w[pid];
-  if (n == HEAPK) { if (wt > hw[0]) { heap_pop<false>(hw, hi, n); heap_push<false>(hw, hi, n, wt, (uint32_t)pid); } }
-  else heap_push<false>(hw, hi, n, wt, (uint32_t)pid);
+  if (n == HEAPK) { if (wt > hw[0]) { heap_pop(false, hw, hi, n); heap_push(false, hw, hi, n, wt, (uint32_t)pid); } }
+  else heap_push(false, hw, hi, n, wt, (uint32_t)pid);
   w.apq_n[bl] = (uint8_t)n;
 }
-DCU_FN int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath (:3989-4056); P == -1 -> empty path
+DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath (:3989-4056); P == -1 -> empty path
   const WS& w = c.ws;
   int ppos = P < 0 ? 0 : w.fp_pos[P], plen = P < 0 ? 0 : w.fp_len[P];
   int o = sfo_fwd(c, s, ppos);
@@ -912,12 +1016,13 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
   int nfp = 0, nsi = 0, nsq = 0;
   const int K = c.k;
   for (int i = 0; i < c.cap.BL; ++i) w.apq_n[i] = 0;
-  for (int s = 0; s < c.nds; ++s) if (ds_first(c, s) == Fnode) { int id = fp_extend(c, nfp, -1, s); if (id < 0) return; apq_push(c, id); }
+  if (w.n_dsf[Fnode] != NID_NONE)
+    for (int s = w.n_dsf[Fnode], se = s + w.n_dsn[Fnode]; s < se; ++s) { int id = fp_extend(c, nfp, -1, s); if (id < 0) return; apq_push(c, id); }
   for (int zz = 0; zz < c.cap.BL && !c.overflow; ++zz) {
     while (w.apq_n[zz] > 0) {
       double* hw = w.apq_w + zz * HEAPK; uint32_t* hi = w.apq_id + zz * HEAPK; int n = w.apq_n[zz];
       int P = (int)hi[0];
-      heap_pop<false>(hw, hi, n); w.apq_n[zz] = (uint8_t)n;
+      heap_pop(false, hw, hi, n); w.apq_n[zz] = (uint8_t)n;
       int candlen = w.fp_pos[P] + K;
       int pls = w.fp_stretch[P];
       int plast = ds_last(c, pls); uint32_t plk = w.n_kmer[plast];
@@ -934,12 +1039,11 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
         int rec = nsi++;
         w.si_left[rec] = (uint16_t)left; w.si_right[rec] = (uint16_t)right; w.si_cur[rec] = (uint16_t)cur; w.si_path[rec] = (uint32_t)P;
         w.si_w[rec] = pair_score(c, P, (int)w.arp[cur]);
-        heap_push<true>(w.sq_w, w.sq_id, nsq, w.si_w[rec], (uint32_t)rec);
+        heap_push(true, w.sq_w, w.sq_id, nsq, w.si_w[rec], (uint32_t)rec);
       }
       int pbl = w.fp_baselen[P];
       if (pbl < K || (pbl - K) < ((lmax + 1) / 2)) {
-        for (int s = 0; s < c.nds; ++s) {
-          if (ds_first(c, s) != plast) continue;
+        for (int s = w.n_dsf[plast], se = (s == NID_NONE ? 0 : s + w.n_dsn[plast]); s < se; ++s) {
           int o = sfo_fwd(c, s, w.fp_pos[P]);
           double ew = o >= 0 ? w.sf_w[o] : 0.0;
           if (ew > 0.1) {
@@ -958,7 +1062,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
   int prevlen = -1;
   for (int nfull = 0; nsq > 0 && nfull < 16 && !c.overflow; ++nfull) {        // :5049-5092
     int rec = (int)w.sq_id[0]; double weight = w.sq_w[0];
-    heap_pop<true>(w.sq_w, w.sq_id, nsq);
+    heap_pop(true, w.sq_w, w.sq_id, nsq);
     int P = (int)w.si_path[rec], cur = w.si_cur[rec];
     int nxt = interval_next(c, w.si_left[rec], w.si_right[rec], cur);
     if (nxt >= 0) {
@@ -966,12 +1070,12 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
       int r2 = nsi++;
       w.si_left[r2] = w.si_left[rec]; w.si_right[r2] = w.si_right[rec]; w.si_cur[r2] = (uint16_t)nxt; w.si_path[r2] = (uint32_t)P;
       w.si_w[r2] = pair_score(c, P, (int)w.arp[nxt]);
-      heap_push<true>(w.sq_w, w.sq_id, nsq, w.si_w[r2], (uint32_t)r2);
+      heap_push(true, w.sq_w, w.sq_id, nsq, w.si_w[r2], (uint32_t)r2);
     }
     if (ncdh == CDH_N) {
       if (weight <= w.cdh_w[0]) continue;
       freeslots |= 1u << w.cdh_id[0];
-      heap_pop<false>(w.cdh_w, w.cdh_id, ncdh);
+      heap_pop(false, w.cdh_w, w.cdh_id, ncdh);
     }
     int len = decode_pair(c, P, (int)w.arp[cur], w.tmps);
     if (len < 0) { c.overflow = 17; return; }
@@ -981,7 +1085,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
     freeslots &= ~(1u << slot);
     for (int i = 0; i < len; ++i) { w.prevs[i] = w.tmps[i]; w.cand[slot * MAXCAND + i] = w.tmps[i]; }
     w.candlen[slot] = (uint8_t)len;
-    heap_push<false>(w.cdh_w, w.cdh_id, ncdh, weight, (uint32_t)slot);
+    heap_push(false, w.cdh_w, w.cdh_id, ncdh, weight, (uint32_t)slot);
   }
 }
 
@@ -1017,8 +1121,8 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
   int nacc = 0;
   if (lane == 0) {
     int nch = 0;
-    while (ncdh > 0) { double wt = w.cdh_w[0]; uint32_t id = w.cdh_id[0]; heap_pop<false>(w.cdh_w, w.cdh_id, ncdh); heap_push<true>(w.ch_w, w.ch_id, nch, wt, id); }
-    while (nch > 0) { w.acc_w[nacc] = w.ch_w[0]; w.acc_slot[nacc] = (uint8_t)w.ch_id[0]; ++nacc; heap_pop<true>(w.ch_w, w.ch_id, nch); }
+    while (ncdh > 0) { double wt = w.cdh_w[0]; uint32_t id = w.cdh_id[0]; heap_pop(false, w.cdh_w, w.cdh_id, ncdh); heap_push(true, w.ch_w, w.ch_id, nch, wt, id); }
+    while (nch > 0) { w.acc_w[nacc] = w.ch_w[0]; w.acc_slot[nacc] = (uint8_t)w.ch_id[0]; ++nacc; heap_pop(true, w.ch_w, w.ch_id, nch); }
   }
   nacc = bcast(nacc, 0);
   wsync();
@@ -1107,11 +1211,13 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
       int f = ff > 1 ? ff : 1;
       if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
       build_nodes(c, f, lane);
+      if (!c.overflow) node_weights(c, lane);
       if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
       if (ff == 0) {
         gap_fill(c, lane);
         if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
         build_nodes(c, 1, lane);                         // setupNodes over all prenodes (:2248)
+        if (!c.overflow) node_weights(c, lane);
         if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
       }
       build_edges(c, lane);
