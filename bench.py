@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""bench.py -- consensus windows/s of the B200 window-consensus engine on a synthetic 40x pile.
+
+One "step" = one pass of the hot path (the dcu_* C ABI) over all windows of this rank's shard of A-reads.
+  value  : windows/s with windows, slices and the packed read DB already resident in HBM (kernel launches only)
+  e2e    : the same through dcu_run with HOST buffers (H2D of descriptors + D2H of results inside the timed region)
+  --impl reference : the CPU oracle (restatement of gt1/daccord; the upstream binary cannot be built here) on all
+                     host threads over a bounded sample of the same windows.
+Multi-GPU (torchrun): rank r processes the reads of `-J r,N` (reference src/daccord.cpp:1156-1184) of a dataset
+N times larger (weak scaling); the packed DB is broadcast once over NCCL; no collective during compute.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+
+def j_shard(nreads, i, j):
+    """reference -J i,j arithmetic (src/daccord.cpp:1156-1184)"""
+    part = (nreads + j - 1) // j
+    lo = min(i * part, nreads)
+    return lo, min(lo + part, nreads)
+
+
+def algorithmic_bytes(win, sl, res):
+    """sum over attempted windows of  sum_j ceil(len_j/4) + 8*MAo + 16 + (clen + 16)"""
+    att = res["status"] != 0
+    sl_bytes = (sl["len"].astype(np.int64) + 3) // 4 + 8
+    cs = np.concatenate([[0], np.cumsum(sl_bytes)])
+    b = win["slice_begin"].astype(np.int64)
+    e = b + win["slice_cnt"].astype(np.int64)
+    per = cs[e] - cs[b] + 16 + res["clen"].astype(np.int64) + 16
+    return int(per[att].sum()), int(att.sum())
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.stop_flag, self.sm, self.reasons, self.smmax = gpu, False, [], set(), None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.sm.append(float(f[0])); self.smmax = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smmax, "reasons": sorted(self.reasons)}
+
+
+def build_workload(args, rank, world):
+    from daccord_b200.host import Dataset
+    genome = int(args.mb * 1e6 * world / args.coverage)
+    t0 = time.time()
+    ds = Dataset.simulate(genome, read_len=args.read_len, coverage=args.coverage, seed=args.seed)
+    lo, hi = j_shard(ds.nreads, rank, world)
+    t1 = time.time()
+    nthreads = max(1, (os.cpu_count() or 1) // world)
+    batch = ds.pile(lo, hi, w=args.w, a=args.a, nthreads=nthreads)
+    t2 = time.time()
+    info = {"reads_total": int(ds.nreads), "overlaps": int(ds.novl), "shard": [int(lo), int(hi)], "sim_s": round(t1 - t0, 2), "pile_s": round(t2 - t1, 2), "pile_threads": nthreads}
+    return ds, batch, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mb", type=float, default=50.0, help="sum of A-read lengths per GPU in Mb (BASELINE config 2: 50)")
+    ap.add_argument("--coverage", type=float, default=40.0)
+    ap.add_argument("--read-len", type=int, default=10000)
+    ap.add_argument("--w", type=int, default=40)
+    ap.add_argument("--a", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample-s", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "%.0f Mb synthetic 40x pile per GPU (10 kb reads, 15%% error, LAS-equivalent overlaps with tspace=100 trace points), -w%d -a%d -k8" % (args.mb, args.w, args.a)
+    base = {"metric": "consensus_windows_per_s", "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 + f64", "data": "synthetic"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from common import run_oracle, default_params
+        ds, batch, info = build_workload(args, 0, 1)
+        pi, pd, cor = ds.profile()
+        p = default_params(w=args.w, p_i=pi, p_d=pd, est_cor=cor)
+        packed = np.array(ds.packed(), copy=True)
+        win_all, sl = batch.win, batch.sl
+        threads = os.cpu_count() or 1
+        # bounded sample: probe, then size each step to ~cpu_sample_s / steps of CPU work
+        probe = min(len(win_all), 4000 * threads // 8 + 2000)
+        _, _, _, t = run_oracle(p, packed, win_all[:probe].copy(), sl, threads)
+        rate = probe / max(t, 1e-6)
+        n = int(min(len(win_all), max(2000, rate * args.cpu_sample_s / max(args.steps + args.warmup, 1))))
+        sample = win_all[:n].copy()
+        for _ in range(args.warmup):
+            run_oracle(p, packed, sample, sl, threads)
+        tt, att = 0.0, 0
+        for _ in range(args.steps):
+            res, _, _, t = run_oracle(p, packed, sample, sl, threads)
+            tt += t; att += int((res["status"] != 0).sum())
+        v = att / tt
+        out = dict(base, impl="reference", value=v, ms_per_step=1e3 * tt / args.steps, n_gpus=world,
+                   config={"workload": workload, "sample": "first %d windows of the shard per step" % n, "threads": threads},
+                   cpu_baseline={"value": v, "unit": "windows/s", "cores": threads, "kind": "port", "sample": "first %d windows x %d steps" % (n, args.steps)},
+                   e2e={"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import daccord_b200 as d
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ds, batch, info = build_workload(args, rank, world)
+    pi, pd, cor = ds.profile()
+    params = d.Params.default(w=args.w, p_i=pi, p_d=pd, est_cor=cor)
+    eng = d.Engine(params, local)
+    # packed read DB: one-time broadcast from rank 0 over NCCL (every rank needs the whole DB: B reads come from anywhere)
+    packed_h = np.array(ds.packed(), copy=True)
+    dbt = torch.empty(packed_h.size, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        dbt.copy_(torch.from_numpy(packed_h))
+    if dist is not None:
+        dist.broadcast(dbt, src=0)
+    torch.cuda.synchronize()
+    eng.set_reads_device(dbt.data_ptr(), dbt.numel())
+
+    # pinned host staging of the step's inputs / outputs (the e2e leg copies them every step)
+    win_p = torch.from_numpy(batch.win.view(np.uint8).copy()).pin_memory()
+    sl_p = torch.from_numpy(batch.sl.view(np.uint8).copy()).pin_memory()
+    win = win_p.numpy().view(d.WINDOW_DT); sl = sl_p.numpy().view(d.SLICE_DT)
+    nwin = len(win)
+    res_p = torch.empty(nwin * 16, dtype=torch.uint8).pin_memory(); cons_p = torch.empty(nwin * 64, dtype=torch.uint8).pin_memory(); ops_p = torch.empty(nwin * 128, dtype=torch.uint8).pin_memory()
+    out = (res_p.numpy().view(d.RESULT_DT), cons_p.numpy(), ops_p.numpy())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg
+    eng.upload(win, sl)
+    for _ in range(args.warmup):
+        eng.launch()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    kms, launches, hard = 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        kms += eng.launch()                 # CUDA-event time of the launch(es) on the engine's stream
+        st = eng.stats(); launches += st["launches"]; hard += st["hard_windows"]
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    res, cons, ops = eng.download(out)
+    att = int((res["status"] != 0).sum()); okw = int((res["status"] == 1).sum())
+    alg_bytes, _ = algorithmic_bytes(win, sl, res)
+    tsec = kms / 1e3
+    # ---- end-to-end leg through dcu_run (host buffers)
+    for _ in range(min(args.warmup, 1)):
+        eng.run(win, sl, out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.run(win, sl, out)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    fasta, nseq = batch.vote(*out)
+    corrected = sum(len(l) for l in fasta.split(b"\n") if l and not l.startswith(b">"))
+
+    vals = torch.tensor([tsec, e2e_wall, wall], dtype=torch.float64, device="cuda")
+    cnts = torch.tensor([att, nwin, okw, corrected, launches, hard, alg_bytes, win.nbytes + sl.nbytes, res_p.numel() + cons_p.numel() + ops_p.numel()], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX); dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
+    tsec, e2e_wall, wall = [float(x) for x in vals.tolist()]
+    att_t, nwin_t, ok_t, corr_t, launches_t, hard_t, alg_t, h2d_t, d2h_t = [float(x) for x in cnts.tolist()]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    ach = (alg_bytes * args.steps) / tsec / 1e9           # this rank's kernel: algorithmic GB/s
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj["dram_bytes_per_window"] * att
+    except Exception:
+        pass
+    value = att_t * args.steps / tsec
+    line = dict(base, value=value, ms_per_step=1e3 * tsec / args.steps,
+                config={"workload": workload, "windows_per_step": int(nwin_t), "attempted_per_step": int(att_t), "consensus_per_step": int(ok_t),
+                        "corrected_mbp_per_s": corr_t * args.steps / tsec / 1e6, "l2": "inputs %.0f MB per GPU, larger than L2 (126 MB)" % ((win.nbytes + sl.nbytes) / 1e6),
+                        "parallelism": "-J r,%d by A-read, no data-path collective" % world, "setup": info},
+                e2e={"value": att_t * args.steps / e2e_wall, "unit": "windows/s", "h2d_bytes_per_step": int(h2d_t), "d2h_bytes_per_step": int(d2h_t)},
+                gpu_launches=int(launches_t), hard_windows=int(hard_t),
+                roofline={"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                          "peak_source": peak_src, "bytes_per_window": alg_bytes / max(att, 1),
+                          "note": "integer / latency bound path (SURVEY 8d): the HBM fraction is reported as the contract asks, see DESIGN.md for the instruction-issue analysis"},
+                clocks=sampler.summary(), wall_s_timed=wall)
+    # CPU baseline: the oracle on a bounded sample of the same windows, all host threads (rank 0, N=1 only)
+    if world == 1 and args.cpu_sample_s > 0:
+        from common import run_oracle, default_params
+        p = default_params(w=args.w, p_i=pi, p_d=pd, est_cor=cor)
+        threads = os.cpu_count() or 1
+        probe = min(nwin, 2000 + 500 * threads)
+        r0, _, _, t = run_oracle(p, packed_h, batch.win[:probe].copy(), batch.sl, threads)
+        n = int(min(nwin, max(probe, probe / max(t, 1e-6) * args.cpu_sample_s)))
+        r1, c1, o1, t = run_oracle(p, packed_h, batch.win[:n].copy(), batch.sl, threads)
+        same = bool((r1 == res[:n]).all())
+        line["cpu_baseline"] = {"value": float((r1["status"] != 0).sum() / t), "unit": "windows/s", "cores": threads, "kind": "port",
+                                "sample": "first %d windows of the step, %.1f s" % (n, t), "gpu_results_identical_on_sample": same}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libdaccord_b200.so")
+HOST_LIB = os.path.join(BUILD, "libdaccord_host.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-fopenmp", "-shared"]
 
@@ -18,13 +19,18 @@ def _newer(out, deps):
 def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     csrc = os.path.join(HERE, "csrc")
-    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, "include", "daccord_b200.h")]
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if os.path.isfile(os.path.join(csrc, f))] + [os.path.join(ROOT, "include", "daccord_b200.h")]
     if force or _newer(LIB, deps):
         srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith(".cu")]
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs + ["-lcudart", "-lgomp"]
         env = dict(os.environ)
         env["PATH"] = "/usr/bin:" + env.get("PATH", "")      # system g++ (the /opt/gcc wrapper lacks libgomp.spec)
         subprocess.check_call(cmd, env=env)
+    host_src = os.path.join(csrc, "host", "hostlib.cpp")
+    host_deps = [os.path.join(csrc, "host", f) for f in os.listdir(os.path.join(csrc, "host"))] + [os.path.join(ROOT, "include", "daccord_b200.h")]
+    if force or _newer(HOST_LIB, host_deps):
+        subprocess.check_call(["/usr/bin/g++", "-O3", "-g", "-std=c++17", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
+                               "-o", HOST_LIB, host_src])
     return LIB
 
 

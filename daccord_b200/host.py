@@ -1,0 +1,114 @@
+"""ctypes view of the host tools library (synthetic data, LAS / Dazzler-DB I/O, window piling, pile vote)."""
+import ctypes as C
+import os
+import numpy as np
+from . import SLICE_DT, WINDOW_DT, RESULT_DT, CONS_STRIDE, OPS_STRIDE, DcuError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "_build", "libdaccord_host.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise DcuError("host library %s not built: run `python -m daccord_b200.build`" % HOST_LIB_PATH)
+        L = C.CDLL(HOST_LIB_PATH)
+        for f in ("dh_sim_create", "dh_data_load", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first"):
+            getattr(L, f).restype = C.c_void_p
+        for f in ("dh_data_nreads", "dh_data_novl", "dh_data_totlen"):
+            getattr(L, f).restype = C.c_uint64
+        L.dh_data_error.restype = C.c_char_p
+        L.dh_data_readlen.restype = C.c_uint32
+        _lib = L
+    return _lib
+
+
+class Dataset:
+    """packed read database + overlaps (simulated or loaded from .las / Dazzler DB files)"""
+
+    def __init__(self, handle):
+        if not handle:
+            raise DcuError("could not create / load dataset")
+        self.h = C.c_void_p(handle)
+
+    @staticmethod
+    def simulate(genome_len, read_len=10000, coverage=40.0, p_ins=0.09, p_del=0.045, p_sub=0.015, repeat_frac=0.0, seed=0, tspace=100, min_ovl=1000):
+        return Dataset(lib().dh_sim_create(C.c_uint64(genome_len), C.c_uint64(read_len), C.c_double(coverage), C.c_double(p_ins), C.c_double(p_del),
+                                           C.c_double(p_sub), C.c_double(repeat_frac), C.c_uint64(seed), C.c_int32(tspace), C.c_uint64(min_ovl)))
+
+    @staticmethod
+    def load(las, db):
+        return Dataset(lib().dh_data_load(las.encode(), db.encode()))
+
+    def write(self, las, db):
+        if lib().dh_data_write(self.h, las.encode(), db.encode()):
+            raise DcuError(lib().dh_data_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().dh_data_destroy(self.h)
+            self.h = None
+
+    @property
+    def nreads(self):
+        return lib().dh_data_nreads(self.h)
+
+    @property
+    def novl(self):
+        return lib().dh_data_novl(self.h)
+
+    @property
+    def totlen(self):
+        return lib().dh_data_totlen(self.h)
+
+    def packed(self):
+        n = C.c_uint64(0)
+        p = lib().dh_data_packed(self.h, C.byref(n))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,))
+
+    def profile(self):
+        """(p_i, p_d, est_cor) the way daccord derives them from its error profile (reference src/daccord.cpp:1867-1880)"""
+        a = (C.c_uint64 * 4)()
+        lib().dh_data_profile(self.h, a)
+        m, mis, ins, dele = [int(x) for x in a]
+        ln = m + mis + dele
+        return ins / ln, dele / ln, 1.0 - (mis + dele + ins) / ln
+
+    def pile(self, first=0, last=None, w=40, a=10, maxalign=2**64 - 1, maxinput=5000, nthreads=0):
+        last = self.nreads if last is None else last
+        nthreads = nthreads or (os.cpu_count() or 1)
+        b = lib().dh_pile(self.h, C.c_uint64(first), C.c_uint64(last), C.c_uint32(w), C.c_uint32(a), C.c_uint64(maxalign), C.c_uint64(maxinput), C.c_int(nthreads))
+        if not b:
+            raise DcuError("piling failed")
+        return Batch(self, b)
+
+
+class Batch:
+    def __init__(self, ds, handle):
+        self.ds = ds
+        self.h = C.c_void_p(handle)
+        n = C.c_uint64(0)
+        p = lib().dh_batch_windows(self.h, C.byref(n))
+        self.win = np.frombuffer((C.c_uint8 * (n.value * 16)).from_address(p), dtype=WINDOW_DT) if n.value else np.zeros(0, WINDOW_DT)
+        p = lib().dh_batch_slices(self.h, C.byref(n))
+        self.sl = np.frombuffer((C.c_uint8 * (n.value * 8)).from_address(p), dtype=SLICE_DT) if n.value else np.zeros(0, SLICE_DT)
+        p = lib().dh_batch_read_first(self.h, C.byref(n))
+        self.read_first = np.frombuffer((C.c_uint8 * (n.value * 8)).from_address(p), dtype=np.uint64)
+
+    def vote(self, res, cons, ops, producefull=False, minlen=0, counter=0, nthreads=0):
+        """pile vote + FastA text (bytes) for the reads of this batch; returns (fasta, next counter)"""
+        c = C.c_uint64(counter)
+        n = C.c_uint64(0)
+        nthreads = nthreads or (os.cpu_count() or 1)
+        p = lib().dh_vote(self.ds.h, self.h, res.ctypes.data_as(C.c_void_p), cons.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p),
+                          C.c_int(int(producefull)), C.c_uint64(minlen), C.byref(c), C.byref(n), C.c_int(nthreads))
+        out = C.string_at(p, n.value)
+        lib().dh_free(C.c_void_p(p))
+        return out, c.value
+
+    def close(self):
+        if self.h:
+            lib().dh_batch_destroy(self.h)
+            self.h = None
