@@ -31,6 +31,7 @@
 #ifdef DCU_EMU
 #define DCU_FN static inline
 #define DCU_BIG static
+#define DCU_NOUNROLL
 #define DCU_NOINL static inline
 #define DCU_CTOR
 #define DCU_NL 1
@@ -53,6 +54,7 @@ template <class T> static inline T ldg(const T* p) { return *p; }
 #else
 #define DCU_FN __device__ __forceinline__
 #define DCU_BIG __device__ __noinline__
+#define DCU_NOUNROLL _Pragma("unroll 1")
 #define DCU_NOINL __device__ __noinline__
 #define DCU_CTOR __device__
 #define DCU_NL 32
@@ -224,6 +226,7 @@ struct Ctx {
 DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - c.cap.LOGH); }
 DCU_NOINL int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
   uint32_t h = hslot(c, v), mask = (uint32_t)c.cap.H - 1;
+  DCU_NOUNROLL
   for (;;) {
     uint32_t key = c.ws.hkey[h];
     if (key == v) return c.ws.hnid[h];
@@ -240,6 +243,7 @@ DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
   const unsigned long long* row = c.T.VSq + (size_t)p * c.T.MS;
   int f = c.ws.n_freq[n];
   unsigned long long u = 0;
+  DCU_NOUNROLL
   for (int t = 0; t < f; ++t) { int pos = ip[t]; if (pos < c.T.MS) u += ldg(row + pos); }
   return (double)u / 4294967296.0;
 }
@@ -249,6 +253,7 @@ DCU_FN bool hless(bool maxh, double a, double b) { return maxh ? (a > b) : (a < 
 DCU_NOINL void heap_push(bool MAXH, double* hw, uint32_t* hi, int& n, double w, uint32_t id) {
   int i = n++;
   hw[i] = w; hi[i] = id;
+  DCU_NOUNROLL
   while (i > 0) {
     int p = (i - 1) >> 1;
     if (hless(MAXH, hw[i], hw[p])) { double tw = hw[i]; hw[i] = hw[p]; hw[p] = tw; uint32_t ti = hi[i]; hi[i] = hi[p]; hi[p] = ti; i = p; } else break;
@@ -257,6 +262,7 @@ DCU_NOINL void heap_push(bool MAXH, double* hw, uint32_t* hi, int& n, double w, 
 DCU_NOINL void heap_pop(bool MAXH, double* hw, uint32_t* hi, int& n) {
   --n; hw[0] = hw[n]; hi[0] = hi[n];
   int p = 0;
+  DCU_NOUNROLL
   for (;;) {
     int l = 2 * p + 1, r = l + 1;
     if (l >= n) break;
@@ -274,6 +280,7 @@ DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
   const Slice* sl = c.sl + win.slice_begin;
   if (lane == 0) {
     uint32_t o = 0;
+    DCU_NOUNROLL
     for (int j = 0; j < c.MAo; ++j) { w.soff[j] = (uint16_t)o; o += sl[j].len; if (sl[j].len > 255) o = 0x10000000u; }
     w.soff[c.MAo] = (uint16_t)(o > 65535u ? 65535u : o);
     c.nbases = (int)(o > 0x0fffffffu ? 0x0fffffff : o);
@@ -281,12 +288,15 @@ DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
   c.nbases = bcast(c.nbases, 0);
   wsync();
   if (c.nbases > c.cap.B || c.nbases > 65000) { c.overflow = 2; return; }
+  DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
     Slice s = sl[j];
     uint8_t* out = w.bases + w.soff[j];
     if (!(s.flags & 1)) {
+      DCU_NOUNROLL
       for (int i = 0; i < s.len; ++i) { uint32_t g = s.gpos + i; out[i] = (ldg(c.packed + (g >> 2)) >> (6 - 2 * (g & 3))) & 3; }
     } else {
+      DCU_NOUNROLL
       for (int i = 0; i < s.len; ++i) { uint32_t g = s.gpos + (s.len - 1 - i); out[i] = 3 - ((ldg(c.packed + (g >> 2)) >> (6 - 2 * (g & 3))) & 3); }
     }
   }
@@ -300,14 +310,17 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
   int maxv = -1;
   if (c.MAo) {
     int mn = 0x7fffffff, mx = -0x7fffffff;
+    DCU_NOUNROLL
     for (int j = 0; j < c.MAo; ++j) { int lp = seqlen(c, j) - 1; mn = lp < mn ? lp : mn; mx = lp > mx ? lp : mx; }
     if (mn < 0) mn = 0;
     if (mx < 0) mx = 0;
     int s0 = sup_lo(c, mn), s1 = sup_hi(c, mx);
     double best = DBL_MIN; int bi = 0x7fffffff;
+    DCU_NOUNROLL
     for (int i = s0 + lane; i < s1; i += DCU_NL) {
       const double* row = c.T.DPn + (size_t)i * c.T.MS;
       double vprod = 1.0;
+      DCU_NOUNROLL
       for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len) { int lp = len - 1; vprod *= (lp < c.T.MS ? ldg(row + lp) : 0.0); } }
       if (vprod > best) { best = vprod; bi = i; }
     }
@@ -317,13 +330,17 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
   if (maxv == -1) {            // density fallback (:2103-2155), rare -> lane 0
     if (lane == 0) {
       int Os = 0;
+      DCU_NOUNROLL
       for (int i = 0; i < 256; ++i) w.lenhist[i] = 0;
+      DCU_NOUNROLL
       for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len + 1 > Os) Os = len + 1; if (len < 256) w.lenhist[len]++; }
       int maxoff = -1; double maxoffv = DBL_MIN;
+      DCU_NOUNROLL
       for (int i = 0; i < c.T.NP; ++i) {
         const double* row = c.T.DPsq + (size_t)i * c.T.MS;
         double s = 0;
         int lim = Os < c.T.MS ? Os : c.T.MS;
+        DCU_NOUNROLL
         for (int j = 0; j < lim; ++j) { double o = (j < 256 && w.lenhist[j]) ? (double)(w.lenhist[j] - 1) : 0.0; s += ldg(row + j) * o; }
         if (s > maxoffv) { maxoff = i; maxoffv = s; }
       }
@@ -337,19 +354,24 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
 // ------------------------------------------------------------------ k-mer hash build (replaces setupPreNodes :2018-2304)
 DCU_BIG void build_hash(Ctx& c, int lane) {
   const WS& w = c.ws;
+  DCU_NOUNROLL
   for (int i = lane; i < c.cap.H; i += DCU_NL) { w.hkey[i] = W_EMPTY; w.hcnt[i] = 0; }
   wsync();
   uint32_t mask = (uint32_t)c.cap.H - 1;
   uint32_t ni = 0;
+  DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
     int len = seqlen(c, j);
     if (len < c.k) continue;
     const uint8_t* u = w.bases + w.soff[j];
     uint32_t v = 0;
+    DCU_NOUNROLL
     for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i];
+    DCU_NOUNROLL
     for (int i = 0; i + c.k <= len; ++i) {
       v = ((v << 2) & c.kmask) | u[i + c.k - 1];
       uint32_t h = hslot(c, v);
+      DCU_NOUNROLL
       for (;;) {
         uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
         if (old == W_EMPTY || old == v) { a_add(&w.hcnt[h], 1); break; }
@@ -363,18 +385,23 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
   // last k-mer of every sequence (the `last` array, :2108, :1360-1391): (count, kmer) sorted descending
   if (lane == 0) {
     int nl = 0;
+    DCU_NOUNROLL
     for (int j = 0; j < c.MAo; ++j) {
       int len = seqlen(c, j);
       if (len < c.k) continue;
       const uint8_t* u = w.bases + w.soff[j] + (len - c.k);
       uint32_t v = 0;
+      DCU_NOUNROLL
       for (int i = 0; i < c.k; ++i) v = (v << 2) | u[i];
       int t = 0;
+      DCU_NOUNROLL
       while (t < nl && w.ll_kmer[t] != v) ++t;
       if (t == nl) { w.ll_kmer[nl] = v; w.ll_cnt[nl] = 1; ++nl; } else w.ll_cnt[t]++;
     }
+    DCU_NOUNROLL
     for (int a = 1; a < nl; ++a) {          // insertion sort by (cnt, kmer) descending
       uint32_t kv = w.ll_kmer[a]; uint16_t cv = w.ll_cnt[a]; int b = a;
+      DCU_NOUNROLL
       while (b > 0 && (w.ll_cnt[b - 1] < cv || (w.ll_cnt[b - 1] == cv && w.ll_kmer[b - 1] < kv))) { w.ll_kmer[b] = w.ll_kmer[b - 1]; w.ll_cnt[b] = w.ll_cnt[b - 1]; --b; }
       w.ll_kmer[b] = kv; w.ll_cnt[b] = cv;
     }
@@ -388,6 +415,7 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
 DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   const WS& w = c.ws;
   int nn = 0;
+  DCU_NOUNROLL
   for (int base = 0; base < c.cap.H; base += DCU_NL) {
     int i = base + lane;
     bool keep = (w.hkey[i] != W_EMPTY) && ((int)w.hcnt[i] >= f);
@@ -405,30 +433,36 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   c.ni = bcast(c.ni, 0);
   wsync();
   if (c.ni > c.cap.NI) { c.overflow = 4; return; }
+  DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
     int len = seqlen(c, j);
     if (len < c.k) continue;
     const uint8_t* u = w.bases + w.soff[j];
     uint32_t v = 0;
+    DCU_NOUNROLL
     for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i];
+    DCU_NOUNROLL
     for (int i = 0; i + c.k <= len; ++i) {
       v = ((v << 2) & c.kmask) | u[i + c.k - 1];
       int n = lookup(c, v);
       if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = (uint8_t)i; w.irpos[w.n_ioff[n] + t] = (uint8_t)(len - i - c.k); }
     }
   }
+  DCU_NOUNROLL
   for (int e = lane; e < c.nex; e += DCU_NL) {       // synthesised k-mers of the gap filler (:1148-1157)
     int n = lookup(c, w.ex_kmer[e]);
     if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = w.ex_pos[e]; w.irpos[w.n_ioff[n] + t] = w.ex_rpos[e]; }
   }
   wsync();
   uint32_t nf = 0;
+  DCU_NOUNROLL
   for (int base = 0; base < nn; base += DCU_NL) {
     int n = base + lane;
     int c0 = 0;
     if (n < nn) {
       int f0 = w.n_freq[n]; const uint8_t* ip = w.ipos + w.n_ioff[n]; const uint8_t* irp = w.irpos + w.n_ioff[n];
       int lo = 255, hi = 0, clo = 255, chi = 0;
+      DCU_NOUNROLL
       for (int t = 0; t < f0; ++t) { int a = ip[t], b = irp[t]; lo = a < lo ? a : lo; hi = a > hi ? a : hi; clo = b < clo ? b : clo; chi = b > chi ? b : chi; c0 += (a == 0); }
       w.n_plow[n] = (uint8_t)lo; w.n_phigh[n] = (uint8_t)hi; w.n_cplow[n] = (uint8_t)clo; w.n_cphigh[n] = (uint8_t)chi;
     }
@@ -440,8 +474,10 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   wsync();
   if ((int)nf > c.cap.S) { c.overflow = 5; return; }
   if (lane == 0) {
+    DCU_NOUNROLL
     for (int a = 1; a < (int)nf; ++a) {         // (count, kmer) descending
       uint32_t kv = w.fl_kmer[a]; uint16_t cv = w.fl_cnt[a], nv = w.fl_nid[a]; int b = a;
+      DCU_NOUNROLL
       while (b > 0 && (w.fl_cnt[b - 1] < cv || (w.fl_cnt[b - 1] == cv && w.fl_kmer[b - 1] < kv))) { w.fl_kmer[b] = w.fl_kmer[b - 1]; w.fl_cnt[b] = w.fl_cnt[b - 1]; w.fl_nid[b] = w.fl_nid[b - 1]; --b; }
       w.fl_kmer[b] = kv; w.fl_cnt[b] = cv; w.fl_nid[b] = nv;
     }
@@ -454,14 +490,17 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
 DCU_BIG void compute_npred(Ctx& c, int lane) {
   const WS& w = c.ws;
   int shift = 2 * (c.k - 1);
+  DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
     uint32_t v = w.n_kmer[n];
     int cnt = 0;
+    DCU_NOUNROLL
     for (uint32_t s = 0; s < 4; ++s) {
       uint32_t pv = ((v >> 2) & c.kmask) | (s << shift);
       int p = lookup(c, pv);
       if (p == NID_NONE) continue;
       int na = w.n_nact[p];
+      DCU_NOUNROLL
       for (int e = 0; e < na; ++e) if (w.n_snid[4 * p + e] == n) { ++cnt; break; }
     }
     w.n_npred[n] = (uint8_t)cnt;
@@ -473,23 +512,29 @@ DCU_BIG void build_edges(Ctx& c, int lane) {
   const WS& w = c.ws;
   int no = c.MAo < c.T.KLIMN ? c.MAo : c.T.KLIMN - 1;
   unsigned long long lim = c.P.check ? ldg(c.T.klim + (size_t)c.kidx * c.T.KLIMN + no) : 0;
+  DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
     uint32_t v = w.n_kmer[n];
     uint32_t key[4]; uint16_t nid[4]; int ns = 0;
+    DCU_NOUNROLL
     for (uint32_t s = 0; s < 4; ++s) {
       int t = lookup(c, ((v << 2) & c.kmask) | s);
       if (t != NID_NONE) { key[ns] = ((uint32_t)w.n_freq[t] << 8) | s; nid[ns] = (uint16_t)t; ++ns; }
     }
+    DCU_NOUNROLL
     for (int a = 1; a < ns; ++a) {              // Links::sort, descending (Links.hpp:35-57)
       uint32_t kv = key[a]; uint16_t nv = nid[a]; int b = a;
+      DCU_NOUNROLL
       while (b > 0 && key[b - 1] < kv) { key[b] = key[b - 1]; nid[b] = nid[b - 1]; --b; }
       key[b] = kv; nid[b] = nv;
     }
     int na = 0;
     if (ns) {
       na = 1;
+      DCU_NOUNROLL
       while (na < ns && (((key[na] >> 8) >= (key[0] >> 8) / 2) || (c.P.check && (unsigned long long)(key[na] >> 8) >= lim))) ++na;
     }
+    DCU_NOUNROLL
     for (int e = 0; e < 4; ++e) { w.n_sfreq[4 * n + e] = e < ns ? (uint16_t)(key[e] >> 8) : 0; w.n_snid[4 * n + e] = e < ns ? nid[e] : (uint16_t)NID_NONE; }
     w.n_nsucc[n] = (uint8_t)ns; w.n_nact[n] = (uint8_t)na; w.n_mark[n] = 0;
   }
@@ -500,11 +545,14 @@ DCU_BIG void build_edges(Ctx& c, int lane) {
 DCU_BIG bool add_next(Ctx& c, int lane) {
   const WS& w = c.ws;
   uint32_t top = 0;
+  DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) { int na = w.n_nact[n]; if (na < w.n_nsucc[n]) { uint32_t f = w.n_sfreq[4 * n + na]; top = f > top ? f : top; } }
   top = red_max_u32(top);
   if (!top) return false;
+  DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
     int na = w.n_nact[n], ns = w.n_nsucc[n];
+    DCU_NOUNROLL
     while (na < ns && w.n_sfreq[4 * n + na] == top) ++na;
     w.n_nact[n] = (uint8_t)na;
   }
@@ -519,6 +567,7 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
 DCU_BIG void node_weights(Ctx& c, int lane) {
   const WS& w = c.ws;
   uint32_t run0 = 0, run1 = 0;
+  DCU_NOUNROLL
   for (int base = 0; base < c.nn; base += DCU_NL) {
     int n = base + lane;
     uint32_t a = 0, b = 0;
@@ -536,13 +585,16 @@ DCU_BIG void node_weights(Ctx& c, int lane) {
   }
   wsync();
   if ((int)run0 > c.cap.KW || (int)run1 > c.cap.KW) { c.overflow = 18; return; }
+  DCU_NOUNROLL
   for (int dir = 0; dir < 2; ++dir) {
     const uint32_t* off = dir ? w.n_ckwo : w.n_kwo;
     const uint8_t* lo = dir ? w.n_cpf : w.n_pf;
     double* out = dir ? w.kwR : w.kwF;
     uint32_t tot = dir ? run1 : run0;
+    DCU_NOUNROLL
     for (uint32_t q = (uint32_t)lane; q < tot; q += DCU_NL) {
       int a = 0, b = c.nn;                 // last node with off[n] <= q
+      DCU_NOUNROLL
       while (b - a > 1) { int mid = (a + b) >> 1; if (off[mid] <= q) a = mid; else b = mid; }
       out[q] = kweight(c, a, (int)lo[a] + (int)(q - off[a]), dir == 1);
     }
@@ -558,8 +610,10 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   uint32_t* nexp = &w.n_fill[0];      // n_fill[0] doubles as the append counter here (rebuilt afterwards)
   if (lane == 0) *nexp = 0;
   wsync();
+  DCU_NOUNROLL
   for (int a = lane; a < c.nn; a += DCU_NL) {
     uint32_t v = w.n_kmer[a];
+    DCU_NOUNROLL
     for (uint32_t x = 0; x < 16; ++x) {
       uint32_t nv = ((v << 4) & c.kmask) | x;
       int b = lookup(c, nv);
@@ -567,6 +621,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
       uint32_t cv = ((v << 2) & c.kmask) | (nv >> 2);
       if (lookup(c, cv) != NID_NONE) continue;
       double mweight = DBL_MIN; int mp = 0;
+      DCU_NOUNROLL
       for (int p = w.n_pf[a]; p < w.n_pt[a]; ++p) {
         double wa = kw_fwd(c, a, p);
         if (!(wa >= 1e-3)) continue;
@@ -578,6 +633,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
       }
       if (mweight != DBL_MIN) {
         int seqid = -1;
+        DCU_NOUNROLL
         for (int j = 0; j < c.MAo && seqid < 0; ++j) if (mp + c.k <= seqlen(c, j)) seqid = j;
         if (seqid >= 0) {
           uint32_t e = a_add(nexp, 1);
@@ -592,8 +648,10 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   if (nex > c.cap.EX) { c.overflow = 6; c.nex = 0; return; }
   c.nex = nex;
   uint32_t mask = (uint32_t)c.cap.H - 1;
+  DCU_NOUNROLL
   for (int e = lane; e < nex; e += DCU_NL) {
     uint32_t v = w.ex_kmer[e], h = hslot(c, v);
+    DCU_NOUNROLL
     for (;;) {
       uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
       if (old == W_EMPTY || old == v) { a_add(&w.hcnt[h], 1); break; }
@@ -609,10 +667,13 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
   const WS& w = c.ws;
   if (lane == 0) {
     int nrs = 0, slO = 0; uint16_t stamp = 0; bool ovf = false;
+    DCU_NOUNROLL
     for (int n = 0; n < c.nn; ++n) w.n_mark[n] = 0;
+    DCU_NOUNROLL
     for (int z = 0; z < c.nn && !ovf; ++z) {
       int numsucc = w.n_nact[z], numpred = w.n_npred[z];
       if (!(numsucc && (numpred != 1 || numsucc > 1))) continue;
+      DCU_NOUNROLL
       for (int i = 0; i < numsucc; ++i) {
         if (nrs >= c.cap.ST || slO + 2 > c.cap.SL) { ovf = true; break; }
         int start = slO;
@@ -621,6 +682,7 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
         w.slinks[slO++] = (uint16_t)z; w.n_mark[z] = stamp;
         w.slinks[slO++] = (uint16_t)ext; w.n_mark[ext] = stamp;
         int len = 2; bool loop = (z == ext); int cur = ext;
+        DCU_NOUNROLL
         while (!loop && w.n_nact[cur] == 1 && w.n_npred[cur] == 1) {
           cur = w.n_snid[4 * cur];
           if (slO >= c.cap.SL) { ovf = true; break; }
@@ -631,6 +693,7 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
         int last = cur;
         if (loop && z != last) {
           int j = 0;
+          DCU_NOUNROLL
           while (w.slinks[start + j] != last) ++j;
           j += 1;
           int retract = len - j;
@@ -648,8 +711,11 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
 
 // ascending bitonic sort of P (power of two) 64-bit keys, lanes strided over compare-exchange pairs
 DCU_BIG void warp_sort_u64(unsigned long long* a, int P, int lane) {
+  DCU_NOUNROLL
   for (int k = 2; k <= P; k <<= 1)
+    DCU_NOUNROLL
     for (int j = k >> 1; j > 0; j >>= 1) {
+      DCU_NOUNROLL
       for (int i = lane; i < P; i += DCU_NL) {
         int x = i ^ j;
         if (x > i) {
@@ -662,8 +728,11 @@ DCU_BIG void warp_sort_u64(unsigned long long* a, int P, int lane) {
     }
 }
 DCU_BIG void warp_sort_u32(uint32_t* a, int P, int lane) {
+  DCU_NOUNROLL
   for (int k = 2; k <= P; k <<= 1)
+    DCU_NOUNROLL
     for (int j = k >> 1; j > 0; j >>= 1) {
+      DCU_NOUNROLL
       for (int i = lane; i < P; i += DCU_NL) {
         int x = i ^ j;
         if (x > i) {
@@ -681,11 +750,13 @@ DCU_BIG void warp_sort_u32(uint32_t* a, int P, int lane) {
 DCU_BIG int split_pass(Ctx& c, const uint16_t* ioff, const uint16_t* ilen, int n, uint16_t* ooff, uint16_t* olen, int v, int lane) {
   const WS& w = c.ws;
   int base = 0;
+  DCU_NOUNROLL
   for (int b0 = 0; b0 < n; b0 += DCU_NL) {
     int z = b0 + lane;
     int off = 0, len = 0, split = -1;
     if (z < n) {
       off = ioff[z]; len = ilen[z];
+      DCU_NOUNROLL
       for (int i = 1; i + 1 < len; ++i) if (w.slinks[off + i] == v) { split = i; break; }
     }
     uint32_t act = ballot(z < n), sp = ballot(split >= 0);
@@ -708,6 +779,7 @@ DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
   n = split_pass(c, w.dt_off, w.dt_len, n, w.du_off, w.du_len, L, lane);
   if (n > c.cap.ST) { c.overflow = 8; return; }
   int P = 32; while (P < n) P <<= 1;
+  DCU_NOUNROLL
   for (int i = lane; i < P; i += DCU_NL) {
     unsigned long long key = ~0ull;
     if (i < n) {
@@ -719,9 +791,11 @@ DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
   }
   wsync();
   warp_sort_u64(w.skey, P, lane);
+  DCU_NOUNROLL
   for (int i = lane; i < c.nn; i += DCU_NL) { w.n_dsf[i] = NID_NONE; w.n_dsn[i] = 0; }
   wsync();
   int o = 0;
+  DCU_NOUNROLL
   for (int b0 = 0; b0 < n; b0 += DCU_NL) {
     int i = b0 + lane;
     bool keep = false; unsigned long long key = 0;
@@ -739,6 +813,7 @@ DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
   }
   c.nds = o;
   wsync();
+  DCU_NOUNROLL
   for (int s = lane; s < o; s += DCU_NL) {          // count per first node (<= 4, distinct ext symbols)
     int fn = w.slinks[w.ds_off[s]];
     if (w.n_dsf[fn] == s) { int cnt = 1; while (s + cnt < o && w.slinks[w.ds_off[s + cnt]] == fn) ++cnt; w.n_dsn[fn] = (uint8_t)cnt; }
@@ -754,6 +829,7 @@ DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s] + c.
 DCU_BIG void stretch_positions(Ctx& c, int lane) {
   const WS& w = c.ws;
   uint32_t run0 = 0, run1 = 0;
+  DCU_NOUNROLL
   for (int base = 0; base < c.nds; base += DCU_NL) {
     int s = base + lane;
     uint32_t a = 0, b = 0;
@@ -768,17 +844,21 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
   }
   wsync();
   if ((int)run0 > c.cap.SF || (int)run1 > c.cap.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
+  DCU_NOUNROLL
   for (int dir = 0; dir < 2; ++dir) {
     const uint16_t* so = dir ? w.ds_cO : w.ds_fO;
     const uint8_t* sb = dir ? w.ds_cB : w.ds_fB;
     double* ow = dir ? w.sc_w : w.sf_w; double* owf = dir ? w.sc_wf : w.sf_wf; double* owl = dir ? w.sc_wl : w.sf_wl;
     uint32_t tot = dir ? run1 : run0;
+    DCU_NOUNROLL
     for (uint32_t q = (uint32_t)lane; q < tot; q += DCU_NL) {
       int a = 0, b = c.nds;                // last stretch with so[s] <= q
+      DCU_NOUNROLL
       while (b - a > 1) { int mid = (a + b) >> 1; if (so[mid] <= q) a = mid; else b = mid; }
       int off = w.ds_off[a], L = w.ds_len[a];
       int p0 = (int)sb[a] + (int)(q - so[a]);
       double sum = 0.0, wfirst = 0.0, wlast = 0.0; bool ok = true;
+      DCU_NOUNROLL
       for (int jj = 0; jj < L; ++jj) {
         int nj = dir == 0 ? w.slinks[off + jj] : w.slinks[off + L - 1 - jj];
         double wt = dir == 0 ? kw_fwd(c, nj, p0 + jj) : kw_rev(c, nj, p0 + jj);
@@ -812,14 +892,17 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
   uint32_t* cnt = &w.n_fill[0];
   if (lane == 0) *cnt = 0;
   wsync();
+  DCU_NOUNROLL
   for (int A = lane; A < c.nds; A += DCU_NL) {
     int ln = ds_last(c, A);
     int b0 = w.n_dsf[ln], bn = w.n_dsn[ln];
     if (b0 == NID_NONE) continue;
+    DCU_NOUNROLL
     for (int B = b0; B < b0 + bn; ++B) {
       int shift = w.ds_len[B] - 1;
       double weight = 0.0;
       int cb = w.ds_cB[B], cn = w.ds_cN[B], co = w.ds_cO[B];
+      DCU_NOUNROLL
       for (int d = 0; d < cn; ++d) {
         double wb = w.sc_w[co + d];
         if (!(wb >= 0.0)) continue;
@@ -835,10 +918,13 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
   if (nrl > c.cap.RL) { c.overflow = 10; return; }
   c.nrl = nrl;
   int P = 32; while (P < nrl) P <<= 1;
+  DCU_NOUNROLL
   for (int i = nrl + lane; i < P; i += DCU_NL) w.rl[i] = 0xFFFFFFFFu;
+  DCU_NOUNROLL
   for (int s = lane; s < c.nds; s += DCU_NL) { w.ds_rlO[s] = 0; w.ds_rlN[s] = 0; }
   wsync();
   warp_sort_u32(w.rl, P, lane);
+  DCU_NOUNROLL
   for (int t = lane; t < nrl; t += DCU_NL) {
     int B = (int)(w.rl[t] >> 16);
     if (t == 0 || (int)(w.rl[t - 1] >> 16) != B) { int e = t + 1; while (e < nrl && (int)(w.rl[e] >> 16) == B) ++e; w.ds_rlO[B] = (uint16_t)t; w.ds_rlN[B] = (uint16_t)(e - t); }
@@ -852,6 +938,7 @@ DCU_NOINL int myers_dist(const unsigned long long* peq, int m, const uint8_t* t,
   if (m == 0) return n;
   unsigned long long pv = ~0ull, mv = 0, top = 1ull << (m - 1);
   int score = m;
+  DCU_NOUNROLL
   for (int j = 0; j < n; ++j) {
     unsigned long long eq = peq[t[j]];
     unsigned long long xv = eq | mv;
@@ -866,6 +953,7 @@ DCU_NOINL int myers_dist(const unsigned long long* peq, int m, const uint8_t* t,
 }
 DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool ascii) {
   peq[0] = peq[1] = peq[2] = peq[3] = 0;
+  DCU_NOUNROLL
   for (int i = 0; i < m; ++i) {
     int cde = pat[i];
     if (ascii) cde = (cde == 'A') ? 0 : (cde == 'C') ? 1 : (cde == 'G') ? 2 : 3;
@@ -889,10 +977,12 @@ DCU_NOINL int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t fro
 DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
   const WS& w = c.ws;
   int nrp = 0, nq = 0; narp = 0;
+  DCU_NOUNROLL
   for (int i = 0; i < c.cap.BL; ++i) w.arph_n[i] = 0;
   int seed = rp_new(c, nrp, 0.0, IDX_NONE, w.n_kmer[Lnode], NID_NONE, 0, 0, c.k);
   if (seed < 0) return;
   heap_push(true, w.rq_w, w.rq_id, nq, 0.0, (uint32_t)seed);
+  DCU_NOUNROLL
   while (nq > 0 && !c.overflow) {
     double wt = w.rq_w[0]; int id = (int)w.rq_id[0];
     heap_pop(true, w.rq_w, w.rq_id, nq);
@@ -901,6 +991,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
     double* hw = w.arph_w + bl * HEAPK; int hn = w.arph_n[bl];
     if (hn == HEAPK) {                                  // bounded per-length heap (:3626-3665); only weights matter
       int mi = 0;
+      DCU_NOUNROLL
       for (int t = 1; t < HEAPK; ++t) if (hw[t] < hw[mi]) mi = t;
       if (wt <= hw[mi]) continue;
       hw[mi] = wt;
@@ -908,6 +999,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
     w.arp[narp++] = (uint32_t)id;
     int rlen = w.rp_len[id], rpos = w.rp_pos[id];
     if (rlen == 0) {
+      DCU_NOUNROLL
       for (int s = 0; s < c.nds; ++s) if (ds_last(c, s) == Lnode) {
         int o = sfo_rev(c, s, rpos);                    // extendReversePath (:4058-4105) + feasibility (:4130-4159)
         if (o >= 0 && w.sc_w[o] >= 0.5) {
@@ -920,6 +1012,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
       }
     } else if (bl < (lmax + 1) / 2) {
       int ls = w.rp_stretch[id];
+      DCU_NOUNROLL
       for (int t = w.ds_rlO[ls], te = w.ds_rlO[ls] + w.ds_rlN[ls]; t < te; ++t) {
         int s = (int)(w.rl[t] & 0xFFFF);
         int o = sfo_rev(c, s, rpos);
@@ -935,8 +1028,10 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
     }
   }
   // sort accepted paths by (front, baselen), ties in acceptance order (:3742, convention C7)
+  DCU_NOUNROLL
   for (int a = 1; a < narp; ++a) {
     uint32_t id = w.arp[a]; uint32_t fr = w.rp_front[id]; int bl = w.rp_baselen[id]; int b = a;
+    DCU_NOUNROLL
     while (b > 0) {
       uint32_t pid = w.arp[b - 1];
       bool greater = w.rp_front[pid] != fr ? (w.rp_front[pid] > fr) : (w.rp_baselen[pid] > bl);
@@ -960,6 +1055,7 @@ DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
   const WS& w = c.ws;
   int best = -1; double bw = 0;
   double cw = cur >= 0 ? w.rp_w[w.arp[cur]] : 0;
+  DCU_NOUNROLL
   for (int i = left; i < right; ++i) {
     double wi = w.rp_w[w.arp[i]];
     if (cur >= 0 && !(wi < cw || (wi == cw && i < cur))) continue;
@@ -995,16 +1091,22 @@ DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath 
 DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
   const WS& w = c.ws;
   int stack[MAXCAND]; int sp = 0;
+  DCU_NOUNROLL
   for (int q = P; q >= 0; q = (w.fp_parent[q] == IDX_NONE ? -1 : (int)w.fp_parent[q])) { if (sp >= MAXCAND) return -1; stack[sp++] = w.fp_stretch[q]; }
   int o = 0;
   uint32_t fk = w.n_kmer[ds_first(c, stack[sp - 1])];
+  DCU_NOUNROLL
   for (int i = 0; i < c.k; ++i) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[(fk >> (2 * (c.k - 1 - i))) & 3]; }
+  DCU_NOUNROLL
   for (int t = sp - 1; t >= 0; --t) {
     int s = stack[t], off = w.ds_off[s], L = w.ds_len[s];
+    DCU_NOUNROLL
     for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.n_kmer[w.slinks[off + j]] & 3]; }
   }
+  DCU_NOUNROLL
   for (int q = rpid; w.rp_len[q] > 0; q = (int)w.rp_parent[q]) {
     int s = w.rp_stretch[q], off = w.ds_off[s], L = w.ds_len[s];
+    DCU_NOUNROLL
     for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.n_kmer[w.slinks[off + j]] & 3]; }
   }
   return o;
@@ -1015,10 +1117,14 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
   const WS& w = c.ws;
   int nfp = 0, nsi = 0, nsq = 0;
   const int K = c.k;
+  DCU_NOUNROLL
   for (int i = 0; i < c.cap.BL; ++i) w.apq_n[i] = 0;
   if (w.n_dsf[Fnode] != NID_NONE)
+    DCU_NOUNROLL
     for (int s = w.n_dsf[Fnode], se = s + w.n_dsn[Fnode]; s < se; ++s) { int id = fp_extend(c, nfp, -1, s); if (id < 0) return; apq_push(c, id); }
+  DCU_NOUNROLL
   for (int zz = 0; zz < c.cap.BL && !c.overflow; ++zz) {
+    DCU_NOUNROLL
     while (w.apq_n[zz] > 0) {
       double* hw = w.apq_w + zz * HEAPK; uint32_t* hi = w.apq_id + zz * HEAPK; int n = w.apq_n[zz];
       int P = (int)hi[0];
@@ -1029,6 +1135,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
       int blo = lmin + K - candlen; if (blo < 0) blo = 0;
       int bhi = lmax + K - candlen; if (bhi < 0) bhi = 0;
       int left = -1, right = -1;
+      DCU_NOUNROLL
       for (int i = 0; i < narp; ++i) {
         uint32_t id = w.arp[i];
         if (w.rp_front[id] == plk && (int)w.rp_baselen[id] >= blo && (int)w.rp_baselen[id] <= bhi) { if (left < 0) left = i; right = i + 1; }
@@ -1043,6 +1150,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
       }
       int pbl = w.fp_baselen[P];
       if (pbl < K || (pbl - K) < ((lmax + 1) / 2)) {
+        DCU_NOUNROLL
         for (int s = w.n_dsf[plast], se = (s == NID_NONE ? 0 : s + w.n_dsn[plast]); s < se; ++s) {
           int o = sfo_fwd(c, s, w.fp_pos[P]);
           double ew = o >= 0 ? w.sf_w[o] : 0.0;
@@ -1060,6 +1168,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
     }
   }
   int prevlen = -1;
+  DCU_NOUNROLL
   for (int nfull = 0; nsq > 0 && nfull < 16 && !c.overflow; ++nfull) {        // :5049-5092
     int rec = (int)w.sq_id[0]; double weight = w.sq_w[0];
     heap_pop(true, w.sq_w, w.sq_id, nsq);
@@ -1083,6 +1192,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
     prevlen = len;
     int slot = 0; while (!((freeslots >> slot) & 1u)) ++slot;
     freeslots &= ~(1u << slot);
+    DCU_NOUNROLL
     for (int i = 0; i < len; ++i) { w.prevs[i] = w.tmps[i]; w.cand[slot * MAXCAND + i] = w.tmps[i]; }
     w.candlen[slot] = (uint8_t)len;
     heap_push(false, w.cdh_w, w.cdh_id, ncdh, weight, (uint32_t)slot);
@@ -1097,7 +1207,9 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
   int ncdh = 0; uint32_t freeslots = (1u << (CDH_N + 1)) - 1;
   int firstthres = c.nfirst ? (w.fl_cnt[0] * 3) / 4 : 0;
   int lastthres = c.nlast ? (w.ll_cnt[0] * 3) / 4 : 0;
+  DCU_NOUNROLL
   for (int fi = 0; fi < c.nfirst && w.fl_cnt[fi] >= firstthres; ++fi)
+    DCU_NOUNROLL
     for (int li = 0; li < c.nlast && w.ll_cnt[li] >= lastthres; ++li) {
       int F = w.fl_nid[fi];
       int L = lookup(c, w.ll_kmer[li]);
@@ -1121,25 +1233,31 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
   int nacc = 0;
   if (lane == 0) {
     int nch = 0;
+    DCU_NOUNROLL
     while (ncdh > 0) { double wt = w.cdh_w[0]; uint32_t id = w.cdh_id[0]; heap_pop(false, w.cdh_w, w.cdh_id, ncdh); heap_push(true, w.ch_w, w.ch_id, nch, wt, id); }
+    DCU_NOUNROLL
     while (nch > 0) { w.acc_w[nacc] = w.ch_w[0]; w.acc_slot[nacc] = (uint8_t)w.ch_id[0]; ++nacc; heap_pop(true, w.ch_w, w.ch_id, nch); }
   }
   nacc = bcast(nacc, 0);
   wsync();
   // getSimpleCandidateError (:5355-5363): lanes over sequences
+  DCU_NOUNROLL
   for (int a = 0; a < nacc; ++a) {
     int slot = w.acc_slot[a], m = w.candlen[slot];
     unsigned long long peq[4];
     make_peq(peq, w.cand + slot * MAXCAND, m, true);
     uint32_t e = 0;
+    DCU_NOUNROLL
     for (int j = lane; j < c.MAo; j += DCU_NL) e += (uint32_t)myers_dist(peq, m, w.bases + w.soff[j], seqlen(c, j));
     e = red_sum_u32(e);
     if (lane == 0) w.acc_err[a] = e;
   }
   wsync();
   if (lane == 0) {                       // std::sort by error, n <= 16 => stable insertion sort (:5156)
+    DCU_NOUNROLL
     for (int a = 1; a < nacc; ++a) {
       double tw = w.acc_w[a]; uint32_t te = w.acc_err[a]; uint8_t ts = w.acc_slot[a]; int b = a;
+      DCU_NOUNROLL
       while (b > 0 && w.acc_err[b - 1] > te) { w.acc_w[b] = w.acc_w[b - 1]; w.acc_err[b] = w.acc_err[b - 1]; w.acc_slot[b] = w.acc_slot[b - 1]; --b; }
       w.acc_w[b] = tw; w.acc_err[b] = te; w.acc_slot[b] = ts;
     }
@@ -1155,6 +1273,7 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
   unsigned long long peq[4];
   make_peq(peq, a, la, false);            // a = base codes
   unsigned long long pv = ~0ull, mv = 0;
+  DCU_NOUNROLL
   for (int j = 1; j <= lb; ++j) {
     int ch = cons[j - 1]; ch = (ch == 'A') ? 0 : (ch == 'C') ? 1 : (ch == 'G') ? 2 : 3;
     unsigned long long eq = peq[ch];
@@ -1169,6 +1288,7 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
   }
   int i = la, j = lb, n = 0;
   // ops are produced backwards, then reversed in place
+  DCU_NOUNROLL
   while (i > 0 || j > 0) {
     int op;
     if (i > 0 && j > 0) {
@@ -1185,6 +1305,7 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
     ++n;
   }
   if (n > 128) return -1;
+  DCU_NOUNROLL
   for (int x = 0, y = n - 1; x < y; ++x, --y) { uint8_t t = ops[x]; ops[x] = ops[y]; ops[y] = t; }
   return n;
 }
@@ -1203,10 +1324,12 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
   bool pathfailed = true, have = false;
   unsigned long long minrate = c.P.eminrate;
   int bestlen = 0, bestk = 0, bestff = -1, bestn = 0;
+  DCU_NOUNROLL
   for (int k = c.P.k_lo; k <= c.P.k_hi; ++k) {
     c.k = k; c.kidx = k - c.P.k_lo; c.kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     c.nex = 0;
     build_hash(c, lane);
+    DCU_NOUNROLL
     for (int ff = c.P.maxff; ff >= c.P.minff; --ff) {
       int f = ff > 1 ? ff : 1;
       if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
@@ -1222,6 +1345,7 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
       }
       build_edges(c, lane);
       int mintry = 0; bool lconsok = false;
+      DCU_NOUNROLL
       for (;;) {
         int nacc = traverse(c, lmin, lmax, lane);
         if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
@@ -1230,6 +1354,7 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
           if (e0 < minrate) {
             lconsok = true; minrate = e0; have = true;
             int slot = w.acc_slot[0]; bestlen = w.candlen[slot]; bestk = k; bestff = ff; bestn = nacc;
+            DCU_NOUNROLL
             for (int i = lane; i < bestlen; i += DCU_NL) w.best[i] = w.cand[slot * MAXCAND + i];
             wsync();
           } else if (have) lconsok = true;
@@ -1243,6 +1368,7 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
   if (pathfailed) { res.status = ST_FAILED; return; }
   int nops = 0;
   if (lane == 0) {
+    DCU_NOUNROLL
     for (int i = 0; i < bestlen; ++i) cons_out[i] = w.best[i];
     nops = placement(c, w.bases, c.P.w, w.best, bestlen, ops_out);
   }
