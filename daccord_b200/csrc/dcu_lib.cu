@@ -32,7 +32,7 @@ struct KArgs {
   unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this tier
 };
 
-__global__ void __launch_bounds__(WPB * 32) dcu_window_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(WPB * 32, 8) dcu_window_kernel(const __grid_constant__ KArgs a) {
   __shared__ dcu::WS s_ws[WPB];
   __shared__ dcu::Caps s_cap; __shared__ dcu::Tables s_T; __shared__ dcu::Params s_P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -86,7 +86,7 @@ struct dcu_ctx {
   dcu::Tables T{}; dcu::Params P{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int num_sms = 0, blocks_per_sm[2] = {4, 1};
+  int num_sms = 0, blocks_per_sm[2] = {8, 1};
   // tables
   DevBuf<double> dDPn, dDPsq; DevBuf<unsigned long long> dVSq, dklim; DevBuf<uint16_t> dsuplo, dsuphi;
   // database
@@ -96,6 +96,7 @@ struct dcu_ctx {
   DevBuf<uint32_t> dovf[2]; DevBuf<unsigned int> dcnt;     // dcnt: [ticket0, ovf0, ticket1, ovf1]
   DevBuf<uint8_t> dslab[2];
   dcu::Caps caps[2]; dcu::Layout lay[2]; int grid[2] = {0, 0};
+  dcu::Caps slab_caps[2] = {}; uint32_t slab_bytes[2] = {0, 0};
   uint64_t nwin = 0, nsl = 0; int maxS = 0, maxB = 0;
   uint64_t launches = 0, hard = 0;
   std::string err;
@@ -222,7 +223,15 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   int grid = ctx->num_sms * bps;
   size_t need_blocks = ((size_t)n + WPB - 1) / WPB;
   if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
-  CK(ctx->dslab[tier].ensure((size_t)grid * WPB * ctx->lay[tier].bytes));
+  {
+    size_t need = (size_t)grid * WPB * ctx->lay[tier].bytes;
+    bool fresh = need > ctx->dslab[tier].cap || ctx->slab_bytes[tier] != ctx->lay[tier].bytes || memcmp(&ctx->slab_caps[tier], &ctx->caps[tier], sizeof(dcu::Caps)) != 0;
+    CK(ctx->dslab[tier].ensure(need));
+    if (fresh) {      // a zeroed slab is how a warp recognises that its hash table still has to be initialised
+      CK(cudaMemsetAsync(ctx->dslab[tier].p, 0, ctx->dslab[tier].cap, ctx->stream));
+      ctx->slab_bytes[tier] = ctx->lay[tier].bytes; ctx->slab_caps[tier] = ctx->caps[tier];
+    }
+  }
   KArgs a;
   a.L = ctx->lay[tier]; a.cap = ctx->caps[tier]; a.T = ctx->T; a.P = ctx->P;
   a.packed = ctx->dpacked; a.sl = ctx->dsl.p; a.win = ctx->dwin.p; a.res = ctx->dres.p; a.cons = ctx->dcons.p; a.ops = ctx->dops.p;

@@ -12,7 +12,7 @@ inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
   c.B = maxB < 64 ? 64 : maxB;
   c.NI = c.B;
   c.EX = tier == 0 ? 256 : 4096;
-  c.LOGH = ceil_pow2_log(2 * (c.NI + c.EX));
+  c.LOGH = ceil_pow2_log((c.NI + c.EX) * 3 / 2);
   c.H = 1 << c.LOGH;
   c.BL = w + 8;
   if (tier == 0) {

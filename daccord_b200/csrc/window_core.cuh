@@ -118,18 +118,18 @@ struct Result { uint8_t status, k; int8_t ff; uint8_t clen; uint32_t err; uint16
 // one warp's workspace: pointers into its slab (all arrays SoA)
 struct WS {
   uint8_t* bases; uint16_t* soff; uint16_t* lenhist;
-  uint32_t* hkey; uint32_t* hcnt; uint16_t* hnid;
+  uint32_t* hkey; uint32_t* hcnt; uint16_t* hnid; uint32_t* occ; uint32_t* hstate;   // hstate[0] = #occupied slots, hstate[1] = table initialised
   uint32_t* n_kmer; uint16_t* n_freq; uint32_t* n_ioff; uint32_t* n_fill;
   uint8_t *n_plow, *n_phigh, *n_cplow, *n_cphigh, *n_nsucc, *n_nact, *n_npred;
   uint16_t* n_sfreq; uint16_t* n_snid; uint16_t* n_mark;
   uint8_t *ipos, *irpos;
   uint32_t* ex_kmer; uint8_t *ex_pos, *ex_rpos;
   uint32_t* ll_kmer; uint16_t* ll_cnt; uint32_t* fl_kmer; uint16_t* fl_cnt; uint16_t* fl_nid;
-  uint16_t* slinks; uint16_t *rs_off, *rs_len;
+  uint16_t* slinks; uint8_t* slsym; uint16_t *rs_off, *rs_len;
   uint16_t *ds_off, *ds_len, *ds_fO, *ds_cO, *dt_off, *dt_len, *du_off, *du_len, *ds_rlO, *ds_rlN;
   uint8_t *ds_fB, *ds_fN, *ds_cB, *ds_cN;           // slot range of a stretch: positions [B, B+N)
-  double *sf_w, *sf_wf, *sf_wl;                      // forward stretch objects, slot = ds_fO[s] + (p - ds_fB[s]); w < 0: infeasible
-  double *sc_w, *sc_wf, *sc_wl;                      // reverse stretch objects
+  double *sf_w;                                      // forward stretch objects, slot = ds_fO[s] + (p - ds_fB[s]); w < 0: infeasible
+  double *sc_w;                                      // reverse stretch objects (first / last link weights come from kwF / kwR)
   uint8_t *n_pf, *n_pt, *n_cpf, *n_cpt; uint32_t *n_kwo, *n_ckwo; double *kwF, *kwR;   // dense per-node position weights
   uint16_t* n_dsf; uint8_t* n_dsn;                   // node -> derived stretches starting there
   unsigned long long* skey;
@@ -154,7 +154,8 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
 
 #define DCU_WS_FIELDS(X)                                                                                  \
   X(bases, uint8_t, c.B) X(soff, uint16_t, c.S + 1) X(lenhist, uint16_t, 256)                              \
-  X(hkey, uint32_t, c.H) X(hcnt, uint32_t, c.H) X(hnid, uint16_t, c.H)                                     \
+  X(hkey, uint32_t, c.H) X(hcnt, uint32_t, c.H) X(hnid, uint16_t, c.H) X(occ, uint32_t, c.NI + c.EX)         \
+  X(hstate, uint32_t, 4)                                                                                   \
   X(n_kmer, uint32_t, c.NN) X(n_freq, uint16_t, c.NN) X(n_ioff, uint32_t, c.NN) X(n_fill, uint32_t, c.NN)  \
   X(n_plow, uint8_t, c.NN) X(n_phigh, uint8_t, c.NN) X(n_cplow, uint8_t, c.NN) X(n_cphigh, uint8_t, c.NN)  \
   X(n_nsucc, uint8_t, c.NN) X(n_nact, uint8_t, c.NN) X(n_npred, uint8_t, c.NN)                             \
@@ -163,13 +164,12 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(ex_kmer, uint32_t, c.EX) X(ex_pos, uint8_t, c.EX) X(ex_rpos, uint8_t, c.EX)                            \
   X(ll_kmer, uint32_t, c.S) X(ll_cnt, uint16_t, c.S) X(fl_kmer, uint32_t, c.S) X(fl_cnt, uint16_t, c.S)    \
   X(fl_nid, uint16_t, c.S)                                                                                 \
-  X(slinks, uint16_t, c.SL) X(rs_off, uint16_t, c.ST) X(rs_len, uint16_t, c.ST)                            \
+  X(slinks, uint16_t, c.SL) X(slsym, uint8_t, c.SL) X(rs_off, uint16_t, c.ST) X(rs_len, uint16_t, c.ST)    \
   X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint16_t, c.ST) X(ds_cO, uint16_t, c.ST)    \
   X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST) X(du_off, uint16_t, c.ST) X(du_len, uint16_t, c.ST)  \
   X(ds_rlO, uint16_t, c.ST) X(ds_rlN, uint16_t, c.ST)                                                      \
   X(ds_fB, uint8_t, c.ST) X(ds_fN, uint8_t, c.ST) X(ds_cB, uint8_t, c.ST) X(ds_cN, uint8_t, c.ST)          \
-  X(sf_w, double, c.SF) X(sf_wf, double, c.SF) X(sf_wl, double, c.SF)                                      \
-  X(sc_w, double, c.SF) X(sc_wf, double, c.SF) X(sc_wl, double, c.SF)                                      \
+  X(sf_w, double, c.SF) X(sc_w, double, c.SF)                                                              \
   X(n_pf, uint8_t, c.NN) X(n_pt, uint8_t, c.NN) X(n_cpf, uint8_t, c.NN) X(n_cpt, uint8_t, c.NN)            \
   X(n_kwo, uint32_t, c.NN) X(n_ckwo, uint32_t, c.NN) X(kwF, double, c.KW) X(kwR, double, c.KW)             \
   X(n_dsf, uint16_t, c.NN) X(n_dsn, uint8_t, c.NN) X(skey, unsigned long long, c.STP)                      \
@@ -352,12 +352,34 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
 }
 
 // ------------------------------------------------------------------ k-mer hash build (replaces setupPreNodes :2018-2304)
+// claim / count one k-mer; newly claimed slots are appended to the occupancy list so that nothing ever scans or
+// clears the whole table (the slab is reused from window to window, only touched slots are reset)
+DCU_FN void hash_insert(const Ctx& c, uint32_t v) {
+  const WS& w = c.ws;
+  uint32_t mask = (uint32_t)c.cap.H - 1, h = hslot(c, v);
+  DCU_NOUNROLL
+  for (;;) {
+    uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
+    if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate[0], 1); w.occ[t] = h; a_add(&w.hcnt[h], 1); break; }
+    if (old == v) { a_add(&w.hcnt[h], 1); break; }
+    h = (h + 1) & mask;
+  }
+}
 DCU_BIG void build_hash(Ctx& c, int lane) {
   const WS& w = c.ws;
-  DCU_NOUNROLL
-  for (int i = lane; i < c.cap.H; i += DCU_NL) { w.hkey[i] = W_EMPTY; w.hcnt[i] = 0; }
+  if (w.hstate[1] != 0x600DF00Du) {          // first use of this slab: full initialisation
+    DCU_NOUNROLL
+    for (int i = lane; i < c.cap.H; i += DCU_NL) { w.hkey[i] = W_EMPTY; w.hcnt[i] = 0; w.hnid[i] = NID_NONE; }
+    wsync();
+    if (lane == 0) { w.hstate[0] = 0; w.hstate[1] = 0x600DF00Du; }
+  } else {
+    int nocc = (int)w.hstate[0];
+    DCU_NOUNROLL
+    for (int i = lane; i < nocc; i += DCU_NL) { int h = w.occ[i]; w.hkey[h] = W_EMPTY; w.hcnt[h] = 0; w.hnid[h] = NID_NONE; }
+    wsync();
+    if (lane == 0) w.hstate[0] = 0;
+  }
   wsync();
-  uint32_t mask = (uint32_t)c.cap.H - 1;
   uint32_t ni = 0;
   DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
@@ -370,13 +392,7 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
     DCU_NOUNROLL
     for (int i = 0; i + c.k <= len; ++i) {
       v = ((v << 2) & c.kmask) | u[i + c.k - 1];
-      uint32_t h = hslot(c, v);
-      DCU_NOUNROLL
-      for (;;) {
-        uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
-        if (old == W_EMPTY || old == v) { a_add(&w.hcnt[h], 1); break; }
-        h = (h + 1) & mask;
-      }
+      hash_insert(c, v);
       ++ni;
     }
   }
@@ -415,15 +431,17 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
 DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   const WS& w = c.ws;
   int nn = 0;
+  const int nocc = (int)w.hstate[0];
   DCU_NOUNROLL
-  for (int base = 0; base < c.cap.H; base += DCU_NL) {
-    int i = base + lane;
-    bool keep = (w.hkey[i] != W_EMPTY) && ((int)w.hcnt[i] >= f);
+  for (int base = 0; base < nocc; base += DCU_NL) {
+    int t = base + lane;
+    int i = t < nocc ? (int)w.occ[t] : 0;
+    bool keep = (t < nocc) && ((int)w.hcnt[i] >= f);
     uint32_t b = ballot(keep);
     int idx = nn + popc(b & lanemask_lt(lane));
     if (keep) {
       if (idx < c.cap.NN) { w.n_kmer[idx] = w.hkey[i]; w.n_freq[idx] = (uint16_t)w.hcnt[i]; w.hnid[i] = (uint16_t)idx; w.n_fill[idx] = 0; }
-    } else w.hnid[i] = NID_NONE;
+    } else if (t < nocc) w.hnid[i] = NID_NONE;
     nn += popc(b);
   }
   if (nn > c.cap.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
@@ -647,65 +665,54 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   wsync();
   if (nex > c.cap.EX) { c.overflow = 6; c.nex = 0; return; }
   c.nex = nex;
-  uint32_t mask = (uint32_t)c.cap.H - 1;
   DCU_NOUNROLL
-  for (int e = lane; e < nex; e += DCU_NL) {
-    uint32_t v = w.ex_kmer[e], h = hslot(c, v);
-    DCU_NOUNROLL
-    for (;;) {
-      uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
-      if (old == W_EMPTY || old == v) { a_add(&w.hcnt[h], 1); break; }
-      h = (h + 1) & mask;
-    }
-  }
+  for (int e = lane; e < nex; e += DCU_NL) hash_insert(c, w.ex_kmer[e]);
   wsync();
 }
 
 // ------------------------------------------------------------------ stretches (unitigs)
-// computeStretches(checkpredecessors=true) (:2844-2986); serial walk over the precomputed successor ids
+// computeStretches(checkpredecessors=true) (:2844-2986).  Lanes over start nodes; every (start, active successor)
+// pair is walked twice: once to measure, once (after a warp scan gave it its slot) to write the links.  With
+// predecessor checks on, a walk can only close a loop by coming back to its own start (any other revisited node
+// would have two active predecessors and end the walk before), so loop detection is a comparison with the start.
 DCU_BIG void raw_stretches(Ctx& c, int lane) {
   const WS& w = c.ws;
-  if (lane == 0) {
-    int nrs = 0, slO = 0; uint16_t stamp = 0; bool ovf = false;
+  int nrs = 0, slO = 0; bool ovf = false;
+  DCU_NOUNROLL
+  for (int base = 0; base < c.nn; base += DCU_NL) {
+    const int z = base + lane;
+    int numsucc = 0; int lens[4] = {0, 0, 0, 0};
+    if (z < c.nn) { int ns = w.n_nact[z], np = w.n_npred[z]; if (ns && (np != 1 || ns > 1)) numsucc = ns; }
+    uint32_t tot = 0; bool bad = false;
     DCU_NOUNROLL
-    for (int n = 0; n < c.nn; ++n) w.n_mark[n] = 0;
-    DCU_NOUNROLL
-    for (int z = 0; z < c.nn && !ovf; ++z) {
-      int numsucc = w.n_nact[z], numpred = w.n_npred[z];
-      if (!(numsucc && (numpred != 1 || numsucc > 1))) continue;
+    for (int i = 0; i < numsucc; ++i) {
+      int cur = w.n_snid[4 * z + i]; int len = 2; bool loop = (cur == z);
       DCU_NOUNROLL
-      for (int i = 0; i < numsucc; ++i) {
-        if (nrs >= c.cap.ST || slO + 2 > c.cap.SL) { ovf = true; break; }
-        int start = slO;
-        int ext = w.n_snid[4 * z + i];
-        ++stamp;
-        w.slinks[slO++] = (uint16_t)z; w.n_mark[z] = stamp;
-        w.slinks[slO++] = (uint16_t)ext; w.n_mark[ext] = stamp;
-        int len = 2; bool loop = (z == ext); int cur = ext;
-        DCU_NOUNROLL
-        while (!loop && w.n_nact[cur] == 1 && w.n_npred[cur] == 1) {
-          cur = w.n_snid[4 * cur];
-          if (slO >= c.cap.SL) { ovf = true; break; }
-          w.slinks[slO++] = (uint16_t)cur; ++len;
-          if (w.n_mark[cur] == stamp) loop = true; else w.n_mark[cur] = stamp;
-        }
-        if (ovf) break;
-        int last = cur;
-        if (loop && z != last) {
-          int j = 0;
-          DCU_NOUNROLL
-          while (w.slinks[start + j] != last) ++j;
-          j += 1;
-          int retract = len - j;
-          len -= retract; slO -= retract;
-        }
-        w.rs_off[nrs] = (uint16_t)start; w.rs_len[nrs] = (uint16_t)len; ++nrs;
+      while (!loop && w.n_nact[cur] == 1 && w.n_npred[cur] == 1) {
+        cur = w.n_snid[4 * cur]; ++len;
+        if (cur == z) loop = true;
+        if (len > c.nn + 1) { bad = true; break; }
       }
+      lens[i] = len; tot += (uint32_t)len;
     }
-    c.nrs = nrs; c.slO = slO;
-    if (ovf) c.overflow = 7;
+    if (ballot(bad)) { ovf = true; break; }
+    uint32_t it = scan_incl(tot, lane), ic = scan_incl((uint32_t)numsucc, lane);
+    int lo = slO + (int)(it - tot), so = nrs + (int)(ic - (uint32_t)numsucc);
+    int ttot = (int)bcast(it, DCU_NL - 1), tcnt = (int)bcast(ic, DCU_NL - 1);
+    if (nrs + tcnt > c.cap.ST || slO + ttot > c.cap.SL) { ovf = true; break; }
+    DCU_NOUNROLL
+    for (int i = 0; i < numsucc; ++i) {
+      int cur = w.n_snid[4 * z + i]; int o = lo;
+      w.slinks[o] = (uint16_t)z; w.slsym[o] = (uint8_t)(w.n_kmer[z] & 3); ++o;
+      w.slinks[o] = (uint16_t)cur; w.slsym[o] = (uint8_t)(w.n_kmer[cur] & 3); ++o;
+      DCU_NOUNROLL
+      for (int t = 2; t < lens[i]; ++t) { cur = w.n_snid[4 * cur]; w.slinks[o] = (uint16_t)cur; w.slsym[o] = (uint8_t)(w.n_kmer[cur] & 3); ++o; }
+      w.rs_off[so] = (uint16_t)lo; w.rs_len[so] = (uint16_t)lens[i]; ++so; lo = o;
+    }
+    nrs += tcnt; slO += ttot;
   }
-  c.nrs = bcast(c.nrs, 0); c.slO = bcast(c.slO, 0); c.overflow = bcast(c.overflow, 0);
+  c.nrs = nrs; c.slO = slO;
+  if (ovf) c.overflow = 7;
   wsync();
 }
 
@@ -848,7 +855,7 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
   for (int dir = 0; dir < 2; ++dir) {
     const uint16_t* so = dir ? w.ds_cO : w.ds_fO;
     const uint8_t* sb = dir ? w.ds_cB : w.ds_fB;
-    double* ow = dir ? w.sc_w : w.sf_w; double* owf = dir ? w.sc_wf : w.sf_wf; double* owl = dir ? w.sc_wl : w.sf_wl;
+    double* ow = dir ? w.sc_w : w.sf_w;
     uint32_t tot = dir ? run1 : run0;
     DCU_NOUNROLL
     for (uint32_t q = (uint32_t)lane; q < tot; q += DCU_NL) {
@@ -857,17 +864,15 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
       while (b - a > 1) { int mid = (a + b) >> 1; if (so[mid] <= q) a = mid; else b = mid; }
       int off = w.ds_off[a], L = w.ds_len[a];
       int p0 = (int)sb[a] + (int)(q - so[a]);
-      double sum = 0.0, wfirst = 0.0, wlast = 0.0; bool ok = true;
+      double sum = 0.0; bool ok = true;
       DCU_NOUNROLL
       for (int jj = 0; jj < L; ++jj) {
         int nj = dir == 0 ? w.slinks[off + jj] : w.slinks[off + L - 1 - jj];
         double wt = dir == 0 ? kw_fwd(c, nj, p0 + jj) : kw_rev(c, nj, p0 + jj);
         if (!(wt >= 1e-3)) { ok = false; break; }
         sum += wt;
-        if (jj == 0) wfirst = wt;
-        wlast = wt;
       }
-      ow[q] = ok ? sum : -1.0; owf[q] = wfirst; owl[q] = wlast;
+      ow[q] = ok ? sum : -1.0;
     }
   }
   wsync();
@@ -884,6 +889,11 @@ DCU_NOINL int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchRever
   int o = w.ds_cO[s] + d;
   return w.sc_w[o] >= 0.0 ? o : -1;
 }
+
+// weight of the first / last link of a stretch object (StretchFeasObject::wf / wl, :875-889), read back from the node tables
+DCU_FN double fwd_wf(const Ctx& c, int s, int p) { return kw_fwd(c, ds_first(c, s), p); }
+DCU_FN double fwd_wl(const Ctx& c, int s, int p) { return kw_fwd(c, ds_last(c, s), p + c.ws.ds_len[s] - 1); }
+DCU_FN double rev_wf(const Ctx& c, int s, int p) { return kw_rev(c, ds_last(c, s), p); }
 
 // computeStretchLinks / getReverseStretchLinkWeight (:3388-3480): link A -> B (B.first == A.last) kept iff
 // max over common reverse positions of w_B + (w_A - wf_A) >= 0.1; stored as (B,A), sorted; lanes over A
@@ -907,7 +917,7 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
         double wb = w.sc_w[co + d];
         if (!(wb >= 0.0)) continue;
         int oa = sfo_rev(c, A, cb + d + shift);
-        if (oa >= 0) { double lw = wb + (w.sc_w[oa] - w.sc_wf[oa]); weight = lw > weight ? lw : weight; }
+        if (oa >= 0) { double lw = wb + (w.sc_w[oa] - rev_wf(c, A, cb + d + shift)); weight = lw > weight ? lw : weight; }
       }
       if (weight >= 1e-1) { uint32_t t = a_add(cnt, 1); if ((int)t < c.cap.RL) w.rl[t] = ((uint32_t)B << 16) | (uint32_t)A; }
     }
@@ -1018,7 +1028,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
         int o = sfo_rev(c, s, rpos);
         if (o >= 0 && w.sc_w[o] >= 0.5) {
           int L = w.ds_len[s];
-          double nw = wt + (w.sc_w[o] - w.sc_wf[o]);
+          double nw = wt + (w.sc_w[o] - rev_wf(c, s, rpos));
           int nid = rp_new(c, nrp, nw, (uint32_t)id, w.n_kmer[ds_first(c, s)], s, rpos + L - 1, rlen + 1, bl + L - 1);
           if (nid < 0) return;
           if (nq >= c.cap.RP) { c.overflow = 13; return; }
@@ -1048,7 +1058,7 @@ DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScor
   int lpos = w.fp_pos[P] - (w.ds_len[ls] - 1);
   int o = sfo_fwd(c, ls, lpos);
   double s = w.fp_w[P] + w.rp_w[rpid];
-  return o >= 0 ? (s - w.sf_wl[o]) : s;
+  return o >= 0 ? (s - fwd_wl(c, ls, lpos)) : s;
 }
 // best / next-best reverse path of an interval in (weight, sorted index) order (:3499-3534)
 DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
@@ -1080,7 +1090,7 @@ DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath 
   int L = w.ds_len[s];
   double wt; int bl;
   if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sf_w[o] : 0.0; }
-  else { bl = w.fp_baselen[P] + L - 1; wt = w.fp_w[P]; if (o >= 0) wt += w.sf_w[o] - w.sf_wf[o]; }
+  else { bl = w.fp_baselen[P] + L - 1; wt = w.fp_w[P]; if (o >= 0) wt += w.sf_w[o] - fwd_wf(c, s, ppos); }
   if (nfp >= c.cap.FP) { c.overflow = 14; return -1; }
   int id = nfp++;
   w.fp_w[id] = wt; w.fp_parent[id] = P < 0 ? IDX_NONE : (uint32_t)P; w.fp_stretch[id] = (uint16_t)s;
@@ -1101,13 +1111,13 @@ DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
   for (int t = sp - 1; t >= 0; --t) {
     int s = stack[t], off = w.ds_off[s], L = w.ds_len[s];
     DCU_NOUNROLL
-    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.n_kmer[w.slinks[off + j]] & 3]; }
+    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym[off + j]]; }
   }
   DCU_NOUNROLL
   for (int q = rpid; w.rp_len[q] > 0; q = (int)w.rp_parent[q]) {
     int s = w.rp_stretch[q], off = w.ds_off[s], L = w.ds_len[s];
     DCU_NOUNROLL
-    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.n_kmer[w.slinks[off + j]] & 3]; }
+    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym[off + j]]; }
   }
   return o;
 }
@@ -1156,7 +1166,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
           double ew = o >= 0 ? w.sf_w[o] : 0.0;
           if (ew > 0.1) {
             int L = w.ds_len[s];
-            double nwt = w.fp_w[P] + (w.sf_w[o] - w.sf_wf[o]);
+            double nwt = w.fp_w[P] + (w.sf_w[o] - fwd_wf(c, s, w.fp_pos[P]));
             if (nwt > 0.1 && (w.fp_pos[P] + L - 1 + K) <= lmax) {
               int id = fp_extend(c, nfp, P, s);
               if (id < 0) return;
