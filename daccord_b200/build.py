@@ -26,11 +26,15 @@ def build(force=False, verbose=False):
         env = dict(os.environ)
         env["PATH"] = "/usr/bin:" + env.get("PATH", "")      # system g++ (the /opt/gcc wrapper lacks libgomp.spec)
         subprocess.check_call(cmd, env=env)
-    host_src = os.path.join(csrc, "host", "hostlib.cpp")
+    host_src = os.path.join(csrc, "host", "hostlib.cpp")  # noqa
     host_deps = [os.path.join(csrc, "host", f) for f in os.listdir(os.path.join(csrc, "host"))] + [os.path.join(ROOT, "include", "daccord_b200.h")]
     if force or _newer(HOST_LIB, host_deps):
         subprocess.check_call(["/usr/bin/g++", "-O3", "-g", "-std=c++17", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
                                "-o", HOST_LIB, host_src])
+    cli = os.path.join(BUILD, "daccord")
+    if force or _newer(cli, host_deps + [LIB]):
+        subprocess.check_call(["/usr/bin/g++", "-O3", "-g", "-std=c++17", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-o", cli,
+                               os.path.join(csrc, "host", "daccord_main.cpp"), "-L" + BUILD, "-ldaccord_b200", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

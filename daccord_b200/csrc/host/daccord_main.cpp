@@ -1,0 +1,171 @@
+// daccord_main.cpp -- `daccord [options] reads.las reads.db` : drop-in command line for the window-consensus path
+// of gt1/daccord (reference src/daccord.cpp:185-241 help text, :1061-1305 option handling, :2107-2540 main loop),
+// with the per-window consensus running on a B200 through the C ABI in include/daccord_b200.h.
+// Host side (this file + pile.hpp / vote.hpp): LAS + Dazzler-DB input, overlap selection, trace reconstruction,
+// window/slice extraction, pile vote, FastA on stdout, progress on stderr.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <fstream>
+#include <iostream>
+#include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "las.hpp"
+#include "dazzdb.hpp"
+#include "pile.hpp"
+#include "vote.hpp"
+#include "../../../include/daccord_b200.h"
+
+using namespace dhost;
+
+static const char* HELP =
+    "usage: daccord [options] reads.las reads.db\n"
+    "\t-t: number of host threads (default: all)\n\t-w: window size (default 40)\n\t-a: advance size (default 10)\n"
+    "\t-d: max depth (default unlimited)\n\t-f: produce full sequences\n\t-V: verbosity\n\t-I: read interval i,j (inclusive)\n"
+    "\t-J: reads part i,j\n\t-E: error profile file name (default input.las.eprof)\n\t-m: minimum window coverage (default 3)\n"
+    "\t-e: maximum window error (default unlimited)\n\t-l: minimum length of output (default 0)\n"
+    "\t--minfilterfreq: minimum k-mer filter frequency (default 0)\n\t--maxfilterfreq: maximum k-mer filter frequency (default 2)\n"
+    "\t-D: maximum number of alignments considered per read (default 5000)\n\t-k: kmer size lo[,hi] (default 8)\n"
+    "\t--device: CUDA device ordinal (default 0)\n\t--batchreads: A-reads per GPU batch (default 256)\n";
+
+struct Args { std::map<std::string, std::string> opt; std::vector<std::string> pos; };
+static bool parse_args(int argc, char** argv, Args& A) {
+  static const char* longs[] = {"minfilterfreq", "maxfilterfreq", "vard", "eprofonly", "deepprofileonly", "keepeprof", "device", "batchreads", "help", "version", nullptr};
+  int i = 1;
+  for (; i < argc; ++i) {
+    std::string s = argv[i];
+    if (s.size() >= 2 && s[0] == '-' && s[1] == '-') {
+      std::string body = s.substr(2), key, val; bool found = false;
+      for (int j = 0; longs[j]; ++j) { size_t n = strlen(longs[j]); if (body.compare(0, n, longs[j]) == 0 && n > key.size()) { key = longs[j]; found = true; } }
+      if (!found) { fprintf(stderr, "[E] unknown option %s\n", s.c_str()); return false; }
+      val = body.substr(key.size());
+      if (!val.empty() && val[0] == '=') val = val.substr(1);
+      A.opt[key] = val;
+    } else if (s.size() >= 2 && s[0] == '-' && !isdigit((unsigned char)s[1])) {
+      A.opt[std::string(1, s[1])] = s.substr(2);          // libmaus2 ArgParser style: value attached (-w40)
+    } else break;                                          // options must precede positionals (README.md:99)
+  }
+  for (; i < argc; ++i) A.pos.push_back(argv[i]);
+  return true;
+}
+static bool parse_pair(const std::string& s, int64_t& a, int64_t& b) { return sscanf(s.c_str(), "%ld,%ld", &a, &b) == 2; }
+
+int main(int argc, char** argv) {
+  Args A;
+  if (!parse_args(argc, argv, A)) return EXIT_FAILURE;
+  if (A.opt.count("h") || A.opt.count("help") || A.pos.size() < 2) { fprintf(stderr, "%s", HELP); return A.pos.size() < 2 && !A.opt.count("h") && !A.opt.count("help") ? EXIT_FAILURE : EXIT_SUCCESS; }
+  auto getu = [&](const char* k, uint64_t def) -> uint64_t { auto it = A.opt.find(k); return (it == A.opt.end() || it->second.empty()) ? def : strtoull(it->second.c_str(), nullptr, 10); };
+  const std::string lasfn = A.pos[0], dbfn = A.pos[1];
+  if (A.pos.size() > 2 && A.pos[2] != dbfn) { fprintf(stderr, "[E] asymmetric (DB1 != DB2) input is not supported by this build\n"); return EXIT_FAILURE; }
+  if (A.opt.count("eprofonly") || A.opt.count("deepprofileonly")) { fprintf(stderr, "[E] error-profile estimation is not part of this build; supply a profile with -E (or <las>.eprof)\n"); return EXIT_FAILURE; }
+  if (getu("vard", 0)) { fprintf(stderr, "[E] --vard is not supported by this build\n"); return EXIT_FAILURE; }
+  dcu_params prm; memset(&prm, 0, sizeof(prm));
+  prm.w = (uint32_t)getu("w", 40); const uint32_t advance = (uint32_t)getu("a", 10);
+  prm.k_lo = prm.k_hi = 8;
+  if (A.opt.count("k")) { unsigned lo = 0, hi = 0; int n = sscanf(A.opt["k"].c_str(), "%u,%u", &lo, &hi); if (n < 1) { fprintf(stderr, "[E] unable to parse k argument %s\n", A.opt["k"].c_str()); return EXIT_FAILURE; } prm.k_lo = lo; prm.k_hi = n == 2 ? hi : lo; }
+  prm.min_cov = (uint32_t)getu("m", 3); prm.max_err = getu("e", UINT64_MAX);
+  prm.min_ff = (int32_t)getu("minfilterfreq", 0); prm.max_ff = (int32_t)getu("maxfilterfreq", 2);
+  const uint64_t maxalign = getu("d", UINT64_MAX), maxinput = getu("D", 5000), minlen = getu("l", 0);
+  const bool producefull = A.opt.count("f") != 0;
+  int nthreads = (int)getu("t", 0);
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  nthreads = 1;
+#endif
+  const int device = (int)getu("device", 0); const uint64_t batchreads = getu("batchreads", 256);
+  auto t_start = std::chrono::steady_clock::now();
+  try {
+    PackedDB db; LasData las;
+    fprintf(stderr, "[V] loading %s ...", dbfn.c_str()); read_dazzdb(dbfn, db); fprintf(stderr, "done.\n");
+    fprintf(stderr, "[V] loading %s ...", lasfn.c_str()); read_las(lasfn, las); las.build_index(db.rlen.size()); fprintf(stderr, "done.\n");
+    // read range: -J i,j or -I i,j (inclusive) (reference src/daccord.cpp:1116-1227)
+    int64_t minaread = 0, maxaread = (int64_t)db.rlen.size() - 1;
+    if (!las.ovl.empty()) { minaread = las.ovl.front().aread; maxaread = las.ovl.back().aread; } else maxaread = -1;
+    if (A.opt.count("J")) {
+      int64_t Icnt, Idiv; if (!parse_pair(A.opt["J"], Icnt, Idiv)) { fprintf(stderr, "[E] unable to parse %s\n", A.opt["J"].c_str()); return EXIT_FAILURE; }
+      int64_t top = maxaread + 1, span = top > minaread ? top - minaread : 0;
+      if (span && !Idiv) { fprintf(stderr, "[E] denominator of J argument cannot be zero\n"); return EXIT_FAILURE; }
+      if (top > minaread) { int64_t part = Idiv ? (span + Idiv - 1) / Idiv : 0; int64_t lo = std::min(minaread + Icnt * part, top), hi = std::min(lo + part, top); if (hi > lo) { minaread = lo; maxaread = hi - 1; } else { minaread = 0; maxaread = -1; } }
+    } else if (A.opt.count("I")) {
+      int64_t lo, hi; if (!parse_pair(A.opt["I"], lo, hi)) { fprintf(stderr, "[E] unable to parse %s\n", A.opt["I"].c_str()); return EXIT_FAILURE; }
+      minaread = std::max(lo, minaread); maxaread = std::min(hi, maxaread);
+    }
+    const int64_t toparead = maxaread >= 0 ? maxaread + 1 : maxaread;
+    fprintf(stderr, "[V] minaread=%ld toparead=%ld\n", (long)minaread, (long)toparead);
+    fprintf(stderr, "[V] minfilterfreq=%d maxfilterfreq=%d\n", prm.min_ff, prm.max_ff);
+    // error profile (reference: <las>.eprof or -E, src/daccord.cpp:1652-1880). This build reads a text profile:
+    // "matches mismatches insertions deletions"
+    std::string eproffn = A.opt.count("E") ? A.opt["E"] : lasfn + ".eprof";
+    uint64_t em = 0, es = 0, ei = 0, ed = 0;
+    { std::ifstream ef(eproffn); if (!(ef >> em >> es >> ei >> ed)) { fprintf(stderr, "[E] cannot read error profile %s (this build does not estimate it; see INTEGRATION.md)\n", eproffn.c_str()); return EXIT_FAILURE; } }
+    const uint64_t len = em + es + ed, numerr = es + ed + ei;
+    prm.p_i = (double)ei / (double)len; prm.p_d = (double)ed / (double)len; prm.est_cor = 1.0 - (double)numerr / (double)len;
+    fprintf(stderr, "error estimates\nerate=%g\ncor=%g\nins=%g\ndel=%g\n", (double)numerr / len, prm.est_cor, prm.p_i, prm.p_d);
+    fprintf(stderr, "[V] using kmer range [%u,%u]\n", prm.k_lo, prm.k_hi);
+    dcu_ctx* ctx = nullptr;
+    int rc = dcu_create(&prm, device, &ctx);
+    if (rc) { fprintf(stderr, "[E] dcu_create: %s %s\n", dcu_strerror(rc), ctx ? dcu_last_error(ctx) : ""); return EXIT_FAILURE; }
+    rc = dcu_set_reads(ctx, db.bytes.data(), db.bytes.size());
+    if (rc) { fprintf(stderr, "[E] dcu_set_reads: %s %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+    PileParams PP; PP.w = prm.w; PP.a = advance; PP.maxalign = maxalign; PP.maxinput = maxinput;
+    VoteParams VP; VP.producefull = producefull; VP.minlen = minlen;
+    uint64_t wellcounter = 0, totwin = 0, totok = 0;
+    std::vector<dcu_result> res; std::vector<uint8_t> cons, ops;
+    for (int64_t b0 = minaread; b0 < toparead; b0 += (int64_t)batchreads) {
+      const int64_t b1 = std::min<int64_t>(b0 + (int64_t)batchreads, toparead), nr = b1 - b0;
+      std::vector<std::vector<dcu_window>> wv(nr); std::vector<std::vector<dcu_slice>> sv(nr);
+      std::string perr;
+#pragma omp parallel num_threads(nthreads)
+      {
+        ReadPiler RP(db, las, PP);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t i = 0; i < nr; ++i) {
+          try { RP.pile((uint64_t)(b0 + i), wv[i], sv[i]); }
+          catch (std::exception& e) {       // per-read failures are logged and skipped (reference src/daccord.cpp:2466-2478)
+#pragma omp critical
+            { fprintf(stderr, "[E] read %ld: %s\n", (long)(b0 + i), e.what()); }
+            wv[i].clear(); sv[i].clear();
+          }
+        }
+      }
+      std::vector<dcu_window> win; std::vector<dcu_slice> sl; std::vector<uint64_t> first(nr + 1, 0);
+      for (int64_t i = 0; i < nr; ++i) { first[i] = win.size(); uint32_t base = (uint32_t)sl.size(); for (auto x : wv[i]) { x.slice_begin += base; win.push_back(x); } sl.insert(sl.end(), sv[i].begin(), sv[i].end()); }
+      first[nr] = win.size();
+      res.resize(win.size()); cons.resize(win.size() * DCU_CONS_STRIDE); ops.resize(win.size() * DCU_OPS_STRIDE);
+      rc = dcu_run(ctx, win.data(), win.size(), sl.data(), sl.size(), res.data(), cons.data(), ops.data());
+      if (rc) { fprintf(stderr, "[E] dcu_run: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+      std::vector<std::string> parts(nr); std::vector<uint64_t> cnt(nr, 0);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+      for (int64_t i = 0; i < nr; ++i) {
+        if (first[i] == first[i + 1]) continue;
+        std::vector<PileElement> PV;
+        for (uint64_t wi = first[i]; wi < first[i + 1]; ++wi) if (res[wi].status == DCU_WIN_OK) place_window(win[wi], res[wi], cons.data() + wi * DCU_CONS_STRIDE, ops.data() + wi * DCU_OPS_STRIDE, PV);
+        std::string ab;
+        if (producefull) { std::vector<uint8_t> codes; decode_read(db, (uint32_t)(b0 + i), false, codes); ab.resize(codes.size()); for (size_t q = 0; q < codes.size(); ++q) ab[q] = "ACGT"[codes[q]]; }
+        uint64_t c0 = 0; vote_read(b0 + i, PV, VP, ab, c0, parts[i]); cnt[i] = c0;
+      }
+      for (int64_t i = 0; i < nr; ++i) {        // release in A-read order, numbering sequences like -t1
+        const std::string& s = parts[i]; size_t p = 0;
+        while (p < s.size()) {
+          size_t e = s.find('\n', p); if (e == std::string::npos) e = s.size();
+          if (s[p] == '>') { size_t s1 = s.find('/', p), s2 = s.find('/', s1 + 1); fwrite(s.data() + p, 1, s1 + 1 - p, stdout); fprintf(stdout, "%lu", (unsigned long)wellcounter++); fwrite(s.data() + s2, 1, e - s2, stdout); }
+          else fwrite(s.data() + p, 1, e - p, stdout);
+          fputc('\n', stdout); p = e + 1;
+        }
+      }
+      for (auto& r : res) { totwin += r.status != DCU_WIN_SKIPPED; totok += r.status == DCU_WIN_OK; }
+      fprintf(stderr, "[V] reads [%ld,%ld) windows %zu\n", (long)b0, (long)b1, win.size());
+    }
+    fflush(stdout);
+    dcu_destroy(ctx);
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    fprintf(stderr, "[V] processed in time %.3fs, %lu windows attempted, %lu consensus\n", secs, (unsigned long)totwin, (unsigned long)totok);
+  } catch (std::exception& e) { std::cerr << e.what() << std::endl; return EXIT_FAILURE; }
+  return EXIT_SUCCESS;
+}

@@ -49,7 +49,7 @@ inline void write_dazzdb(const std::string& dbfn, const PackedDB& db) {
   fclose(f);
   f = fopen(hidden(dbfn, ".bps").c_str(), "wb");
   if (!f) throw std::runtime_error("cannot write bps");
-  fwrite(db.bytes.data(), 1, db.bytes.size(), f);
+  fwrite(db.bytes.data(), 1, db.bytes.size() >= 16 ? db.bytes.size() - 16 : 0, f);   // the in-memory copy carries 16 padding bytes
   fclose(f);
 }
 inline void read_dazzdb(const std::string& dbfn, PackedDB& db) {

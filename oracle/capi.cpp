@@ -84,3 +84,45 @@ int64_t oracle_get_tables(const dcu_params* prm, int which, double* out, int64_t
 }
 
 }  // extern "C"
+
+// ---- read-level driver: .las + Dazzler DB in, FastA text out (the daccord CLI surface on the CPU)
+#include "pipeline.hpp"
+extern "C" {
+// processes A-reads [first, last] (inclusive, reference -I semantics); returns malloc'ed FastA text
+char* oracle_daccord_files(const dcu_params* prm, uint32_t advance, uint64_t maxalign, uint64_t maxinput, int producefull, uint64_t minlen,
+                           const char* lasfn, const char* dbfn, int64_t first, int64_t last, int nthreads, uint64_t* outlen, uint64_t* stats) {
+  try {
+    Params P = to_params(prm); P.a = advance; P.maxalign = maxalign; P.maxinput = maxinput; P.producefull = producefull != 0; P.minlen = minlen;
+    Tables T(P);
+    ReadDB DB; loadDB(dbfn, DB);
+    LasFile L; loadLas(lasfn, L, DB.reads.size());
+    if (first < 0) first = 0;
+    if (last < 0 || last >= (int64_t)DB.reads.size()) last = (int64_t)DB.reads.size() - 1;
+    const int64_t nr = last >= first ? last - first + 1 : 0;
+    std::vector<std::string> parts(nr);
+    std::vector<ReadStats> st(nr);
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+      ReadHandler H(T, L, DB);
+#pragma omp for schedule(dynamic, 1)
+      for (int64_t i = 0; i < nr; ++i) { uint64_t c = 0; st[i] = H.handle((uint64_t)(first + i), c, parts[i]); }
+    }
+    std::string out; uint64_t counter = 0;
+    uint64_t s0 = 0, s1 = 0, s2 = 0;
+    for (int64_t i = 0; i < nr; ++i) {
+      s0 += st[i].windows; s1 += st[i].attempted; s2 += st[i].ok;
+      std::istringstream is(parts[i]); std::string line;
+      while (std::getline(is, line)) {
+        if (!line.empty() && line[0] == '>') { size_t a = line.find('/'), b = line.find('/', a + 1); line = line.substr(0, a + 1) + std::to_string(counter++) + line.substr(b); }
+        out += line; out.push_back('\n');
+      }
+    }
+    if (stats) { stats[0] = s0; stats[1] = s1; stats[2] = s2; }
+    char* buf = (char*)malloc(out.size() + 1); memcpy(buf, out.data(), out.size()); buf[out.size()] = 0;
+    *outlen = out.size();
+    return buf;
+  } catch (std::exception& e) { fprintf(stderr, "[oracle] %s\n", e.what()); return nullptr; }
+}
+void oracle_free(void* p) { free(p); }
+}
