@@ -263,7 +263,13 @@ int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
     if (rc) return rc;
     CK(cudaMemcpyAsync(cnt, ctx->dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (cnt[3]) { char b[128]; snprintf(b, sizeof b, "%u windows exceeded the large-workspace capacities", cnt[3]); ctx->err = b; ret = DCU_ERR_OVERFLOW; }
+    if (cnt[3]) {
+      uint32_t wi = 0; dcu::Result r; memset(&r, 0, sizeof(r));
+      CK(cudaMemcpy(&wi, ctx->dovf[1].p, sizeof(wi), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&r, ctx->dres.p + wi, sizeof(r), cudaMemcpyDeviceToHost));
+      char b[192]; snprintf(b, sizeof b, "%u windows exceeded the large-workspace capacities (first: window %u, capacity code %u)", cnt[3], wi, r.err);
+      ctx->err = b; ret = DCU_ERR_OVERFLOW;
+    }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaEventSynchronize(ctx->ev1));

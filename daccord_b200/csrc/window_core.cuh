@@ -160,7 +160,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(n_plow, uint8_t, c.NN) X(n_phigh, uint8_t, c.NN) X(n_cplow, uint8_t, c.NN) X(n_cphigh, uint8_t, c.NN)  \
   X(n_nsucc, uint8_t, c.NN) X(n_nact, uint8_t, c.NN) X(n_npred, uint8_t, c.NN)                             \
   X(n_sfreq, uint16_t, 4 * c.NN) X(n_snid, uint16_t, 4 * c.NN) X(n_mark, uint16_t, c.NN)                   \
-  X(ipos, uint8_t, c.NI) X(irpos, uint8_t, c.NI)                                                           \
+  X(ipos, uint8_t, c.NI + c.EX) X(irpos, uint8_t, c.NI + c.EX)                                                           \
   X(ex_kmer, uint32_t, c.EX) X(ex_pos, uint8_t, c.EX) X(ex_rpos, uint8_t, c.EX)                            \
   X(ll_kmer, uint32_t, c.S) X(ll_cnt, uint16_t, c.S) X(fl_kmer, uint32_t, c.S) X(fl_cnt, uint16_t, c.S)    \
   X(fl_nid, uint16_t, c.S)                                                                                 \
@@ -450,7 +450,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   if (lane == 0) { uint32_t o = 0; for (int n = 0; n < nn; ++n) { w.n_ioff[n] = o; o += w.n_freq[n]; } c.ni = (int)o; }
   c.ni = bcast(c.ni, 0);
   wsync();
-  if (c.ni > c.cap.NI) { c.overflow = 4; return; }
+  if (c.ni > c.cap.NI + c.cap.EX) { c.overflow = 4; return; }
   DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
     int len = seqlen(c, j);
@@ -1037,19 +1037,24 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
       }
     }
   }
-  // sort accepted paths by (front, baselen), ties in acceptance order (:3742, convention C7)
+}
+// sort accepted reverse paths by (front, baselen), ties in acceptance order (:3742, convention C7); all lanes
+DCU_BIG void sort_reverse_paths(Ctx& c, int narp, int lane) {
+  const WS& w = c.ws;
+  if (narp <= 1) return;
+  unsigned long long* key = (unsigned long long*)w.sq_w;      // the score-interval heap is not in use yet
+  int P = 32; while (P < narp) P <<= 1;
   DCU_NOUNROLL
-  for (int a = 1; a < narp; ++a) {
-    uint32_t id = w.arp[a]; uint32_t fr = w.rp_front[id]; int bl = w.rp_baselen[id]; int b = a;
-    DCU_NOUNROLL
-    while (b > 0) {
-      uint32_t pid = w.arp[b - 1];
-      bool greater = w.rp_front[pid] != fr ? (w.rp_front[pid] > fr) : (w.rp_baselen[pid] > bl);
-      if (!greater) break;
-      w.arp[b] = pid; --b;
-    }
-    w.arp[b] = id;
+  for (int i = lane; i < P; i += DCU_NL) {
+    unsigned long long k = ~0ull;
+    if (i < narp) { uint32_t id = w.arp[i]; k = ((((unsigned long long)w.rp_front[id] << 8) | (unsigned long long)(w.rp_baselen[id] & 0xFF)) << 16) | (unsigned long long)i; w.rq_id[i] = id; }
+    key[i] = k;
   }
+  wsync();
+  warp_sort_u64(key, P, lane);
+  DCU_NOUNROLL
+  for (int i = lane; i < narp; i += DCU_NL) w.arp[i] = w.rq_id[(int)(key[i] & 0xFFFF)];
+  wsync();
 }
 
 DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScore (:3482-3497)
@@ -1230,11 +1235,13 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
       if (c.overflow) return 0;
       stretch_links(c, lane);
       if (c.overflow) return 0;
-      if (lane == 0) {
-        int narp = 0;
-        reverse_paths(c, L, lmax, narp);
-        if (!c.overflow) search_pair(c, F, lmin, lmax, narp, ncdh, freeslots);
-      }
+      int narp = 0;
+      if (lane == 0) reverse_paths(c, L, lmax, narp);
+      c.overflow = bcast(c.overflow, 0); narp = bcast(narp, 0);
+      wsync();
+      if (c.overflow) return 0;
+      sort_reverse_paths(c, narp, lane);
+      if (lane == 0) search_pair(c, F, lmin, lmax, narp, ncdh, freeslots);
       c.overflow = bcast(c.overflow, 0);
       wsync();
       if (c.overflow) return 0;
