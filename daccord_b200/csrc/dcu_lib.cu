@@ -27,7 +27,7 @@ struct KArgs {
   dcu::Result* res; uint8_t* cons; uint8_t* ops;
   uint8_t* slabs;                      // [total warps][L.bytes]
   const uint32_t* todo;                // window indices to run (nullptr: 0..n-1)
-  uint32_t n;
+  uint32_t n; uint32_t vs_words;       // vs_words != 0: stage the VS table in dynamic shared memory
   unsigned int* ticket;                // work counter
   unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this tier
 };
@@ -35,8 +35,10 @@ struct KArgs {
 __global__ void __launch_bounds__(WPB * 32, 8) dcu_window_kernel(const __grid_constant__ KArgs a) {
   __shared__ dcu::WS s_ws[WPB];
   __shared__ dcu::Caps s_cap; __shared__ dcu::Tables s_T; __shared__ dcu::Params s_P;
+  extern __shared__ unsigned long long s_vs[];          // block-shared copy of the transposed VS table (when it fits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_cap = a.cap; s_T = a.T; s_P = a.P; }
+  if (a.vs_words) for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = a.T.VSq[i];
+  if (threadIdx.x == 0) { s_cap = a.cap; s_T = a.T; s_P = a.P; if (a.vs_words) s_T.VSq = s_vs; }
   if (lane == 0) {
     size_t gw = (size_t)blockIdx.x * WPB + warp;
     dcu::bind_ws(s_ws[warp], a.slabs + gw * (size_t)a.L.bytes, a.L);
@@ -237,7 +239,10 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   a.packed = ctx->dpacked; a.sl = ctx->dsl.p; a.win = ctx->dwin.p; a.res = ctx->dres.p; a.cons = ctx->dcons.p; a.ops = ctx->dops.p;
   a.slabs = ctx->dslab[tier].p; a.todo = todo; a.n = n;
   a.ticket = ctx->dcnt.p + 2 * tier; a.ovf_cnt = ctx->dcnt.p + 2 * tier + 1; a.ovf_list = ctx->dovf[tier].p;
-  dcu_window_kernel<<<grid, WPB * 32, 0, ctx->stream>>>(a);
+  size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
+  if (vs_bytes > 24 * 1024) vs_bytes = 0;            // keeps 8 blocks / SM resident; larger tables are read from L2
+  a.vs_words = (uint32_t)(vs_bytes / 8);
+  dcu_window_kernel<<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;
   return DCU_OK;
@@ -308,7 +313,7 @@ int64_t dcu_get_tables(dcu_ctx* ctx, int which, double* out, int64_t cap) {
   if (!ctx) return -1;
   std::vector<double> v; auto& H = ctx->HT;
   if (which == 0) v = H.DPn; else if (which == 1) v = H.DPsq;
-  else if (which == 2) for (auto x : H.VSq) v.push_back((double)x);
+  else if (which == 2) { for (int l = 0; l < H.NP; ++l) for (int q = 0; q < H.MS; ++q) v.push_back((double)H.VSq[(size_t)q * H.NP + l]); }
   else if (which == 3) for (int i = 0; i < H.MS; ++i) { v.push_back(H.suplo[i]); v.push_back(H.suphi[i]); }
   else if (which == 4) for (auto x : H.klim) v.push_back((double)x);
   else if (which == 5) { v.push_back(H.NP); v.push_back(H.MS); v.push_back(H.KLIMN); }

@@ -16,7 +16,7 @@ namespace dcu_host {
 struct HostTables {
   int NP = 0, MS = 0, KLIMN = 0, nk = 0;
   std::vector<double> DPn, DPsq;                 // [NP][MS]
-  std::vector<unsigned long long> VSq;           // [NP][MS]
+  std::vector<unsigned long long> VSq;           // [MS+1][NP] transposed, last row zero (guard for read positions >= MS)
   std::vector<uint16_t> suplo, suphi;            // [MS]
   std::vector<unsigned long long> klim;          // [nk][KLIMN]
 };
@@ -79,7 +79,7 @@ inline void build_tables(int w, double p_i, double p_d, double est_cor, int k_lo
   int MS = 0;
   for (int l = 0; l < NP; ++l) MS = std::max(MS, first[l] + (int)rows[l].size());
   T.NP = NP; T.MS = MS;
-  T.DPn.assign((size_t)NP * MS, 0.0); T.DPsq.assign((size_t)NP * MS, 0.0); T.VSq.assign((size_t)NP * MS, 0ull);
+  T.DPn.assign((size_t)NP * MS, 0.0); T.DPsq.assign((size_t)NP * MS, 0.0); T.VSq.assign((size_t)(MS + 1) * NP, 0ull);
   // column sums over true positions, ascending l (OffsetLikely.hpp:68-77)
   std::vector<double> colsum(MS, 0.0);
   for (int pos = 0; pos < MS; ++pos) {
@@ -96,7 +96,7 @@ inline void build_tables(int w, double p_i, double p_d, double est_cor, int k_lo
       T.DPn[(size_t)l * MS + pos] = rows[l][o] / colsum[pos];
       double v = rows[l][o] * cn;
       T.DPsq[(size_t)l * MS + pos] = v;
-      T.VSq[(size_t)l * MS + pos] = (unsigned long long)(4294967296.0 * v);
+      T.VSq[(size_t)pos * NP + l] = (unsigned long long)(4294967296.0 * v);
     }
   }
   // support ranges per read position (OffsetLikely.hpp:81-93)

@@ -98,7 +98,7 @@ enum { HEAPK = 12, CDH_N = 16, MAXCAND = 64 };
 struct Tables {
   const double* DPn;               // [NP][MS] DPnorm, zero padded           (OffsetLikely.hpp:75-79)
   const double* DPsq;              // [NP][MS] DPnormSquare.V, zero padded   (OffsetLikely.hpp:96-98)
-  const unsigned long long* VSq;   // [NP][MS] floor(2^32 * DPnormSquare.V)  (DotProduct.hpp:54-60)
+  const unsigned long long* VSq;   // [MS+1][NP] transposed floor(2^32 * DPnormSquare.V), row MS all zero  (DotProduct.hpp:54-60)
   const uint16_t* suplo;           // [MS] Vsupport[i].first
   const uint16_t* suphi;           // [MS] Vsupport[i].second
   const unsigned long long* klim;  // [nk][KLIMN] KmerLimit::Vlim per k     (DebruijnGraph.hpp:28-75)
@@ -118,7 +118,7 @@ struct Result { uint8_t status, k; int8_t ff; uint8_t clen; uint32_t err; uint16
 // one warp's workspace: pointers into its slab (all arrays SoA)
 struct WS {
   uint8_t* bases; uint16_t* soff; uint16_t* lenhist;
-  uint32_t* hkey; uint32_t* hcnt; uint16_t* hnid; uint32_t* occ; uint32_t* hstate;   // hstate[0] = #occupied slots, hstate[1] = table initialised
+  uint32_t* hkey; uint32_t* hcnt; uint16_t* hnid; uint32_t* occ; uint32_t* hstate; uint32_t* islot; uint8_t *praw, *rraw; uint16_t *koff, *choff; uint32_t* lastk; uint32_t* ts_k; uint16_t *ts_c, *ts_n;   // hstate[0] = #occupied slots, hstate[1] = table initialised
   uint32_t* n_kmer; uint16_t* n_freq; uint32_t* n_ioff; uint32_t* n_fill;
   uint8_t *n_plow, *n_phigh, *n_cplow, *n_cphigh, *n_nsucc, *n_nact, *n_npred;
   uint16_t* n_sfreq; uint16_t* n_snid; uint16_t* n_mark;
@@ -155,7 +155,9 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
 #define DCU_WS_FIELDS(X)                                                                                  \
   X(bases, uint8_t, c.B) X(soff, uint16_t, c.S + 1) X(lenhist, uint16_t, 256)                              \
   X(hkey, uint32_t, c.H) X(hcnt, uint32_t, c.H) X(hnid, uint16_t, c.H) X(occ, uint32_t, c.NI + c.EX)         \
-  X(hstate, uint32_t, 4)                                                                                   \
+  X(hstate, uint32_t, 4) X(islot, uint32_t, c.NI) X(praw, uint8_t, c.NI) X(rraw, uint8_t, c.NI)              \
+  X(koff, uint16_t, c.S + 1) X(choff, uint16_t, c.S + 1) X(lastk, uint32_t, c.S)                            \
+  X(ts_k, uint32_t, c.S) X(ts_c, uint16_t, c.S) X(ts_n, uint16_t, c.S)                                      \
   X(n_kmer, uint32_t, c.NN) X(n_freq, uint16_t, c.NN) X(n_ioff, uint32_t, c.NN) X(n_fill, uint32_t, c.NN)  \
   X(n_plow, uint8_t, c.NN) X(n_phigh, uint8_t, c.NN) X(n_cplow, uint8_t, c.NN) X(n_cphigh, uint8_t, c.NN)  \
   X(n_nsucc, uint8_t, c.NN) X(n_nact, uint8_t, c.NN) X(n_npred, uint8_t, c.NN)                             \
@@ -240,11 +242,11 @@ DCU_FN int sup_hi(const Ctx& c, int pos) { return pos < c.T.MS ? (int)ldg(c.T.su
 // positional weight of node n at true position p (DebruijnGraph.hpp:3826-3904, fixed point per SURVEY D7)
 DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
   const uint8_t* ip = (rev ? c.ws.irpos : c.ws.ipos) + c.ws.n_ioff[n];
-  const unsigned long long* row = c.T.VSq + (size_t)p * c.T.MS;
+  const unsigned long long* col = c.T.VSq + p;
   int f = c.ws.n_freq[n];
   unsigned long long u = 0;
   DCU_NOUNROLL
-  for (int t = 0; t < f; ++t) { int pos = ip[t]; if (pos < c.T.MS) u += ldg(row + pos); }
+  for (int t = 0; t < f; ++t) { int pos = ip[t]; pos = pos < c.T.MS ? pos : c.T.MS; u += col[(size_t)pos * c.T.NP]; }
   return (double)u / 4294967296.0;
 }
 
@@ -352,9 +354,26 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
 }
 
 // ------------------------------------------------------------------ k-mer hash build (replaces setupPreNodes :2018-2304)
+// sort a short (count, kmer[, node]) list descending by (count, kmer) -- std::greater on pairs (:1297-1301, :1384-1388);
+// k-mers are distinct, so the rank of an entry is the number of larger entries: lanes over entries
+DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, int n, int lane) {
+  const WS& w = c.ws;
+  DCU_NOUNROLL
+  for (int e = lane; e < n; e += DCU_NL) {
+    uint32_t k = km[e]; uint16_t cc = cn[e]; int r = 0;
+    DCU_NOUNROLL
+    for (int i = 0; i < n; ++i) r += (cn[i] > cc) || (cn[i] == cc && km[i] > k);
+    w.ts_k[r] = k; w.ts_c[r] = cc; if (nd) w.ts_n[r] = nd[e];
+  }
+  wsync();
+  DCU_NOUNROLL
+  for (int e = lane; e < n; e += DCU_NL) { km[e] = w.ts_k[e]; cn[e] = w.ts_c[e]; if (nd) nd[e] = w.ts_n[e]; }
+  wsync();
+}
+
 // claim / count one k-mer; newly claimed slots are appended to the occupancy list so that nothing ever scans or
 // clears the whole table (the slab is reused from window to window, only touched slots are reset)
-DCU_FN void hash_insert(const Ctx& c, uint32_t v) {
+DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
   const WS& w = c.ws;
   uint32_t mask = (uint32_t)c.cap.H - 1, h = hslot(c, v);
   DCU_NOUNROLL
@@ -364,6 +383,7 @@ DCU_FN void hash_insert(const Ctx& c, uint32_t v) {
     if (old == v) { a_add(&w.hcnt[h], 1); break; }
     h = (h + 1) & mask;
   }
+  return h;
 }
 DCU_BIG void build_hash(Ctx& c, int lane) {
   const WS& w = c.ws;
@@ -380,51 +400,66 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
     if (lane == 0) w.hstate[0] = 0;
   }
   wsync();
-  uint32_t ni = 0;
-  DCU_NOUNROLL
-  for (int j = lane; j < c.MAo; j += DCU_NL) {
-    int len = seqlen(c, j);
-    if (len < c.k) continue;
-    const uint8_t* u = w.bases + w.soff[j];
-    uint32_t v = 0;
+  // k-mer instances are numbered seq-major; work is cut into chunks of CH consecutive k-mers of one sequence so that
+  // lanes stay balanced whatever the pile depth
+  enum { CH = 8 };
+  {
+    uint32_t runk = 0, runc = 0;
     DCU_NOUNROLL
-    for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i];
-    DCU_NOUNROLL
-    for (int i = 0; i + c.k <= len; ++i) {
-      v = ((v << 2) & c.kmask) | u[i + c.k - 1];
-      hash_insert(c, v);
-      ++ni;
+    for (int base = 0; base < c.MAo; base += DCU_NL) {
+      int j = base + lane; uint32_t nk = 0, nc = 0;
+      if (j < c.MAo) { int len = seqlen(c, j); if (len >= c.k) { nk = (uint32_t)(len - c.k + 1); nc = (nk + CH - 1) / CH; } }
+      uint32_t ik = scan_incl(nk, lane), ic = scan_incl(nc, lane);
+      if (j < c.MAo) { w.koff[j] = (uint16_t)(runk + ik - nk); w.choff[j] = (uint16_t)(runc + ic - nc); }
+      runk += bcast(ik, DCU_NL - 1); runc += bcast(ic, DCU_NL - 1);
     }
-  }
-  c.ni = (int)red_sum_u32(ni);
-  wsync();
-  // last k-mer of every sequence (the `last` array, :2108, :1360-1391): (count, kmer) sorted descending
-  if (lane == 0) {
-    int nl = 0;
+    if (lane == 0) { w.koff[c.MAo] = (uint16_t)runk; w.choff[c.MAo] = (uint16_t)runc; }
+    c.ni = (int)runk;
+    wsync();
+    const int nch = (int)runc;
     DCU_NOUNROLL
-    for (int j = 0; j < c.MAo; ++j) {
-      int len = seqlen(c, j);
-      if (len < c.k) continue;
-      const uint8_t* u = w.bases + w.soff[j] + (len - c.k);
+    for (int t = lane; t < nch; t += DCU_NL) {
+      int a = 0, b = c.MAo;                       // last j with choff[j] <= t (sequences without k-mers share the next one's offset)
+      DCU_NOUNROLL
+      while (b - a > 1) { int mid = (a + b) >> 1; if ((int)w.choff[mid] <= t) a = mid; else b = mid; }
+      const int j = a, len = seqlen(c, j), numk = len - c.k + 1;
+      const int i0 = (t - (int)w.choff[j]) * CH, i1 = i0 + CH < numk ? i0 + CH : numk;
+      const uint8_t* u = w.bases + w.soff[j];
       uint32_t v = 0;
       DCU_NOUNROLL
-      for (int i = 0; i < c.k; ++i) v = (v << 2) | u[i];
-      int t = 0;
+      for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i0 + i];
       DCU_NOUNROLL
-      while (t < nl && w.ll_kmer[t] != v) ++t;
-      if (t == nl) { w.ll_kmer[nl] = v; w.ll_cnt[nl] = 1; ++nl; } else w.ll_cnt[t]++;
+      for (int i = i0; i < i1; ++i) {
+        v = ((v << 2) & c.kmask) | u[i + c.k - 1];
+        uint32_t h = hash_insert(c, v);
+        const int q = (int)w.koff[j] + i;
+        w.islot[q] = h; w.praw[q] = (uint8_t)i; w.rraw[q] = (uint8_t)(len - i - c.k);
+      }
+      if (i1 == numk) w.lastk[j] = v;             // final k-mer of the sequence (the `last` array, :2108)
     }
-    DCU_NOUNROLL
-    for (int a = 1; a < nl; ++a) {          // insertion sort by (cnt, kmer) descending
-      uint32_t kv = w.ll_kmer[a]; uint16_t cv = w.ll_cnt[a]; int b = a;
-      DCU_NOUNROLL
-      while (b > 0 && (w.ll_cnt[b - 1] < cv || (w.ll_cnt[b - 1] == cv && w.ll_kmer[b - 1] < kv))) { w.ll_kmer[b] = w.ll_kmer[b - 1]; w.ll_cnt[b] = w.ll_cnt[b - 1]; --b; }
-      w.ll_kmer[b] = kv; w.ll_cnt[b] = cv;
-    }
-    c.nlast = nl;
   }
-  c.nlast = bcast(c.nlast, 0);
   wsync();
+  // (count, kmer) of the distinct last k-mers, sorted descending (:1360-1391)
+  {
+    int nl = 0;
+    DCU_NOUNROLL
+    for (int base = 0; base < c.MAo; base += DCU_NL) {
+      int j = base + lane; int cnt = 0; bool first = false; uint32_t v = 0;
+      if (j < c.MAo && seqlen(c, j) >= c.k) {
+        v = w.lastk[j]; first = true;
+        DCU_NOUNROLL
+        for (int i = 0; i < c.MAo; ++i) if (seqlen(c, i) >= c.k && w.lastk[i] == v) { ++cnt; if (i < j) first = false; }
+      }
+      uint32_t bb = ballot(first);
+      int idx = nl + popc(bb & lanemask_lt(lane));
+      if (first) { w.ll_kmer[idx] = v; w.ll_cnt[idx] = (uint16_t)cnt; }
+      nl += popc(bb);
+    }
+    wsync();
+    rank_sort_desc(c, w.ll_kmer, w.ll_cnt, nullptr, nl, lane);
+    c.nlast = nl;
+    wsync();
+  }
 }
 
 // nodes = k-mers with count >= f (filterFreq :1181-1197), instance lists (setupNodes :1918-2014)
@@ -451,19 +486,12 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   c.ni = bcast(c.ni, 0);
   wsync();
   if (c.ni > c.cap.NI + c.cap.EX) { c.overflow = 4; return; }
-  DCU_NOUNROLL
-  for (int j = lane; j < c.MAo; j += DCU_NL) {
-    int len = seqlen(c, j);
-    if (len < c.k) continue;
-    const uint8_t* u = w.bases + w.soff[j];
-    uint32_t v = 0;
+  {
+    const int nraw = (int)w.koff[c.MAo];
     DCU_NOUNROLL
-    for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i];
-    DCU_NOUNROLL
-    for (int i = 0; i + c.k <= len; ++i) {
-      v = ((v << 2) & c.kmask) | u[i + c.k - 1];
-      int n = lookup(c, v);
-      if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = (uint8_t)i; w.irpos[w.n_ioff[n] + t] = (uint8_t)(len - i - c.k); }
+    for (int q = lane; q < nraw; q += DCU_NL) {
+      int n = w.hnid[w.islot[q]];
+      if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = w.praw[q]; w.irpos[w.n_ioff[n] + t] = w.rraw[q]; }
     }
   }
   DCU_NOUNROLL
@@ -491,15 +519,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   }
   wsync();
   if ((int)nf > c.cap.S) { c.overflow = 5; return; }
-  if (lane == 0) {
-    DCU_NOUNROLL
-    for (int a = 1; a < (int)nf; ++a) {         // (count, kmer) descending
-      uint32_t kv = w.fl_kmer[a]; uint16_t cv = w.fl_cnt[a], nv = w.fl_nid[a]; int b = a;
-      DCU_NOUNROLL
-      while (b > 0 && (w.fl_cnt[b - 1] < cv || (w.fl_cnt[b - 1] == cv && w.fl_kmer[b - 1] < kv))) { w.fl_kmer[b] = w.fl_kmer[b - 1]; w.fl_cnt[b] = w.fl_cnt[b - 1]; w.fl_nid[b] = w.fl_nid[b - 1]; --b; }
-      w.fl_kmer[b] = kv; w.fl_cnt[b] = cv; w.fl_nid[b] = nv;
-    }
-  }
+  rank_sort_desc(c, w.fl_kmer, w.fl_cnt, w.fl_nid, (int)nf, lane);
   c.nfirst = (int)nf;
   wsync();
 }
@@ -603,18 +623,29 @@ DCU_BIG void node_weights(Ctx& c, int lane) {
   }
   wsync();
   if ((int)run0 > c.cap.KW || (int)run1 > c.cap.KW) { c.overflow = 18; return; }
+  // one node at a time, lanes over its positions: instance positions are warp-uniform loads; the table is stored
+  // transposed ([read position][true position]) so that the lanes of one load touch consecutive words
+  const unsigned long long* VT = c.T.VSq; const int NP = c.T.NP, MS = c.T.MS;
   DCU_NOUNROLL
-  for (int dir = 0; dir < 2; ++dir) {
-    const uint32_t* off = dir ? w.n_ckwo : w.n_kwo;
-    const uint8_t* lo = dir ? w.n_cpf : w.n_pf;
-    double* out = dir ? w.kwR : w.kwF;
-    uint32_t tot = dir ? run1 : run0;
+  for (int n = 0; n < c.nn; ++n) {
+    const int f = w.n_freq[n];
+    const uint8_t* ipf = w.ipos + w.n_ioff[n]; const uint8_t* ipr = w.irpos + w.n_ioff[n];
+    const int pf = w.n_pf[n], rf = (int)w.n_pt[n] - pf, cf = w.n_cpf[n], rr = (int)w.n_cpt[n] - cf;
+    const int rmax = rf > rr ? rf : rr;
     DCU_NOUNROLL
-    for (uint32_t q = (uint32_t)lane; q < tot; q += DCU_NL) {
-      int a = 0, b = c.nn;                 // last node with off[n] <= q
+    for (int p0 = lane; p0 < rmax; p0 += DCU_NL) {
+      int pa = pf + p0, pb = cf + p0;
+      pa = pa < NP ? pa : NP - 1; pb = pb < NP ? pb : NP - 1;        // lanes past a range compute a value that is not stored
+      const unsigned long long* colf = VT + pa; const unsigned long long* colr = VT + pb;
+      unsigned long long uf = 0, ur = 0;
       DCU_NOUNROLL
-      while (b - a > 1) { int mid = (a + b) >> 1; if (off[mid] <= q) a = mid; else b = mid; }
-      out[q] = kweight(c, a, (int)lo[a] + (int)(q - off[a]), dir == 1);
+      for (int t = 0; t < f; ++t) {
+        int a = ipf[t], b = ipr[t];
+        a = a < MS ? a : MS; b = b < MS ? b : MS;                    // row MS is the zero guard
+        uf += colf[a * NP]; ur += colr[b * NP];
+      }
+      if (p0 < rf) w.kwF[w.n_kwo[n] + (uint32_t)p0] = (double)uf / 4294967296.0;
+      if (p0 < rr) w.kwR[w.n_ckwo[n] + (uint32_t)p0] = (double)ur / 4294967296.0;
     }
   }
   wsync();
@@ -852,27 +883,24 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
   wsync();
   if ((int)run0 > c.cap.SF || (int)run1 > c.cap.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
   DCU_NOUNROLL
-  for (int dir = 0; dir < 2; ++dir) {
-    const uint16_t* so = dir ? w.ds_cO : w.ds_fO;
-    const uint8_t* sb = dir ? w.ds_cB : w.ds_fB;
-    double* ow = dir ? w.sc_w : w.sf_w;
-    uint32_t tot = dir ? run1 : run0;
+  for (int s = 0; s < c.nds; ++s) {
+    const int off = w.ds_off[s], L = w.ds_len[s];
+    const int nf = w.ds_fN[s], nr = w.ds_cN[s], bf = w.ds_fB[s], br = w.ds_cB[s];
+    const int nmax = nf > nr ? nf : nr;
     DCU_NOUNROLL
-    for (uint32_t q = (uint32_t)lane; q < tot; q += DCU_NL) {
-      int a = 0, b = c.nds;                // last stretch with so[s] <= q
-      DCU_NOUNROLL
-      while (b - a > 1) { int mid = (a + b) >> 1; if (so[mid] <= q) a = mid; else b = mid; }
-      int off = w.ds_off[a], L = w.ds_len[a];
-      int p0 = (int)sb[a] + (int)(q - so[a]);
-      double sum = 0.0; bool ok = true;
-      DCU_NOUNROLL
-      for (int jj = 0; jj < L; ++jj) {
-        int nj = dir == 0 ? w.slinks[off + jj] : w.slinks[off + L - 1 - jj];
-        double wt = dir == 0 ? kw_fwd(c, nj, p0 + jj) : kw_rev(c, nj, p0 + jj);
-        if (!(wt >= 1e-3)) { ok = false; break; }
-        sum += wt;
+    for (int q = lane; q < nmax; q += DCU_NL) {
+      if (q < nf) {                                   // forward: object p = start position, links first -> last
+        double sum = 0.0; bool ok = true;
+        DCU_NOUNROLL
+        for (int jj = 0; jj < L; ++jj) { double wt = kw_fwd(c, w.slinks[off + jj], bf + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
+        w.sf_w[w.ds_fO[s] + q] = ok ? sum : -1.0;
       }
-      ow[q] = ok ? sum : -1.0;
+      if (q < nr) {                                   // reverse: object p = reverse position of the last k-mer, links last -> first
+        double sum = 0.0; bool ok = true;
+        DCU_NOUNROLL
+        for (int jj = 0; jj < L; ++jj) { double wt = kw_rev(c, w.slinks[off + L - 1 - jj], br + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
+        w.sc_w[w.ds_cO[s] + q] = ok ? sum : -1.0;
+      }
     }
   }
   wsync();

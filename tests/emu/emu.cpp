@@ -49,7 +49,7 @@ extern "C" int64_t emu_get_tables(const dcu_params* prm, int which, double* out,
   dcu_host::build_tables((int)prm->w, prm->p_i, prm->p_d, prm->est_cor, (int)prm->k_lo, (int)prm->k_hi, klimn, HT);
   std::vector<double> v;
   if (which == 0) v = HT.DPn; else if (which == 1) v = HT.DPsq;
-  else if (which == 2) for (auto x : HT.VSq) v.push_back((double)x);
+  else if (which == 2) { for (int l = 0; l < HT.NP; ++l) for (int q = 0; q < HT.MS; ++q) v.push_back((double)HT.VSq[(size_t)q * HT.NP + l]); }
   else if (which == 3) for (int i = 0; i < HT.MS; ++i) { v.push_back(HT.suplo[i]); v.push_back(HT.suphi[i]); }
   else if (which == 4) for (auto x : HT.klim) v.push_back((double)x);
   else if (which == 5) { v.push_back(HT.NP); v.push_back(HT.MS); }
