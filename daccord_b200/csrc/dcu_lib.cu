@@ -19,32 +19,27 @@ static_assert(sizeof(dcu::Slice) == sizeof(dcu_slice) && sizeof(dcu::Window) == 
 
 namespace {
 
-constexpr int WPB = 4;                 // warps per block
+constexpr int WPB = 16;                // warps per block
+constexpr int BPS = 2;                 // resident blocks per SM the kernel is compiled for (64 registers / thread)
 
 struct KArgs {
-  dcu::Layout L; dcu::Caps cap; dcu::Tables T; dcu::Params P;
   const uint8_t* packed; const dcu::Slice* sl; const dcu::Window* win;
   dcu::Result* res; uint8_t* cons; uint8_t* ops;
-  uint8_t* slabs;                      // [total warps][L.bytes]
+  uint8_t* slabs;                      // [total warps][layout bytes]
   const uint32_t* todo;                // window indices to run (nullptr: 0..n-1)
   uint32_t n; uint32_t vs_words;       // vs_words != 0: stage the VS table in dynamic shared memory
   unsigned int* ticket;                // work counter
   unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this tier
 };
 
-__global__ void __launch_bounds__(WPB * 32, 8) dcu_window_kernel(const __grid_constant__ KArgs a) {
-  __shared__ dcu::WS s_ws[WPB];
-  __shared__ dcu::Caps s_cap; __shared__ dcu::Tables s_T; __shared__ dcu::Params s_P;
+// layout, capacities, table descriptors and parameters are in __constant__ memory (window_core.cuh), set per launch
+__global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ unsigned long long s_vs[];          // block-shared copy of the transposed VS table (when it fits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (a.vs_words) for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = a.T.VSq[i];
-  if (threadIdx.x == 0) { s_cap = a.cap; s_T = a.T; s_P = a.P; if (a.vs_words) s_T.VSq = s_vs; }
-  if (lane == 0) {
-    size_t gw = (size_t)blockIdx.x * WPB + warp;
-    dcu::bind_ws(s_ws[warp], a.slabs + gw * (size_t)a.L.bytes, a.L);
-  }
-  __syncthreads();
-  dcu::Ctx c(s_ws[warp], s_cap, s_T, s_P);
+  if (a.vs_words) { for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = dcu::c_T.VSq[i]; __syncthreads(); }
+  dcu::Ctx c;
+  c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcu::c_layout.bytes;
+  c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq;
   c.packed = a.packed; c.sl = a.sl;
   for (;;) {
     unsigned int t = 0;
@@ -88,7 +83,7 @@ struct dcu_ctx {
   dcu::Tables T{}; dcu::Params P{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int num_sms = 0, blocks_per_sm[2] = {8, 1};
+  int num_sms = 0, blocks_per_sm[2] = {BPS, 1};
   // tables
   DevBuf<double> dDPn, dDPsq; DevBuf<unsigned long long> dVSq, dklim; DevBuf<uint16_t> dsuplo, dsuphi;
   // database
@@ -235,12 +230,15 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
     }
   }
   KArgs a;
-  a.L = ctx->lay[tier]; a.cap = ctx->caps[tier]; a.T = ctx->T; a.P = ctx->P;
+  CK(cudaMemcpyToSymbolAsync(dcu::c_layout, &ctx->lay[tier], sizeof(dcu::Layout), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(dcu::c_cap, &ctx->caps[tier], sizeof(dcu::Caps), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(dcu::c_T, &ctx->T, sizeof(dcu::Tables), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(dcu::c_P, &ctx->P, sizeof(dcu::Params), 0, cudaMemcpyHostToDevice, ctx->stream));
   a.packed = ctx->dpacked; a.sl = ctx->dsl.p; a.win = ctx->dwin.p; a.res = ctx->dres.p; a.cons = ctx->dcons.p; a.ops = ctx->dops.p;
   a.slabs = ctx->dslab[tier].p; a.todo = todo; a.n = n;
   a.ticket = ctx->dcnt.p + 2 * tier; a.ovf_cnt = ctx->dcnt.p + 2 * tier + 1; a.ovf_list = ctx->dovf[tier].p;
   size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
-  if (vs_bytes > 24 * 1024) vs_bytes = 0;            // keeps 8 blocks / SM resident; larger tables are read from L2
+  if (vs_bytes > 40 * 1024) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);
   dcu_window_kernel<<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
   CK(cudaGetLastError());

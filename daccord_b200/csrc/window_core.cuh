@@ -31,6 +31,7 @@
 #ifdef DCU_EMU
 #define DCU_FN static inline
 #define DCU_BIG static
+#define DCU_MEM inline
 #define DCU_NOUNROLL
 #define DCU_NOINL static inline
 #define DCU_CTOR
@@ -54,6 +55,7 @@ template <class T> static inline T ldg(const T* p) { return *p; }
 #else
 #define DCU_FN __device__ __forceinline__
 #define DCU_BIG __device__ __noinline__
+#define DCU_MEM __device__ __forceinline__
 #define DCU_NOUNROLL _Pragma("unroll 1")
 #define DCU_NOINL __device__ __noinline__
 #define DCU_CTOR __device__
@@ -115,40 +117,7 @@ struct Slice { uint32_t gpos; uint16_t len; uint16_t flags; };
 struct Window { uint32_t slice_begin; uint16_t slice_cnt; uint16_t reserved; uint32_t aread; uint32_t astart; };
 struct Result { uint8_t status, k; int8_t ff; uint8_t clen; uint32_t err; uint16_t nops, ncand; int32_t elength; };
 
-// one warp's workspace: pointers into its slab (all arrays SoA)
-struct WS {
-  uint8_t* bases; uint16_t* soff; uint16_t* lenhist;
-  uint32_t* hkey; uint32_t* hcnt; uint16_t* hnid; uint32_t* occ; uint32_t* hstate; uint32_t* islot; uint8_t *praw, *rraw; uint16_t *koff, *choff; uint32_t* lastk; uint32_t* ts_k; uint16_t *ts_c, *ts_n;   // hstate[0] = #occupied slots, hstate[1] = table initialised
-  uint32_t* n_kmer; uint16_t* n_freq; uint32_t* n_ioff; uint32_t* n_fill;
-  uint8_t *n_plow, *n_phigh, *n_cplow, *n_cphigh, *n_nsucc, *n_nact, *n_npred;
-  uint16_t* n_sfreq; uint16_t* n_snid; uint16_t* n_mark;
-  uint8_t *ipos, *irpos;
-  uint32_t* ex_kmer; uint8_t *ex_pos, *ex_rpos;
-  uint32_t* ll_kmer; uint16_t* ll_cnt; uint32_t* fl_kmer; uint16_t* fl_cnt; uint16_t* fl_nid;
-  uint16_t* slinks; uint8_t* slsym; uint16_t *rs_off, *rs_len;
-  uint16_t *ds_off, *ds_len, *ds_fO, *ds_cO, *dt_off, *dt_len, *du_off, *du_len, *ds_rlO, *ds_rlN;
-  uint8_t *ds_fB, *ds_fN, *ds_cB, *ds_cN;           // slot range of a stretch: positions [B, B+N)
-  double *sf_w;                                      // forward stretch objects, slot = ds_fO[s] + (p - ds_fB[s]); w < 0: infeasible
-  double *sc_w;                                      // reverse stretch objects (first / last link weights come from kwF / kwR)
-  uint8_t *n_pf, *n_pt, *n_cpf, *n_cpt; uint32_t *n_kwo, *n_ckwo; double *kwF, *kwR;   // dense per-node position weights
-  uint16_t* n_dsf; uint8_t* n_dsn;                   // node -> derived stretches starting there
-  unsigned long long* skey;
-  uint32_t* rl;
-  double* rp_w; uint32_t* rp_parent; uint32_t* rp_front; uint16_t *rp_stretch, *rp_pos, *rp_len, *rp_baselen;
-  double* rq_w; uint32_t* rq_id;                    // RPST heap
-  uint32_t* arp;                                    // accepted reverse paths, then sorted
-  double* arph_w; uint8_t* arph_n;
-  double* fp_w; uint32_t* fp_parent; uint16_t *fp_stretch, *fp_pos, *fp_len, *fp_baselen;
-  double* apq_w; uint32_t* apq_id; uint8_t* apq_n;
-  double* si_w; uint16_t *si_left, *si_right, *si_cur; uint32_t* si_path;
-  double* sq_w; uint32_t* sq_id;                    // SIQ heap
-  uint8_t* cand; uint8_t* candlen;                  // [CDH_N+1][MAXCAND]
-  double* cdh_w; uint32_t* cdh_id; double* ch_w; uint32_t* ch_id;
-  double* acc_w; uint32_t* acc_err; uint8_t* acc_slot;
-  uint8_t *prevs, *tmps, *best;
-  unsigned long long *m_pv, *m_mv, *m_ph, *m_mh;
-};
-
+// (struct WS is defined after the field list below)
 // byte layout of a workspace slab, computed once on the host for a Caps
 struct Layout { uint32_t off[128]; uint32_t bytes; };
 
@@ -199,23 +168,40 @@ static inline void make_layout(const Caps& c, Layout& L) {
 #undef X
   L.bytes = (o + 255u) & ~255u;
 }
+// Launch-wide read-only state.  On the GPU it lives in __constant__ memory, so that slab field addresses
+// (base + constant offset), capacities, table descriptors and parameters are constant-bank operands instead of
+// loads; the emulation build keeps them in plain globals.
 #ifdef DCU_EMU
-static inline
+static Layout g_layout; static Caps g_cap; static Tables g_T; static Params g_P;
+#define DCU_LAYOUT g_layout
+#define DCU_CAP g_cap
+#define DCU_T g_T
+#define DCU_P g_P
 #else
-__device__ inline
+__constant__ Layout c_layout; __constant__ Caps c_cap; __constant__ Tables c_T; __constant__ Params c_P;
+#define DCU_LAYOUT c_layout
+#define DCU_CAP c_cap
+#define DCU_T c_T
+#define DCU_P c_P
 #endif
-void bind_ws(WS& w, uint8_t* base, const Layout& L) {
-  int i = 0;
-#define X(name, type, n) w.name = (type*)(base + L.off[i++]);
-  // note: 'c' is unused in this expansion
+enum {
+#define X(name, type, n) F_##name,
   DCU_WS_FIELDS(X)
 #undef X
-}
+  F_COUNT
+};
+// one warp's workspace: a slab base pointer; every SoA array is an accessor (base + layout offset)
+struct WS {
+  uint8_t* base;
+#define X(name, type, n) DCU_MEM type* name() const { return (type*)(base + DCU_LAYOUT.off[F_##name]); }
+  DCU_WS_FIELDS(X)
+#undef X
+};
 
 // per-window state that all lanes hold identically
 struct Ctx {
-  const WS& ws; const Caps& cap; const Tables& T; const Params& P;   // read-only, shared by the warp's lanes
-  DCU_CTOR Ctx(const WS& rws, const Caps& rcap, const Tables& rT, const Params& rP) : ws(rws), cap(rcap), T(rT), P(rP) {}
+  WS ws;                                   // slab base of this warp
+  const unsigned long long* vsq;           // transposed VS table (shared-memory copy when it fits, else HBM)
   const uint8_t* packed; const Slice* sl;
   int MAo, nbases;
   int k; uint32_t kmask; int kidx;
@@ -225,28 +211,28 @@ struct Ctx {
 };
 
 // ------------------------------------------------------------------ small helpers
-DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - c.cap.LOGH); }
+DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - DCU_CAP.LOGH); }
 DCU_NOINL int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
-  uint32_t h = hslot(c, v), mask = (uint32_t)c.cap.H - 1;
+  uint32_t h = hslot(c, v), mask = (uint32_t)DCU_CAP.H - 1;
   DCU_NOUNROLL
   for (;;) {
-    uint32_t key = c.ws.hkey[h];
-    if (key == v) return c.ws.hnid[h];
+    uint32_t key = c.ws.hkey()[h];
+    if (key == v) return c.ws.hnid()[h];
     if (key == W_EMPTY) return NID_NONE;
     h = (h + 1) & mask;
   }
 }
-DCU_FN int sup_lo(const Ctx& c, int pos) { return pos < c.T.MS ? (int)ldg(c.T.suplo + pos) : c.T.NP; }   // OffsetLikely.hpp:34-37
-DCU_FN int sup_hi(const Ctx& c, int pos) { return pos < c.T.MS ? (int)ldg(c.T.suphi + pos) : c.T.NP; }   // OffsetLikely.hpp:39-43
+DCU_FN int sup_lo(const Ctx& c, int pos) { return pos < DCU_T.MS ? (int)ldg(DCU_T.suplo + pos) : DCU_T.NP; }   // OffsetLikely.hpp:34-37
+DCU_FN int sup_hi(const Ctx& c, int pos) { return pos < DCU_T.MS ? (int)ldg(DCU_T.suphi + pos) : DCU_T.NP; }   // OffsetLikely.hpp:39-43
 
 // positional weight of node n at true position p (DebruijnGraph.hpp:3826-3904, fixed point per SURVEY D7)
 DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
-  const uint8_t* ip = (rev ? c.ws.irpos : c.ws.ipos) + c.ws.n_ioff[n];
-  const unsigned long long* col = c.T.VSq + p;
-  int f = c.ws.n_freq[n];
+  const uint8_t* ip = (rev ? c.ws.irpos() : c.ws.ipos()) + c.ws.n_ioff()[n];
+  const unsigned long long* col = c.vsq + p;
+  int f = c.ws.n_freq()[n];
   unsigned long long u = 0;
   DCU_NOUNROLL
-  for (int t = 0; t < f; ++t) { int pos = ip[t]; pos = pos < c.T.MS ? pos : c.T.MS; u += col[(size_t)pos * c.T.NP]; }
+  for (int t = 0; t < f; ++t) { int pos = ip[t]; pos = pos < DCU_T.MS ? pos : DCU_T.MS; u += col[(size_t)pos * DCU_T.NP]; }
   return (double)u / 4294967296.0;
 }
 
@@ -278,22 +264,22 @@ DCU_NOINL void heap_pop(bool MAXH, double* hw, uint32_t* hi, int& n) {
 DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
   const WS& w = c.ws;
   c.MAo = win.slice_cnt; c.overflow = 0;
-  if (c.MAo > c.cap.S) { c.overflow = 1; return; }
+  if (c.MAo > DCU_CAP.S) { c.overflow = 1; return; }
   const Slice* sl = c.sl + win.slice_begin;
   if (lane == 0) {
     uint32_t o = 0;
     DCU_NOUNROLL
-    for (int j = 0; j < c.MAo; ++j) { w.soff[j] = (uint16_t)o; o += sl[j].len; if (sl[j].len > 255) o = 0x10000000u; }
-    w.soff[c.MAo] = (uint16_t)(o > 65535u ? 65535u : o);
+    for (int j = 0; j < c.MAo; ++j) { w.soff()[j] = (uint16_t)o; o += sl[j].len; if (sl[j].len > 255) o = 0x10000000u; }
+    w.soff()[c.MAo] = (uint16_t)(o > 65535u ? 65535u : o);
     c.nbases = (int)(o > 0x0fffffffu ? 0x0fffffff : o);
   }
   c.nbases = bcast(c.nbases, 0);
   wsync();
-  if (c.nbases > c.cap.B || c.nbases > 65000) { c.overflow = 2; return; }
+  if (c.nbases > DCU_CAP.B || c.nbases > 65000) { c.overflow = 2; return; }
   DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
     Slice s = sl[j];
-    uint8_t* out = w.bases + w.soff[j];
+    uint8_t* out = w.bases() + w.soff()[j];
     if (!(s.flags & 1)) {
       DCU_NOUNROLL
       for (int i = 0; i < s.len; ++i) { uint32_t g = s.gpos + i; out[i] = (ldg(c.packed + (g >> 2)) >> (6 - 2 * (g & 3))) & 3; }
@@ -304,7 +290,7 @@ DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
   }
   wsync();
 }
-DCU_FN int seqlen(const Ctx& c, int j) { return c.ws.soff[j + 1] - c.ws.soff[j]; }
+DCU_FN int seqlen(const Ctx& c, int j) { return c.ws.soff()[j + 1] - c.ws.soff()[j]; }
 
 // ------------------------------------------------------------------ expected length (HandleContext.hpp:2051-2155)
 DCU_BIG int estimate_length(Ctx& c, int lane) {
@@ -320,10 +306,10 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
     double best = DBL_MIN; int bi = 0x7fffffff;
     DCU_NOUNROLL
     for (int i = s0 + lane; i < s1; i += DCU_NL) {
-      const double* row = c.T.DPn + (size_t)i * c.T.MS;
+      const double* row = DCU_T.DPn + (size_t)i * DCU_T.MS;
       double vprod = 1.0;
       DCU_NOUNROLL
-      for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len) { int lp = len - 1; vprod *= (lp < c.T.MS ? ldg(row + lp) : 0.0); } }
+      for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len) { int lp = len - 1; vprod *= (lp < DCU_T.MS ? ldg(row + lp) : 0.0); } }
       if (vprod > best) { best = vprod; bi = i; }
     }
     red_argmax_d(best, bi);
@@ -333,17 +319,17 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
     if (lane == 0) {
       int Os = 0;
       DCU_NOUNROLL
-      for (int i = 0; i < 256; ++i) w.lenhist[i] = 0;
+      for (int i = 0; i < 256; ++i) w.lenhist()[i] = 0;
       DCU_NOUNROLL
-      for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len + 1 > Os) Os = len + 1; if (len < 256) w.lenhist[len]++; }
+      for (int j = 0; j < c.MAo; ++j) { int len = seqlen(c, j); if (len + 1 > Os) Os = len + 1; if (len < 256) w.lenhist()[len]++; }
       int maxoff = -1; double maxoffv = DBL_MIN;
       DCU_NOUNROLL
-      for (int i = 0; i < c.T.NP; ++i) {
-        const double* row = c.T.DPsq + (size_t)i * c.T.MS;
+      for (int i = 0; i < DCU_T.NP; ++i) {
+        const double* row = DCU_T.DPsq + (size_t)i * DCU_T.MS;
         double s = 0;
-        int lim = Os < c.T.MS ? Os : c.T.MS;
+        int lim = Os < DCU_T.MS ? Os : DCU_T.MS;
         DCU_NOUNROLL
-        for (int j = 0; j < lim; ++j) { double o = (j < 256 && w.lenhist[j]) ? (double)(w.lenhist[j] - 1) : 0.0; s += ldg(row + j) * o; }
+        for (int j = 0; j < lim; ++j) { double o = (j < 256 && w.lenhist()[j]) ? (double)(w.lenhist()[j] - 1) : 0.0; s += ldg(row + j) * o; }
         if (s > maxoffv) { maxoff = i; maxoffv = s; }
       }
       if (maxoff != -1 && maxoffv >= 1e-3) maxv = maxoff;
@@ -363,11 +349,11 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
     uint32_t k = km[e]; uint16_t cc = cn[e]; int r = 0;
     DCU_NOUNROLL
     for (int i = 0; i < n; ++i) r += (cn[i] > cc) || (cn[i] == cc && km[i] > k);
-    w.ts_k[r] = k; w.ts_c[r] = cc; if (nd) w.ts_n[r] = nd[e];
+    w.ts_k()[r] = k; w.ts_c()[r] = cc; if (nd) w.ts_n()[r] = nd[e];
   }
   wsync();
   DCU_NOUNROLL
-  for (int e = lane; e < n; e += DCU_NL) { km[e] = w.ts_k[e]; cn[e] = w.ts_c[e]; if (nd) nd[e] = w.ts_n[e]; }
+  for (int e = lane; e < n; e += DCU_NL) { km[e] = w.ts_k()[e]; cn[e] = w.ts_c()[e]; if (nd) nd[e] = w.ts_n()[e]; }
   wsync();
 }
 
@@ -375,29 +361,29 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
 // clears the whole table (the slab is reused from window to window, only touched slots are reset)
 DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
   const WS& w = c.ws;
-  uint32_t mask = (uint32_t)c.cap.H - 1, h = hslot(c, v);
+  uint32_t mask = (uint32_t)DCU_CAP.H - 1, h = hslot(c, v);
   DCU_NOUNROLL
   for (;;) {
-    uint32_t old = a_cas(&w.hkey[h], W_EMPTY, v);
-    if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate[0], 1); w.occ[t] = h; a_add(&w.hcnt[h], 1); break; }
-    if (old == v) { a_add(&w.hcnt[h], 1); break; }
+    uint32_t old = a_cas(&w.hkey()[h], W_EMPTY, v);
+    if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate()[0], 1); w.occ()[t] = h; a_add(&w.hcnt()[h], 1); break; }
+    if (old == v) { a_add(&w.hcnt()[h], 1); break; }
     h = (h + 1) & mask;
   }
   return h;
 }
 DCU_BIG void build_hash(Ctx& c, int lane) {
   const WS& w = c.ws;
-  if (w.hstate[1] != 0x600DF00Du) {          // first use of this slab: full initialisation
+  if (w.hstate()[1] != 0x600DF00Du) {          // first use of this slab: full initialisation
     DCU_NOUNROLL
-    for (int i = lane; i < c.cap.H; i += DCU_NL) { w.hkey[i] = W_EMPTY; w.hcnt[i] = 0; w.hnid[i] = NID_NONE; }
+    for (int i = lane; i < DCU_CAP.H; i += DCU_NL) { w.hkey()[i] = W_EMPTY; w.hcnt()[i] = 0; w.hnid()[i] = NID_NONE; }
     wsync();
-    if (lane == 0) { w.hstate[0] = 0; w.hstate[1] = 0x600DF00Du; }
+    if (lane == 0) { w.hstate()[0] = 0; w.hstate()[1] = 0x600DF00Du; }
   } else {
-    int nocc = (int)w.hstate[0];
+    int nocc = (int)w.hstate()[0];
     DCU_NOUNROLL
-    for (int i = lane; i < nocc; i += DCU_NL) { int h = w.occ[i]; w.hkey[h] = W_EMPTY; w.hcnt[h] = 0; w.hnid[h] = NID_NONE; }
+    for (int i = lane; i < nocc; i += DCU_NL) { int h = w.occ()[i]; w.hkey()[h] = W_EMPTY; w.hcnt()[h] = 0; w.hnid()[h] = NID_NONE; }
     wsync();
-    if (lane == 0) w.hstate[0] = 0;
+    if (lane == 0) w.hstate()[0] = 0;
   }
   wsync();
   // k-mer instances are numbered seq-major; work is cut into chunks of CH consecutive k-mers of one sequence so that
@@ -410,10 +396,10 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
       int j = base + lane; uint32_t nk = 0, nc = 0;
       if (j < c.MAo) { int len = seqlen(c, j); if (len >= c.k) { nk = (uint32_t)(len - c.k + 1); nc = (nk + CH - 1) / CH; } }
       uint32_t ik = scan_incl(nk, lane), ic = scan_incl(nc, lane);
-      if (j < c.MAo) { w.koff[j] = (uint16_t)(runk + ik - nk); w.choff[j] = (uint16_t)(runc + ic - nc); }
+      if (j < c.MAo) { w.koff()[j] = (uint16_t)(runk + ik - nk); w.choff()[j] = (uint16_t)(runc + ic - nc); }
       runk += bcast(ik, DCU_NL - 1); runc += bcast(ic, DCU_NL - 1);
     }
-    if (lane == 0) { w.koff[c.MAo] = (uint16_t)runk; w.choff[c.MAo] = (uint16_t)runc; }
+    if (lane == 0) { w.koff()[c.MAo] = (uint16_t)runk; w.choff()[c.MAo] = (uint16_t)runc; }
     c.ni = (int)runk;
     wsync();
     const int nch = (int)runc;
@@ -421,10 +407,10 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
     for (int t = lane; t < nch; t += DCU_NL) {
       int a = 0, b = c.MAo;                       // last j with choff[j] <= t (sequences without k-mers share the next one's offset)
       DCU_NOUNROLL
-      while (b - a > 1) { int mid = (a + b) >> 1; if ((int)w.choff[mid] <= t) a = mid; else b = mid; }
+      while (b - a > 1) { int mid = (a + b) >> 1; if ((int)w.choff()[mid] <= t) a = mid; else b = mid; }
       const int j = a, len = seqlen(c, j), numk = len - c.k + 1;
-      const int i0 = (t - (int)w.choff[j]) * CH, i1 = i0 + CH < numk ? i0 + CH : numk;
-      const uint8_t* u = w.bases + w.soff[j];
+      const int i0 = (t - (int)w.choff()[j]) * CH, i1 = i0 + CH < numk ? i0 + CH : numk;
+      const uint8_t* u = w.bases() + w.soff()[j];
       uint32_t v = 0;
       DCU_NOUNROLL
       for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i0 + i];
@@ -432,10 +418,10 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
       for (int i = i0; i < i1; ++i) {
         v = ((v << 2) & c.kmask) | u[i + c.k - 1];
         uint32_t h = hash_insert(c, v);
-        const int q = (int)w.koff[j] + i;
-        w.islot[q] = h; w.praw[q] = (uint8_t)i; w.rraw[q] = (uint8_t)(len - i - c.k);
+        const int q = (int)w.koff()[j] + i;
+        w.islot()[q] = h; w.praw()[q] = (uint8_t)i; w.rraw()[q] = (uint8_t)(len - i - c.k);
       }
-      if (i1 == numk) w.lastk[j] = v;             // final k-mer of the sequence (the `last` array, :2108)
+      if (i1 == numk) w.lastk()[j] = v;             // final k-mer of the sequence (the `last` array, :2108)
     }
   }
   wsync();
@@ -446,17 +432,17 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
     for (int base = 0; base < c.MAo; base += DCU_NL) {
       int j = base + lane; int cnt = 0; bool first = false; uint32_t v = 0;
       if (j < c.MAo && seqlen(c, j) >= c.k) {
-        v = w.lastk[j]; first = true;
+        v = w.lastk()[j]; first = true;
         DCU_NOUNROLL
-        for (int i = 0; i < c.MAo; ++i) if (seqlen(c, i) >= c.k && w.lastk[i] == v) { ++cnt; if (i < j) first = false; }
+        for (int i = 0; i < c.MAo; ++i) if (seqlen(c, i) >= c.k && w.lastk()[i] == v) { ++cnt; if (i < j) first = false; }
       }
       uint32_t bb = ballot(first);
       int idx = nl + popc(bb & lanemask_lt(lane));
-      if (first) { w.ll_kmer[idx] = v; w.ll_cnt[idx] = (uint16_t)cnt; }
+      if (first) { w.ll_kmer()[idx] = v; w.ll_cnt()[idx] = (uint16_t)cnt; }
       nl += popc(bb);
     }
     wsync();
-    rank_sort_desc(c, w.ll_kmer, w.ll_cnt, nullptr, nl, lane);
+    rank_sort_desc(c, w.ll_kmer(), w.ll_cnt(), nullptr, nl, lane);
     c.nlast = nl;
     wsync();
   }
@@ -466,38 +452,38 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
 DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   const WS& w = c.ws;
   int nn = 0;
-  const int nocc = (int)w.hstate[0];
+  const int nocc = (int)w.hstate()[0];
   DCU_NOUNROLL
   for (int base = 0; base < nocc; base += DCU_NL) {
     int t = base + lane;
-    int i = t < nocc ? (int)w.occ[t] : 0;
-    bool keep = (t < nocc) && ((int)w.hcnt[i] >= f);
+    int i = t < nocc ? (int)w.occ()[t] : 0;
+    bool keep = (t < nocc) && ((int)w.hcnt()[i] >= f);
     uint32_t b = ballot(keep);
     int idx = nn + popc(b & lanemask_lt(lane));
     if (keep) {
-      if (idx < c.cap.NN) { w.n_kmer[idx] = w.hkey[i]; w.n_freq[idx] = (uint16_t)w.hcnt[i]; w.hnid[i] = (uint16_t)idx; w.n_fill[idx] = 0; }
-    } else if (t < nocc) w.hnid[i] = NID_NONE;
+      if (idx < DCU_CAP.NN) { w.n_kmer()[idx] = w.hkey()[i]; w.n_freq()[idx] = (uint16_t)w.hcnt()[i]; w.hnid()[i] = (uint16_t)idx; w.n_fill()[idx] = 0; }
+    } else if (t < nocc) w.hnid()[i] = NID_NONE;
     nn += popc(b);
   }
-  if (nn > c.cap.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
+  if (nn > DCU_CAP.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
   c.nn = nn;
   wsync();
-  if (lane == 0) { uint32_t o = 0; for (int n = 0; n < nn; ++n) { w.n_ioff[n] = o; o += w.n_freq[n]; } c.ni = (int)o; }
+  if (lane == 0) { uint32_t o = 0; for (int n = 0; n < nn; ++n) { w.n_ioff()[n] = o; o += w.n_freq()[n]; } c.ni = (int)o; }
   c.ni = bcast(c.ni, 0);
   wsync();
-  if (c.ni > c.cap.NI + c.cap.EX) { c.overflow = 4; return; }
+  if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
   {
-    const int nraw = (int)w.koff[c.MAo];
+    const int nraw = (int)w.koff()[c.MAo];
     DCU_NOUNROLL
     for (int q = lane; q < nraw; q += DCU_NL) {
-      int n = w.hnid[w.islot[q]];
-      if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = w.praw[q]; w.irpos[w.n_ioff[n] + t] = w.rraw[q]; }
+      int n = w.hnid()[w.islot()[q]];
+      if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill()[n], 1); w.ipos()[w.n_ioff()[n] + t] = w.praw()[q]; w.irpos()[w.n_ioff()[n] + t] = w.rraw()[q]; }
     }
   }
   DCU_NOUNROLL
   for (int e = lane; e < c.nex; e += DCU_NL) {       // synthesised k-mers of the gap filler (:1148-1157)
-    int n = lookup(c, w.ex_kmer[e]);
-    if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill[n], 1); w.ipos[w.n_ioff[n] + t] = w.ex_pos[e]; w.irpos[w.n_ioff[n] + t] = w.ex_rpos[e]; }
+    int n = lookup(c, w.ex_kmer()[e]);
+    if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill()[n], 1); w.ipos()[w.n_ioff()[n] + t] = w.ex_pos()[e]; w.irpos()[w.n_ioff()[n] + t] = w.ex_rpos()[e]; }
   }
   wsync();
   uint32_t nf = 0;
@@ -506,20 +492,20 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
     int n = base + lane;
     int c0 = 0;
     if (n < nn) {
-      int f0 = w.n_freq[n]; const uint8_t* ip = w.ipos + w.n_ioff[n]; const uint8_t* irp = w.irpos + w.n_ioff[n];
+      int f0 = w.n_freq()[n]; const uint8_t* ip = w.ipos() + w.n_ioff()[n]; const uint8_t* irp = w.irpos() + w.n_ioff()[n];
       int lo = 255, hi = 0, clo = 255, chi = 0;
       DCU_NOUNROLL
       for (int t = 0; t < f0; ++t) { int a = ip[t], b = irp[t]; lo = a < lo ? a : lo; hi = a > hi ? a : hi; clo = b < clo ? b : clo; chi = b > chi ? b : chi; c0 += (a == 0); }
-      w.n_plow[n] = (uint8_t)lo; w.n_phigh[n] = (uint8_t)hi; w.n_cplow[n] = (uint8_t)clo; w.n_cphigh[n] = (uint8_t)chi;
+      w.n_plow()[n] = (uint8_t)lo; w.n_phigh()[n] = (uint8_t)hi; w.n_cplow()[n] = (uint8_t)clo; w.n_cphigh()[n] = (uint8_t)chi;
     }
     uint32_t b = ballot(c0 > 0);               // k-mers seen at position 0 (maxForPosList :1280-1304)
     int idx = (int)nf + popc(b & lanemask_lt(lane));
-    if (c0 > 0 && idx < c.cap.S) { w.fl_kmer[idx] = w.n_kmer[n]; w.fl_cnt[idx] = (uint16_t)c0; w.fl_nid[idx] = (uint16_t)n; }
+    if (c0 > 0 && idx < DCU_CAP.S) { w.fl_kmer()[idx] = w.n_kmer()[n]; w.fl_cnt()[idx] = (uint16_t)c0; w.fl_nid()[idx] = (uint16_t)n; }
     nf += popc(b);
   }
   wsync();
-  if ((int)nf > c.cap.S) { c.overflow = 5; return; }
-  rank_sort_desc(c, w.fl_kmer, w.fl_cnt, w.fl_nid, (int)nf, lane);
+  if ((int)nf > DCU_CAP.S) { c.overflow = 5; return; }
+  rank_sort_desc(c, w.fl_kmer(), w.fl_cnt(), w.fl_nid(), (int)nf, lane);
   c.nfirst = (int)nf;
   wsync();
 }
@@ -530,34 +516,34 @@ DCU_BIG void compute_npred(Ctx& c, int lane) {
   int shift = 2 * (c.k - 1);
   DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
-    uint32_t v = w.n_kmer[n];
+    uint32_t v = w.n_kmer()[n];
     int cnt = 0;
     DCU_NOUNROLL
     for (uint32_t s = 0; s < 4; ++s) {
       uint32_t pv = ((v >> 2) & c.kmask) | (s << shift);
       int p = lookup(c, pv);
       if (p == NID_NONE) continue;
-      int na = w.n_nact[p];
+      int na = w.n_nact()[p];
       DCU_NOUNROLL
-      for (int e = 0; e < na; ++e) if (w.n_snid[4 * p + e] == n) { ++cnt; break; }
+      for (int e = 0; e < na; ++e) if (w.n_snid()[4 * p + e] == n) { ++cnt; break; }
     }
-    w.n_npred[n] = (uint8_t)cnt;
+    w.n_npred()[n] = (uint8_t)cnt;
   }
   wsync();
 }
 // successor lists + primary activation (setNodesActive :1770-1814 / setupAddHeap :1818-1859)
 DCU_BIG void build_edges(Ctx& c, int lane) {
   const WS& w = c.ws;
-  int no = c.MAo < c.T.KLIMN ? c.MAo : c.T.KLIMN - 1;
-  unsigned long long lim = c.P.check ? ldg(c.T.klim + (size_t)c.kidx * c.T.KLIMN + no) : 0;
+  int no = c.MAo < DCU_T.KLIMN ? c.MAo : DCU_T.KLIMN - 1;
+  unsigned long long lim = DCU_P.check ? ldg(DCU_T.klim + (size_t)c.kidx * DCU_T.KLIMN + no) : 0;
   DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
-    uint32_t v = w.n_kmer[n];
+    uint32_t v = w.n_kmer()[n];
     uint32_t key[4]; uint16_t nid[4]; int ns = 0;
     DCU_NOUNROLL
     for (uint32_t s = 0; s < 4; ++s) {
       int t = lookup(c, ((v << 2) & c.kmask) | s);
-      if (t != NID_NONE) { key[ns] = ((uint32_t)w.n_freq[t] << 8) | s; nid[ns] = (uint16_t)t; ++ns; }
+      if (t != NID_NONE) { key[ns] = ((uint32_t)w.n_freq()[t] << 8) | s; nid[ns] = (uint16_t)t; ++ns; }
     }
     DCU_NOUNROLL
     for (int a = 1; a < ns; ++a) {              // Links::sort, descending (Links.hpp:35-57)
@@ -570,11 +556,11 @@ DCU_BIG void build_edges(Ctx& c, int lane) {
     if (ns) {
       na = 1;
       DCU_NOUNROLL
-      while (na < ns && (((key[na] >> 8) >= (key[0] >> 8) / 2) || (c.P.check && (unsigned long long)(key[na] >> 8) >= lim))) ++na;
+      while (na < ns && (((key[na] >> 8) >= (key[0] >> 8) / 2) || (DCU_P.check && (unsigned long long)(key[na] >> 8) >= lim))) ++na;
     }
     DCU_NOUNROLL
-    for (int e = 0; e < 4; ++e) { w.n_sfreq[4 * n + e] = e < ns ? (uint16_t)(key[e] >> 8) : 0; w.n_snid[4 * n + e] = e < ns ? nid[e] : (uint16_t)NID_NONE; }
-    w.n_nsucc[n] = (uint8_t)ns; w.n_nact[n] = (uint8_t)na; w.n_mark[n] = 0;
+    for (int e = 0; e < 4; ++e) { w.n_sfreq()[4 * n + e] = e < ns ? (uint16_t)(key[e] >> 8) : 0; w.n_snid()[4 * n + e] = e < ns ? nid[e] : (uint16_t)NID_NONE; }
+    w.n_nsucc()[n] = (uint8_t)ns; w.n_nact()[n] = (uint8_t)na; w.n_mark()[n] = 0;
   }
   wsync();
   compute_npred(c, lane);
@@ -584,15 +570,15 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
   const WS& w = c.ws;
   uint32_t top = 0;
   DCU_NOUNROLL
-  for (int n = lane; n < c.nn; n += DCU_NL) { int na = w.n_nact[n]; if (na < w.n_nsucc[n]) { uint32_t f = w.n_sfreq[4 * n + na]; top = f > top ? f : top; } }
+  for (int n = lane; n < c.nn; n += DCU_NL) { int na = w.n_nact()[n]; if (na < w.n_nsucc()[n]) { uint32_t f = w.n_sfreq()[4 * n + na]; top = f > top ? f : top; } }
   top = red_max_u32(top);
   if (!top) return false;
   DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
-    int na = w.n_nact[n], ns = w.n_nsucc[n];
+    int na = w.n_nact()[n], ns = w.n_nsucc()[n];
     DCU_NOUNROLL
-    while (na < ns && w.n_sfreq[4 * n + na] == top) ++na;
-    w.n_nact[n] = (uint8_t)na;
+    while (na < ns && w.n_sfreq()[4 * n + na] == top) ++na;
+    w.n_nact()[n] = (uint8_t)na;
   }
   wsync();
   compute_npred(c, lane);
@@ -610,27 +596,27 @@ DCU_BIG void node_weights(Ctx& c, int lane) {
     int n = base + lane;
     uint32_t a = 0, b = 0;
     if (n < c.nn) {
-      int pf = sup_lo(c, w.n_plow[n]), pt = sup_hi(c, w.n_phigh[n]);
-      int cf = sup_lo(c, w.n_cplow[n]), ct = sup_hi(c, w.n_cphigh[n]);
+      int pf = sup_lo(c, w.n_plow()[n]), pt = sup_hi(c, w.n_phigh()[n]);
+      int cf = sup_lo(c, w.n_cplow()[n]), ct = sup_hi(c, w.n_cphigh()[n]);
       if (pt < pf) pt = pf;
       if (ct < cf) ct = cf;
-      w.n_pf[n] = (uint8_t)pf; w.n_pt[n] = (uint8_t)pt; w.n_cpf[n] = (uint8_t)cf; w.n_cpt[n] = (uint8_t)ct;
+      w.n_pf()[n] = (uint8_t)pf; w.n_pt()[n] = (uint8_t)pt; w.n_cpf()[n] = (uint8_t)cf; w.n_cpt()[n] = (uint8_t)ct;
       a = (uint32_t)(pt - pf); b = (uint32_t)(ct - cf);
     }
     uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
-    if (n < c.nn) { w.n_kwo[n] = run0 + ia - a; w.n_ckwo[n] = run1 + ib - b; }
+    if (n < c.nn) { w.n_kwo()[n] = run0 + ia - a; w.n_ckwo()[n] = run1 + ib - b; }
     run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
   }
   wsync();
-  if ((int)run0 > c.cap.KW || (int)run1 > c.cap.KW) { c.overflow = 18; return; }
+  if ((int)run0 > DCU_CAP.KW || (int)run1 > DCU_CAP.KW) { c.overflow = 18; return; }
   // one node at a time, lanes over its positions: instance positions are warp-uniform loads; the table is stored
   // transposed ([read position][true position]) so that the lanes of one load touch consecutive words
-  const unsigned long long* VT = c.T.VSq; const int NP = c.T.NP, MS = c.T.MS;
+  const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
   DCU_NOUNROLL
   for (int n = 0; n < c.nn; ++n) {
-    const int f = w.n_freq[n];
-    const uint8_t* ipf = w.ipos + w.n_ioff[n]; const uint8_t* ipr = w.irpos + w.n_ioff[n];
-    const int pf = w.n_pf[n], rf = (int)w.n_pt[n] - pf, cf = w.n_cpf[n], rr = (int)w.n_cpt[n] - cf;
+    const int f = w.n_freq()[n];
+    const uint8_t* ipf = w.ipos() + w.n_ioff()[n]; const uint8_t* ipr = w.irpos() + w.n_ioff()[n];
+    const int pf = w.n_pf()[n], rf = (int)w.n_pt()[n] - pf, cf = w.n_cpf()[n], rr = (int)w.n_cpt()[n] - cf;
     const int rmax = rf > rr ? rf : rr;
     DCU_NOUNROLL
     for (int p0 = lane; p0 < rmax; p0 += DCU_NL) {
@@ -644,24 +630,24 @@ DCU_BIG void node_weights(Ctx& c, int lane) {
         a = a < MS ? a : MS; b = b < MS ? b : MS;                    // row MS is the zero guard
         uf += colf[a * NP]; ur += colr[b * NP];
       }
-      if (p0 < rf) w.kwF[w.n_kwo[n] + (uint32_t)p0] = (double)uf / 4294967296.0;
-      if (p0 < rr) w.kwR[w.n_ckwo[n] + (uint32_t)p0] = (double)ur / 4294967296.0;
+      if (p0 < rf) w.kwF()[w.n_kwo()[n] + (uint32_t)p0] = (double)uf / 4294967296.0;
+      if (p0 < rr) w.kwR()[w.n_ckwo()[n] + (uint32_t)p0] = (double)ur / 4294967296.0;
     }
   }
   wsync();
 }
-DCU_FN double kw_fwd(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_pf[n] && p < w.n_pt[n]) ? w.kwF[w.n_kwo[n] + (uint32_t)(p - w.n_pf[n])] : 0.0; }
-DCU_FN double kw_rev(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_cpf[n] && p < w.n_cpt[n]) ? w.kwR[w.n_ckwo[n] + (uint32_t)(p - w.n_cpf[n])] : 0.0; }
+DCU_FN double kw_fwd(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_pf()[n] && p < w.n_pt()[n]) ? w.kwF()[w.n_kwo()[n] + (uint32_t)(p - w.n_pf()[n])] : 0.0; }
+DCU_FN double kw_rev(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_cpf()[n] && p < w.n_cpt()[n]) ? w.kwR()[w.n_ckwo()[n] + (uint32_t)(p - w.n_cpf()[n])] : 0.0; }
 
 // ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
 DCU_BIG void gap_fill(Ctx& c, int lane) {
   const WS& w = c.ws;
-  uint32_t* nexp = &w.n_fill[0];      // n_fill[0] doubles as the append counter here (rebuilt afterwards)
+  uint32_t* nexp = &w.n_fill()[0];      // n_fill[0] doubles as the append counter here (rebuilt afterwards)
   if (lane == 0) *nexp = 0;
   wsync();
   DCU_NOUNROLL
   for (int a = lane; a < c.nn; a += DCU_NL) {
-    uint32_t v = w.n_kmer[a];
+    uint32_t v = w.n_kmer()[a];
     DCU_NOUNROLL
     for (uint32_t x = 0; x < 16; ++x) {
       uint32_t nv = ((v << 4) & c.kmask) | x;
@@ -671,7 +657,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
       if (lookup(c, cv) != NID_NONE) continue;
       double mweight = DBL_MIN; int mp = 0;
       DCU_NOUNROLL
-      for (int p = w.n_pf[a]; p < w.n_pt[a]; ++p) {
+      for (int p = w.n_pf()[a]; p < w.n_pt()[a]; ++p) {
         double wa = kw_fwd(c, a, p);
         if (!(wa >= 1e-3)) continue;
         double wb = kw_fwd(c, b, p + 2);
@@ -686,7 +672,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
         for (int j = 0; j < c.MAo && seqid < 0; ++j) if (mp + c.k <= seqlen(c, j)) seqid = j;
         if (seqid >= 0) {
           uint32_t e = a_add(nexp, 1);
-          if ((int)e < c.cap.EX) { w.ex_kmer[e] = cv; w.ex_pos[e] = (uint8_t)mp; w.ex_rpos[e] = (uint8_t)(seqlen(c, seqid) - mp - c.k); }
+          if ((int)e < DCU_CAP.EX) { w.ex_kmer()[e] = cv; w.ex_pos()[e] = (uint8_t)mp; w.ex_rpos()[e] = (uint8_t)(seqlen(c, seqid) - mp - c.k); }
         }
       }
     }
@@ -694,10 +680,10 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   wsync();
   int nex = (int)bcast(*nexp, 0);
   wsync();
-  if (nex > c.cap.EX) { c.overflow = 6; c.nex = 0; return; }
+  if (nex > DCU_CAP.EX) { c.overflow = 6; c.nex = 0; return; }
   c.nex = nex;
   DCU_NOUNROLL
-  for (int e = lane; e < nex; e += DCU_NL) hash_insert(c, w.ex_kmer[e]);
+  for (int e = lane; e < nex; e += DCU_NL) hash_insert(c, w.ex_kmer()[e]);
   wsync();
 }
 
@@ -713,14 +699,14 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
   for (int base = 0; base < c.nn; base += DCU_NL) {
     const int z = base + lane;
     int numsucc = 0; int lens[4] = {0, 0, 0, 0};
-    if (z < c.nn) { int ns = w.n_nact[z], np = w.n_npred[z]; if (ns && (np != 1 || ns > 1)) numsucc = ns; }
+    if (z < c.nn) { int ns = w.n_nact()[z], np = w.n_npred()[z]; if (ns && (np != 1 || ns > 1)) numsucc = ns; }
     uint32_t tot = 0; bool bad = false;
     DCU_NOUNROLL
     for (int i = 0; i < numsucc; ++i) {
-      int cur = w.n_snid[4 * z + i]; int len = 2; bool loop = (cur == z);
+      int cur = w.n_snid()[4 * z + i]; int len = 2; bool loop = (cur == z);
       DCU_NOUNROLL
-      while (!loop && w.n_nact[cur] == 1 && w.n_npred[cur] == 1) {
-        cur = w.n_snid[4 * cur]; ++len;
+      while (!loop && w.n_nact()[cur] == 1 && w.n_npred()[cur] == 1) {
+        cur = w.n_snid()[4 * cur]; ++len;
         if (cur == z) loop = true;
         if (len > c.nn + 1) { bad = true; break; }
       }
@@ -730,15 +716,15 @@ DCU_BIG void raw_stretches(Ctx& c, int lane) {
     uint32_t it = scan_incl(tot, lane), ic = scan_incl((uint32_t)numsucc, lane);
     int lo = slO + (int)(it - tot), so = nrs + (int)(ic - (uint32_t)numsucc);
     int ttot = (int)bcast(it, DCU_NL - 1), tcnt = (int)bcast(ic, DCU_NL - 1);
-    if (nrs + tcnt > c.cap.ST || slO + ttot > c.cap.SL) { ovf = true; break; }
+    if (nrs + tcnt > DCU_CAP.ST || slO + ttot > DCU_CAP.SL) { ovf = true; break; }
     DCU_NOUNROLL
     for (int i = 0; i < numsucc; ++i) {
-      int cur = w.n_snid[4 * z + i]; int o = lo;
-      w.slinks[o] = (uint16_t)z; w.slsym[o] = (uint8_t)(w.n_kmer[z] & 3); ++o;
-      w.slinks[o] = (uint16_t)cur; w.slsym[o] = (uint8_t)(w.n_kmer[cur] & 3); ++o;
+      int cur = w.n_snid()[4 * z + i]; int o = lo;
+      w.slinks()[o] = (uint16_t)z; w.slsym()[o] = (uint8_t)(w.n_kmer()[z] & 3); ++o;
+      w.slinks()[o] = (uint16_t)cur; w.slsym()[o] = (uint8_t)(w.n_kmer()[cur] & 3); ++o;
       DCU_NOUNROLL
-      for (int t = 2; t < lens[i]; ++t) { cur = w.n_snid[4 * cur]; w.slinks[o] = (uint16_t)cur; w.slsym[o] = (uint8_t)(w.n_kmer[cur] & 3); ++o; }
-      w.rs_off[so] = (uint16_t)lo; w.rs_len[so] = (uint16_t)lens[i]; ++so; lo = o;
+      for (int t = 2; t < lens[i]; ++t) { cur = w.n_snid()[4 * cur]; w.slinks()[o] = (uint16_t)cur; w.slsym()[o] = (uint8_t)(w.n_kmer()[cur] & 3); ++o; }
+      w.rs_off()[so] = (uint16_t)lo; w.rs_len()[so] = (uint16_t)lens[i]; ++so; lo = o;
     }
     nrs += tcnt; slO += ttot;
   }
@@ -795,11 +781,11 @@ DCU_BIG int split_pass(Ctx& c, const uint16_t* ioff, const uint16_t* ilen, int n
     if (z < n) {
       off = ioff[z]; len = ilen[z];
       DCU_NOUNROLL
-      for (int i = 1; i + 1 < len; ++i) if (w.slinks[off + i] == v) { split = i; break; }
+      for (int i = 1; i + 1 < len; ++i) if (w.slinks()[off + i] == v) { split = i; break; }
     }
     uint32_t act = ballot(z < n), sp = ballot(split >= 0);
     int idx = base + popc(act & lanemask_lt(lane)) + popc(sp & lanemask_lt(lane));
-    if (z < n && idx + 2 <= c.cap.ST) {
+    if (z < n && idx + 2 <= DCU_CAP.ST) {
       if (split < 0) { ooff[idx] = (uint16_t)off; olen[idx] = (uint16_t)len; }
       else { ooff[idx] = (uint16_t)off; olen[idx] = (uint16_t)(split + 1); ooff[idx + 1] = (uint16_t)(off + split); olen[idx + 1] = (uint16_t)(len - split); }
     }
@@ -812,40 +798,40 @@ DCU_BIG int split_pass(Ctx& c, const uint16_t* ioff, const uint16_t* ilen, int n
 // the first view per (first, ext); equal (first, ext, len) implies identical content, so `last` never decides.
 DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
   const WS& w = c.ws;
-  int n = split_pass(c, w.rs_off, w.rs_len, c.nrs, w.dt_off, w.dt_len, F, lane);
-  if (n > c.cap.ST) { c.overflow = 8; return; }
-  n = split_pass(c, w.dt_off, w.dt_len, n, w.du_off, w.du_len, L, lane);
-  if (n > c.cap.ST) { c.overflow = 8; return; }
+  int n = split_pass(c, w.rs_off(), w.rs_len(), c.nrs, w.dt_off(), w.dt_len(), F, lane);
+  if (n > DCU_CAP.ST) { c.overflow = 8; return; }
+  n = split_pass(c, w.dt_off(), w.dt_len(), n, w.du_off(), w.du_len(), L, lane);
+  if (n > DCU_CAP.ST) { c.overflow = 8; return; }
   int P = 32; while (P < n) P <<= 1;
   DCU_NOUNROLL
   for (int i = lane; i < P; i += DCU_NL) {
     unsigned long long key = ~0ull;
     if (i < n) {
-      int off = w.du_off[i], len = w.du_len[i];
-      unsigned long long fe = ((unsigned long long)w.n_kmer[w.slinks[off]] << 2) | (w.n_kmer[w.slinks[off + 1]] & 3);
+      int off = w.du_off()[i], len = w.du_len()[i];
+      unsigned long long fe = ((unsigned long long)w.n_kmer()[w.slinks()[off]] << 2) | (w.n_kmer()[w.slinks()[off + 1]] & 3);
       key = (fe << 32) | ((unsigned long long)(0xFFFF - len) << 16) | (unsigned long long)i;
     }
-    w.skey[i] = key;
+    w.skey()[i] = key;
   }
   wsync();
-  warp_sort_u64(w.skey, P, lane);
+  warp_sort_u64(w.skey(), P, lane);
   DCU_NOUNROLL
-  for (int i = lane; i < c.nn; i += DCU_NL) { w.n_dsf[i] = NID_NONE; w.n_dsn[i] = 0; }
+  for (int i = lane; i < c.nn; i += DCU_NL) { w.n_dsf()[i] = NID_NONE; w.n_dsn()[i] = 0; }
   wsync();
   int o = 0;
   DCU_NOUNROLL
   for (int b0 = 0; b0 < n; b0 += DCU_NL) {
     int i = b0 + lane;
     bool keep = false; unsigned long long key = 0;
-    if (i < n) { key = w.skey[i]; keep = (i == 0) || ((w.skey[i - 1] >> 32) != (key >> 32)); }
+    if (i < n) { key = w.skey()[i]; keep = (i == 0) || ((w.skey()[i - 1] >> 32) != (key >> 32)); }
     uint32_t b = ballot(keep);
     int idx = o + popc(b & lanemask_lt(lane));
     if (keep) {
       int src = (int)(key & 0xFFFF);
-      w.ds_off[idx] = w.du_off[src]; w.ds_len[idx] = w.du_len[src];
-      int fn = w.slinks[w.du_off[src]];
-      bool firstOfNode = (i == 0) || ((w.skey[i - 1] >> 34) != (key >> 34));
-      if (firstOfNode) w.n_dsf[fn] = (uint16_t)idx;
+      w.ds_off()[idx] = w.du_off()[src]; w.ds_len()[idx] = w.du_len()[src];
+      int fn = w.slinks()[w.du_off()[src]];
+      bool firstOfNode = (i == 0) || ((w.skey()[i - 1] >> 34) != (key >> 34));
+      if (firstOfNode) w.n_dsf()[fn] = (uint16_t)idx;
     }
     o += popc(b);
   }
@@ -853,13 +839,13 @@ DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
   wsync();
   DCU_NOUNROLL
   for (int s = lane; s < o; s += DCU_NL) {          // count per first node (<= 4, distinct ext symbols)
-    int fn = w.slinks[w.ds_off[s]];
-    if (w.n_dsf[fn] == s) { int cnt = 1; while (s + cnt < o && w.slinks[w.ds_off[s + cnt]] == fn) ++cnt; w.n_dsn[fn] = (uint8_t)cnt; }
+    int fn = w.slinks()[w.ds_off()[s]];
+    if (w.n_dsf()[fn] == s) { int cnt = 1; while (s + cnt < o && w.slinks()[w.ds_off()[s + cnt]] == fn) ++cnt; w.n_dsn()[fn] = (uint8_t)cnt; }
   }
   wsync();
 }
-DCU_FN int ds_first(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s]]; }
-DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks[c.ws.ds_off[s] + c.ws.ds_len[s] - 1]; }
+DCU_FN int ds_first(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s]]; }
+DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s] + c.ws.ds_len()[s] - 1]; }
 
 // computeFeasibleStretchPositions (:3176-3330).  Every stretch owns one slot per position of its anchor's
 // support range (forward: first k-mer, object p = start position; reverse: last k-mer, object p = its reverse
@@ -873,99 +859,99 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
     uint32_t a = 0, b = 0;
     if (s < c.nds) {
       int n0 = ds_first(c, s), n1 = ds_last(c, s);
-      a = (uint32_t)(w.n_pt[n0] - w.n_pf[n0]); b = (uint32_t)(w.n_cpt[n1] - w.n_cpf[n1]);
-      w.ds_fB[s] = w.n_pf[n0]; w.ds_fN[s] = (uint8_t)a; w.ds_cB[s] = w.n_cpf[n1]; w.ds_cN[s] = (uint8_t)b;
+      a = (uint32_t)(w.n_pt()[n0] - w.n_pf()[n0]); b = (uint32_t)(w.n_cpt()[n1] - w.n_cpf()[n1]);
+      w.ds_fB()[s] = w.n_pf()[n0]; w.ds_fN()[s] = (uint8_t)a; w.ds_cB()[s] = w.n_cpf()[n1]; w.ds_cN()[s] = (uint8_t)b;
     }
     uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
-    if (s < c.nds) { uint32_t oa = run0 + ia - a, ob = run1 + ib - b; w.ds_fO[s] = (uint16_t)(oa > 65535u ? 65535u : oa); w.ds_cO[s] = (uint16_t)(ob > 65535u ? 65535u : ob); }
+    if (s < c.nds) { uint32_t oa = run0 + ia - a, ob = run1 + ib - b; w.ds_fO()[s] = (uint16_t)(oa > 65535u ? 65535u : oa); w.ds_cO()[s] = (uint16_t)(ob > 65535u ? 65535u : ob); }
     run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
   }
   wsync();
-  if ((int)run0 > c.cap.SF || (int)run1 > c.cap.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
+  if ((int)run0 > DCU_CAP.SF || (int)run1 > DCU_CAP.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
   DCU_NOUNROLL
   for (int s = 0; s < c.nds; ++s) {
-    const int off = w.ds_off[s], L = w.ds_len[s];
-    const int nf = w.ds_fN[s], nr = w.ds_cN[s], bf = w.ds_fB[s], br = w.ds_cB[s];
+    const int off = w.ds_off()[s], L = w.ds_len()[s];
+    const int nf = w.ds_fN()[s], nr = w.ds_cN()[s], bf = w.ds_fB()[s], br = w.ds_cB()[s];
     const int nmax = nf > nr ? nf : nr;
     DCU_NOUNROLL
     for (int q = lane; q < nmax; q += DCU_NL) {
       if (q < nf) {                                   // forward: object p = start position, links first -> last
         double sum = 0.0; bool ok = true;
         DCU_NOUNROLL
-        for (int jj = 0; jj < L; ++jj) { double wt = kw_fwd(c, w.slinks[off + jj], bf + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
-        w.sf_w[w.ds_fO[s] + q] = ok ? sum : -1.0;
+        for (int jj = 0; jj < L; ++jj) { double wt = kw_fwd(c, w.slinks()[off + jj], bf + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
+        w.sf_w()[w.ds_fO()[s] + q] = ok ? sum : -1.0;
       }
       if (q < nr) {                                   // reverse: object p = reverse position of the last k-mer, links last -> first
         double sum = 0.0; bool ok = true;
         DCU_NOUNROLL
-        for (int jj = 0; jj < L; ++jj) { double wt = kw_rev(c, w.slinks[off + L - 1 - jj], br + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
-        w.sc_w[w.ds_cO[s] + q] = ok ? sum : -1.0;
+        for (int jj = 0; jj < L; ++jj) { double wt = kw_rev(c, w.slinks()[off + L - 1 - jj], br + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
+        w.sc_w()[w.ds_cO()[s] + q] = ok ? sum : -1.0;
       }
     }
   }
   wsync();
 }
 DCU_NOINL int sfo_fwd(const Ctx& c, int s, int p) {     // getCachedStretchPositionWeight (:3906-3918)
-  const WS& w = c.ws; int d = p - (int)w.ds_fB[s];
-  if (d < 0 || d >= (int)w.ds_fN[s]) return -1;
-  int o = w.ds_fO[s] + d;
-  return w.sf_w[o] >= 0.0 ? o : -1;
+  const WS& w = c.ws; int d = p - (int)w.ds_fB()[s];
+  if (d < 0 || d >= (int)w.ds_fN()[s]) return -1;
+  int o = w.ds_fO()[s] + d;
+  return w.sf_w()[o] >= 0.0 ? o : -1;
 }
 DCU_NOINL int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchReversePositionWeight (:3920-3932)
-  const WS& w = c.ws; int d = p - (int)w.ds_cB[s];
-  if (d < 0 || d >= (int)w.ds_cN[s]) return -1;
-  int o = w.ds_cO[s] + d;
-  return w.sc_w[o] >= 0.0 ? o : -1;
+  const WS& w = c.ws; int d = p - (int)w.ds_cB()[s];
+  if (d < 0 || d >= (int)w.ds_cN()[s]) return -1;
+  int o = w.ds_cO()[s] + d;
+  return w.sc_w()[o] >= 0.0 ? o : -1;
 }
 
 // weight of the first / last link of a stretch object (StretchFeasObject::wf / wl, :875-889), read back from the node tables
 DCU_FN double fwd_wf(const Ctx& c, int s, int p) { return kw_fwd(c, ds_first(c, s), p); }
-DCU_FN double fwd_wl(const Ctx& c, int s, int p) { return kw_fwd(c, ds_last(c, s), p + c.ws.ds_len[s] - 1); }
+DCU_FN double fwd_wl(const Ctx& c, int s, int p) { return kw_fwd(c, ds_last(c, s), p + c.ws.ds_len()[s] - 1); }
 DCU_FN double rev_wf(const Ctx& c, int s, int p) { return kw_rev(c, ds_last(c, s), p); }
 
 // computeStretchLinks / getReverseStretchLinkWeight (:3388-3480): link A -> B (B.first == A.last) kept iff
 // max over common reverse positions of w_B + (w_A - wf_A) >= 0.1; stored as (B,A), sorted; lanes over A
 DCU_BIG void stretch_links(Ctx& c, int lane) {
   const WS& w = c.ws;
-  uint32_t* cnt = &w.n_fill[0];
+  uint32_t* cnt = &w.n_fill()[0];
   if (lane == 0) *cnt = 0;
   wsync();
   DCU_NOUNROLL
   for (int A = lane; A < c.nds; A += DCU_NL) {
     int ln = ds_last(c, A);
-    int b0 = w.n_dsf[ln], bn = w.n_dsn[ln];
+    int b0 = w.n_dsf()[ln], bn = w.n_dsn()[ln];
     if (b0 == NID_NONE) continue;
     DCU_NOUNROLL
     for (int B = b0; B < b0 + bn; ++B) {
-      int shift = w.ds_len[B] - 1;
+      int shift = w.ds_len()[B] - 1;
       double weight = 0.0;
-      int cb = w.ds_cB[B], cn = w.ds_cN[B], co = w.ds_cO[B];
+      int cb = w.ds_cB()[B], cn = w.ds_cN()[B], co = w.ds_cO()[B];
       DCU_NOUNROLL
       for (int d = 0; d < cn; ++d) {
-        double wb = w.sc_w[co + d];
+        double wb = w.sc_w()[co + d];
         if (!(wb >= 0.0)) continue;
         int oa = sfo_rev(c, A, cb + d + shift);
-        if (oa >= 0) { double lw = wb + (w.sc_w[oa] - rev_wf(c, A, cb + d + shift)); weight = lw > weight ? lw : weight; }
+        if (oa >= 0) { double lw = wb + (w.sc_w()[oa] - rev_wf(c, A, cb + d + shift)); weight = lw > weight ? lw : weight; }
       }
-      if (weight >= 1e-1) { uint32_t t = a_add(cnt, 1); if ((int)t < c.cap.RL) w.rl[t] = ((uint32_t)B << 16) | (uint32_t)A; }
+      if (weight >= 1e-1) { uint32_t t = a_add(cnt, 1); if ((int)t < DCU_CAP.RL) w.rl()[t] = ((uint32_t)B << 16) | (uint32_t)A; }
     }
   }
   wsync();
   int nrl = (int)bcast(*cnt, 0);
   wsync();
-  if (nrl > c.cap.RL) { c.overflow = 10; return; }
+  if (nrl > DCU_CAP.RL) { c.overflow = 10; return; }
   c.nrl = nrl;
   int P = 32; while (P < nrl) P <<= 1;
   DCU_NOUNROLL
-  for (int i = nrl + lane; i < P; i += DCU_NL) w.rl[i] = 0xFFFFFFFFu;
+  for (int i = nrl + lane; i < P; i += DCU_NL) w.rl()[i] = 0xFFFFFFFFu;
   DCU_NOUNROLL
-  for (int s = lane; s < c.nds; s += DCU_NL) { w.ds_rlO[s] = 0; w.ds_rlN[s] = 0; }
+  for (int s = lane; s < c.nds; s += DCU_NL) { w.ds_rlO()[s] = 0; w.ds_rlN()[s] = 0; }
   wsync();
-  warp_sort_u32(w.rl, P, lane);
+  warp_sort_u32(w.rl(), P, lane);
   DCU_NOUNROLL
   for (int t = lane; t < nrl; t += DCU_NL) {
-    int B = (int)(w.rl[t] >> 16);
-    if (t == 0 || (int)(w.rl[t - 1] >> 16) != B) { int e = t + 1; while (e < nrl && (int)(w.rl[e] >> 16) == B) ++e; w.ds_rlO[B] = (uint16_t)t; w.ds_rlN[B] = (uint16_t)(e - t); }
+    int B = (int)(w.rl()[t] >> 16);
+    if (t == 0 || (int)(w.rl()[t - 1] >> 16) != B) { int e = t + 1; while (e < nrl && (int)(w.rl()[e] >> 16) == B) ++e; w.ds_rlO()[B] = (uint16_t)t; w.ds_rlN()[B] = (uint16_t)(e - t); }
   }
   wsync();
 }
@@ -1004,10 +990,10 @@ struct TravOut { int nacc; };
 
 DCU_NOINL int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front, int stretch, int pos, int len, int baselen) {
   const WS& w = c.ws;
-  if (nrp >= c.cap.RP) { c.overflow = 11; return -1; }
+  if (nrp >= DCU_CAP.RP) { c.overflow = 11; return -1; }
   int id = nrp++;
-  w.rp_w[id] = wgt; w.rp_parent[id] = parent; w.rp_front[id] = front; w.rp_stretch[id] = (uint16_t)stretch;
-  w.rp_pos[id] = (uint16_t)pos; w.rp_len[id] = (uint16_t)len; w.rp_baselen[id] = (uint16_t)baselen;
+  w.rp_w()[id] = wgt; w.rp_parent()[id] = parent; w.rp_front()[id] = front; w.rp_stretch()[id] = (uint16_t)stretch;
+  w.rp_pos()[id] = (uint16_t)pos; w.rp_len()[id] = (uint16_t)len; w.rp_baselen()[id] = (uint16_t)baselen;
   return id;
 }
 
@@ -1016,51 +1002,51 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
   const WS& w = c.ws;
   int nrp = 0, nq = 0; narp = 0;
   DCU_NOUNROLL
-  for (int i = 0; i < c.cap.BL; ++i) w.arph_n[i] = 0;
-  int seed = rp_new(c, nrp, 0.0, IDX_NONE, w.n_kmer[Lnode], NID_NONE, 0, 0, c.k);
+  for (int i = 0; i < DCU_CAP.BL; ++i) w.arph_n()[i] = 0;
+  int seed = rp_new(c, nrp, 0.0, IDX_NONE, w.n_kmer()[Lnode], NID_NONE, 0, 0, c.k);
   if (seed < 0) return;
-  heap_push(true, w.rq_w, w.rq_id, nq, 0.0, (uint32_t)seed);
+  heap_push(true, w.rq_w(), w.rq_id(), nq, 0.0, (uint32_t)seed);
   DCU_NOUNROLL
   while (nq > 0 && !c.overflow) {
-    double wt = w.rq_w[0]; int id = (int)w.rq_id[0];
-    heap_pop(true, w.rq_w, w.rq_id, nq);
-    int bl = w.rp_baselen[id];
-    if (bl >= c.cap.BL) continue;                       // longer than any admissible pairing, inert
-    double* hw = w.arph_w + bl * HEAPK; int hn = w.arph_n[bl];
+    double wt = w.rq_w()[0]; int id = (int)w.rq_id()[0];
+    heap_pop(true, w.rq_w(), w.rq_id(), nq);
+    int bl = w.rp_baselen()[id];
+    if (bl >= DCU_CAP.BL) continue;                       // longer than any admissible pairing, inert
+    double* hw = w.arph_w() + bl * HEAPK; int hn = w.arph_n()[bl];
     if (hn == HEAPK) {                                  // bounded per-length heap (:3626-3665); only weights matter
       int mi = 0;
       DCU_NOUNROLL
       for (int t = 1; t < HEAPK; ++t) if (hw[t] < hw[mi]) mi = t;
       if (wt <= hw[mi]) continue;
       hw[mi] = wt;
-    } else { hw[hn] = wt; w.arph_n[bl] = (uint8_t)(hn + 1); }
-    w.arp[narp++] = (uint32_t)id;
-    int rlen = w.rp_len[id], rpos = w.rp_pos[id];
+    } else { hw[hn] = wt; w.arph_n()[bl] = (uint8_t)(hn + 1); }
+    w.arp()[narp++] = (uint32_t)id;
+    int rlen = w.rp_len()[id], rpos = w.rp_pos()[id];
     if (rlen == 0) {
       DCU_NOUNROLL
       for (int s = 0; s < c.nds; ++s) if (ds_last(c, s) == Lnode) {
         int o = sfo_rev(c, s, rpos);                    // extendReversePath (:4058-4105) + feasibility (:4130-4159)
-        if (o >= 0 && w.sc_w[o] >= 0.5) {
-          int L = w.ds_len[s];
-          int nid = rp_new(c, nrp, w.sc_w[o], (uint32_t)id, w.n_kmer[ds_first(c, s)], s, rpos + L - 1, 1, L + c.k - 1);
+        if (o >= 0 && w.sc_w()[o] >= 0.5) {
+          int L = w.ds_len()[s];
+          int nid = rp_new(c, nrp, w.sc_w()[o], (uint32_t)id, w.n_kmer()[ds_first(c, s)], s, rpos + L - 1, 1, L + c.k - 1);
           if (nid < 0) return;
-          if (nq >= c.cap.RP) { c.overflow = 12; return; }
-          heap_push(true, w.rq_w, w.rq_id, nq, w.sc_w[o], (uint32_t)nid);
+          if (nq >= DCU_CAP.RP) { c.overflow = 12; return; }
+          heap_push(true, w.rq_w(), w.rq_id(), nq, w.sc_w()[o], (uint32_t)nid);
         }
       }
     } else if (bl < (lmax + 1) / 2) {
-      int ls = w.rp_stretch[id];
+      int ls = w.rp_stretch()[id];
       DCU_NOUNROLL
-      for (int t = w.ds_rlO[ls], te = w.ds_rlO[ls] + w.ds_rlN[ls]; t < te; ++t) {
-        int s = (int)(w.rl[t] & 0xFFFF);
+      for (int t = w.ds_rlO()[ls], te = w.ds_rlO()[ls] + w.ds_rlN()[ls]; t < te; ++t) {
+        int s = (int)(w.rl()[t] & 0xFFFF);
         int o = sfo_rev(c, s, rpos);
-        if (o >= 0 && w.sc_w[o] >= 0.5) {
-          int L = w.ds_len[s];
-          double nw = wt + (w.sc_w[o] - rev_wf(c, s, rpos));
-          int nid = rp_new(c, nrp, nw, (uint32_t)id, w.n_kmer[ds_first(c, s)], s, rpos + L - 1, rlen + 1, bl + L - 1);
+        if (o >= 0 && w.sc_w()[o] >= 0.5) {
+          int L = w.ds_len()[s];
+          double nw = wt + (w.sc_w()[o] - rev_wf(c, s, rpos));
+          int nid = rp_new(c, nrp, nw, (uint32_t)id, w.n_kmer()[ds_first(c, s)], s, rpos + L - 1, rlen + 1, bl + L - 1);
           if (nid < 0) return;
-          if (nq >= c.cap.RP) { c.overflow = 13; return; }
-          heap_push(true, w.rq_w, w.rq_id, nq, nw, (uint32_t)nid);
+          if (nq >= DCU_CAP.RP) { c.overflow = 13; return; }
+          heap_push(true, w.rq_w(), w.rq_id(), nq, nw, (uint32_t)nid);
         }
       }
     }
@@ -1070,37 +1056,37 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
 DCU_BIG void sort_reverse_paths(Ctx& c, int narp, int lane) {
   const WS& w = c.ws;
   if (narp <= 1) return;
-  unsigned long long* key = (unsigned long long*)w.sq_w;      // the score-interval heap is not in use yet
+  unsigned long long* key = (unsigned long long*)w.sq_w();      // the score-interval heap is not in use yet
   int P = 32; while (P < narp) P <<= 1;
   DCU_NOUNROLL
   for (int i = lane; i < P; i += DCU_NL) {
     unsigned long long k = ~0ull;
-    if (i < narp) { uint32_t id = w.arp[i]; k = ((((unsigned long long)w.rp_front[id] << 8) | (unsigned long long)(w.rp_baselen[id] & 0xFF)) << 16) | (unsigned long long)i; w.rq_id[i] = id; }
+    if (i < narp) { uint32_t id = w.arp()[i]; k = ((((unsigned long long)w.rp_front()[id] << 8) | (unsigned long long)(w.rp_baselen()[id] & 0xFF)) << 16) | (unsigned long long)i; w.rq_id()[i] = id; }
     key[i] = k;
   }
   wsync();
   warp_sort_u64(key, P, lane);
   DCU_NOUNROLL
-  for (int i = lane; i < narp; i += DCU_NL) w.arp[i] = w.rq_id[(int)(key[i] & 0xFFFF)];
+  for (int i = lane; i < narp; i += DCU_NL) w.arp()[i] = w.rq_id()[(int)(key[i] & 0xFFFF)];
   wsync();
 }
 
 DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScore (:3482-3497)
   const WS& w = c.ws;
-  int ls = w.fp_stretch[P];
-  int lpos = w.fp_pos[P] - (w.ds_len[ls] - 1);
+  int ls = w.fp_stretch()[P];
+  int lpos = w.fp_pos()[P] - (w.ds_len()[ls] - 1);
   int o = sfo_fwd(c, ls, lpos);
-  double s = w.fp_w[P] + w.rp_w[rpid];
+  double s = w.fp_w()[P] + w.rp_w()[rpid];
   return o >= 0 ? (s - fwd_wl(c, ls, lpos)) : s;
 }
 // best / next-best reverse path of an interval in (weight, sorted index) order (:3499-3534)
 DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
   const WS& w = c.ws;
   int best = -1; double bw = 0;
-  double cw = cur >= 0 ? w.rp_w[w.arp[cur]] : 0;
+  double cw = cur >= 0 ? w.rp_w()[w.arp()[cur]] : 0;
   DCU_NOUNROLL
   for (int i = left; i < right; ++i) {
-    double wi = w.rp_w[w.arp[i]];
+    double wi = w.rp_w()[w.arp()[i]];
     if (cur >= 0 && !(wi < cw || (wi == cw && i < cur))) continue;
     if (best < 0 || wi > bw || (wi == bw && i > best)) { best = i; bw = wi; }
   }
@@ -1108,26 +1094,26 @@ DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
 }
 DCU_NOINL void apq_push(Ctx& c, int pid) {                        // :4843-4862, :4997-5017
   const WS& w = c.ws;
-  int bl = w.fp_baselen[pid];
-  if (bl >= c.cap.BL) return;                                  // longer than lmax: never pairs, never extends
-  double* hw = w.apq_w + bl * HEAPK; uint32_t* hi = w.apq_id + bl * HEAPK; int n = w.apq_n[bl];
-  double wt = w.fp_w[pid];
+  int bl = w.fp_baselen()[pid];
+  if (bl >= DCU_CAP.BL) return;                                  // longer than lmax: never pairs, never extends
+  double* hw = w.apq_w() + bl * HEAPK; uint32_t* hi = w.apq_id() + bl * HEAPK; int n = w.apq_n()[bl];
+  double wt = w.fp_w()[pid];
   if (n == HEAPK) { if (wt > hw[0]) { heap_pop(false, hw, hi, n); heap_push(false, hw, hi, n, wt, (uint32_t)pid); } }
   else heap_push(false, hw, hi, n, wt, (uint32_t)pid);
-  w.apq_n[bl] = (uint8_t)n;
+  w.apq_n()[bl] = (uint8_t)n;
 }
 DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath (:3989-4056); P == -1 -> empty path
   const WS& w = c.ws;
-  int ppos = P < 0 ? 0 : w.fp_pos[P], plen = P < 0 ? 0 : w.fp_len[P];
+  int ppos = P < 0 ? 0 : w.fp_pos()[P], plen = P < 0 ? 0 : w.fp_len()[P];
   int o = sfo_fwd(c, s, ppos);
-  int L = w.ds_len[s];
+  int L = w.ds_len()[s];
   double wt; int bl;
-  if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sf_w[o] : 0.0; }
-  else { bl = w.fp_baselen[P] + L - 1; wt = w.fp_w[P]; if (o >= 0) wt += w.sf_w[o] - fwd_wf(c, s, ppos); }
-  if (nfp >= c.cap.FP) { c.overflow = 14; return -1; }
+  if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sf_w()[o] : 0.0; }
+  else { bl = w.fp_baselen()[P] + L - 1; wt = w.fp_w()[P]; if (o >= 0) wt += w.sf_w()[o] - fwd_wf(c, s, ppos); }
+  if (nfp >= DCU_CAP.FP) { c.overflow = 14; return -1; }
   int id = nfp++;
-  w.fp_w[id] = wt; w.fp_parent[id] = P < 0 ? IDX_NONE : (uint32_t)P; w.fp_stretch[id] = (uint16_t)s;
-  w.fp_pos[id] = (uint16_t)(ppos + L - 1); w.fp_len[id] = (uint16_t)(plen + 1); w.fp_baselen[id] = (uint16_t)bl;
+  w.fp_w()[id] = wt; w.fp_parent()[id] = P < 0 ? IDX_NONE : (uint32_t)P; w.fp_stretch()[id] = (uint16_t)s;
+  w.fp_pos()[id] = (uint16_t)(ppos + L - 1); w.fp_len()[id] = (uint16_t)(plen + 1); w.fp_baselen()[id] = (uint16_t)bl;
   return id;
 }
 // decodePathPair (:4267-4300) into ASCII; returns length or -1
@@ -1135,22 +1121,22 @@ DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
   const WS& w = c.ws;
   int stack[MAXCAND]; int sp = 0;
   DCU_NOUNROLL
-  for (int q = P; q >= 0; q = (w.fp_parent[q] == IDX_NONE ? -1 : (int)w.fp_parent[q])) { if (sp >= MAXCAND) return -1; stack[sp++] = w.fp_stretch[q]; }
+  for (int q = P; q >= 0; q = (w.fp_parent()[q] == IDX_NONE ? -1 : (int)w.fp_parent()[q])) { if (sp >= MAXCAND) return -1; stack[sp++] = w.fp_stretch()[q]; }
   int o = 0;
-  uint32_t fk = w.n_kmer[ds_first(c, stack[sp - 1])];
+  uint32_t fk = w.n_kmer()[ds_first(c, stack[sp - 1])];
   DCU_NOUNROLL
   for (int i = 0; i < c.k; ++i) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[(fk >> (2 * (c.k - 1 - i))) & 3]; }
   DCU_NOUNROLL
   for (int t = sp - 1; t >= 0; --t) {
-    int s = stack[t], off = w.ds_off[s], L = w.ds_len[s];
+    int s = stack[t], off = w.ds_off()[s], L = w.ds_len()[s];
     DCU_NOUNROLL
-    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym[off + j]]; }
+    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym()[off + j]]; }
   }
   DCU_NOUNROLL
-  for (int q = rpid; w.rp_len[q] > 0; q = (int)w.rp_parent[q]) {
-    int s = w.rp_stretch[q], off = w.ds_off[s], L = w.ds_len[s];
+  for (int q = rpid; w.rp_len()[q] > 0; q = (int)w.rp_parent()[q]) {
+    int s = w.rp_stretch()[q], off = w.ds_off()[s], L = w.ds_len()[s];
     DCU_NOUNROLL
-    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym[off + j]]; }
+    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym()[off + j]]; }
   }
   return o;
 }
@@ -1161,46 +1147,46 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
   int nfp = 0, nsi = 0, nsq = 0;
   const int K = c.k;
   DCU_NOUNROLL
-  for (int i = 0; i < c.cap.BL; ++i) w.apq_n[i] = 0;
-  if (w.n_dsf[Fnode] != NID_NONE)
+  for (int i = 0; i < DCU_CAP.BL; ++i) w.apq_n()[i] = 0;
+  if (w.n_dsf()[Fnode] != NID_NONE)
     DCU_NOUNROLL
-    for (int s = w.n_dsf[Fnode], se = s + w.n_dsn[Fnode]; s < se; ++s) { int id = fp_extend(c, nfp, -1, s); if (id < 0) return; apq_push(c, id); }
+    for (int s = w.n_dsf()[Fnode], se = s + w.n_dsn()[Fnode]; s < se; ++s) { int id = fp_extend(c, nfp, -1, s); if (id < 0) return; apq_push(c, id); }
   DCU_NOUNROLL
-  for (int zz = 0; zz < c.cap.BL && !c.overflow; ++zz) {
+  for (int zz = 0; zz < DCU_CAP.BL && !c.overflow; ++zz) {
     DCU_NOUNROLL
-    while (w.apq_n[zz] > 0) {
-      double* hw = w.apq_w + zz * HEAPK; uint32_t* hi = w.apq_id + zz * HEAPK; int n = w.apq_n[zz];
+    while (w.apq_n()[zz] > 0) {
+      double* hw = w.apq_w() + zz * HEAPK; uint32_t* hi = w.apq_id() + zz * HEAPK; int n = w.apq_n()[zz];
       int P = (int)hi[0];
-      heap_pop(false, hw, hi, n); w.apq_n[zz] = (uint8_t)n;
-      int candlen = w.fp_pos[P] + K;
-      int pls = w.fp_stretch[P];
-      int plast = ds_last(c, pls); uint32_t plk = w.n_kmer[plast];
+      heap_pop(false, hw, hi, n); w.apq_n()[zz] = (uint8_t)n;
+      int candlen = w.fp_pos()[P] + K;
+      int pls = w.fp_stretch()[P];
+      int plast = ds_last(c, pls); uint32_t plk = w.n_kmer()[plast];
       int blo = lmin + K - candlen; if (blo < 0) blo = 0;
       int bhi = lmax + K - candlen; if (bhi < 0) bhi = 0;
       int left = -1, right = -1;
       DCU_NOUNROLL
       for (int i = 0; i < narp; ++i) {
-        uint32_t id = w.arp[i];
-        if (w.rp_front[id] == plk && (int)w.rp_baselen[id] >= blo && (int)w.rp_baselen[id] <= bhi) { if (left < 0) left = i; right = i + 1; }
+        uint32_t id = w.arp()[i];
+        if (w.rp_front()[id] == plk && (int)w.rp_baselen()[id] >= blo && (int)w.rp_baselen()[id] <= bhi) { if (left < 0) left = i; right = i + 1; }
       }
       if (left >= 0) {
         int cur = interval_next(c, left, right, -1);
-        if (nsi >= c.cap.SI || nsq >= c.cap.SI) { c.overflow = 15; return; }
+        if (nsi >= DCU_CAP.SI || nsq >= DCU_CAP.SI) { c.overflow = 15; return; }
         int rec = nsi++;
-        w.si_left[rec] = (uint16_t)left; w.si_right[rec] = (uint16_t)right; w.si_cur[rec] = (uint16_t)cur; w.si_path[rec] = (uint32_t)P;
-        w.si_w[rec] = pair_score(c, P, (int)w.arp[cur]);
-        heap_push(true, w.sq_w, w.sq_id, nsq, w.si_w[rec], (uint32_t)rec);
+        w.si_left()[rec] = (uint16_t)left; w.si_right()[rec] = (uint16_t)right; w.si_cur()[rec] = (uint16_t)cur; w.si_path()[rec] = (uint32_t)P;
+        w.si_w()[rec] = pair_score(c, P, (int)w.arp()[cur]);
+        heap_push(true, w.sq_w(), w.sq_id(), nsq, w.si_w()[rec], (uint32_t)rec);
       }
-      int pbl = w.fp_baselen[P];
+      int pbl = w.fp_baselen()[P];
       if (pbl < K || (pbl - K) < ((lmax + 1) / 2)) {
         DCU_NOUNROLL
-        for (int s = w.n_dsf[plast], se = (s == NID_NONE ? 0 : s + w.n_dsn[plast]); s < se; ++s) {
-          int o = sfo_fwd(c, s, w.fp_pos[P]);
-          double ew = o >= 0 ? w.sf_w[o] : 0.0;
+        for (int s = w.n_dsf()[plast], se = (s == NID_NONE ? 0 : s + w.n_dsn()[plast]); s < se; ++s) {
+          int o = sfo_fwd(c, s, w.fp_pos()[P]);
+          double ew = o >= 0 ? w.sf_w()[o] : 0.0;
           if (ew > 0.1) {
-            int L = w.ds_len[s];
-            double nwt = w.fp_w[P] + (w.sf_w[o] - fwd_wf(c, s, w.fp_pos[P]));
-            if (nwt > 0.1 && (w.fp_pos[P] + L - 1 + K) <= lmax) {
+            int L = w.ds_len()[s];
+            double nwt = w.fp_w()[P] + (w.sf_w()[o] - fwd_wf(c, s, w.fp_pos()[P]));
+            if (nwt > 0.1 && (w.fp_pos()[P] + L - 1 + K) <= lmax) {
               int id = fp_extend(c, nfp, P, s);
               if (id < 0) return;
               apq_push(c, id);
@@ -1213,32 +1199,32 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
   int prevlen = -1;
   DCU_NOUNROLL
   for (int nfull = 0; nsq > 0 && nfull < 16 && !c.overflow; ++nfull) {        // :5049-5092
-    int rec = (int)w.sq_id[0]; double weight = w.sq_w[0];
-    heap_pop(true, w.sq_w, w.sq_id, nsq);
-    int P = (int)w.si_path[rec], cur = w.si_cur[rec];
-    int nxt = interval_next(c, w.si_left[rec], w.si_right[rec], cur);
+    int rec = (int)w.sq_id()[0]; double weight = w.sq_w()[0];
+    heap_pop(true, w.sq_w(), w.sq_id(), nsq);
+    int P = (int)w.si_path()[rec], cur = w.si_cur()[rec];
+    int nxt = interval_next(c, w.si_left()[rec], w.si_right()[rec], cur);
     if (nxt >= 0) {
-      if (nsi >= c.cap.SI) { c.overflow = 16; return; }
+      if (nsi >= DCU_CAP.SI) { c.overflow = 16; return; }
       int r2 = nsi++;
-      w.si_left[r2] = w.si_left[rec]; w.si_right[r2] = w.si_right[rec]; w.si_cur[r2] = (uint16_t)nxt; w.si_path[r2] = (uint32_t)P;
-      w.si_w[r2] = pair_score(c, P, (int)w.arp[nxt]);
-      heap_push(true, w.sq_w, w.sq_id, nsq, w.si_w[r2], (uint32_t)r2);
+      w.si_left()[r2] = w.si_left()[rec]; w.si_right()[r2] = w.si_right()[rec]; w.si_cur()[r2] = (uint16_t)nxt; w.si_path()[r2] = (uint32_t)P;
+      w.si_w()[r2] = pair_score(c, P, (int)w.arp()[nxt]);
+      heap_push(true, w.sq_w(), w.sq_id(), nsq, w.si_w()[r2], (uint32_t)r2);
     }
     if (ncdh == CDH_N) {
-      if (weight <= w.cdh_w[0]) continue;
-      freeslots |= 1u << w.cdh_id[0];
-      heap_pop(false, w.cdh_w, w.cdh_id, ncdh);
+      if (weight <= w.cdh_w()[0]) continue;
+      freeslots |= 1u << w.cdh_id()[0];
+      heap_pop(false, w.cdh_w(), w.cdh_id(), ncdh);
     }
-    int len = decode_pair(c, P, (int)w.arp[cur], w.tmps);
+    int len = decode_pair(c, P, (int)w.arp()[cur], w.tmps());
     if (len < 0) { c.overflow = 17; return; }
-    if (len == prevlen) { bool eq = true; for (int i = 0; i < len; ++i) if (w.tmps[i] != w.prevs[i]) { eq = false; break; } if (eq) continue; }
+    if (len == prevlen) { bool eq = true; for (int i = 0; i < len; ++i) if (w.tmps()[i] != w.prevs()[i]) { eq = false; break; } if (eq) continue; }
     prevlen = len;
     int slot = 0; while (!((freeslots >> slot) & 1u)) ++slot;
     freeslots &= ~(1u << slot);
     DCU_NOUNROLL
-    for (int i = 0; i < len; ++i) { w.prevs[i] = w.tmps[i]; w.cand[slot * MAXCAND + i] = w.tmps[i]; }
-    w.candlen[slot] = (uint8_t)len;
-    heap_push(false, w.cdh_w, w.cdh_id, ncdh, weight, (uint32_t)slot);
+    for (int i = 0; i < len; ++i) { w.prevs()[i] = w.tmps()[i]; w.cand()[slot * MAXCAND + i] = w.tmps()[i]; }
+    w.candlen()[slot] = (uint8_t)len;
+    heap_push(false, w.cdh_w(), w.cdh_id(), ncdh, weight, (uint32_t)slot);
   }
 }
 
@@ -1248,14 +1234,14 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
   raw_stretches(c, lane);
   if (c.overflow) return 0;
   int ncdh = 0; uint32_t freeslots = (1u << (CDH_N + 1)) - 1;
-  int firstthres = c.nfirst ? (w.fl_cnt[0] * 3) / 4 : 0;
-  int lastthres = c.nlast ? (w.ll_cnt[0] * 3) / 4 : 0;
+  int firstthres = c.nfirst ? (w.fl_cnt()[0] * 3) / 4 : 0;
+  int lastthres = c.nlast ? (w.ll_cnt()[0] * 3) / 4 : 0;
   DCU_NOUNROLL
-  for (int fi = 0; fi < c.nfirst && w.fl_cnt[fi] >= firstthres; ++fi)
+  for (int fi = 0; fi < c.nfirst && w.fl_cnt()[fi] >= firstthres; ++fi)
     DCU_NOUNROLL
-    for (int li = 0; li < c.nlast && w.ll_cnt[li] >= lastthres; ++li) {
-      int F = w.fl_nid[fi];
-      int L = lookup(c, w.ll_kmer[li]);
+    for (int li = 0; li < c.nlast && w.ll_cnt()[li] >= lastthres; ++li) {
+      int F = w.fl_nid()[fi];
+      int L = lookup(c, w.ll_kmer()[li]);
       if (L == NID_NONE) continue;        // no reverse seed (:3582) => no pairs; forward search has no side effects
       derive_stretches(c, F, L, lane);
       if (c.overflow) return 0;
@@ -1279,32 +1265,32 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
   if (lane == 0) {
     int nch = 0;
     DCU_NOUNROLL
-    while (ncdh > 0) { double wt = w.cdh_w[0]; uint32_t id = w.cdh_id[0]; heap_pop(false, w.cdh_w, w.cdh_id, ncdh); heap_push(true, w.ch_w, w.ch_id, nch, wt, id); }
+    while (ncdh > 0) { double wt = w.cdh_w()[0]; uint32_t id = w.cdh_id()[0]; heap_pop(false, w.cdh_w(), w.cdh_id(), ncdh); heap_push(true, w.ch_w(), w.ch_id(), nch, wt, id); }
     DCU_NOUNROLL
-    while (nch > 0) { w.acc_w[nacc] = w.ch_w[0]; w.acc_slot[nacc] = (uint8_t)w.ch_id[0]; ++nacc; heap_pop(true, w.ch_w, w.ch_id, nch); }
+    while (nch > 0) { w.acc_w()[nacc] = w.ch_w()[0]; w.acc_slot()[nacc] = (uint8_t)w.ch_id()[0]; ++nacc; heap_pop(true, w.ch_w(), w.ch_id(), nch); }
   }
   nacc = bcast(nacc, 0);
   wsync();
   // getSimpleCandidateError (:5355-5363): lanes over sequences
   DCU_NOUNROLL
   for (int a = 0; a < nacc; ++a) {
-    int slot = w.acc_slot[a], m = w.candlen[slot];
+    int slot = w.acc_slot()[a], m = w.candlen()[slot];
     unsigned long long peq[4];
-    make_peq(peq, w.cand + slot * MAXCAND, m, true);
+    make_peq(peq, w.cand() + slot * MAXCAND, m, true);
     uint32_t e = 0;
     DCU_NOUNROLL
-    for (int j = lane; j < c.MAo; j += DCU_NL) e += (uint32_t)myers_dist(peq, m, w.bases + w.soff[j], seqlen(c, j));
+    for (int j = lane; j < c.MAo; j += DCU_NL) e += (uint32_t)myers_dist(peq, m, w.bases() + w.soff()[j], seqlen(c, j));
     e = red_sum_u32(e);
-    if (lane == 0) w.acc_err[a] = e;
+    if (lane == 0) w.acc_err()[a] = e;
   }
   wsync();
   if (lane == 0) {                       // std::sort by error, n <= 16 => stable insertion sort (:5156)
     DCU_NOUNROLL
     for (int a = 1; a < nacc; ++a) {
-      double tw = w.acc_w[a]; uint32_t te = w.acc_err[a]; uint8_t ts = w.acc_slot[a]; int b = a;
+      double tw = w.acc_w()[a]; uint32_t te = w.acc_err()[a]; uint8_t ts = w.acc_slot()[a]; int b = a;
       DCU_NOUNROLL
-      while (b > 0 && w.acc_err[b - 1] > te) { w.acc_w[b] = w.acc_w[b - 1]; w.acc_err[b] = w.acc_err[b - 1]; w.acc_slot[b] = w.acc_slot[b - 1]; --b; }
-      w.acc_w[b] = tw; w.acc_err[b] = te; w.acc_slot[b] = ts;
+      while (b > 0 && w.acc_err()[b - 1] > te) { w.acc_w()[b] = w.acc_w()[b - 1]; w.acc_err()[b] = w.acc_err()[b - 1]; w.acc_slot()[b] = w.acc_slot()[b - 1]; --b; }
+      w.acc_w()[b] = tw; w.acc_err()[b] = te; w.acc_slot()[b] = ts;
     }
   }
   wsync();
@@ -1326,10 +1312,10 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
     unsigned long long xh = (((eq & pv) + pv) ^ pv) | eq;
     unsigned long long ph = mv | ~(xh | pv);
     unsigned long long mh = pv & xh;
-    w.m_ph[j] = ph; w.m_mh[j] = mh;       // horizontal deltas of rows 1..m (bit i-1), before the shift
+    w.m_ph()[j] = ph; w.m_mh()[j] = mh;       // horizontal deltas of rows 1..m (bit i-1), before the shift
     ph = (ph << 1) | 1ull; mh <<= 1;
     pv = mh | ~(xv | ph); mv = ph & xv;
-    w.m_pv[j] = pv; w.m_mv[j] = mv;       // vertical deltas in column j
+    w.m_pv()[j] = pv; w.m_mv()[j] = mv;       // vertical deltas in column j
   }
   int i = la, j = lb, n = 0;
   // ops are produced backwards, then reversed in place
@@ -1337,8 +1323,8 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
   while (i > 0 || j > 0) {
     int op;
     if (i > 0 && j > 0) {
-      int dv = ((w.m_pv[j] >> (i - 1)) & 1ull) ? 1 : (((w.m_mv[j] >> (i - 1)) & 1ull) ? -1 : 0);
-      int dhup = (i == 1) ? 1 : (((w.m_ph[j] >> (i - 2)) & 1ull) ? 1 : (((w.m_mh[j] >> (i - 2)) & 1ull) ? -1 : 0));
+      int dv = ((w.m_pv()[j] >> (i - 1)) & 1ull) ? 1 : (((w.m_mv()[j] >> (i - 1)) & 1ull) ? -1 : 0);
+      int dhup = (i == 1) ? 1 : (((w.m_ph()[j] >> (i - 2)) & 1ull) ? 1 : (((w.m_mh()[j] >> (i - 2)) & 1ull) ? -1 : 0));
       int ca = a[i - 1]; int cb = cons[j - 1]; cb = (cb == 'A') ? 0 : (cb == 'C') ? 1 : (cb == 'G') ? 2 : 3;
       int cost = ca != cb;
       if (dv + dhup == cost) { op = cost ? 1 : 0; --i; --j; }
@@ -1363,19 +1349,19 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
   if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
   int elength = estimate_length(c, lane);
   res.elength = elength;
-  if (c.MAo < c.P.mincov) return;
-  if (seqlen(c, 0) != c.P.w) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+  if (c.MAo < DCU_P.mincov) return;
+  if (seqlen(c, 0) != DCU_P.w) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
   int lmin = elength - 4, lmax = elength + 4;
   bool pathfailed = true, have = false;
-  unsigned long long minrate = c.P.eminrate;
+  unsigned long long minrate = DCU_P.eminrate;
   int bestlen = 0, bestk = 0, bestff = -1, bestn = 0;
   DCU_NOUNROLL
-  for (int k = c.P.k_lo; k <= c.P.k_hi; ++k) {
-    c.k = k; c.kidx = k - c.P.k_lo; c.kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+  for (int k = DCU_P.k_lo; k <= DCU_P.k_hi; ++k) {
+    c.k = k; c.kidx = k - DCU_P.k_lo; c.kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     c.nex = 0;
     build_hash(c, lane);
     DCU_NOUNROLL
-    for (int ff = c.P.maxff; ff >= c.P.minff; --ff) {
+    for (int ff = DCU_P.maxff; ff >= DCU_P.minff; --ff) {
       int f = ff > 1 ? ff : 1;
       if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
       build_nodes(c, f, lane);
@@ -1395,12 +1381,12 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
         int nacc = traverse(c, lmin, lmax, lane);
         if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
         if (nacc > 0) {
-          unsigned long long e0 = bcast(w.acc_err[0], 0);    // checkCandidatesU == error of candidate 0 (:5476-5482)
+          unsigned long long e0 = bcast(w.acc_err()[0], 0);    // checkCandidatesU == error of candidate 0 (:5476-5482)
           if (e0 < minrate) {
             lconsok = true; minrate = e0; have = true;
-            int slot = w.acc_slot[0]; bestlen = w.candlen[slot]; bestk = k; bestff = ff; bestn = nacc;
+            int slot = w.acc_slot()[0]; bestlen = w.candlen()[slot]; bestk = k; bestff = ff; bestn = nacc;
             DCU_NOUNROLL
-            for (int i = lane; i < bestlen; i += DCU_NL) w.best[i] = w.cand[slot * MAXCAND + i];
+            for (int i = lane; i < bestlen; i += DCU_NL) w.best()[i] = w.cand()[slot * MAXCAND + i];
             wsync();
           } else if (have) lconsok = true;
           break;
@@ -1414,8 +1400,8 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
   int nops = 0;
   if (lane == 0) {
     DCU_NOUNROLL
-    for (int i = 0; i < bestlen; ++i) cons_out[i] = w.best[i];
-    nops = placement(c, w.bases, c.P.w, w.best, bestlen, ops_out);
+    for (int i = 0; i < bestlen; ++i) cons_out[i] = w.best()[i];
+    nops = placement(c, w.bases(), DCU_P.w, w.best(), bestlen, ops_out);
   }
   nops = bcast(nops, 0);
   if (nops < 0) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }

@@ -23,13 +23,14 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
   dcu::Caps caps = dcu_host::make_caps(tier, (int)prm->w, maxS, maxB);
   dcu::Layout L; dcu::make_layout(caps, L);
   std::vector<uint8_t> slab(L.bytes + 64);
-  dcu::WS ws; dcu::Tables T; dcu::Params P;
-  dcu::bind_ws(ws, slab.data(), L);
+  dcu::Tables T; dcu::Params P;
   T.DPn = HT.DPn.data(); T.DPsq = HT.DPsq.data(); T.VSq = HT.VSq.data(); T.suplo = HT.suplo.data(); T.suphi = HT.suphi.data();
   T.klim = HT.klim.data(); T.NP = HT.NP; T.MS = HT.MS; T.KLIMN = HT.KLIMN;
   P.w = (int)prm->w; P.k_lo = (int)prm->k_lo; P.k_hi = (int)prm->k_hi; P.minff = prm->min_ff; P.maxff = prm->max_ff;
   P.mincov = (int)prm->min_cov; P.check = prm->est_cor != 0.0; P.eminrate = prm->max_err;
-  dcu::Ctx c(ws, caps, T, P);
+  dcu::g_layout = L; dcu::g_cap = caps; dcu::g_T = T; dcu::g_P = P;
+  dcu::Ctx c;
+  c.ws.base = slab.data(); c.vsq = T.VSq;
   c.packed = packed; c.sl = (const dcu::Slice*)sl;
   uint64_t nov = 0;
   for (uint64_t i = 0; i < nwin; ++i) {
