@@ -28,6 +28,7 @@ struct KArgs {
   uint8_t* slabs;                      // [total warps][layout bytes]
   const uint32_t* todo;                // window indices to run (nullptr: 0..n-1)
   uint32_t n; uint32_t vs_words;       // vs_words != 0: stage the VS table in dynamic shared memory
+  int sync_group;                      // warps per phase-synchronous group (1 = free running, WPB = whole block)
   unsigned int* ticket;                // work counter
   unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this tier
 };
@@ -41,20 +42,49 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
   c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcu::c_layout.bytes;
   c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq;
   c.packed = a.packed; c.sl = a.sl;
+  // phase-synchronous execution: every warp owns one window at a time and walks it through the stages of
+  // window_core.cuh; warps are tied into groups of `sync_group` warps by named barriers so that the warps of a group
+  // run the same stage's code at the same time (instruction-cache locality) without waiting on the whole block
+  __shared__ int s_done[WPB];
+  const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
+  auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
+  dcu::WinState st; st.ph = dcu::PH_END;
+  uint32_t wi = 0; bool done = false;
   for (;;) {
-    unsigned int t = 0;
-    if (lane == 0) t = atomicAdd(a.ticket, 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= a.n) break;
-    uint32_t wi = a.todo ? a.todo[t] : t;
-    dcu::Window W = a.win[wi];
-    dcu::Result r;
-    dcu::process_window(c, W, r, a.cons + (size_t)wi * DCU_CONS_STRIDE, a.ops + (size_t)wi * DCU_OPS_STRIDE, lane);
-    if (lane == 0) {
-      a.res[wi] = r;
-      if (r.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
+    // stage 0: finish / fetch
+    while (!done && st.ph == dcu::PH_END) {
+      unsigned int t = 0;
+      if (lane == 0) t = atomicAdd(a.ticket, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= a.n) { done = true; break; }
+      wi = a.todo ? a.todo[t] : t;
+      dcu::Window W = a.win[wi];
+      dcu::st_begin(c, st, W, lane);
+      if (st.ph == dcu::PH_END && lane == 0) {         // skipped or overflowed right away
+        a.res[wi] = st.res;
+        if (st.res.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
+      }
     }
-    __syncwarp();
+    if (lane == 0) s_done[warp] = (done && st.ph == dcu::PH_END) ? 1 : 0;
+    gsync();
+    bool alldone = true;
+    for (int i = 0; i < G; ++i) alldone = alldone && (s_done[gfirst + i] != 0);
+    if (alldone) break;
+    if (st.ph == dcu::PH_HASH) dcu::st_hash(c, st, lane);
+    gsync();
+    if (st.ph == dcu::PH_NODES) dcu::st_nodes(c, st, lane);
+    gsync();
+    if (st.ph == dcu::PH_TRAV) dcu::st_trav(c, st, lane);
+    gsync();
+    if (st.ph == dcu::PH_FINAL) dcu::st_final(c, st, a.cons + (size_t)wi * DCU_CONS_STRIDE, a.ops + (size_t)wi * DCU_OPS_STRIDE, lane);
+    if (st.ph == dcu::PH_END && !done) {
+      // window finished in this round (final stage, or an overflow inside a stage): publish
+      if (lane == 0) {
+        a.res[wi] = st.res;
+        if (st.res.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -83,7 +113,7 @@ struct dcu_ctx {
   dcu::Tables T{}; dcu::Params P{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int num_sms = 0, blocks_per_sm[2] = {BPS, 1};
+  int num_sms = 0, blocks_per_sm[2] = {BPS, 1}; int sync_group = WPB; int sync_group_env = 0;
   // tables
   DevBuf<double> dDPn, dDPsq; DevBuf<unsigned long long> dVSq, dklim; DevBuf<uint16_t> dsuplo, dsuphi;
   // database
@@ -148,6 +178,8 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   CK(ctx->dcnt.ensure(4));
   const char* e = getenv("DCU_BLOCKS_PER_SM");
   if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);
+  e = getenv("DCU_SYNC_GROUP");
+  if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16)) ctx->sync_group_env = atoi(e);
   return DCU_OK;
 }
 
@@ -205,6 +237,10 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
   }
   if (maxS >= ctx->HT.KLIMN || maxB > 65000) { ctx->err = "pile deeper than this build supports"; return DCU_ERR_UNSUPPORTED; }
   ctx->maxS = maxS; ctx->maxB = maxB;
+  // phase-synchronous group size: deep, homogeneous piles gain from large groups (instruction-cache locality); shallow
+  // piles have a heavy tail of windows that need the filterfreq-1 pass, where waiting on the slowest warp costs more
+  // than the locality brings (measured: profiles/r01_summary.md).  Results do not depend on it.
+  { double mean = nwin ? (double)nsl / (double)nwin : 0.0; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : (mean >= 30.0 ? 16 : (mean >= 16.0 ? 8 : 1)); }
   for (int t = 0; t < 2; ++t) { ctx->caps[t] = dcu_host::make_caps(t, (int)ctx->prm.w, maxS, maxB); dcu::make_layout(ctx->caps[t], ctx->lay[t]); }
   CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
   CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));
@@ -240,6 +276,7 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
   if (vs_bytes > 40 * 1024) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);
+  a.sync_group = ctx->sync_group;
   dcu_window_kernel<<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;

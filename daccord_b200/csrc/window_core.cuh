@@ -142,7 +142,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(ds_fB, uint8_t, c.ST) X(ds_fN, uint8_t, c.ST) X(ds_cB, uint8_t, c.ST) X(ds_cN, uint8_t, c.ST)          \
   X(sf_w, double, c.SF) X(sc_w, double, c.SF)                                                              \
   X(n_pf, uint8_t, c.NN) X(n_pt, uint8_t, c.NN) X(n_cpf, uint8_t, c.NN) X(n_cpt, uint8_t, c.NN)            \
-  X(n_kwo, uint32_t, c.NN) X(n_ckwo, uint32_t, c.NN) X(kwF, double, c.KW) X(kwR, double, c.KW)             \
+  X(n_kwo, uint32_t, c.NN) X(n_ckwo, uint32_t, c.NN) X(kwF, double, 2) X(kwR, double, 2)                           \
   X(n_dsf, uint16_t, c.NN) X(n_dsn, uint8_t, c.NN) X(skey, unsigned long long, c.STP)                      \
   X(rl, uint32_t, c.RLP)                                                                                   \
   X(rp_w, double, c.RP) X(rp_parent, uint32_t, c.RP) X(rp_front, uint32_t, c.RP)                           \
@@ -608,36 +608,10 @@ DCU_BIG void node_weights(Ctx& c, int lane) {
     run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
   }
   wsync();
-  if ((int)run0 > DCU_CAP.KW || (int)run1 > DCU_CAP.KW) { c.overflow = 18; return; }
-  // one node at a time, lanes over its positions: instance positions are warp-uniform loads; the table is stored
-  // transposed ([read position][true position]) so that the lanes of one load touch consecutive words
-  const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
-  DCU_NOUNROLL
-  for (int n = 0; n < c.nn; ++n) {
-    const int f = w.n_freq()[n];
-    const uint8_t* ipf = w.ipos() + w.n_ioff()[n]; const uint8_t* ipr = w.irpos() + w.n_ioff()[n];
-    const int pf = w.n_pf()[n], rf = (int)w.n_pt()[n] - pf, cf = w.n_cpf()[n], rr = (int)w.n_cpt()[n] - cf;
-    const int rmax = rf > rr ? rf : rr;
-    DCU_NOUNROLL
-    for (int p0 = lane; p0 < rmax; p0 += DCU_NL) {
-      int pa = pf + p0, pb = cf + p0;
-      pa = pa < NP ? pa : NP - 1; pb = pb < NP ? pb : NP - 1;        // lanes past a range compute a value that is not stored
-      const unsigned long long* colf = VT + pa; const unsigned long long* colr = VT + pb;
-      unsigned long long uf = 0, ur = 0;
-      DCU_NOUNROLL
-      for (int t = 0; t < f; ++t) {
-        int a = ipf[t], b = ipr[t];
-        a = a < MS ? a : MS; b = b < MS ? b : MS;                    // row MS is the zero guard
-        uf += colf[a * NP]; ur += colr[b * NP];
-      }
-      if (p0 < rf) w.kwF()[w.n_kwo()[n] + (uint32_t)p0] = (double)uf / 4294967296.0;
-      if (p0 < rr) w.kwR()[w.n_ckwo()[n] + (uint32_t)p0] = (double)ur / 4294967296.0;
-    }
-  }
   wsync();
 }
-DCU_FN double kw_fwd(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_pf()[n] && p < w.n_pt()[n]) ? w.kwF()[w.n_kwo()[n] + (uint32_t)(p - w.n_pf()[n])] : 0.0; }
-DCU_FN double kw_rev(const Ctx& c, int n, int p) { const WS& w = c.ws; return (p >= w.n_cpf()[n] && p < w.n_cpt()[n]) ? w.kwR()[w.n_ckwo()[n] + (uint32_t)(p - w.n_cpf()[n])] : 0.0; }
+DCU_NOINL double kw_fwd(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_T.NP) ? kweight(c, n, p, false) : 0.0; }
+DCU_NOINL double kw_rev(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_T.NP) ? kweight(c, n, p, true) : 0.0; }
 
 // ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
 DCU_BIG void gap_fill(Ctx& c, int lane) {
@@ -868,25 +842,44 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
   }
   wsync();
   if ((int)run0 > DCU_CAP.SF || (int)run1 > DCU_CAP.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
+  // per stretch, lanes over anchor positions; the link weights are evaluated on the fly from the instance lists
+  // (all lanes share the node, so instance positions are uniform loads and only the table column differs per lane)
+  const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
   DCU_NOUNROLL
   for (int s = 0; s < c.nds; ++s) {
     const int off = w.ds_off()[s], L = w.ds_len()[s];
     const int nf = w.ds_fN()[s], nr = w.ds_cN()[s], bf = w.ds_fB()[s], br = w.ds_cB()[s];
     const int nmax = nf > nr ? nf : nr;
     DCU_NOUNROLL
-    for (int q = lane; q < nmax; q += DCU_NL) {
-      if (q < nf) {                                   // forward: object p = start position, links first -> last
-        double sum = 0.0; bool ok = true;
-        DCU_NOUNROLL
-        for (int jj = 0; jj < L; ++jj) { double wt = kw_fwd(c, w.slinks()[off + jj], bf + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
-        w.sf_w()[w.ds_fO()[s] + q] = ok ? sum : -1.0;
+    for (int q0 = 0; q0 < nmax; q0 += DCU_NL) {
+      const int q = q0 + lane;
+      bool af = q < nf, ar = q < nr;
+      double sumf = 0.0, sumr = 0.0;
+      DCU_NOUNROLL
+      for (int jj = 0; jj < L; ++jj) {
+        if (!ballot(af || ar)) break;
+        const int nF = w.slinks()[off + jj], nR = w.slinks()[off + L - 1 - jj];
+        if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
+          int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
+          const uint8_t* ip = w.ipos() + w.n_ioff()[nF]; const int f = w.n_freq()[nF];
+          const unsigned long long* col = VT + p; unsigned long long u = 0;
+          DCU_NOUNROLL
+          for (int t = 0; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += col[a * NP]; }
+          double wt = in ? (double)u / 4294967296.0 : 0.0;
+          if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
+        }
+        if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
+          int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
+          const uint8_t* ip = w.irpos() + w.n_ioff()[nR]; const int f = w.n_freq()[nR];
+          const unsigned long long* col = VT + p; unsigned long long u = 0;
+          DCU_NOUNROLL
+          for (int t = 0; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += col[a * NP]; }
+          double wt = in ? (double)u / 4294967296.0 : 0.0;
+          if (ar) { if (wt >= 1e-3) sumr += wt; else ar = false; }
+        }
       }
-      if (q < nr) {                                   // reverse: object p = reverse position of the last k-mer, links last -> first
-        double sum = 0.0; bool ok = true;
-        DCU_NOUNROLL
-        for (int jj = 0; jj < L; ++jj) { double wt = kw_rev(c, w.slinks()[off + L - 1 - jj], br + q + jj); if (!(wt >= 1e-3)) { ok = false; break; } sum += wt; }
-        w.sc_w()[w.ds_cO()[s] + q] = ok ? sum : -1.0;
-      }
+      if (q < nf) w.sf_w()[w.ds_fO()[s] + q] = af ? sumf : -1.0;
+      if (q < nr) w.sc_w()[w.ds_cO()[s] + q] = ar ? sumr : -1.0;
     }
   }
   wsync();
@@ -1342,71 +1335,117 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
 }
 
 // ------------------------------------------------------------------ one window (HandleContext.hpp:2164-2494)
-DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons_out, uint8_t* ops_out, int lane) {
-  const WS& w = c.ws;
+// The per-window control flow (k range x filterfreq descent x <=3 edge-activation rounds, :2194-2351) is written as a
+// small state machine so that the kernel can run the warps of a block phase by phase (all warps of a block execute
+// the same phase's code between two block barriers, which is what keeps the instruction caches effective);
+// process_window below is the plain sequential driver over the same stages.
+enum { PH_BEGIN = 0, PH_HASH, PH_NODES, PH_TRAV, PH_FINAL, PH_END };
+struct WinState {
+  int ph;
+  Result res;
+  int lmin, lmax, k, ff, mintry;
+  bool pathfailed, have;
+  unsigned long long minrate;
+  int bestlen, bestk, bestff, bestn;
+};
+
+DCU_FN void st_overflow(Ctx& c, WinState& s) { s.res.status = ST_OVERFLOW; s.res.err = (uint32_t)c.overflow; s.ph = PH_END; }
+
+DCU_BIG void st_begin(Ctx& c, WinState& s, const Window& win, int lane) {
+  Result& res = s.res;
   res.status = ST_SKIPPED; res.k = 0; res.ff = -1; res.clen = 0; res.err = 0; res.nops = 0; res.ncand = 0; res.elength = 0;
+  s.ph = PH_END;
   load_window(c, win, lane);
-  if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
+  if (c.overflow) { st_overflow(c, s); return; }
   int elength = estimate_length(c, lane);
   res.elength = elength;
   if (c.MAo < DCU_P.mincov) return;
-  if (seqlen(c, 0) != DCU_P.w) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
-  int lmin = elength - 4, lmax = elength + 4;
-  bool pathfailed = true, have = false;
-  unsigned long long minrate = DCU_P.eminrate;
-  int bestlen = 0, bestk = 0, bestff = -1, bestn = 0;
-  DCU_NOUNROLL
-  for (int k = DCU_P.k_lo; k <= DCU_P.k_hi; ++k) {
-    c.k = k; c.kidx = k - DCU_P.k_lo; c.kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-    c.nex = 0;
-    build_hash(c, lane);
-    DCU_NOUNROLL
-    for (int ff = DCU_P.maxff; ff >= DCU_P.minff; --ff) {
-      int f = ff > 1 ? ff : 1;
-      if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
-      build_nodes(c, f, lane);
-      if (!c.overflow) node_weights(c, lane);
-      if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
-      if (ff == 0) {
-        gap_fill(c, lane);
-        if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
-        build_nodes(c, 1, lane);                         // setupNodes over all prenodes (:2248)
-        if (!c.overflow) node_weights(c, lane);
-        if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
-      }
-      build_edges(c, lane);
-      int mintry = 0; bool lconsok = false;
-      DCU_NOUNROLL
-      for (;;) {
-        int nacc = traverse(c, lmin, lmax, lane);
-        if (c.overflow) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
-        if (nacc > 0) {
-          unsigned long long e0 = bcast(w.acc_err()[0], 0);    // checkCandidatesU == error of candidate 0 (:5476-5482)
-          if (e0 < minrate) {
-            lconsok = true; minrate = e0; have = true;
-            int slot = w.acc_slot()[0]; bestlen = w.candlen()[slot]; bestk = k; bestff = ff; bestn = nacc;
-            DCU_NOUNROLL
-            for (int i = lane; i < bestlen; i += DCU_NL) w.best()[i] = w.cand()[slot * MAXCAND + i];
-            wsync();
-          } else if (have) lconsok = true;
-          break;
-        } else if (++mintry >= 3) break;
-        if (!add_next(c, lane)) break;
-      }
-      if (lconsok) { pathfailed = false; break; }
-    }
+  if (seqlen(c, 0) != DCU_P.w) { c.overflow = 19; st_overflow(c, s); return; }
+  s.lmin = elength - 4; s.lmax = elength + 4;
+  s.pathfailed = true; s.have = false; s.minrate = DCU_P.eminrate;
+  s.bestlen = 0; s.bestk = 0; s.bestff = -1; s.bestn = 0;
+  s.k = DCU_P.k_lo; s.ph = PH_HASH;
+}
+DCU_BIG void st_hash(Ctx& c, WinState& s, int lane) {
+  const int k = s.k;
+  c.k = k; c.kidx = k - DCU_P.k_lo; c.kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+  c.nex = 0;
+  build_hash(c, lane);
+  s.ff = DCU_P.maxff; s.ph = PH_NODES;
+}
+DCU_BIG void st_nodes(Ctx& c, WinState& s, int lane) {
+  const int ff = s.ff, f = ff > 1 ? ff : 1;
+  if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
+  build_nodes(c, f, lane);
+  if (!c.overflow) node_weights(c, lane);
+  if (c.overflow) { st_overflow(c, s); return; }
+  if (ff == 0) {
+    gap_fill(c, lane);
+    if (c.overflow) { st_overflow(c, s); return; }
+    build_nodes(c, 1, lane);                         // setupNodes over all prenodes (:2248)
+    if (!c.overflow) node_weights(c, lane);
+    if (c.overflow) { st_overflow(c, s); return; }
   }
-  if (pathfailed) { res.status = ST_FAILED; return; }
+  build_edges(c, lane);
+  s.mintry = 0; s.ph = PH_TRAV;
+}
+// next state once the tries at (k, ff) are over
+DCU_FN void st_after_tries(WinState& s, bool lconsok) {
+  bool nextk = lconsok;
+  if (lconsok) s.pathfailed = false;
+  else { s.ff -= 1; if (s.ff >= DCU_P.minff) { s.ph = PH_NODES; return; } nextk = true; }
+  if (nextk) { s.k += 1; s.ph = (s.k <= DCU_P.k_hi) ? PH_HASH : PH_FINAL; }
+}
+DCU_BIG void st_trav(Ctx& c, WinState& s, int lane) {
+  const WS& w = c.ws;
+  for (;;) {                       // up to 3 tries, activating the next edge frequency class in between (:2274-2322)
+    int nacc = traverse(c, s.lmin, s.lmax, lane);
+    if (c.overflow) { st_overflow(c, s); return; }
+    if (nacc > 0) {
+      bool lconsok = false;
+      unsigned long long e0 = bcast(w.acc_err()[0], 0);    // checkCandidatesU == error of candidate 0 (:5476-5482)
+      if (e0 < s.minrate) {
+        lconsok = true; s.minrate = e0; s.have = true;
+        int slot = w.acc_slot()[0]; s.bestlen = w.candlen()[slot]; s.bestk = s.k; s.bestff = s.ff; s.bestn = nacc;
+        DCU_NOUNROLL
+        for (int i = lane; i < s.bestlen; i += DCU_NL) w.best()[i] = w.cand()[slot * MAXCAND + i];
+        wsync();
+      } else if (s.have) lconsok = true;
+      st_after_tries(s, lconsok);
+      return;
+    }
+    if (++s.mintry >= 3) break;
+    if (!add_next(c, lane)) break;
+  }
+  st_after_tries(s, false);
+}
+DCU_BIG void st_final(Ctx& c, WinState& s, uint8_t* cons_out, uint8_t* ops_out, int lane) {
+  const WS& w = c.ws;
+  Result& res = s.res;
+  s.ph = PH_END;
+  if (s.pathfailed) { res.status = ST_FAILED; return; }
   int nops = 0;
   if (lane == 0) {
     DCU_NOUNROLL
-    for (int i = 0; i < bestlen; ++i) cons_out[i] = w.best()[i];
-    nops = placement(c, w.bases(), DCU_P.w, w.best(), bestlen, ops_out);
+    for (int i = 0; i < s.bestlen; ++i) cons_out[i] = w.best()[i];
+    nops = placement(c, w.bases(), DCU_P.w, w.best(), s.bestlen, ops_out);
   }
   nops = bcast(nops, 0);
-  if (nops < 0) { res.status = ST_OVERFLOW; res.err = (uint32_t)c.overflow; return; }
-  res.status = ST_OK; res.k = (uint8_t)bestk; res.ff = (int8_t)bestff; res.clen = (uint8_t)bestlen;
-  res.err = (uint32_t)minrate; res.nops = (uint16_t)nops; res.ncand = (uint16_t)bestn;
+  if (nops < 0) { c.overflow = 20; st_overflow(c, s); return; }
+  res.status = ST_OK; res.k = (uint8_t)s.bestk; res.ff = (int8_t)s.bestff; res.clen = (uint8_t)s.bestlen;
+  res.err = (uint32_t)s.minrate; res.nops = (uint16_t)nops; res.ncand = (uint16_t)s.bestn;
+}
+
+DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons_out, uint8_t* ops_out, int lane) {
+  WinState s;
+  st_begin(c, s, win, lane);
+  while (s.ph != PH_END) {
+    if (s.ph == PH_HASH) st_hash(c, s, lane);
+    else if (s.ph == PH_NODES) st_nodes(c, s, lane);
+    else if (s.ph == PH_TRAV) st_trav(c, s, lane);
+    else st_final(c, s, cons_out, ops_out, lane);
+  }
+  res = s.res;
 }
 
 }  // namespace dcu
