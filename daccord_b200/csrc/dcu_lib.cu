@@ -220,7 +220,7 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
   if (nwin >= 0xFFFFFFF0ull || nsl >= 0xFFFFFFF0ull) return DCU_ERR_UNSUPPORTED;
   CK(cudaSetDevice(ctx->device));
   // validate and size the workspaces for this batch
-  int maxS = 4, maxB = 64;
+  int maxS = 4, maxB = 64; uint64_t totS = 0;
   const uint64_t nbases = ctx->packed_bytes * 4;
   for (uint64_t i = 0; i < nwin; ++i) {
     const dcu_window& W = win[i];
@@ -233,14 +233,14 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
       b += s.len;
     }
     if (W.slice_cnt && sl[W.slice_begin].len != ctx->prm.w && W.slice_cnt >= ctx->prm.min_cov) { ctx->err = "slice 0 of a window must be the A window of length w"; return DCU_ERR_PARAM; }
-    maxS = std::max<int>(maxS, W.slice_cnt); maxB = std::max(maxB, b);
+    maxS = std::max<int>(maxS, W.slice_cnt); maxB = std::max(maxB, b); totS += W.slice_cnt;
   }
   if (maxS >= ctx->HT.KLIMN || maxB > 65000) { ctx->err = "pile deeper than this build supports"; return DCU_ERR_UNSUPPORTED; }
   ctx->maxS = maxS; ctx->maxB = maxB;
   // phase-synchronous group size: deep, homogeneous piles gain from large groups (instruction-cache locality); shallow
   // piles have a heavy tail of windows that need the filterfreq-1 pass, where waiting on the slowest warp costs more
   // than the locality brings (measured: profiles/r01_summary.md).  Results do not depend on it.
-  { double mean = nwin ? (double)nsl / (double)nwin : 0.0; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : (mean >= 30.0 ? 16 : (mean >= 16.0 ? 8 : 1)); }
+  { double mean = nwin ? (double)totS / (double)nwin : 0.0; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : (mean >= 30.0 ? 16 : (mean >= 16.0 ? 8 : 1)); }
   for (int t = 0; t < 2; ++t) { ctx->caps[t] = dcu_host::make_caps(t, (int)ctx->prm.w, maxS, maxB); dcu::make_layout(ctx->caps[t], ctx->lay[t]); }
   CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
   CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));

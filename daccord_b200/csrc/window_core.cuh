@@ -123,7 +123,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
 
 #define DCU_WS_FIELDS(X)                                                                                  \
   X(bases, uint8_t, c.B) X(soff, uint16_t, c.S + 1) X(lenhist, uint16_t, 256)                              \
-  X(hkey, uint32_t, c.H) X(hcnt, uint32_t, c.H) X(hnid, uint16_t, c.H) X(occ, uint32_t, c.NI + c.EX)         \
+  X(hs, uint32_t, 2 * c.H) X(occ, uint32_t, c.NI + c.EX)                                               \
   X(hstate, uint32_t, 4) X(islot, uint32_t, c.NI) X(praw, uint8_t, c.NI) X(rraw, uint8_t, c.NI)              \
   X(koff, uint16_t, c.S + 1) X(choff, uint16_t, c.S + 1) X(lastk, uint32_t, c.S)                            \
   X(ts_k, uint32_t, c.S) X(ts_c, uint16_t, c.S) X(ts_n, uint16_t, c.S)                                      \
@@ -216,8 +216,8 @@ DCU_NOINL int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> nod
   uint32_t h = hslot(c, v), mask = (uint32_t)DCU_CAP.H - 1;
   DCU_NOUNROLL
   for (;;) {
-    uint32_t key = c.ws.hkey()[h];
-    if (key == v) return c.ws.hnid()[h];
+    uint32_t key = c.ws.hs()[2 * h];
+    if (key == v) return (int)(c.ws.hs()[2 * h + 1] >> 16);
     if (key == W_EMPTY) return NID_NONE;
     h = (h + 1) & mask;
   }
@@ -364,9 +364,9 @@ DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
   uint32_t mask = (uint32_t)DCU_CAP.H - 1, h = hslot(c, v);
   DCU_NOUNROLL
   for (;;) {
-    uint32_t old = a_cas(&w.hkey()[h], W_EMPTY, v);
-    if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate()[0], 1); w.occ()[t] = h; a_add(&w.hcnt()[h], 1); break; }
-    if (old == v) { a_add(&w.hcnt()[h], 1); break; }
+    uint32_t old = a_cas(&w.hs()[2 * h], W_EMPTY, v);
+    if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate()[0], 1); w.occ()[t] = h; a_add(&w.hs()[2 * h + 1], 1); break; }
+    if (old == v) { a_add(&w.hs()[2 * h + 1], 1); break; }
     h = (h + 1) & mask;
   }
   return h;
@@ -375,13 +375,13 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
   const WS& w = c.ws;
   if (w.hstate()[1] != 0x600DF00Du) {          // first use of this slab: full initialisation
     DCU_NOUNROLL
-    for (int i = lane; i < DCU_CAP.H; i += DCU_NL) { w.hkey()[i] = W_EMPTY; w.hcnt()[i] = 0; w.hnid()[i] = NID_NONE; }
+    for (int i = lane; i < DCU_CAP.H; i += DCU_NL) { w.hs()[2 * i] = W_EMPTY; w.hs()[2 * i + 1] = 0xFFFF0000u; }
     wsync();
     if (lane == 0) { w.hstate()[0] = 0; w.hstate()[1] = 0x600DF00Du; }
   } else {
     int nocc = (int)w.hstate()[0];
     DCU_NOUNROLL
-    for (int i = lane; i < nocc; i += DCU_NL) { int h = w.occ()[i]; w.hkey()[h] = W_EMPTY; w.hcnt()[h] = 0; w.hnid()[h] = NID_NONE; }
+    for (int i = lane; i < nocc; i += DCU_NL) { int h = w.occ()[i]; w.hs()[2 * h] = W_EMPTY; w.hs()[2 * h + 1] = 0xFFFF0000u; }
     wsync();
     if (lane == 0) w.hstate()[0] = 0;
   }
@@ -457,12 +457,13 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   for (int base = 0; base < nocc; base += DCU_NL) {
     int t = base + lane;
     int i = t < nocc ? (int)w.occ()[t] : 0;
-    bool keep = (t < nocc) && ((int)w.hcnt()[i] >= f);
+    const uint32_t cv = t < nocc ? w.hs()[2 * i + 1] : 0; const int cnt = (int)(cv & 0xFFFFu);
+    bool keep = (t < nocc) && (cnt >= f);
     uint32_t b = ballot(keep);
     int idx = nn + popc(b & lanemask_lt(lane));
     if (keep) {
-      if (idx < DCU_CAP.NN) { w.n_kmer()[idx] = w.hkey()[i]; w.n_freq()[idx] = (uint16_t)w.hcnt()[i]; w.hnid()[i] = (uint16_t)idx; w.n_fill()[idx] = 0; }
-    } else if (t < nocc) w.hnid()[i] = NID_NONE;
+      if (idx < DCU_CAP.NN) { w.n_kmer()[idx] = w.hs()[2 * i]; w.n_freq()[idx] = (uint16_t)cnt; w.hs()[2 * i + 1] = (uint32_t)cnt | ((uint32_t)idx << 16); w.n_fill()[idx] = 0; }
+    } else if (t < nocc) w.hs()[2 * i + 1] = (uint32_t)cnt | 0xFFFF0000u;
     nn += popc(b);
   }
   if (nn > DCU_CAP.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
@@ -476,7 +477,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
     const int nraw = (int)w.koff()[c.MAo];
     DCU_NOUNROLL
     for (int q = lane; q < nraw; q += DCU_NL) {
-      int n = w.hnid()[w.islot()[q]];
+      int n = (int)(w.hs()[2 * w.islot()[q] + 1] >> 16);
       if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill()[n], 1); w.ipos()[w.n_ioff()[n] + t] = w.praw()[q]; w.irpos()[w.n_ioff()[n] + t] = w.rraw()[q]; }
     }
   }
@@ -821,6 +822,25 @@ DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
 DCU_FN int ds_first(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s]]; }
 DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s] + c.ws.ds_len()[s] - 1]; }
 
+// sum over the instance list ip[0,f) of col[min(ip[t],MS) * NP] (one table column per lane, instance positions shared by
+// the warp): the warp fetches the positions with one coalesced load per 32 instances and hands them round by shuffle
+DCU_FN unsigned long long inst_colsum(const uint8_t* ip, int f, const unsigned long long* col, int NP, int MS, int lane) {
+  unsigned long long u = 0;
+#ifdef DCU_EMU
+  for (int t = 0; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += col[a * NP]; }
+  (void)lane;
+#else
+  for (int t0 = 0; t0 < f; t0 += 32) {
+    int mine = (t0 + lane < f) ? (int)ip[t0 + lane] : 0;
+    mine = mine < MS ? mine : MS;
+    const int n = f - t0 < 32 ? f - t0 : 32;
+#pragma unroll 4
+    for (int t = 0; t < n; ++t) { int a = __shfl_sync(0xffffffffu, mine, t); u += col[a * NP]; }
+  }
+#endif
+  return u;
+}
+
 // computeFeasibleStretchPositions (:3176-3330).  Every stretch owns one slot per position of its anchor's
 // support range (forward: first k-mer, object p = start position; reverse: last k-mer, object p = its reverse
 // position); slot weight < 0 marks "not feasible".  Lanes over all slots of all stretches.
@@ -862,18 +882,14 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
         if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
           int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
           const uint8_t* ip = w.ipos() + w.n_ioff()[nF]; const int f = w.n_freq()[nF];
-          const unsigned long long* col = VT + p; unsigned long long u = 0;
-          DCU_NOUNROLL
-          for (int t = 0; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += col[a * NP]; }
+          const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
           double wt = in ? (double)u / 4294967296.0 : 0.0;
           if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
         }
         if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
           int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
           const uint8_t* ip = w.irpos() + w.n_ioff()[nR]; const int f = w.n_freq()[nR];
-          const unsigned long long* col = VT + p; unsigned long long u = 0;
-          DCU_NOUNROLL
-          for (int t = 0; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += col[a * NP]; }
+          const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
           double wt = in ? (double)u / 4294967296.0 : 0.0;
           if (ar) { if (wt >= 1e-3) sumr += wt; else ar = false; }
         }
