@@ -99,6 +99,20 @@ class Engine:
         self.nwin = len(win)
         self._ck(self.lib.dcu_upload(self.ctx, _p(win), C.c_uint64(len(win)), _p(sl), C.c_uint64(len(sl))))
 
+    def pile(self, ovl, trace, tspace, read_boff, read_len, advance=10, maxalign=2**64 - 1):
+        """trace reconstruction + window / slice extraction on the GPU; the batch stays resident (then launch / download)"""
+        nw, ns = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.dcu_pile(self.ctx, _p(ovl), C.c_uint64(len(ovl)), _p(trace), C.c_uint64(len(trace)), C.c_int32(tspace), _p(read_boff), _p(read_len),
+                                   C.c_uint64(len(read_len)), C.c_uint32(advance), C.c_uint64(maxalign), C.byref(nw), C.byref(ns)))
+        self.nwin, self.nsl = nw.value, ns.value
+        return nw.value, ns.value
+
+    def get_windows(self, with_slices=False):
+        win = np.zeros(self.nwin, WINDOW_DT)
+        sl = np.zeros(self.nsl, SLICE_DT) if with_slices else None
+        self._ck(self.lib.dcu_get_windows(self.ctx, _p(win), _p(sl)))
+        return (win, sl) if with_slices else win
+
     def launch(self):
         ms = C.c_float(0)
         self._ck(self.lib.dcu_launch(self.ctx, C.byref(ms)))

@@ -13,6 +13,7 @@
 #include "window_core.cuh"
 #include "host_tables.hpp"
 #include "host_caps.hpp"
+#include "pile_host.hpp"
 #include "../../include/daccord_b200.h"
 
 static_assert(sizeof(dcu::Slice) == sizeof(dcu_slice) && sizeof(dcu::Window) == sizeof(dcu_window) && sizeof(dcu::Result) == sizeof(dcu_result), "ABI structs");
@@ -88,6 +89,43 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
   }
 }
 
+
+// ---------------------------------------------------------------- piling kernels (pile_core.cuh), one thread per item
+__global__ void pile_k0(const dpile::Ovl* ovl, uint64_t novl, const uint16_t* trace, uint32_t* tile_b) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < novl) dpile::pile_tile_starts(ovl[i], trace, tile_b);
+}
+__global__ void __launch_bounds__(64) pile_k1(const dpile::Ovl* ovl, uint64_t novl, uint64_t ntiles, const dpile::ReadInfo* reads, dpile::Params P, const uint16_t* trace,
+                                              const uint32_t* tile_b, const uint8_t* packed, const uint64_t* read_boff, const uint32_t* read_len, uint32_t* bm) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  uint64_t a = 0, b = novl;                       // last overlap with tile_off <= t
+  while (b - a > 1) { uint64_t mid = (a + b) >> 1; if (ovl[mid].tile_off <= t) a = mid; else b = mid; }
+  const dpile::Ovl o = ovl[a];
+  const uint32_t l = reads[o.ridx].maxaepos, s0 = l >= P.w ? l - P.w : 0;
+  dpile::U128 PV[dpile::PILE_MAXB + 1], MV[dpile::PILE_MAXB + 1], PH[dpile::PILE_MAXB + 1], MH[dpile::PILE_MAXB + 1];
+  dpile::pile_align_tile(o, (int)(t - o.tile_off), P, trace, tile_b, packed, read_boff, read_len, s0, l, bm, PV, MV, PH, MH);
+}
+__global__ void pile_k2(const dpile::ReadInfo* reads, const uint32_t* read_id, uint64_t nr, const dpile::Ovl* ovl, dpile::Params P, const uint32_t* bm,
+                        const uint64_t* read_boff, const uint32_t* read_len, const double* minerate, const double* ediv, int fill,
+                        dpile::Win* win, dpile::Sl* sl, uint32_t* nwin, uint32_t* nsl, unsigned long long* act, int* err) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nr) return;
+  const dpile::ReadInfo R = reads[r];
+  uint32_t nw = 0, ns = 0;
+  int rc = dpile::pile_read(R, ovl, P, bm, read_boff, read_len, minerate[r], ediv[r], fill != 0, win, sl, &nw, &ns, act + R.ovl_begin, (int)(R.ovl_end - R.ovl_begin), read_id[r]);
+  if (rc) atomicExch(err, rc);
+  nwin[r] = nw; nsl[r] = ns;
+}
+// per-window pile statistics of a device-built batch: max slice count and max bases of a window
+__global__ void pile_k3(const dpile::Win* win, const dpile::Sl* sl, uint64_t nwin, unsigned int* maxS, unsigned int* maxB) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nwin) return;
+  const dpile::Win w = win[i]; unsigned int b = 0;
+  for (uint32_t j = 0; j < w.slice_cnt; ++j) b += sl[w.slice_begin + j].len;
+  atomicMax(maxS, (unsigned int)w.slice_cnt); atomicMax(maxB, b);
+}
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DCU_ERR_CUDA; } } while (0)
 
 template <class T> struct DevBuf {
@@ -125,6 +163,9 @@ struct dcu_ctx {
   dcu::Caps caps[2]; dcu::Layout lay[2]; int grid[2] = {0, 0};
   dcu::Caps slab_caps[2] = {}; uint32_t slab_bytes[2] = {0, 0};
   uint64_t nwin = 0, nsl = 0; int maxS = 0, maxB = 0;
+  // piling scratch
+  DevBuf<dpile::Ovl> dpo; DevBuf<dpile::ReadInfo> dpr; DevBuf<uint32_t> dprid, dptile, dpbm, dpnw, dpns, dprlen; DevBuf<uint64_t> dpboff; DevBuf<uint16_t> dptrace;
+  DevBuf<double> dpmin, dpdiv; DevBuf<unsigned long long> dpact;
   uint64_t launches = 0, hard = 0;
   std::string err;
 };
@@ -175,7 +216,7 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   ctx->T.suplo = ctx->dsuplo.p; ctx->T.suphi = ctx->dsuphi.p; ctx->T.NP = H.NP; ctx->T.MS = H.MS; ctx->T.KLIMN = H.KLIMN;
   ctx->P.w = (int)p->w; ctx->P.k_lo = (int)p->k_lo; ctx->P.k_hi = (int)p->k_hi; ctx->P.minff = p->min_ff; ctx->P.maxff = p->max_ff;
   ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err;
-  CK(ctx->dcnt.ensure(4));
+  CK(ctx->dcnt.ensure(8));
   const char* e = getenv("DCU_BLOCKS_PER_SM");
   if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);
   e = getenv("DCU_SYNC_GROUP");
@@ -189,6 +230,8 @@ void dcu_destroy(dcu_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->dDPn.release(); ctx->dDPsq.release(); ctx->dVSq.release(); ctx->dklim.release(); ctx->dsuplo.release(); ctx->dsuphi.release();
   ctx->dpacked_own.release(); ctx->dwin.release(); ctx->dsl.release(); ctx->dres.release(); ctx->dcons.release(); ctx->dops.release();
+  ctx->dpo.release(); ctx->dpr.release(); ctx->dprid.release(); ctx->dptile.release(); ctx->dpbm.release(); ctx->dpnw.release(); ctx->dpns.release(); ctx->dprlen.release();
+  ctx->dpboff.release(); ctx->dptrace.release(); ctx->dpmin.release(); ctx->dpdiv.release(); ctx->dpact.release();
   ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -214,6 +257,24 @@ int dcu_set_reads_device(dcu_ctx* ctx, const void* dpacked, uint64_t nbytes) {
   return DCU_OK;
 }
 
+// sizes the workspaces and result buffers for a batch whose descriptors are (or will be) in ctx->dwin / ctx->dsl
+static int finish_batch(dcu_ctx* ctx, int maxS, int maxB, uint64_t totS, uint64_t nwin, uint64_t nsl) {
+  if (maxS < 4) maxS = 4;
+  if (maxB < 64) maxB = 64;
+  if (maxS >= ctx->HT.KLIMN || maxB > 65000) { ctx->err = "pile deeper than this build supports"; return DCU_ERR_UNSUPPORTED; }
+  ctx->maxS = maxS; ctx->maxB = maxB;
+  // phase-synchronous group size: deep, homogeneous piles gain from large groups (instruction-cache locality); shallow
+  // piles have a heavy tail of windows that need the filterfreq-1 pass, where waiting on the slowest warp costs more
+  // than the locality brings (measured: profiles/r01_summary.md).  Results do not depend on it.
+  { double mean = nwin ? (double)totS / (double)nwin : 0.0; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : (mean >= 30.0 ? 16 : (mean >= 16.0 ? 8 : 1)); }
+  for (int t = 0; t < 2; ++t) { ctx->caps[t] = dcu_host::make_caps(t, (int)ctx->prm.w, maxS, maxB); dcu::make_layout(ctx->caps[t], ctx->lay[t]); }
+  CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
+  CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));
+  CK(ctx->dovf[0].ensure(nwin + 1)); CK(ctx->dovf[1].ensure(nwin + 1));
+  ctx->nwin = nwin; ctx->nsl = nsl;
+  return DCU_OK;
+}
+
 int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_slice* sl, uint64_t nsl) {
   if (!ctx || (!win && nwin) || (!sl && nsl)) return DCU_ERR_PARAM;
   if (!ctx->dpacked) { ctx->err = "dcu_set_reads not called"; return DCU_ERR_STATE; }
@@ -235,19 +296,85 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
     if (W.slice_cnt && sl[W.slice_begin].len != ctx->prm.w && W.slice_cnt >= ctx->prm.min_cov) { ctx->err = "slice 0 of a window must be the A window of length w"; return DCU_ERR_PARAM; }
     maxS = std::max<int>(maxS, W.slice_cnt); maxB = std::max(maxB, b); totS += W.slice_cnt;
   }
-  if (maxS >= ctx->HT.KLIMN || maxB > 65000) { ctx->err = "pile deeper than this build supports"; return DCU_ERR_UNSUPPORTED; }
-  ctx->maxS = maxS; ctx->maxB = maxB;
-  // phase-synchronous group size: deep, homogeneous piles gain from large groups (instruction-cache locality); shallow
-  // piles have a heavy tail of windows that need the filterfreq-1 pass, where waiting on the slowest warp costs more
-  // than the locality brings (measured: profiles/r01_summary.md).  Results do not depend on it.
-  { double mean = nwin ? (double)totS / (double)nwin : 0.0; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : (mean >= 30.0 ? 16 : (mean >= 16.0 ? 8 : 1)); }
-  for (int t = 0; t < 2; ++t) { ctx->caps[t] = dcu_host::make_caps(t, (int)ctx->prm.w, maxS, maxB); dcu::make_layout(ctx->caps[t], ctx->lay[t]); }
-  CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
-  CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));
-  CK(ctx->dovf[0].ensure(nwin + 1)); CK(ctx->dovf[1].ensure(nwin + 1));
+  int rc = finish_batch(ctx, maxS, maxB, totS, nwin, nsl);
+  if (rc) return rc;
   if (nwin) CK(cudaMemcpyAsync(ctx->dwin.p, win, nwin * sizeof(dcu_window), cudaMemcpyHostToDevice, ctx->stream));
   if (nsl) CK(cudaMemcpyAsync(ctx->dsl.p, sl, nsl * sizeof(dcu_slice), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->nwin = nwin; ctx->nsl = nsl;
+  return DCU_OK;
+}
+
+// trace reconstruction + window / slice extraction on the device (pile_core.cuh)
+int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t* trace, uint64_t ntrace, int32_t tspace,
+             const uint64_t* read_boff, const uint32_t* read_len, uint64_t nreads, uint32_t advance, uint64_t maxalign, uint64_t* nwin_out, uint64_t* nsl_out) {
+  if (!ctx || (!ovl && novl) || (!trace && ntrace) || !read_boff || !read_len) return DCU_ERR_PARAM;
+  if (!ctx->dpacked) { ctx->err = "dcu_set_reads not called"; return DCU_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  dpile::Prep P;
+  if (!dpile::prepare(ovl, novl, ntrace, tspace, ctx->prm.w, advance, nreads, read_len, P)) { ctx->err = P.err; return DCU_ERR_UNSUPPORTED; }
+  for (uint64_t i = 0; i < novl; ++i) {          // every B block must lie inside its read and fit the tile aligner
+    uint64_t b = (uint64_t)ovl[i].bbpos;
+    for (int32_t t = 1; t < ovl[i].tlen; t += 2) { uint16_t bl = trace[ovl[i].trace_off + t]; if (bl > dpile::PILE_MAXB) { ctx->err = "trace block longer than 256"; return DCU_ERR_UNSUPPORTED; } b += bl; }
+    if (b > read_len[ovl[i].bread]) { ctx->err = "trace points run past the B read"; return DCU_ERR_PARAM; }
+    if ((read_boff[ovl[i].bread] + (read_len[ovl[i].bread] + 3) / 4) > ctx->packed_bytes) { ctx->err = "read outside the packed database"; return DCU_ERR_PARAM; }
+  }
+  const uint64_t nr = P.reads.size();
+  dpile::Params prm; prm.tspace = tspace; prm.w = ctx->prm.w; prm.a = advance; prm.maxalign = maxalign;
+  CK(ctx->dpo.ensure(novl + 1)); CK(ctx->dpr.ensure(nr + 1)); CK(ctx->dprid.ensure(nr + 1)); CK(ctx->dptile.ensure(P.ntiles + 1)); CK(ctx->dpbm.ensure(P.nbm + 1));
+  CK(ctx->dpnw.ensure(nr + 1)); CK(ctx->dpns.ensure(nr + 1)); CK(ctx->dprlen.ensure(nreads + 1)); CK(ctx->dpboff.ensure(nreads + 1)); CK(ctx->dptrace.ensure(ntrace + 1));
+  CK(ctx->dpmin.ensure(nr + 1)); CK(ctx->dpdiv.ensure(nr + 1)); CK(ctx->dpact.ensure(novl + 1)); CK(ctx->dcnt.ensure(8));
+  cudaStream_t st = ctx->stream;
+  if (novl) CK(cudaMemcpyAsync(ctx->dpo.p, P.ovl.data(), novl * sizeof(dpile::Ovl), cudaMemcpyHostToDevice, st));
+  if (ntrace) CK(cudaMemcpyAsync(ctx->dptrace.p, trace, ntrace * 2, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->dpboff.p, read_boff, nreads * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->dprlen.p, read_len, nreads * 4, cudaMemcpyHostToDevice, st));
+  if (nr) {
+    CK(cudaMemcpyAsync(ctx->dpr.p, P.reads.data(), nr * sizeof(dpile::ReadInfo), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->dprid.p, P.read_id.data(), nr * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->dpmin.p, P.minerate.data(), nr * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->dpdiv.p, P.ediv.data(), nr * 8, cudaMemcpyHostToDevice, st));
+  }
+  uint64_t tw = 0, ts = 0;
+  unsigned int mx[2] = {4, 64};
+  if (novl) {
+    int* derr = (int*)(ctx->dcnt.p + 4);
+    CK(cudaMemsetAsync(ctx->dcnt.p + 4, 0, 4 * sizeof(unsigned int), st));
+    pile_k0<<<(unsigned)((novl + 127) / 128), 128, 0, st>>>(ctx->dpo.p, novl, ctx->dptrace.p, ctx->dptile.p);
+    pile_k1<<<(unsigned)((P.ntiles + 63) / 64), 64, 0, st>>>(ctx->dpo.p, novl, P.ntiles, ctx->dpr.p, prm, ctx->dptrace.p, ctx->dptile.p, ctx->dpacked, ctx->dpboff.p, ctx->dprlen.p, ctx->dpbm.p);
+    pile_k2<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(ctx->dpr.p, ctx->dprid.p, nr, ctx->dpo.p, prm, ctx->dpbm.p, ctx->dpboff.p, ctx->dprlen.p, ctx->dpmin.p, ctx->dpdiv.p, 0,
+                                                     nullptr, nullptr, ctx->dpnw.p, ctx->dpns.p, ctx->dpact.p, derr);
+    CK(cudaGetLastError());
+    std::vector<uint32_t> hnw(nr), hns(nr); int herr = 0;
+    CK(cudaMemcpyAsync(hnw.data(), ctx->dpnw.p, nr * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hns.data(), ctx->dpns.p, nr * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (herr) { ctx->err = "piling failed on the device (active-set capacity)"; return DCU_ERR_OVERFLOW; }
+    for (uint64_t r = 0; r < nr; ++r) { P.reads[r].win_off = tw; P.reads[r].sl_off = ts; tw += hnw[r]; ts += hns[r]; }
+    if (tw >= 0xFFFFFFF0ull || ts >= 0xFFFFFFF0ull) { ctx->err = "batch too large"; return DCU_ERR_UNSUPPORTED; }
+    CK(ctx->dwin.ensure(tw + 1)); CK(ctx->dsl.ensure(ts + 1));
+    CK(cudaMemcpyAsync(ctx->dpr.p, P.reads.data(), nr * sizeof(dpile::ReadInfo), cudaMemcpyHostToDevice, st));
+    pile_k2<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(ctx->dpr.p, ctx->dprid.p, nr, ctx->dpo.p, prm, ctx->dpbm.p, ctx->dpboff.p, ctx->dprlen.p, ctx->dpmin.p, ctx->dpdiv.p, 1,
+                                                     (dpile::Win*)ctx->dwin.p, (dpile::Sl*)ctx->dsl.p, ctx->dpnw.p, ctx->dpns.p, ctx->dpact.p, derr);
+    unsigned int* dmx = ctx->dcnt.p + 6;
+    CK(cudaMemcpyAsync(dmx, mx, sizeof(mx), cudaMemcpyHostToDevice, st));
+    if (tw) pile_k3<<<(unsigned)((tw + 255) / 256), 256, 0, st>>>((const dpile::Win*)ctx->dwin.p, (const dpile::Sl*)ctx->dsl.p, tw, dmx, dmx + 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(mx, dmx, sizeof(mx), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (herr) { ctx->err = "piling failed on the device (slice longer than 255 bases)"; return DCU_ERR_UNSUPPORTED; }
+  }
+  if (nwin_out) *nwin_out = tw;
+  if (nsl_out) *nsl_out = ts;
+  return finish_batch(ctx, (int)mx[0], (int)mx[1], ts, tw, ts);
+}
+
+int dcu_get_windows(dcu_ctx* ctx, dcu_window* win, dcu_slice* sl) {
+  if (!ctx) return DCU_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  if (win && ctx->nwin) CK(cudaMemcpyAsync(win, ctx->dwin.p, ctx->nwin * sizeof(dcu_window), cudaMemcpyDeviceToHost, ctx->stream));
+  if (sl && ctx->nsl) CK(cudaMemcpyAsync(sl, ctx->dsl.p, ctx->nsl * sizeof(dcu_slice), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return DCU_OK;
 }
 

@@ -109,6 +109,31 @@ dh_batch* dh_pile(dh_data* d, uint64_t first_read, uint64_t last_read, uint32_t 
   return B.release();
 }
 void dh_batch_destroy(dh_batch* b) { delete b; }
+
+// the overlaps daccord would hand to HandleContext for A-reads [first,last): top-D selection, ordered by abpos
+// (reference src/daccord.cpp:2112-2288), in the dcu_overlap form of the C ABI.  Buffers are malloc'ed (dh_free).
+struct dh_ovlset { std::vector<dcu_overlap> ovl; };
+dh_ovlset* dh_select_overlaps(dh_data* d, uint64_t first_read, uint64_t last_read, uint64_t maxinput) {
+  std::unique_ptr<dh_ovlset> S(new dh_ovlset());
+  if (last_read > d->db.rlen.size()) last_read = d->db.rlen.size();
+  std::vector<uint32_t> sel;
+  for (uint64_t r = first_read; r < last_read; ++r) {
+    select_overlaps(d->las, r, maxinput, sel);
+    for (auto i : sel) {
+      const Overlap& o = d->las.ovl[i];
+      dcu_overlap x; memset(&x, 0, sizeof(x));
+      x.abpos = o.abpos; x.aepos = o.aepos; x.bbpos = o.bbpos; x.bepos = o.bepos; x.flags = o.flags; x.aread = o.aread; x.bread = o.bread; x.diffs = o.diffs;
+      x.tlen = o.tlen; x.trace_off = o.trace_off;
+      S->ovl.push_back(x);
+    }
+  }
+  return S.release();
+}
+const dcu_overlap* dh_ovlset_data(dh_ovlset* s, uint64_t* n) { *n = s->ovl.size(); return s->ovl.data(); }
+void dh_ovlset_destroy(dh_ovlset* s) { delete s; }
+const uint16_t* dh_data_trace(dh_data* d, uint64_t* n) { *n = d->las.trace.size(); return d->las.trace.data(); }
+const uint64_t* dh_data_boff(dh_data* d) { return d->db.boff.data(); }
+const uint32_t* dh_data_rlen(dh_data* d) { return d->db.rlen.data(); }
 const dcu_window* dh_batch_windows(dh_batch* b, uint64_t* n) { *n = b->win.size(); return b->win.data(); }
 const dcu_slice* dh_batch_slices(dh_batch* b, uint64_t* n) { *n = b->sl.size(); return b->sl.data(); }
 const uint64_t* dh_batch_read_first(dh_batch* b, uint64_t* n) { *n = b->read_first.size(); return b->read_first.data(); }

@@ -6,6 +6,9 @@ from . import SLICE_DT, WINDOW_DT, RESULT_DT, CONS_STRIDE, OPS_STRIDE, DcuError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_HERE, "_build", "libdaccord_host.so")
+OVERLAP_DT = np.dtype([("abpos", "<i4"), ("aepos", "<i4"), ("bbpos", "<i4"), ("bepos", "<i4"), ("flags", "<u4"), ("aread", "<i4"), ("bread", "<i4"),
+                       ("diffs", "<i4"), ("tlen", "<i4"), ("reserved", "<i4"), ("trace_off", "<u8")])
+assert OVERLAP_DT.itemsize == 48
 _lib = None
 
 
@@ -15,7 +18,8 @@ def lib():
         if not os.path.exists(HOST_LIB_PATH):
             raise DcuError("host library %s not built: run `python -m daccord_b200.build`" % HOST_LIB_PATH)
         L = C.CDLL(HOST_LIB_PATH)
-        for f in ("dh_sim_create", "dh_data_load", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first"):
+        for f in ("dh_sim_create", "dh_data_load", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first",
+                  "dh_select_overlaps", "dh_ovlset_data", "dh_data_trace", "dh_data_boff", "dh_data_rlen"):
             getattr(L, f).restype = C.c_void_p
         for f in ("dh_data_nreads", "dh_data_novl", "dh_data_totlen"):
             getattr(L, f).restype = C.c_uint64
@@ -75,6 +79,25 @@ class Dataset:
         m, mis, ins, dele = [int(x) for x in a]
         ln = m + mis + dele
         return ins / ln, dele / ln, 1.0 - (mis + dele + ins) / ln
+
+    def overlaps(self, first=0, last=None, maxinput=5000):
+        """selected overlaps of A-reads [first,last) in dcu_overlap form + the trace array + read offsets / lengths (numpy copies)"""
+        last = self.nreads if last is None else last
+        h = lib().dh_select_overlaps(self.h, C.c_uint64(first), C.c_uint64(last), C.c_uint64(maxinput))
+        n = C.c_uint64(0)
+        p = lib().dh_ovlset_data(C.c_void_p(h), C.byref(n))
+        ovl = np.frombuffer((C.c_uint8 * (n.value * 48)).from_address(p), dtype=OVERLAP_DT).copy() if n.value else np.zeros(0, OVERLAP_DT)
+        lib().dh_ovlset_destroy(C.c_void_p(h))
+        p = lib().dh_data_trace(self.h, C.byref(n))
+        trace = np.frombuffer((C.c_uint8 * (n.value * 2)).from_address(p), dtype=np.uint16).copy() if n.value else np.zeros(0, np.uint16)
+        nr = self.nreads
+        boff = np.frombuffer((C.c_uint8 * (nr * 8)).from_address(lib().dh_data_boff(self.h)), dtype=np.uint64).copy()
+        rlen = np.frombuffer((C.c_uint8 * (nr * 4)).from_address(lib().dh_data_rlen(self.h)), dtype=np.uint32).copy()
+        return ovl, trace, boff, rlen
+
+    @property
+    def tspace(self):
+        return int(lib().dh_data_tspace(self.h))
 
     def pile(self, first=0, last=None, w=40, a=10, maxalign=2**64 - 1, maxinput=5000, nthreads=0):
         last = self.nreads if last is None else last

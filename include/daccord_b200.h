@@ -83,6 +83,22 @@ int dcu_run(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_slice*
 int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_slice* sl, uint64_t nsl);
 int dcu_launch(dcu_ctx* ctx, float* kernel_ms);   /* runs the resident batch; kernel_ms may be NULL */
 int dcu_download(dcu_ctx* ctx, dcu_result* res, uint8_t* cons, uint8_t* ops);
+/* ---- caller stage on the GPU: trace reconstruction + window / slice extraction --------------------
+ * Replaces, for w % a == 0 and tspace <= 128, the host work of reference src/HandleContext.hpp:1740-2049
+ * (OverlapDataInterface::computeTrace per activated overlap, advanceA / getStringLengthUsed per window, the active set
+ * ordered by (escore<<32)|z).  Input: the overlaps the caller selected for its A-reads (reference
+ * src/daccord.cpp:2112-2288: top -D by score, ordered by abpos), grouped by A-read in ascending order, with their
+ * trace points.  The descriptors are built in device memory and become the resident batch (as after dcu_upload). */
+typedef struct dcu_overlap {
+  int32_t abpos, aepos, bbpos, bepos; uint32_t flags; int32_t aread, bread, diffs;
+  int32_t tlen, reserved;       /* number of trace values (2 per tile) */
+  uint64_t trace_off;           /* index of this overlap's first value in `trace` */
+} dcu_overlap;
+int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t* trace, uint64_t ntrace, int32_t tspace,
+             const uint64_t* read_boff /* byte offset of every read in the packed DB */, const uint32_t* read_len, uint64_t nreads,
+             uint32_t advance, uint64_t maxalign, uint64_t* nwin, uint64_t* nsl);
+/* window descriptors of the resident batch (aread / astart are what the pile vote needs), nwin entries */
+int dcu_get_windows(dcu_ctx* ctx, dcu_window* win, dcu_slice* sl /* may be NULL */);
 /* statistics of the last launch: kernels launched, windows that needed the large-workspace pass */
 int dcu_last_stats(dcu_ctx* ctx, uint64_t* launches, uint64_t* hard_windows);
 /* dump the host-built tables (for tests): returns number of doubles written / needed */

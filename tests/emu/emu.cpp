@@ -57,3 +57,35 @@ extern "C" int64_t emu_get_tables(const dcu_params* prm, int which, double* out,
   if ((int64_t)v.size() <= cap) memcpy(out, v.data(), v.size() * sizeof(double));
   return (int64_t)v.size();
 }
+
+// ---- host emulation of the GPU piling stage (pile_core.cuh), for the parity test against the host piler
+#include "../../daccord_b200/csrc/pile_host.hpp"
+extern "C" int emu_pile(const dcu_overlap* ovl, uint64_t novl, const uint16_t* trace, uint64_t ntrace, int32_t tspace, const uint8_t* packed,
+                        const uint64_t* read_boff, const uint32_t* read_len, uint64_t nreads, uint32_t w, uint32_t a, uint64_t maxalign,
+                        dcu_window* win_out, uint64_t win_cap, dcu_slice* sl_out, uint64_t sl_cap, uint64_t* nwin, uint64_t* nsl) {
+  dpile::Prep P;
+  if (!dpile::prepare(ovl, novl, ntrace, tspace, w, a, nreads, read_len, P)) { fprintf(stderr, "emu_pile: %s\n", P.err.c_str()); return 1; }
+  dpile::Params prm; prm.tspace = tspace; prm.w = w; prm.a = a; prm.maxalign = maxalign;
+  std::vector<uint32_t> tile_b(P.ntiles + 1), bm(P.nbm + 1, 0xDEADBEEFu);
+  for (auto& o : P.ovl) dpile::pile_tile_starts(o, trace, tile_b.data());
+  std::vector<dpile::U128> PV(dpile::PILE_MAXB + 1), MV(dpile::PILE_MAXB + 1), PH(dpile::PILE_MAXB + 1), MH(dpile::PILE_MAXB + 1);
+  for (size_t r = 0; r < P.reads.size(); ++r) {
+    const uint32_t l = P.reads[r].maxaepos, s0 = l >= w ? l - w : 0, s1 = l;
+    for (uint64_t i = P.reads[r].ovl_begin; i < P.reads[r].ovl_end; ++i)
+      for (int t = 0; t < P.ovl[i].ntiles; ++t) dpile::pile_align_tile(P.ovl[i], t, prm, trace, tile_b.data(), packed, read_boff, read_len, s0, s1, bm.data(), PV.data(), MV.data(), PH.data(), MH.data());
+  }
+  std::vector<unsigned long long> act(novl + 1);
+  uint64_t tw = 0, ts = 0;
+  for (size_t r = 0; r < P.reads.size(); ++r) {
+    uint32_t nw = 0, ns = 0;
+    if (dpile::pile_read(P.reads[r], P.ovl.data(), prm, bm.data(), read_boff, read_len, P.minerate[r], P.ediv[r], false, nullptr, nullptr, &nw, &ns, act.data() + P.reads[r].ovl_begin, (int)(P.reads[r].ovl_end - P.reads[r].ovl_begin), P.read_id[r])) return 2;
+    P.reads[r].win_off = tw; P.reads[r].sl_off = ts; tw += nw; ts += ns;
+  }
+  *nwin = tw; *nsl = ts;
+  if (tw > win_cap || ts > sl_cap) return 3;
+  for (size_t r = 0; r < P.reads.size(); ++r) {
+    uint32_t nw = 0, ns = 0;
+    if (dpile::pile_read(P.reads[r], P.ovl.data(), prm, bm.data(), read_boff, read_len, P.minerate[r], P.ediv[r], true, (dpile::Win*)win_out, (dpile::Sl*)sl_out, &nw, &ns, act.data() + P.reads[r].ovl_begin, (int)(P.reads[r].ovl_end - P.reads[r].ovl_begin), P.read_id[r])) return 2;
+  }
+  return 0;
+}
