@@ -119,6 +119,29 @@ int main(int argc, char** argv) {
     std::vector<dcu_result> res; std::vector<uint8_t> cons, ops;
     for (int64_t b0 = minaread; b0 < toparead; b0 += (int64_t)batchreads) {
       const int64_t b1 = std::min<int64_t>(b0 + (int64_t)batchreads, toparead), nr = b1 - b0;
+      std::vector<dcu_window> win; std::vector<dcu_slice> sl; std::vector<uint64_t> first(nr + 1, 0);
+      const bool gpu_pile = (prm.w % advance == 0) && las.tspace <= 128 && !getenv("DACCORD_HOST_PILE");
+      if (gpu_pile) {
+        // overlap selection on the host (top -D, order by abpos), trace reconstruction + slices on the GPU
+        std::vector<dcu_overlap> ov; std::vector<uint32_t> sel;
+        for (int64_t r = b0; r < b1; ++r) {
+          select_overlaps(las, (uint64_t)r, maxinput, sel);
+          for (auto i : sel) { const Overlap& o = las.ovl[i]; dcu_overlap x; memset(&x, 0, sizeof(x)); x.abpos = o.abpos; x.aepos = o.aepos; x.bbpos = o.bbpos; x.bepos = o.bepos; x.flags = o.flags; x.aread = o.aread; x.bread = o.bread; x.diffs = o.diffs; x.tlen = o.tlen; x.trace_off = o.trace_off; ov.push_back(x); }
+        }
+        uint64_t nw = 0, ns = 0;
+        rc = dcu_pile(ctx, ov.data(), ov.size(), las.trace.data(), las.trace.size(), las.tspace, db.boff.data(), db.rlen.data(), db.rlen.size(), advance, maxalign, &nw, &ns);
+        if (rc) { fprintf(stderr, "[E] dcu_pile: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+        win.resize(nw);
+        rc = dcu_launch(ctx, nullptr);
+        if (rc) { fprintf(stderr, "[E] dcu_launch: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+        res.resize(nw); cons.resize(nw * DCU_CONS_STRIDE); ops.resize(nw * DCU_OPS_STRIDE);
+        rc = dcu_download(ctx, res.data(), cons.data(), ops.data());
+        if (!rc) rc = dcu_get_windows(ctx, win.data(), nullptr);
+        if (rc) { fprintf(stderr, "[E] dcu_download: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+        uint64_t wi = 0;
+        for (int64_t i = 0; i < nr; ++i) { first[i] = wi; while (wi < nw && (int64_t)win[wi].aread == b0 + i) ++wi; }
+        first[nr] = nw;
+      } else {
       std::vector<std::vector<dcu_window>> wv(nr); std::vector<std::vector<dcu_slice>> sv(nr);
       std::string perr;
 #pragma omp parallel num_threads(nthreads)
@@ -134,12 +157,12 @@ int main(int argc, char** argv) {
           }
         }
       }
-      std::vector<dcu_window> win; std::vector<dcu_slice> sl; std::vector<uint64_t> first(nr + 1, 0);
       for (int64_t i = 0; i < nr; ++i) { first[i] = win.size(); uint32_t base = (uint32_t)sl.size(); for (auto x : wv[i]) { x.slice_begin += base; win.push_back(x); } sl.insert(sl.end(), sv[i].begin(), sv[i].end()); }
       first[nr] = win.size();
       res.resize(win.size()); cons.resize(win.size() * DCU_CONS_STRIDE); ops.resize(win.size() * DCU_OPS_STRIDE);
       rc = dcu_run(ctx, win.data(), win.size(), sl.data(), sl.size(), res.data(), cons.data(), ops.data());
       if (rc) { fprintf(stderr, "[E] dcu_run: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+      }
       std::vector<std::string> parts(nr); std::vector<uint64_t> cnt(nr, 0);
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
       for (int64_t i = 0; i < nr; ++i) {
