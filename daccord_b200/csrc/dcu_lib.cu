@@ -403,7 +403,7 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
   if (vs_bytes > 40 * 1024) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);
-  a.sync_group = ctx->sync_group;
+  a.sync_group = tier ? 1 : ctx->sync_group;       // the large-workspace pass only sees heavy-tailed windows: free running
   dcu_window_kernel<<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;

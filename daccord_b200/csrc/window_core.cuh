@@ -140,7 +140,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST) X(du_off, uint16_t, c.ST) X(du_len, uint16_t, c.ST)  \
   X(ds_rlO, uint16_t, c.ST) X(ds_rlN, uint16_t, c.ST)                                                      \
   X(ds_fB, uint8_t, c.ST) X(ds_fN, uint8_t, c.ST) X(ds_cB, uint8_t, c.ST) X(ds_cN, uint8_t, c.ST)          \
-  X(sf_w, double, c.SF) X(sc_w, double, c.SF)                                                              \
+  X(sf_w, double, c.SF) X(sc_w, double, c.SF) X(sc_wf, double, c.SF)                                        \
   X(n_pf, uint8_t, c.NN) X(n_pt, uint8_t, c.NN) X(n_cpf, uint8_t, c.NN) X(n_cpt, uint8_t, c.NN)            \
   X(n_kwo, uint32_t, c.NN) X(n_ckwo, uint32_t, c.NN) X(kwF, double, 2) X(kwR, double, 2)                           \
   X(n_dsf, uint16_t, c.NN) X(n_dsn, uint8_t, c.NN) X(skey, unsigned long long, c.STP)                      \
@@ -233,7 +233,7 @@ DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
   unsigned long long u = 0;
   DCU_NOUNROLL
   for (int t = 0; t < f; ++t) { int pos = ip[t]; pos = pos < DCU_T.MS ? pos : DCU_T.MS; u += col[(size_t)pos * DCU_T.NP]; }
-  return (double)u / 4294967296.0;
+  return (double)u * 2.3283064365386963e-10;
 }
 
 // bounded binary heap on (weight,id) pairs; convention C2 of oracle/README.md.  MAXH: top = largest weight.
@@ -874,7 +874,7 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
     for (int q0 = 0; q0 < nmax; q0 += DCU_NL) {
       const int q = q0 + lane;
       bool af = q < nf, ar = q < nr;
-      double sumf = 0.0, sumr = 0.0;
+      double sumf = 0.0, sumr = 0.0, wfr = 0.0;
       DCU_NOUNROLL
       for (int jj = 0; jj < L; ++jj) {
         if (!ballot(af || ar)) break;
@@ -883,19 +883,19 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
           int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
           const uint8_t* ip = w.ipos() + w.n_ioff()[nF]; const int f = w.n_freq()[nF];
           const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
-          double wt = in ? (double)u / 4294967296.0 : 0.0;
+          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
           if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
         }
         if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
           int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
           const uint8_t* ip = w.irpos() + w.n_ioff()[nR]; const int f = w.n_freq()[nR];
           const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
-          double wt = in ? (double)u / 4294967296.0 : 0.0;
-          if (ar) { if (wt >= 1e-3) sumr += wt; else ar = false; }
+          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
+          if (ar) { if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false; }
         }
       }
       if (q < nf) w.sf_w()[w.ds_fO()[s] + q] = af ? sumf : -1.0;
-      if (q < nr) w.sc_w()[w.ds_cO()[s] + q] = ar ? sumr : -1.0;
+      if (q < nr) { w.sc_w()[w.ds_cO()[s] + q] = ar ? sumr : -1.0; w.sc_wf()[w.ds_cO()[s] + q] = wfr; }
     }
   }
   wsync();
@@ -940,7 +940,7 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
         double wb = w.sc_w()[co + d];
         if (!(wb >= 0.0)) continue;
         int oa = sfo_rev(c, A, cb + d + shift);
-        if (oa >= 0) { double lw = wb + (w.sc_w()[oa] - rev_wf(c, A, cb + d + shift)); weight = lw > weight ? lw : weight; }
+        if (oa >= 0) { double lw = wb + (w.sc_w()[oa] - w.sc_wf()[oa]); weight = lw > weight ? lw : weight; }
       }
       if (weight >= 1e-1) { uint32_t t = a_add(cnt, 1); if ((int)t < DCU_CAP.RL) w.rl()[t] = ((uint32_t)B << 16) | (uint32_t)A; }
     }
@@ -1051,7 +1051,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
         int o = sfo_rev(c, s, rpos);
         if (o >= 0 && w.sc_w()[o] >= 0.5) {
           int L = w.ds_len()[s];
-          double nw = wt + (w.sc_w()[o] - rev_wf(c, s, rpos));
+          double nw = wt + (w.sc_w()[o] - w.sc_wf()[o]);
           int nid = rp_new(c, nrp, nw, (uint32_t)id, w.n_kmer()[ds_first(c, s)], s, rpos + L - 1, rlen + 1, bl + L - 1);
           if (nid < 0) return;
           if (nq >= DCU_CAP.RP) { c.overflow = 13; return; }
@@ -1238,7 +1238,13 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
 }
 
 // returns number of candidates, ordered as ACC after the error sort (:5101-5156)
+#ifdef DCU_EMU_STATS
+static long g_stats[16];
+#endif
 DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
+#ifdef DCU_EMU_STATS
+  g_stats[6]++;
+#endif
   const WS& w = c.ws;
   raw_stretches(c, lane);
   if (c.overflow) return 0;
@@ -1252,6 +1258,9 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
       int F = w.fl_nid()[fi];
       int L = lookup(c, w.ll_kmer()[li]);
       if (L == NID_NONE) continue;        // no reverse seed (:3582) => no pairs; forward search has no side effects
+#ifdef DCU_EMU_STATS
+      g_stats[0]++; 
+#endif
       derive_stretches(c, F, L, lane);
       if (c.overflow) return 0;
       stretch_positions(c, lane);
@@ -1263,6 +1272,9 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
       c.overflow = bcast(c.overflow, 0); narp = bcast(narp, 0);
       wsync();
       if (c.overflow) return 0;
+#ifdef DCU_EMU_STATS
+      g_stats[1] += narp; g_stats[2] += c.nds; g_stats[3] += c.nn; g_stats[4] += c.nrl; { long sl=0; for (int s=0;s<c.nds;++s) sl += c.ws.ds_len()[s]; g_stats[5] += sl; }
+#endif
       sort_reverse_paths(c, narp, lane);
       if (lane == 0) search_pair(c, F, lmin, lmax, narp, ncdh, freeslots);
       c.overflow = bcast(c.overflow, 0);

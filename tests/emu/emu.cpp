@@ -41,6 +41,10 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
     memcpy(&res[i], &r, sizeof(r));
     if (r.status == dcu::ST_OVERFLOW) ++nov;
   }
+#ifdef DCU_EMU_STATS
+  fprintf(stderr, "windows %lu traverse calls %ld pairs %ld narp/pair %.1f nds/pair %.1f nn %.1f nrl %.1f links/pair %.1f\n", (unsigned long)nwin, dcu::g_stats[6], dcu::g_stats[0], (double)dcu::g_stats[1] / dcu::g_stats[0], (double)dcu::g_stats[2] / dcu::g_stats[0], (double)dcu::g_stats[3] / dcu::g_stats[0], (double)dcu::g_stats[4] / dcu::g_stats[0], (double)dcu::g_stats[5] / dcu::g_stats[0]);
+  for (int i = 0; i < 16; ++i) dcu::g_stats[i] = 0;
+#endif
   if (noverflow) *noverflow = nov;
   return 0;
 }
