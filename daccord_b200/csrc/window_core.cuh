@@ -1237,51 +1237,71 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
   }
 }
 
-// returns number of candidates, ordered as ACC after the error sort (:5101-5156)
+// traverse (:4496-5170) as a resumable sequence so that the kernel can interleave it with other warps' stages:
+// trav_start (unitigs, first / last thresholds), trav_pair (one admissible (first,last) pair per call),
+// trav_finish (candidate heap -> scored, error-sorted list)
 #ifdef DCU_EMU_STATS
 static long g_stats[16];
 #endif
-DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
+struct TravState { int fi, li, ncdh, firstthres, lastthres; uint32_t freeslots; bool started; };
+
+DCU_BIG void trav_start(Ctx& c, TravState& t, int lane) {
 #ifdef DCU_EMU_STATS
   g_stats[6]++;
 #endif
   const WS& w = c.ws;
   raw_stretches(c, lane);
-  if (c.overflow) return 0;
-  int ncdh = 0; uint32_t freeslots = (1u << (CDH_N + 1)) - 1;
-  int firstthres = c.nfirst ? (w.fl_cnt()[0] * 3) / 4 : 0;
-  int lastthres = c.nlast ? (w.ll_cnt()[0] * 3) / 4 : 0;
+  t.ncdh = 0; t.freeslots = (1u << (CDH_N + 1)) - 1;
+  t.firstthres = c.nfirst ? (w.fl_cnt()[0] * 3) / 4 : 0;
+  t.lastthres = c.nlast ? (w.ll_cnt()[0] * 3) / 4 : 0;
+  t.fi = 0; t.li = 0; t.started = true;
+}
+// moves (fi, li) to the next pair whose last k-mer is a node (:3582: no reverse seed otherwise => the pair cannot
+// produce candidates and its forward search has no side effects); returns false when the pairs are exhausted
+DCU_BIG bool trav_seek(Ctx& c, TravState& t) {
+  const WS& w = c.ws;
   DCU_NOUNROLL
-  for (int fi = 0; fi < c.nfirst && w.fl_cnt()[fi] >= firstthres; ++fi)
-    DCU_NOUNROLL
-    for (int li = 0; li < c.nlast && w.ll_cnt()[li] >= lastthres; ++li) {
-      int F = w.fl_nid()[fi];
-      int L = lookup(c, w.ll_kmer()[li]);
-      if (L == NID_NONE) continue;        // no reverse seed (:3582) => no pairs; forward search has no side effects
+  for (;;) {
+    if (!(t.fi < c.nfirst && w.fl_cnt()[t.fi] >= t.firstthres)) return false;
+    if (!(t.li < c.nlast && w.ll_cnt()[t.li] >= t.lastthres)) { t.fi += 1; t.li = 0; continue; }
+    if (lookup(c, w.ll_kmer()[t.li]) != NID_NONE) return true;
+    t.li += 1;
+  }
+}
+// one (first,last) pair at (fi, li), then advances li  (:4802-5097)
+DCU_BIG void trav_pair(Ctx& c, TravState& t, int lmin, int lmax, int lane) {
+  const WS& w = c.ws;
+  const int F = w.fl_nid()[t.fi];
+  const int L = lookup(c, w.ll_kmer()[t.li]);
+  t.li += 1;
 #ifdef DCU_EMU_STATS
-      g_stats[0]++; 
+  g_stats[0]++;
 #endif
-      derive_stretches(c, F, L, lane);
-      if (c.overflow) return 0;
-      stretch_positions(c, lane);
-      if (c.overflow) return 0;
-      stretch_links(c, lane);
-      if (c.overflow) return 0;
-      int narp = 0;
-      if (lane == 0) reverse_paths(c, L, lmax, narp);
-      c.overflow = bcast(c.overflow, 0); narp = bcast(narp, 0);
-      wsync();
-      if (c.overflow) return 0;
+  derive_stretches(c, F, L, lane);
+  if (c.overflow) return;
+  stretch_positions(c, lane);
+  if (c.overflow) return;
+  stretch_links(c, lane);
+  if (c.overflow) return;
+  int narp = 0;
+  if (lane == 0) reverse_paths(c, L, lmax, narp);
+  c.overflow = bcast(c.overflow, 0); narp = bcast(narp, 0);
+  wsync();
+  if (c.overflow) return;
 #ifdef DCU_EMU_STATS
-      g_stats[1] += narp; g_stats[2] += c.nds; g_stats[3] += c.nn; g_stats[4] += c.nrl; { long sl=0; for (int s=0;s<c.nds;++s) sl += c.ws.ds_len()[s]; g_stats[5] += sl; }
+  g_stats[1] += narp; g_stats[2] += c.nds; g_stats[3] += c.nn; g_stats[4] += c.nrl; { long sl = 0; for (int s = 0; s < c.nds; ++s) sl += c.ws.ds_len()[s]; g_stats[5] += sl; }
 #endif
-      sort_reverse_paths(c, narp, lane);
-      if (lane == 0) search_pair(c, F, lmin, lmax, narp, ncdh, freeslots);
-      c.overflow = bcast(c.overflow, 0);
-      wsync();
-      if (c.overflow) return 0;
-    }
-  // CDH -> CH -> ACC (descending weight, heap tie order) (:5101-5136)
+  sort_reverse_paths(c, narp, lane);
+  int ncdh = t.ncdh; uint32_t fs = t.freeslots;
+  if (lane == 0) search_pair(c, F, lmin, lmax, narp, ncdh, fs);
+  t.ncdh = bcast(ncdh, 0); t.freeslots = bcast(fs, 0);
+  c.overflow = bcast(c.overflow, 0);
+  wsync();
+}
+// CDH -> CH -> ACC (descending weight, heap tie order), candidate errors, stable sort by error (:5101-5156)
+DCU_BIG int trav_finish(Ctx& c, TravState& t, int lane) {
+  const WS& w = c.ws;
+  int ncdh = t.ncdh;
   int nacc = 0;
   if (lane == 0) {
     int nch = 0;
@@ -1315,6 +1335,7 @@ DCU_BIG int traverse(Ctx& c, int lmin, int lmax, int lane) {
     }
   }
   wsync();
+  t.started = false;
   return nacc;
 }
 
@@ -1375,6 +1396,7 @@ struct WinState {
   bool pathfailed, have;
   unsigned long long minrate;
   int bestlen, bestk, bestff, bestn;
+  TravState tv;
 };
 
 DCU_FN void st_overflow(Ctx& c, WinState& s) { s.res.status = ST_OVERFLOW; s.res.err = (uint32_t)c.overflow; s.ph = PH_END; }
@@ -1415,7 +1437,7 @@ DCU_BIG void st_nodes(Ctx& c, WinState& s, int lane) {
     if (c.overflow) { st_overflow(c, s); return; }
   }
   build_edges(c, lane);
-  s.mintry = 0; s.ph = PH_TRAV;
+  s.mintry = 0; s.tv.started = false; s.ph = PH_TRAV;
 }
 // next state once the tries at (k, ff) are over
 DCU_FN void st_after_tries(WinState& s, bool lconsok) {
@@ -1424,28 +1446,34 @@ DCU_FN void st_after_tries(WinState& s, bool lconsok) {
   else { s.ff -= 1; if (s.ff >= DCU_P.minff) { s.ph = PH_NODES; return; } nextk = true; }
   if (nextk) { s.k += 1; s.ph = (s.k <= DCU_P.k_hi) ? PH_HASH : PH_FINAL; }
 }
+// one call = at most one (first,last) pair of the current traverse; the call that exhausts the pairs also scores the
+// candidates and takes the decision of the try loop (:2274-2322: up to 3 tries, next edge frequency class in between)
 DCU_BIG void st_trav(Ctx& c, WinState& s, int lane) {
   const WS& w = c.ws;
-  for (;;) {                       // up to 3 tries, activating the next edge frequency class in between (:2274-2322)
-    int nacc = traverse(c, s.lmin, s.lmax, lane);
+  TravState& t = s.tv;
+  if (!t.started) { trav_start(c, t, lane); if (c.overflow) { st_overflow(c, s); return; } }
+  if (trav_seek(c, t)) {
+    trav_pair(c, t, s.lmin, s.lmax, lane);
     if (c.overflow) { st_overflow(c, s); return; }
-    if (nacc > 0) {
-      bool lconsok = false;
-      unsigned long long e0 = bcast(w.acc_err()[0], 0);    // checkCandidatesU == error of candidate 0 (:5476-5482)
-      if (e0 < s.minrate) {
-        lconsok = true; s.minrate = e0; s.have = true;
-        int slot = w.acc_slot()[0]; s.bestlen = w.candlen()[slot]; s.bestk = s.k; s.bestff = s.ff; s.bestn = nacc;
-        DCU_NOUNROLL
-        for (int i = lane; i < s.bestlen; i += DCU_NL) w.best()[i] = w.cand()[slot * MAXCAND + i];
-        wsync();
-      } else if (s.have) lconsok = true;
-      st_after_tries(s, lconsok);
-      return;
-    }
-    if (++s.mintry >= 3) break;
-    if (!add_next(c, lane)) break;
+    if (trav_seek(c, t)) { s.ph = PH_TRAV; return; }      // more pairs: next round
   }
-  st_after_tries(s, false);
+  int nacc = trav_finish(c, t, lane);
+  if (nacc > 0) {
+    bool lconsok = false;
+    unsigned long long e0 = bcast(w.acc_err()[0], 0);    // checkCandidatesU == error of candidate 0 (:5476-5482)
+    if (e0 < s.minrate) {
+      lconsok = true; s.minrate = e0; s.have = true;
+      int slot = w.acc_slot()[0]; s.bestlen = w.candlen()[slot]; s.bestk = s.k; s.bestff = s.ff; s.bestn = nacc;
+      DCU_NOUNROLL
+      for (int i = lane; i < s.bestlen; i += DCU_NL) w.best()[i] = w.cand()[slot * MAXCAND + i];
+      wsync();
+    } else if (s.have) lconsok = true;
+    st_after_tries(s, lconsok);
+    return;
+  }
+  if (++s.mintry >= 3) { st_after_tries(s, false); return; }
+  if (!add_next(c, lane)) { st_after_tries(s, false); return; }
+  s.ph = PH_TRAV;                                          // retry: the next call starts a new traverse
 }
 DCU_BIG void st_final(Ctx& c, WinState& s, uint8_t* cons_out, uint8_t* ops_out, int lane) {
   const WS& w = c.ws;
