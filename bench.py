@@ -210,7 +210,7 @@ def main():
     alg_bytes, _ = algorithmic_bytes(win, sl, res)
     tsec = kms / 1e3
     # ---- end-to-end leg through dcu_run (host buffers)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(max(args.warmup, 1)):
         eng.run(win, sl, out)
     barrier()
     t0 = time.perf_counter()
