@@ -16,10 +16,10 @@ inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
   c.H = 1 << c.LOGH;
   c.BL = w + 8;
   if (tier == 0) {
-    c.NN = 512; c.ST = 256; c.SL = 2048; c.SF = 8192; c.RL = 512; c.RP = 1024; c.FP = 1024; c.SI = 1024; c.KW = 12288;
+    c.NN = 4096; c.ST = 1024; c.SL = 8192; c.SF = 16384; c.RL = 2048; c.RP = 2048; c.FP = 2048; c.SI = 2048; c.KW = 2;
   } else {
     c.NN = c.NI + c.EX; if (c.NN > 65000) c.NN = 65000;
-    c.ST = 8192; c.SL = 65000; c.SF = 65000; c.RL = 32768; c.RP = 32768; c.FP = 32768; c.SI = 32768; c.KW = 1 << 19;
+    c.ST = 8192; c.SL = 65000; c.SF = 65000; c.RL = 32768; c.RP = 32768; c.FP = 32768; c.SI = 32768; c.KW = 2;
   }
   if (c.NN > c.NI + c.EX) c.NN = c.NI + c.EX;
   c.STP = 1 << ceil_pow2_log(c.ST);

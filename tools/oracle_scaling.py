@@ -1,5 +1,5 @@
 import sys, time, os
-sys.path.insert(0, "tests")
+sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "..", "tests")); sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), ".."))
 import numpy as np
 from common import default_params, run_oracle
 from daccord_b200.host import Dataset
