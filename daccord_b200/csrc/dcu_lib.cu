@@ -268,6 +268,7 @@ static int finish_batch(dcu_ctx* ctx, int maxS, int maxB, uint64_t totS, uint64_
   // than the locality brings (measured: profiles/r01_summary.md).  Results do not depend on it.
   { double mean = nwin ? (double)totS / (double)nwin : 0.0; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : (mean >= 30.0 ? 16 : (mean >= 16.0 ? 8 : 1)); }
   for (int t = 0; t < 2; ++t) { ctx->caps[t] = dcu_host::make_caps(t, (int)ctx->prm.w, maxS, maxB); dcu::make_layout(ctx->caps[t], ctx->lay[t]); }
+  { const char* e = getenv("DCU_HEAVY_NN"); if (e) ctx->caps[0].HEAVY = atoi(e); if (ctx->sync_group == 1) ctx->caps[0].HEAVY = 0; }   // free-running batches keep heavy windows in place
   CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
   CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));
   CK(ctx->dovf[0].ensure(nwin + 1)); CK(ctx->dovf[1].ensure(nwin + 1));

@@ -111,7 +111,7 @@ struct Params {
   unsigned long long eminrate;
 };
 // capacities of one warp's workspace (two tiers: small for the common case, large for the rest)
-struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, STP, SL, SF, RL, RLP, RP, FP, SI, BL, KW; };
+struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, STP, SL, SF, RL, RLP, RP, FP, SI, BL, KW, HEAVY; };
 
 struct Slice { uint32_t gpos; uint16_t len; uint16_t flags; };
 struct Window { uint32_t slice_begin; uint16_t slice_cnt; uint16_t reserved; uint32_t aread; uint32_t astart; };
@@ -467,6 +467,9 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
     nn += popc(b);
   }
   if (nn > DCU_CAP.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
+  // graphs this large (the filterfreq-1 fall-through) take ~50 ms on one warp: in the phase-synchronous pass they would
+  // hold their whole warp group, so they are handed to the free-running large-workspace pass instead
+  if (DCU_CAP.HEAVY && nn > DCU_CAP.HEAVY) { c.overflow = 21; c.nn = 0; wsync(); return; }
   c.nn = nn;
   wsync();
   if (lane == 0) { uint32_t o = 0; for (int n = 0; n < nn; ++n) { w.n_ioff()[n] = o; o += w.n_freq()[n]; } c.ni = (int)o; }
