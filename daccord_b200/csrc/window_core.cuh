@@ -142,7 +142,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(ds_fB, uint8_t, c.ST) X(ds_fN, uint8_t, c.ST) X(ds_cB, uint8_t, c.ST) X(ds_cN, uint8_t, c.ST)          \
   X(sf_w, double, c.SF) X(sc_w, double, c.SF) X(sc_wf, double, c.SF)                                        \
   X(n_pf, uint8_t, c.NN) X(n_pt, uint8_t, c.NN) X(n_cpf, uint8_t, c.NN) X(n_cpt, uint8_t, c.NN)            \
-  X(n_kwo, uint32_t, c.NN) X(n_ckwo, uint32_t, c.NN) X(kwF, double, 2) X(kwR, double, 2)                           \
+               \
   X(n_dsf, uint16_t, c.NN) X(n_dsn, uint8_t, c.NN) X(skey, unsigned long long, c.STP)                      \
   X(rl, uint32_t, c.RLP)                                                                                   \
   X(rp_w, double, c.RP) X(rp_parent, uint32_t, c.RP) X(rp_front, uint32_t, c.RP)                           \
@@ -589,29 +589,21 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
   return true;
 }
 
-// ------------------------------------------------------------------ dense per-node position weights
-// computeFeasibleKmerPositions (:3117-3174): weight of every node at every true position of its support
-// range, forward (PF) and reverse (RPF); a value below 1e-3 means "not feasible".  Lanes over (node,position).
-DCU_BIG void node_weights(Ctx& c, int lane) {
+// ------------------------------------------------------------------ per-node support ranges
+// computeFeasibleKmerPositions (:3117-3174) evaluates every node at every true position of its support range
+// [supportLow(plow), supportHigh(phigh)) (forward, PF) and the mirrored range (reverse, RPF).  Only the ranges are
+// materialised here; the weights themselves (:3826-3904) are fixed-point sums evaluated where they are consumed
+// (stretch_positions, kw_fwd / kw_rev).
+DCU_BIG void node_ranges(Ctx& c, int lane) {
   const WS& w = c.ws;
-  uint32_t run0 = 0, run1 = 0;
   DCU_NOUNROLL
-  for (int base = 0; base < c.nn; base += DCU_NL) {
-    int n = base + lane;
-    uint32_t a = 0, b = 0;
-    if (n < c.nn) {
-      int pf = sup_lo(c, w.n_plow()[n]), pt = sup_hi(c, w.n_phigh()[n]);
-      int cf = sup_lo(c, w.n_cplow()[n]), ct = sup_hi(c, w.n_cphigh()[n]);
-      if (pt < pf) pt = pf;
-      if (ct < cf) ct = cf;
-      w.n_pf()[n] = (uint8_t)pf; w.n_pt()[n] = (uint8_t)pt; w.n_cpf()[n] = (uint8_t)cf; w.n_cpt()[n] = (uint8_t)ct;
-      a = (uint32_t)(pt - pf); b = (uint32_t)(ct - cf);
-    }
-    uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
-    if (n < c.nn) { w.n_kwo()[n] = run0 + ia - a; w.n_ckwo()[n] = run1 + ib - b; }
-    run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
+  for (int n = lane; n < c.nn; n += DCU_NL) {
+    int pf = sup_lo(c, w.n_plow()[n]), pt = sup_hi(c, w.n_phigh()[n]);
+    int cf = sup_lo(c, w.n_cplow()[n]), ct = sup_hi(c, w.n_cphigh()[n]);
+    if (pt < pf) pt = pf;
+    if (ct < cf) ct = cf;
+    w.n_pf()[n] = (uint8_t)pf; w.n_pt()[n] = (uint8_t)pt; w.n_cpf()[n] = (uint8_t)cf; w.n_cpt()[n] = (uint8_t)ct;
   }
-  wsync();
   wsync();
 }
 DCU_NOINL double kw_fwd(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_T.NP) ? kweight(c, n, p, false) : 0.0; }
@@ -1430,13 +1422,13 @@ DCU_BIG void st_nodes(Ctx& c, WinState& s, int lane) {
   const int ff = s.ff, f = ff > 1 ? ff : 1;
   if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
   build_nodes(c, f, lane);
-  if (!c.overflow) node_weights(c, lane);
+  if (!c.overflow) node_ranges(c, lane);
   if (c.overflow) { st_overflow(c, s); return; }
   if (ff == 0) {
     gap_fill(c, lane);
     if (c.overflow) { st_overflow(c, s); return; }
     build_nodes(c, 1, lane);                         // setupNodes over all prenodes (:2248)
-    if (!c.overflow) node_weights(c, lane);
+    if (!c.overflow) node_ranges(c, lane);
     if (c.overflow) { st_overflow(c, s); return; }
   }
   build_edges(c, lane);

@@ -44,6 +44,10 @@ CASES = [
     ("w56", dict(depth=25, n=150, seed=13, rf=0.2), dict(w=56)),
     ("nocor", dict(depth=25, n=150, seed=14, rf=0.2), dict(est_cor=0.0)),
     ("deep", dict(depth=200, n=40, seed=15, rf=0.3), {}),
+    ("w59", dict(depth=20, n=80, seed=16, rf=0.2), dict(w=59)),          # largest window the 64-bit aligners take
+    ("k3", dict(depth=20, n=80, seed=17, rf=0.2), dict(k_lo=3, k_hi=3)),  # smallest k
+    ("k14", dict(depth=25, n=80, seed=18, rf=0.1), dict(k_lo=14, k_hi=14)),
+    ("w8", dict(depth=15, n=80, seed=19, rf=0.0), dict(w=8, k_lo=4, k_hi=4)),
 ]
 
 
@@ -73,6 +77,42 @@ def test_edge_cases_empty_and_ragged():
     re_ = run_emu(p, packed, win, sl, 1)
     assert not compare_results(ro, re_)
     assert ro[0][0]["status"] == 0 and ro[0][1]["status"] == 0
+
+
+def test_long_and_degenerate_slices():
+    """slices of the maximum length (255), slices shorter than k, identical slices, and a 400-deep pile"""
+    p = default_params()
+    rng = np.random.default_rng(5)
+    from common import pack_bases, WINDOW_DT, SLICE_DT
+    truth = rng.integers(0, 4, 300).astype(np.uint8)
+    wins, sls, pos = [], [], 0
+    chunks = []
+    def add(seq):
+        nonlocal pos
+        chunks.append(seq); start = pos; pos += len(seq); return start
+    # window 0: A window + 30 long slices (the first 255 bases of noisy copies) -- elength fallbacks, no consensus expected
+    s0 = len(sls); sls.append((add(truth[:40]), 40, 0))
+    for _ in range(30):
+        b = truth[:255].copy(); b[rng.integers(0, 255, 20)] = rng.integers(0, 4, 20); sls.append((add(b), 255, 0))
+    wins.append((s0, 31, 0, 0, 0))
+    # window 1: identical slices (a clean pile) ; window 2: slices shorter than k ; window 3: 400 identical-ish slices
+    s1 = len(sls); sls.append((add(truth[:40]), 40, 0))
+    for _ in range(12): sls.append((add(truth[:40]), 40, 0))
+    wins.append((s1, 13, 0, 1, 0))
+    s2 = len(sls); sls.append((add(truth[:40]), 40, 0))
+    for _ in range(8): sls.append((add(truth[:5]), 5, 0))
+    wins.append((s2, 9, 0, 2, 0))
+    s3 = len(sls); sls.append((add(truth[:40]), 40, 0))
+    for _ in range(399):
+        b = truth[:40].copy(); b[rng.integers(0, 40)] = rng.integers(0, 4); sls.append((add(b), 40, int(rng.integers(0, 2)) * 0))
+    wins.append((s3, 400, 0, 3, 0))
+    packed = np.concatenate([pack_bases(np.concatenate(chunks)), np.zeros(16, np.uint8)])
+    win = np.array(wins, dtype=WINDOW_DT); sl = np.array(sls, dtype=SLICE_DT)
+    ro = run_oracle(p, packed, win, sl, 2)
+    re_ = run_emu(p, packed, win, sl, 1)
+    assert not compare_results(ro, re_), (ro[0], re_[0])
+    assert ro[0][1]["status"] == 1 and bytes(ro[1][64:64 + 40]) == bytes(b"ACGT"[x] for x in truth[:40])
+    assert ro[0][3]["status"] == 1
 
 
 def test_c_abi_library_exports_every_declared_symbol():

@@ -38,6 +38,10 @@ CASES = [
     ("w32", dict(depth=25, n=300, seed=112, rf=0.2), dict(w=32)),
     ("w56", dict(depth=25, n=300, seed=113, rf=0.2), dict(w=56)),
     ("deep200", dict(depth=200, n=100, seed=115, rf=0.3), {}),
+    ("w59", dict(depth=20, n=200, seed=116, rf=0.2), dict(w=59)),
+    ("k3", dict(depth=20, n=200, seed=117, rf=0.2), dict(k_lo=3, k_hi=3)),
+    ("w8", dict(depth=15, n=200, seed=119, rf=0.0), dict(w=8, k_lo=4, k_hi=4)),
+    ("deep400", dict(depth=400, n=30, seed=121, rf=0.2), {}),
 ]
 
 
