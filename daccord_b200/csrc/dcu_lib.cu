@@ -284,19 +284,26 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
   // validate and size the workspaces for this batch
   int maxS = 4, maxB = 64; uint64_t totS = 0;
   const uint64_t nbases = ctx->packed_bytes * 4;
-  for (uint64_t i = 0; i < nwin; ++i) {
+  int bad = 0;                                     // 1 range, 2 slice too long, 3 slice outside DB, 4 A window length
+  const uint32_t wlen = ctx->prm.w, mincov = ctx->prm.min_cov;
+#pragma omp parallel for schedule(static) reduction(max : maxS, maxB, bad) reduction(+ : totS)
+  for (int64_t i = 0; i < (int64_t)nwin; ++i) {
     const dcu_window& W = win[i];
-    if ((uint64_t)W.slice_begin + W.slice_cnt > nsl) { ctx->err = "window slice range out of bounds"; return DCU_ERR_PARAM; }
+    if ((uint64_t)W.slice_begin + W.slice_cnt > nsl) { bad = std::max(bad, 1); continue; }
     int b = 0;
     for (uint32_t j = 0; j < W.slice_cnt; ++j) {
       const dcu_slice& s = sl[W.slice_begin + j];
-      if (s.len > 255) { ctx->err = "slice longer than 255 bases"; return DCU_ERR_UNSUPPORTED; }
-      if ((uint64_t)s.gpos + s.len > nbases) { ctx->err = "slice outside the read database"; return DCU_ERR_PARAM; }
+      if (s.len > 255) bad = std::max(bad, 2);
+      if ((uint64_t)s.gpos + s.len > nbases) bad = std::max(bad, 3);
       b += s.len;
     }
-    if (W.slice_cnt && sl[W.slice_begin].len != ctx->prm.w && W.slice_cnt >= ctx->prm.min_cov) { ctx->err = "slice 0 of a window must be the A window of length w"; return DCU_ERR_PARAM; }
+    if (W.slice_cnt && sl[W.slice_begin].len != wlen && W.slice_cnt >= mincov) bad = std::max(bad, 4);
     maxS = std::max<int>(maxS, W.slice_cnt); maxB = std::max(maxB, b); totS += W.slice_cnt;
   }
+  if (bad == 1) { ctx->err = "window slice range out of bounds"; return DCU_ERR_PARAM; }
+  if (bad == 2) { ctx->err = "slice longer than 255 bases"; return DCU_ERR_UNSUPPORTED; }
+  if (bad == 3) { ctx->err = "slice outside the read database"; return DCU_ERR_PARAM; }
+  if (bad == 4) { ctx->err = "slice 0 of a window must be the A window of length w"; return DCU_ERR_PARAM; }
   int rc = finish_batch(ctx, maxS, maxB, totS, nwin, nsl);
   if (rc) return rc;
   if (nwin) CK(cudaMemcpyAsync(ctx->dwin.p, win, nwin * sizeof(dcu_window), cudaMemcpyHostToDevice, ctx->stream));
