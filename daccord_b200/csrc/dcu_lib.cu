@@ -409,9 +409,15 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   a.slabs = ctx->dslab[tier].p; a.todo = todo; a.n = n;
   a.ticket = ctx->dcnt.p + 2 * tier; a.ovf_cnt = ctx->dcnt.p + 2 * tier + 1; a.ovf_list = ctx->dovf[tier].p;
   size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
-  if (vs_bytes > 40 * 1024) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
+  if (vs_bytes > 40 * 1024 || getenv("DCU_VS_GLOBAL")) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);
   a.sync_group = tier ? 1 : ctx->sync_group;       // the large-workspace pass only sees heavy-tailed windows: free running
+  {   // leave as much of the 228 KB as possible to L1: the kernel lives on cached scratch data (measured +5 %, profiles/r01_summary.md)
+    int pct = (int)((ctx->blocks_per_sm[tier] * (vs_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
+    const char* e = getenv("DCU_CARVEOUT");
+    if (e) pct = atoi(e);
+    CK(cudaFuncSetAttribute(dcu_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+  }
   dcu_window_kernel<<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;
