@@ -20,8 +20,20 @@ struct TileAligner {
   // a: m symbols (codes 0..3), b: n symbols; fills bmap[0..m]; returns edit distance
   int align(const uint8_t* a, int m, const uint8_t* b, int n, uint32_t* bmap) {
     bmap[0] = 0;
-    if (m == 0) return n;
-    if (m > 128) return align_dp(a, m, b, n, bmap);
+    return walk(a, m, b, n, [&](int kind, int i, int j) { if (kind != 2) bmap[i] = (uint32_t)j; });
+  }
+  // same alignment, counted: cnt[0] matches, [1] mismatches, [2] insertions (B symbol only), [3] deletions (A symbol only);
+  // what libmaus2's AlignmentStatistics holds after Aligner::align(a, b) (reference call site src/daccord.cpp:588-597)
+  int align_count(const uint8_t* a, int m, const uint8_t* b, int n, uint64_t cnt[4]) {
+    return walk(a, m, b, n, [&](int kind, int i, int j) { if (kind == 0) cnt[a[i - 1] != b[j - 1]]++; else cnt[kind == 1 ? 3 : 2]++; });
+  }
+
+ private:
+  // forward pass + traceback; emit(kind, i, j) is called back to front, kind 0 = diagonal consuming a[i-1], b[j-1],
+  // 1 = DEL consuming a[i-1] with j B symbols before it, 2 = INS consuming b[j-1]
+  template <class F> int walk(const uint8_t* a, int m, const uint8_t* b, int n, F emit) {
+    if (m == 0) { for (int j = n; j > 0; --j) emit(2, 0, j); return n; }
+    if (m > 128) return walk_dp(a, m, b, n, emit);
     u128 peq[4] = {0, 0, 0, 0};
     for (int i = 0; i < m; ++i) peq[a[i] & 3] |= (u128)1 << i;
     PV.resize(n + 1); MV.resize(n + 1); PH.resize(n + 1); MH.resize(n + 1);
@@ -45,14 +57,15 @@ struct TileAligner {
         int dv = ((PV[j] >> (i - 1)) & 1) ? 1 : (((MV[j] >> (i - 1)) & 1) ? -1 : 0);
         int dhup = (i == 1) ? 1 : (((PH[j] >> (i - 2)) & 1) ? 1 : (((MH[j] >> (i - 2)) & 1) ? -1 : 0));
         int cost = a[i - 1] != b[j - 1];
-        if (dv + dhup == cost) { bmap[i] = (uint32_t)j; --i; --j; }
-        else if (dv == 1) { bmap[i] = (uint32_t)j; --i; }
-        else --j;
-      } else { bmap[i] = 0; --i; }
+        if (dv + dhup == cost) { emit(0, i, j); --i; --j; }
+        else if (dv == 1) { emit(1, i, j); --i; }
+        else { emit(2, i, j); --j; }
+      } else { emit(1, i, 0); --i; }
     }
+    for (; j > 0; --j) emit(2, 0, j);
     return score;
   }
-  int align_dp(const uint8_t* a, int m, const uint8_t* b, int n, uint32_t* bmap) {
+  template <class F> int walk_dp(const uint8_t* a, int m, const uint8_t* b, int n, F emit) {
     const int W = n + 1;
     D.assign((size_t)(m + 1) * W, 0);
     for (int j = 0; j <= n; ++j) D[j] = j;
@@ -63,10 +76,11 @@ struct TileAligner {
     int i = m, j = n;
     while (i > 0) {
       int cur = D[(size_t)i * W + j];
-      if (j > 0 && cur == D[(size_t)(i - 1) * W + j - 1] + (a[i - 1] != b[j - 1])) { bmap[i] = (uint32_t)j; --i; --j; }
-      else if (cur == D[(size_t)(i - 1) * W + j] + 1) { bmap[i] = (uint32_t)j; --i; }
-      else --j;
+      if (j > 0 && cur == D[(size_t)(i - 1) * W + j - 1] + (a[i - 1] != b[j - 1])) { emit(0, i, j); --i; --j; }
+      else if (cur == D[(size_t)(i - 1) * W + j] + 1) { emit(1, i, j); --i; }
+      else { emit(2, i, j); --j; }
     }
+    for (; j > 0; --j) emit(2, 0, j);
     return D[(size_t)m * W + n];
   }
 };

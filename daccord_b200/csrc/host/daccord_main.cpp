@@ -19,6 +19,7 @@
 #include "dazzdb.hpp"
 #include "pile.hpp"
 #include "vote.hpp"
+#include "eprof.hpp"
 #include "../../../include/daccord_b200.h"
 
 using namespace dhost;
@@ -27,7 +28,7 @@ static const char* HELP =
     "usage: daccord [options] reads.las reads.db\n"
     "\t-t: number of host threads (default: all)\n\t-w: window size (default 40)\n\t-a: advance size (default 10)\n"
     "\t-d: max depth (default unlimited)\n\t-f: produce full sequences\n\t-V: verbosity\n\t-I: read interval i,j (inclusive)\n"
-    "\t-J: reads part i,j\n\t-E: error profile file name (default input.las.eprof)\n\t-m: minimum window coverage (default 3)\n"
+    "\t-J: reads part i,j\n\t-E: error profile file name (default input.las.eprof)\n\t--eprofonly: compute error profile only\n\t-m: minimum window coverage (default 3)\n"
     "\t-e: maximum window error (default unlimited)\n\t-l: minimum length of output (default 0)\n"
     "\t--minfilterfreq: minimum k-mer filter frequency (default 0)\n\t--maxfilterfreq: maximum k-mer filter frequency (default 2)\n"
     "\t-D: maximum number of alignments considered per read (default 5000)\n\t-k: kmer size lo[,hi] (default 8)\n"
@@ -62,7 +63,7 @@ int main(int argc, char** argv) {
   auto getu = [&](const char* k, uint64_t def) -> uint64_t { auto it = A.opt.find(k); return (it == A.opt.end() || it->second.empty()) ? def : strtoull(it->second.c_str(), nullptr, 10); };
   const std::string lasfn = A.pos[0], dbfn = A.pos[1];
   if (A.pos.size() > 2 && A.pos[2] != dbfn) { fprintf(stderr, "[E] asymmetric (DB1 != DB2) input is not supported by this build\n"); return EXIT_FAILURE; }
-  if (A.opt.count("eprofonly") || A.opt.count("deepprofileonly")) { fprintf(stderr, "[E] error-profile estimation is not part of this build; supply a profile with -E (or <las>.eprof)\n"); return EXIT_FAILURE; }
+  if (A.opt.count("deepprofileonly")) { fprintf(stderr, "[E] --deepprofileonly is not supported by this build\n"); return EXIT_FAILURE; }
   if (getu("vard", 0)) { fprintf(stderr, "[E] --vard is not supported by this build\n"); return EXIT_FAILURE; }
   dcu_params prm; memset(&prm, 0, sizeof(prm));
   prm.w = (uint32_t)getu("w", 40); const uint32_t advance = (uint32_t)getu("a", 10);
@@ -99,11 +100,21 @@ int main(int argc, char** argv) {
     const int64_t toparead = maxaread >= 0 ? maxaread + 1 : maxaread;
     fprintf(stderr, "[V] minaread=%ld toparead=%ld\n", (long)minaread, (long)toparead);
     fprintf(stderr, "[V] minfilterfreq=%d maxfilterfreq=%d\n", prm.min_ff, prm.max_ff);
-    // error profile (reference: <las>.eprof or -E, src/daccord.cpp:1652-1880). This build reads a text profile:
-    // "matches mismatches insertions deletions"
+    // error profile: <las>.eprof or -E; estimated from the first <= 1024 A-reads when the file does not exist
+    // (reference src/daccord.cpp:1652-1880).  Text form: "matches mismatches insertions deletions" [newline "eavg edif"]
     std::string eproffn = A.opt.count("E") ? A.opt["E"] : lasfn + ".eprof";
     uint64_t em = 0, es = 0, ei = 0, ed = 0;
-    { std::ifstream ef(eproffn); if (!(ef >> em >> es >> ei >> ed)) { fprintf(stderr, "[E] cannot read error profile %s (this build does not estimate it; see INTEGRATION.md)\n", eproffn.c_str()); return EXIT_FAILURE; } }
+    if (!std::ifstream(eproffn).good()) {
+      ProfileCounts PC = estimate_profile(db, las, minaread, toparead, maxalign, maxinput, nthreads);
+      fprintf(stderr, "usable=%lu unusable=%lu eavg=%g edif=%g\n", (unsigned long)PC.usable, (unsigned long)PC.unusable, PC.eavg, PC.edif);
+      const std::string tmpfn = eproffn + ".tmp";
+      { std::ofstream of(tmpfn); of << PC.cnt[0] << " " << PC.cnt[1] << " " << PC.cnt[2] << " " << PC.cnt[3] << "\n" << PC.eavg << " " << PC.edif << "\n";
+        if (!of) { fprintf(stderr, "[E] cannot write error profile %s\n", tmpfn.c_str()); return EXIT_FAILURE; } }
+      if (rename(tmpfn.c_str(), eproffn.c_str())) { fprintf(stderr, "[E] cannot rename %s to %s\n", tmpfn.c_str(), eproffn.c_str()); return EXIT_FAILURE; }
+    }
+    { std::ifstream ef(eproffn); if (!(ef >> em >> es >> ei >> ed)) { fprintf(stderr, "[E] cannot read error profile %s\n", eproffn.c_str()); return EXIT_FAILURE; } }
+    if (em + es + ed == 0) { fprintf(stderr, "[E] error profile %s is empty (no usable window in the sampled reads)\n", eproffn.c_str()); return EXIT_FAILURE; }
+    if (A.opt.count("eprofonly")) return EXIT_SUCCESS;                  // src/daccord.cpp:1895-1896
     const uint64_t len = em + es + ed, numerr = es + ed + ei;
     prm.p_i = (double)ei / (double)len; prm.p_d = (double)ed / (double)len; prm.est_cor = 1.0 - (double)numerr / (double)len;
     fprintf(stderr, "error estimates\nerate=%g\ncor=%g\nins=%g\ndel=%g\n", (double)numerr / len, prm.est_cor, prm.p_i, prm.p_d);

@@ -15,6 +15,7 @@
 #include "dazzdb.hpp"
 #include "pile.hpp"
 #include "vote.hpp"
+#include "eprof.hpp"
 
 using namespace dhost;
 
@@ -180,6 +181,19 @@ char* dh_vote(dh_data* d, dh_batch* b, const dcu_result* res, const uint8_t* con
   memcpy(buf, out.data(), out.size()); buf[out.size()] = 0;
   *outlen = out.size();
   return buf;
+}
+// error profile estimated from the data itself over A-reads [first_read, min(last_read, first_read + 1024)) (reference
+// src/daccord.cpp:1652-1880): out7 = matches, mismatches, insertions, deletions, usable windows, unusable windows, reads; dout2 = eavg, edif
+int dh_estimate_profile(dh_data* d, int64_t first_read, int64_t last_read, uint64_t maxalign, uint64_t maxinput, int nthreads, uint64_t* out7, double* dout2) {
+  try {
+    if (first_read < 0) first_read = 0;
+    if (last_read < 0 || last_read > (int64_t)d->db.rlen.size()) last_read = (int64_t)d->db.rlen.size();
+    ProfileCounts C = estimate_profile(d->db, d->las, first_read, last_read, maxalign, maxinput, nthreads);
+    for (int i = 0; i < 4; ++i) out7[i] = C.cnt[i];
+    out7[4] = C.usable; out7[5] = C.unusable; out7[6] = C.reads;
+    if (dout2) { dout2[0] = C.eavg; dout2[1] = C.edif; }
+    return 0;
+  } catch (std::exception& e) { d->err = e.what(); return 1; }
 }
 void dh_free(void* p) { free(p); }
 

@@ -80,6 +80,19 @@ class Dataset:
         ln = m + mis + dele
         return ins / ln, dele / ln, 1.0 - (mis + dele + ins) / ln
 
+    def estimate_profile(self, first=0, last=None, maxalign=2**64 - 1, maxinput=5000, nthreads=0):
+        """error profile estimated from the overlaps themselves (reference src/daccord.cpp:1652-1880): dict with the four step counts,
+        usable / unusable window counts, reads visited and (eavg, edif)"""
+        a = (C.c_uint64 * 7)()
+        d = (C.c_double * 2)()
+        last = -1 if last is None else last
+        if lib().dh_estimate_profile(self.h, C.c_int64(first), C.c_int64(last), C.c_uint64(maxalign), C.c_uint64(maxinput), C.c_int(nthreads or (os.cpu_count() or 1)), a, d):
+            raise DcuError(lib().dh_data_error(self.h).decode())
+        keys = ("matches", "mismatches", "insertions", "deletions", "usable", "unusable", "reads")
+        out = {k: int(v) for k, v in zip(keys, a)}
+        out["eavg"], out["edif"] = float(d[0]), float(d[1])
+        return out
+
     def overlaps(self, first=0, last=None, maxinput=5000):
         """selected overlaps of A-reads [first,last) in dcu_overlap form + the trace array + read offsets / lengths (numpy copies)"""
         last = self.nreads if last is None else last

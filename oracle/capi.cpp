@@ -124,5 +124,19 @@ char* oracle_daccord_files(const dcu_params* prm, uint32_t advance, uint64_t max
     return buf;
   } catch (std::exception& e) { fprintf(stderr, "[oracle] %s\n", e.what()); return nullptr; }
 }
+// error profile of A-reads [first, top) (at most 1024 are used): out = matches, mismatches, insertions, deletions, usable, unusable, reads;
+// dout = eavg, edif
+int oracle_estimate_profile(const char* lasfn, const char* dbfn, int64_t first, int64_t top, uint64_t maxalign, uint64_t maxinput, uint64_t* out, double* dout) {
+  try {
+    ReadDB DB; loadDB(dbfn, DB);
+    LasFile L; loadLas(lasfn, L, DB.reads.size());
+    if (first < 0) first = 0;
+    if (top < 0 || top > (int64_t)DB.reads.size()) top = (int64_t)DB.reads.size();
+    ProfileResult R = estimateProfile(L, DB, first, top, maxalign, maxinput);
+    out[0] = R.stats.matches; out[1] = R.stats.mismatches; out[2] = R.stats.insertions; out[3] = R.stats.deletions; out[4] = R.usable; out[5] = R.unusable; out[6] = R.nreads;
+    if (dout) { dout[0] = R.eavg; dout[1] = R.edif; }
+    return 0;
+  } catch (std::exception& e) { fprintf(stderr, "[oracle] %s\n", e.what()); return 1; }
+}
 void oracle_free(void* p) { free(p); }
 }

@@ -706,6 +706,39 @@ class DebruijnGraph {
     std::stable_sort(ACC.begin(), ACC.end(), [](const ConsensusCandidate& a, const ConsensusCandidate& b) { return a.error < b.error; });
     return !ACC.empty();
   }
+  // ---- error-profile estimator's trivial traversal: :1256-1278 (maxForPos), :1329-1357 (maxLastWord), :3794-3826 ----
+  uint64_t maxForPos(uint64_t pos) const {
+    uint64_t maxv = 0, maxc = 0;
+    for (auto& node : nodes) {
+      uint64_t c = 0;
+      for (uint64_t j = 0; j < node.freq; ++j) if (SP[node.spo + j].pos == pos) ++c;
+      if (c > maxc) { maxc = c; maxv = node.v; }
+    }
+    return maxv;
+  }
+  uint64_t maxLastWord() const {
+    uint64_t maxv = 0, maxc = 0, l = 0;
+    while (l < last.size()) {
+      uint64_t h = l + 1;
+      while (h < last.size() && (last[h] >> 32) == (last[l] >> 32)) ++h;
+      if (h - l > maxc) { maxc = h - l; maxv = last[l] >> 32; }
+      l = h;
+    }
+    return maxv;
+  }
+  // consensus = the one unitig leading from the most frequent first k-mer to the most frequent last k-mer
+  bool traverseTrivial(std::string& cons) {
+    cons.clear();
+    const uint64_t first = maxForPos(0), lastk = maxLastWord();
+    prepareTraverse(false, first, lastk, 0);
+    for (auto& st : stretches)
+      if (st.first == first && st.last == lastk) {
+        for (unsigned i = 0, shift = 2 * (kmersize - 1); i < kmersize; ++i, shift -= 2) cons.push_back((char)remapChar((first >> shift) & 3));
+        for (uint64_t j = 1; j < st.len; ++j) cons.push_back((char)remapChar(stretchLinks[st.stretchO + j] & 3));
+        return true;
+      }
+    return false;
+  }
   uint64_t getNumCandidates() const { return ACC.size(); }
   std::pair<const uint8_t*, const uint8_t*> getCandidate(uint64_t i) const { return {Acons.data() + ACC[i].o, Acons.data() + ACC[i].o + ACC[i].l}; }   // :5177-5182
   // :5476-5482, :5408-5447

@@ -256,4 +256,158 @@ struct ReadHandler {
   }
 };
 
+// ------------------------------------------------------------------ error profile estimation
+// handleIndelEstimate<8> (reference src/daccord.cpp:271-631) and its driver (:1652-1880): windows of 40 advancing by 5 over
+// the first <= 1024 A-reads, piles without a repeated 7-mer, consensus = the trivial unitig of the k=8 graph at frequency
+// >= 2, every slice aligned to that consensus; the step counts are the profile.
+struct AlignStats { uint64_t matches = 0, mismatches = 0, insertions = 0, deletions = 0;
+  void add(const AlignStats& o) { matches += o.matches; mismatches += o.mismatches; insertions += o.insertions; deletions += o.deletions; }
+  // libmaus2::lcs::AlignmentStatistics::getErrorRate (libmaus2 is not vendored; published definition)
+  double errorRate() const { uint64_t e = mismatches + insertions + deletions; return (double)e / (double)(matches + e); } };
+struct ProfileResult { AlignStats stats; uint64_t usable = 0, unusable = 0; double eavg = 0, edif = 0; uint64_t nreads = 0; };
+
+// libmaus2::fastx::KmerRepeatDetector(k).detect (call site src/daccord.cpp:541): does any k-mer occur twice in the sequence (convention C9)
+inline bool hasRepeatedKmer(const uint8_t* s, uint64_t n, unsigned k) {
+  if (n < k) return false;
+  std::vector<uint32_t> v;
+  for (uint64_t i = 0; i + k <= n; ++i) { uint32_t w = 0; for (unsigned j = 0; j < k; ++j) w = (w << 2) | mapChar(s[i + j]); v.push_back(w); }
+  std::sort(v.begin(), v.end());
+  return std::adjacent_find(v.begin(), v.end()) != v.end();
+}
+
+struct ProfileEstimator {
+  enum { EW = 40, EA = 5, EK = 8 };                 // src/daccord.cpp:1279-1280, :1587 (handleIndelEstimate<8>)
+  const LasFile& L; const ReadDB& DB; uint64_t maxalign, maxinput;
+  Aligner NP;
+  KmerLimit KL; DebruijnGraph DG;
+  ProfileEstimator(const LasFile& rL, const ReadDB& rDB, uint64_t rmaxalign, uint64_t rmaxinput)
+      : L(rL), DB(rDB), maxalign(rmaxalign), maxinput(rmaxinput), KL(0.85, 0), DG(EK, 0.0, KL) {}
+
+  // :1690-1741 -- keeps the D LOWEST scores (the comparator is the opposite of the main loop's), order by abpos (C6)
+  void selectOverlaps(uint64_t aread, std::vector<const OvlRec*>& sel) const {
+    sel.clear();
+    typedef std::pair<uint64_t, uint64_t> SI;
+    struct Cmp { bool operator()(const SI& x, const SI& y) const { return x.first > y.first; } };
+    FiniteHeap<SI, Cmp> H(maxinput);
+    std::vector<uint64_t> slot;
+    for (uint64_t i = L.first[aread]; i < L.first[aread + 1]; ++i) {
+      const OvlRec& o = L.ovl[i];
+      uint64_t score = (uint64_t)std::ldexp((double)o.diffs / (double)(o.aepos - o.abpos), 30);
+      if (H.f == maxinput) {
+        if (score > H.top().first) continue;
+        uint64_t p = H.top().second; H.popvoid(); slot[p] = i; H.push({score, p});
+      } else { uint64_t p = slot.size(); H.push({score, p}); slot.push_back(i); }
+    }
+    std::sort(slot.begin(), slot.end());
+    std::stable_sort(slot.begin(), slot.end(), [&](uint64_t x, uint64_t y) { return L.ovl[x].abpos < L.ovl[y].abpos; });
+    for (auto i : slot) sel.push_back(&L.ovl[i]);
+  }
+  void computeTrace(const OvlRec& o, const uint8_t* a, const uint8_t* b, std::vector<uint8_t>& trace) {     // convention C8
+    trace.clear();
+    int64_t x = o.abpos, bp = o.bbpos; size_t t = 1;
+    while (x < o.aepos) {
+      int64_t y = std::min<int64_t>((x / L.tspace + 1) * L.tspace, o.aepos);
+      int64_t blen = o.tr[t]; t += 2;
+      NP.align(a + x, (uint64_t)(y - x), b + bp, (uint64_t)blen);
+      trace.insert(trace.end(), NP.trace.begin(), NP.trace.end());
+      bp += blen; x = y;
+    }
+  }
+
+  // one A-read; returns the mean per-window error rate (0 if no window gave a consensus)
+  double handleRead(uint64_t aread, ProfileResult& R) {
+    std::vector<const OvlRec*> ita; selectOverlaps(aread, ita);
+    const uint64_t nintv = ita.size();
+    if (!nintv) return 0.0;
+    const std::string& A = DB.reads[aread];
+    double maxerate = 0.0, minerate = 1.0; uint64_t maxaepos = 0;
+    std::vector<std::vector<uint8_t>> traces(nintv); std::vector<std::string> bseq(nintv);
+    for (uint64_t z = 0; z < nintv; ++z) {
+      const OvlRec& o = *ita[z];
+      double er = (double)o.diffs / (double)(o.aepos - o.abpos);
+      if (er > maxerate) maxerate = er;
+      if (er < minerate) minerate = er;
+      if ((uint64_t)o.aepos > maxaepos) maxaepos = (uint64_t)o.aepos;
+      bseq[z] = (o.flags & 1) ? revcomp(DB.reads[o.bread]) : DB.reads[o.bread];
+      computeTrace(o, (const uint8_t*)A.data(), (const uint8_t*)bseq[z].data(), traces[z]);          // all traces up front, :385-398
+    }
+    const double ediv = (maxerate > minerate) ? (maxerate - minerate) : 1.0;
+    typedef std::pair<uint64_t, uint64_t> upair;
+    FiniteHeap<upair> E(1024);
+    std::map<uint64_t, ActiveElement> activeset;
+    std::vector<SeqRef> MA;
+    const uint64_t ylimit = (maxaepos + EA >= EW) ? ((maxaepos + EA - EW) / EA) : 0;                   // :408
+    double esum = 0; uint64_t ecnt = 0, z = 0;
+    for (uint64_t y = 0; y < ylimit; ++y) {
+      const uint64_t astart = y * EA, aend = astart + EW;
+      while (z < nintv && (int64_t)astart >= ita[z]->abpos) {                                       // :440-478
+        const OvlRec& o = *ita[z];
+        if (o.aepos >= (int64_t)astart) {
+          const uint64_t aoff = astart - (uint64_t)o.abpos;
+          const uint8_t* ta = traces[z].data(); const uint8_t* te = ta + traces[z].size();
+          auto adv = advanceA(ta, te, aoff);
+          uint64_t uboff = (uint64_t)o.bbpos + stringLengthUsed(ta, ta + adv.second).second;
+          ta += adv.second;
+          double er = (double)o.diffs / (double)(o.aepos - o.abpos);
+          uint64_t escore = (uint64_t)(((er - minerate) / ediv) * std::numeric_limits<uint32_t>::max());
+          uint64_t eindex = (escore << 32) | z;
+          activeset[eindex] = ActiveElement{(const uint8_t*)A.data() + astart, (const uint8_t*)bseq[z].data() + uboff, ta, te, uboff};
+          E.pushBump(upair((uint64_t)o.aepos, eindex));
+        }
+        ++z;
+      }
+      while (!E.empty() && E.top().first <= aend) { upair UP = E.pop(); activeset.erase(UP.second); }   // :481-485 (<=, unlike the main loop)
+      MA.clear();
+      for (auto& kv : activeset) {                                                                  // :490-530
+        ActiveElement& AE = kv.second;
+        auto adv = advanceA(AE.ta, AE.te, EW);
+        uint64_t blen = stringLengthUsed(AE.ta, AE.ta + adv.second).second;
+        if (MA.empty()) MA.push_back(SeqRef(AE.ua, EW));
+        if (MA.size() < maxalign) MA.push_back(SeqRef(AE.ub, blen));
+        auto advadv = advanceA(AE.ta, AE.te, EA);
+        uint64_t badv = stringLengthUsed(AE.ta, AE.ta + advadv.second).second;
+        AE.ua += EA; AE.ta += advadv.second; AE.ub += badv; AE.uboff += badv;
+      }
+      if (MA.size() < 3) continue;                                                                  // :532
+      bool rep = false;
+      for (auto& sr : MA) rep = hasRepeatedKmer(sr.first, sr.second, EK - 1) || rep;
+      if (rep) { R.unusable++; continue; }
+      R.usable++;
+      DG.setup(MA.data(), MA.size());
+      DG.filterFreq(2, MA.size());
+      std::string cons;
+      if (!DG.traverseTrivial(cons)) continue;
+      AlignStats GAS;
+      for (auto& sr : MA) {                                                                         // :585-600
+        NP.align((const uint8_t*)cons.data(), cons.size(), sr.first, sr.second);
+        for (uint8_t st : NP.trace) switch (st) {
+          case STEP_MATCH: GAS.matches++; break; case STEP_MISMATCH: GAS.mismatches++; break;
+          case STEP_INS: GAS.insertions++; break; default: GAS.deletions++; break; }
+      }
+      R.stats.add(GAS);
+      esum += GAS.errorRate(); ecnt++;
+    }
+    return ecnt ? esum / ecnt : 0.0;
+  }
+};
+
+// driver :1652-1880 over A-reads [lo, min(hi, lo+1024)) ; sequential accumulation order = read order
+inline ProfileResult estimateProfile(const LasFile& L, const ReadDB& DB, int64_t lo, int64_t hi, uint64_t maxalign, uint64_t maxinput) {
+  ProfileResult R; ProfileEstimator PE(L, DB, maxalign, maxinput);
+  std::vector<double> loc;
+  const int64_t top = std::min(hi, lo + 1024);
+  for (int64_t r = lo; r < top; ++r) {
+    if (L.first[r] == L.first[r + 1]) continue;
+    double e = PE.handleRead((uint64_t)r, R); R.nreads++;
+    if (e != 0.0) loc.push_back(e);
+  }
+  if (!loc.empty()) {
+    double s = 0; for (double e : loc) s += e;
+    R.eavg = s / loc.size();
+    double d = 0; for (double e : loc) d += (R.eavg - e) * (R.eavg - e);
+    R.edif = std::sqrt(d / loc.size());
+  }
+  return R;
+}
+
 }  // namespace oracle
