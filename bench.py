@@ -235,12 +235,27 @@ def main():
         pile_same = bool((out[0] == res_ref).all())
     fasta, nseq = batch.vote(*out)
     corrected = sum(len(l) for l in fasta.split(b"\n") if l and not l.startswith(b">"))
+    # ---- the whole read-level path on the GPU: overlaps in, corrected bases out (dcu_pile + launch + dcu_vote); D2H = corrected bases only
+    full_wall, full_same, full_d2h = None, None, 0
+    if args.w % args.a == 0:
+        from daccord_b200.host import format_segments
+        eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a); eng.launch(); seg, chars = eng.vote()      # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a)
+            eng.launch()
+            seg, chars = eng.vote()
+        barrier()
+        full_wall = time.perf_counter() - t0
+        full_same = bool(format_segments(seg, chars)[0] == fasta)
+        full_d2h = int(chars.nbytes + seg.nbytes + 16 * nwin)       # + the window descriptors dcu_vote reads back to lay out the reads
 
-    vals = torch.tensor([tsec, e2e_wall, wall, pile_wall or 0.0], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([tsec, e2e_wall, wall, pile_wall or 0.0, full_wall or 0.0], dtype=torch.float64, device="cuda")
     cnts = torch.tensor([att, nwin, okw, corrected, launches, hard, alg_bytes, win.nbytes + sl.nbytes, res_p.numel() + cons_p.numel() + ops_p.numel()], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX); dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
-    tsec, e2e_wall, wall, pile_wall_max = [float(x) for x in vals.tolist()]
+    tsec, e2e_wall, wall, pile_wall_max, full_wall_max = [float(x) for x in vals.tolist()]
     att_t, nwin_t, ok_t, corr_t, launches_t, hard_t, alg_t, h2d_t, d2h_t = [float(x) for x in cnts.tolist()]
     if rank != 0:
         if dist is not None:
@@ -269,6 +284,9 @@ def main():
                 e2e={"value": att_t * args.steps / e2e_wall, "unit": "windows/s", "h2d_bytes_per_step": int(h2d_t), "d2h_bytes_per_step": int(d2h_t)},
                 e2e_from_overlaps=(None if not pile_wall else {"value": att_t * args.steps / pile_wall_max, "unit": "windows/s", "what": "dcu_pile (trace reconstruction + slices on the GPU) + launch + download",
                                                                "h2d_bytes_per_step": int((ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes) * world), "results_identical": pile_same}),
+                e2e_overlaps_to_fasta=(None if not full_wall else {"value": att_t * args.steps / full_wall_max, "unit": "windows/s", "what": "dcu_pile + launch + dcu_vote (pile vote on the GPU): overlaps in, corrected bases out",
+                                                                   "h2d_bytes_per_step": int((ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes) * world), "d2h_bytes_per_step": int(full_d2h * world),
+                                                                   "fasta_identical_to_host_vote": full_same}),
                 gpu_launches=int(launches_t), hard_windows=int(hard_t),
                 roofline={"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                           "peak_source": peak_src, "bytes_per_window": alg_bytes / max(att, 1),

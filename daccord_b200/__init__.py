@@ -15,6 +15,7 @@ SLICE_DT = np.dtype([("gpos", "<u4"), ("len", "<u2"), ("flags", "<u2")])
 WINDOW_DT = np.dtype([("slice_begin", "<u4"), ("slice_cnt", "<u2"), ("reserved", "<u2"), ("aread", "<u4"), ("astart", "<u4")])
 RESULT_DT = np.dtype([("status", "u1"), ("k", "u1"), ("ff", "i1"), ("clen", "u1"), ("err", "<u4"), ("nops", "<u2"),
                       ("ncand", "<u2"), ("elength", "<i4")])
+SEGMENT_DT = np.dtype([("aread", "<u4"), ("first", "<u4"), ("last", "<u4"), ("reserved", "<u4"), ("len", "<u8"), ("off", "<u8")])
 CONS_STRIDE, OPS_STRIDE = 64, 128
 WIN_SKIPPED, WIN_OK, WIN_FAILED = 0, 1, 2
 
@@ -128,6 +129,16 @@ class Engine:
         res, cons, ops = out if out is not None else alloc_out(len(win))
         self._ck(self.lib.dcu_run(self.ctx, _p(win), C.c_uint64(len(win)), _p(sl), C.c_uint64(len(sl)), _p(res), _p(cons), _p(ops)))
         return res, cons, ops
+
+    def vote(self, producefull=False, minlen=0, read_boff=None, read_len=None):
+        """pile vote of the resident results on the GPU; returns (segments, chars) -- see dcu_vote in include/daccord_b200.h"""
+        ns, nc = C.c_uint64(0), C.c_uint64(0)
+        nreads = 0 if read_len is None else len(read_len)
+        self._ck(self.lib.dcu_vote(self.ctx, C.c_int(1 if producefull else 0), C.c_uint64(minlen), _p(read_boff), _p(read_len), C.c_uint64(nreads), C.byref(ns), C.byref(nc)))
+        seg = np.zeros(ns.value, SEGMENT_DT)
+        chars = np.zeros(nc.value, np.uint8)
+        self._ck(self.lib.dcu_get_corrected(self.ctx, _p(seg), _p(chars)))
+        return seg, chars
 
     def stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)

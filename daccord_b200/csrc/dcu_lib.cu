@@ -14,9 +14,11 @@
 #include "host_tables.hpp"
 #include "host_caps.hpp"
 #include "pile_host.hpp"
+#include "vote_host.hpp"
 #include "../../include/daccord_b200.h"
 
 static_assert(sizeof(dcu::Slice) == sizeof(dcu_slice) && sizeof(dcu::Window) == sizeof(dcu_window) && sizeof(dcu::Result) == sizeof(dcu_result), "ABI structs");
+static_assert(sizeof(dvote::Win) == sizeof(dcu_window) && sizeof(dvote::Res) == sizeof(dcu_result), "ABI structs (vote)");
 
 namespace {
 
@@ -126,6 +128,69 @@ __global__ void pile_k3(const dpile::Win* win, const dpile::Sl* sl, uint64_t nwi
   atomicMax(maxS, (unsigned int)w.slice_cnt); atomicMax(maxB, b);
 }
 
+// ---- pile vote (vote_core.cuh): per window the offset table, per A position the column votes (count pass, then fill pass)
+constexpr int VOTE_TPB = 256;
+__global__ void vote_k0(const dvote::Res* res, const uint8_t* ops, uint64_t nwin, dvote::Params P, uint16_t* ent, int* err) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nwin || res[i].status != dvote::ST_OK) return;
+  if (!dvote::vote_window_table(res[i], ops + i * P.ops_stride, P.w, ent + i * (P.w + 1))) atomicExch(err, 1);
+}
+// block-wide exclusive scan of one value per thread (VOTE_TPB threads); returns the thread's offset, *total = block sum
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t s_w[VOTE_TPB / 32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_w[wp] = x;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+  for (int i = 0; i < VOTE_TPB / 32; ++i) { if (i < wp) base += s_w[i]; tot += s_w[i]; }
+  __syncthreads();
+  *total = tot;
+  return base + x - v;
+}
+// pass 0 (chars == nullptr): per position the character count (bit 7: the pile holds something there) and per block the sum;
+// pass 1: the characters at blk_off[block] + in-block offset, and the run boundary records
+__global__ void __launch_bounds__(VOTE_TPB) vote_k1(dvote::Ctx c, const dvote::Read* reads, uint32_t nr, uint64_t npos, uint8_t* flag, uint64_t* blk,
+                                                   char* chars, dvote::Bound* bound, unsigned int* nbound, unsigned int bound_cap) {
+  const uint64_t idx = (uint64_t)blockIdx.x * VOTE_TPB + threadIdx.x;
+  uint32_t n = 0; bool present = false; uint32_t r = 0, p = 0;
+  if (idx < npos) {
+    uint32_t a = 0, b = nr;                       // last read with pos_off <= idx
+    while (b - a > 1) { uint32_t mid = (a + b) >> 1; if (reads[mid].pos_off <= idx) a = mid; else b = mid; }
+    r = a; p = (uint32_t)(idx - reads[r].pos_off);
+    if (!chars) { n = (uint32_t)dvote::vote_position(c, reads[r], p, nullptr, &present); flag[idx] = (uint8_t)(n | (present ? 0x80u : 0u)); }
+    else { n = flag[idx] & 0x7Fu; present = (flag[idx] & 0x80u) != 0; }
+  }
+  uint32_t total;
+  const uint32_t off = block_exscan(n, &total);
+  if (!chars) { if (threadIdx.x == 0) blk[blockIdx.x] = total; return; }
+  if (idx >= npos || !present) return;
+  const uint64_t o = blk[blockIdx.x] + off;
+  if (n) { bool pr; dvote::vote_position(c, reads[r], p, chars + o, &pr); }
+  const bool left = p > 0 && (flag[idx - 1] & 0x80u), right = p + 1 < reads[r].span && (flag[idx + 1] & 0x80u);
+  if (!left) { unsigned int q = atomicAdd(nbound, 1u); if (q < bound_cap) bound[q] = dvote::Bound{o, r, p, 0u, 0u}; }
+  if (!right) { unsigned int q = atomicAdd(nbound, 1u); if (q < bound_cap) bound[q] = dvote::Bound{o + n, r, p, 1u, 0u}; }
+}
+// exclusive scan of the block sums in place (one block); blk[nblk] = grand total
+__global__ void __launch_bounds__(VOTE_TPB) vote_kscan(uint64_t* blk, uint64_t nblk) {
+  __shared__ uint64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < nblk; base += VOTE_TPB) {
+    const uint64_t i = base + threadIdx.x;
+    const uint32_t v = i < nblk ? (uint32_t)blk[i] : 0u;          // a block sum is < 2^32 (<= 127 * VOTE_TPB)
+    uint32_t total;
+    const uint32_t off = block_exscan(v, &total);
+    const uint64_t carry = s_carry;
+    if (i < nblk) blk[i] = carry + off;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blk[nblk] = s_carry;
+}
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DCU_ERR_CUDA; } } while (0)
 
 template <class T> struct DevBuf {
@@ -166,6 +231,9 @@ struct dcu_ctx {
   // piling scratch
   DevBuf<dpile::Ovl> dpo; DevBuf<dpile::ReadInfo> dpr; DevBuf<uint32_t> dprid, dptile, dpbm, dpnw, dpns, dprlen; DevBuf<uint64_t> dpboff; DevBuf<uint16_t> dptrace;
   DevBuf<double> dpmin, dpdiv; DevBuf<unsigned long long> dpact;
+  // vote scratch and results
+  DevBuf<uint16_t> dvent; DevBuf<uint8_t> dvflag; DevBuf<uint64_t> dvblk; DevBuf<char> dvchars; DevBuf<dvote::Read> dvreads; DevBuf<dvote::Bound> dvbound;
+  std::vector<dcu_segment> segs; uint64_t nchars = 0; bool results_valid = false;
   uint64_t launches = 0, hard = 0;
   std::string err;
 };
@@ -233,6 +301,7 @@ void dcu_destroy(dcu_ctx* ctx) {
   ctx->dpo.release(); ctx->dpr.release(); ctx->dprid.release(); ctx->dptile.release(); ctx->dpbm.release(); ctx->dpnw.release(); ctx->dpns.release(); ctx->dprlen.release();
   ctx->dpboff.release(); ctx->dptrace.release(); ctx->dpmin.release(); ctx->dpdiv.release(); ctx->dpact.release();
   ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release();
+  ctx->dvent.release(); ctx->dvflag.release(); ctx->dvblk.release(); ctx->dvchars.release(); ctx->dvreads.release(); ctx->dvbound.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -272,7 +341,7 @@ static int finish_batch(dcu_ctx* ctx, int maxS, int maxB, uint64_t totS, uint64_
   CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
   CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));
   CK(ctx->dovf[0].ensure(nwin + 1)); CK(ctx->dovf[1].ensure(nwin + 1));
-  ctx->nwin = nwin; ctx->nsl = nsl;
+  ctx->nwin = nwin; ctx->nsl = nsl; ctx->results_valid = false;
   return DCU_OK;
 }
 
@@ -455,6 +524,7 @@ int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaEventSynchronize(ctx->ev1));
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+  ctx->results_valid = true;
   return ret;
 }
 
@@ -466,6 +536,69 @@ int dcu_download(dcu_ctx* ctx, dcu_result* res, uint8_t* cons, uint8_t* ops) {
   if (cons) CK(cudaMemcpyAsync(cons, ctx->dcons.p, ctx->nwin * DCU_CONS_STRIDE, cudaMemcpyDeviceToHost, ctx->stream));
   if (ops) CK(cudaMemcpyAsync(ops, ctx->dops.p, ctx->nwin * DCU_OPS_STRIDE, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return DCU_OK;
+}
+
+// pile vote of the resident batch on the device (vote_core.cuh)
+int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* read_boff, const uint32_t* read_len, uint64_t nreads, uint64_t* nseg, uint64_t* nchars) {
+  if (!ctx) return DCU_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  ctx->segs.clear(); ctx->nchars = 0;
+  if (nseg) *nseg = 0;
+  if (nchars) *nchars = 0;
+  if (!ctx->nwin) return DCU_OK;
+  if (!ctx->results_valid) { ctx->err = "dcu_vote needs the results of dcu_launch"; return DCU_ERR_STATE; }
+  if (ctx->prm.w > 127) { ctx->err = "vote tables hold w <= 127"; return DCU_ERR_UNSUPPORTED; }
+  cudaStream_t st = ctx->stream;
+  const uint64_t nwin = ctx->nwin;
+  std::vector<dcu_window> hwin(nwin);
+  CK(cudaMemcpyAsync(hwin.data(), ctx->dwin.p, nwin * sizeof(dcu_window), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  dvote::Layout L;
+  if (!dvote::layout_reads(hwin.data(), nwin, ctx->prm.w, producefull != 0, read_boff, read_len, nreads, L)) { ctx->err = L.err; return DCU_ERR_PARAM; }
+  if (producefull) for (auto& R : L.reads) if (R.boff + (R.rlen + 3) / 4 > ctx->packed_bytes) { ctx->err = "read outside the packed database"; return DCU_ERR_PARAM; }
+  const uint32_t nr = (uint32_t)L.reads.size();
+  const uint64_t npos = L.npos, nblk = (npos + VOTE_TPB - 1) / VOTE_TPB;
+  if (nblk >= 0x7FFFFFFFull) { ctx->err = "batch too large for the vote"; return DCU_ERR_UNSUPPORTED; }
+  const uint64_t bound_cap = 2 * (nwin + nr) + 16;
+  CK(ctx->dvent.ensure(nwin * (ctx->prm.w + 1))); CK(ctx->dvflag.ensure(npos + 1)); CK(ctx->dvblk.ensure(nblk + 2)); CK(ctx->dvreads.ensure(nr + 1));
+  CK(ctx->dvbound.ensure(bound_cap)); CK(ctx->dcnt.ensure(8));
+  CK(cudaMemcpyAsync(ctx->dvreads.p, L.reads.data(), nr * sizeof(dvote::Read), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->dcnt.p + 4, 0, 4 * sizeof(unsigned int), st));
+  int* derr = (int*)(ctx->dcnt.p + 4); unsigned int* dnb = ctx->dcnt.p + 5;
+  dvote::Params vp; vp.w = ctx->prm.w; vp.cons_stride = DCU_CONS_STRIDE; vp.ops_stride = DCU_OPS_STRIDE; vp.producefull = producefull ? 1 : 0;
+  dvote::Ctx vc; vc.win = (const dvote::Win*)ctx->dwin.p; vc.res = (const dvote::Res*)ctx->dres.p; vc.cons = ctx->dcons.p; vc.ent = ctx->dvent.p; vc.packed = ctx->dpacked; vc.P = vp;
+  vote_k0<<<(unsigned)((nwin + 255) / 256), 256, 0, st>>>((const dvote::Res*)ctx->dres.p, ctx->dops.p, nwin, vp, ctx->dvent.p, derr);
+  vote_k1<<<(unsigned)nblk, VOTE_TPB, 0, st>>>(vc, ctx->dvreads.p, nr, npos, ctx->dvflag.p, ctx->dvblk.p, nullptr, nullptr, nullptr, 0u);
+  vote_kscan<<<1, VOTE_TPB, 0, st>>>(ctx->dvblk.p, nblk);
+  CK(cudaGetLastError());
+  uint64_t total = 0; int herr = 0;
+  CK(cudaMemcpyAsync(&total, ctx->dvblk.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (herr) { ctx->err = "a placement trace does not cover its window"; return DCU_ERR_STATE; }
+  CK(ctx->dvchars.ensure(total + 1));
+  vote_k1<<<(unsigned)nblk, VOTE_TPB, 0, st>>>(vc, ctx->dvreads.p, nr, npos, ctx->dvflag.p, ctx->dvblk.p, ctx->dvchars.p, ctx->dvbound.p, dnb, (unsigned int)bound_cap);
+  CK(cudaGetLastError());
+  unsigned int nb = 0;
+  CK(cudaMemcpyAsync(&nb, dnb, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (nb > bound_cap) { ctx->err = "run boundary list overflow"; return DCU_ERR_OVERFLOW; }
+  std::vector<dvote::Bound> hb(nb);
+  if (nb) CK(cudaMemcpyAsync(hb.data(), ctx->dvbound.p, nb * sizeof(dvote::Bound), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::string perr;
+  if (!dvote::pair_bounds(hb, L, producefull != 0, minlen, ctx->segs, perr)) { ctx->err = perr; return DCU_ERR_STATE; }
+  ctx->nchars = total; ctx->launches += 4;
+  if (nseg) *nseg = ctx->segs.size();
+  if (nchars) *nchars = total;
+  return DCU_OK;
+}
+int dcu_get_corrected(dcu_ctx* ctx, dcu_segment* seg, char* chars) {
+  if (!ctx) return DCU_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  if (seg && !ctx->segs.empty()) memcpy(seg, ctx->segs.data(), ctx->segs.size() * sizeof(dcu_segment));
+  if (chars && ctx->nchars) { CK(cudaMemcpyAsync(chars, ctx->dvchars.p, ctx->nchars, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
   return DCU_OK;
 }
 

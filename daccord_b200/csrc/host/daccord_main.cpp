@@ -132,69 +132,79 @@ int main(int argc, char** argv) {
       const int64_t b1 = std::min<int64_t>(b0 + (int64_t)batchreads, toparead), nr = b1 - b0;
       std::vector<dcu_window> win; std::vector<dcu_slice> sl; std::vector<uint64_t> first(nr + 1, 0);
       const bool gpu_pile = (prm.w % advance == 0) && las.tspace <= 128 && !getenv("DACCORD_HOST_PILE");
+      const bool gpu_vote = !getenv("DACCORD_HOST_VOTE");
+      uint64_t nw = 0, ns = 0;
+      // stage 1: windows + slices -- on the GPU from the selected overlaps (dcu_pile), or by the host piler (dcu_upload)
       if (gpu_pile) {
-        // overlap selection on the host (top -D, order by abpos), trace reconstruction + slices on the GPU
         std::vector<dcu_overlap> ov; std::vector<uint32_t> sel;
         for (int64_t r = b0; r < b1; ++r) {
           select_overlaps(las, (uint64_t)r, maxinput, sel);
           for (auto i : sel) { const Overlap& o = las.ovl[i]; dcu_overlap x; memset(&x, 0, sizeof(x)); x.abpos = o.abpos; x.aepos = o.aepos; x.bbpos = o.bbpos; x.bepos = o.bepos; x.flags = o.flags; x.aread = o.aread; x.bread = o.bread; x.diffs = o.diffs; x.tlen = o.tlen; x.trace_off = o.trace_off; ov.push_back(x); }
         }
-        uint64_t nw = 0, ns = 0;
         rc = dcu_pile(ctx, ov.data(), ov.size(), las.trace.data(), las.trace.size(), las.tspace, db.boff.data(), db.rlen.data(), db.rlen.size(), advance, maxalign, &nw, &ns);
         if (rc) { fprintf(stderr, "[E] dcu_pile: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-        win.resize(nw);
-        rc = dcu_launch(ctx, nullptr);
-        if (rc) { fprintf(stderr, "[E] dcu_launch: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-        res.resize(nw); cons.resize(nw * DCU_CONS_STRIDE); ops.resize(nw * DCU_OPS_STRIDE);
-        rc = dcu_download(ctx, res.data(), cons.data(), ops.data());
-        if (!rc) rc = dcu_get_windows(ctx, win.data(), nullptr);
-        if (rc) { fprintf(stderr, "[E] dcu_download: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-        uint64_t wi = 0;
-        for (int64_t i = 0; i < nr; ++i) { first[i] = wi; while (wi < nw && (int64_t)win[wi].aread == b0 + i) ++wi; }
-        first[nr] = nw;
       } else {
-      std::vector<std::vector<dcu_window>> wv(nr); std::vector<std::vector<dcu_slice>> sv(nr);
-      std::string perr;
+        std::vector<std::vector<dcu_window>> wv(nr); std::vector<std::vector<dcu_slice>> sv(nr);
 #pragma omp parallel num_threads(nthreads)
-      {
-        ReadPiler RP(db, las, PP);
+        {
+          ReadPiler RP(db, las, PP);
 #pragma omp for schedule(dynamic, 1)
-        for (int64_t i = 0; i < nr; ++i) {
-          try { RP.pile((uint64_t)(b0 + i), wv[i], sv[i]); }
-          catch (std::exception& e) {       // per-read failures are logged and skipped (reference src/daccord.cpp:2466-2478)
+          for (int64_t i = 0; i < nr; ++i) {
+            try { RP.pile((uint64_t)(b0 + i), wv[i], sv[i]); }
+            catch (std::exception& e) {       // per-read failures are logged and skipped (reference src/daccord.cpp:2466-2478)
 #pragma omp critical
-            { fprintf(stderr, "[E] read %ld: %s\n", (long)(b0 + i), e.what()); }
-            wv[i].clear(); sv[i].clear();
+              { fprintf(stderr, "[E] read %ld: %s\n", (long)(b0 + i), e.what()); }
+              wv[i].clear(); sv[i].clear();
+            }
+          }
+        }
+        for (int64_t i = 0; i < nr; ++i) { uint32_t base = (uint32_t)sl.size(); for (auto x : wv[i]) { x.slice_begin += base; win.push_back(x); } sl.insert(sl.end(), sv[i].begin(), sv[i].end()); }
+        nw = win.size(); ns = sl.size();
+        rc = dcu_upload(ctx, win.data(), nw, sl.data(), ns);
+        if (rc) { fprintf(stderr, "[E] dcu_upload: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+      }
+      // stage 2: per-window consensus
+      rc = dcu_launch(ctx, nullptr);
+      if (rc) { fprintf(stderr, "[E] dcu_launch: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+      res.resize(nw);
+      // stage 3: pile vote -- on the GPU (only corrected bases and the 16-byte results cross PCIe), or on the host from the full results
+      if (gpu_vote) {
+        rc = dcu_download(ctx, res.data(), nullptr, nullptr);
+        uint64_t nseg = 0, nch = 0;
+        if (!rc) rc = dcu_vote(ctx, producefull ? 1 : 0, minlen, db.boff.data(), db.rlen.data(), db.rlen.size(), &nseg, &nch);
+        std::vector<dcu_segment> seg(nseg); std::vector<char> chars(nch + 1);
+        if (!rc) rc = dcu_get_corrected(ctx, seg.data(), chars.data());
+        if (rc) { fprintf(stderr, "[E] dcu_vote: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+        std::string text; format_segments(seg.data(), nseg, chars.data(), wellcounter, text);     // A-read order, sequences numbered like -t1
+        fwrite(text.data(), 1, text.size(), stdout);
+      } else {
+        cons.resize(nw * DCU_CONS_STRIDE); ops.resize(nw * DCU_OPS_STRIDE);
+        rc = dcu_download(ctx, res.data(), cons.data(), ops.data());
+        if (!rc && gpu_pile) { win.resize(nw); rc = dcu_get_windows(ctx, win.data(), nullptr); }
+        if (rc) { fprintf(stderr, "[E] dcu_download: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+        { uint64_t wi = 0; for (int64_t i = 0; i < nr; ++i) { first[i] = wi; while (wi < nw && (int64_t)win[wi].aread == b0 + i) ++wi; } first[nr] = nw; }
+        std::vector<std::string> parts(nr); std::vector<uint64_t> cnt(nr, 0);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+        for (int64_t i = 0; i < nr; ++i) {
+          if (first[i] == first[i + 1]) continue;
+          std::vector<PileElement> PV;
+          for (uint64_t wi = first[i]; wi < first[i + 1]; ++wi) if (res[wi].status == DCU_WIN_OK) place_window(win[wi], res[wi], cons.data() + wi * DCU_CONS_STRIDE, ops.data() + wi * DCU_OPS_STRIDE, PV);
+          std::string ab;
+          if (producefull) { std::vector<uint8_t> codes; decode_read(db, (uint32_t)(b0 + i), false, codes); ab.resize(codes.size()); for (size_t q = 0; q < codes.size(); ++q) ab[q] = "ACGT"[codes[q]]; }
+          uint64_t c0 = 0; vote_read(b0 + i, PV, VP, ab, c0, parts[i]); cnt[i] = c0;
+        }
+        for (int64_t i = 0; i < nr; ++i) {        // release in A-read order, numbering sequences like -t1
+          const std::string& s = parts[i]; size_t p = 0;
+          while (p < s.size()) {
+            size_t e = s.find('\n', p); if (e == std::string::npos) e = s.size();
+            if (s[p] == '>') { size_t s1 = s.find('/', p), s2 = s.find('/', s1 + 1); fwrite(s.data() + p, 1, s1 + 1 - p, stdout); fprintf(stdout, "%lu", (unsigned long)wellcounter++); fwrite(s.data() + s2, 1, e - s2, stdout); }
+            else fwrite(s.data() + p, 1, e - p, stdout);
+            fputc('\n', stdout); p = e + 1;
           }
         }
       }
-      for (int64_t i = 0; i < nr; ++i) { first[i] = win.size(); uint32_t base = (uint32_t)sl.size(); for (auto x : wv[i]) { x.slice_begin += base; win.push_back(x); } sl.insert(sl.end(), sv[i].begin(), sv[i].end()); }
-      first[nr] = win.size();
-      res.resize(win.size()); cons.resize(win.size() * DCU_CONS_STRIDE); ops.resize(win.size() * DCU_OPS_STRIDE);
-      rc = dcu_run(ctx, win.data(), win.size(), sl.data(), sl.size(), res.data(), cons.data(), ops.data());
-      if (rc) { fprintf(stderr, "[E] dcu_run: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-      }
-      std::vector<std::string> parts(nr); std::vector<uint64_t> cnt(nr, 0);
-#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
-      for (int64_t i = 0; i < nr; ++i) {
-        if (first[i] == first[i + 1]) continue;
-        std::vector<PileElement> PV;
-        for (uint64_t wi = first[i]; wi < first[i + 1]; ++wi) if (res[wi].status == DCU_WIN_OK) place_window(win[wi], res[wi], cons.data() + wi * DCU_CONS_STRIDE, ops.data() + wi * DCU_OPS_STRIDE, PV);
-        std::string ab;
-        if (producefull) { std::vector<uint8_t> codes; decode_read(db, (uint32_t)(b0 + i), false, codes); ab.resize(codes.size()); for (size_t q = 0; q < codes.size(); ++q) ab[q] = "ACGT"[codes[q]]; }
-        uint64_t c0 = 0; vote_read(b0 + i, PV, VP, ab, c0, parts[i]); cnt[i] = c0;
-      }
-      for (int64_t i = 0; i < nr; ++i) {        // release in A-read order, numbering sequences like -t1
-        const std::string& s = parts[i]; size_t p = 0;
-        while (p < s.size()) {
-          size_t e = s.find('\n', p); if (e == std::string::npos) e = s.size();
-          if (s[p] == '>') { size_t s1 = s.find('/', p), s2 = s.find('/', s1 + 1); fwrite(s.data() + p, 1, s1 + 1 - p, stdout); fprintf(stdout, "%lu", (unsigned long)wellcounter++); fwrite(s.data() + s2, 1, e - s2, stdout); }
-          else fwrite(s.data() + p, 1, e - p, stdout);
-          fputc('\n', stdout); p = e + 1;
-        }
-      }
       for (auto& r : res) { totwin += r.status != DCU_WIN_SKIPPED; totok += r.status == DCU_WIN_OK; }
-      fprintf(stderr, "[V] reads [%ld,%ld) windows %zu\n", (long)b0, (long)b1, win.size());
+      fprintf(stderr, "[V] reads [%ld,%ld) windows %lu\n", (long)b0, (long)b1, (unsigned long)nw);
     }
     fflush(stdout);
     dcu_destroy(ctx);

@@ -195,6 +195,16 @@ int dh_estimate_profile(dh_data* d, int64_t first_read, int64_t last_read, uint6
     return 0;
   } catch (std::exception& e) { d->err = e.what(); return 1; }
 }
+// FastA text for the segments of the GPU vote; counter as in dh_vote; malloc'ed result
+char* dh_format_segments(const dcu_segment* seg, uint64_t nseg, const char* chars, uint64_t* counter, uint64_t* outlen) {
+  std::string out; uint64_t c = *counter;
+  format_segments(seg, nseg, chars, c, out);
+  *counter = c;
+  char* buf = (char*)malloc(out.size() + 1);
+  memcpy(buf, out.data(), out.size()); buf[out.size()] = 0;
+  *outlen = out.size();
+  return buf;
+}
 void dh_free(void* p) { free(p); }
 
 }  // extern "C"

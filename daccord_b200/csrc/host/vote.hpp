@@ -83,4 +83,14 @@ inline void vote_read(int64_t aid, std::vector<PileElement>& PV, const VoteParam
   }
 }
 
+// FastA text of the segments the GPU vote returns (dcu_vote / dcu_get_corrected): same header and line layout as vote_read (:2710-2724)
+inline void format_segments(const dcu_segment* seg, uint64_t nseg, const char* chars, uint64_t& counter, std::string& out) {
+  for (uint64_t i = 0; i < nseg; ++i) {
+    const dcu_segment& g = seg[i];
+    out += ">" + std::to_string((uint64_t)g.aread + 1) + "/" + std::to_string(counter++) + "/" + std::to_string(g.first) + "_" + std::to_string((uint64_t)g.first + g.len) +
+           " A=[" + std::to_string(g.first) + "," + std::to_string(g.last) + "]\n";
+    for (uint64_t z = 0; z < g.len; z += 80) { out.append(chars + g.off + z, (size_t)std::min<uint64_t>(80, g.len - z)); out.push_back('\n'); }
+  }
+}
+
 }  // namespace dhost

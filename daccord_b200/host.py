@@ -19,7 +19,7 @@ def lib():
             raise DcuError("host library %s not built: run `python -m daccord_b200.build`" % HOST_LIB_PATH)
         L = C.CDLL(HOST_LIB_PATH)
         for f in ("dh_sim_create", "dh_data_load", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first",
-                  "dh_select_overlaps", "dh_ovlset_data", "dh_data_trace", "dh_data_boff", "dh_data_rlen"):
+                  "dh_select_overlaps", "dh_ovlset_data", "dh_data_trace", "dh_data_boff", "dh_data_rlen", "dh_format_segments"):
             getattr(L, f).restype = C.c_void_p
         for f in ("dh_data_nreads", "dh_data_novl", "dh_data_totlen"):
             getattr(L, f).restype = C.c_uint64
@@ -148,3 +148,15 @@ class Batch:
         if self.h:
             lib().dh_batch_destroy(self.h)
             self.h = None
+
+
+def format_segments(seg, chars, counter=0):
+    """FastA text (bytes) of the segments returned by Engine.vote; returns (fasta, next counter)"""
+    c = C.c_uint64(counter)
+    n = C.c_uint64(0)
+    seg = np.ascontiguousarray(seg)
+    chars = np.ascontiguousarray(chars)
+    p = lib().dh_format_segments(seg.ctypes.data_as(C.c_void_p), C.c_uint64(len(seg)), chars.ctypes.data_as(C.c_void_p), C.byref(c), C.byref(n))
+    out = C.string_at(p, n.value)
+    lib().dh_free(C.c_void_p(p))
+    return out, c.value

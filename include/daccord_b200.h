@@ -99,6 +99,19 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
              uint32_t advance, uint64_t maxalign, uint64_t* nwin, uint64_t* nsl);
 /* window descriptors of the resident batch (aread / astart are what the pile vote needs), nwin entries */
 int dcu_get_windows(dcu_ctx* ctx, dcu_window* win, dcu_slice* sl /* may be NULL */);
+/* ---- caller stage behind the kernel on the GPU: pile vote ------------------------------------------
+ * Replaces, for the resident batch after dcu_launch, the host work of reference src/HandleContext.hpp:2446-2493
+ * (placement walk into PileElements) and :2541-2710 (sort, optional -f fill, runs of consecutive positions spanning
+ * >= 100 bases, column vote), so that corrected bases instead of per-window traces cross PCIe.  The windows of the
+ * batch must be grouped by ascending A-read and ordered by astart inside a read (what dcu_pile and the reference's
+ * window loop produce).  read_boff / read_len are needed for producefull (-f) only and may be NULL otherwise.
+ * A segment is one output sequence of the reference (:2710-2724): its FastA header is
+ * ">{aread+1}/{counter}/{first}_{first+len} A=[{first},{last}]", its bases chars[off .. off+len). */
+typedef struct dcu_segment { uint32_t aread, first, last, reserved; uint64_t len, off; } dcu_segment;
+int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* read_boff, const uint32_t* read_len, uint64_t nreads,
+             uint64_t* nseg, uint64_t* nchars);
+/* segments (in A-read, position order) and the character buffer (nchars bytes) of the last dcu_vote */
+int dcu_get_corrected(dcu_ctx* ctx, dcu_segment* seg, char* chars);
 /* statistics of the last launch: kernels launched, windows that needed the large-workspace pass */
 int dcu_last_stats(dcu_ctx* ctx, uint64_t* launches, uint64_t* hard_windows);
 /* dump the host-built tables (for tests): returns number of doubles written / needed */

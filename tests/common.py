@@ -41,7 +41,7 @@ def build_oracle():
 def build_emu():
     out = os.path.join(ROOT, "tests", "emu", "_build", "libemu.so")
     src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
-    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "host_tables.hpp", "host_caps.hpp")]
+    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "host_tables.hpp", "host_caps.hpp", "pile_core.cuh", "pile_host.hpp", "vote_core.cuh", "vote_host.hpp")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src])
@@ -85,6 +85,55 @@ def run_emu(params, packed, win, sl, tier=0):
     rc = emu_lib().emu_run_batch(C.byref(params), _ptr(packed), _ptr(win), C.c_uint64(len(win)), _ptr(sl), _ptr(res), _ptr(cons), _ptr(ops), C.c_int(tier), C.byref(nov))
     assert rc == 0
     return res, cons, ops, nov.value
+
+
+def emu_vote(win, res, cons, ops, w, producefull, minlen, packed, boff, rlen):
+    """vote_core.cuh (the GPU pile vote) compiled for the host; returns (segments, chars)"""
+    from daccord_b200 import SEGMENT_DT
+    seg = np.zeros(len(win) + 16, SEGMENT_DT)
+    chars = np.zeros(int(rlen.sum()) * 2 + 1024, np.uint8)
+    ns, nc = C.c_uint64(0), C.c_uint64(0)
+    packed = np.ascontiguousarray(packed)
+    rc = emu_lib().emu_vote(_ptr(win), _ptr(res), _ptr(cons), _ptr(ops), C.c_uint64(len(win)), C.c_uint32(w), C.c_int(1 if producefull else 0), C.c_uint64(minlen),
+                            _ptr(packed), _ptr(boff), _ptr(rlen), C.c_uint64(len(rlen)), _ptr(seg), C.c_uint64(len(seg)), _ptr(chars), C.c_uint64(len(chars)),
+                            C.byref(ns), C.byref(nc))
+    assert rc == 0, rc
+    return seg[:ns.value], chars[:nc.value]
+
+
+def random_placements(win, w, rng, pfail, pins):
+    """random but well-formed window results (status, consensus, placement trace covering exactly w A bases) to stress the votes:
+    clumps of failed windows (gaps, short runs), insertion runs, trailing insertions"""
+    from daccord_b200 import RESULT_DT
+    n = len(win)
+    res = np.zeros(n, RESULT_DT); cons = np.zeros(n * CONS_STRIDE, np.uint8); ops = np.zeros(n * OPS_STRIDE, np.uint8)
+    st = np.ones(n, np.uint8); i = 0
+    while i < n:
+        if rng.random() < pfail * 0.2:
+            ln = int(rng.integers(1, 30)); st[i:i + ln] = 2; i += ln
+        else:
+            i += 1
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    for i in range(n):
+        o, c, j = [], [], 0
+        while j < w:
+            while rng.random() < pins and len(c) < 60 and len(o) < 120:
+                o.append(2); c.append(int(rng.integers(0, 4)))
+            if len(c) >= 62 or len(o) >= 124:
+                o.append(3); j += 1; continue
+            x = rng.random()
+            if x < 0.1:
+                o.append(3)
+            else:
+                o.append(0 if x < 0.9 else 1); c.append(int(rng.integers(0, 4)))
+            j += 1
+        while rng.random() < pins * 2 and len(c) < 63 and len(o) < 127:
+            o.append(2); c.append(int(rng.integers(0, 4)))
+        res[i]["status"] = st[i]; res[i]["nops"] = len(o); res[i]["clen"] = len(c)
+        ops[i * OPS_STRIDE:i * OPS_STRIDE + len(o)] = o
+        if c:
+            cons[i * CONS_STRIDE:i * CONS_STRIDE + len(c)] = acgt[np.array(c, dtype=np.int64)]
+    return res, cons, ops
 
 
 def get_tables(lib, fn, params, which, klimn=64):
