@@ -22,7 +22,7 @@ static_assert(sizeof(dvote::Win) == sizeof(dcu_window) && sizeof(dvote::Res) == 
 
 namespace {
 
-constexpr int WPB = 16;                // warps per block
+constexpr int WPB = 16;                // warps per block (one 32-warp block per SM with whole-block barriers measured 5 % slower, profiles/r01_summary.md)
 constexpr int BPS = 2;                 // resident blocks per SM the kernel is compiled for (64 registers / thread)
 
 struct KArgs {
@@ -32,6 +32,7 @@ struct KArgs {
   const uint32_t* todo;                // window indices to run (nullptr: 0..n-1)
   uint32_t n; uint32_t vs_words;       // vs_words != 0: stage the VS table in dynamic shared memory
   int sync_group;                      // warps per phase-synchronous group (1 = free running, WPB = whole block)
+  int sync_mask;                       // inner stage boundaries that are barriers
   unsigned int* ticket;                // work counter
   unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this tier
 };
@@ -48,12 +49,13 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
   // phase-synchronous execution: every warp owns one window at a time and walks it through the stages of
   // window_core.cuh; warps are tied into groups of `sync_group` warps by named barriers so that the warps of a group
   // run the same stage's code at the same time (instruction-cache locality) without waiting on the whole block
-  __shared__ int s_done[WPB];
+  __shared__ int s_done[2][WPB];                       // double buffered: with a single barrier per round a fast warp must not overwrite what a slow one still reads
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
   auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
+  const int smask = a.sync_mask;                       // which of the inner stage boundaries are barriers (bit 0: hash|nodes, 5: nodes|edges, 1: edges|trav, 4: trav|pos, 2: pos|rpath, 6: rpath|search, 7: search|score, 3: score|final)
   dcu::WinState st; st.ph = dcu::PH_END;
-  uint32_t wi = 0; bool done = false;
-  for (;;) {
+  uint32_t wi = 0; bool done = false; int par = 0;
+  for (;; par ^= 1) {
     // stage 0: finish / fetch
     while (!done && st.ph == dcu::PH_END) {
       unsigned int t = 0;
@@ -68,17 +70,27 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
         if (st.res.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
       }
     }
-    if (lane == 0) s_done[warp] = (done && st.ph == dcu::PH_END) ? 1 : 0;
+    if (lane == 0) s_done[par][warp] = (done && st.ph == dcu::PH_END) ? 1 : 0;
     gsync();
     bool alldone = true;
-    for (int i = 0; i < G; ++i) alldone = alldone && (s_done[gfirst + i] != 0);
+    for (int i = 0; i < G; ++i) alldone = alldone && (s_done[par][gfirst + i] != 0);
     if (alldone) break;
     if (st.ph == dcu::PH_HASH) dcu::st_hash(c, st, lane);
-    gsync();
+    if (smask & 1) gsync();
     if (st.ph == dcu::PH_NODES) dcu::st_nodes(c, st, lane);
-    gsync();
+    if (smask & 32) gsync();
+    if (st.ph == dcu::PH_EDGES) dcu::st_edges(c, st, lane);
+    if (smask & 2) gsync();
     if (st.ph == dcu::PH_TRAV) dcu::st_trav(c, st, lane);
-    gsync();
+    if (smask & 16) gsync();
+    if (st.ph == dcu::PH_POS) dcu::st_pos(c, st, lane);
+    if (smask & 4) gsync();
+    if (st.ph == dcu::PH_RPATH) dcu::st_rpath(c, st, lane);
+    if (smask & 64) gsync();
+    if (st.ph == dcu::PH_SEARCH) dcu::st_search(c, st, lane);
+    if (smask & 128) gsync();
+    if (st.ph == dcu::PH_SCORE) dcu::st_score(c, st, lane);
+    if (smask & 8) gsync();
     if (st.ph == dcu::PH_FINAL) dcu::st_final(c, st, a.cons + (size_t)wi * DCU_CONS_STRIDE, a.ops + (size_t)wi * DCU_OPS_STRIDE, lane);
     if (st.ph == dcu::PH_END && !done) {
       // window finished in this round (final stage, or an overflow inside a stage): publish
@@ -481,8 +493,9 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   if (vs_bytes > 40 * 1024 || getenv("DCU_VS_GLOBAL")) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);
   a.sync_group = tier ? 1 : ctx->sync_group;       // the large-workspace pass only sees heavy-tailed windows: free running
+  { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 15; }
   {   // leave as much of the 228 KB as possible to L1: the kernel lives on cached scratch data (measured +5 %, profiles/r01_summary.md)
-    int pct = (int)((ctx->blocks_per_sm[tier] * (vs_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
+    int pct = (int)((bps * (vs_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
     const char* e = getenv("DCU_CARVEOUT");
     if (e) pct = atoi(e);
     CK(cudaFuncSetAttribute(dcu_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));

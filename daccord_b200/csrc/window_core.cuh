@@ -1238,7 +1238,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
 #ifdef DCU_EMU_STATS
 static long g_stats[16];
 #endif
-struct TravState { int fi, li, ncdh, firstthres, lastthres; uint32_t freeslots; bool started; };
+struct TravState { int fi, li, ncdh, firstthres, lastthres; uint32_t freeslots; bool started; int F, L, narp; };
 
 DCU_BIG void trav_start(Ctx& c, TravState& t, int lane) {
 #ifdef DCU_EMU_STATS
@@ -1263,32 +1263,38 @@ DCU_BIG bool trav_seek(Ctx& c, TravState& t) {
     t.li += 1;
   }
 }
-// one (first,last) pair at (fi, li), then advances li  (:4802-5097)
-DCU_BIG void trav_pair(Ctx& c, TravState& t, int lmin, int lmax, int lane) {
+// one (first,last) pair at (fi, li), then advances li  (:4802-5097), in two halves so that the kernel can put a barrier between
+// the lane-parallel graph work (trav_pair_graph) and the single-lane searches (trav_pair_search)
+DCU_BIG void trav_pair_graph(Ctx& c, TravState& t, int lane) {
   const WS& w = c.ws;
-  const int F = w.fl_nid()[t.fi];
-  const int L = lookup(c, w.ll_kmer()[t.li]);
+  t.F = w.fl_nid()[t.fi];
+  t.L = lookup(c, w.ll_kmer()[t.li]);
   t.li += 1;
 #ifdef DCU_EMU_STATS
   g_stats[0]++;
 #endif
-  derive_stretches(c, F, L, lane);
-  if (c.overflow) return;
+  derive_stretches(c, t.F, t.L, lane);
+}
+DCU_BIG void trav_pair_weights(Ctx& c, int lane) {
   stretch_positions(c, lane);
   if (c.overflow) return;
   stretch_links(c, lane);
-  if (c.overflow) return;
+}
+DCU_BIG void trav_pair_rpaths(Ctx& c, TravState& t, int lmax, int lane) {
   int narp = 0;
-  if (lane == 0) reverse_paths(c, L, lmax, narp);
+  if (lane == 0) reverse_paths(c, t.L, lmax, narp);
   c.overflow = bcast(c.overflow, 0); narp = bcast(narp, 0);
   wsync();
+  t.narp = narp;
   if (c.overflow) return;
 #ifdef DCU_EMU_STATS
   g_stats[1] += narp; g_stats[2] += c.nds; g_stats[3] += c.nn; g_stats[4] += c.nrl; { long sl = 0; for (int s = 0; s < c.nds; ++s) sl += c.ws.ds_len()[s]; g_stats[5] += sl; }
 #endif
   sort_reverse_paths(c, narp, lane);
+}
+DCU_BIG void trav_pair_search(Ctx& c, TravState& t, int lmin, int lmax, int lane) {
   int ncdh = t.ncdh; uint32_t fs = t.freeslots;
-  if (lane == 0) search_pair(c, F, lmin, lmax, narp, ncdh, fs);
+  if (lane == 0) search_pair(c, t.F, lmin, lmax, t.narp, ncdh, fs);
   t.ncdh = bcast(ncdh, 0); t.freeslots = bcast(fs, 0);
   c.overflow = bcast(c.overflow, 0);
   wsync();
@@ -1383,7 +1389,7 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
 // small state machine so that the kernel can run the warps of a block phase by phase (all warps of a block execute
 // the same phase's code between two block barriers, which is what keeps the instruction caches effective);
 // process_window below is the plain sequential driver over the same stages.
-enum { PH_BEGIN = 0, PH_HASH, PH_NODES, PH_TRAV, PH_FINAL, PH_END };
+enum { PH_BEGIN = 0, PH_HASH, PH_NODES, PH_EDGES, PH_TRAV, PH_POS, PH_RPATH, PH_SEARCH, PH_SCORE, PH_FINAL, PH_END };
 struct WinState {
   int ph;
   Result res;
@@ -1431,6 +1437,9 @@ DCU_BIG void st_nodes(Ctx& c, WinState& s, int lane) {
     if (!c.overflow) node_ranges(c, lane);
     if (c.overflow) { st_overflow(c, s); return; }
   }
+  s.ph = PH_EDGES;
+}
+DCU_BIG void st_edges(Ctx& c, WinState& s, int lane) {
   build_edges(c, lane);
   s.mintry = 0; s.tv.started = false; s.ph = PH_TRAV;
 }
@@ -1441,17 +1450,13 @@ DCU_FN void st_after_tries(WinState& s, bool lconsok) {
   else { s.ff -= 1; if (s.ff >= DCU_P.minff) { s.ph = PH_NODES; return; } nextk = true; }
   if (nextk) { s.k += 1; s.ph = (s.k <= DCU_P.k_hi) ? PH_HASH : PH_FINAL; }
 }
-// one call = at most one (first,last) pair of the current traverse; the call that exhausts the pairs also scores the
-// candidates and takes the decision of the try loop (:2274-2322: up to 3 tries, next edge frequency class in between)
-DCU_BIG void st_trav(Ctx& c, WinState& s, int lane) {
+// PH_TRAV: starts a traverse if none is running and derives the unitigs of the next (first,last) pair; PH_POS: their position
+// weights and links; PH_RPATH: the reverse paths; PH_SEARCH: the forward search and pairing.  When the pairs are exhausted
+// PH_SCORE scores the candidates and takes the decision of the try loop
+// (:2274-2322: up to 3 tries, next edge frequency class in between)
+DCU_BIG void st_trav_done(Ctx& c, WinState& s, int lane) {
   const WS& w = c.ws;
   TravState& t = s.tv;
-  if (!t.started) { trav_start(c, t, lane); if (c.overflow) { st_overflow(c, s); return; } }
-  if (trav_seek(c, t)) {
-    trav_pair(c, t, s.lmin, s.lmax, lane);
-    if (c.overflow) { st_overflow(c, s); return; }
-    if (trav_seek(c, t)) { s.ph = PH_TRAV; return; }      // more pairs: next round
-  }
   int nacc = trav_finish(c, t, lane);
   if (nacc > 0) {
     bool lconsok = false;
@@ -1470,6 +1475,34 @@ DCU_BIG void st_trav(Ctx& c, WinState& s, int lane) {
   if (!add_next(c, lane)) { st_after_tries(s, false); return; }
   s.ph = PH_TRAV;                                          // retry: the next call starts a new traverse
 }
+DCU_BIG void st_trav(Ctx& c, WinState& s, int lane) {
+  TravState& t = s.tv;
+  if (!t.started) { trav_start(c, t, lane); if (c.overflow) { st_overflow(c, s); return; } }
+  if (trav_seek(c, t)) {
+    trav_pair_graph(c, t, lane);
+    if (c.overflow) { st_overflow(c, s); return; }
+    s.ph = PH_POS;
+    return;
+  }
+  s.ph = PH_SCORE;
+}
+DCU_BIG void st_pos(Ctx& c, WinState& s, int lane) {
+  trav_pair_weights(c, lane);
+  if (c.overflow) { st_overflow(c, s); return; }
+  s.ph = PH_RPATH;
+}
+DCU_BIG void st_rpath(Ctx& c, WinState& s, int lane) {
+  trav_pair_rpaths(c, s.tv, s.lmax, lane);
+  if (c.overflow) { st_overflow(c, s); return; }
+  s.ph = PH_SEARCH;
+}
+DCU_BIG void st_search(Ctx& c, WinState& s, int lane) {
+  TravState& t = s.tv;
+  trav_pair_search(c, t, s.lmin, s.lmax, lane);
+  if (c.overflow) { st_overflow(c, s); return; }
+  s.ph = trav_seek(c, t) ? PH_TRAV : PH_SCORE;            // more pairs: next round
+}
+DCU_BIG void st_score(Ctx& c, WinState& s, int lane) { st_trav_done(c, s, lane); }
 DCU_BIG void st_final(Ctx& c, WinState& s, uint8_t* cons_out, uint8_t* ops_out, int lane) {
   const WS& w = c.ws;
   Result& res = s.res;
@@ -1493,7 +1526,12 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
   while (s.ph != PH_END) {
     if (s.ph == PH_HASH) st_hash(c, s, lane);
     else if (s.ph == PH_NODES) st_nodes(c, s, lane);
+    else if (s.ph == PH_EDGES) st_edges(c, s, lane);
     else if (s.ph == PH_TRAV) st_trav(c, s, lane);
+    else if (s.ph == PH_POS) st_pos(c, s, lane);
+    else if (s.ph == PH_RPATH) st_rpath(c, s, lane);
+    else if (s.ph == PH_SEARCH) st_search(c, s, lane);
+    else if (s.ph == PH_SCORE) st_score(c, s, lane);
     else st_final(c, s, cons_out, ops_out, lane);
   }
   res = s.res;
