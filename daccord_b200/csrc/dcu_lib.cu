@@ -105,6 +105,41 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
 
 
 // ---------------------------------------------------------------- piling kernels (pile_core.cuh), one thread per item
+// ---- scan helpers shared by the piling and vote stages: one value per thread, SCAN_TPB threads per block
+constexpr int VOTE_TPB = 256;
+// block-wide exclusive scan of one value per thread (VOTE_TPB threads); returns the thread's offset, *total = block sum
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t s_w[VOTE_TPB / 32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_w[wp] = x;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+  for (int i = 0; i < VOTE_TPB / 32; ++i) { if (i < wp) base += s_w[i]; tot += s_w[i]; }
+  __syncthreads();
+  *total = tot;
+  return base + x - v;
+}
+// exclusive scan of the block sums in place (one block); blk[nblk] = grand total
+__global__ void __launch_bounds__(VOTE_TPB) vote_kscan(uint64_t* blk, uint64_t nblk) {
+  __shared__ uint64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < nblk; base += VOTE_TPB) {
+    const uint64_t i = base + threadIdx.x;
+    const uint32_t v = i < nblk ? (uint32_t)blk[i] : 0u;          // a block sum is < 2^32 (<= 127 * VOTE_TPB)
+    uint32_t total;
+    const uint32_t off = block_exscan(v, &total);
+    const uint64_t carry = s_carry;
+    if (i < nblk) blk[i] = carry + off;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blk[nblk] = s_carry;
+}
+
 __global__ void pile_k0(const dpile::Ovl* ovl, uint64_t novl, const uint16_t* trace, uint32_t* tile_b) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < novl) dpile::pile_tile_starts(ovl[i], trace, tile_b);
@@ -120,16 +155,31 @@ __global__ void __launch_bounds__(64) pile_k1(const dpile::Ovl* ovl, uint64_t no
   dpile::U128 PV[dpile::PILE_MAXB + 1], MV[dpile::PILE_MAXB + 1], PH[dpile::PILE_MAXB + 1], MH[dpile::PILE_MAXB + 1];
   dpile::pile_align_tile(o, (int)(t - o.tile_off), P, trace, tile_b, packed, read_boff, read_len, s0, l, bm, PV, MV, PH, MH);
 }
-__global__ void pile_k2(const dpile::ReadInfo* reads, const uint32_t* read_id, uint64_t nr, const dpile::Ovl* ovl, dpile::Params P, const uint32_t* bm,
-                        const uint64_t* read_boff, const uint32_t* read_len, const double* minerate, const double* ediv, int fill,
-                        dpile::Win* win, dpile::Sl* sl, uint32_t* nwin, uint32_t* nsl, unsigned long long* act, int* err) {
+__global__ void pile_k2a(const dpile::ReadInfo* reads, uint64_t nr, const dpile::Ovl* ovl, const double* minerate, const double* ediv, unsigned long long* keys) {
   uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nr) return;
-  const dpile::ReadInfo R = reads[r];
-  uint32_t nw = 0, ns = 0;
-  int rc = dpile::pile_read(R, ovl, P, bm, read_boff, read_len, minerate[r], ediv[r], fill != 0, win, sl, &nw, &ns, act + R.ovl_begin, (int)(R.ovl_end - R.ovl_begin), read_id[r]);
-  if (rc) atomicExch(err, rc);
-  nwin[r] = nw; nsl[r] = ns;
+  if (r < nr) dpile::pile_order(reads[r], ovl, minerate[r], ediv[r], keys + reads[r].ovl_begin);
+}
+// one thread per candidate window.  pass 0 (win == nullptr): slices per candidate (0 = empty pile) and per block the number of
+// windows and slices; pass 1: descriptors at the scanned offsets
+__global__ void __launch_bounds__(VOTE_TPB) pile_k2(const dpile::ReadInfo* reads, const uint32_t* read_id, uint32_t nr, uint64_t ncand, const dpile::Ovl* ovl, dpile::Params P,
+                                                   const uint32_t* bm, const uint64_t* read_boff, const uint32_t* read_len, const unsigned long long* keys,
+                                                   uint32_t* cnt, uint64_t* blkw, uint64_t* blks, dpile::Win* win, dpile::Sl* sl, int* err) {
+  const uint64_t idx = (uint64_t)blockIdx.x * VOTE_TPB + threadIdx.x;
+  uint32_t n = 0, r = 0, y = 0;
+  if (idx < ncand) {
+    uint32_t a = 0, b = nr;                       // last read with win_off <= idx that has candidates
+    while (b - a > 1) { uint32_t mid = (a + b) >> 1; if (reads[mid].win_off <= idx) a = mid; else b = mid; }
+    r = a; y = (uint32_t)(idx - reads[r].win_off);
+    if (!win) { n = (uint32_t)dpile::pile_window(reads[r], y, ovl, P, bm, read_boff, read_len, keys + reads[r].ovl_begin, read_id[r], nullptr, nullptr, 0u); cnt[idx] = n; }
+    else n = cnt[idx];
+  }
+  uint32_t totw, tots;
+  const uint32_t woff = block_exscan(n ? 1u : 0u, &totw);
+  const uint32_t soff = block_exscan(n, &tots);
+  if (!win) { if (threadIdx.x == 0) { blkw[blockIdx.x] = totw; blks[blockIdx.x] = tots; } return; }
+  if (!n) return;
+  const uint64_t wo = blkw[blockIdx.x] + woff, so = blks[blockIdx.x] + soff;
+  if (dpile::pile_window(reads[r], y, ovl, P, bm, read_boff, read_len, keys + reads[r].ovl_begin, read_id[r], win + wo, sl + so, (uint32_t)so) < 0) atomicExch(err, 2);
 }
 // per-window pile statistics of a device-built batch: max slice count and max bases of a window
 __global__ void pile_k3(const dpile::Win* win, const dpile::Sl* sl, uint64_t nwin, unsigned int* maxS, unsigned int* maxB) {
@@ -141,25 +191,10 @@ __global__ void pile_k3(const dpile::Win* win, const dpile::Sl* sl, uint64_t nwi
 }
 
 // ---- pile vote (vote_core.cuh): per window the offset table, per A position the column votes (count pass, then fill pass)
-constexpr int VOTE_TPB = 256;
 __global__ void vote_k0(const dvote::Res* res, const uint8_t* ops, uint64_t nwin, dvote::Params P, uint16_t* ent, int* err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nwin || res[i].status != dvote::ST_OK) return;
   if (!dvote::vote_window_table(res[i], ops + i * P.ops_stride, P.w, ent + i * (P.w + 1))) atomicExch(err, 1);
-}
-// block-wide exclusive scan of one value per thread (VOTE_TPB threads); returns the thread's offset, *total = block sum
-__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t s_w[VOTE_TPB / 32];
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  uint32_t x = v;
-  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-  if (lane == 31) s_w[wp] = x;
-  __syncthreads();
-  uint32_t base = 0, tot = 0;
-  for (int i = 0; i < VOTE_TPB / 32; ++i) { if (i < wp) base += s_w[i]; tot += s_w[i]; }
-  __syncthreads();
-  *total = tot;
-  return base + x - v;
 }
 // pass 0 (chars == nullptr): per position the character count (bit 7: the pile holds something there) and per block the sum;
 // pass 1: the characters at blk_off[block] + in-block offset, and the run boundary records
@@ -184,25 +219,6 @@ __global__ void __launch_bounds__(VOTE_TPB) vote_k1(dvote::Ctx c, const dvote::R
   if (!left) { unsigned int q = atomicAdd(nbound, 1u); if (q < bound_cap) bound[q] = dvote::Bound{o, r, p, 0u, 0u}; }
   if (!right) { unsigned int q = atomicAdd(nbound, 1u); if (q < bound_cap) bound[q] = dvote::Bound{o + n, r, p, 1u, 0u}; }
 }
-// exclusive scan of the block sums in place (one block); blk[nblk] = grand total
-__global__ void __launch_bounds__(VOTE_TPB) vote_kscan(uint64_t* blk, uint64_t nblk) {
-  __shared__ uint64_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (uint64_t base = 0; base < nblk; base += VOTE_TPB) {
-    const uint64_t i = base + threadIdx.x;
-    const uint32_t v = i < nblk ? (uint32_t)blk[i] : 0u;          // a block sum is < 2^32 (<= 127 * VOTE_TPB)
-    uint32_t total;
-    const uint32_t off = block_exscan(v, &total);
-    const uint64_t carry = s_carry;
-    if (i < nblk) blk[i] = carry + off;
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry = carry + total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) blk[nblk] = s_carry;
-}
-
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DCU_ERR_CUDA; } } while (0)
 
 template <class T> struct DevBuf {
@@ -241,8 +257,8 @@ struct dcu_ctx {
   dcu::Caps slab_caps[2] = {}; uint32_t slab_bytes[2] = {0, 0};
   uint64_t nwin = 0, nsl = 0; int maxS = 0, maxB = 0;
   // piling scratch
-  DevBuf<dpile::Ovl> dpo; DevBuf<dpile::ReadInfo> dpr; DevBuf<uint32_t> dprid, dptile, dpbm, dpnw, dpns, dprlen; DevBuf<uint64_t> dpboff; DevBuf<uint16_t> dptrace;
-  DevBuf<double> dpmin, dpdiv; DevBuf<unsigned long long> dpact;
+  DevBuf<dpile::Ovl> dpo; DevBuf<dpile::ReadInfo> dpr; DevBuf<uint32_t> dprid, dptile, dpbm, dprlen; DevBuf<uint64_t> dpboff; DevBuf<uint16_t> dptrace;
+  DevBuf<double> dpmin, dpdiv; DevBuf<unsigned long long> dpact; DevBuf<uint32_t> dpcnt; DevBuf<uint64_t> dpblkw, dpblks;
   // vote scratch and results
   DevBuf<uint16_t> dvent; DevBuf<uint8_t> dvflag; DevBuf<uint64_t> dvblk; DevBuf<char> dvchars; DevBuf<dvote::Read> dvreads; DevBuf<dvote::Bound> dvbound;
   std::vector<dcu_segment> segs; uint64_t nchars = 0; bool results_valid = false;
@@ -310,8 +326,8 @@ void dcu_destroy(dcu_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->dDPn.release(); ctx->dDPsq.release(); ctx->dVSq.release(); ctx->dklim.release(); ctx->dsuplo.release(); ctx->dsuphi.release();
   ctx->dpacked_own.release(); ctx->dwin.release(); ctx->dsl.release(); ctx->dres.release(); ctx->dcons.release(); ctx->dops.release();
-  ctx->dpo.release(); ctx->dpr.release(); ctx->dprid.release(); ctx->dptile.release(); ctx->dpbm.release(); ctx->dpnw.release(); ctx->dpns.release(); ctx->dprlen.release();
-  ctx->dpboff.release(); ctx->dptrace.release(); ctx->dpmin.release(); ctx->dpdiv.release(); ctx->dpact.release();
+  ctx->dpo.release(); ctx->dpr.release(); ctx->dprid.release(); ctx->dptile.release(); ctx->dpbm.release(); ctx->dprlen.release();
+  ctx->dpboff.release(); ctx->dptrace.release(); ctx->dpmin.release(); ctx->dpdiv.release(); ctx->dpact.release(); ctx->dpcnt.release(); ctx->dpblkw.release(); ctx->dpblks.release();
   ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release();
   ctx->dvent.release(); ctx->dvflag.release(); ctx->dvblk.release(); ctx->dvchars.release(); ctx->dvreads.release(); ctx->dvbound.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -409,7 +425,7 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
   const uint64_t nr = P.reads.size();
   dpile::Params prm; prm.tspace = tspace; prm.w = ctx->prm.w; prm.a = advance; prm.maxalign = maxalign;
   CK(ctx->dpo.ensure(novl + 1)); CK(ctx->dpr.ensure(nr + 1)); CK(ctx->dprid.ensure(nr + 1)); CK(ctx->dptile.ensure(P.ntiles + 1)); CK(ctx->dpbm.ensure(P.nbm + 1));
-  CK(ctx->dpnw.ensure(nr + 1)); CK(ctx->dpns.ensure(nr + 1)); CK(ctx->dprlen.ensure(nreads + 1)); CK(ctx->dpboff.ensure(nreads + 1)); CK(ctx->dptrace.ensure(ntrace + 1));
+  CK(ctx->dprlen.ensure(nreads + 1)); CK(ctx->dpboff.ensure(nreads + 1)); CK(ctx->dptrace.ensure(ntrace + 1));
   CK(ctx->dpmin.ensure(nr + 1)); CK(ctx->dpdiv.ensure(nr + 1)); CK(ctx->dpact.ensure(novl + 1)); CK(ctx->dcnt.ensure(8));
   cudaStream_t st = ctx->stream;
   if (novl) CK(cudaMemcpyAsync(ctx->dpo.p, P.ovl.data(), novl * sizeof(dpile::Ovl), cudaMemcpyHostToDevice, st));
@@ -426,28 +442,32 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
   unsigned int mx[2] = {4, 64};
   if (novl) {
     int* derr = (int*)(ctx->dcnt.p + 4);
+    const uint64_t ncand = P.ncand, nblk = (ncand + VOTE_TPB - 1) / VOTE_TPB;
+    if (nblk >= 0x7FFFFFFFull) { ctx->err = "batch too large"; return DCU_ERR_UNSUPPORTED; }
+    CK(ctx->dpcnt.ensure(ncand + 1)); CK(ctx->dpblkw.ensure(nblk + 2)); CK(ctx->dpblks.ensure(nblk + 2));
     CK(cudaMemsetAsync(ctx->dcnt.p + 4, 0, 4 * sizeof(unsigned int), st));
     pile_k0<<<(unsigned)((novl + 127) / 128), 128, 0, st>>>(ctx->dpo.p, novl, ctx->dptrace.p, ctx->dptile.p);
     pile_k1<<<(unsigned)((P.ntiles + 63) / 64), 64, 0, st>>>(ctx->dpo.p, novl, P.ntiles, ctx->dpr.p, prm, ctx->dptrace.p, ctx->dptile.p, ctx->dpacked, ctx->dpboff.p, ctx->dprlen.p, ctx->dpbm.p);
-    pile_k2<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(ctx->dpr.p, ctx->dprid.p, nr, ctx->dpo.p, prm, ctx->dpbm.p, ctx->dpboff.p, ctx->dprlen.p, ctx->dpmin.p, ctx->dpdiv.p, 0,
-                                                     nullptr, nullptr, ctx->dpnw.p, ctx->dpns.p, ctx->dpact.p, derr);
-    CK(cudaGetLastError());
-    std::vector<uint32_t> hnw(nr), hns(nr); int herr = 0;
-    CK(cudaMemcpyAsync(hnw.data(), ctx->dpnw.p, nr * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hns.data(), ctx->dpns.p, nr * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (herr) { ctx->err = "piling failed on the device (active-set capacity)"; return DCU_ERR_OVERFLOW; }
-    for (uint64_t r = 0; r < nr; ++r) { P.reads[r].win_off = tw; P.reads[r].sl_off = ts; tw += hnw[r]; ts += hns[r]; }
+    pile_k2a<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(ctx->dpr.p, nr, ctx->dpo.p, ctx->dpmin.p, ctx->dpdiv.p, ctx->dpact.p);
+    if (ncand) {
+      pile_k2<<<(unsigned)nblk, VOTE_TPB, 0, st>>>(ctx->dpr.p, ctx->dprid.p, (uint32_t)nr, ncand, ctx->dpo.p, prm, ctx->dpbm.p, ctx->dpboff.p, ctx->dprlen.p, ctx->dpact.p,
+                                                 ctx->dpcnt.p, ctx->dpblkw.p, ctx->dpblks.p, nullptr, nullptr, derr);
+      vote_kscan<<<1, VOTE_TPB, 0, st>>>(ctx->dpblkw.p, nblk);
+      vote_kscan<<<1, VOTE_TPB, 0, st>>>(ctx->dpblks.p, nblk);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(&tw, ctx->dpblkw.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&ts, ctx->dpblks.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
     if (tw >= 0xFFFFFFF0ull || ts >= 0xFFFFFFF0ull) { ctx->err = "batch too large"; return DCU_ERR_UNSUPPORTED; }
     CK(ctx->dwin.ensure(tw + 1)); CK(ctx->dsl.ensure(ts + 1));
-    CK(cudaMemcpyAsync(ctx->dpr.p, P.reads.data(), nr * sizeof(dpile::ReadInfo), cudaMemcpyHostToDevice, st));
-    pile_k2<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(ctx->dpr.p, ctx->dprid.p, nr, ctx->dpo.p, prm, ctx->dpbm.p, ctx->dpboff.p, ctx->dprlen.p, ctx->dpmin.p, ctx->dpdiv.p, 1,
-                                                     (dpile::Win*)ctx->dwin.p, (dpile::Sl*)ctx->dsl.p, ctx->dpnw.p, ctx->dpns.p, ctx->dpact.p, derr);
+    if (tw) pile_k2<<<(unsigned)nblk, VOTE_TPB, 0, st>>>(ctx->dpr.p, ctx->dprid.p, (uint32_t)nr, ncand, ctx->dpo.p, prm, ctx->dpbm.p, ctx->dpboff.p, ctx->dprlen.p, ctx->dpact.p,
+                                                       ctx->dpcnt.p, ctx->dpblkw.p, ctx->dpblks.p, (dpile::Win*)ctx->dwin.p, (dpile::Sl*)ctx->dsl.p, derr);
     unsigned int* dmx = ctx->dcnt.p + 6;
     CK(cudaMemcpyAsync(dmx, mx, sizeof(mx), cudaMemcpyHostToDevice, st));
     if (tw) pile_k3<<<(unsigned)((tw + 255) / 256), 256, 0, st>>>((const dpile::Win*)ctx->dwin.p, (const dpile::Sl*)ctx->dsl.p, tw, dmx, dmx + 1);
     CK(cudaGetLastError());
+    int herr = 0;
     CK(cudaMemcpyAsync(mx, dmx, sizeof(mx), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

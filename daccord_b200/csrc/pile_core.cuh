@@ -2,12 +2,13 @@
 // trace reconstruction from DALIGNER trace points and window / slice extraction, i.e. daccord's
 // OverlapDataInterface::computeTrace + advanceA / getStringLengthUsed bookkeeping and the active-set loop of
 // HandleContext::operator() (reference src/HandleContext.hpp:1740-2049), producing the dcu_window / dcu_slice
-// descriptors directly in HBM.  Three per-item routines, one GPU thread each:
+// descriptors directly in HBM.  Per-item routines, one GPU thread each:
 //   pile_tile_starts : per overlap, B offset at which every trace tile starts           (prefix over the trace points)
 //   pile_align_tile  : per tile, unit-cost global alignment of the A tile against its B block with 128-bit Myers
 //                      vectors and a bit-vector traceback (rule: diagonal, DEL, INS); records the B offset reached
 //                      after every A position that a window boundary can fall on
-//   pile_read        : per A-read, the window loop: activation, expiry, order by (escore<<32)|z, slices
+//   pile_order       : per A-read, its overlaps in pile order (escore<<32)|z
+//   pile_window      : per window, the pile (a pure function of the read's overlaps, see below) and its slices
 // Requirements of this path (checked by the host, which otherwise uses the host piler): w % a == 0, A tile <= 128.
 // The same source is compiled for the host (tests/emu, -DDCU_EMU) to check it against the host piler without a GPU.
 #pragma once
@@ -34,7 +35,7 @@ struct Ovl {                     // one selected overlap (host order: by A-read,
   uint64_t bm_off;               // first entry of this overlap in the boundary offset array
   uint32_t ridx, pad;            // index of the A-read in the batch
 };
-struct ReadInfo { uint64_t ovl_begin, ovl_end; uint64_t win_off, sl_off; uint32_t maxaepos; uint32_t nwin, nsl; };
+struct ReadInfo { uint64_t ovl_begin, ovl_end; uint64_t win_off, sl_off; uint32_t maxaepos; uint32_t nwin, nsl; };   // win_off / nwin: index of the read's first candidate window / their number
 struct Params { int32_t tspace; uint32_t w, a; uint64_t maxalign; };
 
 PILE_FN uint8_t base_at(const uint8_t* packed, uint64_t boff, uint32_t len, uint32_t pos, bool comp) {
@@ -133,66 +134,60 @@ struct Win { uint32_t slice_begin; uint16_t slice_cnt; uint16_t reserved; uint32
 struct Sl { uint32_t gpos; uint16_t len; uint16_t flags; };
 
 // windows of HandleContext::Windows (reference src/HandleContext.hpp:382-447)
-PILE_FN uint64_t win_count(uint64_t l, uint64_t a, uint64_t w) {
+PILE_HD uint64_t win_count(uint64_t l, uint64_t a, uint64_t w) {
   uint64_t npre = (l + a >= w) ? ((l + a - w) / a) : 0;
   if (npre) return ((npre - 1) * a + w == l) ? npre : npre + 1;
   return l >= w ? 1 : 0;
 }
-PILE_FN uint64_t win_start(uint64_t i, uint64_t l, uint64_t a, uint64_t w) { return (i * a + w <= l) ? i * a : l - w; }
+PILE_HD uint64_t win_start(uint64_t i, uint64_t l, uint64_t a, uint64_t w) { return (i * a + w <= l) ? i * a : l - w; }
 
-// The window loop of one A-read.  fill == false: count windows and slices only.  `act` is this read's scratch list of
-// active overlaps (key = (escore << 32) | z, kept sorted), at most cap entries.  Returns 1 on a capacity problem.
-PILE_FN int pile_read(const ReadInfo& R, const Ovl* ovl, const Params& P, const uint32_t* bm, const uint64_t* read_boff, const uint32_t* read_len,
-                      double minerate, double ediv, bool fill, Win* win, Sl* sl, uint32_t* nwin_out, uint32_t* nsl_out,
-                      unsigned long long* act, int cap, uint32_t aread) {
+// The pile of a window is a pure function of the read's overlaps: the reference's loop activates an overlap at the first window
+// with astart >= abpos if it reaches that window's end, and expires it at the first window it does not reach
+// (src/HandleContext.hpp:1904-1977); window ends only grow, so overlap o is in the pile of window [astart, aend) iff
+// o.abpos <= astart && o.aepos >= aend.  The pile order is the key (escore << 32) | z (:1958-1962).  That makes every window
+// independent: one thread per candidate window instead of one per read.
+//
+// pile_order: per read, the keys of its overlaps in ascending order (z = key & 0xFFFFFFFF indexes the read's overlap list)
+PILE_FN void pile_order(const ReadInfo& R, const Ovl* ovl, double minerate, double ediv, unsigned long long* keys) {
   const uint64_t nintv = R.ovl_end - R.ovl_begin;
-  uint32_t nw = 0, ns = 0;
-  if (!nintv) { *nwin_out = 0; *nsl_out = 0; return 0; }
-  const uint64_t l = R.maxaepos;
-  const uint64_t W = win_count(l, P.a, P.w);
-  const uint32_t special0 = l >= P.w ? (uint32_t)(l - P.w) : 0, special1 = (uint32_t)l;
-  int nact = 0; uint64_t z = 0;
-  for (uint64_t y = 0; y < W; ++y) {
-    const uint64_t astart = win_start(y, l, P.a, P.w), aend = astart + P.w;
-    while (z < nintv && (int64_t)astart >= ovl[R.ovl_begin + z].abpos) {             // activation (:1904-1967)
-      const Ovl& o = ovl[R.ovl_begin + z];
-      if (o.aepos >= (int64_t)aend) {
-        double er = (double)o.diffs / (double)(o.aepos - o.abpos);
-        unsigned long long escore = (unsigned long long)(((er - minerate) / ediv) * 4294967295.0);
-        unsigned long long key = (escore << 32) | z;
-        if (nact >= cap) return 1;
-        int q = nact++;
-        while (q > 0 && act[q - 1] > key) { act[q] = act[q - 1]; --q; }
-        act[q] = key;
-      }
-      ++z;
-    }
-    { int q = 0;                                                                     // expiry (:1969-1977)
-      for (int t = 0; t < nact; ++t) { const Ovl& o = ovl[R.ovl_begin + (act[t] & 0xFFFFFFFFull)]; if (!((uint64_t)o.aepos < aend)) act[q++] = act[t]; }
-      nact = q; }
-    uint64_t MAo = 0; const uint32_t sbegin = ns;
-    for (int t = 0; t < nact; ++t) {                                                 // slices (:1984-2049)
-      const Ovl& o = ovl[R.ovl_begin + (act[t] & 0xFFFFFFFFull)];
-      if (!MAo) { if (fill) { sl[R.sl_off + ns].gpos = (uint32_t)(read_boff[aread] * 4 + astart); sl[R.sl_off + ns].len = (uint16_t)P.w; sl[R.sl_off + ns].flags = 0; } ++ns; ++MAo; }
-      if (MAo < P.maxalign) {
-        if (fill) {
-          uint32_t b0 = bm_lookup(o, P, bm, (uint32_t)astart, special0, special1), b1 = bm_lookup(o, P, bm, (uint32_t)aend, special0, special1);
-          uint32_t s = (uint32_t)o.bbpos + b0, len = b1 - b0, LB = read_len[o.bread];
-          bool comp = (o.flags & 1u) != 0;
-          uint64_t g = read_boff[o.bread] * 4 + (comp ? (uint64_t)(LB - s - len) : (uint64_t)s);
-          if (len > 255) return 1;
-          sl[R.sl_off + ns].gpos = (uint32_t)g; sl[R.sl_off + ns].len = (uint16_t)len; sl[R.sl_off + ns].flags = (uint16_t)(comp ? 1 : 0);
-        }
-        ++ns; ++MAo;
-      }
-    }
-    if (MAo) {
-      if (fill) { Win& wv = win[R.win_off + nw]; wv.slice_begin = (uint32_t)(R.sl_off + sbegin); wv.slice_cnt = (uint16_t)(MAo > 65535 ? 65535 : MAo); wv.reserved = 0; wv.aread = aread; wv.astart = (uint32_t)astart; }
-      ++nw;
-    }
+  for (uint64_t z = 0; z < nintv; ++z) {
+    const Ovl& o = ovl[R.ovl_begin + z];
+    double er = (double)o.diffs / (double)(o.aepos - o.abpos);
+    unsigned long long escore = (unsigned long long)(((er - minerate) / ediv) * 4294967295.0);
+    unsigned long long key = (escore << 32) | z;
+    uint64_t q = z;
+    while (q > 0 && keys[q - 1] > key) { keys[q] = keys[q - 1]; --q; }
+    keys[q] = key;
   }
-  *nwin_out = nw; *nsl_out = ns;
-  return 0;
+}
+// pile_window: candidate window y of read R (R.win_off = index of its candidate 0, R.nwin = number of candidates).
+// win == nullptr: returns the number of slices (0: empty pile, no window is emitted).  Otherwise writes the window
+// descriptor to *win and its slices to sl[0 .. n) with slice_begin = sl_index; returns n, or -1 if a slice exceeds 255 bases.
+PILE_FN int pile_window(const ReadInfo& R, uint32_t y, const Ovl* ovl, const Params& P, const uint32_t* bm, const uint64_t* read_boff, const uint32_t* read_len,
+                        const unsigned long long* keys, uint32_t aread, Win* win, Sl* sl, uint32_t sl_index) {
+  const uint64_t nintv = R.ovl_end - R.ovl_begin;
+  const uint64_t l = R.maxaepos;
+  const uint64_t astart = win_start(y, l, P.a, P.w), aend = astart + P.w;
+  const uint32_t special0 = l >= P.w ? (uint32_t)(l - P.w) : 0, special1 = (uint32_t)l;
+  uint64_t MAo = 0; int ns = 0;
+  for (uint64_t t = 0; t < nintv; ++t) {                                            // members in pile order (:1984-2049)
+    const Ovl& o = ovl[R.ovl_begin + (keys[t] & 0xFFFFFFFFull)];
+    if (!((int64_t)astart >= o.abpos && (uint64_t)o.aepos >= aend)) continue;
+    if (!MAo) { if (win) { sl[ns].gpos = (uint32_t)(read_boff[aread] * 4 + astart); sl[ns].len = (uint16_t)P.w; sl[ns].flags = 0; } ++ns; ++MAo; }
+    if (MAo < P.maxalign) {
+      if (win) {
+        uint32_t b0 = bm_lookup(o, P, bm, (uint32_t)astart, special0, special1), b1 = bm_lookup(o, P, bm, (uint32_t)aend, special0, special1);
+        uint32_t s = (uint32_t)o.bbpos + b0, len = b1 - b0, LB = read_len[o.bread];
+        bool comp = (o.flags & 1u) != 0;
+        uint64_t g = read_boff[o.bread] * 4 + (comp ? (uint64_t)(LB - s - len) : (uint64_t)s);
+        if (len > 255) return -1;
+        sl[ns].gpos = (uint32_t)g; sl[ns].len = (uint16_t)len; sl[ns].flags = (uint16_t)(comp ? 1 : 0);
+      }
+      ++ns; ++MAo;
+    } else break;                                                                   // the pile is full: later members add nothing
+  }
+  if (MAo && win) { win->slice_begin = sl_index; win->slice_cnt = (uint16_t)(MAo > 65535 ? 65535 : MAo); win->reserved = 0; win->aread = aread; win->astart = (uint32_t)astart; }
+  return ns;
 }
 
 }  // namespace dpile

@@ -13,7 +13,7 @@ namespace dpile {
 struct Prep {
   std::vector<Ovl> ovl; std::vector<ReadInfo> reads; std::vector<uint32_t> read_id;
   std::vector<double> minerate, ediv;
-  uint64_t ntiles = 0, nbm = 0;
+  uint64_t ntiles = 0, nbm = 0, ncand = 0;      // ncand: candidate windows of all reads
   std::string err;
 };
 
@@ -40,6 +40,8 @@ inline bool prepare(const dcu_overlap* in, uint64_t novl, uint64_t ntrace, int32
     if ((uint32_t)s.aepos > R.maxaepos) R.maxaepos = (uint32_t)s.aepos;
   }
   P.ntiles = toff; P.nbm = boff;
+  P.ncand = 0;
+  for (auto& R : P.reads) { R.win_off = P.ncand; R.nwin = (uint32_t)win_count(R.maxaepos, a, w); P.ncand += R.nwin; }
   P.minerate.resize(P.reads.size()); P.ediv.resize(P.reads.size());
   for (size_t r = 0; r < P.reads.size(); ++r) {       // HandleContext.hpp:1780-1790
     double mx = 0.0, mn = 1.0;

@@ -78,19 +78,27 @@ extern "C" int emu_pile(const dcu_overlap* ovl, uint64_t novl, const uint16_t* t
     for (uint64_t i = P.reads[r].ovl_begin; i < P.reads[r].ovl_end; ++i)
       for (int t = 0; t < P.ovl[i].ntiles; ++t) dpile::pile_align_tile(P.ovl[i], t, prm, trace, tile_b.data(), packed, read_boff, read_len, s0, s1, bm.data(), PV.data(), MV.data(), PH.data(), MH.data());
   }
-  std::vector<unsigned long long> act(novl + 1);
+  std::vector<unsigned long long> keys(novl + 1);
+  for (size_t r = 0; r < P.reads.size(); ++r) dpile::pile_order(P.reads[r], P.ovl.data(), P.minerate[r], P.ediv[r], keys.data() + P.reads[r].ovl_begin);
+  // pass 0: slices per candidate window; exclusive scans = what the block scans of the kernels produce
+  std::vector<uint32_t> cnt(P.ncand + 1, 0);
+  for (size_t r = 0; r < P.reads.size(); ++r)
+    for (uint32_t y = 0; y < P.reads[r].nwin; ++y)
+      cnt[P.reads[r].win_off + y] = (uint32_t)dpile::pile_window(P.reads[r], y, P.ovl.data(), prm, bm.data(), read_boff, read_len, keys.data() + P.reads[r].ovl_begin, P.read_id[r], nullptr, nullptr, 0);
   uint64_t tw = 0, ts = 0;
-  for (size_t r = 0; r < P.reads.size(); ++r) {
-    uint32_t nw = 0, ns = 0;
-    if (dpile::pile_read(P.reads[r], P.ovl.data(), prm, bm.data(), read_boff, read_len, P.minerate[r], P.ediv[r], false, nullptr, nullptr, &nw, &ns, act.data() + P.reads[r].ovl_begin, (int)(P.reads[r].ovl_end - P.reads[r].ovl_begin), P.read_id[r])) return 2;
-    P.reads[r].win_off = tw; P.reads[r].sl_off = ts; tw += nw; ts += ns;
-  }
+  for (uint64_t i = 0; i < P.ncand; ++i) { tw += cnt[i] ? 1 : 0; ts += cnt[i]; }
   *nwin = tw; *nsl = ts;
   if (tw > win_cap || ts > sl_cap) return 3;
-  for (size_t r = 0; r < P.reads.size(); ++r) {
-    uint32_t nw = 0, ns = 0;
-    if (dpile::pile_read(P.reads[r], P.ovl.data(), prm, bm.data(), read_boff, read_len, P.minerate[r], P.ediv[r], true, (dpile::Win*)win_out, (dpile::Sl*)sl_out, &nw, &ns, act.data() + P.reads[r].ovl_begin, (int)(P.reads[r].ovl_end - P.reads[r].ovl_begin), P.read_id[r])) return 2;
-  }
+  uint64_t wo = 0, so = 0;
+  for (size_t r = 0; r < P.reads.size(); ++r)
+    for (uint32_t y = 0; y < P.reads[r].nwin; ++y) {
+      const uint32_t n = cnt[P.reads[r].win_off + y];
+      if (!n) continue;
+      int rc = dpile::pile_window(P.reads[r], y, P.ovl.data(), prm, bm.data(), read_boff, read_len, keys.data() + P.reads[r].ovl_begin, P.read_id[r],
+                                  (dpile::Win*)win_out + wo, (dpile::Sl*)sl_out + so, (uint32_t)so);
+      if (rc != (int)n) return 2;
+      ++wo; so += n;
+    }
   return 0;
 }
 
