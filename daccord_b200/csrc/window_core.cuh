@@ -27,6 +27,13 @@
 #include <stdint.h>
 #include <float.h>
 #include <stddef.h>
+#if defined(DCU_EMU) && defined(DCU_EMU_STATS)
+// footprint study (tests/emu with -DDCU_EMU_STATS): per-window peaks of the workspace counters, read by tools/footprint.py
+static long g_peak[16];
+#define DCU_PEAK(i, v) do { if ((long)(v) > g_peak[i]) g_peak[i] = (long)(v); } while (0)
+#else
+#define DCU_PEAK(i, v) do { } while (0)
+#endif
 
 #ifdef DCU_EMU
 #define DCU_FN static inline
@@ -275,6 +282,7 @@ DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
   }
   c.nbases = bcast(c.nbases, 0);
   wsync();
+  DCU_PEAK(0, c.MAo); DCU_PEAK(1, c.nbases);
   if (c.nbases > DCU_CAP.B || c.nbases > 65000) { c.overflow = 2; return; }
   DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
@@ -453,6 +461,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   const WS& w = c.ws;
   int nn = 0;
   const int nocc = (int)w.hstate()[0];
+  DCU_PEAK(14, nocc);
   DCU_NOUNROLL
   for (int base = 0; base < nocc; base += DCU_NL) {
     int t = base + lane;
@@ -466,6 +475,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
     } else if (t < nocc) w.hs()[2 * i + 1] = (uint32_t)cnt | 0xFFFF0000u;
     nn += popc(b);
   }
+  DCU_PEAK(2, nn);
   if (nn > DCU_CAP.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
   // graphs this large (the filterfreq-1 fall-through) take ~50 ms on one warp: in the phase-synchronous pass they would
   // hold their whole warp group, so they are handed to the free-running large-workspace pass instead
@@ -475,6 +485,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   if (lane == 0) { uint32_t o = 0; for (int n = 0; n < nn; ++n) { w.n_ioff()[n] = o; o += w.n_freq()[n]; } c.ni = (int)o; }
   c.ni = bcast(c.ni, 0);
   wsync();
+  DCU_PEAK(3, c.ni);
   if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
   {
     const int nraw = (int)w.koff()[c.MAo];
@@ -650,6 +661,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   wsync();
   int nex = (int)bcast(*nexp, 0);
   wsync();
+  DCU_PEAK(4, nex);
   if (nex > DCU_CAP.EX) { c.overflow = 6; c.nex = 0; return; }
   c.nex = nex;
   DCU_NOUNROLL
@@ -856,6 +868,7 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
     run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
   }
   wsync();
+  DCU_PEAK(6, run0 > run1 ? run0 : run1);
   if ((int)run0 > DCU_CAP.SF || (int)run1 > DCU_CAP.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
   // per stretch, lanes over anchor positions; the link weights are evaluated on the fly from the instance lists
   // (all lanes share the node, so instance positions are uniform loads and only the table column differs per lane)
@@ -943,6 +956,7 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
   wsync();
   int nrl = (int)bcast(*cnt, 0);
   wsync();
+  DCU_PEAK(7, nrl);
   if (nrl > DCU_CAP.RL) { c.overflow = 10; return; }
   c.nrl = nrl;
   int P = 32; while (P < nrl) P <<= 1;
@@ -994,6 +1008,7 @@ struct TravOut { int nacc; };
 
 DCU_NOINL int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front, int stretch, int pos, int len, int baselen) {
   const WS& w = c.ws;
+  DCU_PEAK(8, nrp + 1);
   if (nrp >= DCU_CAP.RP) { c.overflow = 11; return -1; }
   int id = nrp++;
   w.rp_w()[id] = wgt; w.rp_parent()[id] = parent; w.rp_front()[id] = front; w.rp_stretch()[id] = (uint16_t)stretch;
@@ -1114,6 +1129,7 @@ DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath 
   double wt; int bl;
   if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sf_w()[o] : 0.0; }
   else { bl = w.fp_baselen()[P] + L - 1; wt = w.fp_w()[P]; if (o >= 0) wt += w.sf_w()[o] - fwd_wf(c, s, ppos); }
+  DCU_PEAK(10, nfp + 1);
   if (nfp >= DCU_CAP.FP) { c.overflow = 14; return -1; }
   int id = nfp++;
   w.fp_w()[id] = wt; w.fp_parent()[id] = P < 0 ? IDX_NONE : (uint32_t)P; w.fp_stretch()[id] = (uint16_t)s;
@@ -1175,6 +1191,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
       }
       if (left >= 0) {
         int cur = interval_next(c, left, right, -1);
+        DCU_PEAK(11, nsi + 1);
         if (nsi >= DCU_CAP.SI || nsq >= DCU_CAP.SI) { c.overflow = 15; return; }
         int rec = nsi++;
         w.si_left()[rec] = (uint16_t)left; w.si_right()[rec] = (uint16_t)right; w.si_cur()[rec] = (uint16_t)cur; w.si_path()[rec] = (uint32_t)P;
@@ -1274,6 +1291,7 @@ DCU_BIG void trav_pair_graph(Ctx& c, TravState& t, int lane) {
   g_stats[0]++;
 #endif
   derive_stretches(c, t.F, t.L, lane);
+  DCU_PEAK(5, c.nds); DCU_PEAK(12, c.nrs); DCU_PEAK(13, c.slO);
 }
 DCU_BIG void trav_pair_weights(Ctx& c, int lane) {
   stretch_positions(c, lane);

@@ -8,6 +8,7 @@
 #include "../../include/daccord_b200.h"
 #include <vector>
 #include <cstring>
+#include <cstdio>
 #include <cstdlib>
 
 extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
@@ -37,7 +38,17 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
     dcu::Result r;
     dcu::Window W; memcpy(&W, &win[i], sizeof(W));
     memset(cons + i * DCU_CONS_STRIDE, 0, DCU_CONS_STRIDE); memset(ops + i * DCU_OPS_STRIDE, 0, DCU_OPS_STRIDE);
+#ifdef DCU_EMU_STATS
+    for (int q = 0; q < 16; ++q) g_peak[q] = 0;
+#endif
     dcu::process_window(c, W, r, cons + i * DCU_CONS_STRIDE, ops + i * DCU_OPS_STRIDE, 0);
+#ifdef DCU_EMU_STATS
+    if (const char* fn = getenv("DCU_FOOTPRINT_OUT")) {      // per-window peaks of the workspace counters (tools/footprint.py)
+      static FILE* fp = nullptr;
+      if (!fp) fp = fopen(fn, "w");
+      if (fp) { for (int q = 0; q < 15; ++q) fprintf(fp, "%ld%c", g_peak[q], q == 14 ? '\n' : ' '); fflush(fp); }
+    }
+#endif
     memcpy(&res[i], &r, sizeof(r));
     if (r.status == dcu::ST_OVERFLOW) ++nov;
   }
