@@ -16,6 +16,7 @@
 #include <omp.h>
 #endif
 #include "las.hpp"
+#include "las_index.hpp"
 #include "dazzdb.hpp"
 #include "pile.hpp"
 #include "vote.hpp"
@@ -84,10 +85,12 @@ int main(int argc, char** argv) {
   try {
     PackedDB db; LasData las;
     fprintf(stderr, "[V] loading %s ...", dbfn.c_str()); read_dazzdb(dbfn, db); fprintf(stderr, "done.\n");
-    fprintf(stderr, "[V] loading %s ...", lasfn.c_str()); read_las(lasfn, las); las.build_index(db.rlen.size()); fprintf(stderr, "done.\n");
+    // LAS: index of record offsets per A-read (cached as <las>.dcuidx; reference src/daccord.cpp:1075-1104), then only the shard's byte range
+    LasIndex lidx; bool built = false;
+    fprintf(stderr, "[V] indexing %s ...", lasfn.c_str()); get_las_index(lasfn, lidx, &built); fprintf(stderr, "%s.\n", built ? "done" : "cached");
     // read range: -J i,j or -I i,j (inclusive) (reference src/daccord.cpp:1116-1227)
     int64_t minaread = 0, maxaread = (int64_t)db.rlen.size() - 1;
-    if (!las.ovl.empty()) { minaread = las.ovl.front().aread; maxaread = las.ovl.back().aread; } else maxaread = -1;
+    if (lidx.maxaread >= lidx.minaread) { minaread = lidx.minaread; maxaread = lidx.maxaread; } else maxaread = -1;
     if (A.opt.count("J")) {
       int64_t Icnt, Idiv; if (!parse_pair(A.opt["J"], Icnt, Idiv)) { fprintf(stderr, "[E] unable to parse %s\n", A.opt["J"].c_str()); return EXIT_FAILURE; }
       int64_t top = maxaread + 1, span = top > minaread ? top - minaread : 0;
@@ -99,6 +102,8 @@ int main(int argc, char** argv) {
     }
     const int64_t toparead = maxaread >= 0 ? maxaread + 1 : maxaread;
     fprintf(stderr, "[V] minaread=%ld toparead=%ld\n", (long)minaread, (long)toparead);
+    fprintf(stderr, "[V] loading %s ...", lasfn.c_str()); read_las_range(lasfn, lidx, minaread, toparead, las, nthreads); las.build_index(db.rlen.size());
+    fprintf(stderr, "done (%zu of %ld overlaps).\n", las.ovl.size(), (long)lidx.novl);
     fprintf(stderr, "[V] minfilterfreq=%d maxfilterfreq=%d\n", prm.min_ff, prm.max_ff);
     // error profile: <las>.eprof or -E; estimated from the first <= 1024 A-reads when the file does not exist
     // (reference src/daccord.cpp:1652-1880).  Text form: "matches mismatches insertions deletions" [newline "eavg edif"]

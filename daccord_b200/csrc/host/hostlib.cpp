@@ -12,6 +12,7 @@
 #include "synth.hpp"
 #include "simlas.hpp"
 #include "las.hpp"
+#include "las_index.hpp"
 #include "dazzdb.hpp"
 #include "pile.hpp"
 #include "vote.hpp"
@@ -52,6 +53,18 @@ dh_data* dh_sim_create(uint64_t genome_len, uint64_t read_len, double coverage, 
 dh_data* dh_data_load(const char* lasfn, const char* dbfn) {
   std::unique_ptr<dh_data> D(new dh_data());
   try { read_dazzdb(dbfn, D->db); read_las(lasfn, D->las); D->las.build_index(D->db.rlen.size()); } catch (std::exception& e) { fprintf(stderr, "[E] %s\n", e.what()); return nullptr; }
+  return D.release();
+}
+// the overlaps of A-reads [first_read, last_read) only, through the offset index (las_index.hpp); out3 = A-read range of the file and its overlap count
+dh_data* dh_data_load_range(const char* lasfn, const char* dbfn, int64_t first_read, int64_t last_read, int nthreads, int64_t* out3) {
+  std::unique_ptr<dh_data> D(new dh_data());
+  try {
+    read_dazzdb(dbfn, D->db);
+    LasIndex I; get_las_index(lasfn, I);
+    if (out3) { out3[0] = I.minaread; out3[1] = I.maxaread; out3[2] = I.novl; }
+    read_las_range(lasfn, I, first_read, last_read, D->las, nthreads);
+    D->las.build_index(D->db.rlen.size());
+  } catch (std::exception& e) { fprintf(stderr, "[E] %s\n", e.what()); return nullptr; }
   return D.release();
 }
 void dh_data_destroy(dh_data* d) { delete d; }

@@ -18,7 +18,7 @@ def lib():
         if not os.path.exists(HOST_LIB_PATH):
             raise DcuError("host library %s not built: run `python -m daccord_b200.build`" % HOST_LIB_PATH)
         L = C.CDLL(HOST_LIB_PATH)
-        for f in ("dh_sim_create", "dh_data_load", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first",
+        for f in ("dh_sim_create", "dh_data_load", "dh_data_load_range", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first",
                   "dh_select_overlaps", "dh_ovlset_data", "dh_data_trace", "dh_data_boff", "dh_data_rlen", "dh_format_segments"):
             getattr(L, f).restype = C.c_void_p
         for f in ("dh_data_nreads", "dh_data_novl", "dh_data_totlen"):
@@ -45,6 +45,14 @@ class Dataset:
     @staticmethod
     def load(las, db):
         return Dataset(lib().dh_data_load(las.encode(), db.encode()))
+
+    @staticmethod
+    def load_range(las, db, first, last, nthreads=0):
+        """only the overlaps of A-reads [first, last), through the record-offset index (built and cached as <las>.dcuidx on first use)"""
+        out = (C.c_int64 * 3)()
+        ds = Dataset(lib().dh_data_load_range(las.encode(), db.encode(), C.c_int64(first), C.c_int64(last), C.c_int(nthreads or (os.cpu_count() or 1)), out))
+        ds.file_range = (int(out[0]), int(out[1]), int(out[2]))
+        return ds
 
     def write(self, las, db):
         if lib().dh_data_write(self.h, las.encode(), db.encode()):
