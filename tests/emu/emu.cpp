@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 
 extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
                              dcu_result* res, uint8_t* cons, uint8_t* ops, int tier, uint64_t* noverflow) {
@@ -40,9 +41,11 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
     memset(cons + i * DCU_CONS_STRIDE, 0, DCU_CONS_STRIDE); memset(ops + i * DCU_OPS_STRIDE, 0, DCU_OPS_STRIDE);
 #ifdef DCU_EMU_STATS
     for (int q = 0; q < 16; ++q) g_peak[q] = 0;
+    const auto t0 = std::chrono::steady_clock::now();
 #endif
     dcu::process_window(c, W, r, cons + i * DCU_CONS_STRIDE, ops + i * DCU_OPS_STRIDE, 0);
 #ifdef DCU_EMU_STATS
+    g_peak[9] = (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();    // single-lane emulation time of the window
     if (const char* fn = getenv("DCU_FOOTPRINT_OUT")) {      // per-window peaks of the workspace counters (tools/footprint.py)
       static FILE* fp = nullptr;
       if (!fp) fp = fopen(fn, "w");

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from common import default_params, alloc_out, _ptr   # noqa: E402
 from daccord_b200.host import Dataset               # noqa: E402
 
-NAMES = ["slices", "bases", "nodes", "instances", "gapfill_extras", "unitigs", "unitig_positions", "reverse_links", "reverse_paths", "-", "forward_paths",
+NAMES = ["slices", "bases", "nodes", "instances", "gapfill_extras", "unitigs", "unitig_positions", "reverse_links", "reverse_paths", "emulation_ns", "forward_paths",
          "score_intervals", "raw_unitigs", "unitig_link_symbols", "distinct_kmers"]
 
 
@@ -41,16 +41,19 @@ def main():
     print("windows %d (coverage %.0f), consensus %d, overflow %d" % (len(win), cov, int((res["status"] == 1).sum()), nov.value))
     print("%-22s %8s %8s %8s %8s %8s" % ("counter", "median", "p90", "p99", "p99.9", "max"))
     for i, n in enumerate(NAMES):
-        if n == "-":
-            continue
         c = a[:, i]
         print("%-22s %8d %8d %8d %8d %8d" % (n, np.median(c), np.percentile(c, 90), np.percentile(c, 99), np.percentile(c, 99.9), c.max()))
     # bytes of a compact layout: hash 8 B / slot at load <= 0.5, instances 2 x 1 B + 4 B slot, nodes ~40 B, unitig positions 3 doubles, paths ~32 B
     def layout(ix):
-        v = {n: np.percentile(a[:, i], ix) for i, n in enumerate(NAMES) if n != "-"}
+        v = {n: np.percentile(a[:, i], ix) for i, n in enumerate(NAMES)}
         hs = 2 ** int(np.ceil(np.log2(max(2 * v["distinct_kmers"], 64))))
         return (v["bases"] + 8 * hs + 6 * v["instances"] + 40 * v["nodes"] + 3 * v["unitig_link_symbols"] + 24 * v["unitigs"] + 24 * v["unitig_positions"] +
                 4 * v["reverse_links"] + 36 * v["reverse_paths"] + 28 * v["forward_paths"] + 26 * v["score_intervals"] + 4096)
+    # imbalance of the phase-synchronous groups: consecutive windows share a group of 16 warps; a group advances at the pace of its slowest member
+    t = a[:, 9].astype(np.float64)
+    g = t[: len(t) // 16 * 16].reshape(-1, 16)
+    print("single-lane emulation time per window: median %.0f us, p99 %.0f us, max %.0f us; sum over groups of 16 of (16 x max) / sum = %.2f" %
+          (np.median(t) / 1e3, np.percentile(t, 99) / 1e3, t.max() / 1e3, 16 * g.max(axis=1).sum() / g.sum()))
     print("compact workspace bytes: median %.0f KB, p90 %.0f KB, p99 %.0f KB, p99.9 %.0f KB" % tuple(layout(q) / 1024 for q in (50, 90, 99, 99.9)))
 
 
