@@ -116,6 +116,7 @@ struct Tables {
 struct Params {
   int w, k_lo, k_hi, minff, maxff, mincov, check;   // check = (est_cor != 0)  (DebruijnGraph.hpp:1832-1837)
   unsigned long long eminrate;
+  int defer_ff;                                      // experimental (DCU_DEFER_FF, first pass only): hand windows whose first filter frequency fails to the second pass
 };
 // capacities of one warp's workspace (two tiers: small for the common case, large for the rest)
 struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, STP, SL, SF, RL, RLP, RP, FP, SI, BL, KW, HEAVY; };
@@ -1465,7 +1466,14 @@ DCU_BIG void st_edges(Ctx& c, WinState& s, int lane) {
 DCU_FN void st_after_tries(WinState& s, bool lconsok) {
   bool nextk = lconsok;
   if (lconsok) s.pathfailed = false;
-  else { s.ff -= 1; if (s.ff >= DCU_P.minff) { s.ph = PH_NODES; return; } nextk = true; }
+  else {
+    s.ff -= 1;
+    if (s.ff >= DCU_P.minff) {
+      if (DCU_P.defer_ff) { s.res.status = ST_OVERFLOW; s.res.err = 22; s.ph = PH_END; return; }     // slow path ahead: not in a synchronous group
+      s.ph = PH_NODES; return;
+    }
+    nextk = true;
+  }
   if (nextk) { s.k += 1; s.ph = (s.k <= DCU_P.k_hi) ? PH_HASH : PH_FINAL; }
 }
 // PH_TRAV: starts a traverse if none is running and derives the unitigs of the next (first,last) pair; PH_POS: their position
