@@ -416,12 +416,18 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
   CK(cudaSetDevice(ctx->device));
   dpile::Prep P;
   if (!dpile::prepare(ovl, novl, ntrace, tspace, ctx->prm.w, advance, nreads, read_len, P)) { ctx->err = P.err; return DCU_ERR_UNSUPPORTED; }
-  for (uint64_t i = 0; i < novl; ++i) {          // every B block must lie inside its read and fit the tile aligner
-    uint64_t b = (uint64_t)ovl[i].bbpos;
-    for (int32_t t = 1; t < ovl[i].tlen; t += 2) { uint16_t bl = trace[ovl[i].trace_off + t]; if (bl > dpile::PILE_MAXB) { ctx->err = "trace block longer than 256"; return DCU_ERR_UNSUPPORTED; } b += bl; }
-    if (b > read_len[ovl[i].bread]) { ctx->err = "trace points run past the B read"; return DCU_ERR_PARAM; }
-    if ((read_boff[ovl[i].bread] + (read_len[ovl[i].bread] + 3) / 4) > ctx->packed_bytes) { ctx->err = "read outside the packed database"; return DCU_ERR_PARAM; }
+  int bad = 0;                                   // every B block must lie inside its read and fit the tile aligner
+#pragma omp parallel for schedule(static) reduction(max : bad)
+  for (int64_t i = 0; i < (int64_t)novl; ++i) {
+    uint64_t b = (uint64_t)ovl[i].bbpos; int e = 0;
+    for (int32_t t = 1; t < ovl[i].tlen; t += 2) { uint16_t bl = trace[ovl[i].trace_off + t]; if (bl > dpile::PILE_MAXB) e = 3; b += bl; }
+    if (b > read_len[ovl[i].bread]) e = std::max(e, 2);
+    if ((read_boff[ovl[i].bread] + (read_len[ovl[i].bread] + 3) / 4) > ctx->packed_bytes) e = std::max(e, 1);
+    bad = std::max(bad, e);
   }
+  if (bad == 3) { ctx->err = "trace block longer than 256"; return DCU_ERR_UNSUPPORTED; }
+  if (bad == 2) { ctx->err = "trace points run past the B read"; return DCU_ERR_PARAM; }
+  if (bad == 1) { ctx->err = "read outside the packed database"; return DCU_ERR_PARAM; }
   const uint64_t nr = P.reads.size();
   dpile::Params prm; prm.tspace = tspace; prm.w = ctx->prm.w; prm.a = advance; prm.maxalign = maxalign;
   CK(ctx->dpo.ensure(novl + 1)); CK(ctx->dpr.ensure(nr + 1)); CK(ctx->dprid.ensure(nr + 1)); CK(ctx->dptile.ensure(P.ntiles + 1)); CK(ctx->dpbm.ensure(P.nbm + 1));
