@@ -28,6 +28,7 @@
 #include <float.h>
 #include <stddef.h>
 #if defined(DCU_EMU) && defined(DCU_EMU_STATS)
+#include <chrono>
 // footprint study (tests/emu with -DDCU_EMU_STATS): per-window peaks of the workspace counters, read by tools/footprint.py
 static long g_peak[16];
 #define DCU_PEAK(i, v) do { if ((long)(v) > g_peak[i]) g_peak[i] = (long)(v); } while (0)
@@ -1546,10 +1547,22 @@ DCU_BIG void st_final(Ctx& c, WinState& s, uint8_t* cons_out, uint8_t* ops_out, 
   res.err = (uint32_t)s.minrate; res.nops = (uint16_t)nops; res.ncand = (uint16_t)s.bestn;
 }
 
+#if defined(DCU_EMU) && defined(DCU_EMU_STATS)
+// footprint study: emulation time per phase of the current window (g_phase_ns[phase], phase call counts in g_phase_calls)
+static long g_phase_ns[16], g_phase_calls[16];
+struct PhaseTimer {
+  int ph; std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(int p) : ph(p), t0(std::chrono::steady_clock::now()) {}
+  ~PhaseTimer() { g_phase_ns[ph] += (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); g_phase_calls[ph]++; }
+};
+#endif
 DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons_out, uint8_t* ops_out, int lane) {
   WinState s;
   st_begin(c, s, win, lane);
   while (s.ph != PH_END) {
+#if defined(DCU_EMU) && defined(DCU_EMU_STATS)
+    PhaseTimer pt_(s.ph);
+#endif
     if (s.ph == PH_HASH) st_hash(c, s, lane);
     else if (s.ph == PH_NODES) st_nodes(c, s, lane);
     else if (s.ph == PH_EDGES) st_edges(c, s, lane);

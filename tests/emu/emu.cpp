@@ -41,7 +41,7 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
     dcu::Window W; memcpy(&W, &win[i], sizeof(W));
     memset(cons + i * DCU_CONS_STRIDE, 0, DCU_CONS_STRIDE); memset(ops + i * DCU_OPS_STRIDE, 0, DCU_OPS_STRIDE);
 #ifdef DCU_EMU_STATS
-    for (int q = 0; q < 16; ++q) g_peak[q] = 0;
+    for (int q = 0; q < 16; ++q) { g_peak[q] = 0; dcu::g_phase_ns[q] = 0; dcu::g_phase_calls[q] = 0; }
     const auto t0 = std::chrono::steady_clock::now();
 #endif
     dcu::process_window(c, W, r, cons + i * DCU_CONS_STRIDE, ops + i * DCU_OPS_STRIDE, 0);
@@ -50,7 +50,7 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
     if (const char* fn = getenv("DCU_FOOTPRINT_OUT")) {      // per-window peaks of the workspace counters (tools/footprint.py)
       static FILE* fp = nullptr;
       if (!fp) fp = fopen(fn, "w");
-      if (fp) { for (int q = 0; q < 15; ++q) fprintf(fp, "%ld%c", g_peak[q], q == 14 ? '\n' : ' '); fflush(fp); }
+      if (fp) { for (int q = 0; q < 15; ++q) fprintf(fp, "%ld ", g_peak[q]); for (int q = 0; q < 11; ++q) fprintf(fp, "%ld %ld%c", dcu::g_phase_ns[q], dcu::g_phase_calls[q], q == 10 ? '\n' : ' '); fflush(fp); }
     }
 #endif
     memcpy(&res[i], &r, sizeof(r));
