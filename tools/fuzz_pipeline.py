@@ -58,6 +58,11 @@ def main():
             seg, chars = emu_vote(win, r[0], r[1], r[2], w, full, minlen, packed, boff, rlen)
             got = format_segments(seg, chars)[0]
             ok = got == want
+            # error-profile estimation: oracle restatement vs the product's host implementation on the same files
+            out = (C.c_uint64 * 7)(); dd = (C.c_double * 2)()
+            assert lib.oracle_estimate_profile(las.encode(), db.encode(), C.c_int64(0), C.c_int64(-1), C.c_uint64(d), C.c_uint64(D), out, dd) == 0
+            g = ds.estimate_profile(0, None, d, D, 4)
+            ok = ok and [g[x] for x in ("matches", "mismatches", "insertions", "deletions", "usable", "unusable", "reads")] == [int(x) for x in out]
             nb += 1; nbad += (not ok)
             print("seed %d w %d a %d k %d reads %d x %d cov %.0f err %.2f tspace %d -d %s -D %d -f %d -l %d windows %d fasta %d %s" % (
                 seed, w, a, k, ds.nreads, rl, cov, e, ds.tspace, "inf" if d > 10**9 else d, D, full, minlen, len(win), len(want), "OK" if ok else "MISMATCH"), flush=True)
