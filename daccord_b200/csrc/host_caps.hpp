@@ -20,7 +20,7 @@ inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
     c.NN = 4096; c.ST = 1024; c.SL = 8192; c.SF = 16384; c.RL = 2048; c.RP = 2048; c.FP = 2048; c.SI = 2048; c.KW = 2; c.HEAVY = 0;       // HEAVY > 0 hands graphs with more nodes to the free-running pass (measured: no gain, profiles/r01_summary.md)
   } else {
     c.NN = c.NI + c.EX; if (c.NN > 65000) c.NN = 65000;
-    c.ST = 8192; c.SL = 65000; c.SF = 65000; c.RL = 32768; c.RP = 32768; c.FP = 32768; c.SI = 32768; c.KW = 2;
+    c.ST = 8192; c.SL = 65000; c.SF = 262144; c.RL = 32768; c.RP = 32768; c.FP = 32768; c.SI = 32768; c.KW = 2;
   }
   if (c.NN > c.NI + c.EX) c.NN = c.NI + c.EX;
   c.STP = 1 << ceil_pow2_log(c.ST);

@@ -145,7 +145,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(ll_kmer, uint32_t, c.S) X(ll_cnt, uint16_t, c.S) X(fl_kmer, uint32_t, c.S) X(fl_cnt, uint16_t, c.S)    \
   X(fl_nid, uint16_t, c.S)                                                                                 \
   X(slinks, uint16_t, c.SL) X(slsym, uint8_t, c.SL) X(rs_off, uint16_t, c.ST) X(rs_len, uint16_t, c.ST)    \
-  X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint16_t, c.ST) X(ds_cO, uint16_t, c.ST)    \
+  X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint32_t, c.ST) X(ds_cO, uint32_t, c.ST)    \
   X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST) X(du_off, uint16_t, c.ST) X(du_len, uint16_t, c.ST)  \
   X(ds_rlO, uint16_t, c.ST) X(ds_rlN, uint16_t, c.ST)                                                      \
   X(ds_fB, uint8_t, c.ST) X(ds_fN, uint8_t, c.ST) X(ds_cB, uint8_t, c.ST) X(ds_cN, uint8_t, c.ST)          \
@@ -866,12 +866,12 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
       w.ds_fB()[s] = w.n_pf()[n0]; w.ds_fN()[s] = (uint8_t)a; w.ds_cB()[s] = w.n_cpf()[n1]; w.ds_cN()[s] = (uint8_t)b;
     }
     uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
-    if (s < c.nds) { uint32_t oa = run0 + ia - a, ob = run1 + ib - b; w.ds_fO()[s] = (uint16_t)(oa > 65535u ? 65535u : oa); w.ds_cO()[s] = (uint16_t)(ob > 65535u ? 65535u : ob); }
+    if (s < c.nds) { uint32_t oa = run0 + ia - a, ob = run1 + ib - b; w.ds_fO()[s] = oa; w.ds_cO()[s] = ob; }
     run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
   }
   wsync();
   DCU_PEAK(6, run0 > run1 ? run0 : run1);
-  if ((int)run0 > DCU_CAP.SF || (int)run1 > DCU_CAP.SF || run0 > 65535u || run1 > 65535u) { c.overflow = 9; return; }
+  if (run0 > (uint32_t)DCU_CAP.SF || run1 > (uint32_t)DCU_CAP.SF) { c.overflow = 9; return; }
   // per stretch, lanes over anchor positions; the link weights are evaluated on the fly from the instance lists
   // (all lanes share the node, so instance positions are uniform loads and only the table column differs per lane)
   const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
