@@ -21,8 +21,8 @@
 // procedure for every weight heap.
 //
 // The file is compiled twice: by nvcc for sm_100a (32 lanes, product) and, for tests only, by
-// g++ with -DDCU_EMU as a single-lane host emulation (tests/emu) so that parity against the
-// oracle can be debugged without a GPU.  The product library contains only the CUDA build.
+// g++ with -DDCU_EMU as a host emulation (tests/emu: single lane, or 32 lanes as cooperative fibers
+// with -DDCU_EMU_LANES) so that parity against the oracle can be debugged without a GPU.  The product library contains only the CUDA build.
 #pragma once
 #include <stdint.h>
 #include <float.h>
@@ -43,6 +43,7 @@ static long g_peak[16];
 #define DCU_NOUNROLL
 #define DCU_NOINL static inline
 #define DCU_CTOR
+#ifndef DCU_EMU_LANES
 #define DCU_NL 1
 namespace dcu {
 static inline void wsync() {}
@@ -60,6 +61,46 @@ static inline void red_argmax_d(double&, int&) {}
 static inline uint32_t scan_incl(uint32_t v, int) { return v; }
 template <class T> static inline T ldg(const T* p) { return *p; }
 }
+#else
+// 32-lane emulation (tests/emu/emu_lanes.cpp): every lane of the warp is a cooperative fiber running this very code with
+// its own registers (Ctx, WinState); a warp collective or __syncwarp is the only place where fibers switch, and the
+// harness picks the order in which the lanes run between two such points (ascending, descending, shuffled).  A result that
+// depends on that order is a missing wsync() in the code below; lanes that do not reach the same collectives deadlock,
+// which the harness reports.  emu_xchg deposits one 64-bit word per lane and returns all 32 once every lane has arrived.
+#include <string.h>
+#define DCU_NL 32
+namespace dcu {
+const unsigned long long* emu_xchg(unsigned long long v);
+extern int emu_skip_sync_line;       // mutation testing of the harness itself (tools/lane_mutants.py): the wsync() of this source line is dropped
+static inline void wsync_line(int line) { if (line != emu_skip_sync_line) emu_xchg(0); }
+#define wsync() wsync_line(__LINE__)
+static inline uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }   // fibers are not preempted
+static inline uint32_t a_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t ballot(bool p) { const unsigned long long* x = emu_xchg(p ? 1 : 0); uint32_t m = 0; for (int i = 0; i < 32; ++i) if (x[i]) m |= 1u << i; return m; }
+static inline uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
+static inline int popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int popcll(uint64_t x) { return __builtin_popcountll(x); }
+template <class T> static inline T bcast(T v, int src) {
+  static_assert(sizeof(T) <= 8, "bcast word");
+  unsigned long long u = 0; memcpy(&u, &v, sizeof(T));
+  const unsigned long long* x = emu_xchg(u);
+  T r; memcpy(&r, &x[src & 31], sizeof(T)); return r;
+}
+static inline uint32_t red_max_u32(uint32_t v) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0; for (int i = 0; i < 32; ++i) if ((uint32_t)x[i] > r) r = (uint32_t)x[i]; return r; }
+static inline uint32_t red_min_u32(uint32_t v) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0xFFFFFFFFu; for (int i = 0; i < 32; ++i) if ((uint32_t)x[i] < r) r = (uint32_t)x[i]; return r; }
+static inline uint32_t red_sum_u32(uint32_t v) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0; for (int i = 0; i < 32; ++i) r += (uint32_t)x[i]; return r; }
+static inline void red_argmax_d(double& v, int& i) {      // larger value wins, ties -> smaller index (same as the butterfly of the CUDA build)
+  double vs[32]; int is[32];
+  { unsigned long long u; memcpy(&u, &v, 8); const unsigned long long* x = emu_xchg(u); memcpy(vs, x, sizeof(vs)); }
+  { const unsigned long long* x = emu_xchg((unsigned long long)(long long)i); for (int q = 0; q < 32; ++q) is[q] = (int)(long long)x[q]; }
+  double bv = vs[0]; int bi = is[0];
+  for (int q = 1; q < 32; ++q) if (vs[q] > bv || (vs[q] == bv && is[q] < bi)) { bv = vs[q]; bi = is[q]; }
+  v = bv; i = bi;
+}
+static inline uint32_t scan_incl(uint32_t v, int lane) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0; for (int i = 0; i <= lane; ++i) r += (uint32_t)x[i]; return r; }
+template <class T> static inline T ldg(const T* p) { return *p; }
+}
+#endif
 #else
 #define DCU_FN __device__ __forceinline__
 #define DCU_BIG __device__ __noinline__

@@ -48,6 +48,16 @@ def build_emu():
     return out
 
 
+def build_emu_lanes():
+    out = os.path.join(ROOT, "tests", "emu", "_build", "libemu_lanes.so")
+    src = os.path.join(ROOT, "tests", "emu", "emu_lanes.cpp")
+    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "host_tables.hpp", "host_caps.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src])
+    return out
+
+
 _libs = {}
 
 
@@ -85,6 +95,19 @@ def run_emu(params, packed, win, sl, tier=0):
     rc = emu_lib().emu_run_batch(C.byref(params), _ptr(packed), _ptr(win), C.c_uint64(len(win)), _ptr(sl), _ptr(res), _ptr(cons), _ptr(ops), C.c_int(tier), C.byref(nov))
     assert rc == 0
     return res, cons, ops, nov.value
+
+
+def run_emu_lanes(params, packed, win, sl, tier=0, schedule=0, seed=1):
+    """window_core.cuh as 32 cooperative fibers per warp (tests/emu/emu_lanes.cpp); schedule 0 ascending, 1 descending, >= 2 shuffled.
+    Returns (res, cons, ops, overflows, collectives); raises on a lane deadlock or on lanes that disagree about the result record."""
+    if "l" not in _libs:
+        _libs["l"] = C.CDLL(build_emu_lanes())
+    res, cons, ops = alloc_out(len(win))
+    nov, ncoll = C.c_uint64(0), C.c_uint64(0)
+    rc = _libs["l"].emu_lanes_run_batch(C.byref(params), _ptr(packed), _ptr(win), C.c_uint64(len(win)), _ptr(sl), _ptr(res), _ptr(cons), _ptr(ops), C.c_int(tier), C.byref(nov),
+                                        C.c_int(schedule), C.c_uint64(seed), C.byref(ncoll))
+    assert rc == 0, "lane emulation: %s" % {101: "deadlock (lanes diverged around a warp collective)", 102: "lanes disagree on the result record"}.get(rc, rc)
+    return res, cons, ops, nov.value, ncoll.value
 
 
 def emu_vote(win, res, cons, ops, w, producefull, minlen, packed, boff, rlen):

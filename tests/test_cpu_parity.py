@@ -6,7 +6,7 @@ import re
 import subprocess
 import numpy as np
 import pytest
-from common import (ROOT, default_params, synth_batch, run_oracle, run_emu, compare_results, get_tables, oracle_lib, emu_lib,
+from common import (ROOT, default_params, synth_batch, run_oracle, run_emu, run_emu_lanes, compare_results, get_tables, oracle_lib, emu_lib,
                     CONS_STRIDE)
 
 
@@ -62,6 +62,24 @@ def test_kernel_emulation_matches_oracle(name, gen, kw):
         assert not bad, (name, tier, bad[:5])
         if tier == 1:
             assert re_[3] == 0
+
+
+@pytest.mark.parametrize("name,gen,kw", CASES, ids=[c[0] for c in CASES])
+def test_lane_emulation_matches_oracle_under_every_schedule(name, gen, kw):
+    """The kernel source as 32 cooperative fibers per warp (tests/emu/emu_lanes.cpp): the lanes run between two warp collectives in
+    ascending, descending and shuffled order.  A missing __syncwarp, a collective in divergent code or lanes that disagree on the
+    per-window state would show as a mismatch against the oracle, a deadlock or a lane disagreement (tools/lane_mutants.py measures
+    how many dropped syncs this notices)."""
+    p = default_params(**kw)
+    n = {"k14": 8, "multik": 24, "gapfill": 40}.get(name, max(10, min(120, 3000 // gen["depth"])))     # the three are slow (filter-frequency descent, gap filling)
+    packed, win, sl, _ = synth_batch(n, gen["depth"], seed=gen["seed"] + 1000, repeat_frac=gen["rf"], depth_jitter=min(gen["depth"], 3), w=p.w)
+    ro = run_oracle(p, packed, win, sl, 4)
+    for tier, schedule in ((1, 0), (1, 1), (1, 2), (0, 3), (0, 1)):
+        rl = run_emu_lanes(p, packed, win, sl, tier, schedule, seed=gen["seed"])
+        bad = [i for i in compare_results(ro, rl) if rl[0][i]["status"] != 250]
+        assert not bad, (name, tier, schedule, bad[:5])
+        assert tier == 0 or rl[3] == 0
+        assert rl[4] > 0                                    # collectives were executed: this was the 32-lane build
 
 
 def test_edge_cases_empty_and_ragged():

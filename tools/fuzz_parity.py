@@ -1,4 +1,4 @@
-"""CPU only: differential fuzzing of the kernel source (host emulation) against the oracle over random parameter sets (w, k range,
+"""CPU only: differential fuzzing of the kernel source (host emulation, single lane and 32 lanes under random lane schedules) against the oracle over random parameter sets (w, k range,
 depth, error rates, repeats, -m, filter frequencies, -e).  Prints one line per batch; any mismatch is a parity bug.
    python tools/fuzz_parity.py [seconds] [first_seed]"""
 import os
@@ -8,7 +8,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from common import default_params, synth_batch, run_oracle, run_emu, compare_results  # noqa: E402
+from common import default_params, synth_batch, run_oracle, run_emu, run_emu_lanes, compare_results  # noqa: E402
 
 
 def main():
@@ -33,6 +33,10 @@ def main():
         ref = run_oracle(p, packed, win, sl, 8)
         got = run_emu(p, packed, win, sl, 1)
         bad = compare_results(ref, got)
+        # the same windows through the 32-lane emulation under a shuffled lane schedule (races, divergent collectives)
+        sched = int(rng.integers(0, 4))
+        gl = run_emu_lanes(p, packed, win, sl, 1, sched, seed)
+        bad = sorted(set(bad) | set(compare_results(ref, gl)))
         nb += 1; nw += n; nbad += len(bad)
         print("seed %d w %d k %d..%d depth %d err %.2f ff %d..%d windows %d ok %d overflow %d %s" % (seed, w, klo, khi, depth, e, maxff, minff, n, int((ref[0]["status"] == 1).sum()), got[3],
                                                                                                      "OK" if not bad else "MISMATCH %s" % bad[:5]), flush=True)
