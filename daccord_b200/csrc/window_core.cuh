@@ -74,8 +74,8 @@ const unsigned long long* emu_xchg(unsigned long long v);
 extern int emu_skip_sync_line;       // mutation testing of the harness itself (tools/lane_mutants.py): the wsync() of this source line is dropped
 static inline void wsync_line(int line) { if (line != emu_skip_sync_line) emu_xchg(0); }
 #define wsync() wsync_line(__LINE__)
-static inline uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }   // fibers are not preempted
-static inline uint32_t a_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { __atomic_compare_exchange_n(p, &c, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return c; }   // real atomics: the lanes are OS threads in the ThreadSanitizer build
+static inline uint32_t a_add(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline uint32_t ballot(bool p) { const unsigned long long* x = emu_xchg(p ? 1 : 0); uint32_t m = 0; for (int i = 0; i < 32; ++i) if (x[i]) m |= 1u << i; return m; }
 static inline uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 static inline int popc(uint32_t x) { return __builtin_popcount(x); }

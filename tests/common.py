@@ -110,6 +110,37 @@ def run_emu_lanes(params, packed, win, sl, tier=0, schedule=0, seed=1):
     return res, cons, ops, nov.value, ncoll.value
 
 
+def build_emu_tsan():
+    out = os.path.join(ROOT, "tests", "emu", "_build", "emu_tsan")
+    src = os.path.join(ROOT, "tests", "emu", "emu_tsan.cpp")
+    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "host_tables.hpp", "host_caps.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-fsanitize=thread", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-pthread", "-o", out, src])
+    return out
+
+
+def run_emu_tsan(params, packed, win, sl, tier=1, timeout=600):
+    """window_core.cuh with the 32 lanes of a warp as OS threads under ThreadSanitizer (tests/emu/emu_tsan.cpp).
+    Returns (res, cons, ops, tsan_report_text); the report is empty when no two lanes race."""
+    import tempfile
+    exe = build_emu_tsan()
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+        packed = np.ascontiguousarray(packed); win = np.ascontiguousarray(win); sl = np.ascontiguousarray(sl)
+        with open(fin, "wb") as f:
+            f.write(bytes(params)); f.write(np.array([packed.nbytes, len(win), len(sl)], np.uint64).tobytes())
+            f.write(packed.tobytes()); f.write(win.tobytes()); f.write(sl.tobytes())
+        env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4")
+        r = subprocess.run([exe, fin, fout, str(tier)], capture_output=True, text=True, timeout=timeout, env=env)
+        assert r.returncode in (0, 66), (r.returncode, r.stderr[-2000:])       # 66: TSan found races (reported through the text)
+        res, cons, ops = alloc_out(len(win))
+        raw = open(fout, "rb").read()
+        a, b = res.nbytes, res.nbytes + cons.nbytes
+        res[:] = np.frombuffer(raw[:a], RESULT_DT); cons[:] = np.frombuffer(raw[a:b], np.uint8); ops[:] = np.frombuffer(raw[b:], np.uint8)
+    return res, cons, ops, r.stderr
+
+
 def emu_vote(win, res, cons, ops, w, producefull, minlen, packed, boff, rlen):
     """vote_core.cuh (the GPU pile vote) compiled for the host; returns (segments, chars)"""
     from daccord_b200 import SEGMENT_DT

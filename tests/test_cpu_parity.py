@@ -6,7 +6,7 @@ import re
 import subprocess
 import numpy as np
 import pytest
-from common import (ROOT, default_params, synth_batch, run_oracle, run_emu, run_emu_lanes, compare_results, get_tables, oracle_lib, emu_lib,
+from common import (ROOT, default_params, synth_batch, run_oracle, run_emu, run_emu_lanes, run_emu_tsan, compare_results, get_tables, oracle_lib, emu_lib,
                     CONS_STRIDE)
 
 
@@ -80,6 +80,27 @@ def test_lane_emulation_matches_oracle_under_every_schedule(name, gen, kw):
         assert not bad, (name, tier, schedule, bad[:5])
         assert tier == 0 or rl[3] == 0
         assert rl[4] > 0                                    # collectives were executed: this was the 32-lane build
+
+
+TSAN_CASES = [("d30", dict(depth=30, n=8, seed=31, rf=0.2), {}),
+              ("gapfill", dict(depth=8, n=10, seed=37, rf=0.4), dict(min_ff=0, max_ff=2, k_lo=6, k_hi=8)),
+              ("repeats", dict(depth=12, n=10, seed=36, rf=0.6), {}),
+              ("tier0", dict(depth=40, n=6, seed=38, rf=0.0), {})]
+
+
+@pytest.mark.parametrize("name,gen,kw", TSAN_CASES, ids=[c[0] for c in TSAN_CASES])
+def test_no_race_between_lanes_under_thread_sanitizer(name, gen, kw):
+    """The kernel source with the 32 lanes of a warp as OS threads (collectives and __syncwarp = barriers, atomics = atomics) under
+    ThreadSanitizer: no two lanes may touch the same workspace bytes between two barriers unless both only read -- and the result is still the
+    oracle's.  (tools/lane_mutants.py --tsan: dropping a needed wsync() is reported with the two racing source lines.)"""
+    p = default_params(**kw)
+    packed, win, sl, _ = synth_batch(gen["n"], gen["depth"], seed=gen["seed"], repeat_frac=gen["rf"], depth_jitter=3, w=p.w)
+    ro = run_oracle(p, packed, win, sl, 4)
+    tier = 0 if name == "tier0" else 1
+    res, cons, ops, report = run_emu_tsan(p, packed, win, sl, tier)
+    assert "ThreadSanitizer" not in report, report[:3000]
+    bad = [i for i in compare_results(ro, (res, cons, ops)) if res[i]["status"] != 250]
+    assert not bad, (name, bad[:5])
 
 
 def test_edge_cases_empty_and_ragged():
