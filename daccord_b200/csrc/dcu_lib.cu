@@ -312,6 +312,7 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   ctx->T.suplo = ctx->dsuplo.p; ctx->T.suphi = ctx->dsuphi.p; ctx->T.NP = H.NP; ctx->T.MS = H.MS; ctx->T.KLIMN = H.KLIMN;
   ctx->P.w = (int)p->w; ctx->P.k_lo = (int)p->k_lo; ctx->P.k_hi = (int)p->k_hi; ctx->P.minff = p->min_ff; ctx->P.maxff = p->max_ff;
   ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err; ctx->P.defer_ff = 0;
+  { const char* e = getenv("DCU_POSCACHE"); ctx->P.poscache = e ? atoi(e) : 1; }
   CK(ctx->dcnt.ensure(8));
   const char* e = getenv("DCU_BLOCKS_PER_SM");
   if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);

@@ -159,6 +159,7 @@ struct Params {
   int w, k_lo, k_hi, minff, maxff, mincov, check;   // check = (est_cor != 0)  (DebruijnGraph.hpp:1832-1837)
   unsigned long long eminrate;
   int defer_ff;                                      // experimental (DCU_DEFER_FF, first pass only): hand windows whose first filter frequency fails to the second pass
+  int poscache;                                      // keep the position weights of unsplit unitigs across the (first,last) pairs of a traverse (DCU_POSCACHE=0 turns it off; results identical)
 };
 // capacities of one warp's workspace (two tiers: small for the common case, large for the rest)
 struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, STP, SL, SF, RL, RLP, RP, FP, SI, BL, KW, HEAVY; };
@@ -186,6 +187,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(ll_kmer, uint32_t, c.S) X(ll_cnt, uint16_t, c.S) X(fl_kmer, uint32_t, c.S) X(fl_cnt, uint16_t, c.S)    \
   X(fl_nid, uint16_t, c.S)                                                                                 \
   X(slinks, uint16_t, c.SL) X(slsym, uint8_t, c.SL) X(rs_off, uint16_t, c.ST) X(rs_len, uint16_t, c.ST)    \
+  X(rs_fO, uint32_t, c.ST) X(rs_cO, uint32_t, c.ST) X(spc, uint32_t, 4)                                    \
   X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint32_t, c.ST) X(ds_cO, uint32_t, c.ST)    \
   X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST) X(du_off, uint16_t, c.ST) X(du_len, uint16_t, c.ST)  \
   X(ds_rlO, uint16_t, c.ST) X(ds_rlN, uint16_t, c.ST)                                                      \
@@ -893,61 +895,118 @@ DCU_FN unsigned long long inst_colsum(const uint8_t* ip, int f, const unsigned l
 
 // computeFeasibleStretchPositions (:3176-3330).  Every stretch owns one slot per position of its anchor's
 // support range (forward: first k-mer, object p = start position; reverse: last k-mer, object p = its reverse
-// position); slot weight < 0 marks "not feasible".  Lanes over all slots of all stretches.
+// position); slot weight < 0 marks "not feasible".
+// sp_view fills the slots of one view (off, L) of the link array: lanes over anchor positions; the link weights are evaluated
+// on the fly from the instance lists (all lanes share the node, so instance positions are uniform loads and only the table
+// column differs per lane).  Warp-uniform arguments.
+DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
+  const WS& w = c.ws;
+  const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
+  const int nmax = nf > nr ? nf : nr;
+  DCU_NOUNROLL
+  for (int q0 = 0; q0 < nmax; q0 += DCU_NL) {
+    const int q = q0 + lane;
+    bool af = q < nf, ar = q < nr;
+    double sumf = 0.0, sumr = 0.0, wfr = 0.0;
+    DCU_NOUNROLL
+    for (int jj = 0; jj < L; ++jj) {
+      if (!ballot(af || ar)) break;
+      const int nF = w.slinks()[off + jj], nR = w.slinks()[off + L - 1 - jj];
+      if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
+        int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
+        const uint8_t* ip = w.ipos() + w.n_ioff()[nF]; const int f = w.n_freq()[nF];
+        const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
+        double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
+        if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
+      }
+      if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
+        int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
+        const uint8_t* ip = w.irpos() + w.n_ioff()[nR]; const int f = w.n_freq()[nR];
+        const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
+        double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
+        if (ar) { if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false; }
+      }
+    }
+    if (q < nf) w.sf_w()[fO + q] = af ? sumf : -1.0;
+    if (q < nr) { w.sc_w()[cO + q] = ar ? sumr : -1.0; w.sc_wf()[cO + q] = wfr; }
+  }
+}
+// The slots of a view depend on its links only, not on the (first,last) pair, and a pair splits at most the two unitigs that hold
+// its first / last k-mer as an interior node: the slots of the raw unitigs are therefore computed once per traverse (the first
+// call after trav_start) in the front part of the slot arrays and a later pair only computes its split pieces behind them; an
+// unsplit stretch (same offset and length as a raw unitig) points at the cached slots.  Windows that walk through many pairs
+// (filterfreq-1 graphs with ~1000 nodes: a median of 17 pairs) spent most of their time recomputing these.
 DCU_BIG void stretch_positions(Ctx& c, int lane) {
   const WS& w = c.ws;
-  uint32_t run0 = 0, run1 = 0;
+  const bool cache = DCU_P.poscache != 0;
+  uint32_t base0 = 0, base1 = 0;
+  if (cache) {
+    if (!w.spc()[0]) {                               // first pair of this traverse: slots of all raw unitigs
+      uint32_t run0 = 0, run1 = 0;
+      DCU_NOUNROLL
+      for (int base = 0; base < c.nrs; base += DCU_NL) {
+        int r = base + lane;
+        uint32_t a = 0, b = 0;
+        if (r < c.nrs) {
+          int off = w.rs_off()[r], n0 = w.slinks()[off], n1 = w.slinks()[off + w.rs_len()[r] - 1];
+          a = (uint32_t)(uint8_t)(w.n_pt()[n0] - w.n_pf()[n0]); b = (uint32_t)(uint8_t)(w.n_cpt()[n1] - w.n_cpf()[n1]);
+        }
+        uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
+        if (r < c.nrs) { w.rs_fO()[r] = run0 + ia - a; w.rs_cO()[r] = run1 + ib - b; }
+        run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
+      }
+      wsync();
+      DCU_PEAK(6, run0 > run1 ? run0 : run1);
+      if (run0 > (uint32_t)DCU_CAP.SF || run1 > (uint32_t)DCU_CAP.SF) { c.overflow = 9; return; }
+      DCU_NOUNROLL
+      for (int r = 0; r < c.nrs; ++r) {
+        const int off = w.rs_off()[r], L = w.rs_len()[r];
+        const int n0 = w.slinks()[off], n1 = w.slinks()[off + L - 1];
+        const int bf = w.n_pf()[n0], br = w.n_cpf()[n1];
+        const int nf = (uint8_t)(w.n_pt()[n0] - bf), nr = (uint8_t)(w.n_cpt()[n1] - br);
+        sp_view(c, off, L, nf, nr, bf, br, w.rs_fO()[r], w.rs_cO()[r], lane);
+      }
+      if (lane == 0) { w.spc()[0] = 1; w.spc()[1] = run0; w.spc()[2] = run1; }
+      wsync();
+    }
+    base0 = w.spc()[1]; base1 = w.spc()[2];
+  }
+  // the stretches of this pair: unsplit ones take the cached slots, the others get fresh slots behind the cache and go on the todo list
+  uint32_t run0 = base0, run1 = base1; int ntodo = 0;
+  uint16_t* todo = w.dt_off();                       // scratch of derive_stretches, free again
   DCU_NOUNROLL
   for (int base = 0; base < c.nds; base += DCU_NL) {
     int s = base + lane;
-    uint32_t a = 0, b = 0;
+    uint32_t a = 0, b = 0; bool fresh = false; uint32_t cfO = 0, ccO = 0;
     if (s < c.nds) {
       int n0 = ds_first(c, s), n1 = ds_last(c, s);
-      a = (uint32_t)(w.n_pt()[n0] - w.n_pf()[n0]); b = (uint32_t)(w.n_cpt()[n1] - w.n_cpf()[n1]);
+      a = (uint32_t)(uint8_t)(w.n_pt()[n0] - w.n_pf()[n0]); b = (uint32_t)(uint8_t)(w.n_cpt()[n1] - w.n_cpf()[n1]);
       w.ds_fB()[s] = w.n_pf()[n0]; w.ds_fN()[s] = (uint8_t)a; w.ds_cB()[s] = w.n_cpf()[n1]; w.ds_cN()[s] = (uint8_t)b;
+      fresh = true;
+      if (cache) {                                   // raw unitig with this offset (offsets ascend with the raw index)
+        const int off = w.ds_off()[s];
+        int lo = 0, hi = c.nrs;
+        DCU_NOUNROLL
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)w.rs_off()[mid] <= off) lo = mid; else hi = mid; }
+        if (c.nrs > 0 && (int)w.rs_off()[lo] == off && w.rs_len()[lo] == w.ds_len()[s]) { fresh = false; cfO = w.rs_fO()[lo]; ccO = w.rs_cO()[lo]; }
+      }
+      if (!fresh) { a = 0; b = 0; }
     }
     uint32_t ia = scan_incl(a, lane), ib = scan_incl(b, lane);
-    if (s < c.nds) { uint32_t oa = run0 + ia - a, ob = run1 + ib - b; w.ds_fO()[s] = oa; w.ds_cO()[s] = ob; }
-    run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1);
+    const uint32_t tb = ballot(fresh);
+    if (s < c.nds) {
+      if (fresh) { w.ds_fO()[s] = run0 + ia - a; w.ds_cO()[s] = run1 + ib - b; todo[ntodo + popc(tb & lanemask_lt(lane))] = (uint16_t)s; }
+      else { w.ds_fO()[s] = cfO; w.ds_cO()[s] = ccO; }
+    }
+    run0 += bcast(ia, DCU_NL - 1); run1 += bcast(ib, DCU_NL - 1); ntodo += popc(tb);
   }
   wsync();
   DCU_PEAK(6, run0 > run1 ? run0 : run1);
   if (run0 > (uint32_t)DCU_CAP.SF || run1 > (uint32_t)DCU_CAP.SF) { c.overflow = 9; return; }
-  // per stretch, lanes over anchor positions; the link weights are evaluated on the fly from the instance lists
-  // (all lanes share the node, so instance positions are uniform loads and only the table column differs per lane)
-  const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
   DCU_NOUNROLL
-  for (int s = 0; s < c.nds; ++s) {
-    const int off = w.ds_off()[s], L = w.ds_len()[s];
-    const int nf = w.ds_fN()[s], nr = w.ds_cN()[s], bf = w.ds_fB()[s], br = w.ds_cB()[s];
-    const int nmax = nf > nr ? nf : nr;
-    DCU_NOUNROLL
-    for (int q0 = 0; q0 < nmax; q0 += DCU_NL) {
-      const int q = q0 + lane;
-      bool af = q < nf, ar = q < nr;
-      double sumf = 0.0, sumr = 0.0, wfr = 0.0;
-      DCU_NOUNROLL
-      for (int jj = 0; jj < L; ++jj) {
-        if (!ballot(af || ar)) break;
-        const int nF = w.slinks()[off + jj], nR = w.slinks()[off + L - 1 - jj];
-        if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
-          int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-          const uint8_t* ip = w.ipos() + w.n_ioff()[nF]; const int f = w.n_freq()[nF];
-          const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
-          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
-          if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
-        }
-        if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
-          int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-          const uint8_t* ip = w.irpos() + w.n_ioff()[nR]; const int f = w.n_freq()[nR];
-          const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
-          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
-          if (ar) { if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false; }
-        }
-      }
-      if (q < nf) w.sf_w()[w.ds_fO()[s] + q] = af ? sumf : -1.0;
-      if (q < nr) { w.sc_w()[w.ds_cO()[s] + q] = ar ? sumr : -1.0; w.sc_wf()[w.ds_cO()[s] + q] = wfr; }
-    }
+  for (int t = 0; t < ntodo; ++t) {
+    const int s = todo[t];
+    sp_view(c, w.ds_off()[s], w.ds_len()[s], w.ds_fN()[s], w.ds_cN()[s], w.ds_fB()[s], w.ds_cB()[s], w.ds_fO()[s], w.ds_cO()[s], lane);
   }
   wsync();
 }
@@ -1305,6 +1364,7 @@ DCU_BIG void trav_start(Ctx& c, TravState& t, int lane) {
   g_stats[6]++;
 #endif
   const WS& w = c.ws;
+  if (lane == 0) w.spc()[0] = 0;                     // new unitigs: the cached position slots are stale (raw_stretches ends with a wsync)
   raw_stretches(c, lane);
   t.ncdh = 0; t.freeslots = (1u << (CDH_N + 1)) - 1;
   t.firstthres = c.nfirst ? (w.fl_cnt()[0] * 3) / 4 : 0;

@@ -30,7 +30,8 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
   T.klim = HT.klim.data(); T.NP = HT.NP; T.MS = HT.MS; T.KLIMN = HT.KLIMN;
   P.w = (int)prm->w; P.k_lo = (int)prm->k_lo; P.k_hi = (int)prm->k_hi; P.minff = prm->min_ff; P.maxff = prm->max_ff;
   P.mincov = (int)prm->min_cov; P.check = prm->est_cor != 0.0; P.eminrate = prm->max_err;
-  P.defer_ff = (tier == 0 && getenv("DCU_DEFER_FF")) ? 1 : 0;        // same experimental switch as the library's first pass
+  P.defer_ff = (tier == 0 && getenv("DCU_DEFER_FF")) ? 1 : 0;
+  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }        // same experimental switch as the library's first pass
   dcu::g_layout = L; dcu::g_cap = caps; dcu::g_T = T; dcu::g_P = P;
   dcu::Ctx c;
   c.ws.base = slab.data(); c.vsq = T.VSq;

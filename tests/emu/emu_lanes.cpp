@@ -155,6 +155,7 @@ extern "C" int emu_lanes_run_batch(const dcu_params* prm, const uint8_t* packed,
   P.w = (int)prm->w; P.k_lo = (int)prm->k_lo; P.k_hi = (int)prm->k_hi; P.minff = prm->min_ff; P.maxff = prm->max_ff;
   P.mincov = (int)prm->min_cov; P.check = prm->est_cor != 0.0; P.eminrate = prm->max_err;
   P.defer_ff = (tier == 0 && getenv("DCU_DEFER_FF")) ? 1 : 0;
+  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }
   dcu::g_layout = L; dcu::g_cap = caps; dcu::g_T = T; dcu::g_P = P;
   g_rng = seed * 2 + 1; g_ncoll = 0;
   { const char* e = getenv("DCU_EMU_SKIP_SYNC_LINE"); dcu::emu_skip_sync_line = e ? atoi(e) : -1; }

@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
   T.klim = HT.klim.data(); T.NP = HT.NP; T.MS = HT.MS; T.KLIMN = HT.KLIMN;
   P.w = (int)prm.w; P.k_lo = (int)prm.k_lo; P.k_hi = (int)prm.k_hi; P.minff = prm.min_ff; P.maxff = prm.max_ff;
   P.mincov = (int)prm.min_cov; P.check = prm.est_cor != 0.0; P.eminrate = prm.max_err; P.defer_ff = 0;
+  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }
   dcu::g_layout = L; dcu::g_cap = caps; dcu::g_T = T; dcu::g_P = P;
   std::vector<dcu_result> res(nwin); std::vector<uint8_t> cons(nwin * DCU_CONS_STRIDE, 0), ops(nwin * DCU_OPS_STRIDE, 0);
   std::vector<dcu::Result> lane_res((size_t)NL * nwin);

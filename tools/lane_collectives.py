@@ -1,7 +1,8 @@
 """CPU only: where a window's warp collectives come from.  Runs windows through the 32-lane emulation (tests/emu/emu_lanes.cpp) with
 DCU_EMU_PROFILE, which counts every collective / wsync by call site, and resolves the sites to source lines of window_core.cuh
 (addr2line on the emulation library).  Collectives are a proxy for the serial depth of the lane-parallel code: ~30 issue cycles each on the GPU.
-   python tools/lane_collectives.py [k] [depth] [windows] [repeat_frac]"""
+   python tools/lane_collectives.py [k] [depth] [windows] [repeat_frac]      (synthetic window batch)
+   python tools/lane_collectives.py pile [coverage] [windows]               (windows of a simulated pile, as in bench.py)"""
 import collections
 import os
 import subprocess
@@ -13,6 +14,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
+    pile = len(sys.argv) > 1 and sys.argv[1] == "pile"
+    if pile:
+        sys.argv[1] = "8"
     k = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     depth = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 200
@@ -21,7 +25,16 @@ def main():
     os.environ["DCU_EMU_PROFILE"] = out
     from common import default_params, synth_batch, run_emu_lanes, build_emu_lanes
     p = default_params(k_lo=k, k_hi=k)
-    packed, win, sl, _ = synth_batch(n, depth, seed=18, repeat_frac=rf, depth_jitter=3, w=p.w)
+    if pile:
+        import numpy as np
+        from daccord_b200.host import Dataset
+        ds = Dataset.simulate(60000, read_len=10000, coverage=depth, seed=1)
+        pi, pd, cor = ds.profile()
+        p = default_params(p_i=pi, p_d=pd, est_cor=cor)
+        b = ds.pile(nthreads=8)
+        win = b.win[:: max(1, len(b.win) // n)].copy(); sl = b.sl.copy(); packed = np.ascontiguousarray(ds.packed()); n = len(win)
+    else:
+        packed, win, sl, _ = synth_batch(n, depth, seed=18, repeat_frac=rf, depth_jitter=3, w=p.w)
     r = run_emu_lanes(p, packed, win, sl, 1, 0, 1)
     rows = [l.split() for l in open(out)]
     os.unlink(out)
