@@ -200,6 +200,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; };
   X(rp_w, double, c.RP) X(rp_parent, uint32_t, c.RP) X(rp_front, uint32_t, c.RP)                           \
   X(rp_stretch, uint16_t, c.RP) X(rp_pos, uint16_t, c.RP) X(rp_len, uint16_t, c.RP)                        \
   X(rp_baselen, uint16_t, c.RP) X(rq_w, double, c.RP) X(rq_id, uint32_t, c.RP) X(arp, uint32_t, c.RP)      \
+  X(arp_k, unsigned long long, c.RP) X(arp_wt, double, c.RP)                                               \
   X(arph_w, double, c.BL* HEAPK) X(arph_n, uint8_t, c.BL)                                                  \
   X(fp_w, double, c.FP) X(fp_parent, uint32_t, c.FP) X(fp_stretch, uint16_t, c.FP)                         \
   X(fp_pos, uint16_t, c.FP) X(fp_len, uint16_t, c.FP) X(fp_baselen, uint16_t, c.FP)                        \
@@ -1176,7 +1177,13 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
 // sort accepted reverse paths by (front, baselen), ties in acceptance order (:3742, convention C7); all lanes
 DCU_BIG void sort_reverse_paths(Ctx& c, int narp, int lane) {
   const WS& w = c.ws;
-  if (narp <= 1) return;
+  // arp_k[i] = (front << 8) | baselen and arp_wt[i] = weight of the i-th accepted path in sorted order: the forward search finds its
+  // pairing range by two binary searches on arp_k and scans weights in arp_wt, instead of chasing arp[i] -> rp_front / rp_baselen / rp_w
+  if (narp <= 1) {
+    if (narp == 1 && lane == 0) { uint32_t id = w.arp()[0]; w.arp_k()[0] = ((unsigned long long)w.rp_front()[id] << 8) | (unsigned long long)(w.rp_baselen()[id] & 0xFF); w.arp_wt()[0] = w.rp_w()[id]; }
+    wsync();
+    return;
+  }
   unsigned long long* key = (unsigned long long*)w.sq_w();      // the score-interval heap is not in use yet
   int P = 32; while (P < narp) P <<= 1;
   DCU_NOUNROLL
@@ -1188,7 +1195,7 @@ DCU_BIG void sort_reverse_paths(Ctx& c, int narp, int lane) {
   wsync();
   warp_sort_u64(key, P, lane);
   DCU_NOUNROLL
-  for (int i = lane; i < narp; i += DCU_NL) w.arp()[i] = w.rq_id()[(int)(key[i] & 0xFFFF)];
+  for (int i = lane; i < narp; i += DCU_NL) { uint32_t id = w.rq_id()[(int)(key[i] & 0xFFFF)]; w.arp()[i] = id; w.arp_k()[i] = key[i] >> 16; w.arp_wt()[i] = w.rp_w()[id]; }
   wsync();
 }
 
@@ -1204,10 +1211,11 @@ DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScor
 DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
   const WS& w = c.ws;
   int best = -1; double bw = 0;
-  double cw = cur >= 0 ? w.rp_w()[w.arp()[cur]] : 0;
+  const double* wt = w.arp_wt();
+  double cw = cur >= 0 ? wt[cur] : 0;
   DCU_NOUNROLL
   for (int i = left; i < right; ++i) {
-    double wi = w.rp_w()[w.arp()[i]];
+    double wi = wt[i];
     if (cur >= 0 && !(wi < cw || (wi == cw && i < cur))) continue;
     if (best < 0 || wi > bw || (wi == bw && i > best)) { best = i; bw = wi; }
   }
@@ -1285,11 +1293,18 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
       int plast = ds_last(c, pls); uint32_t plk = w.n_kmer()[plast];
       int blo = lmin + K - candlen; if (blo < 0) blo = 0;
       int bhi = lmax + K - candlen; if (bhi < 0) bhi = 0;
+      // reverse paths with front == plk and blo <= baselen <= bhi: a contiguous range of the (front, baselen) order
       int left = -1, right = -1;
-      DCU_NOUNROLL
-      for (int i = 0; i < narp; ++i) {
-        uint32_t id = w.arp()[i];
-        if (w.rp_front()[id] == plk && (int)w.rp_baselen()[id] >= blo && (int)w.rp_baselen()[id] <= bhi) { if (left < 0) left = i; right = i + 1; }
+      if (blo <= 255) {
+        const unsigned long long* ak = w.arp_k();
+        const unsigned long long klo = ((unsigned long long)plk << 8) | (unsigned long long)blo, khi = ((unsigned long long)plk << 8) | (unsigned long long)(bhi > 255 ? 255 : bhi);
+        int a = 0, b = narp;                           // first i with ak[i] >= klo
+        DCU_NOUNROLL
+        while (a < b) { int mid = (a + b) >> 1; if (ak[mid] < klo) a = mid + 1; else b = mid; }
+        int e = a, f = narp;                           // first i with ak[i] > khi
+        DCU_NOUNROLL
+        while (e < f) { int mid = (e + f) >> 1; if (ak[mid] <= khi) e = mid + 1; else f = mid; }
+        if (e > a) { left = a; right = e; }
       }
       if (left >= 0) {
         int cur = interval_next(c, left, right, -1);
