@@ -1,17 +1,24 @@
 #!/bin/bash
-# First GPU call of the next round (about 6 GPU-minutes): everything that could not be measured when round 1 ran out of budget.
-#   gpurun --timeout 900 -- 'bash tools/round2_first_run.sh'
+# First GPU call of the next round (about 10 GPU-minutes): everything that could not be measured when round 1 ran out of budget.
+#   gpurun --timeout 1200 -- 'bash tools/round2_first_run.sh'
 set -u
 mkdir -p gpurun_out
-# 1. the whole GPU suite: three tests were not reached after the per-window piling kernels went in, and the window kernel's unitig position
-#    offsets were widened to 32 bit afterwards (emulation parity only)
-timeout 400 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest=$?"; tail -3 gpurun_out/r2_pytest_gpu.log
-# 2. A/B of the deferral switch on the bench workload
-for d in 0 1; do
-  if [ $d = 1 ]; then export DCU_DEFER_FF=1; else unset DCU_DEFER_FF; fi
-  python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_defer_$d.json
-  python -c "import json; l=json.load(open('gpurun_out/r2_defer_$d.json')); print('defer=$d value %.3f e2e %.3f from_overlaps %.3f to_fasta %.3f hard %d' % (l['value']/1e6, l['e2e']['value']/1e6, l['e2e_from_overlaps']['value']/1e6, l['e2e_overlaps_to_fasta']['value']/1e6, l['hard_windows']))"
+# 1. the whole GPU suite: the per-window piling kernels, the 32-bit unitig slot offsets, the position-slot cache and the binary-search
+#    pairing range went in after the last GPU run (emulation parity only: single lane, 32 lanes under adversarial schedules, TSan)
+timeout 500 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest=$?"; tail -3 gpurun_out/r2_pytest_gpu.log
+line() { python -c "import json,sys; l=json.load(open(sys.argv[1])); print(sys.argv[2], 'value %.3f e2e %.3f from_overlaps %.3f to_fasta %.3f hard %d' % (l['value']/1e6, l['e2e']['value']/1e6, l['e2e_from_overlaps']['value']/1e6, l['e2e_overlaps_to_fasta']['value']/1e6, l['hard_windows']))" "$1" "$2"; }
+# 2. A/B of the position-slot cache (profiles/r01_summary.md) on the bench workload at 40x and 20x
+for pc in 1 0; do
+  for cov in 40 20; do
+    DCU_POSCACHE=$pc python bench.py --mb 20 --coverage $cov --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_poscache_${pc}_cov${cov}.json
+    line gpurun_out/r2_poscache_${pc}_cov${cov}.json "poscache=$pc coverage=$cov"
+  done
 done
-unset DCU_DEFER_FF
-# 3. launch list of the bench command with the new piling kernels
+# 3. A/B of the deferral switch
+DCU_DEFER_FF=1 python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_defer_1.json; line gpurun_out/r2_defer_1.json "defer=1"
+# 4. resident warps per SM against the L2 (4 736 workspaces of ~64-100 KB do not fit 126 MB): 1 block of 16 warps per SM
+DCU_BLOCKS_PER_SM=1 python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_bps_1.json; line gpurun_out/r2_bps_1.json "blocks_per_sm=1"
+# 5. hard configurations the cache was written for (tools/kernel_bench.py: synthetic windows, device-timed)
+for pc in 1 0; do DCU_POSCACHE=$pc python tools/kernel_bench.py 10 20 2>&1 | tail -1 | sed "s/^/poscache=$pc depth10 /"; done
+# 6. launch list of the bench command with the new piling kernels
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_5mb.csv python bench.py --mb 5 --steps 2 --warmup 1 --cpu-sample-s 0 > /dev/null 2>&1; echo "launch list rc=$?"
