@@ -319,14 +319,21 @@ DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
   c.MAo = win.slice_cnt; c.overflow = 0;
   if (c.MAo > DCU_CAP.S) { c.overflow = 1; return; }
   const Slice* sl = c.sl + win.slice_begin;
-  if (lane == 0) {
-    uint32_t o = 0;
+  {                                                  // slice offsets: warp scan over the descriptor lengths (was a lane-0 loop of dependent loads)
+    uint32_t run = 0; bool big = false;
     DCU_NOUNROLL
-    for (int j = 0; j < c.MAo; ++j) { w.soff()[j] = (uint16_t)o; o += sl[j].len; if (sl[j].len > 255) o = 0x10000000u; }
-    w.soff()[c.MAo] = (uint16_t)(o > 65535u ? 65535u : o);
-    c.nbases = (int)(o > 0x0fffffffu ? 0x0fffffff : o);
+    for (int base = 0; base < c.MAo; base += DCU_NL) {
+      const int j = base + lane;
+      const uint32_t len = j < c.MAo ? (uint32_t)sl[j].len : 0u;
+      big = big || len > 255u;                         // slices are at most 255 bases (8-bit instance positions)
+      const uint32_t inc = scan_incl(len, lane);
+      if (j < c.MAo) w.soff()[j] = (uint16_t)(run + inc - len);
+      run += bcast(inc, DCU_NL - 1);
+    }
+    if (ballot(big)) run = 0x10000000u;
+    if (lane == 0) w.soff()[c.MAo] = (uint16_t)(run > 65535u ? 65535u : run);
+    c.nbases = (int)(run > 0x0fffffffu ? 0x0fffffff : run);
   }
-  c.nbases = bcast(c.nbases, 0);
   wsync();
   DCU_PEAK(0, c.MAo); DCU_PEAK(1, c.nbases);
   if (c.nbases > DCU_CAP.B || c.nbases > 65000) { c.overflow = 2; return; }
@@ -528,8 +535,18 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   if (DCU_CAP.HEAVY && nn > DCU_CAP.HEAVY) { c.overflow = 21; c.nn = 0; wsync(); return; }
   c.nn = nn;
   wsync();
-  if (lane == 0) { uint32_t o = 0; for (int n = 0; n < nn; ++n) { w.n_ioff()[n] = o; o += w.n_freq()[n]; } c.ni = (int)o; }
-  c.ni = bcast(c.ni, 0);
+  {                                                  // instance list offsets: warp scan over the node frequencies (was a lane-0 loop)
+    uint32_t run = 0;
+    DCU_NOUNROLL
+    for (int base = 0; base < nn; base += DCU_NL) {
+      const int n = base + lane;
+      const uint32_t f0 = n < nn ? (uint32_t)w.n_freq()[n] : 0u;
+      const uint32_t inc = scan_incl(f0, lane);
+      if (n < nn) w.n_ioff()[n] = run + inc - f0;
+      run += bcast(inc, DCU_NL - 1);
+    }
+    c.ni = (int)run;
+  }
   wsync();
   DCU_PEAK(3, c.ni);
   if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
@@ -1120,7 +1137,7 @@ DCU_NOINL int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t fro
 }
 
 // reverse half-paths (prepareTraverse :3576-3757); lane 0
-DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
+DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp, int nseed) {
   const WS& w = c.ws;
   int nrp = 0, nq = 0; narp = 0;
   DCU_NOUNROLL
@@ -1146,7 +1163,8 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp) {
     int rlen = w.rp_len()[id], rpos = w.rp_pos()[id];
     if (rlen == 0) {
       DCU_NOUNROLL
-      for (int s = 0; s < c.nds; ++s) if (ds_last(c, s) == Lnode) {
+      for (int qs = 0; qs < nseed; ++qs) {              // stretches that end in Lnode, ascending (listed by trav_pair_rpaths)
+        const int s = w.dt_len()[qs];
         int o = sfo_rev(c, s, rpos);                    // extendReversePath (:4058-4105) + feasibility (:4130-4159)
         if (o >= 0 && w.sc_w()[o] >= 0.5) {
           int L = w.ds_len()[s];
@@ -1418,7 +1436,19 @@ DCU_BIG void trav_pair_weights(Ctx& c, int lane) {
 }
 DCU_BIG void trav_pair_rpaths(Ctx& c, TravState& t, int lmax, int lane) {
   int narp = 0;
-  if (lane == 0) reverse_paths(c, t.L, lmax, narp);
+  // stretches whose last k-mer is L, in index order (all lanes; the seed of the reverse search used to scan all stretches on lane 0)
+  const WS& w = c.ws;
+  int nseed = 0;
+  DCU_NOUNROLL
+  for (int base = 0; base < c.nds; base += DCU_NL) {
+    const int s = base + lane;
+    const bool hit = s < c.nds && ds_last(c, s) == t.L;
+    const uint32_t hb = ballot(hit);
+    if (hit) w.dt_len()[nseed + popc(hb & lanemask_lt(lane))] = (uint16_t)s;      // scratch of derive_stretches, free again
+    nseed += popc(hb);
+  }
+  wsync();
+  if (lane == 0) reverse_paths(c, t.L, lmax, narp, nseed);
   c.overflow = bcast(c.overflow, 0); narp = bcast(narp, 0);
   wsync();
   t.narp = narp;
