@@ -893,19 +893,24 @@ DCU_FN int ds_first(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s]
 DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s] + c.ws.ds_len()[s] - 1]; }
 
 // sum over the instance list ip[0,f) of col[min(ip[t],MS) * NP] (one table column per lane, instance positions shared by
-// the warp): the warp fetches the positions with one coalesced load per 32 instances and hands them round by shuffle
-DCU_FN unsigned long long inst_colsum(const uint8_t* ip, int f, const unsigned long long* col, int NP, int MS, int lane) {
+// the warp): the warp fetches the positions with one coalesced load per 32 instances and hands them round by shuffle.
+// `mine0` is this lane's byte of the first 32 instances (ip[lane], 0 beyond f), loaded by the caller one link ahead.
+DCU_FN unsigned long long inst_colsum(int mine0, const uint8_t* ip, int f, const unsigned long long* col, int NP, int MS, int lane) {
   unsigned long long u = 0;
-#ifdef DCU_EMU
+#if DCU_NL == 1
   for (int t = 0; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += col[a * NP]; }
-  (void)lane;
+  (void)lane; (void)mine0;
 #else
+  // (also what the 32-lane emulations run: bcast is __shfl_sync on the GPU and a lane exchange there)
+  DCU_NOUNROLL
   for (int t0 = 0; t0 < f; t0 += 32) {
-    int mine = (t0 + lane < f) ? (int)ip[t0 + lane] : 0;
+    int mine = t0 == 0 ? mine0 : ((t0 + lane < f) ? (int)ip[t0 + lane] : 0);
     mine = mine < MS ? mine : MS;
     const int n = f - t0 < 32 ? f - t0 : 32;
+#ifndef DCU_EMU
 #pragma unroll 4
-    for (int t = 0; t < n; ++t) { int a = __shfl_sync(0xffffffffu, mine, t); u += col[a * NP]; }
+#endif
+    for (int t = 0; t < n; ++t) { int a = bcast(mine, t); u += col[a * NP]; }
   }
 #endif
   return u;
@@ -916,7 +921,18 @@ DCU_FN unsigned long long inst_colsum(const uint8_t* ip, int f, const unsigned l
 // position); slot weight < 0 marks "not feasible".
 // sp_view fills the slots of one view (off, L) of the link array: lanes over anchor positions; the link weights are evaluated
 // on the fly from the instance lists (all lanes share the node, so instance positions are uniform loads and only the table
-// column differs per lane).  Warp-uniform arguments.
+// column differs per lane).  Warp-uniform arguments.  The loop over the links is a chain of dependent loads from the workspace
+// (link -> node -> instance list offset -> instance bytes), each an L2 or HBM round trip, so it is software pipelined by hand:
+// the descriptors and instance bytes of link jj + 1 are requested before link jj is evaluated.
+struct SpLink { uint32_t ioF, ioR; int fF, fR, mF, mR; };
+DCU_FN SpLink sp_fetch(const WS& w, int off, int L, int jj, int lane) {
+  SpLink x;
+  const int nF = w.slinks()[off + jj], nR = w.slinks()[off + L - 1 - jj];
+  x.ioF = w.n_ioff()[nF]; x.fF = w.n_freq()[nF]; x.ioR = w.n_ioff()[nR]; x.fR = w.n_freq()[nR];
+  x.mF = lane < x.fF ? (int)w.ipos()[x.ioF + lane] : 0;
+  x.mR = lane < x.fR ? (int)w.irpos()[x.ioR + lane] : 0;
+  return x;
+}
 DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
   const WS& w = c.ws;
   const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
@@ -926,24 +942,26 @@ DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int
     const int q = q0 + lane;
     bool af = q < nf, ar = q < nr;
     double sumf = 0.0, sumr = 0.0, wfr = 0.0;
+    if (L <= 0) break;                               // (views have at least two links)
+    SpLink cur = sp_fetch(w, off, L, 0, lane);
     DCU_NOUNROLL
     for (int jj = 0; jj < L; ++jj) {
+      SpLink nxt = cur;
+      if (jj + 1 < L) nxt = sp_fetch(w, off, L, jj + 1, lane);      // in flight while this link is evaluated
       if (!ballot(af || ar)) break;
-      const int nF = w.slinks()[off + jj], nR = w.slinks()[off + L - 1 - jj];
       if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
         int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-        const uint8_t* ip = w.ipos() + w.n_ioff()[nF]; const int f = w.n_freq()[nF];
-        const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
+        const unsigned long long u = inst_colsum(cur.mF, w.ipos() + cur.ioF, cur.fF, VT + p, NP, MS, lane);
         double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
         if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
       }
       if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
         int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-        const uint8_t* ip = w.irpos() + w.n_ioff()[nR]; const int f = w.n_freq()[nR];
-        const unsigned long long u = inst_colsum(ip, f, VT + p, NP, MS, lane);
+        const unsigned long long u = inst_colsum(cur.mR, w.irpos() + cur.ioR, cur.fR, VT + p, NP, MS, lane);
         double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
         if (ar) { if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false; }
       }
+      cur = nxt;
     }
     if (q < nf) w.sf_w()[fO + q] = af ? sumf : -1.0;
     if (q < nr) { w.sc_w()[cO + q] = ar ? sumr : -1.0; w.sc_wf()[cO + q] = wfr; }
