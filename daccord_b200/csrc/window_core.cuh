@@ -284,8 +284,17 @@ DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
   const unsigned long long* col = c.vsq + p;
   int f = c.ws.n_freq()[n];
   unsigned long long u = 0;
+  const int MS = DCU_T.MS; const size_t NP = (size_t)DCU_T.NP;
+  int t = 0;
   DCU_NOUNROLL
-  for (int t = 0; t < f; ++t) { int pos = ip[t]; pos = pos < DCU_T.MS ? pos : DCU_T.MS; u += col[(size_t)pos * DCU_T.NP]; }
+  for (; t + 4 <= f; t += 4) {      // four instance bytes requested before the first is used (lane 0 runs this: every load is a full round trip)
+    int a0 = ip[t], a1 = ip[t + 1], a2 = ip[t + 2], a3 = ip[t + 3];
+    a0 = a0 < MS ? a0 : MS; a1 = a1 < MS ? a1 : MS; a2 = a2 < MS ? a2 : MS; a3 = a3 < MS ? a3 : MS;
+    const unsigned long long v0 = col[a0 * NP], v1 = col[a1 * NP], v2 = col[a2 * NP], v3 = col[a3 * NP];
+    u += v0; u += v1; u += v2; u += v3;
+  }
+  DCU_NOUNROLL
+  for (; t < f; ++t) { int pos = ip[t]; pos = pos < MS ? pos : MS; u += col[pos * NP]; }
   return (double)u * 2.3283064365386963e-10;
 }
 
@@ -1133,8 +1142,25 @@ DCU_NOINL int myers_dist(const unsigned long long* peq, int m, const uint8_t* t,
 }
 DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool ascii) {
   peq[0] = peq[1] = peq[2] = peq[3] = 0;
+  int i = 0;
+  if ((((size_t)pat) & 7) == 0) {                  // aligned pattern (candidate slots, the A slice): eight symbols per load
+    DCU_NOUNROLL
+    for (; i + 8 <= m; i += 8) {
+#ifdef DCU_EMU
+      unsigned long long wd; __builtin_memcpy(&wd, pat + i, 8);
+#else
+      const unsigned long long wd = *(const unsigned long long*)(pat + i);
+#endif
+      DCU_NOUNROLL
+      for (int b = 0; b < 8; ++b) {
+        int cde = (int)((wd >> (8 * b)) & 0xFF);
+        if (ascii) cde = (cde == 'A') ? 0 : (cde == 'C') ? 1 : (cde == 'G') ? 2 : 3;
+        peq[cde] |= 1ull << (i + b);
+      }
+    }
+  }
   DCU_NOUNROLL
-  for (int i = 0; i < m; ++i) {
+  for (; i < m; ++i) {
     int cde = pat[i];
     if (ascii) cde = (cde == 'A') ? 0 : (cde == 'C') ? 1 : (cde == 'G') ? 2 : 3;
     peq[cde] |= 1ull << i;
@@ -1282,6 +1308,21 @@ DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath 
   w.fp_pos()[id] = (uint16_t)(ppos + L - 1); w.fp_len()[id] = (uint16_t)(plen + 1); w.fp_baselen()[id] = (uint16_t)bl;
   return id;
 }
+// appends the symbols 1..L-1 of a stretch as ASCII (codes -> "ACGT" by shifts); four symbols are requested before the first is used.
+// Returns the new length or -1 when the candidate buffer is full.
+DCU_FN int decode_syms(const uint8_t* sym, int L, uint8_t* out, int o) {
+  if (o + (L > 1 ? L - 1 : 0) > MAXCAND) return -1;
+  int j = 1;
+  DCU_NOUNROLL
+  for (; j + 4 <= L; j += 4) {
+    const uint32_t s0 = sym[j], s1 = sym[j + 1], s2 = sym[j + 2], s3 = sym[j + 3];
+    out[o] = (uint8_t)(0x54474341u >> (8 * s0)); out[o + 1] = (uint8_t)(0x54474341u >> (8 * s1)); out[o + 2] = (uint8_t)(0x54474341u >> (8 * s2)); out[o + 3] = (uint8_t)(0x54474341u >> (8 * s3));
+    o += 4;
+  }
+  DCU_NOUNROLL
+  for (; j < L; ++j) out[o++] = (uint8_t)(0x54474341u >> (8 * (uint32_t)sym[j]));
+  return o;
+}
 // decodePathPair (:4267-4300) into ASCII; returns length or -1
 DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
   const WS& w = c.ws;
@@ -1295,14 +1336,14 @@ DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
   DCU_NOUNROLL
   for (int t = sp - 1; t >= 0; --t) {
     int s = stack[t], off = w.ds_off()[s], L = w.ds_len()[s];
-    DCU_NOUNROLL
-    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym()[off + j]]; }
+    o = decode_syms(w.slsym() + off, L, out, o);
+    if (o < 0) return -1;
   }
   DCU_NOUNROLL
   for (int q = rpid; w.rp_len()[q] > 0; q = (int)w.rp_parent()[q]) {
     int s = w.rp_stretch()[q], off = w.ds_off()[s], L = w.ds_len()[s];
-    DCU_NOUNROLL
-    for (int j = 1; j < L; ++j) { if (o >= MAXCAND) return -1; out[o++] = "ACGT"[w.slsym()[off + j]]; }
+    o = decode_syms(w.slsym() + off, L, out, o);
+    if (o < 0) return -1;
   }
   return o;
 }
