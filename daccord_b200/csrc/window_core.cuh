@@ -562,9 +562,15 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   {
     const int nraw = (int)w.koff()[c.MAo];
     DCU_NOUNROLL
+    // two dependent loads (slot -> node id) in front of an atomic round trip per instance: the node id of the lane's next instance is
+    // requested before this one is filed
+    int n = lane < nraw ? (int)(w.hs()[2 * w.islot()[lane] + 1] >> 16) : NID_NONE;
+    DCU_NOUNROLL
     for (int q = lane; q < nraw; q += DCU_NL) {
-      int n = (int)(w.hs()[2 * w.islot()[q] + 1] >> 16);
+      const int qn = q + DCU_NL;
+      const int nn1 = qn < nraw ? (int)(w.hs()[2 * w.islot()[qn] + 1] >> 16) : NID_NONE;
       if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill()[n], 1); w.ipos()[w.n_ioff()[n] + t] = w.praw()[q]; w.irpos()[w.n_ioff()[n] + t] = w.rraw()[q]; }
+      n = nn1;
     }
   }
   DCU_NOUNROLL
@@ -582,7 +588,14 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
       int f0 = w.n_freq()[n]; const uint8_t* ip = w.ipos() + w.n_ioff()[n]; const uint8_t* irp = w.irpos() + w.n_ioff()[n];
       int lo = 255, hi = 0, clo = 255, chi = 0;
       DCU_NOUNROLL
-      for (int t = 0; t < f0; ++t) { int a = ip[t], b = irp[t]; lo = a < lo ? a : lo; hi = a > hi ? a : hi; clo = b < clo ? b : clo; chi = b > chi ? b : chi; c0 += (a == 0); }
+      for (int t = 0; t < f0; t += 4) {                   // four instances per step: the eight loads are requested before the first is used
+        const int m1 = t + 1 < f0 ? t + 1 : t, m2 = t + 2 < f0 ? t + 2 : t, m3 = t + 3 < f0 ? t + 3 : t;      // past the end: instance t again (min / max unchanged)
+        const int a0 = ip[t], a1 = ip[m1], a2 = ip[m2], a3 = ip[m3], b0 = irp[t], b1 = irp[m1], b2 = irp[m2], b3 = irp[m3];
+        const int amin = (a0 < a1 ? a0 : a1) < (a2 < a3 ? a2 : a3) ? (a0 < a1 ? a0 : a1) : (a2 < a3 ? a2 : a3), amax = (a0 > a1 ? a0 : a1) > (a2 > a3 ? a2 : a3) ? (a0 > a1 ? a0 : a1) : (a2 > a3 ? a2 : a3);
+        const int bmin = (b0 < b1 ? b0 : b1) < (b2 < b3 ? b2 : b3) ? (b0 < b1 ? b0 : b1) : (b2 < b3 ? b2 : b3), bmax = (b0 > b1 ? b0 : b1) > (b2 > b3 ? b2 : b3) ? (b0 > b1 ? b0 : b1) : (b2 > b3 ? b2 : b3);
+        lo = amin < lo ? amin : lo; hi = amax > hi ? amax : hi; clo = bmin < clo ? bmin : clo; chi = bmax > chi ? bmax : chi;
+        c0 += (a0 == 0) + (t + 1 < f0 && a1 == 0) + (t + 2 < f0 && a2 == 0) + (t + 3 < f0 && a3 == 0);
+      }
       w.n_plow()[n] = (uint8_t)lo; w.n_phigh()[n] = (uint8_t)hi; w.n_cplow()[n] = (uint8_t)clo; w.n_cphigh()[n] = (uint8_t)chi;
     }
     uint32_t b = ballot(c0 > 0);               // k-mers seen at position 0 (maxForPosList :1280-1304)
