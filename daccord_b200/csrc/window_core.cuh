@@ -41,6 +41,7 @@ static long g_peak[16];
 #define DCU_BIG static
 #define DCU_MEM inline
 #define DCU_NOUNROLL
+#define DCU_UNROLL
 #define DCU_NOINL static inline
 #define DCU_CTOR
 #ifndef DCU_EMU_LANES
@@ -106,6 +107,7 @@ template <class T> static inline T ldg(const T* p) { return *p; }
 #define DCU_BIG __device__ __noinline__
 #define DCU_MEM __device__ __forceinline__
 #define DCU_NOUNROLL _Pragma("unroll 1")
+#define DCU_UNROLL _Pragma("unroll")
 #define DCU_NOINL __device__ __noinline__
 #define DCU_CTOR __device__
 #define DCU_NL 32
@@ -429,17 +431,22 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
 
 // claim / count one k-mer; newly claimed slots are appended to the occupancy list so that nothing ever scans or
 // clears the whole table (the slab is reused from window to window, only touched slots are reset)
-DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
+// `old` is what the compare-and-swap of v into slot h returned; follows the probe sequence from there
+DCU_FN uint32_t hash_insert_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t old) {
   const WS& w = c.ws;
-  uint32_t mask = (uint32_t)DCU_CAP.H - 1, h = hslot(c, v);
+  const uint32_t mask = (uint32_t)DCU_CAP.H - 1;
   DCU_NOUNROLL
   for (;;) {
-    uint32_t old = a_cas(&w.hs()[2 * h], W_EMPTY, v);
     if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate()[0], 1); w.occ()[t] = h; a_add(&w.hs()[2 * h + 1], 1); break; }
     if (old == v) { a_add(&w.hs()[2 * h + 1], 1); break; }
     h = (h + 1) & mask;
+    old = a_cas(&w.hs()[2 * h], W_EMPTY, v);
   }
   return h;
+}
+DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
+  const uint32_t h = hslot(c, v);
+  return hash_insert_from(c, v, h, a_cas(&c.ws.hs()[2 * h], W_EMPTY, v));
 }
 DCU_BIG void build_hash(Ctx& c, int lane) {
   const WS& w = c.ws;
@@ -484,12 +491,24 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
       uint32_t v = 0;
       DCU_NOUNROLL
       for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i0 + i];
-      DCU_NOUNROLL
-      for (int i = i0; i < i1; ++i) {
-        v = ((v << 2) & c.kmask) | u[i + c.k - 1];
-        uint32_t h = hash_insert(c, v);
-        const int q = (int)w.koff()[j] + i;
-        w.islot()[q] = h; w.praw()[q] = (uint8_t)i; w.rraw()[q] = (uint8_t)(len - i - c.k);
+      // the first compare-and-swap of every k-mer of the chunk is issued before any result is looked at (CH atomics in flight instead of
+      // one round trip after the other; at load <= 0.5 the first probe settles most k-mers), then the k-mers are completed in order
+      uint32_t kv[CH], kh[CH], ko[CH];
+      DCU_UNROLL
+      for (int e = 0; e < CH; ++e) {
+        kv[e] = 0; kh[e] = 0; ko[e] = 0;
+        if (i0 + e < i1) {
+          v = ((v << 2) & c.kmask) | u[i0 + e + c.k - 1];
+          kv[e] = v; kh[e] = hslot(c, v); ko[e] = a_cas(&w.hs()[2 * kh[e]], W_EMPTY, v);
+        }
+      }
+      const int q0 = (int)w.koff()[j] + i0;
+      DCU_UNROLL
+      for (int e = 0; e < CH; ++e) {
+        if (i0 + e < i1) {
+          const uint32_t h = hash_insert_from(c, kv[e], kh[e], ko[e]);
+          w.islot()[q0 + e] = h; w.praw()[q0 + e] = (uint8_t)(i0 + e); w.rraw()[q0 + e] = (uint8_t)(len - (i0 + e) - c.k);
+        }
       }
       if (i1 == numk) w.lastk()[j] = v;             // final k-mer of the sequence (the `last` array, :2108)
     }
