@@ -267,15 +267,34 @@ struct Ctx {
 
 // ------------------------------------------------------------------ small helpers
 DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - DCU_CAP.LOGH); }
-DCU_NOINL int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
-  uint32_t h = hslot(c, v), mask = (uint32_t)DCU_CAP.H - 1;
+// one 8-byte load per probe: (key, count | node id << 16)
+DCU_FN unsigned long long hs_slot(const Ctx& c, uint32_t h) {
+#ifdef DCU_EMU
+  unsigned long long sv; __builtin_memcpy(&sv, c.ws.hs() + 2 * h, 8); return sv;
+#else
+  return *(const unsigned long long*)(c.ws.hs() + 2 * h);
+#endif
+}
+DCU_FN int lookup_from(const Ctx& c, uint32_t v, uint32_t h, unsigned long long sv) {      // sv = slot h, already loaded
+  const uint32_t mask = (uint32_t)DCU_CAP.H - 1;
   DCU_NOUNROLL
   for (;;) {
-    uint32_t key = c.ws.hs()[2 * h];
-    if (key == v) return (int)(c.ws.hs()[2 * h + 1] >> 16);
+    const uint32_t key = (uint32_t)sv;
+    if (key == v) return (int)((uint32_t)(sv >> 32) >> 16);
     if (key == W_EMPTY) return NID_NONE;
     h = (h + 1) & mask;
+    sv = hs_slot(c, h);
   }
+}
+DCU_NOINL int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
+  const uint32_t h = hslot(c, v);
+  return lookup_from(c, v, h, hs_slot(c, h));
+}
+// the four neighbours of a k-mer: the home slots of all four are requested before the first is examined
+DCU_NOINL void lookup4(const Ctx& c, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, int* out) {
+  const uint32_t h0 = hslot(c, v0), h1 = hslot(c, v1), h2 = hslot(c, v2), h3 = hslot(c, v3);
+  const unsigned long long s0 = hs_slot(c, h0), s1 = hs_slot(c, h1), s2 = hs_slot(c, h2), s3 = hs_slot(c, h3);
+  out[0] = lookup_from(c, v0, h0, s0); out[1] = lookup_from(c, v1, h1, s1); out[2] = lookup_from(c, v2, h2, s2); out[3] = lookup_from(c, v3, h3, s3);
 }
 DCU_FN int sup_lo(const Ctx& c, int pos) { return pos < DCU_T.MS ? (int)ldg(DCU_T.suplo + pos) : DCU_T.NP; }   // OffsetLikely.hpp:34-37
 DCU_FN int sup_hi(const Ctx& c, int pos) { return pos < DCU_T.MS ? (int)ldg(DCU_T.suphi + pos) : DCU_T.NP; }   // OffsetLikely.hpp:39-43
@@ -637,10 +656,11 @@ DCU_BIG void compute_npred(Ctx& c, int lane) {
   for (int n = lane; n < c.nn; n += DCU_NL) {
     uint32_t v = w.n_kmer()[n];
     int cnt = 0;
+    int pn[4];
+    { const uint32_t b = (v >> 2) & c.kmask; lookup4(c, b, b | (1u << shift), b | (2u << shift), b | (3u << shift), pn); }
     DCU_NOUNROLL
     for (uint32_t s = 0; s < 4; ++s) {
-      uint32_t pv = ((v >> 2) & c.kmask) | (s << shift);
-      int p = lookup(c, pv);
+      int p = pn[s];
       if (p == NID_NONE) continue;
       int na = w.n_nact()[p];
       DCU_NOUNROLL
@@ -659,9 +679,11 @@ DCU_BIG void build_edges(Ctx& c, int lane) {
   for (int n = lane; n < c.nn; n += DCU_NL) {
     uint32_t v = w.n_kmer()[n];
     uint32_t key[4]; uint16_t nid[4]; int ns = 0;
+    int sn[4];
+    { const uint32_t b = (v << 2) & c.kmask; lookup4(c, b, b | 1u, b | 2u, b | 3u, sn); }
     DCU_NOUNROLL
     for (uint32_t s = 0; s < 4; ++s) {
-      int t = lookup(c, ((v << 2) & c.kmask) | s);
+      int t = sn[s];
       if (t != NID_NONE) { key[ns] = ((uint32_t)w.n_freq()[t] << 8) | s; nid[ns] = (uint16_t)t; ++ns; }
     }
     DCU_NOUNROLL
