@@ -245,6 +245,7 @@ enum {
 #undef X
   F_COUNT
 };
+static_assert(F_COUNT <= 128, "Layout::off holds 128 field offsets");
 // one warp's workspace: a slab base pointer; every SoA array is an accessor (base + layout offset)
 struct WS {
   uint8_t* base;
