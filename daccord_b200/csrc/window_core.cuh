@@ -1151,6 +1151,7 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
     int ln = ds_last(c, A);
     int b0 = w.n_dsf()[ln], bn = w.n_dsn()[ln];
     if (b0 == NID_NONE) continue;
+    const int aB = w.ds_cB()[A], aN = w.ds_cN()[A]; const uint32_t aO = w.ds_cO()[A];      // A's reverse slots (what sfo_rev(A, .) looks at), loaded once
     DCU_NOUNROLL
     for (int B = b0; B < b0 + bn; ++B) {
       int shift = w.ds_len()[B] - 1;
@@ -1158,10 +1159,11 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
       int cb = w.ds_cB()[B], cn = w.ds_cN()[B], co = w.ds_cO()[B];
       DCU_NOUNROLL
       for (int d = 0; d < cn; ++d) {
-        double wb = w.sc_w()[co + d];
-        if (!(wb >= 0.0)) continue;
-        int oa = sfo_rev(c, A, cb + d + shift);
-        if (oa >= 0) { double lw = wb + (w.sc_w()[oa] - w.sc_wf()[oa]); weight = lw > weight ? lw : weight; }
+        const int da = cb + d + shift - aB;
+        if (da < 0 || da >= aN) continue;
+        const double wb = w.sc_w()[co + d], wa = w.sc_w()[aO + da], wf = w.sc_wf()[aO + da];      // three independent loads
+        if (!(wb >= 0.0) || !(wa >= 0.0)) continue;
+        const double lw = wb + (wa - wf); weight = lw > weight ? lw : weight;
       }
       if (weight >= 1e-1) { uint32_t t = a_add(cnt, 1); if ((int)t < DCU_CAP.RL) w.rl()[t] = ((uint32_t)B << 16) | (uint32_t)A; }
     }
