@@ -260,6 +260,7 @@ struct Ctx {
   const unsigned long long* vsq;           // transposed VS table (shared-memory copy when it fits, else HBM)
   const uint8_t* packed; const Slice* sl;
   int MAo, nbases;
+  int logh;                                // this window's hash uses the first 2^logh slots of the table (st_begin)
   int k; uint32_t kmask; int kidx;
   int nn, ni, nex, nlast, nfirst;
   int nrs, slO, nds, nrl, kwtot;
@@ -267,7 +268,7 @@ struct Ctx {
 };
 
 // ------------------------------------------------------------------ small helpers
-DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - DCU_CAP.LOGH); }
+DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - c.logh); }
 // one 8-byte load per probe: (key, count | node id << 16)
 DCU_FN unsigned long long hs_slot(const Ctx& c, uint32_t h) {
 #ifdef DCU_EMU
@@ -277,7 +278,7 @@ DCU_FN unsigned long long hs_slot(const Ctx& c, uint32_t h) {
 #endif
 }
 DCU_FN int lookup_from(const Ctx& c, uint32_t v, uint32_t h, unsigned long long sv) {      // sv = slot h, already loaded
-  const uint32_t mask = (uint32_t)DCU_CAP.H - 1;
+  const uint32_t mask = (1u << c.logh) - 1u;
   DCU_NOUNROLL
   for (;;) {
     const uint32_t key = (uint32_t)sv;
@@ -465,7 +466,7 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
 // `old` is what the compare-and-swap of v into slot h returned; follows the probe sequence from there
 DCU_FN uint32_t hash_insert_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t old) {
   const WS& w = c.ws;
-  const uint32_t mask = (uint32_t)DCU_CAP.H - 1;
+  const uint32_t mask = (1u << c.logh) - 1u;
   DCU_NOUNROLL
   for (;;) {
     if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate()[0], 1); w.occ()[t] = h; a_add(&w.hs()[2 * h + 1], 1); break; }
@@ -1701,6 +1702,11 @@ DCU_BIG void st_begin(Ctx& c, WinState& s, const Window& win, int lane) {
   s.ph = PH_END;
   load_window(c, win, lane);
   if (c.overflow) { st_overflow(c, s); return; }
+  // hash size of this window: the smallest power of two above (k-mer instances + gap filler extras), so that a free slot always
+  // remains, instead of the batch-wide capacity: a 40x window then spreads its ~870 distinct k-mers over 2 048 slots (16 KB) and
+  // not over 8 192 (64 KB, one useful slot per touched 32-byte sector -- 42 % of all bytes a window touched, tools/field_traffic.py).
+  // Results do not depend on the table size (the two workspace tiers already differ in it).
+  { int lg = 5; const int need = c.nbases + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; }
   int elength = estimate_length(c, lane);
   res.elength = elength;
   if (c.MAo < DCU_P.mincov) return;

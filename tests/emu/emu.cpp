@@ -12,6 +12,10 @@
 #include <cstdlib>
 #include <chrono>
 
+#ifdef DCU_EMU_TRACE
+extern "C" void trace_begin_window(const uint8_t* base, uint64_t bytes, const uint32_t* off, int nfields);      // tests/emu/trace_rt.cpp
+extern "C" void trace_end_window();
+#endif
 extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
                              dcu_result* res, uint8_t* cons, uint8_t* ops, int tier, uint64_t* noverflow) {
   dcu_host::HostTables HT;
@@ -45,7 +49,13 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
     for (int q = 0; q < 16; ++q) { g_peak[q] = 0; dcu::g_phase_ns[q] = 0; dcu::g_phase_calls[q] = 0; }
     const auto t0 = std::chrono::steady_clock::now();
 #endif
+#ifdef DCU_EMU_TRACE
+    trace_begin_window(slab.data(), L.bytes, L.off, (int)dcu::F_COUNT);
+#endif
     dcu::process_window(c, W, r, cons + i * DCU_CONS_STRIDE, ops + i * DCU_OPS_STRIDE, 0);
+#ifdef DCU_EMU_TRACE
+    trace_end_window();
+#endif
 #ifdef DCU_EMU_STATS
     g_peak[9] = (long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();    // single-lane emulation time of the window
     if (const char* fn = getenv("DCU_FOOTPRINT_OUT")) {      // per-window peaks of the workspace counters (tools/footprint.py)
