@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 import numpy as np
 import pytest
 from common import (ROOT, default_params, synth_batch, run_oracle, run_emu, run_emu_lanes, run_emu_tsan, compare_results, get_tables, oracle_lib, emu_lib,
@@ -101,6 +102,27 @@ def test_no_race_between_lanes_under_thread_sanitizer(name, gen, kw):
     assert "ThreadSanitizer" not in report, report[:3000]
     bad = [i for i in compare_results(ro, (res, cons, ops)) if res[i]["status"] != 250]
     assert not bad, (name, bad[:5])
+
+
+def test_position_slot_cache_switch_changes_nothing():
+    """DCU_POSCACHE=0 (every (first,last) pair recomputes all unitig position slots, the round-1 behaviour) and the default (slots of unsplit
+    unitigs kept across the pairs of a traverse) give identical results on a repeat-rich shallow pile, where windows walk through many pairs."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np\n"
+            "from common import default_params, synth_batch, run_emu, run_emu_lanes\n"
+            "p = default_params(k_lo=7, k_hi=9)\n"
+            "packed, win, sl, _ = synth_batch(150, 10, seed=41, repeat_frac=0.6, depth_jitter=3, w=p.w)\n"
+            "r = run_emu(p, packed, win, sl, 1); l = run_emu_lanes(p, packed, win, sl, 1, 2, 5)\n"
+            "assert (r[0] == l[0]).all() and (r[1] == l[1]).all() and (r[2] == l[2]).all()\n"
+            "np.save(sys.argv[1], np.concatenate([r[0].view(np.uint8).ravel(), r[1], r[2]]))\n") % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for pc in ("0", "1"):
+            out = os.path.join(tmp, "r%s.npy" % pc)
+            subprocess.check_call([sys.executable, "-c", code, out], env=dict(os.environ, DCU_POSCACHE=pc))
+            outs.append(np.load(out))
+    assert (outs[0] == outs[1]).all()
 
 
 def test_edge_cases_empty_and_ragged():
