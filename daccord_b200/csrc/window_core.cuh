@@ -997,18 +997,10 @@ DCU_FN unsigned long long inst_colsum(int mine0, const uint8_t* ip, int f, const
 // position); slot weight < 0 marks "not feasible".
 // sp_view fills the slots of one view (off, L) of the link array: lanes over anchor positions; the link weights are evaluated
 // on the fly from the instance lists (all lanes share the node, so instance positions are uniform loads and only the table
-// column differs per lane).  Warp-uniform arguments.  The loop over the links is a chain of dependent loads from the workspace
-// (link -> node -> instance list offset -> instance bytes), each an L2 or HBM round trip, so it is software pipelined by hand:
-// the descriptors and instance bytes of link jj + 1 are requested before link jj is evaluated.
-struct SpLink { uint32_t ioF, ioR; int fF, fR, mF, mR; };
-DCU_FN SpLink sp_fetch(const WS& w, int off, int L, int jj, int lane) {
-  SpLink x;
-  const int nF = w.slinks()[off + jj], nR = w.slinks()[off + L - 1 - jj];
-  x.ioF = w.n_ioff()[nF]; x.fF = w.n_freq()[nF]; x.ioR = w.n_ioff()[nR]; x.fR = w.n_freq()[nR];
-  x.mF = lane < x.fF ? (int)w.ipos()[x.ioF + lane] : 0;
-  x.mR = lane < x.fR ? (int)w.irpos()[x.ioR + lane] : 0;
-  return x;
-}
+// column differs per lane).  Warp-uniform arguments.  The loop over the links used to be a chain of dependent loads from the
+// workspace per link (link -> node -> instance list offset -> instance bytes), each an L2 or HBM round trip.  Now the descriptors of up
+// to 32 links are fetched at once, lane t taking link j0 + t (two round trips for the whole chunk), the loop gets them by shuffle,
+// and the instance bytes of link jj + 1 are requested before link jj is evaluated.
 DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
   const WS& w = c.ws;
   const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
@@ -1018,26 +1010,41 @@ DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int
     const int q = q0 + lane;
     bool af = q < nf, ar = q < nr;
     double sumf = 0.0, sumr = 0.0, wfr = 0.0;
-    if (L <= 0) break;                               // (views have at least two links)
-    SpLink cur = sp_fetch(w, off, L, 0, lane);
+    bool live = true;
     DCU_NOUNROLL
-    for (int jj = 0; jj < L; ++jj) {
-      SpLink nxt = cur;
-      if (jj + 1 < L) nxt = sp_fetch(w, off, L, jj + 1, lane);      // in flight while this link is evaluated
-      if (!ballot(af || ar)) break;
-      if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
-        int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-        const unsigned long long u = inst_colsum(cur.mF, w.ipos() + cur.ioF, cur.fF, VT + p, NP, MS, lane);
-        double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
-        if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
+    for (int j0 = 0; j0 < L && live; j0 += DCU_NL) {
+      // descriptors of the links j0 .. j0 + 31: lane t holds link j0 + t (forward node of link jj, reverse node of link L - 1 - jj)
+      uint32_t dioF = 0, dioR = 0; int dfF = 0, dfR = 0;
+      if (j0 + lane < L) {
+        const int nF = w.slinks()[off + j0 + lane], nR = w.slinks()[off + L - 1 - (j0 + lane)];
+        dioF = w.n_ioff()[nF]; dfF = w.n_freq()[nF]; dioR = w.n_ioff()[nR]; dfR = w.n_freq()[nR];
       }
-      if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
-        int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-        const unsigned long long u = inst_colsum(cur.mR, w.irpos() + cur.ioR, cur.fR, VT + p, NP, MS, lane);
-        double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
-        if (ar) { if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false; }
+      const int jn = L - j0 < DCU_NL ? L - j0 : DCU_NL;
+      uint32_t ioF = bcast(dioF, 0), ioR = bcast(dioR, 0); int fF = bcast(dfF, 0), fR = bcast(dfR, 0);
+      int mF = lane < fF ? (int)w.ipos()[ioF + lane] : 0, mR = lane < fR ? (int)w.irpos()[ioR + lane] : 0;
+      DCU_NOUNROLL
+      for (int t = 0; t < jn; ++t) {
+        const int jj = j0 + t;
+        uint32_t nioF = ioF, nioR = ioR; int nfF = fF, nfR = fR, nmF = mF, nmR = mR;
+        if (t + 1 < jn) {                              // next link: descriptors by shuffle, instance bytes in flight while this link is evaluated
+          nioF = bcast(dioF, t + 1); nfF = bcast(dfF, t + 1); nioR = bcast(dioR, t + 1); nfR = bcast(dfR, t + 1);
+          nmF = lane < nfF ? (int)w.ipos()[nioF + lane] : 0; nmR = lane < nfR ? (int)w.irpos()[nioR + lane] : 0;
+        }
+        if (!ballot(af || ar)) { live = false; break; }
+        if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
+          int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
+          const unsigned long long u = inst_colsum(mF, w.ipos() + ioF, fF, VT + p, NP, MS, lane);
+          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
+          if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
+        }
+        if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
+          int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
+          const unsigned long long u = inst_colsum(mR, w.irpos() + ioR, fR, VT + p, NP, MS, lane);
+          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
+          if (ar) { if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false; }
+        }
+        ioF = nioF; fF = nfF; mF = nmF; ioR = nioR; fR = nfR; mR = nmR;
       }
-      cur = nxt;
     }
     if (q < nf) w.sf_w()[fO + q] = af ? sumf : -1.0;
     if (q < nr) { w.sc_w()[cO + q] = ar ? sumr : -1.0; w.sc_wf()[cO + q] = wfr; }
