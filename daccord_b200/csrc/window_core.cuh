@@ -347,7 +347,7 @@ DCU_NOINL void heap_pop(bool MAXH, double* hw, uint32_t* hi, int& n) {
 // ------------------------------------------------------------------ load: slices -> base codes
 // replaces DecodedReadContainer + the MA array (HandleContext.hpp:2032-2043); bases as codes 0..3
 DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   c.MAo = win.slice_cnt; c.overflow = 0;
   if (c.MAo > DCU_CAP.S) { c.overflow = 1; return; }
   const Slice* sl = c.sl + win.slice_begin;
@@ -398,7 +398,7 @@ DCU_FN int seqlen(const Ctx& c, int j) { return c.ws.soff()[j + 1] - c.ws.soff()
 
 // ------------------------------------------------------------------ expected length (HandleContext.hpp:2051-2155)
 DCU_BIG int estimate_length(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int maxv = -1;
   if (c.MAo) {
     int mn = 0x7fffffff, mx = -0x7fffffff;
@@ -447,7 +447,7 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
 // sort a short (count, kmer[, node]) list descending by (count, kmer) -- std::greater on pairs (:1297-1301, :1384-1388);
 // k-mers are distinct, so the rank of an entry is the number of larger entries: lanes over entries
 DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, int n, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   DCU_NOUNROLL
   for (int e = lane; e < n; e += DCU_NL) {
     uint32_t k = km[e]; uint16_t cc = cn[e]; int r = 0;
@@ -465,7 +465,7 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
 // clears the whole table (the slab is reused from window to window, only touched slots are reset)
 // `old` is what the compare-and-swap of v into slot h returned; follows the probe sequence from there
 DCU_FN uint32_t hash_insert_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t old) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   const uint32_t mask = (1u << c.logh) - 1u;
   DCU_NOUNROLL
   for (;;) {
@@ -481,7 +481,7 @@ DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
   return hash_insert_from(c, v, h, a_cas(&c.ws.hs()[2 * h], W_EMPTY, v));
 }
 DCU_BIG void build_hash(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   if (w.hstate()[1] != 0x600DF00Du) {          // first use of this slab: full initialisation
     DCU_NOUNROLL
     for (int i = lane; i < DCU_CAP.H; i += DCU_NL) { w.hs()[2 * i] = W_EMPTY; w.hs()[2 * i + 1] = 0xFFFF0000u; }
@@ -571,7 +571,7 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
 
 // nodes = k-mers with count >= f (filterFreq :1181-1197), instance lists (setupNodes :1918-2014)
 DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int nn = 0;
   const int nocc = (int)w.hstate()[0];
   DCU_PEAK(14, nocc);
@@ -663,7 +663,7 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
 
 // active predecessors (:2552-2597): p->v is active iff v is among p's first nact successors
 DCU_BIG void compute_npred(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int shift = 2 * (c.k - 1);
   DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
@@ -685,7 +685,7 @@ DCU_BIG void compute_npred(Ctx& c, int lane) {
 }
 // successor lists + primary activation (setNodesActive :1770-1814 / setupAddHeap :1818-1859)
 DCU_BIG void build_edges(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int no = c.MAo < DCU_T.KLIMN ? c.MAo : DCU_T.KLIMN - 1;
   unsigned long long lim = DCU_P.check ? ldg(DCU_T.klim + (size_t)c.kidx * DCU_T.KLIMN + no) : 0;
   DCU_NOUNROLL
@@ -721,7 +721,7 @@ DCU_BIG void build_edges(Ctx& c, int lane) {
 }
 // addNextFromHeap (:1861-1897): activate every pending edge of the highest pending frequency
 DCU_BIG bool add_next(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   uint32_t top = 0;
   DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) { int na = w.n_nact()[n]; if (na < w.n_nsucc()[n]) { uint32_t f = w.n_sfreq()[4 * n + na]; top = f > top ? f : top; } }
@@ -745,7 +745,7 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
 // materialised here; the weights themselves (:3826-3904) are fixed-point sums evaluated where they are consumed
 // (stretch_positions, kw_fwd / kw_rev).
 DCU_BIG void node_ranges(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   DCU_NOUNROLL
   for (int n = lane; n < c.nn; n += DCU_NL) {
     int pf = sup_lo(c, w.n_plow()[n]), pt = sup_hi(c, w.n_phigh()[n]);
@@ -761,7 +761,7 @@ DCU_NOINL double kw_rev(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_
 
 // ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
 DCU_BIG void gap_fill(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   uint32_t* nexp = &w.n_fill()[0];      // n_fill[0] doubles as the append counter here (rebuilt afterwards)
   if (lane == 0) *nexp = 0;
   wsync();
@@ -814,7 +814,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
 // predecessor checks on, a walk can only close a loop by coming back to its own start (any other revisited node
 // would have two active predecessors and end the walk before), so loop detection is a comparison with the start.
 DCU_BIG void raw_stretches(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int nrs = 0, slO = 0; bool ovf = false;
   DCU_NOUNROLL
   for (int base = 0; base < c.nn; base += DCU_NL) {
@@ -893,7 +893,7 @@ DCU_BIG void warp_sort_u32(uint32_t* a, int P, int lane) {
 // one splitStretches pass (:2772-2841) on views: in (n views) -> out; every view with an interior occurrence of
 // node v becomes two views.  Returns the new count (order is irrelevant, the result is sorted afterwards).
 DCU_BIG int split_pass(Ctx& c, const uint16_t* ioff, const uint16_t* ilen, int n, uint16_t* ooff, uint16_t* olen, int v, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int base = 0;
   DCU_NOUNROLL
   for (int b0 = 0; b0 < n; b0 += DCU_NL) {
@@ -918,7 +918,7 @@ DCU_BIG int split_pass(Ctx& c, const uint16_t* ioff, const uint16_t* ilen, int n
 // splitStretches(first), splitStretches(last), stretchesUnique (:3087-3114): sort by (first, ext, len desc) and keep
 // the first view per (first, ext); equal (first, ext, len) implies identical content, so `last` never decides.
 DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int n = split_pass(c, w.rs_off(), w.rs_len(), c.nrs, w.dt_off(), w.dt_len(), F, lane);
   if (n > DCU_CAP.ST) { c.overflow = 8; return; }
   n = split_pass(c, w.dt_off(), w.dt_len(), n, w.du_off(), w.du_len(), L, lane);
@@ -1130,13 +1130,13 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
   wsync();
 }
 DCU_NOINL int sfo_fwd(const Ctx& c, int s, int p) {     // getCachedStretchPositionWeight (:3906-3918)
-  const WS& w = c.ws; int d = p - (int)w.ds_fB()[s];
+  const WS w = c.ws; int d = p - (int)w.ds_fB()[s];
   if (d < 0 || d >= (int)w.ds_fN()[s]) return -1;
   int o = w.ds_fO()[s] + d;
   return w.sf_w()[o] >= 0.0 ? o : -1;
 }
 DCU_NOINL int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchReversePositionWeight (:3920-3932)
-  const WS& w = c.ws; int d = p - (int)w.ds_cB()[s];
+  const WS w = c.ws; int d = p - (int)w.ds_cB()[s];
   if (d < 0 || d >= (int)w.ds_cN()[s]) return -1;
   int o = w.ds_cO()[s] + d;
   return w.sc_w()[o] >= 0.0 ? o : -1;
@@ -1150,7 +1150,7 @@ DCU_FN double rev_wf(const Ctx& c, int s, int p) { return kw_rev(c, ds_last(c, s
 // computeStretchLinks / getReverseStretchLinkWeight (:3388-3480): link A -> B (B.first == A.last) kept iff
 // max over common reverse positions of w_B + (w_A - wf_A) >= 0.1; stored as (B,A), sorted; lanes over A
 DCU_BIG void stretch_links(Ctx& c, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   uint32_t* cnt = &w.n_fill()[0];
   if (lane == 0) *cnt = 0;
   wsync();
@@ -1247,7 +1247,7 @@ DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool as
 struct TravOut { int nacc; };
 
 DCU_NOINL int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t front, int stretch, int pos, int len, int baselen) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   DCU_PEAK(8, nrp + 1);
   if (nrp >= DCU_CAP.RP) { c.overflow = 11; return -1; }
   int id = nrp++;
@@ -1258,7 +1258,7 @@ DCU_NOINL int rp_new(Ctx& c, int& nrp, double wgt, uint32_t parent, uint32_t fro
 
 // reverse half-paths (prepareTraverse :3576-3757); lane 0
 DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp, int nseed) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int nrp = 0, nq = 0; narp = 0;
   DCU_NOUNROLL
   for (int i = 0; i < DCU_CAP.BL; ++i) w.arph_n()[i] = 0;
@@ -1314,7 +1314,7 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp, int nseed) {
 }
 // sort accepted reverse paths by (front, baselen), ties in acceptance order (:3742, convention C7); all lanes
 DCU_BIG void sort_reverse_paths(Ctx& c, int narp, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   // arp_k[i] = (front << 8) | baselen and arp_wt[i] = weight of the i-th accepted path in sorted order: the forward search finds its
   // pairing range by two binary searches on arp_k and scans weights in arp_wt, instead of chasing arp[i] -> rp_front / rp_baselen / rp_w
   if (narp <= 1) {
@@ -1338,7 +1338,7 @@ DCU_BIG void sort_reverse_paths(Ctx& c, int narp, int lane) {
 }
 
 DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScore (:3482-3497)
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int ls = w.fp_stretch()[P];
   int lpos = w.fp_pos()[P] - (w.ds_len()[ls] - 1);
   int o = sfo_fwd(c, ls, lpos);
@@ -1347,7 +1347,7 @@ DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScor
 }
 // best / next-best reverse path of an interval in (weight, sorted index) order (:3499-3534)
 DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int best = -1; double bw = 0;
   const double* wt = w.arp_wt();
   double cw = cur >= 0 ? wt[cur] : 0;
@@ -1360,7 +1360,7 @@ DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
   return best;
 }
 DCU_NOINL void apq_push(Ctx& c, int pid) {                        // :4843-4862, :4997-5017
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int bl = w.fp_baselen()[pid];
   if (bl >= DCU_CAP.BL) return;                                  // longer than lmax: never pairs, never extends
   double* hw = w.apq_w() + bl * HEAPK; uint32_t* hi = w.apq_id() + bl * HEAPK; int n = w.apq_n()[bl];
@@ -1370,7 +1370,7 @@ DCU_NOINL void apq_push(Ctx& c, int pid) {                        // :4843-4862,
   w.apq_n()[bl] = (uint8_t)n;
 }
 DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath (:3989-4056); P == -1 -> empty path
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int ppos = P < 0 ? 0 : w.fp_pos()[P], plen = P < 0 ? 0 : w.fp_len()[P];
   int o = sfo_fwd(c, s, ppos);
   int L = w.ds_len()[s];
@@ -1401,7 +1401,7 @@ DCU_FN int decode_syms(const uint8_t* sym, int L, uint8_t* out, int o) {
 }
 // decodePathPair (:4267-4300) into ASCII; returns length or -1
 DCU_BIG int decode_pair(const Ctx& c, int P, int rpid, uint8_t* out) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int stack[MAXCAND]; int sp = 0;
   DCU_NOUNROLL
   for (int q = P; q >= 0; q = (w.fp_parent()[q] == IDX_NONE ? -1 : (int)w.fp_parent()[q])) { if (sp >= MAXCAND) return -1; stack[sp++] = w.fp_stretch()[q]; }
@@ -1531,7 +1531,7 @@ DCU_BIG void trav_start(Ctx& c, TravState& t, int lane) {
 #ifdef DCU_EMU_STATS
   g_stats[6]++;
 #endif
-  const WS& w = c.ws;
+  const WS w = c.ws;
   if (lane == 0) w.spc()[0] = 0;                     // new unitigs: the cached position slots are stale (raw_stretches ends with a wsync)
   raw_stretches(c, lane);
   t.ncdh = 0; t.freeslots = (1u << (CDH_N + 1)) - 1;
@@ -1542,7 +1542,7 @@ DCU_BIG void trav_start(Ctx& c, TravState& t, int lane) {
 // moves (fi, li) to the next pair whose last k-mer is a node (:3582: no reverse seed otherwise => the pair cannot
 // produce candidates and its forward search has no side effects); returns false when the pairs are exhausted
 DCU_BIG bool trav_seek(Ctx& c, TravState& t) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   DCU_NOUNROLL
   for (;;) {
     if (!(t.fi < c.nfirst && w.fl_cnt()[t.fi] >= t.firstthres)) return false;
@@ -1554,7 +1554,7 @@ DCU_BIG bool trav_seek(Ctx& c, TravState& t) {
 // one (first,last) pair at (fi, li), then advances li  (:4802-5097), in two halves so that the kernel can put a barrier between
 // the lane-parallel graph work (trav_pair_graph) and the single-lane searches (trav_pair_search)
 DCU_BIG void trav_pair_graph(Ctx& c, TravState& t, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   t.F = w.fl_nid()[t.fi];
   t.L = lookup(c, w.ll_kmer()[t.li]);
   t.li += 1;
@@ -1572,7 +1572,7 @@ DCU_BIG void trav_pair_weights(Ctx& c, int lane) {
 DCU_BIG void trav_pair_rpaths(Ctx& c, TravState& t, int lmax, int lane) {
   int narp = 0;
   // stretches whose last k-mer is L, in index order (all lanes; the seed of the reverse search used to scan all stretches on lane 0)
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int nseed = 0;
   DCU_NOUNROLL
   for (int base = 0; base < c.nds; base += DCU_NL) {
@@ -1602,7 +1602,7 @@ DCU_BIG void trav_pair_search(Ctx& c, TravState& t, int lmin, int lmax, int lane
 }
 // CDH -> CH -> ACC (descending weight, heap tie order), candidate errors, stable sort by error (:5101-5156)
 DCU_BIG int trav_finish(Ctx& c, TravState& t, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   int ncdh = t.ncdh;
   int nacc = 0;
   if (lane == 0) {
@@ -1644,7 +1644,7 @@ DCU_BIG int trav_finish(Ctx& c, TravState& t, int lane) {
 // ------------------------------------------------------------------ placement: align(A window, consensus) with traceback
 // (HandleContext.hpp:2434-2493); convention C1 via bit-vector deltas.  lane 0.  Returns number of ops.
 DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int lb, uint8_t* ops) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   unsigned long long peq[4];
   make_peq(peq, a, la, false);            // a = base codes
   unsigned long long pv = ~0ull, mv = 0;
@@ -1768,7 +1768,7 @@ DCU_FN void st_after_tries(WinState& s, bool lconsok) {
 // PH_SCORE scores the candidates and takes the decision of the try loop
 // (:2274-2322: up to 3 tries, next edge frequency class in between)
 DCU_BIG void st_trav_done(Ctx& c, WinState& s, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   TravState& t = s.tv;
   int nacc = trav_finish(c, t, lane);
   if (nacc > 0) {
@@ -1817,7 +1817,7 @@ DCU_BIG void st_search(Ctx& c, WinState& s, int lane) {
 }
 DCU_BIG void st_score(Ctx& c, WinState& s, int lane) { st_trav_done(c, s, lane); }
 DCU_BIG void st_final(Ctx& c, WinState& s, uint8_t* cons_out, uint8_t* ops_out, int lane) {
-  const WS& w = c.ws;
+  const WS w = c.ws;
   Result& res = s.res;
   s.ph = PH_END;
   if (s.pathfailed) { res.status = ST_FAILED; return; }
