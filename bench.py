@@ -270,10 +270,11 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     ach = (alg_bytes * args.steps) / tsec / 1e9           # this rank's kernel: algorithmic GB/s
-    traffic = None
+    traffic = None; traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = tj["dram_bytes_per_window"] * att
+        traffic_src = "%d B / window x windows of the launch; %s" % (tj["dram_bytes_per_window"], tj.get("source", ""))
     except Exception:
         pass
     value = att_t * args.steps / tsec
@@ -288,7 +289,7 @@ def main():
                                                                    "h2d_bytes_per_step": int((ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes) * world), "d2h_bytes_per_step": int(full_d2h * world),
                                                                    "fasta_identical_to_host_vote": full_same}),
                 gpu_launches=int(launches_t), hard_windows=int(hard_t),
-                roofline={"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                roofline={"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                           "peak_source": peak_src, "bytes_per_window": alg_bytes / max(att, 1),
                           "note": "integer / latency bound path (SURVEY 8d): the HBM fraction is reported as the contract asks, see DESIGN.md for the instruction-issue analysis"},
                 clocks=sampler.summary(), wall_s_timed=wall)
