@@ -90,3 +90,21 @@ def test_errors_are_loud():
     with pytest.raises(d.DcuError):
         d.Engine(d.Params.default(w=100), 0)   # unsupported window size
     e.close()
+
+
+def test_position_slot_cache_switch_changes_nothing_on_the_gpu(monkeypatch):
+    """DCU_POSCACHE=0 (all unitig position slots recomputed for every (first,last) pair) against the default (slots of unsplit unitigs kept across
+    the pairs of a traverse), on a repeat-rich shallow pile whose windows walk through many pairs: identical to each other and to the oracle."""
+    p = default_params(k_lo=7, k_hi=9)
+    packed, win, sl, _ = synth_batch(600, 10, seed=141, repeat_frac=0.6, depth_jitter=3)
+    ro = run_oracle(p, packed, win, sl, 8)
+    out = []
+    for pc in ("0", "1"):
+        monkeypatch.setenv("DCU_POSCACHE", pc)       # read by dcu_create
+        e = _engine(p)
+        e.set_reads(packed)
+        out.append(e.run(win, sl))
+        e.close()
+    assert not compare_results(ro, out[0])
+    assert not compare_results(ro, out[1])
+    assert not compare_results(out[0], out[1])
