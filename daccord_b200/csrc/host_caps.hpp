@@ -4,6 +4,7 @@
 // A window that overflows tier 0 is re-run in tier 1; one that overflows tier 1 is reported as an error.
 #pragma once
 #include "window_core.cuh"
+#include <cstdlib>
 namespace dcu_host {
 inline int ceil_pow2_log(int v) { int l = 4; while ((1 << l) < v) ++l; return l; }
 inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
@@ -16,7 +17,11 @@ inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
   c.H = 1 << c.LOGH;
   c.BL = w + 8;
   c.HEAVY = 0;
-  if (tier == 0) {
+  if (tier == 0 && getenv("DCU_T0_SMALL")) {
+    // measurement knob (tools/round2_first_run.sh): first-pass capacities near the p99.9 of the 40x bench workload instead of 5x above it.
+    // The slab of a warp then spans ~1/4 of the address range (fewer 2 MB pages live per SM), at the price of more windows for the second pass.
+    c.NN = 1024; c.ST = 512; c.SL = 2048; c.SF = 6144; c.RL = 512; c.RP = 512; c.FP = 512; c.SI = 512; c.KW = 2; c.HEAVY = 0;
+  } else if (tier == 0) {
     c.NN = 4096; c.ST = 1024; c.SL = 8192; c.SF = 16384; c.RL = 2048; c.RP = 2048; c.FP = 2048; c.SI = 2048; c.KW = 2; c.HEAVY = 0;       // HEAVY > 0 hands graphs with more nodes to the free-running pass (measured: no gain, profiles/r01_summary.md)
   } else {
     c.NN = c.NI + c.EX; if (c.NN > 65000) c.NN = 65000;

@@ -18,6 +18,8 @@ done
 DCU_DEFER_FF=1 python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_defer_1.json; line gpurun_out/r2_defer_1.json "defer=1"
 # 4. resident warps per SM against the L2 (4 736 workspaces of ~64-100 KB do not fit 126 MB): 1 block of 16 warps per SM
 DCU_BLOCKS_PER_SM=1 python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_bps_1.json; line gpurun_out/r2_bps_1.json "blocks_per_sm=1"
+# 4b. first-pass capacities near the workload's p99.9 (slab 399 KB instead of 950 KB per warp: fewer live 2 MB pages per SM, more second-pass windows)
+DCU_T0_SMALL=1 python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_t0small.json; line gpurun_out/r2_t0small.json "t0_small=1"
 # 5. hard configurations the cache was written for (tools/kernel_bench.py: synthetic windows, device-timed)
 for pc in 1 0; do DCU_POSCACHE=$pc python tools/kernel_bench.py 10 20 2>&1 | tail -1 | sed "s/^/poscache=$pc depth10 /"; done
 # 6. launch list of the bench command with the new piling kernels
