@@ -128,6 +128,28 @@ def test_position_slot_cache_switch_changes_nothing():
     assert (outs[0] == outs[1]).all()
 
 
+def test_trace_runtime_attributes_workspace_accesses():
+    """tests/emu/trace_rt.cpp (a stand-in for the TSan runtime that attributes every workspace access to its field; tools/field_traffic.py):
+    results unchanged under instrumentation, and the hash table, the instance bytes and the unitig slots all show up with plausible byte counts."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("field_traffic", os.path.join(ROOT, "tools", "field_traffic.py"))
+    ft = importlib.util.module_from_spec(spec); spec.loader.exec_module(ft)
+    lib = C.CDLL(ft.build()); lib.trace_report.restype = C.c_uint64
+    p = default_params()
+    packed, win, sl, _ = synth_batch(40, 30, seed=71, repeat_frac=0.1, depth_jitter=3, w=p.w)
+    from common import alloc_out, _ptr
+    res, cons, ops = alloc_out(len(win)); nov = C.c_uint64(0)
+    assert lib.emu_run_batch(C.byref(p), _ptr(packed), _ptr(win), C.c_uint64(len(win)), _ptr(sl), _ptr(res), _ptr(cons), _ptr(ops), C.c_int(0), C.byref(nov)) == 0
+    ro = run_oracle(p, packed, win, sl, 4)
+    assert not compare_results(ro, (res, cons, ops))
+    names = [n for n, _ in ft.field_names()]
+    rep = np.zeros(4 * len(names), np.uint64)
+    n = lib.trace_report(_ptr(rep), C.c_int(len(names)))
+    assert n == len(win)
+    per = dict(zip(names, rep.reshape(-1, 4)[:, 2].astype(np.float64) * 32 / n))
+    assert 5000 < per["hs"] < 60000 and per["ipos"] > 100 and per["sf_w"] > 1000 and 20000 < sum(per.values()) < 300000, per
+
+
 def test_edge_cases_empty_and_ragged():
     p = default_params()
     packed, win, sl, _ = synth_batch(30, 6, seed=31)
