@@ -6,6 +6,9 @@ mkdir -p gpurun_out
 # 1. the whole GPU suite: the per-window piling kernels, the 32-bit unitig slot offsets, the position-slot cache and the binary-search
 #    pairing range went in after the last GPU run (emulation parity only: single lane, 32 lanes under adversarial schedules, TSan)
 timeout 500 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest=$?"; tail -3 gpurun_out/r2_pytest_gpu.log
+# 1b. memcheck of a small mixed batch through every kernel: the changes made without a GPU include 8-byte slot / pattern loads and
+#     new workspace fields (alignment and bounds are what the host emulations cannot see)
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/r2_memcheck.log 2>&1; echo "memcheck=$?"; grep -c "Invalid\|out of bounds\|misaligned" gpurun_out/r2_memcheck.log; tail -2 gpurun_out/r2_memcheck.log
 line() { python -c "import json,sys; l=json.load(open(sys.argv[1])); print(sys.argv[2], 'value %.3f e2e %.3f from_overlaps %.3f to_fasta %.3f hard %d' % (l['value']/1e6, l['e2e']['value']/1e6, l['e2e_from_overlaps']['value']/1e6, l['e2e_overlaps_to_fasta']['value']/1e6, l['hard_windows']))" "$1" "$2"; }
 # 2. A/B of the position-slot cache (profiles/r01_summary.md) on the bench workload at 40x and 20x
 for pc in 1 0; do
