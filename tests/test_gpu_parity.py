@@ -108,3 +108,19 @@ def test_position_slot_cache_switch_changes_nothing_on_the_gpu(monkeypatch):
     assert not compare_results(ro, out[0])
     assert not compare_results(ro, out[1])
     assert not compare_results(out[0], out[1])
+
+
+def test_small_first_pass_capacities(monkeypatch):
+    """DCU_T0_SMALL=1 shrinks the first-pass workspace to about the p99.9 of a clean 40x pile (slab 399 KB instead of 950 KB per warp); on a deep
+    small-k repeat-rich batch a few windows overflow it and take the large-workspace launch: the results are still the oracle's."""
+    p = default_params(k_lo=6, k_hi=6)
+    packed, win, sl, _ = synth_batch(400, 60, seed=151, repeat_frac=0.6, depth_jitter=3)
+    ro = run_oracle(p, packed, win, sl, 8)
+    monkeypatch.setenv("DCU_T0_SMALL", "1")          # read by the host when the batch is uploaded
+    e = _engine(p)
+    e.set_reads(packed)
+    rg = e.run(win, sl)
+    st = e.stats()
+    e.close()
+    assert not compare_results(ro, rg)
+    assert st["launches"] >= 1
