@@ -24,6 +24,7 @@ DCU_BLOCKS_PER_SM=1 python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 
 # 4b. first-pass capacities near the workload's p99.9 (slab 399 KB instead of 950 KB per warp: fewer live 2 MB pages per SM, more second-pass windows)
 DCU_T0_SMALL=1 python bench.py --mb 20 --steps 3 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_t0small.json; line gpurun_out/r2_t0small.json "t0_small=1"
 # 4c. group size at 20x again: the cache removes most of the heavy tail that made small groups win on shallow piles (profiles/r01_summary.md, sync-group sweep)
+for g in 16 8 1; do DCU_SYNC_GROUP=$g python bench.py --mb 5 --coverage 10 --steps 2 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_group_${g}_cov10.json; line gpurun_out/r2_group_${g}_cov10.json "sync_group=$g coverage=10"; done
 for g in 16 8 1; do DCU_SYNC_GROUP=$g python bench.py --mb 10 --coverage 20 --steps 2 --warmup 2 --cpu-sample-s 0 2>/dev/null > gpurun_out/r2_group_${g}_cov20.json; line gpurun_out/r2_group_${g}_cov20.json "sync_group=$g coverage=20"; done
 # 5. hard configurations the cache was written for (tools/kernel_bench.py: synthetic windows, device-timed)
 for pc in 1 0; do DCU_POSCACHE=$pc python tools/kernel_bench.py 10 20 2>&1 | tail -1 | sed "s/^/poscache=$pc depth10 /"; done
