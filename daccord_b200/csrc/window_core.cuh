@@ -464,7 +464,7 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
 // claim / count one k-mer; newly claimed slots are appended to the occupancy list so that nothing ever scans or
 // clears the whole table (the slab is reused from window to window, only touched slots are reset)
 // `old` is what the compare-and-swap of v into slot h returned; follows the probe sequence from there
-DCU_FN uint32_t hash_insert_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t old) {
+DCU_NOINL uint32_t hash_insert_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t old) {
   const WS w = c.ws;
   const uint32_t mask = (1u << c.logh) - 1u;
   DCU_NOUNROLL
