@@ -114,7 +114,7 @@ def test_position_slot_cache_switch_changes_nothing():
             "import numpy as np\n"
             "from common import default_params, synth_batch, run_emu, run_emu_lanes\n"
             "p = default_params(k_lo=7, k_hi=9)\n"
-            "packed, win, sl, _ = synth_batch(150, 10, seed=41, repeat_frac=0.6, depth_jitter=3, w=p.w)\n"
+            "packed, win, sl, _ = synth_batch(80, 10, seed=41, repeat_frac=0.6, depth_jitter=3, w=p.w)\n"
             "r = run_emu(p, packed, win, sl, 1); l = run_emu_lanes(p, packed, win, sl, 1, 2, 5)\n"
             "assert (r[0] == l[0]).all() and (r[1] == l[1]).all() and (r[2] == l[2]).all()\n"
             "np.save(sys.argv[1], np.concatenate([r[0].view(np.uint8).ravel(), r[1], r[2]]))\n") % (ROOT, os.path.join(ROOT, "tests"))
