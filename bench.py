@@ -197,11 +197,11 @@ def main():
         eng.launch()
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    kms, launches, hard = 0.0, 0, 0
+    kms, launches, hard, second = 0.0, 0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         kms += eng.launch()                 # CUDA-event time of the launch(es) on the engine's stream
-        st = eng.stats(); launches += st["launches"]; hard += st["hard_windows"]
+        st = eng.stats(); launches += st["launches"]; hard += st["hard_windows"]; second += st["second_pass_windows"]
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
@@ -288,7 +288,7 @@ def main():
                 e2e_overlaps_to_fasta=(None if not full_wall else {"value": att_t * args.steps / full_wall_max, "unit": "windows/s", "what": "dcu_pile + launch + dcu_vote (pile vote on the GPU): overlaps in, corrected bases out",
                                                                    "h2d_bytes_per_step": int((ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes) * world), "d2h_bytes_per_step": int(full_d2h * world),
                                                                    "fasta_identical_to_host_vote": full_same}),
-                gpu_launches=int(launches_t), hard_windows=int(hard_t),
+                gpu_launches=int(launches_t), hard_windows=int(hard_t), second_pass_windows=int(second), smem_pass={"warps_per_sm": st["smem_warps"], "bytes_per_warp": st["smem_bytes_per_warp"]},
                 roofline={"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                           "peak_source": peak_src, "bytes_per_window": alg_bytes / max(att, 1),
                           "note": "integer / latency bound path (SURVEY 8d): the HBM fraction is reported as the contract asks, see DESIGN.md for the instruction-issue analysis"},

@@ -143,7 +143,9 @@ class Engine:
     def stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._ck(self.lib.dcu_last_stats(self.ctx, C.byref(a), C.byref(b)))
-        return {"launches": a.value, "hard_windows": b.value}
+        c, d = C.c_uint64(0), C.c_uint64(0); e, f = C.c_uint32(0), C.c_uint32(0)
+        self._ck(self.lib.dcu_last_stats2(self.ctx, C.byref(c), C.byref(d), C.byref(e), C.byref(f)))
+        return {"launches": a.value, "hard_windows": b.value, "second_pass_windows": c.value, "lost_windows": d.value, "smem_warps": e.value, "smem_bytes_per_warp": f.value}
 
     def tables(self, which):
         n = self.lib.dcu_get_tables(self.ctx, C.c_int(which), None, C.c_int64(0))

@@ -10,7 +10,10 @@
 #include <vector>
 #include <algorithm>
 #include <new>
-#include "window_core.cuh"
+#include "window_core.cuh"            // namespace dcu : every workspace field in the warp's HBM slab (overflow passes, deep piles)
+#define DCU_NS dcus
+#define DCU_TIER_SMEM 1
+#include "window_core.cuh"            // namespace dcus: hot fields in the warp's shared-memory arena (first pass)
 #include "host_tables.hpp"
 #include "host_caps.hpp"
 #include "pile_host.hpp"
@@ -22,8 +25,9 @@ static_assert(sizeof(dvote::Win) == sizeof(dcu_window) && sizeof(dvote::Res) == 
 
 namespace {
 
-constexpr int WPB = 16;                // warps per block (one 32-warp block per SM with whole-block barriers measured 5 % slower, profiles/r01_summary.md)
-constexpr int BPS = 2;                 // resident blocks per SM the kernel is compiled for (64 registers / thread)
+constexpr int WPB = 16;                // warps per block of the HBM passes
+constexpr int BPS = 2;                 // resident blocks per SM the HBM kernel is compiled for (64 registers / thread)
+constexpr int SWPB = 16;               // most warps per block of the shared-memory pass (one block per SM, 128 registers / thread)
 
 struct KArgs {
   const uint8_t* packed; const dcu::Slice* sl; const dcu::Window* win;
@@ -31,13 +35,46 @@ struct KArgs {
   uint8_t* slabs;                      // [total warps][layout bytes]
   const uint32_t* todo;                // window indices to run (nullptr: 0..n-1)
   uint32_t n; uint32_t vs_words;       // vs_words != 0: stage the VS table in dynamic shared memory
-  int sync_group;                      // warps per phase-synchronous group (1 = free running, WPB = whole block)
+  int sync_group;                      // warps per phase-synchronous group (1 = free running)
   int sync_mask;                       // inner stage boundaries that are barriers
   unsigned int* ticket;                // work counter
-  unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this tier
+  unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this pass
+  unsigned long long packed_bytes;     // readable bytes of the packed database (staging never reads beyond)
+  int stage;                           // shared-memory pass: stage the slices of the next window with cp.async.bulk
 };
 
-// layout, capacities, table descriptors and parameters are in __constant__ memory (window_core.cuh), set per launch
+// One persistent launch per pass.  Every warp owns one window at a time and walks it through the stages of window_core.cuh; the
+// warps of a group (named barriers) run the same stage at the same time, which keeps the instruction caches effective
+// (profiles/r01_summary.md).  NS = dcu (HBM workspace) or dcus (hot fields in shared memory, slices staged by bulk copies).
+#define DCU_STAGE_LOOP(NS, FINAL_HOOK)                                                                                          \
+    if (G == 1) alldone = idle;                                                                                                 \
+    else {                                                                                                                      \
+      if (lane == 0) s_done[par][warp] = idle ? 1 : 0;                                                                          \
+      gsync();                                                                                                                  \
+      alldone = true;                                                                                                           \
+      for (int i = 0; i < G; ++i) alldone = alldone && (s_done[par][gfirst + i] != 0);                                          \
+    }                                                                                                                           \
+    if (alldone) break;                                                                                                         \
+    if (st.ph == NS::PH_HASH) NS::st_hash(c, st, lane);                                                                         \
+    if (smask & 1) gsync();                                                                                                     \
+    if (st.ph == NS::PH_NODES) NS::st_nodes(c, st, lane);                                                                       \
+    if (smask & 32) gsync();                                                                                                    \
+    if (st.ph == NS::PH_EDGES) NS::st_edges(c, st, lane);                                                                       \
+    if (smask & 2) gsync();                                                                                                     \
+    if (st.ph == NS::PH_TRAV) NS::st_trav(c, st, lane);                                                                         \
+    if (smask & 16) gsync();                                                                                                    \
+    if (st.ph == NS::PH_POS) NS::st_pos(c, st, lane);                                                                           \
+    if (smask & 4) gsync();                                                                                                     \
+    if (st.ph == NS::PH_RPATH) NS::st_rpath(c, st, lane);                                                                       \
+    if (smask & 64) gsync();                                                                                                    \
+    if (st.ph == NS::PH_SEARCH) NS::st_search(c, st, lane);                                                                     \
+    if (smask & 128) gsync();                                                                                                   \
+    if (st.ph == NS::PH_SCORE) NS::st_score(c, st, lane);                                                                       \
+    if (smask & 8) gsync();                                                                                                     \
+    if (st.ph == NS::PH_FINAL) { FINAL_HOOK; NS::st_final(c, st, a.cons + (size_t)wi * DCU_CONS_STRIDE, a.ops + (size_t)wi * DCU_OPS_STRIDE, lane); } \
+    if (st.ph == NS::PH_END && !idle) { publish(); __syncwarp(); }
+
+// ---- HBM build: layout, capacities, table descriptors and parameters in __constant__ memory (dcu::c_*), set per launch
 __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ unsigned long long s_vs[];          // block-shared copy of the transposed VS table (when it fits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -46,63 +83,127 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
   c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcu::c_layout.bytes;
   c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq;
   c.packed = a.packed; c.sl = a.sl;
-  // phase-synchronous execution: every warp owns one window at a time and walks it through the stages of
-  // window_core.cuh; warps are tied into groups of `sync_group` warps by named barriers so that the warps of a group
-  // run the same stage's code at the same time (instruction-cache locality) without waiting on the whole block
   __shared__ int s_done[2][WPB];                       // double buffered: with a single barrier per round a fast warp must not overwrite what a slow one still reads
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
   auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
   const int smask = a.sync_mask;                       // which of the inner stage boundaries are barriers (bit 0: hash|nodes, 5: nodes|edges, 1: edges|trav, 4: trav|pos, 2: pos|rpath, 6: rpath|search, 7: search|score, 3: score|final)
   dcu::WinState st; st.ph = dcu::PH_END;
-  uint32_t wi = 0; bool done = false; int par = 0;
+  uint32_t wi = 0; bool nomore = false; int par = 0;
+  auto publish = [&]() {
+    if (lane == 0) {
+      a.res[wi] = st.res;
+      if (st.res.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
+    }
+  };
   for (;; par ^= 1) {
-    // stage 0: finish / fetch
-    while (!done && st.ph == dcu::PH_END) {
+    while (!nomore && st.ph == dcu::PH_END) {          // finish / fetch
       unsigned int t = 0;
       if (lane == 0) t = atomicAdd(a.ticket, 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
-      if (t >= a.n) { done = true; break; }
+      if (t >= a.n) { nomore = true; break; }
       wi = a.todo ? a.todo[t] : t;
       dcu::Window W = a.win[wi];
-      dcu::st_begin(c, st, W, lane);
-      if (st.ph == dcu::PH_END && lane == 0) {         // skipped or overflowed right away
-        a.res[wi] = st.res;
-        if (st.res.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
-      }
+      dcu::st_begin(c, st, W, lane, nullptr);
+      if (st.ph == dcu::PH_END) publish();             // skipped or overflowed right away
     }
-    if (lane == 0) s_done[par][warp] = (done && st.ph == dcu::PH_END) ? 1 : 0;
-    gsync();
-    bool alldone = true;
-    for (int i = 0; i < G; ++i) alldone = alldone && (s_done[par][gfirst + i] != 0);
-    if (alldone) break;
-    if (st.ph == dcu::PH_HASH) dcu::st_hash(c, st, lane);
-    if (smask & 1) gsync();
-    if (st.ph == dcu::PH_NODES) dcu::st_nodes(c, st, lane);
-    if (smask & 32) gsync();
-    if (st.ph == dcu::PH_EDGES) dcu::st_edges(c, st, lane);
-    if (smask & 2) gsync();
-    if (st.ph == dcu::PH_TRAV) dcu::st_trav(c, st, lane);
-    if (smask & 16) gsync();
-    if (st.ph == dcu::PH_POS) dcu::st_pos(c, st, lane);
-    if (smask & 4) gsync();
-    if (st.ph == dcu::PH_RPATH) dcu::st_rpath(c, st, lane);
-    if (smask & 64) gsync();
-    if (st.ph == dcu::PH_SEARCH) dcu::st_search(c, st, lane);
-    if (smask & 128) gsync();
-    if (st.ph == dcu::PH_SCORE) dcu::st_score(c, st, lane);
-    if (smask & 8) gsync();
-    if (st.ph == dcu::PH_FINAL) dcu::st_final(c, st, a.cons + (size_t)wi * DCU_CONS_STRIDE, a.ops + (size_t)wi * DCU_OPS_STRIDE, lane);
-    if (st.ph == dcu::PH_END && !done) {
-      // window finished in this round (final stage, or an overflow inside a stage): publish
-      if (lane == 0) {
-        a.res[wi] = st.res;
-        if (st.res.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
-      }
-      __syncwarp();
-    }
+    const bool idle = st.ph == dcu::PH_END;
+    bool alldone;
+    DCU_STAGE_LOOP(dcu, (void)0)
   }
 }
 
+// ---- shared-memory build: dynamic shared memory = [transposed VS table | one arena per warp]; the packed bytes of the next
+// window's slices are copied into the (then idle) pre-filter bitmap region of the arena by cp.async.bulk, completion on a
+// per-warp mbarrier, while the current window is placed
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(SWPB * 32, 1) dcus_window_kernel(const __grid_constant__ KArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t vs_bytes = (a.vs_words * 8u + 127u) & ~127u;
+  {
+    unsigned long long* s_vs = (unsigned long long*)dcus::dcu_smem;
+    for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = dcus::c_T.VSq[i];
+  }
+  __shared__ int s_done[2][SWPB];
+  __shared__ __align__(8) unsigned long long s_mbar[SWPB];
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[warp])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  dcus::Ctx c;
+  c.ws.base = a.slabs + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)dcus::c_layout.bytes;
+  c.ws.sm = vs_bytes + (uint32_t)warp * dcus::c_layout.sbytes;
+  c.vsq = a.vs_words ? (const unsigned long long*)dcus::dcu_smem : dcus::c_T.VSq;
+  c.packed = a.packed; c.sl = a.sl;
+  const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
+  auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
+  const int smask = a.sync_mask;
+  dcus::WinState st; st.ph = dcus::PH_END;
+  uint32_t wi = 0; bool nomore = false; int par = 0;
+  // staging state: pf = 0 nothing claimed, 1 window pfwi claimed and its slices in flight / landed, 2 claimed but not staged (direct loads)
+  int pf = 0; uint32_t pfwi = 0, mpar = 0;
+  uint8_t* const raw = dcus::dcu_smem + c.ws.sm + dcus::c_layout.off[dcus::F_hbA];
+  const uint32_t rawcap = dcus::c_layout.off[dcus::F_hstate] - dcus::c_layout.off[dcus::F_hbA];
+  const uint32_t mbar = smem_u32(&s_mbar[warp]);
+  auto publish = [&]() {
+    if (lane == 0) {
+      a.res[wi] = st.res;
+      if (st.res.status == dcus::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
+    }
+  };
+  // claims the next window and starts the copies of its slices; the chunk offsets are the ones load_window recomputes
+  auto claim = [&]() {
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= a.n) { nomore = true; return; }
+    pfwi = a.todo ? a.todo[t] : t;
+    pf = 2;
+    if (!a.stage) return;
+    const dcu::Window W = a.win[pfwi];
+    const int n = W.slice_cnt;
+    if (n == 0 || n > dcus::c_cap.S) return;
+    const dcu::Slice* sl = a.sl + W.slice_begin;
+    uint32_t total = 0; bool ok = true;
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + lane; uint32_t stt = 0, cb = 0;
+      if (j < n) { dcus::slice_chunk(sl[j], stt, cb); if ((unsigned long long)stt + cb > a.packed_bytes) ok = false; }
+      total += __reduce_add_sync(0xffffffffu, cb);
+    }
+    if (__ballot_sync(0xffffffffu, !ok) || total == 0 || total > rawcap) return;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the region was last written through the generic proxy (bitmaps)
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(total), "r"(mbar) : "memory");
+    __syncwarp();
+    uint32_t run = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + lane; uint32_t stt = 0, cb = 0;
+      if (j < n) dcus::slice_chunk(sl[j], stt, cb);
+      const uint32_t inc = dcus::scan_incl(cb, lane);
+      if (cb) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(smem_u32(raw + run + inc - cb)), "l"(a.packed + stt), "r"(cb), "r"(mbar) : "memory");
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    pf = 1;
+  };
+  for (;; par ^= 1) {
+    while (st.ph == dcus::PH_END) {                    // finish / fetch
+      if (pf == 0) { if (nomore) break; claim(); if (pf == 0) break; }
+      const uint8_t* rawp = nullptr;
+      if (pf == 1) {                                   // wait for the bytes
+        asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(mbar), "r"(mpar) : "memory");
+        mpar ^= 1u; rawp = raw;
+      }
+      pf = 0; wi = pfwi;
+      dcu::Window W = a.win[wi];
+      dcus::st_begin(c, st, W, lane, rawp);
+      if (st.ph == dcus::PH_END) publish();            // skipped or overflowed right away
+    }
+    const bool idle = st.ph == dcus::PH_END;
+    bool alldone;
+    DCU_STAGE_LOOP(dcus, if (pf == 0 && !nomore) claim())
+  }
+}
 
 // ---------------------------------------------------------------- piling kernels (pile_core.cuh), one thread per item
 // ---- scan helpers shared by the piling and vote stages: one value per thread, SCAN_TPB threads per block
@@ -245,16 +346,17 @@ struct dcu_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0, blocks_per_sm[2] = {BPS, 1}; int sync_group = WPB; int sync_group_env = 0;
+  int use_smem = 1; int smem_optin = 0;             // first pass in shared memory (DCU_NO_SMEM=1 turns it off); opt-in shared memory per block
   // tables
   DevBuf<double> dDPn, dDPsq; DevBuf<unsigned long long> dVSq, dklim; DevBuf<uint16_t> dsuplo, dsuphi;
   // database
-  DevBuf<uint8_t> dpacked_own; const uint8_t* dpacked = nullptr; uint64_t packed_bytes = 0;
+  DevBuf<uint8_t> dpacked_own; const uint8_t* dpacked = nullptr; uint64_t packed_bytes = 0, packed_padded = 0;     // packed_padded: bytes that may be read (staging copies whole 16-byte chunks)
   // batch
   DevBuf<dcu::Window> dwin; DevBuf<dcu::Slice> dsl; DevBuf<dcu::Result> dres; DevBuf<uint8_t> dcons, dops;
-  DevBuf<uint32_t> dovf[2]; DevBuf<unsigned int> dcnt;     // dcnt: [ticket0, ovf0, ticket1, ovf1]
-  DevBuf<uint8_t> dslab[2];
+  DevBuf<uint32_t> dovf[3]; DevBuf<unsigned int> dcnt;     // dcnt: [ticket, overflows] of the passes at 0 (HBM first), 2 (HBM large), 8 (shared memory); 4..7 piling / vote
+  DevBuf<uint8_t> dslab[3];
   dcu::Caps caps[2]; dcu::Layout lay[2]; int grid[2] = {0, 0};
-  dcu::Caps slab_caps[2] = {}; uint32_t slab_bytes[2] = {0, 0};
+  dcu::Caps capsS{}; dcus::Layout layS{}; int warpsS = 0;   // shared-memory pass: capacities, layout, warps per block
   uint64_t nwin = 0, nsl = 0; int maxS = 0, maxB = 0;
   // piling scratch
   DevBuf<dpile::Ovl> dpo; DevBuf<dpile::ReadInfo> dpr; DevBuf<uint32_t> dprid, dptile, dpbm, dprlen; DevBuf<uint64_t> dpboff; DevBuf<uint16_t> dptrace;
@@ -262,7 +364,7 @@ struct dcu_ctx {
   // vote scratch and results
   DevBuf<uint16_t> dvent; DevBuf<uint8_t> dvflag; DevBuf<uint64_t> dvblk; DevBuf<char> dvchars; DevBuf<dvote::Read> dvreads; DevBuf<dvote::Bound> dvbound;
   std::vector<dcu_segment> segs; uint64_t nchars = 0; bool results_valid = false;
-  uint64_t launches = 0, hard = 0;
+  uint64_t launches = 0, hard = 0, second = 0, lost = 0;     // second: windows the shared-memory pass handed on; hard: windows of the large-workspace pass; lost: beyond every capacity
   std::string err;
 };
 
@@ -313,7 +415,9 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   ctx->P.w = (int)p->w; ctx->P.k_lo = (int)p->k_lo; ctx->P.k_hi = (int)p->k_hi; ctx->P.minff = p->min_ff; ctx->P.maxff = p->max_ff;
   ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err; ctx->P.defer_ff = 0;
   { const char* e = getenv("DCU_POSCACHE"); ctx->P.poscache = e ? atoi(e) : 1; }
-  CK(ctx->dcnt.ensure(8));
+  CK(ctx->dcnt.ensure(16));
+  { const char* e2 = getenv("DCU_NO_SMEM"); ctx->use_smem = (e2 && atoi(e2)) ? 0 : 1; }
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   const char* e = getenv("DCU_BLOCKS_PER_SM");
   if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);
   e = getenv("DCU_SYNC_GROUP");
@@ -329,7 +433,7 @@ void dcu_destroy(dcu_ctx* ctx) {
   ctx->dpacked_own.release(); ctx->dwin.release(); ctx->dsl.release(); ctx->dres.release(); ctx->dcons.release(); ctx->dops.release();
   ctx->dpo.release(); ctx->dpr.release(); ctx->dprid.release(); ctx->dptile.release(); ctx->dpbm.release(); ctx->dprlen.release();
   ctx->dpboff.release(); ctx->dptrace.release(); ctx->dpmin.release(); ctx->dpdiv.release(); ctx->dpact.release(); ctx->dpcnt.release(); ctx->dpblkw.release(); ctx->dpblks.release();
-  ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release();
+  ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dovf[2].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release(); ctx->dslab[2].release();
   ctx->dvent.release(); ctx->dvflag.release(); ctx->dvblk.release(); ctx->dvchars.release(); ctx->dvreads.release(); ctx->dvbound.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -341,17 +445,18 @@ int dcu_set_reads(dcu_ctx* ctx, const uint8_t* packed, uint64_t nbytes) {
   if (!ctx || !packed) return DCU_ERR_PARAM;
   if (nbytes >= (1ull << 30)) { ctx->err = "database larger than 2^32 bases"; return DCU_ERR_UNSUPPORTED; }
   CK(cudaSetDevice(ctx->device));
-  CK(ctx->dpacked_own.ensure(nbytes + 16));
+  CK(ctx->dpacked_own.ensure(nbytes + 64));
   CK(cudaMemcpyAsync(ctx->dpacked_own.p, packed, nbytes, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemsetAsync(ctx->dpacked_own.p + nbytes, 0, 16, ctx->stream));
+  CK(cudaMemsetAsync(ctx->dpacked_own.p + nbytes, 0, 64, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->dpacked = ctx->dpacked_own.p; ctx->packed_bytes = nbytes;
+  ctx->dpacked = ctx->dpacked_own.p; ctx->packed_bytes = nbytes; ctx->packed_padded = (nbytes + 48) & ~(uint64_t)15;
   return DCU_OK;
 }
 int dcu_set_reads_device(dcu_ctx* ctx, const void* dpacked, uint64_t nbytes) {
   if (!ctx || !dpacked) return DCU_ERR_PARAM;
   if (nbytes >= (1ull << 30)) { ctx->err = "database larger than 2^32 bases"; return DCU_ERR_UNSUPPORTED; }
-  ctx->dpacked = (const uint8_t*)dpacked; ctx->packed_bytes = nbytes;
+  ctx->dpacked = (const uint8_t*)dpacked; ctx->packed_bytes = nbytes; ctx->packed_padded = nbytes & ~(uint64_t)15;     // a caller's buffer: whole 16-byte chunks inside it only
+  if (((uintptr_t)dpacked & 15) != 0) ctx->packed_padded = 0;      // unaligned buffer: no staging (direct loads)
   return DCU_OK;
 }
 
@@ -369,7 +474,18 @@ static int finish_batch(dcu_ctx* ctx, int maxS, int maxB, uint64_t totS, uint64_
   { const char* e = getenv("DCU_HEAVY_NN"); if (e) ctx->caps[0].HEAVY = atoi(e); if (ctx->sync_group == 1) ctx->caps[0].HEAVY = 0; }   // free-running batches keep heavy windows in place
   CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
   CK(ctx->dcons.ensure((nwin + 1) * DCU_CONS_STRIDE)); CK(ctx->dops.ensure((nwin + 1) * DCU_OPS_STRIDE));
-  CK(ctx->dovf[0].ensure(nwin + 1)); CK(ctx->dovf[1].ensure(nwin + 1));
+  CK(ctx->dovf[0].ensure(nwin + 1)); CK(ctx->dovf[1].ensure(nwin + 1)); CK(ctx->dovf[2].ensure(nwin + 1));
+  {   // shared-memory pass: as many warps per SM as the arenas of this batch's capacities allow
+    ctx->capsS = dcu_host::make_caps_smem((int)ctx->prm.w, maxS, maxB); dcus::make_layout(ctx->capsS, ctx->layS);
+    size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
+    if (vs_bytes > 40 * 1024) vs_bytes = 0;
+    vs_bytes = (vs_bytes + 127) & ~(size_t)127;
+    const size_t avail = (size_t)ctx->smem_optin - 1024 - vs_bytes;     // static: barrier flags, mbarriers
+    int wps = (int)(avail / ctx->layS.sbytes);
+    if (wps > SWPB) wps = SWPB;
+    { const char* e = getenv("DCU_S_WARPS"); if (e && atoi(e) > 0 && atoi(e) < wps) wps = atoi(e); }
+    ctx->warpsS = wps;
+  }
   ctx->nwin = nwin; ctx->nsl = nsl; ctx->results_valid = false;
   return DCU_OK;
 }
@@ -433,7 +549,7 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
   dpile::Params prm; prm.tspace = tspace; prm.w = ctx->prm.w; prm.a = advance; prm.maxalign = maxalign;
   CK(ctx->dpo.ensure(novl + 1)); CK(ctx->dpr.ensure(nr + 1)); CK(ctx->dprid.ensure(nr + 1)); CK(ctx->dptile.ensure(P.ntiles + 1)); CK(ctx->dpbm.ensure(P.nbm + 1));
   CK(ctx->dprlen.ensure(nreads + 1)); CK(ctx->dpboff.ensure(nreads + 1)); CK(ctx->dptrace.ensure(ntrace + 1));
-  CK(ctx->dpmin.ensure(nr + 1)); CK(ctx->dpdiv.ensure(nr + 1)); CK(ctx->dpact.ensure(novl + 1)); CK(ctx->dcnt.ensure(8));
+  CK(ctx->dpmin.ensure(nr + 1)); CK(ctx->dpdiv.ensure(nr + 1)); CK(ctx->dpact.ensure(novl + 1)); CK(ctx->dcnt.ensure(16));
   cudaStream_t st = ctx->stream;
   if (novl) CK(cudaMemcpyAsync(ctx->dpo.p, P.ovl.data(), novl * sizeof(dpile::Ovl), cudaMemcpyHostToDevice, st));
   if (ntrace) CK(cudaMemcpyAsync(ctx->dptrace.p, trace, ntrace * 2, cudaMemcpyHostToDevice, st));
@@ -494,20 +610,20 @@ int dcu_get_windows(dcu_ctx* ctx, dcu_window* win, dcu_slice* sl) {
   return DCU_OK;
 }
 
+static void fill_args(dcu_ctx* ctx, KArgs& a, int cnt_at, int list, const uint32_t* todo, uint32_t n) {
+  a.packed = ctx->dpacked; a.sl = ctx->dsl.p; a.win = ctx->dwin.p; a.res = ctx->dres.p; a.cons = ctx->dcons.p; a.ops = ctx->dops.p;
+  a.todo = todo; a.n = n;
+  a.ticket = ctx->dcnt.p + cnt_at; a.ovf_cnt = ctx->dcnt.p + cnt_at + 1; a.ovf_list = ctx->dovf[list].p;
+  a.packed_bytes = ctx->packed_padded; a.stage = 0;
+  { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 15; }
+}
+// HBM passes: tier 0 (first overflow pass, or the first pass when the shared-memory pass is off), tier 1 (large workspaces, free running)
 static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n) {
   int bps = ctx->blocks_per_sm[tier];
   int grid = ctx->num_sms * bps;
   size_t need_blocks = ((size_t)n + WPB - 1) / WPB;
   if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
-  {
-    size_t need = (size_t)grid * WPB * ctx->lay[tier].bytes;
-    bool fresh = need > ctx->dslab[tier].cap || ctx->slab_bytes[tier] != ctx->lay[tier].bytes || memcmp(&ctx->slab_caps[tier], &ctx->caps[tier], sizeof(dcu::Caps)) != 0;
-    CK(ctx->dslab[tier].ensure(need));
-    if (fresh) {      // a zeroed slab is how a warp recognises that its hash table still has to be initialised
-      CK(cudaMemsetAsync(ctx->dslab[tier].p, 0, ctx->dslab[tier].cap, ctx->stream));
-      ctx->slab_bytes[tier] = ctx->lay[tier].bytes; ctx->slab_caps[tier] = ctx->caps[tier];
-    }
-  }
+  CK(ctx->dslab[tier].ensure((size_t)grid * WPB * ctx->lay[tier].bytes));
   KArgs a;
   CK(cudaMemcpyToSymbolAsync(dcu::c_layout, &ctx->lay[tier], sizeof(dcu::Layout), 0, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyToSymbolAsync(dcu::c_cap, &ctx->caps[tier], sizeof(dcu::Caps), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -518,14 +634,12 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
     P.defer_ff = (tier == 0 && ctx->sync_group > 1 && getenv("DCU_DEFER_FF")) ? 1 : 0;
     CK(cudaMemcpyToSymbolAsync(dcu::c_P, &P, sizeof(dcu::Params), 0, cudaMemcpyHostToDevice, ctx->stream));
   }
-  a.packed = ctx->dpacked; a.sl = ctx->dsl.p; a.win = ctx->dwin.p; a.res = ctx->dres.p; a.cons = ctx->dcons.p; a.ops = ctx->dops.p;
-  a.slabs = ctx->dslab[tier].p; a.todo = todo; a.n = n;
-  a.ticket = ctx->dcnt.p + 2 * tier; a.ovf_cnt = ctx->dcnt.p + 2 * tier + 1; a.ovf_list = ctx->dovf[tier].p;
+  fill_args(ctx, a, 2 * tier, tier, todo, n);
+  a.slabs = ctx->dslab[tier].p;
   size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
   if (vs_bytes > 40 * 1024 || getenv("DCU_VS_GLOBAL")) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);
   a.sync_group = tier ? 1 : ctx->sync_group;       // the large-workspace pass only sees heavy-tailed windows: free running
-  { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 15; }
   {   // leave as much of the 228 KB as possible to L1: the kernel lives on cached scratch data (measured +5 %, profiles/r01_summary.md)
     int pct = (int)((bps * (vs_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
     const char* e = getenv("DCU_CARVEOUT");
@@ -537,40 +651,80 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   ctx->launches++;
   return DCU_OK;
 }
+// shared-memory pass: one block of warpsS warps per SM, dynamic shared memory = VS table + warpsS arenas
+static int launch_smem(dcu_ctx* ctx, uint32_t n) {
+  const int wps = ctx->warpsS;
+  int grid = ctx->num_sms;
+  size_t need_blocks = ((size_t)n + wps - 1) / wps;
+  if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
+  CK(ctx->dslab[2].ensure((size_t)grid * wps * ctx->layS.bytes));
+  CK(cudaMemcpyToSymbolAsync(dcus::c_layout, &ctx->layS, sizeof(dcus::Layout), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(dcus::c_cap, &ctx->capsS, sizeof(dcu::Caps), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(dcus::c_T, &ctx->T, sizeof(dcu::Tables), 0, cudaMemcpyHostToDevice, ctx->stream));
+  { dcu::Params P = ctx->P; P.defer_ff = 0; ctx->Pl[0] = P; CK(cudaMemcpyToSymbolAsync(dcus::c_P, &ctx->Pl[0], sizeof(dcu::Params), 0, cudaMemcpyHostToDevice, ctx->stream)); }
+  KArgs a;
+  fill_args(ctx, a, 8, 2, nullptr, n);
+  a.slabs = ctx->dslab[2].p;
+  size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
+  if (vs_bytes > 40 * 1024) vs_bytes = 0;
+  a.vs_words = (uint32_t)(vs_bytes / 8);
+  vs_bytes = (vs_bytes + 127) & ~(size_t)127;
+  { int g = ctx->sync_group_env ? ctx->sync_group_env : wps; while (g > 1 && wps % g) --g; a.sync_group = g; }      // groups must tile the block
+  { const char* e = getenv("DCU_STAGE"); a.stage = e ? atoi(e) : 1; }
+  const size_t dyn = vs_bytes + (size_t)wps * ctx->layS.sbytes;
+  CK(cudaFuncSetAttribute(dcus_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  dcus_window_kernel<<<grid, wps * 32, dyn, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return DCU_OK;
+}
 
 int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
   if (!ctx) return DCU_ERR_PARAM;
   CK(cudaSetDevice(ctx->device));
-  ctx->launches = 0; ctx->hard = 0;
+  ctx->launches = 0; ctx->hard = 0; ctx->second = 0; ctx->lost = 0;
   if (kernel_ms) *kernel_ms = 0.f;
   if (!ctx->nwin) return DCU_OK;
   CK(cudaMemsetAsync(ctx->dcnt.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->dcnt.p + 8, 0, 4 * sizeof(unsigned int), ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = launch_tier(ctx, 0, nullptr, (uint32_t)ctx->nwin);
-  if (rc) return rc;
-  unsigned int cnt[4];
-  CK(cudaMemcpyAsync(cnt, ctx->dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  int ret = DCU_OK;
-  if (cnt[1]) {
-    ctx->hard = cnt[1];
-    rc = launch_tier(ctx, 1, ctx->dovf[0].p, cnt[1]);
+  unsigned int cnt[2];
+  const uint32_t* todo = nullptr; uint32_t n = (uint32_t)ctx->nwin;
+  if (ctx->use_smem && ctx->warpsS >= 2) {           // pass 1: shared-memory workspaces
+    int rc = launch_smem(ctx, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(cnt, ctx->dcnt.p + 8, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->second = cnt[1]; todo = ctx->dovf[2].p; n = cnt[1];
+  }
+  if (n) {                                           // HBM workspaces, first-pass capacities
+    int rc = launch_tier(ctx, 0, todo, n);
     if (rc) return rc;
     CK(cudaMemcpyAsync(cnt, ctx->dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (cnt[3]) {
-      uint32_t wi = 0; dcu::Result r; memset(&r, 0, sizeof(r));
-      CK(cudaMemcpy(&wi, ctx->dovf[1].p, sizeof(wi), cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(&r, ctx->dres.p + wi, sizeof(r), cudaMemcpyDeviceToHost));
-      char b[192]; snprintf(b, sizeof b, "%u windows exceeded the large-workspace capacities (first: window %u, capacity code %u)", cnt[3], wi, r.err);
-      ctx->err = b; ret = DCU_ERR_OVERFLOW;
+    n = cnt[1];
+    if (n) {                                         // large workspaces
+      ctx->hard = n;
+      rc = launch_tier(ctx, 1, ctx->dovf[0].p, n);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(cnt, ctx->dcnt.p + 2, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (cnt[1]) {
+        // beyond every capacity of this build: the windows keep status DCU_WIN_OVERFLOW (the caller treats them like failed windows, as the
+        // reference swallows a read's exception, src/daccord.cpp:2466-2478); the batch itself is not an error
+        uint32_t wi = 0; dcu::Result r; memset(&r, 0, sizeof(r));
+        CK(cudaMemcpy(&wi, ctx->dovf[1].p, sizeof(wi), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&r, ctx->dres.p + wi, sizeof(r), cudaMemcpyDeviceToHost));
+        char b[192]; snprintf(b, sizeof b, "%u windows exceeded the large-workspace capacities (first: window %u, capacity code %u)", cnt[1], wi, r.err);
+        ctx->err = b; ctx->lost = cnt[1];
+      }
     }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaEventSynchronize(ctx->ev1));
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
   ctx->results_valid = true;
-  return ret;
+  return DCU_OK;
 }
 
 int dcu_download(dcu_ctx* ctx, dcu_result* res, uint8_t* cons, uint8_t* ops) {
@@ -607,7 +761,7 @@ int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* rea
   if (nblk >= 0x7FFFFFFFull) { ctx->err = "batch too large for the vote"; return DCU_ERR_UNSUPPORTED; }
   const uint64_t bound_cap = 2 * (nwin + nr) + 16;
   CK(ctx->dvent.ensure(nwin * (ctx->prm.w + 1))); CK(ctx->dvflag.ensure(npos + 1)); CK(ctx->dvblk.ensure(nblk + 2)); CK(ctx->dvreads.ensure(nr + 1));
-  CK(ctx->dvbound.ensure(bound_cap)); CK(ctx->dcnt.ensure(8));
+  CK(ctx->dvbound.ensure(bound_cap)); CK(ctx->dcnt.ensure(16));
   CK(cudaMemcpyAsync(ctx->dvreads.p, L.reads.data(), nr * sizeof(dvote::Read), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->dcnt.p + 4, 0, 4 * sizeof(unsigned int), st));
   int* derr = (int*)(ctx->dcnt.p + 4); unsigned int* dnb = ctx->dcnt.p + 5;
@@ -660,6 +814,14 @@ int dcu_last_stats(dcu_ctx* ctx, uint64_t* launches, uint64_t* hard_windows) {
   if (!ctx) return DCU_ERR_PARAM;
   if (launches) *launches = ctx->launches;
   if (hard_windows) *hard_windows = ctx->hard;
+  return DCU_OK;
+}
+int dcu_last_stats2(dcu_ctx* ctx, uint64_t* second_pass_windows, uint64_t* lost_windows, uint32_t* smem_warps, uint32_t* smem_bytes_per_warp) {
+  if (!ctx) return DCU_ERR_PARAM;
+  if (second_pass_windows) *second_pass_windows = ctx->second;
+  if (lost_windows) *lost_windows = ctx->lost;
+  if (smem_warps) *smem_warps = (ctx->use_smem && ctx->warpsS >= 2) ? (uint32_t)ctx->warpsS : 0u;
+  if (smem_bytes_per_warp) *smem_bytes_per_warp = ctx->layS.sbytes;
   return DCU_OK;
 }
 

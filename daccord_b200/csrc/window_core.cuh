@@ -23,207 +23,89 @@
 // The file is compiled twice: by nvcc for sm_100a (32 lanes, product) and, for tests only, by
 // g++ with -DDCU_EMU as a host emulation (tests/emu: single lane, or 32 lanes as cooperative fibers
 // with -DDCU_EMU_LANES) so that parity against the oracle can be debugged without a GPU.  The product library contains only the CUDA build.
-#pragma once
-#include <stdint.h>
-#include <float.h>
-#include <stddef.h>
-#if defined(DCU_EMU) && defined(DCU_EMU_STATS)
-#include <chrono>
-// footprint study (tests/emu with -DDCU_EMU_STATS): per-window peaks of the workspace counters, read by tools/footprint.py
-static long g_peak[16];
-#define DCU_PEAK(i, v) do { if ((long)(v) > g_peak[i]) g_peak[i] = (long)(v); } while (0)
-#else
-#define DCU_PEAK(i, v) do { } while (0)
+//
+// This file has no include guard: it is compiled once per build of the kernel, inside the namespace DCU_NS.
+//   DCU_NS = dcu,  DCU_TIER_SMEM = 0 : every workspace field lives in the warp's slab in HBM (large / deep windows, overflow passes);
+//   DCU_NS = dcus, DCU_TIER_SMEM = 1 : the fields marked S below live in the warp's shared-memory arena, the rest in a (small) slab.
+#include "window_types.cuh"
+#ifndef DCU_NS
+#define DCU_NS dcu
+#endif
+#ifndef DCU_TIER_SMEM
+#define DCU_TIER_SMEM 0
 #endif
 
-#ifdef DCU_EMU
-#define DCU_FN static inline
-#define DCU_BIG static
-#define DCU_MEM inline
-#define DCU_NOUNROLL
-#define DCU_UNROLL
-#define DCU_NOINL static inline
-#define DCU_CTOR
-#ifndef DCU_EMU_LANES
-#define DCU_NL 1
-namespace dcu {
-static inline void wsync() {}
-static inline uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
-static inline uint32_t a_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
-static inline uint32_t ballot(bool p) { return p ? 1u : 0u; }
-static inline uint32_t lanemask_lt(int) { return 0; }
-static inline int popc(uint32_t x) { return __builtin_popcount(x); }
-static inline int popcll(uint64_t x) { return __builtin_popcountll(x); }
-template <class T> static inline T bcast(T v, int) { return v; }
-static inline uint32_t red_max_u32(uint32_t v) { return v; }
-static inline uint32_t red_sum_u32(uint32_t v) { return v; }
-static inline uint32_t red_min_u32(uint32_t v) { return v; }
-static inline void red_argmax_d(double&, int&) {}
-static inline uint32_t scan_incl(uint32_t v, int) { return v; }
-template <class T> static inline T ldg(const T* p) { return *p; }
-}
+namespace DCU_NS {
+using namespace dcub;
+using dcub::ballot;                      // (hides the toolkit's global ::ballot)
+
+// value of a hash slot and offsets into the instance lists: 16 bit in the shared-memory build (its capacities are small)
+#if DCU_TIER_SMEM
+typedef uint16_t hval_t;                 // bit 15 set: node id in the low 15 bits (the count is then n_freq[id]); else the k-mer's count
+typedef uint16_t ioff_t;
 #else
-// 32-lane emulation (tests/emu/emu_lanes.cpp): every lane of the warp is a cooperative fiber running this very code with
-// its own registers (Ctx, WinState); a warp collective or __syncwarp is the only place where fibers switch, and the
-// harness picks the order in which the lanes run between two such points (ascending, descending, shuffled).  A result that
-// depends on that order is a missing wsync() in the code below; lanes that do not reach the same collectives deadlock,
-// which the harness reports.  emu_xchg deposits one 64-bit word per lane and returns all 32 once every lane has arrived.
-#include <string.h>
-#define DCU_NL 32
-namespace dcu {
-const unsigned long long* emu_xchg(unsigned long long v);
-extern int emu_skip_sync_line;       // mutation testing of the harness itself (tools/lane_mutants.py): the wsync() of this source line is dropped
-static inline void wsync_line(int line) { if (line != emu_skip_sync_line) emu_xchg(0); }
-#define wsync() wsync_line(__LINE__)
-static inline uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { __atomic_compare_exchange_n(p, &c, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return c; }   // real atomics: the lanes are OS threads in the ThreadSanitizer build
-static inline uint32_t a_add(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline uint32_t ballot(bool p) { const unsigned long long* x = emu_xchg(p ? 1 : 0); uint32_t m = 0; for (int i = 0; i < 32; ++i) if (x[i]) m |= 1u << i; return m; }
-static inline uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
-static inline int popc(uint32_t x) { return __builtin_popcount(x); }
-static inline int popcll(uint64_t x) { return __builtin_popcountll(x); }
-template <class T> static inline T bcast(T v, int src) {
-  static_assert(sizeof(T) <= 8, "bcast word");
-  unsigned long long u = 0; memcpy(&u, &v, sizeof(T));
-  const unsigned long long* x = emu_xchg(u);
-  T r; memcpy(&r, &x[src & 31], sizeof(T)); return r;
-}
-static inline uint32_t red_max_u32(uint32_t v) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0; for (int i = 0; i < 32; ++i) if ((uint32_t)x[i] > r) r = (uint32_t)x[i]; return r; }
-static inline uint32_t red_min_u32(uint32_t v) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0xFFFFFFFFu; for (int i = 0; i < 32; ++i) if ((uint32_t)x[i] < r) r = (uint32_t)x[i]; return r; }
-static inline uint32_t red_sum_u32(uint32_t v) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0; for (int i = 0; i < 32; ++i) r += (uint32_t)x[i]; return r; }
-static inline void red_argmax_d(double& v, int& i) {      // larger value wins, ties -> smaller index (same as the butterfly of the CUDA build)
-  double vs[32]; int is[32];
-  { unsigned long long u; memcpy(&u, &v, 8); const unsigned long long* x = emu_xchg(u); memcpy(vs, x, sizeof(vs)); }
-  { const unsigned long long* x = emu_xchg((unsigned long long)(long long)i); for (int q = 0; q < 32; ++q) is[q] = (int)(long long)x[q]; }
-  double bv = vs[0]; int bi = is[0];
-  for (int q = 1; q < 32; ++q) if (vs[q] > bv || (vs[q] == bv && is[q] < bi)) { bv = vs[q]; bi = is[q]; }
-  v = bv; i = bi;
-}
-static inline uint32_t scan_incl(uint32_t v, int lane) { const unsigned long long* x = emu_xchg(v); uint32_t r = 0; for (int i = 0; i <= lane; ++i) r += (uint32_t)x[i]; return r; }
-template <class T> static inline T ldg(const T* p) { return *p; }
-}
-#endif
-#else
-#define DCU_FN __device__ __forceinline__
-#define DCU_BIG __device__ __noinline__
-#define DCU_MEM __device__ __forceinline__
-#define DCU_NOUNROLL _Pragma("unroll 1")
-#define DCU_UNROLL _Pragma("unroll")
-#define DCU_NOINL __device__ __noinline__
-#define DCU_CTOR __device__
-#define DCU_NL 32
-namespace dcu {
-__device__ __forceinline__ void wsync() { __syncwarp(); }
-__device__ __forceinline__ uint32_t a_cas(uint32_t* p, uint32_t c, uint32_t v) { return atomicCAS(p, c, v); }
-__device__ __forceinline__ uint32_t a_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
-__device__ __forceinline__ uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
-__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
-__device__ __forceinline__ int popc(uint32_t x) { return __popc(x); }
-__device__ __forceinline__ int popcll(uint64_t x) { return __popcll(x); }
-template <class T> __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ uint32_t red_max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
-__device__ __forceinline__ uint32_t red_min_u32(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
-__device__ __forceinline__ uint32_t red_sum_u32(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
-// (value, index) arg-max: larger value wins, ties -> smaller index
-__device__ __forceinline__ void red_argmax_d(double& v, int& i) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, v, o);
-    int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-  }
-}
-template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
-__device__ __forceinline__ uint32_t scan_incl(uint32_t v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-  return v;
-}
-}
+typedef uint32_t hval_t;                 // count | node id << 16 (0xFFFF: not a node)
+typedef uint32_t ioff_t;
 #endif
 
-namespace dcu {
+// byte layout of a workspace, computed once on the host for a Caps: offsets of the fields marked S are relative to the warp's
+// shared-memory arena in the shared-memory build (sbytes), all others (and all fields of the HBM build) to the warp's slab (bytes)
+struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
 
-enum { W_EMPTY = 0xFFFFFFFFu, NID_NONE = 0xFFFF, IDX_NONE = 0xFFFFFFFFu };
-enum { ST_SKIPPED = 0, ST_OK = 1, ST_FAILED = 2, ST_OVERFLOW = 250 };
-enum { HEAPK = 12, CDH_N = 16, MAXCAND = 64 };
-
-// read-only tables built on the host (daccord_b200/csrc/tables_host.hpp), resident in HBM
-struct Tables {
-  const double* DPn;               // [NP][MS] DPnorm, zero padded           (OffsetLikely.hpp:75-79)
-  const double* DPsq;              // [NP][MS] DPnormSquare.V, zero padded   (OffsetLikely.hpp:96-98)
-  const unsigned long long* VSq;   // [MS+1][NP] transposed floor(2^32 * DPnormSquare.V), row MS all zero  (DotProduct.hpp:54-60)
-  const uint16_t* suplo;           // [MS] Vsupport[i].first
-  const uint16_t* suphi;           // [MS] Vsupport[i].second
-  const unsigned long long* klim;  // [nk][KLIMN] KmerLimit::Vlim per k     (DebruijnGraph.hpp:28-75)
-  int NP, MS, KLIMN;
-};
-struct Params {
-  int w, k_lo, k_hi, minff, maxff, mincov, check;   // check = (est_cor != 0)  (DebruijnGraph.hpp:1832-1837)
-  unsigned long long eminrate;
-  int defer_ff;                                      // experimental (DCU_DEFER_FF, first pass only): hand windows whose first filter frequency fails to the second pass
-  int poscache;                                      // keep the position weights of unsplit unitigs across the (first,last) pairs of a traverse (DCU_POSCACHE=0 turns it off; results identical)
-};
-// capacities of one warp's workspace (two tiers: small for the common case, large for the rest)
-struct Caps { int S, B, H, LOGH, NN, NI, EX, ST, STP, SL, SF, RL, RLP, RP, FP, SI, BL, KW, HEAVY; };
-
-struct Slice { uint32_t gpos; uint16_t len; uint16_t flags; };
-struct Window { uint32_t slice_begin; uint16_t slice_cnt; uint16_t reserved; uint32_t aread; uint32_t astart; };
-struct Result { uint8_t status, k; int8_t ff; uint8_t clen; uint32_t err; uint16_t nops, ncand; int32_t elength; };
-
-// (struct WS is defined after the field list below)
-// byte layout of a workspace slab, computed once on the host for a Caps
-struct Layout { uint32_t off[128]; uint32_t bytes; };
-
-#define DCU_WS_FIELDS(X)                                                                                  \
-  X(bases, uint8_t, c.B) X(soff, uint16_t, c.S + 1) X(lenhist, uint16_t, 256)                              \
-  X(hs, uint32_t, 2 * c.H) X(occ, uint32_t, c.NI + c.EX)                                               \
-  X(hstate, uint32_t, 4) X(islot, uint32_t, c.NI) X(praw, uint8_t, c.NI) X(rraw, uint8_t, c.NI)              \
-  X(koff, uint16_t, c.S + 1) X(choff, uint16_t, c.S + 1) X(lastk, uint32_t, c.S)                            \
-  X(ts_k, uint32_t, c.S) X(ts_c, uint16_t, c.S) X(ts_n, uint16_t, c.S)                                      \
-  X(n_kmer, uint32_t, c.NN) X(n_freq, uint16_t, c.NN) X(n_ioff, uint32_t, c.NN) X(n_fill, uint32_t, c.NN)  \
-  X(n_plow, uint8_t, c.NN) X(n_phigh, uint8_t, c.NN) X(n_cplow, uint8_t, c.NN) X(n_cphigh, uint8_t, c.NN)  \
-  X(n_nsucc, uint8_t, c.NN) X(n_nact, uint8_t, c.NN) X(n_npred, uint8_t, c.NN)                             \
-  X(n_sfreq, uint16_t, 4 * c.NN) X(n_snid, uint16_t, 4 * c.NN) X(n_mark, uint16_t, c.NN)                   \
-  X(ipos, uint8_t, c.NI + c.EX) X(irpos, uint8_t, c.NI + c.EX)                                                           \
-  X(ex_kmer, uint32_t, c.EX) X(ex_pos, uint8_t, c.EX) X(ex_rpos, uint8_t, c.EX)                            \
-  X(ll_kmer, uint32_t, c.S) X(ll_cnt, uint16_t, c.S) X(fl_kmer, uint32_t, c.S) X(fl_cnt, uint16_t, c.S)    \
-  X(fl_nid, uint16_t, c.S)                                                                                 \
-  X(slinks, uint16_t, c.SL) X(slsym, uint8_t, c.SL) X(rs_off, uint16_t, c.ST) X(rs_len, uint16_t, c.ST)    \
-  X(rs_fO, uint32_t, c.ST) X(rs_cO, uint32_t, c.ST) X(spc, uint32_t, 4)                                    \
-  X(ds_off, uint16_t, c.ST) X(ds_len, uint16_t, c.ST) X(ds_fO, uint32_t, c.ST) X(ds_cO, uint32_t, c.ST)    \
-  X(dt_off, uint16_t, c.ST) X(dt_len, uint16_t, c.ST) X(du_off, uint16_t, c.ST) X(du_len, uint16_t, c.ST)  \
-  X(ds_rlO, uint16_t, c.ST) X(ds_rlN, uint16_t, c.ST)                                                      \
-  X(ds_fB, uint8_t, c.ST) X(ds_fN, uint8_t, c.ST) X(ds_cB, uint8_t, c.ST) X(ds_cN, uint8_t, c.ST)          \
-  X(sf_w, double, c.SF) X(sc_w, double, c.SF) X(sc_wf, double, c.SF)                                        \
-  X(n_pf, uint8_t, c.NN) X(n_pt, uint8_t, c.NN) X(n_cpf, uint8_t, c.NN) X(n_cpt, uint8_t, c.NN)            \
-               \
-  X(n_dsf, uint16_t, c.NN) X(n_dsn, uint8_t, c.NN) X(skey, unsigned long long, c.STP)                      \
-  X(rl, uint32_t, c.RLP)                                                                                   \
-  X(rp_w, double, c.RP) X(rp_parent, uint32_t, c.RP) X(rp_front, uint32_t, c.RP)                           \
-  X(rp_stretch, uint16_t, c.RP) X(rp_pos, uint16_t, c.RP) X(rp_len, uint16_t, c.RP)                        \
-  X(rp_baselen, uint16_t, c.RP) X(rq_w, double, c.RP) X(rq_id, uint32_t, c.RP) X(arp, uint32_t, c.RP)      \
-  X(arp_k, unsigned long long, c.RP) X(arp_wt, double, c.RP)                                               \
-  X(arph_w, double, c.BL* HEAPK) X(arph_n, uint8_t, c.BL)                                                  \
-  X(fp_w, double, c.FP) X(fp_parent, uint32_t, c.FP) X(fp_stretch, uint16_t, c.FP)                         \
-  X(fp_pos, uint16_t, c.FP) X(fp_len, uint16_t, c.FP) X(fp_baselen, uint16_t, c.FP)                        \
-  X(apq_w, double, c.BL* HEAPK) X(apq_id, uint32_t, c.BL* HEAPK) X(apq_n, uint8_t, c.BL)                   \
-  X(si_w, double, c.SI) X(si_left, uint16_t, c.SI) X(si_right, uint16_t, c.SI) X(si_cur, uint16_t, c.SI)   \
-  X(si_path, uint32_t, c.SI) X(sq_w, double, c.SI) X(sq_id, uint32_t, c.SI)                                \
-  X(cand, uint8_t, (CDH_N + 1) * MAXCAND) X(candlen, uint8_t, CDH_N + 1)                                   \
-  X(cdh_w, double, CDH_N) X(cdh_id, uint32_t, CDH_N) X(ch_w, double, CDH_N) X(ch_id, uint32_t, CDH_N)      \
-  X(acc_w, double, CDH_N) X(acc_err, uint32_t, CDH_N) X(acc_slot, uint8_t, CDH_N)                          \
-  X(prevs, uint8_t, MAXCAND) X(tmps, uint8_t, MAXCAND) X(best, uint8_t, MAXCAND)                           \
-  X(m_pv, unsigned long long, 65) X(m_mv, unsigned long long, 65) X(m_ph, unsigned long long, 65)          \
-  X(m_mh, unsigned long long, 65)
+// X(name, type, elements, S)    S = 1: hot and small (tools/field_traffic.py: 4 % of the bytes, 2/3 of the accesses)
+#define DCU_WS_FIELDS(X)                                                                                              \
+  X(bw, uint32_t, c.BW, 1) X(sw, uint16_t, c.S + 1, 1) X(soff, uint16_t, c.S + 1, 1) X(lenhist, uint16_t, 256, 0)      \
+  X(hkey, uint32_t, c.H, 1) X(hval, hval_t, c.H, 1) X(hbA, uint32_t, c.NBITS / 32 + 4, 1) X(hbB, uint32_t, c.NBITS / 32 + 4, 1) \
+  X(hstate, uint32_t, 4, 1)                                                                                           \
+  X(koff, uint16_t, c.S + 1, 1) X(choff, uint16_t, c.S + 1, 1) X(lastk, uint32_t, c.S, 1)                              \
+  X(ts_k, uint32_t, c.S, 0) X(ts_c, uint16_t, c.S, 0) X(ts_n, uint16_t, c.S, 0)                                        \
+  X(n_kmer, uint32_t, c.NN, 0) X(n_freq, uint16_t, c.NN, 1) X(n_ioff, ioff_t, c.NN, 1)                                 \
+  X(n_nsucc, uint8_t, c.NN, 0) X(n_nact, uint8_t, c.NN, 0) X(n_npred, uint8_t, c.NN, 0)                                \
+  X(n_sfreq, uint16_t, 4 * c.NN, 0) X(n_snid, uint16_t, 4 * c.NN, 0)                                                  \
+  X(ipos, uint8_t, c.NI + c.EX, 1) X(irpos, uint8_t, c.NI + c.EX, 1)                                                  \
+  X(ex_kmer, uint32_t, c.EX, 0) X(ex_pos, uint8_t, c.EX, 0) X(ex_rpos, uint8_t, c.EX, 0)                               \
+  X(ll_kmer, uint32_t, c.S, 0) X(ll_cnt, uint16_t, c.S, 0) X(fl_kmer, uint32_t, c.S, 0) X(fl_cnt, uint16_t, c.S, 0)    \
+  X(fl_nid, uint16_t, c.S, 0)                                                                                         \
+  X(slinks, uint16_t, c.SL, 1) X(slsym, uint8_t, c.SL, 1) X(rs_off, uint16_t, c.ST, 0) X(rs_len, uint16_t, c.ST, 0)    \
+  X(rs_fO, uint32_t, c.ST, 0) X(rs_cO, uint32_t, c.ST, 0) X(spc, uint32_t, 4, 0)                                       \
+  X(ds_off, uint16_t, c.ST, 0) X(ds_len, uint16_t, c.ST, 0) X(ds_fO, uint32_t, c.ST, 0) X(ds_cO, uint32_t, c.ST, 0)    \
+  X(dt_off, uint16_t, c.ST, 0) X(dt_len, uint16_t, c.ST, 0) X(du_off, uint16_t, c.ST, 0) X(du_len, uint16_t, c.ST, 0)  \
+  X(ds_rlO, uint16_t, c.ST, 0) X(ds_rlN, uint16_t, c.ST, 0)                                                           \
+  X(ds_fB, uint8_t, c.ST, 0) X(ds_fN, uint8_t, c.ST, 0) X(ds_cB, uint8_t, c.ST, 0) X(ds_cN, uint8_t, c.ST, 0)          \
+  X(sf_w, double, c.SF, 0) X(sc_w, double, c.SF, 0) X(sc_wf, double, c.SF, 0)                                          \
+  X(n_pf, uint8_t, c.NN, 0) X(n_pt, uint8_t, c.NN, 0) X(n_cpf, uint8_t, c.NN, 0) X(n_cpt, uint8_t, c.NN, 0)            \
+  X(n_dsf, uint16_t, c.NN, 0) X(n_dsn, uint8_t, c.NN, 0) X(skey, unsigned long long, c.STP, 0)                         \
+  X(rl, uint32_t, c.RLP, 0)                                                                                           \
+  X(rp_w, double, c.RP, 0) X(rp_parent, uint32_t, c.RP, 0) X(rp_front, uint32_t, c.RP, 0)                              \
+  X(rp_stretch, uint16_t, c.RP, 0) X(rp_pos, uint16_t, c.RP, 0) X(rp_len, uint16_t, c.RP, 0)                           \
+  X(rp_baselen, uint16_t, c.RP, 0) X(rq_w, double, c.RP, 0) X(rq_id, uint32_t, c.RP, 0) X(arp, uint32_t, c.RP, 0)      \
+  X(arp_k, unsigned long long, c.RP, 0) X(arp_wt, double, c.RP, 0)                                                    \
+  X(arph_w, double, c.BL* HEAPK, 0) X(arph_n, uint8_t, c.BL, 0)                                                       \
+  X(fp_w, double, c.FP, 0) X(fp_parent, uint32_t, c.FP, 0) X(fp_stretch, uint16_t, c.FP, 0)                            \
+  X(fp_pos, uint16_t, c.FP, 0) X(fp_len, uint16_t, c.FP, 0) X(fp_baselen, uint16_t, c.FP, 0)                           \
+  X(apq_w, double, c.BL* HEAPK, 0) X(apq_id, uint32_t, c.BL* HEAPK, 0) X(apq_n, uint8_t, c.BL, 0)                      \
+  X(si_w, double, c.SI, 0) X(si_left, uint16_t, c.SI, 0) X(si_right, uint16_t, c.SI, 0) X(si_cur, uint16_t, c.SI, 0)   \
+  X(si_path, uint32_t, c.SI, 0) X(sq_w, double, c.SI, 0) X(sq_id, uint32_t, c.SI, 0)                                   \
+  X(cand, uint8_t, (CDH_N + 1) * MAXCAND, 0) X(candlen, uint8_t, CDH_N + 1, 0)                                        \
+  X(cdh_w, double, CDH_N, 0) X(cdh_id, uint32_t, CDH_N, 0) X(ch_w, double, CDH_N, 0) X(ch_id, uint32_t, CDH_N, 0)      \
+  X(acc_w, double, CDH_N, 0) X(acc_err, uint32_t, CDH_N, 0) X(acc_slot, uint8_t, CDH_N, 0)                             \
+  X(prevs, uint8_t, MAXCAND, 0) X(tmps, uint8_t, MAXCAND, 0) X(best, uint8_t, MAXCAND, 0)                              \
+  X(m_pv, unsigned long long, 65, 0) X(m_mv, unsigned long long, 65, 0) X(m_ph, unsigned long long, 65, 0)             \
+  X(m_mh, unsigned long long, 65, 0)
 
 static inline void make_layout(const Caps& c, Layout& L) {
-  uint32_t o = 0; int i = 0;
-#define X(name, type, n) { o = (o + 15u) & ~15u; L.off[i++] = o; o += (uint32_t)(sizeof(type) * (size_t)(n)); }
+  uint32_t o = 0, so = 0; int i = 0;
+#if DCU_TIER_SMEM
+#define X(name, type, n, S) { uint32_t& q = (S) ? so : o; q = (q + 15u) & ~15u; L.off[i++] = q; q += (uint32_t)(sizeof(type) * (size_t)(n)); }
+#else
+#define X(name, type, n, S) { o = (o + 15u) & ~15u; L.off[i++] = o; o += (uint32_t)(sizeof(type) * (size_t)(n)); }
+#endif
   DCU_WS_FIELDS(X)
 #undef X
   L.bytes = (o + 255u) & ~255u;
+  L.sbytes = (so + 127u) & ~127u;
 }
-// Launch-wide read-only state.  On the GPU it lives in __constant__ memory, so that slab field addresses
+// Launch-wide read-only state.  On the GPU it lives in __constant__ memory, so that field addresses
 // (base + constant offset), capacities, table descriptors and parameters are constant-bank operands instead of
 // loads; the emulation build keeps them in plain globals.
 #ifdef DCU_EMU
@@ -238,29 +120,45 @@ __constant__ Layout c_layout; __constant__ Caps c_cap; __constant__ Tables c_T; 
 #define DCU_CAP c_cap
 #define DCU_T c_T
 #define DCU_P c_P
+#if DCU_TIER_SMEM
+extern __shared__ __align__(128) uint8_t dcu_smem[];     // [transposed VS table | per-warp arenas]; fields marked S are addressed from this symbol so that the compiler emits LDS / STS / ATOMS
+#endif
 #endif
 enum {
-#define X(name, type, n) F_##name,
+#define X(name, type, n, S) F_##name,
   DCU_WS_FIELDS(X)
 #undef X
   F_COUNT
 };
 static_assert(F_COUNT <= 128, "Layout::off holds 128 field offsets");
-// one warp's workspace: a slab base pointer; every SoA array is an accessor (base + layout offset)
+// one warp's workspace: a slab base pointer in HBM and (shared-memory build) the offset of the warp's arena; every SoA array is an accessor
 struct WS {
   uint8_t* base;
-#define X(name, type, n) DCU_MEM type* name() const { return (type*)(base + DCU_LAYOUT.off[F_##name]); }
+#if DCU_TIER_SMEM
+#ifdef DCU_EMU
+  uint8_t* sm;                             // emulation: the arena is a host buffer
+#define X(name, type, n, S) DCU_MEM type* name() const { return (type*)(((S) ? sm : base) + DCU_LAYOUT.off[F_##name]); }
+#else
+  uint32_t sm;                             // byte offset of the warp's arena in dcu_smem
+#define X(name, type, n, S) DCU_MEM type* name() const { return (S) ? (type*)(dcu_smem + sm + DCU_LAYOUT.off[F_##name]) : (type*)(base + DCU_LAYOUT.off[F_##name]); }
+#endif
+#else
+#define X(name, type, n, S) DCU_MEM type* name() const { return (type*)(base + DCU_LAYOUT.off[F_##name]); }
+#endif
   DCU_WS_FIELDS(X)
 #undef X
+  DCU_MEM uint16_t* fillcnt() const { return slinks(); }      // per-node fill counters of build_nodes: the link array is not in use while nodes are built (SL >= NN)
 };
 
 // per-window state that all lanes hold identically
 struct Ctx {
-  WS ws;                                   // slab base of this warp
+  WS ws;                                   // workspace of this warp
   const unsigned long long* vsq;           // transposed VS table (shared-memory copy when it fits, else HBM)
   const uint8_t* packed; const Slice* sl;
   int MAo, nbases;
   int logh;                                // this window's hash uses the first 2^logh slots of the table (st_begin)
+  int hcap;                                // distinct k-mers the table accepts (st_begin)
+  int hpre;                                // the table holds only k-mers that passed the pre-filter (seen at least twice, with false positives): valid for filter frequencies >= 2
   int k; uint32_t kmask; int kidx;
   int nn, ni, nex, nlast, nfirst;
   int nrs, slO, nds, nrl, kwtot;
@@ -269,37 +167,52 @@ struct Ctx {
 
 // ------------------------------------------------------------------ small helpers
 DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (32 - c.logh); }
-// one 8-byte load per probe: (key, count | node id << 16)
-DCU_FN unsigned long long hs_slot(const Ctx& c, uint32_t h) {
-#ifdef DCU_EMU
-  unsigned long long sv; __builtin_memcpy(&sv, c.ws.hs() + 2 * h, 8); return sv;
+// slot values (hval_t above)
+#if DCU_TIER_SMEM
+DCU_FN int hv_node(hval_t v) { return (v & 0x8000u) ? (int)(v & 0x7FFFu) : (int)NID_NONE; }
+DCU_FN hval_t hv_make(int cnt, int nid) { return nid == (int)NID_NONE ? (hval_t)cnt : (hval_t)(0x8000u | (uint32_t)nid); }
+// counts are 16-bit halves of 32-bit words: the add goes to the containing word (a count never reaches 2^15: HCAP / NI bound it)
+DCU_FN void hv_inc(hval_t* p) { a_add((uint32_t*)((uintptr_t)p & ~(uintptr_t)3), ((uintptr_t)p & 2) ? 0x10000u : 1u); }
 #else
-  return *(const unsigned long long*)(c.ws.hs() + 2 * h);
+DCU_FN int hv_node(hval_t v) { return (int)(v >> 16); }
+DCU_FN hval_t hv_make(int cnt, int nid) { return (hval_t)cnt | ((hval_t)nid << 16); }
+DCU_FN void hv_inc(hval_t* p) { a_add(p, 1u); }
 #endif
+// 16-bit counter add on the containing 32-bit word; returns the old value of the half (no carry: the counters stay below 2^16)
+DCU_FN uint32_t add16(uint16_t* p, uint32_t v) {
+  const bool hi = ((uintptr_t)p & 2) != 0;
+  const uint32_t o = a_add((uint32_t*)((uintptr_t)p & ~(uintptr_t)3), hi ? (v << 16) : v);
+  return hi ? (o >> 16) : (o & 0xFFFFu);
 }
-DCU_FN int lookup_from(const Ctx& c, uint32_t v, uint32_t h, unsigned long long sv) {      // sv = slot h, already loaded
+DCU_FN int lookup_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t key) {      // key = hkey[h], already loaded
   const uint32_t mask = (1u << c.logh) - 1u;
   DCU_NOUNROLL
   for (;;) {
-    const uint32_t key = (uint32_t)sv;
-    if (key == v) return (int)((uint32_t)(sv >> 32) >> 16);
+    if (key == v) return hv_node(c.ws.hval()[h]);
     if (key == W_EMPTY) return NID_NONE;
     h = (h + 1) & mask;
-    sv = hs_slot(c, h);
+    key = c.ws.hkey()[h];
   }
 }
 DCU_NOINL int lookup(const Ctx& c, uint32_t v) {                 // k-mer -> node id (DebruijnGraph.hpp:968-985)
   const uint32_t h = hslot(c, v);
-  return lookup_from(c, v, h, hs_slot(c, h));
+  return lookup_from(c, v, h, c.ws.hkey()[h]);
 }
 // the four neighbours of a k-mer: the home slots of all four are requested before the first is examined
 DCU_NOINL void lookup4(const Ctx& c, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, int* out) {
   const uint32_t h0 = hslot(c, v0), h1 = hslot(c, v1), h2 = hslot(c, v2), h3 = hslot(c, v3);
-  const unsigned long long s0 = hs_slot(c, h0), s1 = hs_slot(c, h1), s2 = hs_slot(c, h2), s3 = hs_slot(c, h3);
+  const uint32_t* hk = c.ws.hkey();
+  const uint32_t s0 = hk[h0], s1 = hk[h1], s2 = hk[h2], s3 = hk[h3];
   out[0] = lookup_from(c, v0, h0, s0); out[1] = lookup_from(c, v1, h1, s1); out[2] = lookup_from(c, v2, h2, s2); out[3] = lookup_from(c, v3, h3, s3);
 }
 DCU_FN int sup_lo(const Ctx& c, int pos) { return pos < DCU_T.MS ? (int)ldg(DCU_T.suplo + pos) : DCU_T.NP; }   // OffsetLikely.hpp:34-37
 DCU_FN int sup_hi(const Ctx& c, int pos) { return pos < DCU_T.MS ? (int)ldg(DCU_T.suphi + pos) : DCU_T.NP; }   // OffsetLikely.hpp:39-43
+
+// bases of the window: 2-bit codes, 16 per 32-bit word (base i of a slice in bits [2 (i & 15), 2 (i & 15) + 2) of word i >> 4),
+// every slice starts on a word (sw[j]); soff[j] = bases before slice j
+DCU_FN int seqlen(const Ctx& c, int j) { return c.ws.soff()[j + 1] - c.ws.soff()[j]; }
+DCU_FN uint32_t bget(const uint32_t* wd, int i) { return (wd[i >> 4] >> (2 * (i & 15))) & 3u; }
+DCU_FN const uint32_t* slice_words(const Ctx& c, int j) { return c.ws.bw() + c.ws.sw()[j]; }
 
 // positional weight of node n at true position p (DebruijnGraph.hpp:3826-3904, fixed point per SURVEY D7)
 DCU_FN double kweight(const Ctx& c, int n, int p, bool rev) {
@@ -344,57 +257,95 @@ DCU_NOINL void heap_pop(bool MAXH, double* hw, uint32_t* hi, int& n) {
   }
 }
 
-// ------------------------------------------------------------------ load: slices -> base codes
-// replaces DecodedReadContainer + the MA array (HandleContext.hpp:2032-2043); bases as codes 0..3
-DCU_BIG void load_window(Ctx& c, const Window& win, int lane) {
+// ------------------------------------------------------------------ load: slices -> packed base codes
+// replaces DecodedReadContainer + the MA array (HandleContext.hpp:2032-2043); bases as codes 0..3, 16 per word.
+// A slice's bytes in the packed database are fetched as one 16-byte aligned chunk (the shared-memory build stages these chunks
+// with cp.async.bulk one window ahead, `raw` != nullptr; otherwise they are read from HBM here).
+DCU_FN uint32_t brev32(uint32_t x) {
+#ifdef DCU_EMU
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1); x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4); x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+  return (x >> 16) | (x << 16);
+#else
+  return __brev(x);
+#endif
+}
+// the aligned chunk of the packed database that holds a slice: first byte (multiple of 16) and size (multiple of 16)
+DCU_FN void slice_chunk(const Slice& s, uint32_t& start, uint32_t& bytes) {
+  if (s.len == 0) { start = 0; bytes = 0; return; }
+  const uint32_t b0 = s.gpos >> 2, b1 = (s.gpos + s.len - 1) >> 2;
+  start = b0 & ~15u; bytes = ((b1 - start) + 16u) & ~15u;
+}
+// n (1..16) bases lo .. lo+n-1 of the database stream (4 per byte, first base in the top two bits), right aligned: base lo+t at
+// shift 2 (n-1-t).  ld(b) = byte b of the database; bytes after blast are not touched.
+template <class LD> DCU_FN uint32_t take_bases(LD ld, uint32_t lo, int n, uint32_t blast) {
+  const uint32_t bb = lo >> 2;
+  unsigned long long V = 0;
+  DCU_UNROLL
+  for (uint32_t q = 0; q < 5; ++q) if (bb + q <= blast) V |= (unsigned long long)ld(bb + q) << (8 * (7 - q));
+  return (uint32_t)(V >> (64 - 2 * ((int)(lo & 3) + n))) & (n == 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u));
+}
+template <class LD> DCU_FN void decode_slice(LD ld, const Slice& s, uint32_t* out) {
+  const bool rc = (s.flags & 1) != 0;
+  const uint32_t g0 = s.gpos, g1 = s.gpos + s.len - 1, blast = g1 >> 2;
+  const int len = s.len;
+  DCU_NOUNROLL
+  for (int o = 0; o < len; o += 16) {
+    const int n = len - o < 16 ? len - o : 16;
+    uint32_t wd;
+    if (!rc) {                                       // output base o+t = database base g0+o+t: reverse the order of the n two-bit groups
+      const uint32_t x = take_bases(ld, g0 + (uint32_t)o, n, blast);
+      const uint32_t y = brev32(x) >> (32 - 2 * n);
+      wd = ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
+    } else {                                         // output base o+t = complement of database base g1-o-t: already in place, complement
+      const uint32_t x = take_bases(ld, g1 - (uint32_t)o - (uint32_t)(n - 1), n, blast);
+      wd = (~x) & (n == 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u));
+    }
+    out[o >> 4] = wd;
+  }
+}
+DCU_BIG void load_window(Ctx& c, const Window& win, int lane, const uint8_t* raw) {
   const WS w = c.ws;
   c.MAo = win.slice_cnt; c.overflow = 0;
   if (c.MAo > DCU_CAP.S) { c.overflow = 1; return; }
   const Slice* sl = c.sl + win.slice_begin;
-  {                                                  // slice offsets: warp scan over the descriptor lengths (was a lane-0 loop of dependent loads)
-    uint32_t run = 0; bool big = false;
+  uint32_t runw = 0;
+  {                                                  // base, word and staged-chunk offsets of the slices: warp scans over the descriptors
+    uint32_t run = 0, runr = 0; bool big = false;
     DCU_NOUNROLL
     for (int base = 0; base < c.MAo; base += DCU_NL) {
       const int j = base + lane;
-      const uint32_t len = j < c.MAo ? (uint32_t)sl[j].len : 0u;
+      uint32_t len = 0, cb = 0;
+      if (j < c.MAo) { const Slice s = sl[j]; len = s.len; uint32_t st; slice_chunk(s, st, cb); }
       big = big || len > 255u;                         // slices are at most 255 bases (8-bit instance positions)
-      const uint32_t inc = scan_incl(len, lane);
-      if (j < c.MAo) w.soff()[j] = (uint16_t)(run + inc - len);
-      run += bcast(inc, DCU_NL - 1);
+      const uint32_t nw = (len + 15u) >> 4;
+      const uint32_t inc = scan_incl(len, lane), incw = scan_incl(nw, lane), incr = scan_incl(cb, lane);
+      if (j < c.MAo) { w.soff()[j] = (uint16_t)(run + inc - len); w.sw()[j] = (uint16_t)(runw + incw - nw); w.koff()[j] = (uint16_t)(runr + incr - cb); }      // koff: chunk offsets until build_hash overwrites it
+      run += bcast(inc, DCU_NL - 1); runw += bcast(incw, DCU_NL - 1); runr += bcast(incr, DCU_NL - 1);
     }
     if (ballot(big)) run = 0x10000000u;
-    if (lane == 0) w.soff()[c.MAo] = (uint16_t)(run > 65535u ? 65535u : run);
+    if (lane == 0) { w.soff()[c.MAo] = (uint16_t)(run > 65535u ? 65535u : run); w.sw()[c.MAo] = (uint16_t)(runw > 65535u ? 65535u : runw); }
     c.nbases = (int)(run > 0x0fffffffu ? 0x0fffffff : run);
   }
   wsync();
   DCU_PEAK(0, c.MAo); DCU_PEAK(1, c.nbases);
-  if (c.nbases > DCU_CAP.B || c.nbases > 65000) { c.overflow = 2; return; }
-  // unpack: eight packed bytes (32 bases) are requested together and decoded from a register, instead of one dependent byte load per base
+  if (c.nbases > DCU_CAP.B || c.nbases > 65000 || (int)runw > DCU_CAP.BW) { c.overflow = 2; return; }
   DCU_NOUNROLL
   for (int j = lane; j < c.MAo; j += DCU_NL) {
     const Slice s = sl[j];
-    uint8_t* out = w.bases() + w.soff()[j];
     if (s.len == 0) continue;
-    const bool rc = (s.flags & 1) != 0;
-    const uint32_t g0 = s.gpos, g1 = s.gpos + s.len - 1;              // first / last base of the slice in the packed DB
-    const uint32_t b1 = g1 >> 2;
-    DCU_NOUNROLL
-    for (uint32_t cb = g0 >> 2; cb <= b1; cb += 8) {
-      unsigned long long bits = 0;                                      // byte cb + q in bits [8 (7 - q), 8 (7 - q) + 8): base r of the chunk at shift 62 - 2 r
-      DCU_UNROLL
-      for (uint32_t q = 0; q < 8; ++q) if (cb + q <= b1) bits |= (unsigned long long)ldg(c.packed + cb + q) << (8 * (7 - q));
-      const uint32_t c4 = cb * 4;                                       // <= g1: no wrap even at the end of a 4 Gbase DB
-      const uint32_t r0 = g0 > c4 ? g0 - c4 : 0u, r1 = g1 - c4 < 31u ? g1 - c4 : 31u;
-      DCU_NOUNROLL
-      for (uint32_t r = r0; r <= r1; ++r) {
-        const uint32_t code = (uint32_t)(bits >> (62 - 2 * r)) & 3u, idx = c4 + r - g0;
-        if (!rc) out[idx] = (uint8_t)code; else out[s.len - 1 - idx] = (uint8_t)(3 - code);
-      }
+    uint32_t* out = w.bw() + w.sw()[j];
+    if (raw) {
+      uint32_t st, cb; slice_chunk(s, st, cb);
+      const uint8_t* q = raw + w.koff()[j];
+      decode_slice([q, st](uint32_t b) { return (uint32_t)q[b - st]; }, s, out);
+    } else {
+      const uint8_t* p = c.packed;
+      decode_slice([p](uint32_t b) { return (uint32_t)ldg(p + b); }, s, out);
     }
   }
   wsync();
 }
-DCU_FN int seqlen(const Ctx& c, int j) { return c.ws.soff()[j + 1] - c.ws.soff()[j]; }
 
 // ------------------------------------------------------------------ expected length (HandleContext.hpp:2051-2155)
 DCU_BIG int estimate_length(Ctx& c, int lane) {
@@ -461,91 +412,100 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
   wsync();
 }
 
-// claim / count one k-mer; newly claimed slots are appended to the occupancy list so that nothing ever scans or
-// clears the whole table (the slab is reused from window to window, only touched slots are reset)
-// `old` is what the compare-and-swap of v into slot h returned; follows the probe sequence from there
+// claim / count one k-mer.  `old` is what the compare-and-swap of v into slot h returned; follows the probe sequence from there.
+// hstate[0] counts the claimed slots: the callers stop inserting beyond c.hcap, which keeps free slots in the table
 DCU_NOINL uint32_t hash_insert_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t old) {
   const WS w = c.ws;
   const uint32_t mask = (1u << c.logh) - 1u;
   DCU_NOUNROLL
   for (;;) {
-    if (old == W_EMPTY) { uint32_t t = a_add(&w.hstate()[0], 1); w.occ()[t] = h; a_add(&w.hs()[2 * h + 1], 1); break; }
-    if (old == v) { a_add(&w.hs()[2 * h + 1], 1); break; }
+    if (old == W_EMPTY) { a_add(&w.hstate()[0], 1); hv_inc(&w.hval()[h]); break; }
+    if (old == v) { hv_inc(&w.hval()[h]); break; }
     h = (h + 1) & mask;
-    old = a_cas(&w.hs()[2 * h], W_EMPTY, v);
+    old = a_cas(&w.hkey()[h], W_EMPTY, v);
   }
   return h;
 }
 DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
   const uint32_t h = hslot(c, v);
-  return hash_insert_from(c, v, h, a_cas(&c.ws.hs()[2 * h], W_EMPTY, v));
+  return hash_insert_from(c, v, h, a_cas(&c.ws.hkey()[h], W_EMPTY, v));
 }
-DCU_BIG void build_hash(Ctx& c, int lane) {
+// k-mer instances are numbered seq-major; work is cut into chunks of CH consecutive k-mers of one sequence so that lanes stay
+// balanced whatever the pile depth.  f(j, i, len, v) for k-mer i of sequence j; g(j, v) with the final k-mer of a sequence.
+// koff / choff must hold the instance / chunk offsets (kmer_offsets).
+enum { KCH = 8 };
+template <class F, class G> DCU_FN void for_each_kmer(const Ctx& c, int lane, F f, G g) {
   const WS w = c.ws;
-  if (w.hstate()[1] != 0x600DF00Du) {          // first use of this slab: full initialisation
+  const int nch = (int)w.choff()[c.MAo];
+  DCU_NOUNROLL
+  for (int t = lane; t < nch; t += DCU_NL) {
+    int a = 0, b = c.MAo;                       // last j with choff[j] <= t (sequences without k-mers share the next one's offset)
     DCU_NOUNROLL
-    for (int i = lane; i < DCU_CAP.H; i += DCU_NL) { w.hs()[2 * i] = W_EMPTY; w.hs()[2 * i + 1] = 0xFFFF0000u; }
-    wsync();
-    if (lane == 0) { w.hstate()[0] = 0; w.hstate()[1] = 0x600DF00Du; }
-  } else {
-    int nocc = (int)w.hstate()[0];
+    while (b - a > 1) { int mid = (a + b) >> 1; if ((int)w.choff()[mid] <= t) a = mid; else b = mid; }
+    const int j = a, len = seqlen(c, j), numk = len - c.k + 1;
+    const int i0 = (t - (int)w.choff()[j]) * KCH, i1 = i0 + KCH < numk ? i0 + KCH : numk;
+    const uint32_t* u = slice_words(c, j);
+    uint32_t v = 0;
     DCU_NOUNROLL
-    for (int i = lane; i < nocc; i += DCU_NL) { int h = w.occ()[i]; w.hs()[2 * h] = W_EMPTY; w.hs()[2 * h + 1] = 0xFFFF0000u; }
-    wsync();
+    for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | bget(u, i0 + i);
+    DCU_NOUNROLL
+    for (int i = i0; i < i1; ++i) {
+      v = ((v << 2) & c.kmask) | bget(u, i + c.k - 1);
+      f(j, i, len, v);
+    }
+    if (i1 == numk) g(j, v);
+  }
+}
+DCU_BIG void kmer_offsets(Ctx& c, int lane) {
+  const WS w = c.ws;
+  uint32_t runk = 0, runc = 0;
+  DCU_NOUNROLL
+  for (int base = 0; base < c.MAo; base += DCU_NL) {
+    int j = base + lane; uint32_t nk = 0, nc = 0;
+    if (j < c.MAo) { int len = seqlen(c, j); if (len >= c.k) { nk = (uint32_t)(len - c.k + 1); nc = (nk + KCH - 1) / KCH; } }
+    uint32_t ik = scan_incl(nk, lane), ic = scan_incl(nc, lane);
+    if (j < c.MAo) { w.koff()[j] = (uint16_t)(runk + ik - nk); w.choff()[j] = (uint16_t)(runc + ic - nc); }
+    runk += bcast(ik, DCU_NL - 1); runc += bcast(ic, DCU_NL - 1);
+  }
+  if (lane == 0) { w.koff()[c.MAo] = (uint16_t)runk; w.choff()[c.MAo] = (uint16_t)runc; }
+  c.ni = (int)runk;
+  wsync();
+}
+// pre-filter bit of a k-mer (shared-memory build): two bitmaps, A = seen, B = seen again.  A k-mer that occurs twice always has its
+// B bit set; one that occurs once has it set only when another k-mer shares the bit.  The table then holds the k-mers with B set,
+// which is all a filter frequency >= 2 needs (exact counts decide; false positives have count 1 and are dropped like any singleton).
+DCU_FN uint32_t prebit(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - DCU_CAP.LOGNB); }
+DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
+  const WS w = c.ws;
+  pre = pre && DCU_CAP.NBITS > 0;
+  c.hpre = pre ? 1 : 0;
+  {
+    const int H = 1 << c.logh;
+    DCU_NOUNROLL
+    for (int i = lane; i < H; i += DCU_NL) { w.hkey()[i] = W_EMPTY; w.hval()[i] = hv_make(0, NID_NONE); }
+    if (pre) {
+      DCU_NOUNROLL
+      for (int i = lane; i < DCU_CAP.NBITS / 32; i += DCU_NL) { w.hbA()[i] = 0; w.hbB()[i] = 0; }
+    }
     if (lane == 0) w.hstate()[0] = 0;
   }
-  wsync();
-  // k-mer instances are numbered seq-major; work is cut into chunks of CH consecutive k-mers of one sequence so that
-  // lanes stay balanced whatever the pile depth
-  enum { CH = 8 };
-  {
-    uint32_t runk = 0, runc = 0;
-    DCU_NOUNROLL
-    for (int base = 0; base < c.MAo; base += DCU_NL) {
-      int j = base + lane; uint32_t nk = 0, nc = 0;
-      if (j < c.MAo) { int len = seqlen(c, j); if (len >= c.k) { nk = (uint32_t)(len - c.k + 1); nc = (nk + CH - 1) / CH; } }
-      uint32_t ik = scan_incl(nk, lane), ic = scan_incl(nc, lane);
-      if (j < c.MAo) { w.koff()[j] = (uint16_t)(runk + ik - nk); w.choff()[j] = (uint16_t)(runc + ic - nc); }
-      runk += bcast(ik, DCU_NL - 1); runc += bcast(ic, DCU_NL - 1);
-    }
-    if (lane == 0) { w.koff()[c.MAo] = (uint16_t)runk; w.choff()[c.MAo] = (uint16_t)runc; }
-    c.ni = (int)runk;
+  kmer_offsets(c, lane);
+  if (pre) {
+    for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
+      const uint32_t b = prebit(v), m = 1u << (b & 31);
+      if (a_or(&w.hbA()[b >> 5], m) & m) a_or(&w.hbB()[b >> 5], m);
+    }, [](int, uint32_t) {});
     wsync();
-    const int nch = (int)runc;
-    DCU_NOUNROLL
-    for (int t = lane; t < nch; t += DCU_NL) {
-      int a = 0, b = c.MAo;                       // last j with choff[j] <= t (sequences without k-mers share the next one's offset)
-      DCU_NOUNROLL
-      while (b - a > 1) { int mid = (a + b) >> 1; if ((int)w.choff()[mid] <= t) a = mid; else b = mid; }
-      const int j = a, len = seqlen(c, j), numk = len - c.k + 1;
-      const int i0 = (t - (int)w.choff()[j]) * CH, i1 = i0 + CH < numk ? i0 + CH : numk;
-      const uint8_t* u = w.bases() + w.soff()[j];
-      uint32_t v = 0;
-      DCU_NOUNROLL
-      for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | u[i0 + i];
-      // the first compare-and-swap of every k-mer of the chunk is issued before any result is looked at (CH atomics in flight instead of
-      // one round trip after the other; at load <= 0.5 the first probe settles most k-mers), then the k-mers are completed in order
-      uint32_t kv[CH], kh[CH], ko[CH];
-      DCU_UNROLL
-      for (int e = 0; e < CH; ++e) {
-        kv[e] = 0; kh[e] = 0; ko[e] = 0;
-        if (i0 + e < i1) {
-          v = ((v << 2) & c.kmask) | u[i0 + e + c.k - 1];
-          kv[e] = v; kh[e] = hslot(c, v); ko[e] = a_cas(&w.hs()[2 * kh[e]], W_EMPTY, v);
-        }
-      }
-      const int q0 = (int)w.koff()[j] + i0;
-      DCU_UNROLL
-      for (int e = 0; e < CH; ++e) {
-        if (i0 + e < i1) {
-          const uint32_t h = hash_insert_from(c, kv[e], kh[e], ko[e]);
-          w.islot()[q0 + e] = h; w.praw()[q0 + e] = (uint8_t)(i0 + e); w.rraw()[q0 + e] = (uint8_t)(len - (i0 + e) - c.k);
-        }
-      }
-      if (i1 == numk) w.lastk()[j] = v;             // final k-mer of the sequence (the `last` array, :2108)
-    }
   }
+  bool full = false;
+  for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
+    if (full) return;
+    if (pre) { const uint32_t b = prebit(v); if (!((w.hbB()[b >> 5] >> (b & 31)) & 1u)) return; }      // (bitmaps are final: wsync above)
+    if (a_load(&w.hstate()[0]) > (uint32_t)c.hcap) { full = true; return; }        // racy read of a monotone counter: the overshoot is bounded by the lanes' in-flight inserts
+    hash_insert(c, v);
+  }, [&](int j, uint32_t v) { w.lastk()[j] = v; });                                // final k-mer of the sequence (the `last` array, :2108)
   wsync();
+  if (ballot(full) || w.hstate()[0] > (uint32_t)c.hcap) { c.overflow = 23; wsync(); return; }
   // (count, kmer) of the distinct last k-mers, sorted descending (:1360-1391)
   {
     int nl = 0;
@@ -569,40 +529,47 @@ DCU_BIG void build_hash(Ctx& c, int lane) {
   }
 }
 
-// nodes = k-mers with count >= f (filterFreq :1181-1197), instance lists (setupNodes :1918-2014)
+// nodes = k-mers with count >= f (filterFreq :1181-1197), instance lists (setupNodes :1918-2014), support ranges of every node
+// (computeFeasibleKmerPositions :3117-3174: every node is evaluated at the true positions [supportLow(plow), supportHigh(phigh)),
+// forward from PF and mirrored from RPF; only the ranges are materialised, the weights are evaluated where they are consumed)
 DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   const WS w = c.ws;
-  int nn = 0;
-  const int nocc = (int)w.hstate()[0];
-  DCU_PEAK(14, nocc);
+  const int H = 1 << c.logh;
+#if DCU_TIER_SMEM
   DCU_NOUNROLL
-  for (int base = 0; base < nocc; base += DCU_NL) {
-    int t = base + lane;
-    int i = t < nocc ? (int)w.occ()[t] : 0;
-    const uint32_t cv = t < nocc ? w.hs()[2 * i + 1] : 0; const int cnt = (int)(cv & 0xFFFFu);
-    bool keep = (t < nocc) && (cnt >= f);
-    uint32_t b = ballot(keep);
-    int idx = nn + popc(b & lanemask_lt(lane));
+  for (int h = lane; h < H; h += DCU_NL) { const hval_t v = w.hval()[h]; if (v & 0x8000u) w.hval()[h] = (hval_t)w.n_freq()[v & 0x7FFFu]; }      // slots that carry a node id of an earlier build: back to counts before n_freq is rewritten
+  wsync();
+#endif
+  int nn = 0;
+  DCU_NOUNROLL
+  for (int base = 0; base < H; base += DCU_NL) {
+    const int h = base + lane;                         // H is a multiple of 32
+    const uint32_t key = w.hkey()[h];
+    const int cnt = (int)(w.hval()[h] & 0xFFFFu);
+    const bool occ = key != W_EMPTY, keep = occ && cnt >= f;
+    const uint32_t b = ballot(keep);
+    const int idx = nn + popc(b & lanemask_lt(lane));
     if (keep) {
-      if (idx < DCU_CAP.NN) { w.n_kmer()[idx] = w.hs()[2 * i]; w.n_freq()[idx] = (uint16_t)cnt; w.hs()[2 * i + 1] = (uint32_t)cnt | ((uint32_t)idx << 16); w.n_fill()[idx] = 0; }
-    } else if (t < nocc) w.hs()[2 * i + 1] = (uint32_t)cnt | 0xFFFF0000u;
+      if (idx < DCU_CAP.NN && idx < 0x7FFF) { w.n_kmer()[idx] = key; w.n_freq()[idx] = (uint16_t)cnt; w.hval()[h] = hv_make(cnt, idx); w.fillcnt()[idx] = 0; }
+    } else if (occ) w.hval()[h] = hv_make(cnt, NID_NONE);
     nn += popc(b);
   }
+  DCU_PEAK(14, (int)w.hstate()[0]);
   DCU_PEAK(2, nn);
-  if (nn > DCU_CAP.NN || nn >= NID_NONE) { c.overflow = 3; c.nn = 0; wsync(); return; }
+  if (nn > DCU_CAP.NN || nn >= 0x7FFF) { c.overflow = 3; c.nn = 0; wsync(); return; }
   // graphs this large (the filterfreq-1 fall-through) take ~50 ms on one warp: in the phase-synchronous pass they would
   // hold their whole warp group, so they are handed to the free-running large-workspace pass instead
   if (DCU_CAP.HEAVY && nn > DCU_CAP.HEAVY) { c.overflow = 21; c.nn = 0; wsync(); return; }
   c.nn = nn;
   wsync();
-  {                                                  // instance list offsets: warp scan over the node frequencies (was a lane-0 loop)
+  {                                                  // instance list offsets: warp scan over the node frequencies
     uint32_t run = 0;
     DCU_NOUNROLL
     for (int base = 0; base < nn; base += DCU_NL) {
       const int n = base + lane;
       const uint32_t f0 = n < nn ? (uint32_t)w.n_freq()[n] : 0u;
       const uint32_t inc = scan_incl(f0, lane);
-      if (n < nn) w.n_ioff()[n] = run + inc - f0;
+      if (n < nn) w.n_ioff()[n] = (ioff_t)(run + inc - f0);
       run += bcast(inc, DCU_NL - 1);
     }
     c.ni = (int)run;
@@ -610,24 +577,15 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   wsync();
   DCU_PEAK(3, c.ni);
   if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
-  {
-    const int nraw = (int)w.koff()[c.MAo];
-    DCU_NOUNROLL
-    // two dependent loads (slot -> node id) in front of an atomic round trip per instance: the node id of the lane's next instance is
-    // requested before this one is filed
-    int n = lane < nraw ? (int)(w.hs()[2 * w.islot()[lane] + 1] >> 16) : NID_NONE;
-    DCU_NOUNROLL
-    for (int q = lane; q < nraw; q += DCU_NL) {
-      const int qn = q + DCU_NL;
-      const int nn1 = qn < nraw ? (int)(w.hs()[2 * w.islot()[qn] + 1] >> 16) : NID_NONE;
-      if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill()[n], 1); w.ipos()[w.n_ioff()[n] + t] = w.praw()[q]; w.irpos()[w.n_ioff()[n] + t] = w.rraw()[q]; }
-      n = nn1;
-    }
-  }
+  // instances are filed under their nodes: the k-mers are rolled once more and looked up (no per-instance slot array)
+  for_each_kmer(c, lane, [&](int, int i, int len, uint32_t v) {
+    const int n = lookup(c, v);
+    if (n != NID_NONE) { const uint32_t t = add16(&w.fillcnt()[n], 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = (uint8_t)i; w.irpos()[t] = (uint8_t)(len - i - c.k); }
+  }, [](int, uint32_t) {});
   DCU_NOUNROLL
   for (int e = lane; e < c.nex; e += DCU_NL) {       // synthesised k-mers of the gap filler (:1148-1157)
     int n = lookup(c, w.ex_kmer()[e]);
-    if (n != NID_NONE) { uint32_t t = a_add(&w.n_fill()[n], 1); w.ipos()[w.n_ioff()[n] + t] = w.ex_pos()[e]; w.irpos()[w.n_ioff()[n] + t] = w.ex_rpos()[e]; }
+    if (n != NID_NONE) { const uint32_t t = add16(&w.fillcnt()[n], 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = w.ex_pos()[e]; w.irpos()[t] = w.ex_rpos()[e]; }
   }
   wsync();
   uint32_t nf = 0;
@@ -639,15 +597,15 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
       int f0 = w.n_freq()[n]; const uint8_t* ip = w.ipos() + w.n_ioff()[n]; const uint8_t* irp = w.irpos() + w.n_ioff()[n];
       int lo = 255, hi = 0, clo = 255, chi = 0;
       DCU_NOUNROLL
-      for (int t = 0; t < f0; t += 4) {                   // four instances per step: the eight loads are requested before the first is used
-        const int m1 = t + 1 < f0 ? t + 1 : t, m2 = t + 2 < f0 ? t + 2 : t, m3 = t + 3 < f0 ? t + 3 : t;      // past the end: instance t again (min / max unchanged)
-        const int a0 = ip[t], a1 = ip[m1], a2 = ip[m2], a3 = ip[m3], b0 = irp[t], b1 = irp[m1], b2 = irp[m2], b3 = irp[m3];
-        const int amin = (a0 < a1 ? a0 : a1) < (a2 < a3 ? a2 : a3) ? (a0 < a1 ? a0 : a1) : (a2 < a3 ? a2 : a3), amax = (a0 > a1 ? a0 : a1) > (a2 > a3 ? a2 : a3) ? (a0 > a1 ? a0 : a1) : (a2 > a3 ? a2 : a3);
-        const int bmin = (b0 < b1 ? b0 : b1) < (b2 < b3 ? b2 : b3) ? (b0 < b1 ? b0 : b1) : (b2 < b3 ? b2 : b3), bmax = (b0 > b1 ? b0 : b1) > (b2 > b3 ? b2 : b3) ? (b0 > b1 ? b0 : b1) : (b2 > b3 ? b2 : b3);
-        lo = amin < lo ? amin : lo; hi = amax > hi ? amax : hi; clo = bmin < clo ? bmin : clo; chi = bmax > chi ? bmax : chi;
-        c0 += (a0 == 0) + (t + 1 < f0 && a1 == 0) + (t + 2 < f0 && a2 == 0) + (t + 3 < f0 && a3 == 0);
+      for (int t = 0; t < f0; ++t) {
+        const int a0 = ip[t], b0 = irp[t];
+        lo = a0 < lo ? a0 : lo; hi = a0 > hi ? a0 : hi; clo = b0 < clo ? b0 : clo; chi = b0 > chi ? b0 : chi;
+        c0 += (a0 == 0);
       }
-      w.n_plow()[n] = (uint8_t)lo; w.n_phigh()[n] = (uint8_t)hi; w.n_cplow()[n] = (uint8_t)clo; w.n_cphigh()[n] = (uint8_t)chi;
+      int pf = sup_lo(c, lo), pt = sup_hi(c, hi), cf = sup_lo(c, clo), ct = sup_hi(c, chi);
+      if (pt < pf) pt = pf;
+      if (ct < cf) ct = cf;
+      w.n_pf()[n] = (uint8_t)pf; w.n_pt()[n] = (uint8_t)pt; w.n_cpf()[n] = (uint8_t)cf; w.n_cpt()[n] = (uint8_t)ct;
     }
     uint32_t b = ballot(c0 > 0);               // k-mers seen at position 0 (maxForPosList :1280-1304)
     int idx = (int)nf + popc(b & lanemask_lt(lane));
@@ -714,7 +672,7 @@ DCU_BIG void build_edges(Ctx& c, int lane) {
     }
     DCU_NOUNROLL
     for (int e = 0; e < 4; ++e) { w.n_sfreq()[4 * n + e] = e < ns ? (uint16_t)(key[e] >> 8) : 0; w.n_snid()[4 * n + e] = e < ns ? nid[e] : (uint16_t)NID_NONE; }
-    w.n_nsucc()[n] = (uint8_t)ns; w.n_nact()[n] = (uint8_t)na; w.n_mark()[n] = 0;
+    w.n_nsucc()[n] = (uint8_t)ns; w.n_nact()[n] = (uint8_t)na;
   }
   wsync();
   compute_npred(c, lane);
@@ -739,30 +697,13 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
   return true;
 }
 
-// ------------------------------------------------------------------ per-node support ranges
-// computeFeasibleKmerPositions (:3117-3174) evaluates every node at every true position of its support range
-// [supportLow(plow), supportHigh(phigh)) (forward, PF) and the mirrored range (reverse, RPF).  Only the ranges are
-// materialised here; the weights themselves (:3826-3904) are fixed-point sums evaluated where they are consumed
-// (stretch_positions, kw_fwd / kw_rev).
-DCU_BIG void node_ranges(Ctx& c, int lane) {
-  const WS w = c.ws;
-  DCU_NOUNROLL
-  for (int n = lane; n < c.nn; n += DCU_NL) {
-    int pf = sup_lo(c, w.n_plow()[n]), pt = sup_hi(c, w.n_phigh()[n]);
-    int cf = sup_lo(c, w.n_cplow()[n]), ct = sup_hi(c, w.n_cphigh()[n]);
-    if (pt < pf) pt = pf;
-    if (ct < cf) ct = cf;
-    w.n_pf()[n] = (uint8_t)pf; w.n_pt()[n] = (uint8_t)pt; w.n_cpf()[n] = (uint8_t)cf; w.n_cpt()[n] = (uint8_t)ct;
-  }
-  wsync();
-}
 DCU_NOINL double kw_fwd(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_T.NP) ? kweight(c, n, p, false) : 0.0; }
 DCU_NOINL double kw_rev(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_T.NP) ? kweight(c, n, p, true) : 0.0; }
 
 // ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
 DCU_BIG void gap_fill(Ctx& c, int lane) {
   const WS w = c.ws;
-  uint32_t* nexp = &w.n_fill()[0];      // n_fill[0] doubles as the append counter here (rebuilt afterwards)
+  uint32_t* nexp = &w.hstate()[2];      // append counter
   if (lane == 0) *nexp = 0;
   wsync();
   DCU_NOUNROLL
@@ -802,6 +743,7 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   wsync();
   DCU_PEAK(4, nex);
   if (nex > DCU_CAP.EX) { c.overflow = 6; c.nex = 0; return; }
+  if ((int)w.hstate()[0] + nex >= (1 << c.logh) - 1) { c.overflow = 23; c.nex = 0; return; }      // the extras must leave a free slot in the table
   c.nex = nex;
   DCU_NOUNROLL
   for (int e = lane; e < nex; e += DCU_NL) hash_insert(c, w.ex_kmer()[e]);
@@ -1151,7 +1093,7 @@ DCU_FN double rev_wf(const Ctx& c, int s, int p) { return kw_rev(c, ds_last(c, s
 // max over common reverse positions of w_B + (w_A - wf_A) >= 0.1; stored as (B,A), sorted; lanes over A
 DCU_BIG void stretch_links(Ctx& c, int lane) {
   const WS w = c.ws;
-  uint32_t* cnt = &w.n_fill()[0];
+  uint32_t* cnt = &w.hstate()[3];
   if (lane == 0) *cnt = 0;
   wsync();
   DCU_NOUNROLL
@@ -1198,14 +1140,22 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
 }
 
 // ------------------------------------------------------------------ Myers bit-vector edit distance
-// global unit-cost distance of pattern (<=64, Peq masks) against text t[0,n)
-DCU_NOINL int myers_dist(const unsigned long long* peq, int m, const uint8_t* t, int n) {
+struct Peq { unsigned long long p[4]; };
+DCU_FN unsigned long long peq_of(const Peq& q, uint32_t code) { return (code & 2u) ? ((code & 1u) ? q.p[3] : q.p[2]) : ((code & 1u) ? q.p[1] : q.p[0]); }      // selects, no indexed local array
+DCU_FN void peq_set(Peq& q, uint32_t code, int i) {
+  const unsigned long long b = 1ull << i;
+  q.p[0] |= code == 0 ? b : 0ull; q.p[1] |= code == 1 ? b : 0ull; q.p[2] |= code == 2 ? b : 0ull; q.p[3] |= code == 3 ? b : 0ull;
+}
+// global unit-cost distance of pattern (<=64, Peq masks) against the packed text t[0,n) (16 base codes per word)
+DCU_NOINL int myers_dist(const Peq peq, int m, const uint32_t* t, int n) {
   if (m == 0) return n;
   unsigned long long pv = ~0ull, mv = 0, top = 1ull << (m - 1);
   int score = m;
+  uint32_t wd = 0;
   DCU_NOUNROLL
   for (int j = 0; j < n; ++j) {
-    unsigned long long eq = peq[t[j]];
+    if ((j & 15) == 0) wd = t[j >> 4];
+    unsigned long long eq = peq_of(peq, wd & 3u); wd >>= 2;
     unsigned long long xv = eq | mv;
     unsigned long long xh = (((eq & pv) + pv) ^ pv) | eq;
     unsigned long long ph = mv | ~(xh | pv);
@@ -1216,10 +1166,11 @@ DCU_NOINL int myers_dist(const unsigned long long* peq, int m, const uint8_t* t,
   }
   return score;
 }
-DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool ascii) {
-  peq[0] = peq[1] = peq[2] = peq[3] = 0;
+DCU_FN int ascii_code(int ch) { return (ch == 'A') ? 0 : (ch == 'C') ? 1 : (ch == 'G') ? 2 : 3; }
+DCU_FN Peq make_peq_ascii(const uint8_t* pat, int m) {      // candidate strings (ASCII, 8-byte aligned slots): eight symbols per load
+  Peq q; q.p[0] = q.p[1] = q.p[2] = q.p[3] = 0;
   int i = 0;
-  if ((((size_t)pat) & 7) == 0) {                  // aligned pattern (candidate slots, the A slice): eight symbols per load
+  if ((((size_t)pat) & 7) == 0) {
     DCU_NOUNROLL
     for (; i + 8 <= m; i += 8) {
 #ifdef DCU_EMU
@@ -1228,19 +1179,19 @@ DCU_FN void make_peq(unsigned long long* peq, const uint8_t* pat, int m, bool as
       const unsigned long long wd = *(const unsigned long long*)(pat + i);
 #endif
       DCU_NOUNROLL
-      for (int b = 0; b < 8; ++b) {
-        int cde = (int)((wd >> (8 * b)) & 0xFF);
-        if (ascii) cde = (cde == 'A') ? 0 : (cde == 'C') ? 1 : (cde == 'G') ? 2 : 3;
-        peq[cde] |= 1ull << (i + b);
-      }
+      for (int b = 0; b < 8; ++b) peq_set(q, (uint32_t)ascii_code((int)((wd >> (8 * b)) & 0xFF)), i + b);
     }
   }
   DCU_NOUNROLL
-  for (; i < m; ++i) {
-    int cde = pat[i];
-    if (ascii) cde = (cde == 'A') ? 0 : (cde == 'C') ? 1 : (cde == 'G') ? 2 : 3;
-    peq[cde] |= 1ull << i;
-  }
+  for (; i < m; ++i) peq_set(q, (uint32_t)ascii_code(pat[i]), i);
+  return q;
+}
+DCU_FN Peq make_peq_packed(const uint32_t* t, int m) {      // a slice of the window (packed codes)
+  Peq q; q.p[0] = q.p[1] = q.p[2] = q.p[3] = 0;
+  uint32_t wd = 0;
+  DCU_NOUNROLL
+  for (int i = 0; i < m; ++i) { if ((i & 15) == 0) wd = t[i >> 4]; peq_set(q, wd & 3u, i); wd >>= 2; }
+  return q;
 }
 
 // ------------------------------------------------------------------ traverse (:4496-5170)
@@ -1618,11 +1569,10 @@ DCU_BIG int trav_finish(Ctx& c, TravState& t, int lane) {
   DCU_NOUNROLL
   for (int a = 0; a < nacc; ++a) {
     int slot = w.acc_slot()[a], m = w.candlen()[slot];
-    unsigned long long peq[4];
-    make_peq(peq, w.cand() + slot * MAXCAND, m, true);
+    const Peq peq = make_peq_ascii(w.cand() + slot * MAXCAND, m);
     uint32_t e = 0;
     DCU_NOUNROLL
-    for (int j = lane; j < c.MAo; j += DCU_NL) e += (uint32_t)myers_dist(peq, m, w.bases() + w.soff()[j], seqlen(c, j));
+    for (int j = lane; j < c.MAo; j += DCU_NL) e += (uint32_t)myers_dist(peq, m, slice_words(c, j), seqlen(c, j));
     e = red_sum_u32(e);
     if (lane == 0) w.acc_err()[a] = e;
   }
@@ -1643,15 +1593,13 @@ DCU_BIG int trav_finish(Ctx& c, TravState& t, int lane) {
 
 // ------------------------------------------------------------------ placement: align(A window, consensus) with traceback
 // (HandleContext.hpp:2434-2493); convention C1 via bit-vector deltas.  lane 0.  Returns number of ops.
-DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int lb, uint8_t* ops) {
+DCU_BIG int placement(Ctx& c, const uint32_t* a, int la, const uint8_t* cons, int lb, uint8_t* ops) {
   const WS w = c.ws;
-  unsigned long long peq[4];
-  make_peq(peq, a, la, false);            // a = base codes
+  const Peq peq = make_peq_packed(a, la);            // a = packed base codes of the A window
   unsigned long long pv = ~0ull, mv = 0;
   DCU_NOUNROLL
   for (int j = 1; j <= lb; ++j) {
-    int ch = cons[j - 1]; ch = (ch == 'A') ? 0 : (ch == 'C') ? 1 : (ch == 'G') ? 2 : 3;
-    unsigned long long eq = peq[ch];
+    unsigned long long eq = peq_of(peq, (uint32_t)ascii_code(cons[j - 1]));
     unsigned long long xv = eq | mv;
     unsigned long long xh = (((eq & pv) + pv) ^ pv) | eq;
     unsigned long long ph = mv | ~(xh | pv);
@@ -1669,7 +1617,7 @@ DCU_BIG int placement(Ctx& c, const uint8_t* a, int la, const uint8_t* cons, int
     if (i > 0 && j > 0) {
       int dv = ((w.m_pv()[j] >> (i - 1)) & 1ull) ? 1 : (((w.m_mv()[j] >> (i - 1)) & 1ull) ? -1 : 0);
       int dhup = (i == 1) ? 1 : (((w.m_ph()[j] >> (i - 2)) & 1ull) ? 1 : (((w.m_mh()[j] >> (i - 2)) & 1ull) ? -1 : 0));
-      int ca = a[i - 1]; int cb = cons[j - 1]; cb = (cb == 'A') ? 0 : (cb == 'C') ? 1 : (cb == 'G') ? 2 : 3;
+      int ca = (int)bget(a, i - 1); int cb = ascii_code(cons[j - 1]);
       int cost = ca != cb;
       if (dv + dhup == cost) { op = cost ? 1 : 0; --i; --j; }
       else if (dv == 1) { op = 3; --i; }
@@ -1703,17 +1651,19 @@ struct WinState {
 
 DCU_FN void st_overflow(Ctx& c, WinState& s) { s.res.status = ST_OVERFLOW; s.res.err = (uint32_t)c.overflow; s.ph = PH_END; }
 
-DCU_BIG void st_begin(Ctx& c, WinState& s, const Window& win, int lane) {
+DCU_BIG void st_begin(Ctx& c, WinState& s, const Window& win, int lane, const uint8_t* raw) {
   Result& res = s.res;
   res.status = ST_SKIPPED; res.k = 0; res.ff = -1; res.clen = 0; res.err = 0; res.nops = 0; res.ncand = 0; res.elength = 0;
   s.ph = PH_END;
-  load_window(c, win, lane);
+  load_window(c, win, lane, raw);
   if (c.overflow) { st_overflow(c, s); return; }
   // hash size of this window: the smallest power of two above (k-mer instances + gap filler extras), so that a free slot always
   // remains, instead of the batch-wide capacity: a 40x window then spreads its ~870 distinct k-mers over 2 048 slots (16 KB) and
   // not over 8 192 (64 KB, one useful slot per touched 32-byte sector -- 42 % of all bytes a window touched, tools/field_traffic.py).
   // Results do not depend on the table size (the two workspace tiers already differ in it).
-  { int lg = 5; const int need = c.nbases + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; }
+  // Where the capacity (LOGH) cuts the size short, the table only takes hcap distinct k-mers (the margin covers the inserts in flight
+  // when the limit is noticed); beyond that the window is handed to the next pass.
+  { int lg = 5; const int need = c.nbases + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; c.hcap = (1 << lg) >= need ? 0x7fffffff : (1 << lg) - 288; }
   int elength = estimate_length(c, lane);
   res.elength = elength;
   if (c.MAo < DCU_P.mincov) return;
@@ -1727,20 +1677,22 @@ DCU_BIG void st_hash(Ctx& c, WinState& s, int lane) {
   const int k = s.k;
   c.k = k; c.kidx = k - DCU_P.k_lo; c.kmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
   c.nex = 0;
-  build_hash(c, lane);
+  build_hash(c, lane, DCU_P.maxff >= 2);
+  if (c.overflow) { st_overflow(c, s); return; }
   s.ff = DCU_P.maxff; s.ph = PH_NODES;
 }
 DCU_BIG void st_nodes(Ctx& c, WinState& s, int lane) {
   const int ff = s.ff, f = ff > 1 ? ff : 1;
-  if (c.nex) { c.nex = 0; build_hash(c, lane); }     // a previous gap fill touched the counts
+  if (c.nex || (c.hpre && f < 2)) {                  // a previous gap fill touched the counts, or the table only holds the pre-filtered k-mers
+    c.nex = 0; build_hash(c, lane, false);
+    if (c.overflow) { st_overflow(c, s); return; }
+  }
   build_nodes(c, f, lane);
-  if (!c.overflow) node_ranges(c, lane);
   if (c.overflow) { st_overflow(c, s); return; }
   if (ff == 0) {
     gap_fill(c, lane);
     if (c.overflow) { st_overflow(c, s); return; }
     build_nodes(c, 1, lane);                         // setupNodes over all prenodes (:2248)
-    if (!c.overflow) node_ranges(c, lane);
     if (c.overflow) { st_overflow(c, s); return; }
   }
   s.ph = PH_EDGES;
@@ -1825,7 +1777,7 @@ DCU_BIG void st_final(Ctx& c, WinState& s, uint8_t* cons_out, uint8_t* ops_out, 
   if (lane == 0) {
     DCU_NOUNROLL
     for (int i = 0; i < s.bestlen; ++i) cons_out[i] = w.best()[i];
-    nops = placement(c, w.bases(), DCU_P.w, w.best(), s.bestlen, ops_out);
+    nops = placement(c, slice_words(c, 0), DCU_P.w, w.best(), s.bestlen, ops_out);
   }
   nops = bcast(nops, 0);
   if (nops < 0) { c.overflow = 20; st_overflow(c, s); return; }
@@ -1844,7 +1796,7 @@ struct PhaseTimer {
 #endif
 DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons_out, uint8_t* ops_out, int lane) {
   WinState s;
-  st_begin(c, s, win, lane);
+  st_begin(c, s, win, lane, nullptr);
   while (s.ph != PH_END) {
 #if defined(DCU_EMU) && defined(DCU_EMU_STATS)
     PhaseTimer pt_(s.ph);
@@ -1862,4 +1814,12 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
   res = s.res;
 }
 
-}  // namespace dcu
+}  // namespace DCU_NS
+
+#undef DCU_WS_FIELDS
+#undef DCU_LAYOUT
+#undef DCU_CAP
+#undef DCU_T
+#undef DCU_P
+#undef DCU_NS
+#undef DCU_TIER_SMEM

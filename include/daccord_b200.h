@@ -46,7 +46,10 @@ typedef struct dcu_window { uint32_t slice_begin; uint16_t slice_cnt; uint16_t r
 
 enum { DCU_WIN_SKIPPED = 0,   /* slice_cnt < -m : "insufficient depth" (HandleContext.hpp:2499-2503) */
        DCU_WIN_OK = 1,        /* consensus found */
-       DCU_WIN_FAILED = 2 };  /* all k / filterfreq attempts failed (HandleContext.hpp:2496-2497) */
+       DCU_WIN_FAILED = 2,    /* all k / filterfreq attempts failed (HandleContext.hpp:2496-2497) */
+       DCU_WIN_OVERFLOW = 250 }; /* the window exceeded every workspace capacity of this build (err = capacity code): no consensus;
+                                    callers treat it like DCU_WIN_FAILED and log it -- one window never fails a batch (the reference
+                                    swallows a read's exception and continues, src/daccord.cpp:2466-2478) */
 #define DCU_CONS_STRIDE 64    /* bytes of consensus arena per window (ASCII) */
 #define DCU_OPS_STRIDE 128    /* bytes of placement-trace arena per window */
 /* placement trace steps, one byte each, forward order (libmaus2 BaseConstants::STEP_*) */
@@ -114,6 +117,9 @@ int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* rea
 int dcu_get_corrected(dcu_ctx* ctx, dcu_segment* seg, char* chars);
 /* statistics of the last launch: kernels launched, windows that needed the large-workspace pass */
 int dcu_last_stats(dcu_ctx* ctx, uint64_t* launches, uint64_t* hard_windows);
+/* more statistics of the last launch: windows the shared-memory pass handed to the HBM passes, windows beyond every capacity
+ * (status DCU_WIN_OVERFLOW), warps per SM and shared-memory bytes per warp of the shared-memory pass (0 warps = pass not used) */
+int dcu_last_stats2(dcu_ctx* ctx, uint64_t* second_pass_windows, uint64_t* lost_windows, uint32_t* smem_warps, uint32_t* smem_bytes_per_warp);
 /* dump the host-built tables (for tests): returns number of doubles written / needed */
 int64_t dcu_get_tables(dcu_ctx* ctx, int which, double* out, int64_t cap);
 const char* dcu_strerror(int code);

@@ -41,7 +41,7 @@ def build_oracle():
 def build_emu():
     out = os.path.join(ROOT, "tests", "emu", "_build", "libemu.so")
     src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
-    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "host_tables.hpp", "host_caps.hpp", "pile_core.cuh", "pile_host.hpp", "vote_core.cuh", "vote_host.hpp")]
+    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "window_types.cuh", "host_tables.hpp", "host_caps.hpp", "pile_core.cuh", "pile_host.hpp", "vote_core.cuh", "vote_host.hpp")] + [os.path.join(ROOT, "tests", "emu", "emu_builds.hpp")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src])
@@ -51,7 +51,7 @@ def build_emu():
 def build_emu_lanes():
     out = os.path.join(ROOT, "tests", "emu", "_build", "libemu_lanes.so")
     src = os.path.join(ROOT, "tests", "emu", "emu_lanes.cpp")
-    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "host_tables.hpp", "host_caps.hpp")]
+    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "window_types.cuh", "host_tables.hpp", "host_caps.hpp")] + [os.path.join(ROOT, "tests", "emu", "emu_builds.hpp")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", out, src])
@@ -117,7 +117,7 @@ class TsanUnavailable(Exception):
 def build_emu_tsan():
     out = os.path.join(ROOT, "tests", "emu", "_build", "emu_tsan")
     src = os.path.join(ROOT, "tests", "emu", "emu_tsan.cpp")
-    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "host_tables.hpp", "host_caps.hpp")]
+    deps = [src] + [os.path.join(ROOT, "daccord_b200", "csrc", f) for f in ("window_core.cuh", "window_types.cuh", "host_tables.hpp", "host_caps.hpp")] + [os.path.join(ROOT, "tests", "emu", "emu_builds.hpp")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         r = subprocess.run(["/usr/bin/g++", "-fsanitize=thread", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-pthread", "-o", out, src], capture_output=True, text=True)

@@ -2,9 +2,7 @@
 // emulation (-DDCU_EMU): lets the parity tests exercise the product's per-window logic against the
 // oracle in a container without a GPU.  Never linked into the product library.
 #define DCU_EMU 1
-#include "../../daccord_b200/csrc/window_core.cuh"
-#include "../../daccord_b200/csrc/host_tables.hpp"
-#include "../../daccord_b200/csrc/host_caps.hpp"
+#include "emu_builds.hpp"
 #include "../../include/daccord_b200.h"
 #include <vector>
 #include <cstring>
@@ -16,8 +14,8 @@
 extern "C" void trace_begin_window(const uint8_t* base, uint64_t bytes, const uint32_t* off, int nfields);      // tests/emu/trace_rt.cpp
 extern "C" void trace_end_window();
 #endif
-extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
-                             dcu_result* res, uint8_t* cons, uint8_t* ops, int tier, uint64_t* noverflow) {
+template <class B> static int run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
+                                        dcu_result* res, uint8_t* cons, uint8_t* ops, int tier, uint64_t* noverflow) {
   dcu_host::HostTables HT;
   int maxS = 4, maxB = 64;
   for (uint64_t i = 0; i < nwin; ++i) {
@@ -26,19 +24,14 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
     maxS = std::max<int>(maxS, win[i].slice_cnt); maxB = std::max(maxB, b);
   }
   dcu_host::build_tables((int)prm->w, prm->p_i, prm->p_d, prm->est_cor, (int)prm->k_lo, (int)prm->k_hi, maxS + 2, HT);
-  dcu::Caps caps = dcu_host::make_caps(tier, (int)prm->w, maxS, maxB);
-  dcu::Layout L; dcu::make_layout(caps, L);
-  std::vector<uint8_t> slab(L.bytes + 64);
+  dcu::Caps caps = emu::caps_for(tier, (int)prm->w, maxS, maxB);
+  typename B::Layout L; B::layout(caps, L);
+  std::vector<uint8_t> slab(L.bytes + 64), arena(L.sbytes + 64);
   dcu::Tables T; dcu::Params P;
-  T.DPn = HT.DPn.data(); T.DPsq = HT.DPsq.data(); T.VSq = HT.VSq.data(); T.suplo = HT.suplo.data(); T.suphi = HT.suphi.data();
-  T.klim = HT.klim.data(); T.NP = HT.NP; T.MS = HT.MS; T.KLIMN = HT.KLIMN;
-  P.w = (int)prm->w; P.k_lo = (int)prm->k_lo; P.k_hi = (int)prm->k_hi; P.minff = prm->min_ff; P.maxff = prm->max_ff;
-  P.mincov = (int)prm->min_cov; P.check = prm->est_cor != 0.0; P.eminrate = prm->max_err;
-  P.defer_ff = (tier == 0 && getenv("DCU_DEFER_FF")) ? 1 : 0;
-  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }        // same experimental switch as the library's first pass
-  dcu::g_layout = L; dcu::g_cap = caps; dcu::g_T = T; dcu::g_P = P;
-  dcu::Ctx c;
-  c.ws.base = slab.data(); c.vsq = T.VSq;
+  emu::tables_for(HT, T); emu::params_for(prm, tier, P);
+  B::globals(L, caps, T, P);
+  typename B::Ctx c;
+  B::bind(c, slab.data(), arena.data()); c.vsq = T.VSq;
   c.packed = packed; c.sl = (const dcu::Slice*)sl;
   uint64_t nov = 0;
   for (uint64_t i = 0; i < nwin; ++i) {
@@ -52,7 +45,7 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
 #ifdef DCU_EMU_TRACE
     trace_begin_window(slab.data(), L.bytes, L.off, (int)dcu::F_COUNT);
 #endif
-    dcu::process_window(c, W, r, cons + i * DCU_CONS_STRIDE, ops + i * DCU_OPS_STRIDE, 0);
+    B::process(c, W, r, cons + i * DCU_CONS_STRIDE, ops + i * DCU_OPS_STRIDE, 0);
 #ifdef DCU_EMU_TRACE
     trace_end_window();
 #endif
@@ -73,6 +66,12 @@ extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const
 #endif
   if (noverflow) *noverflow = nov;
   return 0;
+}
+// tier 0 / 1: HBM build with the capacities of the library's first / second overflow pass; tier 2: shared-memory build
+extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
+                             dcu_result* res, uint8_t* cons, uint8_t* ops, int tier, uint64_t* noverflow) {
+  return tier == 2 ? run_batch<emu::BuildS>(prm, packed, win, nwin, sl, res, cons, ops, tier, noverflow)
+                   : run_batch<emu::BuildG>(prm, packed, win, nwin, sl, res, cons, ops, tier, noverflow);
 }
 // product table builder exposed for the table-parity test
 extern "C" int64_t emu_get_tables(const dcu_params* prm, int which, double* out, int64_t cap, int klimn) {

@@ -10,10 +10,7 @@
 // Never linked into the product library.
 #define DCU_EMU 1
 #define DCU_EMU_LANES 1
-#include "../../daccord_b200/csrc/window_core.cuh"
-#include "../../daccord_b200/csrc/host_tables.hpp"
-#include "../../daccord_b200/csrc/host_caps.hpp"
-#include "../../include/daccord_b200.h"
+#include "emu_builds.hpp"
 #include <ucontext.h>
 #include <vector>
 #include <cstring>
@@ -68,12 +65,14 @@ unsigned g_gen = 0; int g_arrived = 0;
 unsigned long long g_ncoll = 0;
 
 // what one lane runs
-struct LaneJob { dcu::Ctx c; dcu::Window W; dcu::Result r; uint8_t* cons; uint8_t* ops; };
+struct LaneJob { dcu::Ctx c; dcus::Ctx cs; dcu::Window W; dcu::Result r; uint8_t* cons; uint8_t* ops; };
 LaneJob g_job[NL];
 Fiber g_fib[NL];
+bool g_smem_build = false;             // tier 2: the shared-memory build of the kernel source
 void lane_main(int lane) {
   LaneJob& j = g_job[lane];
-  dcu::process_window(j.c, j.W, j.r, j.cons, j.ops, lane);
+  if (g_smem_build) dcus::process_window(j.cs, j.W, j.r, j.cons, j.ops, lane);
+  else dcu::process_window(j.c, j.W, j.r, j.cons, j.ops, lane);
   g_fib[lane].finished = true;
   TO_SCHED(lane);
 }
@@ -83,7 +82,7 @@ uint64_t g_rng = 1;
 inline uint32_t rnd() { g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(g_rng >> 33); }
 }  // namespace
 
-namespace dcu {
+namespace dcub {
 int emu_skip_sync_line = -1;
 __attribute__((noinline)) const unsigned long long* emu_xchg(unsigned long long v) {
   const int lane = g_cur; const unsigned g = g_gen;
@@ -93,7 +92,7 @@ __attribute__((noinline)) const unsigned long long* emu_xchg(unsigned long long 
   else while (g_gen == g) TO_SCHED(lane);
   return g_x[g & 1];
 }
-}  // namespace dcu
+}  // namespace dcub
 
 // returns 0, or 1 = deadlock (lanes diverged around a collective), 2 = lanes disagree on the result record
 static int run_warp(int schedule) {
@@ -146,17 +145,13 @@ extern "C" int emu_lanes_run_batch(const dcu_params* prm, const uint8_t* packed,
     maxS = std::max<int>(maxS, win[i].slice_cnt); maxB = std::max(maxB, b);
   }
   dcu_host::build_tables((int)prm->w, prm->p_i, prm->p_d, prm->est_cor, (int)prm->k_lo, (int)prm->k_hi, maxS + 2, HT);
-  dcu::Caps caps = dcu_host::make_caps(tier, (int)prm->w, maxS, maxB);
-  dcu::Layout L; dcu::make_layout(caps, L);
-  std::vector<uint8_t> slab(L.bytes + 64);
+  dcu::Caps caps = emu::caps_for(tier, (int)prm->w, maxS, maxB);
+  g_smem_build = tier == 2;
+  dcu::Layout L; dcus::Layout LS; dcu::make_layout(caps, L); dcus::make_layout(caps, LS);
+  std::vector<uint8_t> slab((g_smem_build ? LS.bytes : L.bytes) + 64), arena(LS.sbytes + 64);
   dcu::Tables T; dcu::Params P;
-  T.DPn = HT.DPn.data(); T.DPsq = HT.DPsq.data(); T.VSq = HT.VSq.data(); T.suplo = HT.suplo.data(); T.suphi = HT.suphi.data();
-  T.klim = HT.klim.data(); T.NP = HT.NP; T.MS = HT.MS; T.KLIMN = HT.KLIMN;
-  P.w = (int)prm->w; P.k_lo = (int)prm->k_lo; P.k_hi = (int)prm->k_hi; P.minff = prm->min_ff; P.maxff = prm->max_ff;
-  P.mincov = (int)prm->min_cov; P.check = prm->est_cor != 0.0; P.eminrate = prm->max_err;
-  P.defer_ff = (tier == 0 && getenv("DCU_DEFER_FF")) ? 1 : 0;
-  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }
-  dcu::g_layout = L; dcu::g_cap = caps; dcu::g_T = T; dcu::g_P = P;
+  emu::tables_for(HT, T); emu::params_for(prm, tier, P);
+  if (g_smem_build) emu::BuildS::globals(LS, caps, T, P); else emu::BuildG::globals(L, caps, T, P);
   g_rng = seed * 2 + 1; g_ncoll = 0;
   { const char* e = getenv("DCU_EMU_SKIP_SYNC_LINE"); dcu::emu_skip_sync_line = e ? atoi(e) : -1; }
   if (getenv("DCU_EMU_PROFILE")) g_prof = new std::map<void*, unsigned long long>();
@@ -165,8 +160,9 @@ extern "C" int emu_lanes_run_batch(const dcu_params* prm, const uint8_t* packed,
     memset(cons + i * DCU_CONS_STRIDE, 0, DCU_CONS_STRIDE); memset(ops + i * DCU_OPS_STRIDE, 0, DCU_OPS_STRIDE);
     for (int l = 0; l < NL; ++l) {
       LaneJob& j = g_job[l];
-      memset(&j.c, 0, sizeof(j.c));
+      memset(&j.c, 0, sizeof(j.c)); memset(&j.cs, 0, sizeof(j.cs));
       j.c.ws.base = slab.data(); j.c.vsq = T.VSq; j.c.packed = packed; j.c.sl = (const dcu::Slice*)sl;
+      j.cs.ws.base = slab.data(); j.cs.ws.sm = arena.data(); j.cs.vsq = T.VSq; j.cs.packed = packed; j.cs.sl = (const dcu::Slice*)sl;
       memcpy(&j.W, &win[i], sizeof(j.W));
       memset(&j.r, 0, sizeof(j.r));
       j.cons = cons + i * DCU_CONS_STRIDE; j.ops = ops + i * DCU_OPS_STRIDE;

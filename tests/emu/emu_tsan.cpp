@@ -7,10 +7,7 @@
 //   g++ -fsanitize=thread -O1 -g -std=c++17 -ffp-contract=off -pthread -o emu_tsan emu_tsan.cpp ;  ./emu_tsan batch.bin out.bin tier
 #define DCU_EMU 1
 #define DCU_EMU_LANES 1
-#include "../../daccord_b200/csrc/window_core.cuh"
-#include "../../daccord_b200/csrc/host_tables.hpp"
-#include "../../daccord_b200/csrc/host_caps.hpp"
-#include "../../include/daccord_b200.h"
+#include "emu_builds.hpp"
 #include <pthread.h>
 #include <thread>
 #include <vector>
@@ -26,7 +23,7 @@ unsigned long long g_x[2][NL];
 thread_local int t_lane = 0;
 thread_local unsigned t_gen = 0;
 }
-namespace dcu {
+namespace dcub {
 int emu_skip_sync_line = -1;
 const unsigned long long* emu_xchg(unsigned long long v) {
   const unsigned g = t_gen++;
@@ -58,16 +55,13 @@ int main(int argc, char** argv) {
     maxS = std::max<int>(maxS, win[i].slice_cnt); maxB = std::max(maxB, b);
   }
   dcu_host::build_tables((int)prm.w, prm.p_i, prm.p_d, prm.est_cor, (int)prm.k_lo, (int)prm.k_hi, maxS + 2, HT);
-  dcu::Caps caps = dcu_host::make_caps(tier, (int)prm.w, maxS, maxB);
-  dcu::Layout L; dcu::make_layout(caps, L);
-  std::vector<uint8_t> slab(L.bytes + 64);
+  dcu::Caps caps = emu::caps_for(tier, (int)prm.w, maxS, maxB);
+  const bool smem_build = tier == 2;                  // the shared-memory build of the kernel source (its arena is a host buffer here)
+  dcu::Layout L; dcus::Layout LS; dcu::make_layout(caps, L); dcus::make_layout(caps, LS);
+  std::vector<uint8_t> slab((smem_build ? LS.bytes : L.bytes) + 64), arena(LS.sbytes + 64);
   dcu::Tables T; dcu::Params P;
-  T.DPn = HT.DPn.data(); T.DPsq = HT.DPsq.data(); T.VSq = HT.VSq.data(); T.suplo = HT.suplo.data(); T.suphi = HT.suphi.data();
-  T.klim = HT.klim.data(); T.NP = HT.NP; T.MS = HT.MS; T.KLIMN = HT.KLIMN;
-  P.w = (int)prm.w; P.k_lo = (int)prm.k_lo; P.k_hi = (int)prm.k_hi; P.minff = prm.min_ff; P.maxff = prm.max_ff;
-  P.mincov = (int)prm.min_cov; P.check = prm.est_cor != 0.0; P.eminrate = prm.max_err; P.defer_ff = 0;
-  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }
-  dcu::g_layout = L; dcu::g_cap = caps; dcu::g_T = T; dcu::g_P = P;
+  emu::tables_for(HT, T); emu::params_for(&prm, tier, P); P.defer_ff = 0;
+  if (smem_build) emu::BuildS::globals(LS, caps, T, P); else emu::BuildG::globals(L, caps, T, P);
   std::vector<dcu_result> res(nwin); std::vector<uint8_t> cons(nwin * DCU_CONS_STRIDE, 0), ops(nwin * DCU_OPS_STRIDE, 0);
   std::vector<dcu::Result> lane_res((size_t)NL * nwin);
   pthread_barrier_init(&g_bar, nullptr, NL);
@@ -75,11 +69,17 @@ int main(int argc, char** argv) {
   for (int l = 0; l < NL; ++l) th.emplace_back([&, l]() {
     t_lane = l; t_gen = 0;
     for (uint64_t i = 0; i < nwin; ++i) {
-      dcu::Ctx c; memset(&c, 0, sizeof(c));
-      c.ws.base = slab.data(); c.vsq = T.VSq; c.packed = packed.data(); c.sl = (const dcu::Slice*)sl.data();
       dcu::Window W; memcpy(&W, &win[i], sizeof(W));
       dcu::Result r; memset(&r, 0, sizeof(r));
-      dcu::process_window(c, W, r, cons.data() + i * DCU_CONS_STRIDE, ops.data() + i * DCU_OPS_STRIDE, l);
+      if (smem_build) {
+        dcus::Ctx c; memset(&c, 0, sizeof(c));
+        c.ws.base = slab.data(); c.ws.sm = arena.data(); c.vsq = T.VSq; c.packed = packed.data(); c.sl = (const dcu::Slice*)sl.data();
+        dcus::process_window(c, W, r, cons.data() + i * DCU_CONS_STRIDE, ops.data() + i * DCU_OPS_STRIDE, l);
+      } else {
+        dcu::Ctx c; memset(&c, 0, sizeof(c));
+        c.ws.base = slab.data(); c.vsq = T.VSq; c.packed = packed.data(); c.sl = (const dcu::Slice*)sl.data();
+        dcu::process_window(c, W, r, cons.data() + i * DCU_CONS_STRIDE, ops.data() + i * DCU_OPS_STRIDE, l);
+      }
       lane_res[(size_t)l * nwin + i] = r;
       dcu::emu_xchg(0);                 // the kernel's __syncwarp() after a window is published
     }
