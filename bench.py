@@ -3,11 +3,18 @@
 
 One "step" = one pass of the hot path (the dcu_* C ABI) over all windows of this rank's shard of A-reads.
   value  : windows/s with windows, slices and the packed read DB already resident in HBM (kernel launches only)
-  e2e    : the same through dcu_run with HOST buffers (H2D of descriptors + D2H of results inside the timed region)
+  e2e    : the same through the read-level C ABI with HOST buffers: overlaps + trace points in (what the reference's
+           HandleContext::operator() is handed, src/HandleContext.hpp:1699-1715), corrected bases out
+           (dcu_pile + dcu_launch + dcu_vote + dcu_get_corrected; H2D and D2H inside the timed region)
+  e2e_descriptors : dcu_run with host window / slice descriptors in and result records out (the window-level entry point)
   --impl reference : the CPU oracle (restatement of gt1/daccord; the upstream binary cannot be built here) on all
-                     host threads over a bounded sample of the same windows.
-Multi-GPU (torchrun): rank r processes the reads of `-J r,N` (reference src/daccord.cpp:1156-1184) of a dataset
-N times larger (weak scaling); the packed DB is broadcast once over NCCL; no collective during compute.
+                     host threads over a bounded sample of the same windows -- window consensus only (no piling, no vote),
+                     so the e2e ratio against it is conservative for the GPU side; an upper bound against real daccord
+                     all the same (libmaus2's SIMD aligners are not reproduced).
+Multi-GPU (torchrun): rank r processes the reads of `-J r,N` (reference src/daccord.cpp:1156-1184); --scaling weak
+(default) makes the dataset N times larger, --scaling strong keeps --mb as the total (BASELINE config 3); the packed DB
+is broadcast once over NCCL; no collective during compute.  Other BASELINE configs: --k (config 4), --coverage /
+--depth-cap / --maxinput / --repeat-frac (config 5 and the shallow tail).
 """
 import argparse
 import ctypes as C
@@ -67,6 +74,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smmax, "reasons": sorted(self.reasons)}
 
 
+def full_compare(a, b):
+    """bit-exact comparison of two (res, cons, ops) triples (what tests/common.compare_results does, vectorised):
+    per window True where the result record differs, or -- for windows with a consensus -- the consensus bytes or the placement trace"""
+    ra, ca, oa = a[:3]
+    rb, cb, ob = b[:3]
+    n = len(ra)
+    bad = ra != rb
+    ok = (ra["status"] == 1) & ~bad
+    ca = np.asarray(ca).reshape(n, 64); cb = np.asarray(cb).reshape(n, 64); oa = np.asarray(oa).reshape(n, 128); ob = np.asarray(ob).reshape(n, 128)
+    step = 1 << 18
+    for i in range(0, n, step):
+        j = min(n, i + step)
+        mc = np.arange(64)[None, :] < ra["clen"][i:j, None]
+        mo = np.arange(128)[None, :] < ra["nops"][i:j, None]
+        bad[i:j] |= ok[i:j] & (((ca[i:j] != cb[i:j]) & mc).any(1) | ((oa[i:j] != ob[i:j]) & mo).any(1))
+    return bad
+
+
 def effective_cpus():
     """CPUs this process may really use: affinity mask and cgroup quota (os.cpu_count() ignores both)"""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -91,15 +116,46 @@ def best_oracle_threads(run_oracle, p, packed, win, sl):
     return best
 
 
-def build_workload(args, rank, world):
+def bind_to_gpu_numa_node(local):
+    """keep this rank's host threads and pinned buffers on the NUMA node its GPU hangs off (best effort; returns the node or None)"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        if bus is None:
+            return None
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def maxalign_of(args):
+    return args.depth_cap if args.depth_cap > 0 else 2**64 - 1
+
+
+def build_workload(args, rank, world, keep_truth=False):
     from daccord_b200.host import Dataset
-    genome = int(args.mb * 1e6 * world / args.coverage)
+    total_mb = args.mb * (world if args.scaling == "weak" else 1)
+    genome = int(total_mb * 1e6 / args.coverage)
     t0 = time.time()
-    ds = Dataset.simulate(genome, read_len=args.read_len, coverage=args.coverage, seed=args.seed)
+    ds = Dataset.simulate(genome, read_len=args.read_len, coverage=args.coverage, repeat_frac=args.repeat_frac, seed=args.seed, keep_truth=keep_truth)
     lo, hi = j_shard(ds.nreads, rank, world)
     t1 = time.time()
-    nthreads = max(1, (os.cpu_count() or 1) // world)
-    batch = ds.pile(lo, hi, w=args.w, a=args.a, nthreads=nthreads)
+    nthreads = max(1, effective_cpus() // (1 if getattr(args, "bound", False) else world))
+    batch = ds.pile(lo, hi, w=args.w, a=args.a, maxalign=maxalign_of(args), maxinput=args.maxinput, nthreads=nthreads)
     t2 = time.time()
     info = {"reads_total": int(ds.nreads), "overlaps": int(ds.novl), "shard": [int(lo), int(hi)], "sim_s": round(t1 - t0, 2), "pile_s": round(t2 - t1, 2), "pile_threads": nthreads}
     return ds, batch, info
@@ -118,13 +174,22 @@ def main():
     ap.add_argument("--a", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-sample-s", type=float, default=12.0)
+    ap.add_argument("--k", type=int, default=8, help="k-mer size (BASELINE config 4 sweeps 6..14)")
+    ap.add_argument("--depth-cap", type=int, default=0, help="-d: at most this many sequences per window (0 = unlimited; BASELINE config 5: 200)")
+    ap.add_argument("--maxinput", type=int, default=5000, help="-D: overlaps kept per A-read")
+    ap.add_argument("--repeat-frac", type=float, default=0.0, help="fraction of the genome covered by tandem repeats (BASELINE config 5: 0.2)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --mb is the total over all GPUs (BASELINE config 3)")
+    ap.add_argument("--truth-reads", type=int, default=400, help="corrected reads compared with the simulated truth (0 = off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "%.0f Mb synthetic 40x pile per GPU (10 kb reads, 15%% error, LAS-equivalent overlaps with tspace=100 trace points), -w%d -a%d -k8" % (args.mb, args.w, args.a)
+    workload = "%g Mb synthetic %gx pile %s (%d kb reads, 15%% error%s, LAS-equivalent overlaps with tspace=100 trace points), -w%d -a%d -k%d%s%s" % (
+        args.mb, args.coverage, "per GPU" if args.scaling == "weak" else "in total, -J sharded", args.read_len // 1000,
+        (", %.0f%% of the genome in tandem repeats" % (100 * args.repeat_frac)) if args.repeat_frac else "", args.w, args.a, args.k,
+        (" -d%d" % args.depth_cap) if args.depth_cap else "", (" -D%d" % args.maxinput) if args.maxinput != 5000 else "")
     base = {"metric": "consensus_windows_per_s", "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 + f64", "data": "synthetic"}
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u32/u64 + f64", "data": "synthetic"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -132,7 +197,7 @@ def main():
         from common import run_oracle, default_params
         ds, batch, info = build_workload(args, 0, 1)
         pi, pd, cor = ds.profile()
-        p = default_params(w=args.w, p_i=pi, p_d=pd, est_cor=cor)
+        p = default_params(w=args.w, k_lo=args.k, k_hi=args.k, p_i=pi, p_d=pd, est_cor=cor)
         packed = np.array(ds.packed(), copy=True)
         win_all, sl = batch.win, batch.sl
         threads = best_oracle_threads(run_oracle, p, packed, win_all, sl)
@@ -150,22 +215,29 @@ def main():
             tt += t; att += int((res["status"] != 0).sum())
         v = att / tt
         out = dict(base, impl="reference", value=v, ms_per_step=1e3 * tt / args.steps, n_gpus=world,
-                   config={"workload": workload, "sample": "first %d windows of the shard per step" % n, "threads": threads},
-                   cpu_baseline={"value": v, "unit": "windows/s", "cores": threads, "kind": "port", "sample": "first %d windows x %d steps" % (n, args.steps)},
+                   config={"workload": workload, "sample": "first %d windows of the shard per step" % n, "threads": threads, "host_cpus": os.cpu_count(), "usable_cpus": effective_cpus(),
+                           "what": "window consensus only (oracle_run_batch); CPU restatement of gt1/daccord with bit-parallel scoring, not the upstream binary: the ratio against it is an upper bound vs real daccord"},
+                   cpu_baseline={"value": v, "unit": "windows/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": "port", "sample": "first %d windows x %d steps" % (n, args.steps)},
                    e2e={"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(out))
         return 0
 
     import torch
     import daccord_b200 as d
+    from daccord_b200.host import format_segments
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    args.bound = numa is not None
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ds, batch, info = build_workload(args, rank, world)
+    total_mb = args.mb * (world if args.scaling == "weak" else 1)
+    keep_truth = args.truth_reads > 0 and total_mb <= 260
+    ds, batch, info = build_workload(args, rank, world, keep_truth=keep_truth)
+    info["numa_node"] = numa
     pi, pd, cor = ds.profile()
-    params = d.Params.default(w=args.w, p_i=pi, p_d=pd, est_cor=cor)
+    params = d.Params.default(w=args.w, k_lo=args.k, k_hi=args.k, p_i=pi, p_d=pd, est_cor=cor)
     eng = d.Engine(params, local)
     # packed read DB: one-time broadcast from rank 0 over NCCL (every rank needs the whole DB: B reads come from anywhere)
     packed_h = np.array(ds.packed(), copy=True)
@@ -177,13 +249,14 @@ def main():
     torch.cuda.synchronize()
     eng.set_reads_device(dbt.data_ptr(), dbt.numel())
 
-    # pinned host staging of the step's inputs / outputs (the e2e leg copies them every step)
+    # pinned host staging of the step's inputs / outputs (the e2e legs copy them every step)
     win_p = torch.from_numpy(batch.win.view(np.uint8).copy()).pin_memory()
     sl_p = torch.from_numpy(batch.sl.view(np.uint8).copy()).pin_memory()
     win = win_p.numpy().view(d.WINDOW_DT); sl = sl_p.numpy().view(d.SLICE_DT)
     nwin = len(win)
     res_p = torch.empty(nwin * 16, dtype=torch.uint8).pin_memory(); cons_p = torch.empty(nwin * 64, dtype=torch.uint8).pin_memory(); ops_p = torch.empty(nwin * 128, dtype=torch.uint8).pin_memory()
     out = (res_p.numpy().view(d.RESULT_DT), cons_p.numpy(), ops_p.numpy())
+    maxalign = maxalign_of(args)
 
     def barrier():
         torch.cuda.synchronize()
@@ -197,66 +270,79 @@ def main():
         eng.launch()
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    kms, launches, hard, second = 0.0, 0, 0, 0
+    kms, launches, hard, second, lost = 0.0, 0, 0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         kms += eng.launch()                 # CUDA-event time of the launch(es) on the engine's stream
-        st = eng.stats(); launches += st["launches"]; hard += st["hard_windows"]; second += st["second_pass_windows"]
+        st = eng.stats(); launches += st["launches"]; hard += st["hard_windows"]; second += st["second_pass_windows"]; lost += st["lost_windows"]
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
     res, cons, ops = eng.download(out)
+    res_ref, cons_ref, ops_ref = res.copy(), cons.copy(), ops.copy()
     att = int((res["status"] != 0).sum()); okw = int((res["status"] == 1).sum())
     alg_bytes, _ = algorithmic_bytes(win, sl, res)
     tsec = kms / 1e3
-    # ---- end-to-end leg through dcu_run (host buffers)
-    for _ in range(max(args.warmup, 1)):
+    # ---- window-level entry point: dcu_run with host descriptors in, result records out
+    for _ in range(1):
         eng.run(win, sl, out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         eng.run(win, sl, out)
     barrier()
-    e2e_wall = time.perf_counter() - t0
-    # ---- same, one stage earlier: overlaps + trace points in, trace reconstruction and slice extraction on the GPU (dcu_pile)
-    res_ref = out[0].copy()
-    ovl, trace, boff, rlen = ds.overlaps(info["shard"][0], info["shard"][1])
+    desc_wall = time.perf_counter() - t0
+    desc_same = not full_compare((res_ref, cons_ref, ops_ref), out).any()
+    fasta, nseq = batch.vote(*out)           # host pile vote of the same results: the check of the GPU vote below
+    corrected = sum(len(l) for l in fasta.split(b"\n") if l and not l.startswith(b">"))
+    # ---- one stage earlier: overlaps + trace points in, trace reconstruction and slice extraction on the GPU (dcu_pile), result records out
+    ovl, trace, boff, rlen = ds.overlaps(info["shard"][0], info["shard"][1], maxinput=args.maxinput)
+    ovl_p = torch.from_numpy(ovl.view(np.uint8).copy()).pin_memory(); trace_p = torch.from_numpy(trace.view(np.uint8).copy()).pin_memory()
+    ovl = ovl_p.numpy().view(ovl.dtype); trace = trace_p.numpy().view(np.uint16)
+    gpu_pile = args.w % args.a == 0
     pile_wall, pile_same = None, None
-    if args.w % args.a == 0:
-        eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a); eng.launch(); eng.download(out)      # warm-up
+    if gpu_pile:
+        eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng.launch(); eng.download(out)      # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a)
+            eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign)
             eng.launch()
             eng.download(out)
         barrier()
         pile_wall = time.perf_counter() - t0
-        pile_same = bool((out[0] == res_ref).all())
-    fasta, nseq = batch.vote(*out)
-    corrected = sum(len(l) for l in fasta.split(b"\n") if l and not l.startswith(b">"))
-    # ---- the whole read-level path on the GPU: overlaps in, corrected bases out (dcu_pile + launch + dcu_vote); D2H = corrected bases only
-    full_wall, full_same, full_d2h = None, None, 0
-    if args.w % args.a == 0:
-        from daccord_b200.host import format_segments
-        eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a); eng.launch(); seg, chars = eng.vote()      # warm-up
+        pile_same = not full_compare((res_ref, cons_ref, ops_ref), out).any()
+    # ---- e2e: the whole read-level path on the GPU: overlaps in, corrected bases out (dcu_pile + launch + dcu_vote); D2H = corrected bases only
+    full_wall, full_same, full_d2h, truth = None, None, 0, None
+    if gpu_pile:
+        eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng.launch(); seg, chars = eng.vote()      # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a)
+            eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign)
             eng.launch()
             seg, chars = eng.vote()
         barrier()
         full_wall = time.perf_counter() - t0
-        full_same = bool(format_segments(seg, chars)[0] == fasta)
+        gfasta = format_segments(seg, chars)[0]
+        full_same = bool(gfasta == fasta)
         full_d2h = int(chars.nbytes + seg.nbytes + 16 * nwin)       # + the window descriptors dcu_vote reads back to lay out the reads
+        if keep_truth and rank == 0:
+            # anchor outside the oracle: the corrected reads of the GPU path against the simulated genome (first reads of the shard)
+            truth = ds.truth_eval(gfasta, max_read=info["shard"][0] + args.truth_reads)
+    e2e_wall = full_wall if full_wall else desc_wall
 
-    vals = torch.tensor([tsec, e2e_wall, wall, pile_wall or 0.0, full_wall or 0.0], dtype=torch.float64, device="cuda")
-    cnts = torch.tensor([att, nwin, okw, corrected, launches, hard, alg_bytes, win.nbytes + sl.nbytes, res_p.numel() + cons_p.numel() + ops_p.numel()], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([tsec, e2e_wall, wall, pile_wall or 0.0, desc_wall], dtype=torch.float64, device="cuda")
+    cnts = torch.tensor([att, nwin, okw, corrected, launches, hard, alg_bytes, win.nbytes + sl.nbytes, res_p.numel() + cons_p.numel() + ops_p.numel(), second, lost,
+                         ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes, full_d2h], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, dtype=torch.float64, device="cuda"); per_rank[rank] = tsec
+    per_rank_att = torch.zeros(world, dtype=torch.float64, device="cuda"); per_rank_att[rank] = att
+    flags = torch.tensor([1.0 if desc_same else 0.0, 1.0 if (pile_same or pile_same is None) else 0.0, 1.0 if (full_same or full_same is None) else 0.0], dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX); dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
-    tsec, e2e_wall, wall, pile_wall_max, full_wall_max = [float(x) for x in vals.tolist()]
-    att_t, nwin_t, ok_t, corr_t, launches_t, hard_t, alg_t, h2d_t, d2h_t = [float(x) for x in cnts.tolist()]
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX); dist.all_reduce(cnts, op=dist.ReduceOp.SUM); dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank_att, op=dist.ReduceOp.SUM); dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    tsec_max, e2e_wall, wall, pile_wall_max, desc_wall_max = [float(x) for x in vals.tolist()]
+    att_t, nwin_t, ok_t, corr_t, launches_t, hard_t, alg_t, h2d_desc, d2h_desc, second_t, lost_t, h2d_ovl, d2h_full = [float(x) for x in cnts.tolist()]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -270,41 +356,51 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     ach = (alg_bytes * args.steps) / tsec / 1e9           # this rank's kernel: algorithmic GB/s
-    traffic = None; traffic_src = None
+    traffic = None; traffic_src = None; issue = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = tj["dram_bytes_per_window"] * att
         traffic_src = "%d B / window x windows of the launch; %s" % (tj["dram_bytes_per_window"], tj.get("source", ""))
+        issue = tj.get("issue")
     except Exception:
         pass
-    value = att_t * args.steps / tsec
-    line = dict(base, value=value, ms_per_step=1e3 * tsec / args.steps,
+    value = att_t * args.steps / tsec_max
+    ranks_ms = [1e3 * float(x) / args.steps for x in per_rank.tolist()]
+    line = dict(base, value=value, ms_per_step=1e3 * tsec_max / args.steps,
                 config={"workload": workload, "windows_per_step": int(nwin_t), "attempted_per_step": int(att_t), "consensus_per_step": int(ok_t),
-                        "corrected_mbp_per_s": corr_t * args.steps / tsec / 1e6, "l2": "inputs %.0f MB per GPU, larger than L2 (126 MB)" % ((win.nbytes + sl.nbytes) / 1e6),
+                        "corrected_mbp_per_s": corr_t * args.steps / tsec_max / 1e6, "l2": "inputs %.0f MB per GPU, larger than L2 (126 MB)" % ((win.nbytes + sl.nbytes) / 1e6),
                         "parallelism": "-J r,%d by A-read, no data-path collective" % world, "setup": info},
-                e2e={"value": att_t * args.steps / e2e_wall, "unit": "windows/s", "h2d_bytes_per_step": int(h2d_t), "d2h_bytes_per_step": int(d2h_t)},
-                e2e_from_overlaps=(None if not pile_wall else {"value": att_t * args.steps / pile_wall_max, "unit": "windows/s", "what": "dcu_pile (trace reconstruction + slices on the GPU) + launch + download",
-                                                               "h2d_bytes_per_step": int((ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes) * world), "results_identical": pile_same}),
-                e2e_overlaps_to_fasta=(None if not full_wall else {"value": att_t * args.steps / full_wall_max, "unit": "windows/s", "what": "dcu_pile + launch + dcu_vote (pile vote on the GPU): overlaps in, corrected bases out",
-                                                                   "h2d_bytes_per_step": int((ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes) * world), "d2h_bytes_per_step": int(full_d2h * world),
-                                                                   "fasta_identical_to_host_vote": full_same}),
-                gpu_launches=int(launches_t), hard_windows=int(hard_t), second_pass_windows=int(second), smem_pass={"warps_per_sm": st["smem_warps"], "bytes_per_warp": st["smem_bytes_per_warp"]},
+                e2e=(None if not full_wall else {"value": att_t * args.steps / e2e_wall, "unit": "windows/s", "h2d_bytes_per_step": int(h2d_ovl), "d2h_bytes_per_step": int(d2h_full),
+                                                 "what": "dcu_pile + dcu_launch + dcu_vote + dcu_get_corrected: overlaps and trace points in (pinned host memory), corrected bases out",
+                                                 "corrected_mbp_per_s": corr_t * args.steps / e2e_wall / 1e6, "fasta_identical_to_host_vote": bool(flags[2].item())}),
+                e2e_descriptors={"value": att_t * args.steps / desc_wall_max, "unit": "windows/s", "what": "dcu_run: window / slice descriptors in, result records + consensus + placement out",
+                                 "h2d_bytes_per_step": int(h2d_desc), "d2h_bytes_per_step": int(d2h_desc), "results_identical": bool(flags[0].item())},
+                e2e_from_overlaps=(None if not pile_wall else {"value": att_t * args.steps / pile_wall_max, "unit": "windows/s", "what": "dcu_pile (trace reconstruction + slices on the GPU) + launch + download of the result records",
+                                                               "h2d_bytes_per_step": int(h2d_ovl), "d2h_bytes_per_step": int(d2h_desc), "results_identical": bool(flags[1].item())}),
+                per_gpu={"kernel_ms_per_step": [round(x, 3) for x in ranks_ms], "attempted": [int(x) for x in per_rank_att.tolist()],
+                         "imbalance_max_over_mean": (max(ranks_ms) / (sum(ranks_ms) / len(ranks_ms))) if ranks_ms and sum(ranks_ms) > 0 else None},
+                gpu_launches=int(launches_t), hard_windows=int(hard_t), second_pass_windows=int(second_t), lost_windows=int(lost_t),
+                smem_pass={"warps_per_sm": st["smem_warps"], "bytes_per_warp": st["smem_bytes_per_warp"]},
                 roofline={"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
-                          "peak_source": peak_src, "bytes_per_window": alg_bytes / max(att, 1),
-                          "note": "integer / latency bound path (SURVEY 8d): the HBM fraction is reported as the contract asks, see DESIGN.md for the instruction-issue analysis"},
-                clocks=sampler.summary(), wall_s_timed=wall)
-    # CPU baseline: the oracle on a bounded sample of the same windows, all host threads (rank 0, N=1 only)
+                          "peak_source": peak_src, "bytes_per_window": alg_bytes / max(att, 1), "issue": issue,
+                          "note": "integer / latency bound path (SURVEY 8d): the HBM fraction is reported as the contract asks; `issue` holds the instruction-issue figures of the same ncu capture"},
+                accuracy=truth, clocks=sampler.summary(), wall_s_timed=wall)
+    if not full_wall:       # -w not a multiple of -a: the GPU piler does not apply, the descriptor path is the end-to-end number
+        line["e2e"] = dict(line["e2e_descriptors"])
+    # CPU baseline: the oracle on a bounded sample of the same windows, all host threads (rank 0, N=1 only); full comparison of the sample
     if world == 1 and args.cpu_sample_s > 0:
         from common import run_oracle, default_params
-        p = default_params(w=args.w, p_i=pi, p_d=pd, est_cor=cor)
+        p = default_params(w=args.w, k_lo=args.k, k_hi=args.k, p_i=pi, p_d=pd, est_cor=cor)
         threads = best_oracle_threads(run_oracle, p, packed_h, batch.win, batch.sl)
         probe = min(nwin, 2000 + 500 * threads)
         r0, _, _, t = run_oracle(p, packed_h, batch.win[:probe].copy(), batch.sl, threads)
         n = int(min(nwin, max(probe, probe / max(t, 1e-6) * args.cpu_sample_s)))
         r1, c1, o1, t = run_oracle(p, packed_h, batch.win[:n].copy(), batch.sl, threads)
-        same = bool((r1 == res[:n]).all())
-        line["cpu_baseline"] = {"value": float((r1["status"] != 0).sum() / t), "unit": "windows/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
-                                "sample": "first %d windows of the step, %.1f s" % (n, t), "gpu_results_identical_on_sample": same}
+        diff = full_compare((r1, c1, o1), (res_ref[:n], cons_ref[:n * 64], ops_ref[:n * 128]))
+        line["cpu_baseline"] = {"value": float((r1["status"] != 0).sum() / t), "unit": "windows/s", "cores": threads, "host_cpus": os.cpu_count(), "usable_cpus": effective_cpus(), "kind": "port",
+                                "sample": "first %d windows of the step, %.1f s" % (n, t), "gpu_results_identical_on_sample": not diff.any(),
+                                "compared": "result record, consensus bytes and placement trace of every sampled window", "differing_windows": int(diff.sum()),
+                                "note": "CPU restatement of gt1/daccord (bit-parallel scoring, -march=x86-64-v3), not the upstream binary: GPU/CPU ratios are upper bounds vs real daccord"}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -29,7 +29,7 @@ static const char* HELP =
     "usage: daccord [options] reads.las reads.db\n"
     "\t-t: number of host threads (default: all)\n\t-w: window size (default 40)\n\t-a: advance size (default 10)\n"
     "\t-d: max depth (default unlimited)\n\t-f: produce full sequences\n\t-V: verbosity\n\t-I: read interval i,j (inclusive)\n"
-    "\t-J: reads part i,j\n\t-E: error profile file name (default input.las.eprof)\n\t--eprofonly: compute error profile only\n\t-m: minimum window coverage (default 3)\n"
+    "\t-J: reads part i,j\n\t-E: error profile file name (default input.las.eprof)\n\t--eprofonly: compute error profile only\n\t--keepeprof: keep an error profile older than the .las (default 1)\n\t-m: minimum window coverage (default 3)\n"
     "\t-e: maximum window error (default unlimited)\n\t-l: minimum length of output (default 0)\n"
     "\t--minfilterfreq: minimum k-mer filter frequency (default 0)\n\t--maxfilterfreq: maximum k-mer filter frequency (default 2)\n"
     "\t-D: maximum number of alignments considered per read (default 5000)\n\t-k: kmer size lo[,hi] (default 8)\n"
@@ -102,22 +102,21 @@ int main(int argc, char** argv) {
     }
     const int64_t toparead = maxaread >= 0 ? maxaread + 1 : maxaread;
     fprintf(stderr, "[V] minaread=%ld toparead=%ld\n", (long)minaread, (long)toparead);
-    fprintf(stderr, "[V] loading %s ...", lasfn.c_str()); read_las_range(lasfn, lidx, minaread, toparead, las, nthreads); las.build_index(db.rlen.size());
+    fprintf(stderr, "[V] loading %s ...", lasfn.c_str()); read_las_range(lasfn, lidx, minaread, toparead, las, nthreads); las.build_index(db.rlen.size()); validate_las(las, db.rlen);
     fprintf(stderr, "done (%zu of %ld overlaps).\n", las.ovl.size(), (long)lidx.novl);
     fprintf(stderr, "[V] minfilterfreq=%d maxfilterfreq=%d\n", prm.min_ff, prm.max_ff);
-    // error profile: <las>.eprof or -E; estimated from the first <= 1024 A-reads when the file does not exist
-    // (reference src/daccord.cpp:1652-1880).  Text form: "matches mismatches insertions deletions" [newline "eavg edif"]
+    // error profile: <las>.eprof or -E, in the reference's binary layout (eprof.hpp); estimated from the first <= 1024 A-reads when the
+    // file does not exist, or is older than the .las and --keepeprof is off (reference src/daccord.cpp:1652-1880; keepeprof defaults to 1, :1303)
     std::string eproffn = A.opt.count("E") ? A.opt["E"] : lasfn + ".eprof";
-    uint64_t em = 0, es = 0, ei = 0, ed = 0;
-    if (!std::ifstream(eproffn).good()) {
+    const bool keepeprof = getu("keepeprof", 1) != 0;
+    uint64_t ecnt[4] = {0, 0, 0, 0};
+    if (eprof_is_stale(eproffn, lasfn, keepeprof)) {
       ProfileCounts PC = estimate_profile(db, las, minaread, toparead, maxalign, maxinput, nthreads);
       fprintf(stderr, "usable=%lu unusable=%lu eavg=%g edif=%g\n", (unsigned long)PC.usable, (unsigned long)PC.unusable, PC.eavg, PC.edif);
-      const std::string tmpfn = eproffn + ".tmp";
-      { std::ofstream of(tmpfn); of << PC.cnt[0] << " " << PC.cnt[1] << " " << PC.cnt[2] << " " << PC.cnt[3] << "\n" << PC.eavg << " " << PC.edif << "\n";
-        if (!of) { fprintf(stderr, "[E] cannot write error profile %s\n", tmpfn.c_str()); return EXIT_FAILURE; } }
-      if (rename(tmpfn.c_str(), eproffn.c_str())) { fprintf(stderr, "[E] cannot rename %s to %s\n", tmpfn.c_str(), eproffn.c_str()); return EXIT_FAILURE; }
+      write_eprof(eproffn, PC.cnt, PC.eavg, PC.edif);
     }
-    { std::ifstream ef(eproffn); if (!(ef >> em >> es >> ei >> ed)) { fprintf(stderr, "[E] cannot read error profile %s\n", eproffn.c_str()); return EXIT_FAILURE; } }
+    if (!read_eprof(eproffn, ecnt)) { fprintf(stderr, "[E] cannot read error profile %s\n", eproffn.c_str()); return EXIT_FAILURE; }
+    const uint64_t em = ecnt[0], es = ecnt[1], ei = ecnt[2], ed = ecnt[3];
     if (em + es + ed == 0) { fprintf(stderr, "[E] error profile %s is empty (no usable window in the sampled reads)\n", eproffn.c_str()); return EXIT_FAILURE; }
     if (A.opt.count("eprofonly")) return EXIT_SUCCESS;                  // src/daccord.cpp:1895-1896
     const uint64_t len = em + es + ed, numerr = es + ed + ei;

@@ -52,14 +52,18 @@ inline void write_dazzdb(const std::string& dbfn, const PackedDB& db) {
   fwrite(db.bytes.data(), 1, db.bytes.size() >= 16 ? db.bytes.size() - 16 : 0, f);   // the in-memory copy carries 16 padding bytes
   fclose(f);
 }
+// DB_BEST bit of DAZZ_READ::flags; the trimmed view of a DB holds the reads with rlen >= cutoff that are flagged best (or all of
+// them with -a), in file order (Trim_DB of the public DAZZ_DB sources).  DALIGNER numbers reads in the trimmed view, so that is the
+// numbering a .las refers to.
+enum { DAZZ_DB_BEST = 0x0400 };
 inline void read_dazzdb(const std::string& dbfn, PackedDB& db) {
   FILE* f = fopen(hidden(dbfn, ".idx").c_str(), "rb");
   if (!f) throw std::runtime_error("cannot open " + hidden(dbfn, ".idx"));
   DazzHeader h;
   if (fread(&h, sizeof(h), 1, f) != 1) { fclose(f); throw std::runtime_error("short .idx header"); }
-  if (h.nreads < 0 || h.nreads != h.ureads) { fclose(f); throw std::runtime_error("unsupported Dazzler DB (trimmed/partial block)"); }
-  db.boff.resize(h.nreads); db.rlen.resize(h.nreads);
-  for (int32_t i = 0; i < h.nreads; ++i) { DazzRead r; if (fread(&r, sizeof(r), 1, f) != 1) { fclose(f); throw std::runtime_error("short .idx"); } db.boff[i] = (uint64_t)r.boff; db.rlen[i] = (uint32_t)r.rlen; }
+  if (h.ureads < 0 || h.treads < 0 || h.treads > h.ureads) { fclose(f); throw std::runtime_error("implausible read counts in .idx header (not a 64-bit DAZZ_DB index?)"); }
+  std::vector<DazzRead> all((size_t)h.ureads);
+  if (h.ureads && fread(all.data(), sizeof(DazzRead), (size_t)h.ureads, f) != (size_t)h.ureads) { fclose(f); throw std::runtime_error("short .idx"); }
   fclose(f);
   f = fopen(hidden(dbfn, ".bps").c_str(), "rb");
   if (!f) throw std::runtime_error("cannot open " + hidden(dbfn, ".bps"));
@@ -67,6 +71,18 @@ inline void read_dazzdb(const std::string& dbfn, PackedDB& db) {
   db.bytes.assign((size_t)sz + 16, 0);
   if (sz && fread(db.bytes.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); throw std::runtime_error("short .bps"); }
   fclose(f);
+  // trimmed view (equal to the untrimmed one when the DB was never split or was split with -x0 -a)
+  db.boff.clear(); db.rlen.clear();
+  const bool trim = h.treads != h.ureads;
+  for (int32_t i = 0; i < h.ureads; ++i) {
+    const DazzRead& r = all[(size_t)i];
+    if (trim && !((h.allarr || (r.flags & DAZZ_DB_BEST)) && r.rlen >= h.cutoff)) continue;
+    if (r.rlen < 0 || r.boff < 0 || (uint64_t)r.boff + ((uint64_t)r.rlen + 3) / 4 > (uint64_t)sz)
+      throw std::runtime_error("read " + std::to_string(i) + " of " + hidden(dbfn, ".idx") + " lies outside the .bps file");
+    db.boff.push_back((uint64_t)r.boff); db.rlen.push_back((uint32_t)r.rlen);
+  }
+  if (trim && (int64_t)db.rlen.size() != (int64_t)h.treads)
+    throw std::runtime_error("trimmed view holds " + std::to_string(db.rlen.size()) + " reads, header says " + std::to_string(h.treads) + " (cutoff / best flags not understood)");
 }
 
 }  // namespace dhost

@@ -15,6 +15,11 @@
 #include <map>
 #include <vector>
 #include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+#include <sys/stat.h>
 #include "las.hpp"
 #include "synth.hpp"
 #include "align.hpp"
@@ -27,6 +32,44 @@ struct ProfileCounts {
   uint64_t usable = 0, unusable = 0, reads = 0;
   double eavg = 0.0, edif = 0.0;             // mean / deviation of the per-read window error rate (reported only)
 };
+
+// <las>.eprof on disk, as the reference writes it (src/daccord.cpp:1855-1864): AlignmentStatistics::serialise = matches, mismatches,
+// insertions, deletions as big-endian 64-bit numbers (libmaus2 NumberSerialisation::serialiseNumber), then eavg and edif by
+// serialiseDouble (the 8 bytes of the double as they lie in memory; libmaus2 is not available here, so this follows its public
+// sources).  The reference reads back only the four counts (:1864 GAS.deserialise).  The text form of this repository's first
+// round ("m s i d" newline "eavg edif") is still accepted when reading.
+inline void write_eprof(const std::string& fn, const uint64_t cnt[4], double eavg, double edif) {
+  const std::string tmp = fn + ".tmp";                       // tmp + rename like the reference (:1854-1860)
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) throw std::runtime_error("cannot write error profile " + tmp);
+  uint8_t b[48];
+  for (int i = 0; i < 4; ++i) for (int q = 0; q < 8; ++q) b[8 * i + q] = (uint8_t)(cnt[i] >> (8 * (7 - q)));
+  memcpy(b + 32, &eavg, 8); memcpy(b + 40, &edif, 8);
+  const bool ok = fwrite(b, 1, sizeof(b), f) == sizeof(b);
+  if (fclose(f) != 0 || !ok) throw std::runtime_error("cannot write error profile " + tmp);
+  if (rename(tmp.c_str(), fn.c_str())) throw std::runtime_error("cannot rename " + tmp + " to " + fn);
+}
+inline bool read_eprof(const std::string& fn, uint64_t cnt[4]) {
+  FILE* f = fopen(fn.c_str(), "rb");
+  if (!f) return false;
+  uint8_t b[256]; const size_t n = fread(b, 1, sizeof(b) - 1, f); fclose(f);
+  if (n >= 32 && !(b[0] >= '0' && b[0] <= '9')) {            // binary (a count below 2^56 starts with a zero byte)
+    for (int i = 0; i < 4; ++i) { cnt[i] = 0; for (int q = 0; q < 8; ++q) cnt[i] = (cnt[i] << 8) | b[8 * i + q]; }
+    return true;
+  }
+  b[n] = 0;
+  unsigned long long v[4];
+  if (sscanf((const char*)b, "%llu %llu %llu %llu", &v[0], &v[1], &v[2], &v[3]) != 4) return false;
+  for (int i = 0; i < 4; ++i) cnt[i] = v[i];
+  return true;
+}
+// the reference recomputes the profile when the file is missing, or older than the .las unless --keepeprof (src/daccord.cpp:1652-1657)
+inline bool eprof_is_stale(const std::string& eproffn, const std::string& lasfn, bool keepeprof) {
+  struct stat se, sl;
+  if (stat(eproffn.c_str(), &se) != 0) return true;
+  if (keepeprof || stat(lasfn.c_str(), &sl) != 0) return false;
+  return se.st_mtim.tv_sec < sl.st_mtim.tv_sec || (se.st_mtim.tv_sec == sl.st_mtim.tv_sec && se.st_mtim.tv_nsec < sl.st_mtim.tv_nsec);
+}
 
 struct Seq { const uint8_t* p; uint32_t n; };     // 2-bit codes, one per byte
 

@@ -17,12 +17,14 @@
 #include "pile.hpp"
 #include "vote.hpp"
 #include "eprof.hpp"
+#include "truth.hpp"
 
 using namespace dhost;
 
 struct dh_data {
   PackedDB db; LasData las;
   uint64_t st_match = 0, st_mis = 0, st_ins = 0, st_del = 0;     // error profile counts (reference GAS, src/daccord.cpp:1867-1880)
+  Truth truth;                                                   // simulated data only, on request: genome + edit scripts (truth.hpp)
   std::string err;
 };
 struct dh_batch {
@@ -34,8 +36,8 @@ struct dh_batch {
 
 extern "C" {
 
-dh_data* dh_sim_create(uint64_t genome_len, uint64_t read_len, double coverage, double p_ins, double p_del, double p_sub, double repeat_frac,
-                       uint64_t seed, int32_t tspace, uint64_t min_ovl) {
+dh_data* dh_sim_create_ex(uint64_t genome_len, uint64_t read_len, double coverage, double p_ins, double p_del, double p_sub, double repeat_frac,
+                          uint64_t seed, int32_t tspace, uint64_t min_ovl, int keep) {
   try {
     SimParams P; P.genome_len = genome_len; P.read_len = read_len; P.coverage = coverage; P.p_ins = p_ins; P.p_del = p_del; P.p_sub = p_sub;
     P.repeat_frac = repeat_frac; P.seed_genome = 0xDACC01 ^ (seed * 0x9E3779B97F4A7C15ull); P.seed_sample = 0xDACC02 ^ (seed * 0xC2B2AE3D27D4EB4Full); P.seed_err = 0xDACC03 ^ (seed * 0x165667B19E3779F9ull);
@@ -47,12 +49,26 @@ dh_data* dh_sim_create(uint64_t genome_len, uint64_t read_len, double coverage, 
     for (auto& r : reads) {                 // error profile of the simulation itself (what daccord would estimate, src/daccord.cpp:1652-1865)
       D->st_ins += r.n_ins; D->st_del += r.n_del; D->st_mis += r.n_sub; D->st_match += r.glen - r.n_del - r.n_sub;
     }
+    if (keep) keep_truth(G, reads, D->truth);
     return D.release();
   } catch (...) { return nullptr; }
 }
+dh_data* dh_sim_create(uint64_t genome_len, uint64_t read_len, double coverage, double p_ins, double p_del, double p_sub, double repeat_frac,
+                       uint64_t seed, int32_t tspace, uint64_t min_ovl) {
+  return dh_sim_create_ex(genome_len, read_len, coverage, p_ins, p_del, p_sub, repeat_frac, seed, tspace, min_ovl, 0);
+}
+// corrected FastA against the simulated truth (dh_sim_create_ex with keep != 0), reads < max_read only:
+// out6 = segments, corrected bases, truth bases, edit distance (banded: exact or an upper bound), error events of the raw reads on the same intervals, reads seen
+int dh_truth_eval(dh_data* d, const char* fasta, uint64_t len, uint64_t max_read, uint64_t* out6) {
+  if (!d->truth.have()) { d->err = "dataset holds no truth (simulate with keep_truth)"; return 1; }
+  TruthStats S;
+  if (!truth_eval(d->truth, fasta, len, max_read, S, d->err)) return 1;
+  out6[0] = S.segments; out6[1] = S.bases; out6[2] = S.truth_bases; out6[3] = S.edits; out6[4] = S.raw_events; out6[5] = S.reads;
+  return 0;
+}
 dh_data* dh_data_load(const char* lasfn, const char* dbfn) {
   std::unique_ptr<dh_data> D(new dh_data());
-  try { read_dazzdb(dbfn, D->db); read_las(lasfn, D->las); D->las.build_index(D->db.rlen.size()); } catch (std::exception& e) { fprintf(stderr, "[E] %s\n", e.what()); return nullptr; }
+  try { read_dazzdb(dbfn, D->db); read_las(lasfn, D->las); D->las.build_index(D->db.rlen.size()); validate_las(D->las, D->db.rlen); } catch (std::exception& e) { fprintf(stderr, "[E] %s\n", e.what()); return nullptr; }
   return D.release();
 }
 // the overlaps of A-reads [first_read, last_read) only, through the offset index (las_index.hpp); out3 = A-read range of the file and its overlap count
@@ -63,14 +79,14 @@ dh_data* dh_data_load_range(const char* lasfn, const char* dbfn, int64_t first_r
     LasIndex I; get_las_index(lasfn, I);
     if (out3) { out3[0] = I.minaread; out3[1] = I.maxaread; out3[2] = I.novl; }
     read_las_range(lasfn, I, first_read, last_read, D->las, nthreads);
-    D->las.build_index(D->db.rlen.size());
+    D->las.build_index(D->db.rlen.size()); validate_las(D->las, D->db.rlen);
   } catch (std::exception& e) { fprintf(stderr, "[E] %s\n", e.what()); return nullptr; }
   return D.release();
 }
 void dh_data_destroy(dh_data* d) { delete d; }
 int dh_data_write(dh_data* d, const char* lasfn, const char* dbfn) {
   try { write_dazzdb(dbfn, d->db); write_las(lasfn, d->las);
-    std::ofstream e(std::string(lasfn) + ".eprof"); e << d->st_match << " " << d->st_mis << " " << d->st_ins << " " << d->st_del << "\n"; }
+    const uint64_t c[4] = {d->st_match, d->st_mis, d->st_ins, d->st_del}; write_eprof(std::string(lasfn) + ".eprof", c, 0.0, 0.0); }
   catch (std::exception& e) { d->err = e.what(); return 1; }
   return 0;
 }
@@ -218,6 +234,8 @@ char* dh_format_segments(const dcu_segment* seg, uint64_t nseg, const char* char
   *outlen = out.size();
   return buf;
 }
+// the four counts of an error profile file (binary as the reference writes it, or this repository's earlier text form)
+int dh_read_eprof(const char* fn, uint64_t* out4) { return read_eprof(fn, out4) ? 0 : 1; }
 void dh_free(void* p) { free(p); }
 
 }  // extern "C"

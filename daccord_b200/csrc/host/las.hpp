@@ -29,10 +29,24 @@ struct LasData {
   std::vector<uint64_t> aidx;        // aidx[r]..aidx[r+1] = overlaps of A-read r   (size nreads+1)
   void build_index(uint64_t nreads) {
     aidx.assign(nreads + 1, 0);
-    for (auto& o : ovl) aidx[(uint64_t)o.aread + 1]++;
+    for (auto& o : ovl) { if (o.aread < 0 || (uint64_t)o.aread >= nreads) throw std::runtime_error("LAS does not match DB: aread " + std::to_string(o.aread) + " of " + std::to_string(nreads) + " reads"); aidx[(uint64_t)o.aread + 1]++; }
     for (uint64_t i = 0; i < nreads; ++i) aidx[i + 1] += aidx[i];
   }
 };
+
+// every record must refer to reads of the database and stay inside them: the .las and the .db have to belong together
+// (the reference gets this check from libmaus2's DB accessors; a wrong .db must not become an out-of-bounds access here)
+inline void validate_las(const LasData& L, const std::vector<uint32_t>& rlen) {
+  const int64_t n = (int64_t)rlen.size();
+  for (size_t i = 0; i < L.ovl.size(); ++i) {
+    const Overlap& o = L.ovl[i];
+    const bool ok = o.aread >= 0 && o.aread < n && o.bread >= 0 && o.bread < n && o.abpos >= 0 && o.abpos < o.aepos && (uint32_t)o.aepos <= rlen[o.aread] &&
+                    o.bbpos >= 0 && o.bbpos <= o.bepos && (uint32_t)o.bepos <= rlen[o.bread] && o.tlen >= 0 && (o.tlen & 1) == 0 && o.trace_off + (uint64_t)o.tlen <= L.trace.size();
+    if (!ok) throw std::runtime_error("LAS does not match DB: record " + std::to_string(i) + " (aread " + std::to_string(o.aread) + ", bread " + std::to_string(o.bread) +
+                                      ", a [" + std::to_string(o.abpos) + "," + std::to_string(o.aepos) + "), b [" + std::to_string(o.bbpos) + "," + std::to_string(o.bepos) + ")) of " +
+                                      std::to_string(n) + " reads");
+  }
+}
 
 inline void write_las(const std::string& fn, const LasData& L) {
   FILE* f = fopen(fn.c_str(), "wb");

@@ -18,7 +18,7 @@ def lib():
         if not os.path.exists(HOST_LIB_PATH):
             raise DcuError("host library %s not built: run `python -m daccord_b200.build`" % HOST_LIB_PATH)
         L = C.CDLL(HOST_LIB_PATH)
-        for f in ("dh_sim_create", "dh_data_load", "dh_data_load_range", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first",
+        for f in ("dh_sim_create", "dh_sim_create_ex", "dh_data_load", "dh_data_load_range", "dh_pile", "dh_vote", "dh_data_packed", "dh_batch_windows", "dh_batch_slices", "dh_batch_read_first",
                   "dh_select_overlaps", "dh_ovlset_data", "dh_data_trace", "dh_data_boff", "dh_data_rlen", "dh_format_segments"):
             getattr(L, f).restype = C.c_void_p
         for f in ("dh_data_nreads", "dh_data_novl", "dh_data_totlen"):
@@ -38,9 +38,18 @@ class Dataset:
         self.h = C.c_void_p(handle)
 
     @staticmethod
-    def simulate(genome_len, read_len=10000, coverage=40.0, p_ins=0.09, p_del=0.045, p_sub=0.015, repeat_frac=0.0, seed=0, tspace=100, min_ovl=1000):
-        return Dataset(lib().dh_sim_create(C.c_uint64(genome_len), C.c_uint64(read_len), C.c_double(coverage), C.c_double(p_ins), C.c_double(p_del),
-                                           C.c_double(p_sub), C.c_double(repeat_frac), C.c_uint64(seed), C.c_int32(tspace), C.c_uint64(min_ovl)))
+    def simulate(genome_len, read_len=10000, coverage=40.0, p_ins=0.09, p_del=0.045, p_sub=0.015, repeat_frac=0.0, seed=0, tspace=100, min_ovl=1000, keep_truth=False):
+        return Dataset(lib().dh_sim_create_ex(C.c_uint64(genome_len), C.c_uint64(read_len), C.c_double(coverage), C.c_double(p_ins), C.c_double(p_del),
+                                              C.c_double(p_sub), C.c_double(repeat_frac), C.c_uint64(seed), C.c_int32(tspace), C.c_uint64(min_ovl), C.c_int(int(keep_truth))))
+
+    def truth_eval(self, fasta, max_read=2**62):
+        """corrected FastA (bytes) against the simulated truth (keep_truth=True): dict with the corrected / truth bases compared, their edit distance
+        (banded: exact or an upper bound), the error events of the raw reads on the same intervals and the two error rates"""
+        a = (C.c_uint64 * 6)()
+        if lib().dh_truth_eval(self.h, fasta, C.c_uint64(len(fasta)), C.c_uint64(max_read), a):
+            raise DcuError(lib().dh_data_error(self.h).decode())
+        seg, b, tb, ed, raw, nr = [int(x) for x in a]
+        return {"segments": seg, "reads": nr, "corrected_bases": b, "truth_bases": tb, "edit_distance": ed, "erate": ed / max(tb, 1), "raw_error_events": raw, "raw_erate": raw / max(tb, 1)}
 
     @staticmethod
     def load(las, db):
@@ -156,6 +165,14 @@ class Batch:
         if self.h:
             lib().dh_batch_destroy(self.h)
             self.h = None
+
+
+def read_eprof(path):
+    """(matches, mismatches, insertions, deletions) of an error profile file (the reference's binary layout, or the text form of round 1)"""
+    a = (C.c_uint64 * 4)()
+    if lib().dh_read_eprof(path.encode(), a):
+        raise DcuError("cannot read error profile %s" % path)
+    return [int(x) for x in a]
 
 
 def format_segments(seg, chars, counter=0):

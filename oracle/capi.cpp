@@ -139,4 +139,8 @@ int oracle_estimate_profile(const char* lasfn, const char* dbfn, int64_t first, 
   } catch (std::exception& e) { fprintf(stderr, "[oracle] %s\n", e.what()); return 1; }
 }
 void oracle_free(void* p) { free(p); }
+// both edit distances of one pair (tests: the bit-parallel scoring distance equals the DP definition)
+void oracle_edit_distances(const uint8_t* a, uint64_t la, const uint8_t* b, uint64_t lb, uint64_t* out) {
+  out[0] = oracle::editDistance(a, la, b, lb); out[1] = oracle::editDistanceDP(a, la, b, lb);
+}
 }

@@ -32,6 +32,26 @@ def test_oracle_recovers_truth_at_40x():
     assert exact >= 195
 
 
+def test_oracle_scoring_distance_equals_dp():
+    """the bit-parallel edit distance of the oracle's candidate scoring (the CPU arm's hot loop) is the DP's number on random pairs, every length
+    0..70 on both sides (64 is the word limit, longer pairs take the DP) and on near-identical pairs like candidate vs slice"""
+    lib = oracle_lib()
+    rng = np.random.default_rng(5)
+    out = (C.c_uint64 * 2)()
+    for it in range(4000):
+        la, lb = int(rng.integers(0, 71)), int(rng.integers(0, 71))
+        a = rng.integers(0, 4, la).astype(np.uint8) + 65
+        if it % 2 and la:
+            b = a.copy()[:lb] if lb <= la else np.concatenate([a, rng.integers(0, 4, lb - la).astype(np.uint8) + 65])
+            for _ in range(int(rng.integers(0, 8))):
+                if len(b):
+                    b[int(rng.integers(0, len(b)))] = 65 + int(rng.integers(0, 4))
+        else:
+            b = rng.integers(0, 4, lb).astype(np.uint8) + 65
+        lib.oracle_edit_distances(a.ctypes.data_as(C.c_void_p), C.c_uint64(len(a)), b.ctypes.data_as(C.c_void_p), C.c_uint64(len(b)), out)
+        assert out[0] == out[1], (it, la, lb, out[0], out[1])
+
+
 CASES = [
     ("d40", dict(depth=40, n=250, seed=3, rf=0.0), {}),
     ("d10", dict(depth=10, n=250, seed=4, rf=0.0), {}),
