@@ -10,6 +10,7 @@
 #include <vector>
 #include <algorithm>
 #include <new>
+#include <mutex>
 #include "window_core.cuh"            // namespace dcu : every workspace field in the warp's HBM slab (overflow passes, deep piles)
 #define DCU_NS dcus
 #define DCU_TIER_SMEM 1
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
   if (a.vs_words) { for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = dcu::c_T.VSq[i]; __syncthreads(); }
   dcu::Ctx c;
   c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcu::c_layout.bytes;
-  c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq;
+  c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0;
   c.packed = a.packed; c.sl = a.sl;
   __shared__ int s_done[2][WPB];                       // double buffered: with a single barrier per round a fast warp must not overwrite what a slow one still reads
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(SWPB * 32, 1) dcus_window_kernel(const __grid_
   dcus::Ctx c;
   c.ws.base = a.slabs + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)dcus::c_layout.bytes;
   c.ws.sm = vs_bytes + (uint32_t)warp * dcus::c_layout.sbytes;
-  c.vsq = a.vs_words ? (const unsigned long long*)dcus::dcu_smem : dcus::c_T.VSq;
+  c.vsq = a.vs_words ? (const unsigned long long*)dcus::dcu_smem : dcus::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0;
   c.packed = a.packed; c.sl = a.sl;
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
   auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
@@ -322,6 +323,12 @@ __global__ void __launch_bounds__(VOTE_TPB) vote_k1(dvote::Ctx c, const dvote::R
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DCU_ERR_CUDA; } } while (0)
 
+// The launch-wide state of the window kernels (layout, capacities, tables, parameters) lives in __constant__ memory, one copy per
+// device and process: the window passes of several dcu_ctx on one device are therefore serialised by this lock (held from the
+// constant upload to the end of the last pass).  Everything else -- piling, vote, copies, the host work of a batch -- runs
+// concurrently, which is what lets a caller keep several batches in flight (daccord_main.cpp).
+std::mutex g_window_pass_lock[64];
+
 template <class T> struct DevBuf {
   T* p = nullptr; size_t cap = 0;
   cudaError_t ensure(size_t n) {
@@ -460,11 +467,21 @@ int dcu_set_reads_device(dcu_ctx* ctx, const void* dpacked, uint64_t nbytes) {
   return DCU_OK;
 }
 
+int dcu_share_reads(dcu_ctx* ctx, dcu_ctx* owner) {
+  if (!ctx || !owner || ctx->device != owner->device) return DCU_ERR_PARAM;
+  if (!owner->dpacked) { ctx->err = "owner holds no read database"; return DCU_ERR_STATE; }
+  ctx->dpacked = owner->dpacked; ctx->packed_bytes = owner->packed_bytes; ctx->packed_padded = owner->packed_padded;
+  return DCU_OK;
+}
+
 // sizes the workspaces and result buffers for a batch whose descriptors are (or will be) in ctx->dwin / ctx->dsl
 static int finish_batch(dcu_ctx* ctx, int maxS, int maxB, uint64_t totS, uint64_t nwin, uint64_t nsl) {
   if (maxS < 4) maxS = 4;
   if (maxB < 64) maxB = 64;
-  if (maxS >= ctx->HT.KLIMN || maxB > 65000) { ctx->err = "pile deeper than this build supports"; return DCU_ERR_UNSUPPORTED; }
+  // windows beyond what the 16-bit indices of the kernel address (>= KLIMN slices or > 65000 bases) end as DCU_WIN_OVERFLOW in the
+  // kernel's own capacity checks (load_window); they do not fail the batch
+  if (maxS >= ctx->HT.KLIMN) maxS = ctx->HT.KLIMN - 1;
+  if (maxB > 65000) maxB = 65000;
   ctx->maxS = maxS; ctx->maxB = maxB;
   // phase-synchronous group size: deep, homogeneous piles gain from large groups (instruction-cache locality); shallow
   // piles have a heavy tail of windows that need the filterfreq-1 pass, where waiting on the slowest warp costs more
@@ -498,7 +515,7 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
   // validate and size the workspaces for this batch
   int maxS = 4, maxB = 64; uint64_t totS = 0;
   const uint64_t nbases = ctx->packed_bytes * 4;
-  int bad = 0;                                     // 1 range, 2 slice too long, 3 slice outside DB, 4 A window length
+  int bad = 0;                                     // 1 range, 3 slice outside DB, 4 A window length (a slice longer than 255 bases ends its window as DCU_WIN_OVERFLOW in the kernel)
   const uint32_t wlen = ctx->prm.w, mincov = ctx->prm.min_cov;
 #pragma omp parallel for schedule(static) reduction(max : maxS, maxB, bad) reduction(+ : totS)
   for (int64_t i = 0; i < (int64_t)nwin; ++i) {
@@ -507,7 +524,6 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
     int b = 0;
     for (uint32_t j = 0; j < W.slice_cnt; ++j) {
       const dcu_slice& s = sl[W.slice_begin + j];
-      if (s.len > 255) bad = std::max(bad, 2);
       if ((uint64_t)s.gpos + s.len > nbases) bad = std::max(bad, 3);
       b += s.len;
     }
@@ -515,7 +531,6 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
     maxS = std::max<int>(maxS, W.slice_cnt); maxB = std::max(maxB, b); totS += W.slice_cnt;
   }
   if (bad == 1) { ctx->err = "window slice range out of bounds"; return DCU_ERR_PARAM; }
-  if (bad == 2) { ctx->err = "slice longer than 255 bases"; return DCU_ERR_UNSUPPORTED; }
   if (bad == 3) { ctx->err = "slice outside the read database"; return DCU_ERR_PARAM; }
   if (bad == 4) { ctx->err = "slice 0 of a window must be the A window of length w"; return DCU_ERR_PARAM; }
   int rc = finish_batch(ctx, maxS, maxB, totS, nwin, nsl);
@@ -594,7 +609,7 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
     CK(cudaMemcpyAsync(mx, dmx, sizeof(mx), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (herr) { ctx->err = "piling failed on the device (slice longer than 255 bases)"; return DCU_ERR_UNSUPPORTED; }
+    if (herr) { ctx->err = "piling failed on the device (slice longer than 65535 bases)"; return DCU_ERR_UNSUPPORTED; }
   }
   if (nwin_out) *nwin_out = tw;
   if (nsl_out) *nsl_out = ts;
@@ -685,6 +700,7 @@ int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
   ctx->launches = 0; ctx->hard = 0; ctx->second = 0; ctx->lost = 0;
   if (kernel_ms) *kernel_ms = 0.f;
   if (!ctx->nwin) return DCU_OK;
+  std::lock_guard<std::mutex> pass_lock(g_window_pass_lock[ctx->device & 63]);
   CK(cudaMemsetAsync(ctx->dcnt.p, 0, 4 * sizeof(unsigned int), ctx->stream));
   CK(cudaMemsetAsync(ctx->dcnt.p + 8, 0, 4 * sizeof(unsigned int), ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));

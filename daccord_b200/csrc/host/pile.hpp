@@ -130,7 +130,7 @@ struct ReadPiler {
         if (!MAo) { sl.push_back(dcu_slice{(uint32_t)db.gpos((uint32_t)aread, (uint32_t)astart), (uint16_t)P.w, 0}); ++MAo; }
         if (MAo < P.maxalign) {
           uint32_t s = (uint32_t)o.bbpos + b0, len = b1 - b0;
-          if (len > 255) throw std::runtime_error("B slice longer than 255 bases");
+          if (len > 65535u) throw std::runtime_error("B slice longer than 65535 bases");      // > 255: the kernel ends the window as DCU_WIN_OVERFLOW
           uint32_t LB = db.rlen[o.bread];
           uint64_t g = o.comp() ? db.gpos((uint32_t)o.bread, LB - s - len) : db.gpos((uint32_t)o.bread, s);
           sl.push_back(dcu_slice{(uint32_t)g, (uint16_t)len, (uint16_t)(o.comp() ? 1 : 0)});

@@ -162,7 +162,8 @@ PILE_FN void pile_order(const ReadInfo& R, const Ovl* ovl, double minerate, doub
 }
 // pile_window: candidate window y of read R (R.win_off = index of its candidate 0, R.nwin = number of candidates).
 // win == nullptr: returns the number of slices (0: empty pile, no window is emitted).  Otherwise writes the window
-// descriptor to *win and its slices to sl[0 .. n) with slice_begin = sl_index; returns n, or -1 if a slice exceeds 255 bases.
+// descriptor to *win and its slices to sl[0 .. n) with slice_begin = sl_index; returns n, or -1 if a slice length does not fit the descriptor (16 bit).  Slices longer than 255 bases are
+// written as they are: the window kernel ends such a window as DCU_WIN_OVERFLOW (8-bit instance positions), the batch goes on.
 PILE_FN int pile_window(const ReadInfo& R, uint32_t y, const Ovl* ovl, const Params& P, const uint32_t* bm, const uint64_t* read_boff, const uint32_t* read_len,
                         const unsigned long long* keys, uint32_t aread, Win* win, Sl* sl, uint32_t sl_index) {
   const uint64_t nintv = R.ovl_end - R.ovl_begin;
@@ -180,7 +181,7 @@ PILE_FN int pile_window(const ReadInfo& R, uint32_t y, const Ovl* ovl, const Par
         uint32_t s = (uint32_t)o.bbpos + b0, len = b1 - b0, LB = read_len[o.bread];
         bool comp = (o.flags & 1u) != 0;
         uint64_t g = read_boff[o.bread] * 4 + (comp ? (uint64_t)(LB - s - len) : (uint64_t)s);
-        if (len > 255) return -1;
+        if (len > 65535u) return -1;
         sl[ns].gpos = (uint32_t)g; sl[ns].len = (uint16_t)len; sl[ns].flags = (uint16_t)(comp ? 1 : 0);
       }
       ++ns; ++MAo;

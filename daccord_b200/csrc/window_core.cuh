@@ -57,7 +57,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
   X(bw, uint32_t, c.BW, 1) X(sw, uint16_t, c.S + 1, 1) X(soff, uint16_t, c.S + 1, 1) X(lenhist, uint16_t, 256, 0)      \
   X(hkey, uint32_t, c.H, 1) X(hval, hval_t, c.H, 1) X(hbA, uint32_t, c.NBITS / 32 + 4, 1) X(hbB, uint32_t, c.NBITS / 32 + 4, 1) \
   X(hstate, uint32_t, 4, 1)                                                                                           \
-  X(koff, uint16_t, c.S + 1, 1) X(choff, uint16_t, c.S + 1, 1) X(lastk, uint32_t, c.S, 1)                              \
+  X(koff, uint16_t, c.S + 1, 1) X(lastk, uint32_t, c.S, 1)                              \
   X(ts_k, uint32_t, c.S, 0) X(ts_c, uint16_t, c.S, 0) X(ts_n, uint16_t, c.S, 0)                                        \
   X(n_kmer, uint32_t, c.NN, 0) X(n_freq, uint16_t, c.NN, 1) X(n_ioff, ioff_t, c.NN, 1)                                 \
   X(n_nsucc, uint8_t, c.NN, 0) X(n_nact, uint8_t, c.NN, 0) X(n_npred, uint8_t, c.NN, 0)                                \
@@ -72,7 +72,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
   X(dt_off, uint16_t, c.ST, 0) X(dt_len, uint16_t, c.ST, 0) X(du_off, uint16_t, c.ST, 0) X(du_len, uint16_t, c.ST, 0)  \
   X(ds_rlO, uint16_t, c.ST, 0) X(ds_rlN, uint16_t, c.ST, 0)                                                           \
   X(ds_fB, uint8_t, c.ST, 0) X(ds_fN, uint8_t, c.ST, 0) X(ds_cB, uint8_t, c.ST, 0) X(ds_cN, uint8_t, c.ST, 0)          \
-  X(sf_w, double, c.SF, 0) X(sc_w, double, c.SF, 0) X(sc_wf, double, c.SF, 0)                                          \
+  X(sf_w, double, c.SF, 0) X(sf_wf, double, c.SF, 0) X(sf_wl, double, c.SF, 0) X(sc_w, double, c.SF, 0) X(sc_wf, double, c.SF, 0)                                          \
   X(n_pf, uint8_t, c.NN, 0) X(n_pt, uint8_t, c.NN, 0) X(n_cpf, uint8_t, c.NN, 0) X(n_cpt, uint8_t, c.NN, 0)            \
   X(n_dsf, uint16_t, c.NN, 0) X(n_dsn, uint8_t, c.NN, 0) X(skey, unsigned long long, c.STP, 0)                         \
   X(rl, uint32_t, c.RLP, 0)                                                                                           \
@@ -120,9 +120,7 @@ __constant__ Layout c_layout; __constant__ Caps c_cap; __constant__ Tables c_T; 
 #define DCU_CAP c_cap
 #define DCU_T c_T
 #define DCU_P c_P
-#if DCU_TIER_SMEM
-extern __shared__ __align__(128) uint8_t dcu_smem[];     // [transposed VS table | per-warp arenas]; fields marked S are addressed from this symbol so that the compiler emits LDS / STS / ATOMS
-#endif
+extern __shared__ __align__(128) uint8_t dcu_smem[];     // dynamic shared memory of both kernels: [transposed VS table | per-warp arenas (shared-memory build)]; the table and the fields marked S are addressed from this symbol so that the compiler emits LDS / STS / ATOMS
 #endif
 enum {
 #define X(name, type, n, S) F_##name,
@@ -154,6 +152,7 @@ struct WS {
 struct Ctx {
   WS ws;                                   // workspace of this warp
   const unsigned long long* vsq;           // transposed VS table (shared-memory copy when it fits, else HBM)
+  int vs_sm;                               // CUDA builds: the table sits at the start of dynamic shared memory (read through dcu_smem: LDS with 32-bit addressing)
   const uint8_t* packed; const Slice* sl;
   int MAo, nbases;
   int logh;                                // this window's hash uses the first 2^logh slots of the table (st_begin)
@@ -172,16 +171,16 @@ DCU_FN uint32_t hslot(const Ctx& c, uint32_t v) { return (v * 2654435761u) >> (3
 DCU_FN int hv_node(hval_t v) { return (v & 0x8000u) ? (int)(v & 0x7FFFu) : (int)NID_NONE; }
 DCU_FN hval_t hv_make(int cnt, int nid) { return nid == (int)NID_NONE ? (hval_t)cnt : (hval_t)(0x8000u | (uint32_t)nid); }
 // counts are 16-bit halves of 32-bit words: the add goes to the containing word (a count never reaches 2^15: HCAP / NI bound it)
-DCU_FN void hv_inc(hval_t* p) { a_add((uint32_t*)((uintptr_t)p & ~(uintptr_t)3), ((uintptr_t)p & 2) ? 0x10000u : 1u); }
+DCU_FN void hv_inc(hval_t* base, uint32_t h) { a_add((uint32_t*)base + (h >> 1), (h & 1u) ? 0x10000u : 1u); }      // (arrays are 16-byte aligned; indexing the word keeps the address space known: ATOMS, not a generic atomic)
 #else
 DCU_FN int hv_node(hval_t v) { return (int)(v >> 16); }
 DCU_FN hval_t hv_make(int cnt, int nid) { return (hval_t)cnt | ((hval_t)nid << 16); }
-DCU_FN void hv_inc(hval_t* p) { a_add(p, 1u); }
+DCU_FN void hv_inc(hval_t* base, uint32_t h) { a_add(base + h, 1u); }
 #endif
 // 16-bit counter add on the containing 32-bit word; returns the old value of the half (no carry: the counters stay below 2^16)
-DCU_FN uint32_t add16(uint16_t* p, uint32_t v) {
-  const bool hi = ((uintptr_t)p & 2) != 0;
-  const uint32_t o = a_add((uint32_t*)((uintptr_t)p & ~(uintptr_t)3), hi ? (v << 16) : v);
+DCU_FN uint32_t add16(uint16_t* base, uint32_t i, uint32_t v) {
+  const bool hi = (i & 1u) != 0;
+  const uint32_t o = a_add((uint32_t*)base + (i >> 1), hi ? (v << 16) : v);
   return hi ? (o >> 16) : (o & 0xFFFFu);
 }
 DCU_FN int lookup_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t key) {      // key = hkey[h], already loaded
@@ -320,7 +319,7 @@ DCU_BIG void load_window(Ctx& c, const Window& win, int lane, const uint8_t* raw
       big = big || len > 255u;                         // slices are at most 255 bases (8-bit instance positions)
       const uint32_t nw = (len + 15u) >> 4;
       const uint32_t inc = scan_incl(len, lane), incw = scan_incl(nw, lane), incr = scan_incl(cb, lane);
-      if (j < c.MAo) { w.soff()[j] = (uint16_t)(run + inc - len); w.sw()[j] = (uint16_t)(runw + incw - nw); w.koff()[j] = (uint16_t)(runr + incr - cb); }      // koff: chunk offsets until build_hash overwrites it
+      if (j < c.MAo) { w.soff()[j] = (uint16_t)(run + inc - len); w.sw()[j] = (uint16_t)(runw + incw - nw); w.koff()[j] = (uint16_t)(runr + incr - cb); }      // koff: offsets of the staged chunks
       run += bcast(inc, DCU_NL - 1); runw += bcast(incw, DCU_NL - 1); runr += bcast(incr, DCU_NL - 1);
     }
     if (ballot(big)) run = 0x10000000u;
@@ -412,64 +411,87 @@ DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, in
   wsync();
 }
 
-// claim / count one k-mer.  `old` is what the compare-and-swap of v into slot h returned; follows the probe sequence from there.
-// hstate[0] counts the claimed slots: the callers stop inserting beyond c.hcap, which keeps free slots in the table
+// claim / count one k-mer.  `old` is what slot h held when v was offered to it (compare-and-swap or load); follows the probe sequence
+// from there and counts the k-mer.  Returns the slot, bit 31 set when the slot was free and is now claimed (the callers keep count of
+// the claimed slots and stop inserting beyond c.hcap, which keeps free slots in the table)
 DCU_NOINL uint32_t hash_insert_from(const Ctx& c, uint32_t v, uint32_t h, uint32_t old) {
   const WS w = c.ws;
   const uint32_t mask = (1u << c.logh) - 1u;
+  uint32_t claimed = 0;
   DCU_NOUNROLL
   for (;;) {
-    if (old == W_EMPTY) { a_add(&w.hstate()[0], 1); hv_inc(&w.hval()[h]); break; }
-    if (old == v) { hv_inc(&w.hval()[h]); break; }
+    if (old == W_EMPTY) { claimed = 0x80000000u; break; }
+    if (old == v) break;
     h = (h + 1) & mask;
-    old = a_cas(&w.hkey()[h], W_EMPTY, v);
+    old = a_load(&w.hkey()[h]);
+    if (old == W_EMPTY) old = a_cas(&w.hkey()[h], W_EMPTY, v);
   }
-  return h;
+  hv_inc(w.hval(), h);
+  return h | claimed;
 }
-DCU_FN uint32_t hash_insert(const Ctx& c, uint32_t v) {
+DCU_FN void hash_insert(const Ctx& c, uint32_t v) {     // (the gap filler's extras)
   const uint32_t h = hslot(c, v);
-  return hash_insert_from(c, v, h, a_cas(&c.ws.hkey()[h], W_EMPTY, v));
+  if (hash_insert_from(c, v, h, a_cas(&c.ws.hkey()[h], W_EMPTY, v)) >> 31) a_add(&c.ws.hstate()[0], 1);
 }
-// k-mer instances are numbered seq-major; work is cut into chunks of CH consecutive k-mers of one sequence so that lanes stay
-// balanced whatever the pile depth.  f(j, i, len, v) for k-mer i of sequence j; g(j, v) with the final k-mer of a sequence.
-// koff / choff must hold the instance / chunk offsets (kmer_offsets).
-enum { KCH = 8 };
+// the same with the common cases in line: the home slot already holds the k-mer (a plain load tells), or is free.  `claimed` counts the
+// slots this lane claimed (the caller adds them up) unless `live`: then hstate[0] is kept up to date for the capacity check.
+DCU_FN void hash_insert_fast(const Ctx& c, uint32_t v, uint32_t& claimed, bool live) {
+  const WS& w = c.ws;
+  const uint32_t h = hslot(c, v);
+  uint32_t key = a_load(&w.hkey()[h]);
+  if (key != v) {
+    if (key == W_EMPTY) key = a_cas(&w.hkey()[h], W_EMPTY, v);
+    bool fresh = key == W_EMPTY;
+    if (!fresh && key != v) fresh = (hash_insert_from(c, v, h, key) >> 31) != 0;      // somebody else's k-mer: probe on (out of line; counts the k-mer itself)
+    else hv_inc(w.hval(), h);
+    if (fresh) { if (live) a_add(&w.hstate()[0], 1); else ++claimed; }
+    return;
+  }
+  hv_inc(w.hval(), h);
+}
+// k-mer -> node id with the first probe in line
+DCU_FN int lookup_fast(const Ctx& c, uint32_t v) {
+  const uint32_t h = hslot(c, v);
+  const uint32_t key = c.ws.hkey()[h];
+  if (key == v) return hv_node(c.ws.hval()[h]);
+  if (key == W_EMPTY) return NID_NONE;
+  return lookup_from(c, v, h, key);
+}
+// Every k-mer of the window once: a lane takes one part of one sequence (parts per sequence chosen so that the lanes of a warp are
+// filled whatever the pile depth: 2 for a 40x pile, 4 for shallow ones, 1 for deep ones) and rolls through it -- one base per step from
+// a register-held word, no searching.  f(j, i, len, v) for k-mer i of sequence j; g(j, v) with the final k-mer of a sequence.
+// No collective may be called from f or g (the lanes' trip counts differ).
 template <class F, class G> DCU_FN void for_each_kmer(const Ctx& c, int lane, F f, G g) {
-  const WS w = c.ws;
-  const int nch = (int)w.choff()[c.MAo];
+  const int K = c.k;
+  const int parts = c.MAo > 48 ? 1 : (c.MAo > 20 ? 2 : 4);
+  const int ntask = c.MAo * parts;
   DCU_NOUNROLL
-  for (int t = lane; t < nch; t += DCU_NL) {
-    int a = 0, b = c.MAo;                       // last j with choff[j] <= t (sequences without k-mers share the next one's offset)
-    DCU_NOUNROLL
-    while (b - a > 1) { int mid = (a + b) >> 1; if ((int)w.choff()[mid] <= t) a = mid; else b = mid; }
-    const int j = a, len = seqlen(c, j), numk = len - c.k + 1;
-    const int i0 = (t - (int)w.choff()[j]) * KCH, i1 = i0 + KCH < numk ? i0 + KCH : numk;
+  for (int t = lane; t < ntask; t += DCU_NL) {
+    const int j = t / parts, part = t - j * parts;
+    const int len = seqlen(c, j), numk = len - K + 1;
+    if (numk <= 0) continue;
+    const int per = (numk + parts - 1) / parts;
+    const int i0 = part * per, i1 = i0 + per < numk ? i0 + per : numk;
+    if (i0 >= i1) continue;
     const uint32_t* u = slice_words(c, j);
-    uint32_t v = 0;
+    uint32_t v = 0, wd = u[i0 >> 4] >> (2 * (i0 & 15));
+    int b = i0;                                        // next base to take
     DCU_NOUNROLL
-    for (int i = 0; i < c.k - 1; ++i) v = (v << 2) | bget(u, i0 + i);
+    for (; b < i0 + K - 1; ++b) { v = (v << 2) | (wd & 3u); wd >>= 2; if (((b + 1) & 15) == 0) wd = u[(b + 1) >> 4]; }
     DCU_NOUNROLL
-    for (int i = i0; i < i1; ++i) {
-      v = ((v << 2) & c.kmask) | bget(u, i + c.k - 1);
+    for (int i = i0; i < i1; ++i, ++b) {
+      v = ((v << 2) & c.kmask) | (wd & 3u); wd >>= 2;
+      if (((b + 1) & 15) == 0 && b + 1 < len) wd = u[(b + 1) >> 4];
       f(j, i, len, v);
     }
     if (i1 == numk) g(j, v);
   }
 }
-DCU_BIG void kmer_offsets(Ctx& c, int lane) {
-  const WS w = c.ws;
-  uint32_t runk = 0, runc = 0;
+DCU_BIG void kmer_offsets(Ctx& c, int lane) {          // number of k-mer instances of the window
+  uint32_t nk = 0;
   DCU_NOUNROLL
-  for (int base = 0; base < c.MAo; base += DCU_NL) {
-    int j = base + lane; uint32_t nk = 0, nc = 0;
-    if (j < c.MAo) { int len = seqlen(c, j); if (len >= c.k) { nk = (uint32_t)(len - c.k + 1); nc = (nk + KCH - 1) / KCH; } }
-    uint32_t ik = scan_incl(nk, lane), ic = scan_incl(nc, lane);
-    if (j < c.MAo) { w.koff()[j] = (uint16_t)(runk + ik - nk); w.choff()[j] = (uint16_t)(runc + ic - nc); }
-    runk += bcast(ik, DCU_NL - 1); runc += bcast(ic, DCU_NL - 1);
-  }
-  if (lane == 0) { w.koff()[c.MAo] = (uint16_t)runk; w.choff()[c.MAo] = (uint16_t)runc; }
-  c.ni = (int)runk;
-  wsync();
+  for (int j = lane; j < c.MAo; j += DCU_NL) { const int len = seqlen(c, j); if (len >= c.k) nk += (uint32_t)(len - c.k + 1); }
+  c.ni = (int)red_sum_u32(nk);
 }
 // pre-filter bit of a k-mer (shared-memory build): two bitmaps, A = seen, B = seen again.  A k-mer that occurs twice always has its
 // B bit set; one that occurs once has it set only when another k-mer shares the bit.  The table then holds the k-mers with B set,
@@ -490,6 +512,7 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
     if (lane == 0) w.hstate()[0] = 0;
   }
   kmer_offsets(c, lane);
+  wsync();                                             // the table is cleared before anybody inserts
   if (pre) {
     for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
       const uint32_t b = prebit(v), m = 1u << (b & 31);
@@ -498,12 +521,17 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
     wsync();
   }
   bool full = false;
+  const bool live = c.hcap != 0x7fffffff;              // the table may fill up: the claimed-slot counter has to be current
+  uint32_t claimed = 0;
   for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
     if (full) return;
     if (pre) { const uint32_t b = prebit(v); if (!((w.hbB()[b >> 5] >> (b & 31)) & 1u)) return; }      // (bitmaps are final: wsync above)
-    if (a_load(&w.hstate()[0]) > (uint32_t)c.hcap) { full = true; return; }        // racy read of a monotone counter: the overshoot is bounded by the lanes' in-flight inserts
-    hash_insert(c, v);
+    if (live && a_load(&w.hstate()[0]) > (uint32_t)c.hcap) { full = true; return; }      // racy read of a monotone counter: the overshoot is bounded by the lanes' in-flight inserts
+    hash_insert_fast(c, v, claimed, live);
   }, [&](int j, uint32_t v) { w.lastk()[j] = v; });                                // final k-mer of the sequence (the `last` array, :2108)
+  wsync();
+  claimed = red_sum_u32(claimed);
+  if (lane == 0 && claimed) w.hstate()[0] += claimed;
   wsync();
   if (ballot(full) || w.hstate()[0] > (uint32_t)c.hcap) { c.overflow = 23; wsync(); return; }
   // (count, kmer) of the distinct last k-mers, sorted descending (:1360-1391)
@@ -579,13 +607,13 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
   // instances are filed under their nodes: the k-mers are rolled once more and looked up (no per-instance slot array)
   for_each_kmer(c, lane, [&](int, int i, int len, uint32_t v) {
-    const int n = lookup(c, v);
-    if (n != NID_NONE) { const uint32_t t = add16(&w.fillcnt()[n], 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = (uint8_t)i; w.irpos()[t] = (uint8_t)(len - i - c.k); }
+    const int n = lookup_fast(c, v);
+    if (n != NID_NONE) { const uint32_t t = add16(w.fillcnt(), (uint32_t)n, 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = (uint8_t)i; w.irpos()[t] = (uint8_t)(len - i - c.k); }
   }, [](int, uint32_t) {});
   DCU_NOUNROLL
   for (int e = lane; e < c.nex; e += DCU_NL) {       // synthesised k-mers of the gap filler (:1148-1157)
     int n = lookup(c, w.ex_kmer()[e]);
-    if (n != NID_NONE) { const uint32_t t = add16(&w.fillcnt()[n], 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = w.ex_pos()[e]; w.irpos()[t] = w.ex_rpos()[e]; }
+    if (n != NID_NONE) { const uint32_t t = add16(w.fillcnt(), (uint32_t)n, 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = w.ex_pos()[e]; w.irpos()[t] = w.ex_rpos()[e]; }
   }
   wsync();
   uint32_t nf = 0;
@@ -698,7 +726,6 @@ DCU_BIG bool add_next(Ctx& c, int lane) {
 }
 
 DCU_NOINL double kw_fwd(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_T.NP) ? kweight(c, n, p, false) : 0.0; }
-DCU_NOINL double kw_rev(const Ctx& c, int n, int p) { return (p >= 0 && p < DCU_T.NP) ? kweight(c, n, p, true) : 0.0; }
 
 // ------------------------------------------------------------------ gap filling at filterfreq 0 (:1016-1161)
 DCU_BIG void gap_fill(Ctx& c, int lane) {
@@ -910,27 +937,31 @@ DCU_BIG void derive_stretches(Ctx& c, int F, int L, int lane) {
 DCU_FN int ds_first(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s]]; }
 DCU_FN int ds_last(const Ctx& c, int s) { return c.ws.slinks()[c.ws.ds_off()[s] + c.ws.ds_len()[s] - 1]; }
 
-// sum over the instance list ip[0,f) of col[min(ip[t],MS) * NP] (one table column per lane, instance positions shared by
-// the warp): the warp fetches the positions with one coalesced load per 32 instances and hands them round by shuffle.
-// `mine0` is this lane's byte of the first 32 instances (ip[lane], 0 beyond f), loaded by the caller one link ahead.
-DCU_FN unsigned long long inst_colsum(int mine0, const uint8_t* ip, int f, const unsigned long long* col, int NP, int MS, int lane) {
-  unsigned long long u = 0;
-#if DCU_NL == 1
-  for (int t = 0; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += col[a * NP]; }
-  (void)lane; (void)mine0;
-#else
-  // (also what the 32-lane emulations run: bcast is __shfl_sync on the GPU and a lane exchange there)
-  DCU_NOUNROLL
-  for (int t0 = 0; t0 < f; t0 += 32) {
-    int mine = t0 == 0 ? mine0 : ((t0 + lane < f) ? (int)ip[t0 + lane] : 0);
-    mine = mine < MS ? mine : MS;
-    const int n = f - t0 < 32 ? f - t0 : 32;
+// column p of the transposed VS table (element a at byte a * 8 * NP); SM (CUDA builds only): in the copy at the start of dynamic
+// shared memory, so that an element costs one multiply-add and a load with a 32-bit shared-memory address
+template <bool SM> DCU_FN const uint8_t* vs_col(const Ctx& c, int p) {
 #ifndef DCU_EMU
-#pragma unroll 4
+  if (SM) return dcu_smem + (uint32_t)p * 8u;
 #endif
-    for (int t = 0; t < n; ++t) { int a = bcast(mine, t); u += col[a * NP]; }
+  return (const uint8_t*)c.vsq + (uint32_t)p * 8u;
+}
+// positional weight sum of one node at one true position p (this lane's): sum over the instance list ip[0,f) of VS[min(ip[t],MS)][p].
+// Every lane walks the list itself (all lanes of a warp read the same instance byte: a broadcast load), no shuffles in the loop.
+template <bool SM> DCU_FN unsigned long long inst_colsum(const Ctx& c, const uint8_t* ip, int f, int p, int NP, int MS) {
+  unsigned long long u = 0;
+  const uint32_t row = (uint32_t)NP * 8u;
+  const uint8_t* col = vs_col<SM>(c, p);
+  int t = 0;
+  DCU_NOUNROLL
+  for (; t + 4 <= f; t += 4) {
+    int a0 = ip[t], a1 = ip[t + 1], a2 = ip[t + 2], a3 = ip[t + 3];
+    a0 = a0 < MS ? a0 : MS; a1 = a1 < MS ? a1 : MS; a2 = a2 < MS ? a2 : MS; a3 = a3 < MS ? a3 : MS;
+    const unsigned long long v0 = *(const unsigned long long*)(col + (uint32_t)a0 * row), v1 = *(const unsigned long long*)(col + (uint32_t)a1 * row),
+                             v2 = *(const unsigned long long*)(col + (uint32_t)a2 * row), v3 = *(const unsigned long long*)(col + (uint32_t)a3 * row);
+    u += v0; u += v1; u += v2; u += v3;
   }
-#endif
+  DCU_NOUNROLL
+  for (; t < f; ++t) { int a = ip[t]; a = a < MS ? a : MS; u += *(const unsigned long long*)(col + (uint32_t)a * row); }
   return u;
 }
 
@@ -939,19 +970,19 @@ DCU_FN unsigned long long inst_colsum(int mine0, const uint8_t* ip, int f, const
 // position); slot weight < 0 marks "not feasible".
 // sp_view fills the slots of one view (off, L) of the link array: lanes over anchor positions; the link weights are evaluated
 // on the fly from the instance lists (all lanes share the node, so instance positions are uniform loads and only the table
-// column differs per lane).  Warp-uniform arguments.  The loop over the links used to be a chain of dependent loads from the
-// workspace per link (link -> node -> instance list offset -> instance bytes), each an L2 or HBM round trip.  Now the descriptors of up
-// to 32 links are fetched at once, lane t taking link j0 + t (two round trips for the whole chunk), the loop gets them by shuffle,
-// and the instance bytes of link jj + 1 are requested before link jj is evaluated.
-DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
+// column differs per lane).  Warp-uniform arguments.  The descriptors of up to 32 links are fetched at once, lane t taking link
+// j0 + t (two round trips for the whole chunk), and the loop gets them by shuffle.  Besides the sum of the link weights a forward
+// slot keeps the weight of its first and of its last link (sf_wf, sf_wl: StretchFeasObject::wf / wl, :875-889) and a reverse slot
+// the weight of its first link (sc_wf), so that the searches never evaluate a node weight themselves.
+template <bool SM> DCU_FN void sp_view_t(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
   const WS& w = c.ws;
-  const unsigned long long* VT = c.vsq; const int NP = DCU_T.NP, MS = DCU_T.MS;
+  const int NP = DCU_T.NP, MS = DCU_T.MS;
   const int nmax = nf > nr ? nf : nr;
   DCU_NOUNROLL
   for (int q0 = 0; q0 < nmax; q0 += DCU_NL) {
     const int q = q0 + lane;
     bool af = q < nf, ar = q < nr;
-    double sumf = 0.0, sumr = 0.0, wfr = 0.0;
+    double sumf = 0.0, sumr = 0.0, wfr = 0.0, wff = 0.0, wlf = 0.0;
     bool live = true;
     DCU_NOUNROLL
     for (int j0 = 0; j0 < L && live; j0 += DCU_NL) {
@@ -962,35 +993,34 @@ DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int
         dioF = w.n_ioff()[nF]; dfF = w.n_freq()[nF]; dioR = w.n_ioff()[nR]; dfR = w.n_freq()[nR];
       }
       const int jn = L - j0 < DCU_NL ? L - j0 : DCU_NL;
-      uint32_t ioF = bcast(dioF, 0), ioR = bcast(dioR, 0); int fF = bcast(dfF, 0), fR = bcast(dfR, 0);
-      int mF = lane < fF ? (int)w.ipos()[ioF + lane] : 0, mR = lane < fR ? (int)w.irpos()[ioR + lane] : 0;
       DCU_NOUNROLL
       for (int t = 0; t < jn; ++t) {
         const int jj = j0 + t;
-        uint32_t nioF = ioF, nioR = ioR; int nfF = fF, nfR = fR, nmF = mF, nmR = mR;
-        if (t + 1 < jn) {                              // next link: descriptors by shuffle, instance bytes in flight while this link is evaluated
-          nioF = bcast(dioF, t + 1); nfF = bcast(dfF, t + 1); nioR = bcast(dioR, t + 1); nfR = bcast(dfR, t + 1);
-          nmF = lane < nfF ? (int)w.ipos()[nioF + lane] : 0; nmR = lane < nfR ? (int)w.irpos()[nioR + lane] : 0;
-        }
         if (!ballot(af || ar)) { live = false; break; }
-        if (ballot(af)) {                              // forward: link jj at true position bf + q + jj
-          int p = bf + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-          const unsigned long long u = inst_colsum(mF, w.ipos() + ioF, fF, VT + p, NP, MS, lane);
-          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
-          if (af) { if (wt >= 1e-3) sumf += wt; else af = false; }
+        const uint32_t ioF = bcast(dioF, t), ioR = bcast(dioR, t); const int fF = bcast(dfF, t), fR = bcast(dfR, t);
+        if (af) {                                      // forward: link jj at true position bf + q + jj
+          const int p = bf + q + jj;
+          double wt = 0.0;
+          if (p < NP) wt = (double)inst_colsum<SM>(c, w.ipos() + ioF, fF, p, NP, MS) * 2.3283064365386963e-10;
+          if (wt >= 1e-3) { sumf += wt; if (jj == 0) wff = wt; if (jj == L - 1) wlf = wt; } else af = false;
         }
-        if (ballot(ar)) {                              // reverse: link L-1-jj at reverse position br + q + jj
-          int p = br + q + jj; const bool in = p < NP; p = in ? p : NP - 1;
-          const unsigned long long u = inst_colsum(mR, w.irpos() + ioR, fR, VT + p, NP, MS, lane);
-          double wt = in ? (double)u * 2.3283064365386963e-10 : 0.0;
-          if (ar) { if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false; }
+        if (ar) {                                      // reverse: link L-1-jj at reverse position br + q + jj
+          const int p = br + q + jj;
+          double wt = 0.0;
+          if (p < NP) wt = (double)inst_colsum<SM>(c, w.irpos() + ioR, fR, p, NP, MS) * 2.3283064365386963e-10;
+          if (wt >= 1e-3) { sumr += wt; if (jj == 0) wfr = wt; } else ar = false;
         }
-        ioF = nioF; fF = nfF; mF = nmF; ioR = nioR; fR = nfR; mR = nmR;
       }
     }
-    if (q < nf) w.sf_w()[fO + q] = af ? sumf : -1.0;
+    if (q < nf) { w.sf_w()[fO + q] = af ? sumf : -1.0; w.sf_wf()[fO + q] = wff; w.sf_wl()[fO + q] = wlf; }
     if (q < nr) { w.sc_w()[cO + q] = ar ? sumr : -1.0; w.sc_wf()[cO + q] = wfr; }
   }
+}
+DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
+#ifndef DCU_EMU
+  if (c.vs_sm) { sp_view_t<true>(c, off, L, nf, nr, bf, br, fO, cO, lane); return; }
+#endif
+  sp_view_t<false>(c, off, L, nf, nr, bf, br, fO, cO, lane);
 }
 // The slots of a view depend on its links only, not on the (first,last) pair, and a pair splits at most the two unitigs that hold
 // its first / last k-mer as an interior node: the slots of the raw unitigs are therefore computed once per traverse (the first
@@ -1084,10 +1114,7 @@ DCU_NOINL int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchRever
   return w.sc_w()[o] >= 0.0 ? o : -1;
 }
 
-// weight of the first / last link of a stretch object (StretchFeasObject::wf / wl, :875-889), read back from the node tables
-DCU_FN double fwd_wf(const Ctx& c, int s, int p) { return kw_fwd(c, ds_first(c, s), p); }
-DCU_FN double fwd_wl(const Ctx& c, int s, int p) { return kw_fwd(c, ds_last(c, s), p + c.ws.ds_len()[s] - 1); }
-DCU_FN double rev_wf(const Ctx& c, int s, int p) { return kw_rev(c, ds_last(c, s), p); }
+// (the weights of the first / last link of a stretch object, StretchFeasObject::wf / wl :875-889, are the slot arrays sf_wf / sf_wl / sc_wf)
 
 // computeStretchLinks / getReverseStretchLinkWeight (:3388-3480): link A -> B (B.first == A.last) kept iff
 // max over common reverse positions of w_B + (w_A - wf_A) >= 0.1; stored as (B,A), sorted; lanes over A
@@ -1294,7 +1321,7 @@ DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScor
   int lpos = w.fp_pos()[P] - (w.ds_len()[ls] - 1);
   int o = sfo_fwd(c, ls, lpos);
   double s = w.fp_w()[P] + w.rp_w()[rpid];
-  return o >= 0 ? (s - fwd_wl(c, ls, lpos)) : s;
+  return o >= 0 ? (s - w.sf_wl()[o]) : s;
 }
 // best / next-best reverse path of an interval in (weight, sorted index) order (:3499-3534)
 DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
@@ -1327,7 +1354,7 @@ DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath 
   int L = w.ds_len()[s];
   double wt; int bl;
   if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sf_w()[o] : 0.0; }
-  else { bl = w.fp_baselen()[P] + L - 1; wt = w.fp_w()[P]; if (o >= 0) wt += w.sf_w()[o] - fwd_wf(c, s, ppos); }
+  else { bl = w.fp_baselen()[P] + L - 1; wt = w.fp_w()[P]; if (o >= 0) wt += w.sf_w()[o] - w.sf_wf()[o]; }
   DCU_PEAK(10, nfp + 1);
   if (nfp >= DCU_CAP.FP) { c.overflow = 14; return -1; }
   int id = nfp++;
@@ -1427,7 +1454,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
           double ew = o >= 0 ? w.sf_w()[o] : 0.0;
           if (ew > 0.1) {
             int L = w.ds_len()[s];
-            double nwt = w.fp_w()[P] + (w.sf_w()[o] - fwd_wf(c, s, w.fp_pos()[P]));
+            double nwt = w.fp_w()[P] + (w.sf_w()[o] - w.sf_wf()[o]);
             if (nwt > 0.1 && (w.fp_pos()[P] + L - 1 + K) <= lmax) {
               int id = fp_extend(c, nfp, P, s);
               if (id < 0) return;

@@ -13,8 +13,11 @@
  * trace of align(A-window, consensus) (reference src/HandleContext.hpp:2434-2493).
  *
  * Plain pointers and sizes only; int return codes (0 = ok); no exceptions cross the
- * boundary.  One dcu_ctx per GPU, used from one host thread at a time.  All input arrays
- * stay owned by the caller and may be released when the call returns.
+ * boundary.  A dcu_ctx is used from one host thread at a time and holds one resident batch; a
+ * caller that wants several batches in flight on one GPU (one being piled or voted while
+ * another runs the window kernel) creates one dcu_ctx per in-flight batch -- the library
+ * serialises their window passes and lets everything else overlap.  All input arrays stay
+ * owned by the caller and may be released when the call returns.
  */
 #ifndef DACCORD_B200_H
 #define DACCORD_B200_H
@@ -78,6 +81,8 @@ int dcu_set_reads(dcu_ctx* ctx, const uint8_t* packed, uint64_t nbytes);
 /* same, but the buffer is already resident in device memory on ctx's device (e.g. after an
  * ncclBroadcast of the database); the library does not take ownership */
 int dcu_set_reads_device(dcu_ctx* ctx, const void* dpacked, uint64_t nbytes);
+/* same database as `owner` (a dcu_ctx on the same device that got it through dcu_set_reads[_device]); owner must outlive ctx's use of it */
+int dcu_share_reads(dcu_ctx* ctx, dcu_ctx* owner);
 /* run one batch: host buffers in, host buffers out (results in submission order).
  * cons must hold nwin*DCU_CONS_STRIDE bytes, ops nwin*DCU_OPS_STRIDE bytes. */
 int dcu_run(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_slice* sl, uint64_t nsl,
