@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--repeat-frac", type=float, default=0.0, help="fraction of the genome covered by tandem repeats (BASELINE config 5: 0.2)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --mb is the total over all GPUs (BASELINE config 3)")
     ap.add_argument("--truth-reads", type=int, default=400, help="corrected reads compared with the simulated truth (0 = off)")
+    ap.add_argument("--cli", type=int, default=1, help="N=1 only: also time the `daccord` binary on the same data as .las / .db files (wall clock of the whole process)")
+    ap.add_argument("--cli-oracle-reads", type=int, default=24, help="A-reads on which the oracle's file driver (all threads) is run beside the binary for a byte comparison of the FastA (0 = off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -387,6 +389,38 @@ def main():
                 accuracy=truth, clocks=sampler.summary(), wall_s_timed=wall)
     if not full_wall:       # -w not a multiple of -a: the GPU piler does not apply, the descriptor path is the end-to-end number
         line["e2e"] = dict(line["e2e_descriptors"])
+    # ---- the command line itself: `daccord reads.las reads.db > fasta` on the same data as files (process start, DB + LAS ingest, CUDA context,
+    # error-profile file, pipelined batches, FastA text); compared with the library path above and, on a read range, with the oracle's file driver
+    if world == 1 and args.cli and full_wall:
+        import tempfile
+        exe = os.path.join(ROOT, "daccord_b200", "_build", "daccord")
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+            las, db = os.path.join(tmp, "b.las"), os.path.join(tmp, "b.db")
+            ds.write(las, db)
+            opts = ["-w%d" % args.w, "-a%d" % args.a, "-k%d" % args.k, "-D%d" % args.maxinput] + (["-d%d" % args.depth_cap] if args.depth_cap else [])
+            subprocess.run([exe] + opts + ["-I0,3", las, db], capture_output=True)          # first touch: page in the binary and the files, build the .dcuidx index
+            t0 = time.perf_counter()
+            r = subprocess.run([exe] + opts + ["--device%d" % local, las, db], capture_output=True)
+            cli_wall = time.perf_counter() - t0
+            cli = {"value": att / cli_wall if r.returncode == 0 else None, "unit": "windows/s", "wall_s": cli_wall, "rc": r.returncode,
+                   "what": "`daccord %s b.las b.db` as one process: DB + LAS load, CUDA context, tables, 3 batches in flight, FastA on stdout" % " ".join(opts),
+                   "fasta_identical_to_library_path": bool(r.stdout == gfasta), "fraction_of_e2e": (att / cli_wall) / (att * args.steps / e2e_wall) if r.returncode == 0 else None}
+            if r.returncode != 0:
+                cli["stderr_tail"] = r.stderr.decode(errors="replace")[-400:]
+            if args.cli_oracle_reads > 0 and r.returncode == 0:
+                sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+                from make_golden import oracle_fasta
+                from common import default_params
+                last = min(args.cli_oracle_reads, int(ds.nreads)) - 1
+                po = default_params(w=args.w, k_lo=args.k, k_hi=args.k, p_i=pi, p_d=pd, est_cor=cor)
+                t0 = time.perf_counter()
+                want, ost = oracle_fasta(po, las, db, 0, last, a=args.a, threads=effective_cpus()) if (not args.depth_cap and args.maxinput == 5000) else (None, None)
+                cli["oracle_files_s"] = time.perf_counter() - t0
+                if want is not None:
+                    r2 = subprocess.run([exe] + opts + ["-I0,%d" % last, "--device%d" % local, las, db], capture_output=True)
+                    cli["fasta_identical_to_oracle_file_driver"] = bool(r2.returncode == 0 and r2.stdout == want)
+                    cli["oracle_reads"] = last + 1
+        line["e2e_cli"] = cli
     # CPU baseline: the oracle on a bounded sample of the same windows, all host threads (rank 0, N=1 only); full comparison of the sample
     if world == 1 and args.cpu_sample_s > 0:
         from common import run_oracle, default_params

@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
                                "-o", HOST_LIB, host_src])
     cli = os.path.join(BUILD, "daccord")
     if force or _newer(cli, host_deps + [LIB]):
-        subprocess.check_call(["/usr/bin/g++", "-O3", "-g", "-std=c++17", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-o", cli,
+        subprocess.check_call(["/usr/bin/g++", "-O3", "-g", "-std=c++17", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-pthread", "-o", cli,
                                os.path.join(csrc, "host", "daccord_main.cpp"), "-L" + BUILD, "-ldaccord_b200", "-Wl,-rpath,$ORIGIN"])
     return LIB
 

@@ -42,6 +42,7 @@ struct KArgs {
   unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this pass
   unsigned long long packed_bytes;     // readable bytes of the packed database (staging never reads beyond)
   int stage;                           // shared-memory pass: stage the slices of the next window with cp.async.bulk
+  unsigned int launch_seq;             // number of this launch in the context's life (upper half of the forward slot tags: records of earlier launches in the slab are stale)
 };
 
 // One persistent launch per pass.  Every warp owns one window at a time and walks it through the stages of window_core.cuh; the
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_
   if (a.vs_words) { for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = dcu::c_T.VSq[i]; __syncthreads(); }
   dcu::Ctx c;
   c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcu::c_layout.bytes;
-  c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0;
+  c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0; c.epoch = (unsigned long long)a.launch_seq << 32;
   c.packed = a.packed; c.sl = a.sl;
   __shared__ int s_done[2][WPB];                       // double buffered: with a single barrier per round a fast warp must not overwrite what a slow one still reads
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(SWPB * 32, 1) dcus_window_kernel(const __grid_
   dcus::Ctx c;
   c.ws.base = a.slabs + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)dcus::c_layout.bytes;
   c.ws.sm = vs_bytes + (uint32_t)warp * dcus::c_layout.sbytes;
-  c.vsq = a.vs_words ? (const unsigned long long*)dcus::dcu_smem : dcus::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0;
+  c.vsq = a.vs_words ? (const unsigned long long*)dcus::dcu_smem : dcus::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0; c.epoch = (unsigned long long)a.launch_seq << 32;
   c.packed = a.packed; c.sl = a.sl;
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
   auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
@@ -331,13 +332,13 @@ std::mutex g_window_pass_lock[64];
 
 template <class T> struct DevBuf {
   T* p = nullptr; size_t cap = 0;
-  cudaError_t ensure(size_t n) {
+  cudaError_t ensure(size_t n, bool zero = false) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     size_t want = n + n / 4 + 16;
     cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
-    if (e == cudaSuccess) cap = want;
+    if (e == cudaSuccess) { cap = want; if (zero) e = cudaMemset(p, 0, want * sizeof(T)); }      // (workspace slabs start zeroed: no slot record carries a tag)
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -371,6 +372,7 @@ struct dcu_ctx {
   // vote scratch and results
   DevBuf<uint16_t> dvent; DevBuf<uint8_t> dvflag; DevBuf<uint64_t> dvblk; DevBuf<char> dvchars; DevBuf<dvote::Read> dvreads; DevBuf<dvote::Bound> dvbound;
   std::vector<dcu_segment> segs; uint64_t nchars = 0; bool results_valid = false;
+  unsigned int launch_seq = 0;
   uint64_t launches = 0, hard = 0, second = 0, lost = 0;     // second: windows the shared-memory pass handed on; hard: windows of the large-workspace pass; lost: beyond every capacity
   std::string err;
 };
@@ -629,7 +631,7 @@ static void fill_args(dcu_ctx* ctx, KArgs& a, int cnt_at, int list, const uint32
   a.packed = ctx->dpacked; a.sl = ctx->dsl.p; a.win = ctx->dwin.p; a.res = ctx->dres.p; a.cons = ctx->dcons.p; a.ops = ctx->dops.p;
   a.todo = todo; a.n = n;
   a.ticket = ctx->dcnt.p + cnt_at; a.ovf_cnt = ctx->dcnt.p + cnt_at + 1; a.ovf_list = ctx->dovf[list].p;
-  a.packed_bytes = ctx->packed_padded; a.stage = 0;
+  a.packed_bytes = ctx->packed_padded; a.stage = 0; a.launch_seq = ++ctx->launch_seq;
   { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 15; }
 }
 // HBM passes: tier 0 (first overflow pass, or the first pass when the shared-memory pass is off), tier 1 (large workspaces, free running)
@@ -638,7 +640,7 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   int grid = ctx->num_sms * bps;
   size_t need_blocks = ((size_t)n + WPB - 1) / WPB;
   if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
-  CK(ctx->dslab[tier].ensure((size_t)grid * WPB * ctx->lay[tier].bytes));
+  CK(ctx->dslab[tier].ensure((size_t)grid * WPB * ctx->lay[tier].bytes, true));
   KArgs a;
   CK(cudaMemcpyToSymbolAsync(dcu::c_layout, &ctx->lay[tier], sizeof(dcu::Layout), 0, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyToSymbolAsync(dcu::c_cap, &ctx->caps[tier], sizeof(dcu::Caps), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -672,7 +674,7 @@ static int launch_smem(dcu_ctx* ctx, uint32_t n) {
   int grid = ctx->num_sms;
   size_t need_blocks = ((size_t)n + wps - 1) / wps;
   if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
-  CK(ctx->dslab[2].ensure((size_t)grid * wps * ctx->layS.bytes));
+  CK(ctx->dslab[2].ensure((size_t)grid * wps * ctx->layS.bytes, true));
   CK(cudaMemcpyToSymbolAsync(dcus::c_layout, &ctx->layS, sizeof(dcus::Layout), 0, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyToSymbolAsync(dcus::c_cap, &ctx->capsS, sizeof(dcu::Caps), 0, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyToSymbolAsync(dcus::c_T, &ctx->T, sizeof(dcu::Tables), 0, cudaMemcpyHostToDevice, ctx->stream));

@@ -12,6 +12,11 @@
 #include <fstream>
 #include <iostream>
 #include <chrono>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
+#include <algorithm>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -33,11 +38,11 @@ static const char* HELP =
     "\t-e: maximum window error (default unlimited)\n\t-l: minimum length of output (default 0)\n"
     "\t--minfilterfreq: minimum k-mer filter frequency (default 0)\n\t--maxfilterfreq: maximum k-mer filter frequency (default 2)\n"
     "\t-D: maximum number of alignments considered per read (default 5000)\n\t-k: kmer size lo[,hi] (default 8)\n"
-    "\t--device: CUDA device ordinal (default 0)\n\t--batchreads: A-reads per GPU batch (default 256)\n";
+    "\t--device: CUDA device ordinal (default 0)\n\t--batchreads: A-reads per GPU batch (default 256)\n\t--inflight: batches in flight on the GPU (default 3)\n";
 
 struct Args { std::map<std::string, std::string> opt; std::vector<std::string> pos; };
 static bool parse_args(int argc, char** argv, Args& A) {
-  static const char* longs[] = {"minfilterfreq", "maxfilterfreq", "vard", "eprofonly", "deepprofileonly", "keepeprof", "device", "batchreads", "help", "version", nullptr};
+  static const char* longs[] = {"minfilterfreq", "maxfilterfreq", "vard", "eprofonly", "deepprofileonly", "keepeprof", "device", "batchreads", "inflight", "help", "version", nullptr};
   int i = 1;
   for (; i < argc; ++i) {
     std::string s = argv[i];
@@ -123,95 +128,141 @@ int main(int argc, char** argv) {
     prm.p_i = (double)ei / (double)len; prm.p_d = (double)ed / (double)len; prm.est_cor = 1.0 - (double)numerr / (double)len;
     fprintf(stderr, "error estimates\nerate=%g\ncor=%g\nins=%g\ndel=%g\n", (double)numerr / len, prm.est_cor, prm.p_i, prm.p_d);
     fprintf(stderr, "[V] using kmer range [%u,%u]\n", prm.k_lo, prm.k_hi);
-    dcu_ctx* ctx = nullptr;
-    int rc = dcu_create(&prm, device, &ctx);
-    if (rc) { fprintf(stderr, "[E] dcu_create: %s %s\n", dcu_strerror(rc), ctx ? dcu_last_error(ctx) : ""); return EXIT_FAILURE; }
-    rc = dcu_set_reads(ctx, db.bytes.data(), db.bytes.size());
-    if (rc) { fprintf(stderr, "[E] dcu_set_reads: %s %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-    PileParams PP; PP.w = prm.w; PP.a = advance; PP.maxalign = maxalign; PP.maxinput = maxinput;
+    // Main loop (replaces reference src/daccord.cpp:2107-2540).  The reference overlaps input, compute and ordered output over OpenMP
+    // threads (:2107-2112, :2481-2534); here `inflight` worker threads each own a dcu_ctx and walk the batches round robin: while one
+    // batch runs the window kernel, the others select overlaps, pile, vote and format (the library serialises only the window passes of
+    // the contexts of one device).  Output is released in batch order, sequences numbered like -t1.
+    const uint64_t maxalign_eff = std::min<uint64_t>(maxalign, 2047);       // deeper piles are capped like -d2047 (16-bit slice counts / 2048-entry KmerLimit table)
+    if (maxalign != UINT64_MAX && maxalign > maxalign_eff) fprintf(stderr, "[W] -d%lu capped at %lu\n", (unsigned long)maxalign, (unsigned long)maxalign_eff);
+    const int64_t nbatches = toparead > minaread ? (toparead - minaread + (int64_t)batchreads - 1) / (int64_t)batchreads : 0;
+    int inflight = (int)getu("inflight", 3);
+    if (inflight < 1) inflight = 1;
+    if ((int64_t)inflight > nbatches) inflight = (int)std::max<int64_t>(1, nbatches);
+    const int wthreads = std::max(1, nthreads / inflight);
+    std::vector<dcu_ctx*> ctxs((size_t)inflight, nullptr);
+    for (int i = 0; i < inflight; ++i) {
+      int rc = dcu_create(&prm, device, &ctxs[i]);
+      if (rc) { fprintf(stderr, "[E] dcu_create: %s %s\n", dcu_strerror(rc), ctxs[i] ? dcu_last_error(ctxs[i]) : ""); return EXIT_FAILURE; }
+      rc = i == 0 ? dcu_set_reads(ctxs[0], db.bytes.data(), db.bytes.size()) : dcu_share_reads(ctxs[i], ctxs[0]);
+      if (rc) { fprintf(stderr, "[E] dcu_set_reads: %s %s\n", dcu_strerror(rc), dcu_last_error(ctxs[i])); return EXIT_FAILURE; }
+    }
+    PileParams PP; PP.w = prm.w; PP.a = advance; PP.maxalign = maxalign_eff; PP.maxinput = maxinput;
     VoteParams VP; VP.producefull = producefull; VP.minlen = minlen;
-    uint64_t wellcounter = 0, totwin = 0, totok = 0;
-    std::vector<dcu_result> res; std::vector<uint8_t> cons, ops;
-    for (int64_t b0 = minaread; b0 < toparead; b0 += (int64_t)batchreads) {
-      const int64_t b1 = std::min<int64_t>(b0 + (int64_t)batchreads, toparead), nr = b1 - b0;
-      std::vector<dcu_window> win; std::vector<dcu_slice> sl; std::vector<uint64_t> first(nr + 1, 0);
-      const bool gpu_pile = (prm.w % advance == 0) && las.tspace <= 128 && !getenv("DACCORD_HOST_PILE");
-      const bool gpu_vote = !getenv("DACCORD_HOST_VOTE");
-      uint64_t nw = 0, ns = 0;
-      // stage 1: windows + slices -- on the GPU from the selected overlaps (dcu_pile), or by the host piler (dcu_upload)
-      if (gpu_pile) {
-        std::vector<dcu_overlap> ov; std::vector<uint32_t> sel;
-        for (int64_t r = b0; r < b1; ++r) {
-          select_overlaps(las, (uint64_t)r, maxinput, sel);
-          for (auto i : sel) { const Overlap& o = las.ovl[i]; dcu_overlap x; memset(&x, 0, sizeof(x)); x.abpos = o.abpos; x.aepos = o.aepos; x.bbpos = o.bbpos; x.bepos = o.bepos; x.flags = o.flags; x.aread = o.aread; x.bread = o.bread; x.diffs = o.diffs; x.tlen = o.tlen; x.trace_off = o.trace_off; ov.push_back(x); }
-        }
-        rc = dcu_pile(ctx, ov.data(), ov.size(), las.trace.data(), las.trace.size(), las.tspace, db.boff.data(), db.rlen.data(), db.rlen.size(), advance, maxalign, &nw, &ns);
-        if (rc) { fprintf(stderr, "[E] dcu_pile: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-      } else {
-        std::vector<std::vector<dcu_window>> wv(nr); std::vector<std::vector<dcu_slice>> sv(nr);
-#pragma omp parallel num_threads(nthreads)
-        {
-          ReadPiler RP(db, las, PP);
+    uint64_t wellcounter = 0, totwin = 0, totok = 0, totlost = 0;
+    std::mutex mu; std::condition_variable cv; int64_t turn = 0; std::atomic<int64_t> next{0}; std::atomic<bool> failed{false}; std::string failmsg;
+    const bool gpu_pile = (prm.w % advance == 0) && las.tspace <= 128 && !getenv("DACCORD_HOST_PILE");
+    const bool gpu_vote = !getenv("DACCORD_HOST_VOTE");
+    auto fail = [&](const std::string& m) { std::lock_guard<std::mutex> g(mu); if (!failed.exchange(true)) failmsg = m; cv.notify_all(); };
+    auto worker = [&](int wid) {
+      dcu_ctx* ctx = ctxs[wid];
+      std::vector<dcu_result> res; std::vector<uint8_t> cons, ops;
+      for (;;) {
+        const int64_t bi = next.fetch_add(1);
+        if (bi >= nbatches || failed.load()) break;
+        const int64_t b0 = minaread + bi * (int64_t)batchreads, b1 = std::min<int64_t>(b0 + (int64_t)batchreads, toparead), nr = b1 - b0;
+        std::vector<dcu_window> win; std::vector<dcu_slice> sl; std::vector<uint64_t> first(nr + 1, 0);
+        uint64_t nw = 0, ns = 0; int rc = 0;
+        // stage 1: windows + slices -- on the GPU from the selected overlaps (dcu_pile), or by the host piler (dcu_upload)
+        if (gpu_pile) {
+          std::vector<std::vector<uint32_t>> sels(nr);
+#pragma omp parallel for schedule(dynamic, 8) num_threads(wthreads)
+          for (int64_t r = 0; r < nr; ++r) select_overlaps(las, (uint64_t)(b0 + r), maxinput, sels[r]);
+          size_t tot = 0; for (auto& v : sels) tot += v.size();
+          std::vector<dcu_overlap> ov; ov.reserve(tot);
+          for (auto& sel : sels)
+            for (auto i : sel) { const Overlap& o = las.ovl[i]; dcu_overlap x; memset(&x, 0, sizeof(x)); x.abpos = o.abpos; x.aepos = o.aepos; x.bbpos = o.bbpos; x.bepos = o.bepos; x.flags = o.flags; x.aread = o.aread; x.bread = o.bread; x.diffs = o.diffs; x.tlen = o.tlen; x.trace_off = o.trace_off; ov.push_back(x); }
+          rc = dcu_pile(ctx, ov.data(), ov.size(), las.trace.data(), las.trace.size(), las.tspace, db.boff.data(), db.rlen.data(), db.rlen.size(), advance, maxalign_eff, &nw, &ns);
+          if (rc) { fail(std::string("dcu_pile: ") + dcu_strerror(rc) + ": " + dcu_last_error(ctx)); break; }
+        } else {
+          std::vector<std::vector<dcu_window>> wv(nr); std::vector<std::vector<dcu_slice>> sv(nr);
+#pragma omp parallel num_threads(wthreads)
+          {
+            ReadPiler RP(db, las, PP);
 #pragma omp for schedule(dynamic, 1)
-          for (int64_t i = 0; i < nr; ++i) {
-            try { RP.pile((uint64_t)(b0 + i), wv[i], sv[i]); }
-            catch (std::exception& e) {       // per-read failures are logged and skipped (reference src/daccord.cpp:2466-2478)
+            for (int64_t i = 0; i < nr; ++i) {
+              try { RP.pile((uint64_t)(b0 + i), wv[i], sv[i]); }
+              catch (std::exception& e) {       // per-read failures are logged and skipped (reference src/daccord.cpp:2466-2478)
 #pragma omp critical
-              { fprintf(stderr, "[E] read %ld: %s\n", (long)(b0 + i), e.what()); }
-              wv[i].clear(); sv[i].clear();
+                { fprintf(stderr, "[E] read %ld: %s\n", (long)(b0 + i), e.what()); }
+                wv[i].clear(); sv[i].clear();
+              }
+            }
+          }
+          for (int64_t i = 0; i < nr; ++i) { uint32_t base = (uint32_t)sl.size(); for (auto x : wv[i]) { x.slice_begin += base; win.push_back(x); } sl.insert(sl.end(), sv[i].begin(), sv[i].end()); }
+          nw = win.size(); ns = sl.size();
+          rc = dcu_upload(ctx, win.data(), nw, sl.data(), ns);
+          if (rc) { fail(std::string("dcu_upload: ") + dcu_strerror(rc) + ": " + dcu_last_error(ctx)); break; }
+        }
+        // stage 2: per-window consensus.  Windows beyond every capacity of the build come back as DCU_WIN_OVERFLOW: logged, treated as failed
+        rc = dcu_launch(ctx, nullptr);
+        if (rc) { fail(std::string("dcu_launch: ") + dcu_strerror(rc) + ": " + dcu_last_error(ctx)); break; }
+        uint64_t second = 0, lost = 0; uint32_t d0 = 0, d1 = 0;
+        dcu_last_stats2(ctx, &second, &lost, &d0, &d1);
+        if (lost) fprintf(stderr, "[W] reads [%ld,%ld): %s (no consensus for these windows)\n", (long)b0, (long)b1, dcu_last_error(ctx));
+        res.resize(nw);
+        // stage 3: pile vote -- on the GPU (only corrected bases and the 16-byte results cross PCIe), or on the host from the full results
+        std::vector<dcu_segment> seg; std::vector<char> chars; std::vector<std::string> parts;
+        if (gpu_vote) {
+          rc = dcu_download(ctx, res.data(), nullptr, nullptr);
+          uint64_t nseg = 0, nch = 0;
+          if (!rc) rc = dcu_vote(ctx, producefull ? 1 : 0, minlen, db.boff.data(), db.rlen.data(), db.rlen.size(), &nseg, &nch);
+          seg.resize(nseg); chars.resize(nch + 1);
+          if (!rc) rc = dcu_get_corrected(ctx, seg.data(), chars.data());
+          if (rc) { fail(std::string("dcu_vote: ") + dcu_strerror(rc) + ": " + dcu_last_error(ctx)); break; }
+        } else {
+          cons.resize(nw * DCU_CONS_STRIDE); ops.resize(nw * DCU_OPS_STRIDE);
+          rc = dcu_download(ctx, res.data(), cons.data(), ops.data());
+          if (!rc && gpu_pile) { win.resize(nw); rc = dcu_get_windows(ctx, win.data(), nullptr); }
+          if (rc) { fail(std::string("dcu_download: ") + dcu_strerror(rc) + ": " + dcu_last_error(ctx)); break; }
+          { uint64_t wi = 0; for (int64_t i = 0; i < nr; ++i) { first[i] = wi; while (wi < nw && (int64_t)win[wi].aread == b0 + i) ++wi; } first[nr] = nw; }
+          parts.resize(nr);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(wthreads)
+          for (int64_t i = 0; i < nr; ++i) {
+            if (first[i] == first[i + 1]) continue;
+            std::vector<PileElement> PV;
+            for (uint64_t wi = first[i]; wi < first[i + 1]; ++wi) if (res[wi].status == DCU_WIN_OK) place_window(win[wi], res[wi], cons.data() + wi * DCU_CONS_STRIDE, ops.data() + wi * DCU_OPS_STRIDE, PV);
+            std::string ab;
+            if (producefull) { std::vector<uint8_t> codes; decode_read(db, (uint32_t)(b0 + i), false, codes); ab.resize(codes.size()); for (size_t q = 0; q < codes.size(); ++q) ab[q] = "ACGT"[codes[q]]; }
+            uint64_t c0 = 0; vote_read(b0 + i, PV, VP, ab, c0, parts[i]);
+          }
+        }
+        uint64_t att = 0, okc = 0;
+        for (auto& r : res) { att += r.status != DCU_WIN_SKIPPED; okc += r.status == DCU_WIN_OK; }
+        // ordered release: batch bi writes after batch bi - 1
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return turn == bi || failed.load(); });
+        if (failed.load()) break;
+        if (gpu_vote) {
+          std::string text; format_segments(seg.data(), seg.size(), chars.data(), wellcounter, text);
+          fwrite(text.data(), 1, text.size(), stdout);
+        } else {
+          for (int64_t i = 0; i < nr; ++i) {        // sequences renumbered into the global counter
+            const std::string& s = parts[i]; size_t p = 0;
+            while (p < s.size()) {
+              size_t e = s.find('\n', p); if (e == std::string::npos) e = s.size();
+              if (s[p] == '>') { size_t s1 = s.find('/', p), s2 = s.find('/', s1 + 1); fwrite(s.data() + p, 1, s1 + 1 - p, stdout); fprintf(stdout, "%lu", (unsigned long)wellcounter++); fwrite(s.data() + s2, 1, e - s2, stdout); }
+              else fwrite(s.data() + p, 1, e - p, stdout);
+              fputc('\n', stdout); p = e + 1;
             }
           }
         }
-        for (int64_t i = 0; i < nr; ++i) { uint32_t base = (uint32_t)sl.size(); for (auto x : wv[i]) { x.slice_begin += base; win.push_back(x); } sl.insert(sl.end(), sv[i].begin(), sv[i].end()); }
-        nw = win.size(); ns = sl.size();
-        rc = dcu_upload(ctx, win.data(), nw, sl.data(), ns);
-        if (rc) { fprintf(stderr, "[E] dcu_upload: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
+        totwin += att; totok += okc; totlost += lost;
+        fprintf(stderr, "[V] reads [%ld,%ld) windows %lu\n", (long)b0, (long)b1, (unsigned long)nw);
+        ++turn;
+        lk.unlock();
+        cv.notify_all();
       }
-      // stage 2: per-window consensus
-      rc = dcu_launch(ctx, nullptr);
-      if (rc) { fprintf(stderr, "[E] dcu_launch: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-      res.resize(nw);
-      // stage 3: pile vote -- on the GPU (only corrected bases and the 16-byte results cross PCIe), or on the host from the full results
-      if (gpu_vote) {
-        rc = dcu_download(ctx, res.data(), nullptr, nullptr);
-        uint64_t nseg = 0, nch = 0;
-        if (!rc) rc = dcu_vote(ctx, producefull ? 1 : 0, minlen, db.boff.data(), db.rlen.data(), db.rlen.size(), &nseg, &nch);
-        std::vector<dcu_segment> seg(nseg); std::vector<char> chars(nch + 1);
-        if (!rc) rc = dcu_get_corrected(ctx, seg.data(), chars.data());
-        if (rc) { fprintf(stderr, "[E] dcu_vote: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-        std::string text; format_segments(seg.data(), nseg, chars.data(), wellcounter, text);     // A-read order, sequences numbered like -t1
-        fwrite(text.data(), 1, text.size(), stdout);
-      } else {
-        cons.resize(nw * DCU_CONS_STRIDE); ops.resize(nw * DCU_OPS_STRIDE);
-        rc = dcu_download(ctx, res.data(), cons.data(), ops.data());
-        if (!rc && gpu_pile) { win.resize(nw); rc = dcu_get_windows(ctx, win.data(), nullptr); }
-        if (rc) { fprintf(stderr, "[E] dcu_download: %s: %s\n", dcu_strerror(rc), dcu_last_error(ctx)); return EXIT_FAILURE; }
-        { uint64_t wi = 0; for (int64_t i = 0; i < nr; ++i) { first[i] = wi; while (wi < nw && (int64_t)win[wi].aread == b0 + i) ++wi; } first[nr] = nw; }
-        std::vector<std::string> parts(nr); std::vector<uint64_t> cnt(nr, 0);
-#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
-        for (int64_t i = 0; i < nr; ++i) {
-          if (first[i] == first[i + 1]) continue;
-          std::vector<PileElement> PV;
-          for (uint64_t wi = first[i]; wi < first[i + 1]; ++wi) if (res[wi].status == DCU_WIN_OK) place_window(win[wi], res[wi], cons.data() + wi * DCU_CONS_STRIDE, ops.data() + wi * DCU_OPS_STRIDE, PV);
-          std::string ab;
-          if (producefull) { std::vector<uint8_t> codes; decode_read(db, (uint32_t)(b0 + i), false, codes); ab.resize(codes.size()); for (size_t q = 0; q < codes.size(); ++q) ab[q] = "ACGT"[codes[q]]; }
-          uint64_t c0 = 0; vote_read(b0 + i, PV, VP, ab, c0, parts[i]); cnt[i] = c0;
-        }
-        for (int64_t i = 0; i < nr; ++i) {        // release in A-read order, numbering sequences like -t1
-          const std::string& s = parts[i]; size_t p = 0;
-          while (p < s.size()) {
-            size_t e = s.find('\n', p); if (e == std::string::npos) e = s.size();
-            if (s[p] == '>') { size_t s1 = s.find('/', p), s2 = s.find('/', s1 + 1); fwrite(s.data() + p, 1, s1 + 1 - p, stdout); fprintf(stdout, "%lu", (unsigned long)wellcounter++); fwrite(s.data() + s2, 1, e - s2, stdout); }
-            else fwrite(s.data() + p, 1, e - p, stdout);
-            fputc('\n', stdout); p = e + 1;
-          }
-        }
-      }
-      for (auto& r : res) { totwin += r.status != DCU_WIN_SKIPPED; totok += r.status == DCU_WIN_OK; }
-      fprintf(stderr, "[V] reads [%ld,%ld) windows %lu\n", (long)b0, (long)b1, (unsigned long)nw);
+    };
+    {
+      std::vector<std::thread> th;
+      for (int i = 1; i < inflight; ++i) th.emplace_back(worker, i);
+      worker(0);
+      for (auto& t : th) t.join();
     }
     fflush(stdout);
-    dcu_destroy(ctx);
+    for (auto it = ctxs.rbegin(); it != ctxs.rend(); ++it) dcu_destroy(*it);      // the owner of the read database (ctxs[0]) last
+    if (failed.load()) { fprintf(stderr, "[E] %s\n", failmsg.c_str()); return EXIT_FAILURE; }
+    if (totlost) fprintf(stderr, "[W] %lu windows exceeded the capacities of this build and have no consensus\n", (unsigned long)totlost);
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     fprintf(stderr, "[V] processed in time %.3fs, %lu windows attempted, %lu consensus\n", secs, (unsigned long)totwin, (unsigned long)totok);
   } catch (std::exception& e) { std::cerr << e.what() << std::endl; return EXIT_FAILURE; }

@@ -48,6 +48,11 @@ typedef uint32_t hval_t;                 // count | node id << 16 (0xFFFF: not a
 typedef uint32_t ioff_t;
 #endif
 
+// position slots of a stretch (computeFeasibleStretchPositions :3176-3330): sum of the link weights (< 0: not feasible), weight of the first
+// link and (forward) of the last link (StretchFeasObject::wf / wl, :875-889).  One record per slot: a search reads w and wf / wl of a slot together
+struct FSlot { double w, wf, wl; unsigned long long epoch; };      // epoch: the traverse the record was computed in (forward slots are evaluated on demand)
+struct RSlot { double w, wf; };
+
 // byte layout of a workspace, computed once on the host for a Caps: offsets of the fields marked S are relative to the warp's
 // shared-memory arena in the shared-memory build (sbytes), all others (and all fields of the HBM build) to the warp's slab (bytes)
 struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
@@ -72,7 +77,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
   X(dt_off, uint16_t, c.ST, 0) X(dt_len, uint16_t, c.ST, 0) X(du_off, uint16_t, c.ST, 0) X(du_len, uint16_t, c.ST, 0)  \
   X(ds_rlO, uint16_t, c.ST, 0) X(ds_rlN, uint16_t, c.ST, 0)                                                           \
   X(ds_fB, uint8_t, c.ST, 0) X(ds_fN, uint8_t, c.ST, 0) X(ds_cB, uint8_t, c.ST, 0) X(ds_cN, uint8_t, c.ST, 0)          \
-  X(sf_w, double, c.SF, 0) X(sf_wf, double, c.SF, 0) X(sf_wl, double, c.SF, 0) X(sc_w, double, c.SF, 0) X(sc_wf, double, c.SF, 0)                                          \
+  X(sfs, FSlot, c.SF, 0) X(scs, RSlot, c.SF, 0)                                          \
   X(n_pf, uint8_t, c.NN, 0) X(n_pt, uint8_t, c.NN, 0) X(n_cpf, uint8_t, c.NN, 0) X(n_cpt, uint8_t, c.NN, 0)            \
   X(n_dsf, uint16_t, c.NN, 0) X(n_dsn, uint8_t, c.NN, 0) X(skey, unsigned long long, c.STP, 0)                         \
   X(rl, uint32_t, c.RLP, 0)                                                                                           \
@@ -89,16 +94,14 @@ struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
   X(cand, uint8_t, (CDH_N + 1) * MAXCAND, 0) X(candlen, uint8_t, CDH_N + 1, 0)                                        \
   X(cdh_w, double, CDH_N, 0) X(cdh_id, uint32_t, CDH_N, 0) X(ch_w, double, CDH_N, 0) X(ch_id, uint32_t, CDH_N, 0)      \
   X(acc_w, double, CDH_N, 0) X(acc_err, uint32_t, CDH_N, 0) X(acc_slot, uint8_t, CDH_N, 0)                             \
-  X(prevs, uint8_t, MAXCAND, 0) X(tmps, uint8_t, MAXCAND, 0) X(best, uint8_t, MAXCAND, 0)                              \
-  X(m_pv, unsigned long long, 65, 0) X(m_mv, unsigned long long, 65, 0) X(m_ph, unsigned long long, 65, 0)             \
-  X(m_mh, unsigned long long, 65, 0)
+  X(prevs, uint8_t, MAXCAND, 0) X(tmps, uint8_t, MAXCAND, 0) X(best, uint8_t, MAXCAND, 0)
 
 static inline void make_layout(const Caps& c, Layout& L) {
   uint32_t o = 0, so = 0; int i = 0;
 #if DCU_TIER_SMEM
-#define X(name, type, n, S) { uint32_t& q = (S) ? so : o; q = (q + 15u) & ~15u; L.off[i++] = q; q += (uint32_t)(sizeof(type) * (size_t)(n)); }
+#define X(name, type, n, S) { uint32_t& q = (S) ? so : o; const uint32_t al = (S) ? 15u : 31u; q = (q + al) & ~al; L.off[i++] = q; q += (uint32_t)(sizeof(type) * (size_t)(n)); }
 #else
-#define X(name, type, n, S) { o = (o + 15u) & ~15u; L.off[i++] = o; o += (uint32_t)(sizeof(type) * (size_t)(n)); }
+#define X(name, type, n, S) { o = (o + 31u) & ~31u; L.off[i++] = o; o += (uint32_t)(sizeof(type) * (size_t)(n)); }      // 32 bytes: a slot record never straddles a sector
 #endif
   DCU_WS_FIELDS(X)
 #undef X
@@ -155,13 +158,15 @@ struct Ctx {
   int vs_sm;                               // CUDA builds: the table sits at the start of dynamic shared memory (read through dcu_smem: LDS with 32-bit addressing)
   const uint8_t* packed; const Slice* sl;
   int MAo, nbases;
-  int logh;                                // this window's hash uses the first 2^logh slots of the table (st_begin)
-  int hcap;                                // distinct k-mers the table accepts (st_begin)
+  int logh;                                // this window's hash uses the first 2^logh slots of the table (build_hash)
+  int hcap;                                // distinct k-mers the table accepts (build_hash)
   int hpre;                                // the table holds only k-mers that passed the pre-filter (seen at least twice, with false positives): valid for filter frequencies >= 2
   int k; uint32_t kmask; int kidx;
   int nn, ni, nex, nlast, nfirst;
   int nrs, slO, nds, nrl, kwtot;
   int overflow;
+  unsigned long long epoch, epoch_trav, epoch_pair;   // tags of the forward slot records: a counter ((launch << 32) | events of this warp) stepped at every traverse and pair
+  uint32_t fbase0;                         // forward slots below this offset hold the traverse's cached raw unitigs (tag epoch_trav), the others this pair's pieces (epoch_pair)
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -501,6 +506,11 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
   const WS w = c.ws;
   pre = pre && DCU_CAP.NBITS > 0;
   c.hpre = pre ? 1 : 0;
+  kmer_offsets(c, lane);
+  // table size of this window and k: the smallest power of two above (k-mer instances + gap filler extras), so that a free slot always
+  // remains whatever the k-mers are; where the capacity (LOGH) cuts it short the table only takes hcap distinct k-mers (the margin
+  // covers the inserts in flight when the limit is noticed) and a window beyond that is handed to the next pass
+  { int lg = 5; const int need = c.ni + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; c.hcap = (1 << lg) >= need ? 0x7fffffff : (1 << lg) - 288; }
   {
     const int H = 1 << c.logh;
     DCU_NOUNROLL
@@ -511,7 +521,6 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
     }
     if (lane == 0) w.hstate()[0] = 0;
   }
-  kmer_offsets(c, lane);
   wsync();                                             // the table is cleared before anybody inserts
   if (pre) {
     for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
@@ -534,16 +543,20 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
   if (lane == 0 && claimed) w.hstate()[0] += claimed;
   wsync();
   if (ballot(full) || w.hstate()[0] > (uint32_t)c.hcap) { c.overflow = 23; wsync(); return; }
-  // (count, kmer) of the distinct last k-mers, sorted descending (:1360-1391)
+  // (count, kmer) of the distinct last k-mers, sorted descending (:1360-1391); sequences without a k-mer carry W_EMPTY in lastk
   {
     int nl = 0;
     DCU_NOUNROLL
+    for (int j = lane; j < c.MAo; j += DCU_NL) if (seqlen(c, j) < c.k) w.lastk()[j] = W_EMPTY;
+    wsync();
+    DCU_NOUNROLL
     for (int base = 0; base < c.MAo; base += DCU_NL) {
-      int j = base + lane; int cnt = 0; bool first = false; uint32_t v = 0;
-      if (j < c.MAo && seqlen(c, j) >= c.k) {
-        v = w.lastk()[j]; first = true;
+      int j = base + lane; int cnt = 0; bool first = false; uint32_t v = W_EMPTY;
+      if (j < c.MAo) v = w.lastk()[j];
+      if (v != W_EMPTY) {
+        first = true;
         DCU_NOUNROLL
-        for (int i = 0; i < c.MAo; ++i) if (seqlen(c, i) >= c.k && w.lastk()[i] == v) { ++cnt; if (i < j) first = false; }
+        for (int i = 0; i < c.MAo; ++i) { const bool eq = w.lastk()[i] == v; cnt += eq ? 1 : 0; if (eq && i < j) first = false; }
       }
       uint32_t bb = ballot(first);
       int idx = nl + popc(bb & lanemask_lt(lane));
@@ -967,44 +980,36 @@ template <bool SM> DCU_FN unsigned long long inst_colsum(const Ctx& c, const uin
 
 // computeFeasibleStretchPositions (:3176-3330).  Every stretch owns one slot per position of its anchor's
 // support range (forward: first k-mer, object p = start position; reverse: last k-mer, object p = its reverse
-// position); slot weight < 0 marks "not feasible".
-// sp_view fills the slots of one view (off, L) of the link array: lanes over anchor positions; the link weights are evaluated
-// on the fly from the instance lists (all lanes share the node, so instance positions are uniform loads and only the table
-// column differs per lane).  Warp-uniform arguments.  The descriptors of up to 32 links are fetched at once, lane t taking link
-// j0 + t (two round trips for the whole chunk), and the loop gets them by shuffle.  Besides the sum of the link weights a forward
-// slot keeps the weight of its first and of its last link (sf_wf, sf_wl: StretchFeasObject::wf / wl, :875-889) and a reverse slot
-// the weight of its first link (sc_wf), so that the searches never evaluate a node weight themselves.
-template <bool SM> DCU_FN void sp_view_t(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
-  const WS& w = c.ws;
+// position); slot weight < 0 marks "not feasible".  A slot holds the sum of the link weights and the weight of the first (forward: also of
+// the last) link (StretchFeasObject::wf / wl, :875-889), so that the searches never evaluate a node weight themselves.
+// The REVERSE slots are all needed (stretch_links combines them pairwise) and are filled here, by sp_view.  The FORWARD slots are only ever
+// read by the forward search, which looks at a few per cent of them (tools/field_traffic.py: 1 050 slots written, 40 read per window):
+// they are evaluated on demand by the search itself (fwd_slot_eval) and remembered in the slot record, tagged with the traverse / pair
+// they belong to.  Same arithmetic in the same order either way.
+// sp_view fills the reverse slots of one view (off, L) of the link array: lanes over anchor positions; the link weights are evaluated
+// from the instance lists (all lanes share the node, so instance positions are uniform loads and only the table column differs per
+// lane).  Warp-uniform arguments.  The descriptors of up to 32 links are fetched at once, lane t taking link j0 + t, and the loop gets
+// them by shuffle.
+template <bool SM> DCU_FN void sp_view_t(const Ctx& c, int off, int L, int nr, int br, uint32_t cO, int lane) {
+  const WS w = c.ws;
   const int NP = DCU_T.NP, MS = DCU_T.MS;
-  const int nmax = nf > nr ? nf : nr;
   DCU_NOUNROLL
-  for (int q0 = 0; q0 < nmax; q0 += DCU_NL) {
+  for (int q0 = 0; q0 < nr; q0 += DCU_NL) {
     const int q = q0 + lane;
-    bool af = q < nf, ar = q < nr;
-    double sumf = 0.0, sumr = 0.0, wfr = 0.0, wff = 0.0, wlf = 0.0;
-    bool live = true;
+    bool ar = q < nr;
+    double sumr = 0.0, wfr = 0.0;
     DCU_NOUNROLL
-    for (int j0 = 0; j0 < L && live; j0 += DCU_NL) {
-      // descriptors of the links j0 .. j0 + 31: lane t holds link j0 + t (forward node of link jj, reverse node of link L - 1 - jj)
-      uint32_t dioF = 0, dioR = 0; int dfF = 0, dfR = 0;
-      if (j0 + lane < L) {
-        const int nF = w.slinks()[off + j0 + lane], nR = w.slinks()[off + L - 1 - (j0 + lane)];
-        dioF = w.n_ioff()[nF]; dfF = w.n_freq()[nF]; dioR = w.n_ioff()[nR]; dfR = w.n_freq()[nR];
-      }
+    for (int j0 = 0; j0 < L; j0 += DCU_NL) {
+      // descriptors of the links j0 .. j0 + 31 of the reverse walk: lane t holds the node of link L - 1 - (j0 + t)
+      uint32_t dioR = 0; int dfR = 0;
+      if (j0 + lane < L) { const int nR = w.slinks()[off + L - 1 - (j0 + lane)]; dioR = w.n_ioff()[nR]; dfR = w.n_freq()[nR]; }
       const int jn = L - j0 < DCU_NL ? L - j0 : DCU_NL;
+      if (!ballot(ar)) break;                          // nothing feasible left in this group of positions (checked once per 32 links)
       DCU_NOUNROLL
       for (int t = 0; t < jn; ++t) {
         const int jj = j0 + t;
-        if (!ballot(af || ar)) { live = false; break; }
-        const uint32_t ioF = bcast(dioF, t), ioR = bcast(dioR, t); const int fF = bcast(dfF, t), fR = bcast(dfR, t);
-        if (af) {                                      // forward: link jj at true position bf + q + jj
-          const int p = bf + q + jj;
-          double wt = 0.0;
-          if (p < NP) wt = (double)inst_colsum<SM>(c, w.ipos() + ioF, fF, p, NP, MS) * 2.3283064365386963e-10;
-          if (wt >= 1e-3) { sumf += wt; if (jj == 0) wff = wt; if (jj == L - 1) wlf = wt; } else af = false;
-        }
-        if (ar) {                                      // reverse: link L-1-jj at reverse position br + q + jj
+        const uint32_t ioR = bcast(dioR, t); const int fR = bcast(dfR, t);
+        if (ar) {                                      // link L-1-jj at reverse position br + q + jj
           const int p = br + q + jj;
           double wt = 0.0;
           if (p < NP) wt = (double)inst_colsum<SM>(c, w.irpos() + ioR, fR, p, NP, MS) * 2.3283064365386963e-10;
@@ -1012,15 +1017,40 @@ template <bool SM> DCU_FN void sp_view_t(const Ctx& c, int off, int L, int nf, i
         }
       }
     }
-    if (q < nf) { w.sf_w()[fO + q] = af ? sumf : -1.0; w.sf_wf()[fO + q] = wff; w.sf_wl()[fO + q] = wlf; }
-    if (q < nr) { w.sc_w()[cO + q] = ar ? sumr : -1.0; w.sc_wf()[cO + q] = wfr; }
+    if (q < nr) { RSlot r; r.w = ar ? sumr : -1.0; r.wf = wfr; w.scs()[cO + q] = r; }
   }
 }
-DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nf, int nr, int bf, int br, uint32_t fO, uint32_t cO, int lane) {
+DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nr, int br, uint32_t cO, int lane) {
 #ifndef DCU_EMU
-  if (c.vs_sm) { sp_view_t<true>(c, off, L, nf, nr, bf, br, fO, cO, lane); return; }
+  if (c.vs_sm) { sp_view_t<true>(c, off, L, nr, br, cO, lane); return; }
 #endif
-  sp_view_t<false>(c, off, L, nf, nr, bf, br, fO, cO, lane);
+  sp_view_t<false>(c, off, L, nr, br, cO, lane);
+}
+// one forward slot: stretch s anchored at true position p (one lane; the forward search calls this the first time it looks at a slot)
+template <bool SM> DCU_FN FSlot fwd_slot_eval_t(const Ctx& c, int s, int p, unsigned long long tag) {
+  const WS w = c.ws;
+  const int NP = DCU_T.NP, MS = DCU_T.MS;
+  const int off = w.ds_off()[s], L = w.ds_len()[s];
+  FSlot r; r.w = -1.0; r.wf = 0.0; r.wl = 0.0; r.epoch = tag;
+  double sum = 0.0;
+  DCU_NOUNROLL
+  for (int jj = 0; jj < L; ++jj) {                     // link jj at true position p + jj
+    const int n = w.slinks()[off + jj], pp = p + jj;
+    double wt = 0.0;
+    if (pp < NP) wt = (double)inst_colsum<SM>(c, w.ipos() + w.n_ioff()[n], (int)w.n_freq()[n], pp, NP, MS) * 2.3283064365386963e-10;
+    if (!(wt >= 1e-3)) return r;
+    sum += wt;
+    if (jj == 0) r.wf = wt;
+    if (jj == L - 1) r.wl = wt;
+  }
+  r.w = sum;
+  return r;
+}
+DCU_NOINL FSlot fwd_slot_eval(const Ctx& c, int s, int p, unsigned long long tag) {
+#ifndef DCU_EMU
+  if (c.vs_sm) return fwd_slot_eval_t<true>(c, s, p, tag);
+#endif
+  return fwd_slot_eval_t<false>(c, s, p, tag);
 }
 // The slots of a view depend on its links only, not on the (first,last) pair, and a pair splits at most the two unitigs that hold
 // its first / last k-mer as an interior node: the slots of the raw unitigs are therefore computed once per traverse (the first
@@ -1052,16 +1082,17 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
       DCU_NOUNROLL
       for (int r = 0; r < c.nrs; ++r) {
         const int off = w.rs_off()[r], L = w.rs_len()[r];
-        const int n0 = w.slinks()[off], n1 = w.slinks()[off + L - 1];
-        const int bf = w.n_pf()[n0], br = w.n_cpf()[n1];
-        const int nf = (uint8_t)(w.n_pt()[n0] - bf), nr = (uint8_t)(w.n_cpt()[n1] - br);
-        sp_view(c, off, L, nf, nr, bf, br, w.rs_fO()[r], w.rs_cO()[r], lane);
+        const int n1 = w.slinks()[off + L - 1];
+        const int br = w.n_cpf()[n1];
+        const int nr = (uint8_t)(w.n_cpt()[n1] - br);
+        sp_view(c, off, L, nr, br, w.rs_cO()[r], lane);
       }
       if (lane == 0) { w.spc()[0] = 1; w.spc()[1] = run0; w.spc()[2] = run1; }
       wsync();
     }
     base0 = w.spc()[1]; base1 = w.spc()[2];
   }
+  c.fbase0 = base0;                                  // forward slots below this offset belong to the traverse (cached raw unitigs), the others to this pair
   // the stretches of this pair: unsplit ones take the cached slots, the others get fresh slots behind the cache and go on the todo list
   uint32_t run0 = base0, run1 = base1; int ntodo = 0;
   uint16_t* todo = w.dt_off();                       // scratch of derive_stretches, free again
@@ -1097,24 +1128,28 @@ DCU_BIG void stretch_positions(Ctx& c, int lane) {
   DCU_NOUNROLL
   for (int t = 0; t < ntodo; ++t) {
     const int s = todo[t];
-    sp_view(c, w.ds_off()[s], w.ds_len()[s], w.ds_fN()[s], w.ds_cN()[s], w.ds_fB()[s], w.ds_cB()[s], w.ds_fO()[s], w.ds_cO()[s], lane);
+    sp_view(c, w.ds_off()[s], w.ds_len()[s], w.ds_cN()[s], w.ds_cB()[s], w.ds_cO()[s], lane);
   }
   wsync();
 }
-DCU_NOINL int sfo_fwd(const Ctx& c, int s, int p) {     // getCachedStretchPositionWeight (:3906-3918)
+DCU_NOINL int sfo_fwd(const Ctx& c, int s, int p) {     // getCachedStretchPositionWeight (:3906-3918); evaluates the slot at its first use
   const WS w = c.ws; int d = p - (int)w.ds_fB()[s];
   if (d < 0 || d >= (int)w.ds_fN()[s]) return -1;
-  int o = w.ds_fO()[s] + d;
-  return w.sf_w()[o] >= 0.0 ? o : -1;
+  const uint32_t o = w.ds_fO()[s] + (uint32_t)d;
+  const unsigned long long tag = o < c.fbase0 ? c.epoch_trav : c.epoch_pair;
+  double wt;
+  if (w.sfs()[o].epoch == tag) wt = w.sfs()[o].w;
+  else { const FSlot r = fwd_slot_eval(c, s, p, tag); w.sfs()[o] = r; wt = r.w; }
+  return wt >= 0.0 ? (int)o : -1;
 }
 DCU_NOINL int sfo_rev(const Ctx& c, int s, int p) {     // getCachedStretchReversePositionWeight (:3920-3932)
   const WS w = c.ws; int d = p - (int)w.ds_cB()[s];
   if (d < 0 || d >= (int)w.ds_cN()[s]) return -1;
   int o = w.ds_cO()[s] + d;
-  return w.sc_w()[o] >= 0.0 ? o : -1;
+  return w.scs()[o].w >= 0.0 ? o : -1;
 }
 
-// (the weights of the first / last link of a stretch object, StretchFeasObject::wf / wl :875-889, are the slot arrays sf_wf / sf_wl / sc_wf)
+// (the weights of the first / last link of a stretch object, StretchFeasObject::wf / wl :875-889, are fields of the slot records)
 
 // computeStretchLinks / getReverseStretchLinkWeight (:3388-3480): link A -> B (B.first == A.last) kept iff
 // max over common reverse positions of w_B + (w_A - wf_A) >= 0.1; stored as (B,A), sorted; lanes over A
@@ -1138,7 +1173,7 @@ DCU_BIG void stretch_links(Ctx& c, int lane) {
       for (int d = 0; d < cn; ++d) {
         const int da = cb + d + shift - aB;
         if (da < 0 || da >= aN) continue;
-        const double wb = w.sc_w()[co + d], wa = w.sc_w()[aO + da], wf = w.sc_wf()[aO + da];      // three independent loads
+        const double wb = w.scs()[co + d].w, wa = w.scs()[aO + da].w, wf = w.scs()[aO + da].wf;      // three independent loads
         if (!(wb >= 0.0) || !(wa >= 0.0)) continue;
         const double lw = wb + (wa - wf); weight = lw > weight ? lw : weight;
       }
@@ -1264,12 +1299,12 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp, int nseed) {
       for (int qs = 0; qs < nseed; ++qs) {              // stretches that end in Lnode, ascending (listed by trav_pair_rpaths)
         const int s = w.dt_len()[qs];
         int o = sfo_rev(c, s, rpos);                    // extendReversePath (:4058-4105) + feasibility (:4130-4159)
-        if (o >= 0 && w.sc_w()[o] >= 0.5) {
+        if (o >= 0 && w.scs()[o].w >= 0.5) {
           int L = w.ds_len()[s];
-          int nid = rp_new(c, nrp, w.sc_w()[o], (uint32_t)id, w.n_kmer()[ds_first(c, s)], s, rpos + L - 1, 1, L + c.k - 1);
+          int nid = rp_new(c, nrp, w.scs()[o].w, (uint32_t)id, w.n_kmer()[ds_first(c, s)], s, rpos + L - 1, 1, L + c.k - 1);
           if (nid < 0) return;
           if (nq >= DCU_CAP.RP) { c.overflow = 12; return; }
-          heap_push(true, w.rq_w(), w.rq_id(), nq, w.sc_w()[o], (uint32_t)nid);
+          heap_push(true, w.rq_w(), w.rq_id(), nq, w.scs()[o].w, (uint32_t)nid);
         }
       }
     } else if (bl < (lmax + 1) / 2) {
@@ -1278,9 +1313,9 @@ DCU_BIG void reverse_paths(Ctx& c, int Lnode, int lmax, int& narp, int nseed) {
       for (int t = w.ds_rlO()[ls], te = w.ds_rlO()[ls] + w.ds_rlN()[ls]; t < te; ++t) {
         int s = (int)(w.rl()[t] & 0xFFFF);
         int o = sfo_rev(c, s, rpos);
-        if (o >= 0 && w.sc_w()[o] >= 0.5) {
+        if (o >= 0 && w.scs()[o].w >= 0.5) {
           int L = w.ds_len()[s];
-          double nw = wt + (w.sc_w()[o] - w.sc_wf()[o]);
+          double nw = wt + (w.scs()[o].w - w.scs()[o].wf);
           int nid = rp_new(c, nrp, nw, (uint32_t)id, w.n_kmer()[ds_first(c, s)], s, rpos + L - 1, rlen + 1, bl + L - 1);
           if (nid < 0) return;
           if (nq >= DCU_CAP.RP) { c.overflow = 13; return; }
@@ -1321,7 +1356,7 @@ DCU_NOINL double pair_score(const Ctx& c, int P, int rpid) {      // getPairScor
   int lpos = w.fp_pos()[P] - (w.ds_len()[ls] - 1);
   int o = sfo_fwd(c, ls, lpos);
   double s = w.fp_w()[P] + w.rp_w()[rpid];
-  return o >= 0 ? (s - w.sf_wl()[o]) : s;
+  return o >= 0 ? (s - w.sfs()[o].wl) : s;
 }
 // best / next-best reverse path of an interval in (weight, sorted index) order (:3499-3534)
 DCU_NOINL int interval_next(const Ctx& c, int left, int right, int cur) {
@@ -1353,8 +1388,8 @@ DCU_NOINL int fp_extend(Ctx& c, int& nfp, int P, int s) {         // extendPath 
   int o = sfo_fwd(c, s, ppos);
   int L = w.ds_len()[s];
   double wt; int bl;
-  if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sf_w()[o] : 0.0; }
-  else { bl = w.fp_baselen()[P] + L - 1; wt = w.fp_w()[P]; if (o >= 0) wt += w.sf_w()[o] - w.sf_wf()[o]; }
+  if (plen == 0) { bl = L + c.k - 1; wt = o >= 0 ? w.sfs()[o].w : 0.0; }
+  else { bl = w.fp_baselen()[P] + L - 1; wt = w.fp_w()[P]; if (o >= 0) wt += w.sfs()[o].w - w.sfs()[o].wf; }
   DCU_PEAK(10, nfp + 1);
   if (nfp >= DCU_CAP.FP) { c.overflow = 14; return -1; }
   int id = nfp++;
@@ -1451,10 +1486,10 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
         DCU_NOUNROLL
         for (int s = w.n_dsf()[plast], se = (s == NID_NONE ? 0 : s + w.n_dsn()[plast]); s < se; ++s) {
           int o = sfo_fwd(c, s, w.fp_pos()[P]);
-          double ew = o >= 0 ? w.sf_w()[o] : 0.0;
+          double ew = o >= 0 ? w.sfs()[o].w : 0.0;
           if (ew > 0.1) {
             int L = w.ds_len()[s];
-            double nwt = w.fp_w()[P] + (w.sf_w()[o] - w.sf_wf()[o]);
+            double nwt = w.fp_w()[P] + (w.sfs()[o].w - w.sfs()[o].wf);
             if (nwt > 0.1 && (w.fp_pos()[P] + L - 1 + K) <= lmax) {
               int id = fp_extend(c, nfp, P, s);
               if (id < 0) return;
@@ -1510,6 +1545,7 @@ DCU_BIG void trav_start(Ctx& c, TravState& t, int lane) {
   g_stats[6]++;
 #endif
   const WS w = c.ws;
+  c.epoch_trav = ++c.epoch;                          // forward slot records of earlier traverses are stale
   if (lane == 0) w.spc()[0] = 0;                     // new unitigs: the cached position slots are stale (raw_stretches ends with a wsync)
   raw_stretches(c, lane);
   t.ncdh = 0; t.freeslots = (1u << (CDH_N + 1)) - 1;
@@ -1533,6 +1569,7 @@ DCU_BIG bool trav_seek(Ctx& c, TravState& t) {
 // the lane-parallel graph work (trav_pair_graph) and the single-lane searches (trav_pair_search)
 DCU_BIG void trav_pair_graph(Ctx& c, TravState& t, int lane) {
   const WS w = c.ws;
+  c.epoch_pair = ++c.epoch;
   t.F = w.fl_nid()[t.fi];
   t.L = lookup(c, w.ll_kmer()[t.li]);
   t.li += 1;
@@ -1619,31 +1656,57 @@ DCU_BIG int trav_finish(Ctx& c, TravState& t, int lane) {
 }
 
 // ------------------------------------------------------------------ placement: align(A window, consensus) with traceback
-// (HandleContext.hpp:2434-2493); convention C1 via bit-vector deltas.  lane 0.  Returns number of ops.
-DCU_BIG int placement(Ctx& c, const uint32_t* a, int la, const uint8_t* cons, int lb, uint8_t* ops) {
-  const WS w = c.ws;
+// (HandleContext.hpp:2434-2493); convention C1 via bit-vector deltas.  Returns number of ops (uniform).
+// All lanes run the column recurrence redundantly (it is a serial chain either way); the four delta words of column j stay in the
+// registers of lane j & 31 (two columns per lane) instead of going through the workspace, the traceback -- again the same on every
+// lane -- fetches a column by shuffle when it moves to it, collects the steps as 2-bit codes in registers and the lanes write the
+// trace in forward order at the end.  No memory is touched between reading the consensus and writing the trace.
+DCU_BIG int placement(Ctx& c, const uint32_t* a, int la, const uint8_t* cons, int lb, uint8_t* ops, int lane) {
   const Peq peq = make_peq_packed(a, la);            // a = packed base codes of the A window
   unsigned long long pv = ~0ull, mv = 0;
+#if DCU_NL == 1
+  unsigned long long kpv[64], kmv[64], kph[64], kmh[64];
+#else
+  unsigned long long kpv0 = 0, kmv0 = 0, kph0 = 0, kmh0 = 0, kpv1 = 0, kmv1 = 0, kph1 = 0, kmh1 = 0;
+#endif
+  if (lb > 64) return -1;
   DCU_NOUNROLL
-  for (int j = 1; j <= lb; ++j) {
-    unsigned long long eq = peq_of(peq, (uint32_t)ascii_code(cons[j - 1]));
+  for (int j = 0; j < lb; ++j) {                     // column j + 1 of the DP matrix
+    unsigned long long eq = peq_of(peq, (uint32_t)ascii_code(cons[j]));
     unsigned long long xv = eq | mv;
     unsigned long long xh = (((eq & pv) + pv) ^ pv) | eq;
     unsigned long long ph = mv | ~(xh | pv);
     unsigned long long mh = pv & xh;
-    w.m_ph()[j] = ph; w.m_mh()[j] = mh;       // horizontal deltas of rows 1..m (bit i-1), before the shift
+    const unsigned long long ph0 = ph, mh0 = mh;     // horizontal deltas of rows 1..m (bit i-1), before the shift
     ph = (ph << 1) | 1ull; mh <<= 1;
-    pv = mh | ~(xv | ph); mv = ph & xv;
-    w.m_pv()[j] = pv; w.m_mv()[j] = mv;       // vertical deltas in column j
+    pv = mh | ~(xv | ph); mv = ph & xv;              // vertical deltas in this column
+#if DCU_NL == 1
+    kpv[j] = pv; kmv[j] = mv; kph[j] = ph0; kmh[j] = mh0;
+#else
+    const bool mine = (j & 31) == lane;
+    if (j < 32) { if (mine) { kpv0 = pv; kmv0 = mv; kph0 = ph0; kmh0 = mh0; } }
+    else if (mine) { kpv1 = pv; kmv1 = mv; kph1 = ph0; kmh1 = mh0; }
+#endif
   }
-  int i = la, j = lb, n = 0;
-  // ops are produced backwards, then reversed in place
+  int i = la, j = lb, n = 0, cj = -1;
+  unsigned long long cpv = 0, cmv = 0, cph = 0, cmh = 0;
+  unsigned long long o0 = 0, o1 = 0, o2 = 0, o3 = 0;   // steps, newest last: 2 bits each, step n in word n >> 5
   DCU_NOUNROLL
   while (i > 0 || j > 0) {
     int op;
     if (i > 0 && j > 0) {
-      int dv = ((w.m_pv()[j] >> (i - 1)) & 1ull) ? 1 : (((w.m_mv()[j] >> (i - 1)) & 1ull) ? -1 : 0);
-      int dhup = (i == 1) ? 1 : (((w.m_ph()[j] >> (i - 2)) & 1ull) ? 1 : (((w.m_mh()[j] >> (i - 2)) & 1ull) ? -1 : 0));
+      if (cj != j) {                                 // delta words of column j (uniform branch: every lane walks the same path)
+#if DCU_NL == 1
+        cpv = kpv[j - 1]; cmv = kmv[j - 1]; cph = kph[j - 1]; cmh = kmh[j - 1];
+#else
+        const int src = (j - 1) & 31;
+        if (j - 1 < 32) { cpv = bcast(kpv0, src); cmv = bcast(kmv0, src); cph = bcast(kph0, src); cmh = bcast(kmh0, src); }
+        else { cpv = bcast(kpv1, src); cmv = bcast(kmv1, src); cph = bcast(kph1, src); cmh = bcast(kmh1, src); }
+#endif
+        cj = j;
+      }
+      int dv = ((cpv >> (i - 1)) & 1ull) ? 1 : (((cmv >> (i - 1)) & 1ull) ? -1 : 0);
+      int dhup = (i == 1) ? 1 : (((cph >> (i - 2)) & 1ull) ? 1 : (((cmh >> (i - 2)) & 1ull) ? -1 : 0));
       int ca = (int)bget(a, i - 1); int cb = ascii_code(cons[j - 1]);
       int cost = ca != cb;
       if (dv + dhup == cost) { op = cost ? 1 : 0; --i; --j; }
@@ -1651,12 +1714,20 @@ DCU_BIG int placement(Ctx& c, const uint32_t* a, int la, const uint8_t* cons, in
       else { op = 2; --j; }
     } else if (i > 0) { op = 3; --i; }
     else { op = 2; --j; }
-    if (n < 128) ops[n] = (uint8_t)op;
+    if (n < 128) {
+      const unsigned long long bit = (unsigned long long)op << (2 * (n & 31));
+      const int wi = n >> 5;
+      o0 |= wi == 0 ? bit : 0ull; o1 |= wi == 1 ? bit : 0ull; o2 |= wi == 2 ? bit : 0ull; o3 |= wi == 3 ? bit : 0ull;
+    }
     ++n;
   }
   if (n > 128) return -1;
   DCU_NOUNROLL
-  for (int x = 0, y = n - 1; x < y; ++x, --y) { uint8_t t = ops[x]; ops[x] = ops[y]; ops[y] = t; }
+  for (int x = lane; x < n; x += DCU_NL) {           // forward order
+    const int q = n - 1 - x, wi = q >> 5;
+    const unsigned long long wd = wi == 0 ? o0 : (wi == 1 ? o1 : (wi == 2 ? o2 : o3));
+    ops[x] = (uint8_t)((wd >> (2 * (q & 31))) & 3ull);
+  }
   return n;
 }
 
@@ -1690,7 +1761,7 @@ DCU_BIG void st_begin(Ctx& c, WinState& s, const Window& win, int lane, const ui
   // Results do not depend on the table size (the two workspace tiers already differ in it).
   // Where the capacity (LOGH) cuts the size short, the table only takes hcap distinct k-mers (the margin covers the inserts in flight
   // when the limit is noticed); beyond that the window is handed to the next pass.
-  { int lg = 5; const int need = c.nbases + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; c.hcap = (1 << lg) >= need ? 0x7fffffff : (1 << lg) - 288; }
+  // (build_hash sizes the table, from the number of k-mer instances at its k)
   int elength = estimate_length(c, lane);
   res.elength = elength;
   if (c.MAo < DCU_P.mincov) return;
@@ -1800,13 +1871,9 @@ DCU_BIG void st_final(Ctx& c, WinState& s, uint8_t* cons_out, uint8_t* ops_out, 
   Result& res = s.res;
   s.ph = PH_END;
   if (s.pathfailed) { res.status = ST_FAILED; return; }
-  int nops = 0;
-  if (lane == 0) {
-    DCU_NOUNROLL
-    for (int i = 0; i < s.bestlen; ++i) cons_out[i] = w.best()[i];
-    nops = placement(c, slice_words(c, 0), DCU_P.w, w.best(), s.bestlen, ops_out);
-  }
-  nops = bcast(nops, 0);
+  DCU_NOUNROLL
+  for (int i = lane; i < s.bestlen; i += DCU_NL) cons_out[i] = w.best()[i];
+  const int nops = placement(c, slice_words(c, 0), DCU_P.w, w.best(), s.bestlen, ops_out, lane);
   if (nops < 0) { c.overflow = 20; st_overflow(c, s); return; }
   res.status = ST_OK; res.k = (uint8_t)s.bestk; res.ff = (int8_t)s.bestff; res.clen = (uint8_t)s.bestlen;
   res.err = (uint32_t)s.minrate; res.nops = (uint16_t)nops; res.ncand = (uint16_t)s.bestn;

@@ -163,6 +163,7 @@ extern "C" int emu_lanes_run_batch(const dcu_params* prm, const uint8_t* packed,
       memset(&j.c, 0, sizeof(j.c)); memset(&j.cs, 0, sizeof(j.cs));
       j.c.ws.base = slab.data(); j.c.vsq = T.VSq; j.c.vs_sm = 0; j.c.packed = packed; j.c.sl = (const dcu::Slice*)sl;
       j.cs.ws.base = slab.data(); j.cs.ws.sm = arena.data(); j.cs.vsq = T.VSq; j.cs.vs_sm = 0; j.cs.packed = packed; j.cs.sl = (const dcu::Slice*)sl;
+      j.c.epoch = j.cs.epoch = (unsigned long long)(i + 1) << 32;      // tags of the forward slot records: unique per window, as the kernel's per-warp counter is
       memcpy(&j.W, &win[i], sizeof(j.W));
       memset(&j.r, 0, sizeof(j.r));
       j.cons = cons + i * DCU_CONS_STRIDE; j.ops = ops + i * DCU_OPS_STRIDE;

@@ -73,11 +73,11 @@ int main(int argc, char** argv) {
       dcu::Result r; memset(&r, 0, sizeof(r));
       if (smem_build) {
         dcus::Ctx c; memset(&c, 0, sizeof(c));
-        c.ws.base = slab.data(); c.ws.sm = arena.data(); c.vsq = T.VSq; c.vs_sm = 0; c.packed = packed.data(); c.sl = (const dcu::Slice*)sl.data();
+        c.ws.base = slab.data(); c.ws.sm = arena.data(); c.vsq = T.VSq; c.vs_sm = 0; c.epoch = (unsigned long long)(i + 1) << 32; c.packed = packed.data(); c.sl = (const dcu::Slice*)sl.data();
         dcus::process_window(c, W, r, cons.data() + i * DCU_CONS_STRIDE, ops.data() + i * DCU_OPS_STRIDE, l);
       } else {
         dcu::Ctx c; memset(&c, 0, sizeof(c));
-        c.ws.base = slab.data(); c.vsq = T.VSq; c.vs_sm = 0; c.packed = packed.data(); c.sl = (const dcu::Slice*)sl.data();
+        c.ws.base = slab.data(); c.vsq = T.VSq; c.vs_sm = 0; c.epoch = (unsigned long long)(i + 1) << 32; c.packed = packed.data(); c.sl = (const dcu::Slice*)sl.data();
         dcu::process_window(c, W, r, cons.data() + i * DCU_CONS_STRIDE, ops.data() + i * DCU_OPS_STRIDE, l);
       }
       lane_res[(size_t)l * nwin + i] = r;

@@ -169,7 +169,7 @@ def test_trace_runtime_attributes_workspace_accesses():
     n = lib.trace_report(_ptr(rep), C.c_int(len(names)))
     assert n == len(win)
     per = dict(zip(names, rep.reshape(-1, 4)[:, 2].astype(np.float64) * 32 / n))
-    assert 2000 < per["hkey"] < 60000 and per["ipos"] > 100 and per["sf_w"] > 1000 and 20000 < sum(per.values()) < 300000, per
+    assert 2000 < per["hkey"] < 60000 and per["ipos"] > 100 and per["scs"] > 1000 and 20000 < sum(per.values()) < 300000, per
 
 
 def test_edge_cases_empty_and_ragged():
