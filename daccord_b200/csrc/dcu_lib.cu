@@ -77,15 +77,16 @@ struct KArgs {
     if (st.ph == NS::PH_END && !idle) { publish(); __syncwarp(); }
 
 // ---- HBM build: layout, capacities, table descriptors and parameters in __constant__ memory (dcu::c_*), set per launch
-__global__ void __launch_bounds__(WPB * 32, BPS) dcu_window_kernel(const __grid_constant__ KArgs a) {
+// W warps per block, two blocks per SM: W = 16 gives 64 registers per thread, W = 12 (DCU_WPB=12, measurement knob) 85 at 24 warps per SM
+template <int W> __global__ void __launch_bounds__(W * 32, BPS) dcu_window_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ unsigned long long s_vs[];          // block-shared copy of the transposed VS table (when it fits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (a.vs_words) { for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = dcu::c_T.VSq[i]; __syncthreads(); }
   dcu::Ctx c;
-  c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcu::c_layout.bytes;
+  c.ws.base = a.slabs + ((size_t)blockIdx.x * W + warp) * (size_t)dcu::c_layout.bytes;
   c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0; c.epoch = (unsigned long long)a.launch_seq << 32;
   c.packed = a.packed; c.sl = a.sl;
-  __shared__ int s_done[2][WPB];                       // double buffered: with a single barrier per round a fast warp must not overwrite what a slow one still reads
+  __shared__ int s_done[2][W];                         // double buffered: with a single barrier per round a fast warp must not overwrite what a slow one still reads
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
   auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
   const int smask = a.sync_mask;                       // which of the inner stage boundaries are barriers (bit 0: hash|nodes, 5: nodes|edges, 1: edges|trav, 4: trav|pos, 2: pos|rpath, 6: rpath|search, 7: search|score, 3: score|final)
@@ -638,9 +639,11 @@ static void fill_args(dcu_ctx* ctx, KArgs& a, int cnt_at, int list, const uint32
 static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n) {
   int bps = ctx->blocks_per_sm[tier];
   int grid = ctx->num_sms * bps;
-  size_t need_blocks = ((size_t)n + WPB - 1) / WPB;
+  int wpb = WPB;
+  { const char* e = getenv("DCU_WPB"); if (e && atoi(e) == 12 && tier == 0) wpb = 12; }
+  size_t need_blocks = ((size_t)n + wpb - 1) / wpb;
   if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
-  CK(ctx->dslab[tier].ensure((size_t)grid * WPB * ctx->lay[tier].bytes, true));
+  CK(ctx->dslab[tier].ensure((size_t)grid * wpb * ctx->lay[tier].bytes, true));
   KArgs a;
   CK(cudaMemcpyToSymbolAsync(dcu::c_layout, &ctx->lay[tier], sizeof(dcu::Layout), 0, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyToSymbolAsync(dcu::c_cap, &ctx->caps[tier], sizeof(dcu::Caps), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -657,13 +660,16 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   if (vs_bytes > 40 * 1024 || getenv("DCU_VS_GLOBAL")) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);
   a.sync_group = tier ? 1 : ctx->sync_group;       // the large-workspace pass only sees heavy-tailed windows: free running
+  while (a.sync_group > 1 && wpb % a.sync_group) --a.sync_group;                       // groups must tile the block
   {   // leave as much of the 228 KB as possible to L1: the kernel lives on cached scratch data (measured +5 %, profiles/r01_summary.md)
     int pct = (int)((bps * (vs_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
     const char* e = getenv("DCU_CARVEOUT");
     if (e) pct = atoi(e);
-    CK(cudaFuncSetAttribute(dcu_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+    CK(cudaFuncSetAttribute(dcu_window_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+    CK(cudaFuncSetAttribute(dcu_window_kernel<12>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
   }
-  dcu_window_kernel<<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
+  if (wpb == 12) dcu_window_kernel<12><<<grid, 12 * 32, vs_bytes, ctx->stream>>>(a);
+  else dcu_window_kernel<16><<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;
   return DCU_OK;

@@ -440,10 +440,9 @@ DCU_FN void hash_insert(const Ctx& c, uint32_t v) {     // (the gap filler's ext
 }
 // the same with the common cases in line: the home slot already holds the k-mer (a plain load tells), or is free.  `claimed` counts the
 // slots this lane claimed (the caller adds them up) unless `live`: then hstate[0] is kept up to date for the capacity check.
-DCU_FN void hash_insert_fast(const Ctx& c, uint32_t v, uint32_t& claimed, bool live) {
+DCU_FN void hash_insert_fast(const Ctx& c, uint32_t v, uint32_t key /* what the home slot held a moment ago */, uint32_t& claimed, bool live) {
   const WS& w = c.ws;
   const uint32_t h = hslot(c, v);
-  uint32_t key = a_load(&w.hkey()[h]);
   if (key != v) {
     if (key == W_EMPTY) key = a_cas(&w.hkey()[h], W_EMPTY, v);
     bool fresh = key == W_EMPTY;
@@ -455,9 +454,8 @@ DCU_FN void hash_insert_fast(const Ctx& c, uint32_t v, uint32_t& claimed, bool l
   hv_inc(w.hval(), h);
 }
 // k-mer -> node id with the first probe in line
-DCU_FN int lookup_fast(const Ctx& c, uint32_t v) {
+DCU_FN int lookup_fast(const Ctx& c, uint32_t v, uint32_t key /* hkey[hslot(v)] */) {
   const uint32_t h = hslot(c, v);
-  const uint32_t key = c.ws.hkey()[h];
   if (key == v) return hv_node(c.ws.hval()[h]);
   if (key == W_EMPTY) return NID_NONE;
   return lookup_from(c, v, h, key);
@@ -489,6 +487,39 @@ template <class F, class G> DCU_FN void for_each_kmer(const Ctx& c, int lane, F 
       if (((b + 1) & 15) == 0 && b + 1 < len) wd = u[(b + 1) >> 4];
       f(j, i, len, v);
     }
+    if (i1 == numk) g(j, v);
+  }
+}
+// The same with the table probes of four consecutive k-mers in flight at a time: pre(v) issues the load of a k-mer's home slot and
+// returns what it held, f(j, i, len, v, key) gets it.  A key may be stale by the time f runs (an earlier k-mer of the same group may
+// have claimed the slot): f must treat an empty key as "try to claim", which the compare-and-swap then decides.
+template <class P, class F, class G> DCU_FN void for_each_kmer4(const Ctx& c, int lane, P pre, F f, G g) {
+  const int K = c.k;
+  const int parts = c.MAo > 48 ? 1 : (c.MAo > 20 ? 2 : 4);
+  const int ntask = c.MAo * parts;
+  DCU_NOUNROLL
+  for (int t = lane; t < ntask; t += DCU_NL) {
+    const int j = t / parts, part = t - j * parts;
+    const int len = seqlen(c, j), numk = len - K + 1;
+    if (numk <= 0) continue;
+    const int per = (numk + parts - 1) / parts;
+    const int i0 = part * per, i1 = i0 + per < numk ? i0 + per : numk;
+    if (i0 >= i1) continue;
+    const uint32_t* u = slice_words(c, j);
+    uint32_t v = 0, wd = u[i0 >> 4] >> (2 * (i0 & 15));
+    int b = i0;                                        // next base to take
+    DCU_NOUNROLL
+    for (; b < i0 + K - 1; ++b) { v = (v << 2) | (wd & 3u); wd >>= 2; if (((b + 1) & 15) == 0) wd = u[(b + 1) >> 4]; }
+    auto roll = [&]() { v = ((v << 2) & c.kmask) | (wd & 3u); wd >>= 2; ++b; if ((b & 15) == 0 && b < len) wd = u[b >> 4]; return v; };
+    int i = i0;
+    DCU_NOUNROLL
+    for (; i + 4 <= i1; i += 4) {
+      const uint32_t v0 = roll(), v1 = roll(), v2 = roll(), v3 = roll();
+      const uint32_t k0 = pre(v0), k1 = pre(v1), k2 = pre(v2), k3 = pre(v3);
+      f(j, i, len, v0, k0); f(j, i + 1, len, v1, k1); f(j, i + 2, len, v2, k2); f(j, i + 3, len, v3, k3);
+    }
+    DCU_NOUNROLL
+    for (; i < i1; ++i) { const uint32_t vv = roll(); f(j, i, len, vv, pre(vv)); }
     if (i1 == numk) g(j, v);
   }
 }
@@ -532,11 +563,11 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
   bool full = false;
   const bool live = c.hcap != 0x7fffffff;              // the table may fill up: the claimed-slot counter has to be current
   uint32_t claimed = 0;
-  for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
+  for_each_kmer4(c, lane, [&](uint32_t v) { return a_load(&w.hkey()[hslot(c, v)]); }, [&](int, int, int, uint32_t v, uint32_t key) {
     if (full) return;
     if (pre) { const uint32_t b = prebit(v); if (!((w.hbB()[b >> 5] >> (b & 31)) & 1u)) return; }      // (bitmaps are final: wsync above)
     if (live && a_load(&w.hstate()[0]) > (uint32_t)c.hcap) { full = true; return; }      // racy read of a monotone counter: the overshoot is bounded by the lanes' in-flight inserts
-    hash_insert_fast(c, v, claimed, live);
+    hash_insert_fast(c, v, key, claimed, live);
   }, [&](int j, uint32_t v) { w.lastk()[j] = v; });                                // final k-mer of the sequence (the `last` array, :2108)
   wsync();
   claimed = red_sum_u32(claimed);
@@ -619,8 +650,8 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   DCU_PEAK(3, c.ni);
   if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
   // instances are filed under their nodes: the k-mers are rolled once more and looked up (no per-instance slot array)
-  for_each_kmer(c, lane, [&](int, int i, int len, uint32_t v) {
-    const int n = lookup_fast(c, v);
+  for_each_kmer4(c, lane, [&](uint32_t v) { return w.hkey()[hslot(c, v)]; }, [&](int, int i, int len, uint32_t v, uint32_t key) {
+    const int n = lookup_fast(c, v, key);
     if (n != NID_NONE) { const uint32_t t = add16(w.fillcnt(), (uint32_t)n, 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = (uint8_t)i; w.irpos()[t] = (uint8_t)(len - i - c.k); }
   }, [](int, uint32_t) {});
   DCU_NOUNROLL

@@ -10,7 +10,7 @@ ns = "dcus" if "dcus" in kern else "dcu"
 elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
 funcs = []
 for line in elf.splitlines():
-    m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+0\s+0x[0-9a-f]+\s+\$.*\d+%sE.*\$_ZN\d+%s\d+([A-Za-z_0-9]+?)E" % (kern, ns), line)
+    m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+0\s+0x[0-9a-f]+\s+\$.*\d+%s(?:I\w+?E)?E.*\$_ZN\d+%s\d+([A-Za-z_0-9]+?)E" % (kern, ns), line)
     if m:
         funcs.append((int(m.group(1), 16), int(m.group(2), 16), re.sub(r"I[A-Z].*", "", m.group(3))))
 funcs.sort()
