@@ -78,7 +78,7 @@ struct KArgs {
 
 // ---- HBM build: layout, capacities, table descriptors and parameters in __constant__ memory (dcu::c_*), set per launch
 // W warps per block, two blocks per SM: W = 16 gives 64 registers per thread, W = 12 (DCU_WPB=12, measurement knob) 85 at 24 warps per SM
-template <int W> __global__ void __launch_bounds__(W * 32, BPS) dcu_window_kernel(const __grid_constant__ KArgs a) {
+template <int W, int B = BPS> __global__ void __launch_bounds__(W * 32, B) dcu_window_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ unsigned long long s_vs[];          // block-shared copy of the transposed VS table (when it fits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (a.vs_words) { for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = dcu::c_T.VSq[i]; __syncthreads(); }
@@ -105,8 +105,8 @@ template <int W> __global__ void __launch_bounds__(W * 32, BPS) dcu_window_kerne
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= a.n) { nomore = true; break; }
       wi = a.todo ? a.todo[t] : t;
-      dcu::Window W = a.win[wi];
-      dcu::st_begin(c, st, W, lane, nullptr);
+      const dcu::Window wd = a.win[wi];
+      dcu::st_begin(c, st, wd, lane, nullptr);
       if (st.ph == dcu::PH_END) publish();             // skipped or overflowed right away
     }
     const bool idle = st.ph == dcu::PH_END;
@@ -426,12 +426,14 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err; ctx->P.defer_ff = 0;
   { const char* e = getenv("DCU_POSCACHE"); ctx->P.poscache = e ? atoi(e) : 1; }
   CK(ctx->dcnt.ensure(16));
-  { const char* e2 = getenv("DCU_NO_SMEM"); ctx->use_smem = (e2 && atoi(e2)) ? 0 : 1; }
+  // First pass: the HBM build by default.  The shared-memory build (graph in shared memory, slices staged by bulk copies) is complete and
+  // parity-tested but measured slower on B200 (12-16 resident warps per SM against 32: profiles/r02_summary.md); DCU_SMEM=1 selects it.
+  { const char* e2 = getenv("DCU_SMEM"); ctx->use_smem = (e2 && atoi(e2)) ? 1 : 0; if (getenv("DCU_NO_SMEM") && atoi(getenv("DCU_NO_SMEM"))) ctx->use_smem = 0; }
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   const char* e = getenv("DCU_BLOCKS_PER_SM");
   if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);
   e = getenv("DCU_SYNC_GROUP");
-  if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16)) ctx->sync_group_env = atoi(e);
+  if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)) ctx->sync_group_env = atoi(e);
   return DCU_OK;
 }
 
@@ -489,7 +491,8 @@ static int finish_batch(dcu_ctx* ctx, int maxS, int maxB, uint64_t totS, uint64_
   // phase-synchronous group size: deep, homogeneous piles gain from large groups (instruction-cache locality); shallow
   // piles have a heavy tail of windows that need the filterfreq-1 pass, where waiting on the slowest warp costs more
   // than the locality brings (measured: profiles/r01_summary.md).  Results do not depend on it.
-  { double mean = nwin ? (double)totS / (double)nwin : 0.0; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : (mean >= 30.0 ? 16 : (mean >= 16.0 ? 8 : 1)); }
+  // (round 2: with the leaner stages the whole block in lock step wins at every depth -- 10x: +25 % over free running, 20x: +25 % over groups of 8)
+  (void)totS; ctx->sync_group = ctx->sync_group_env ? ctx->sync_group_env : WPB;
   for (int t = 0; t < 2; ++t) { ctx->caps[t] = dcu_host::make_caps(t, (int)ctx->prm.w, maxS, maxB); dcu::make_layout(ctx->caps[t], ctx->lay[t]); }
   { const char* e = getenv("DCU_HEAVY_NN"); if (e) ctx->caps[0].HEAVY = atoi(e); if (ctx->sync_group == 1) ctx->caps[0].HEAVY = 0; }   // free-running batches keep heavy windows in place
   CK(ctx->dwin.ensure(nwin + 1)); CK(ctx->dsl.ensure(nsl + 1)); CK(ctx->dres.ensure(nwin + 1));
@@ -633,14 +636,14 @@ static void fill_args(dcu_ctx* ctx, KArgs& a, int cnt_at, int list, const uint32
   a.todo = todo; a.n = n;
   a.ticket = ctx->dcnt.p + cnt_at; a.ovf_cnt = ctx->dcnt.p + cnt_at + 1; a.ovf_list = ctx->dovf[list].p;
   a.packed_bytes = ctx->packed_padded; a.stage = 0; a.launch_seq = ++ctx->launch_seq;
-  { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 15; }
+  { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 47; }
 }
 // HBM passes: tier 0 (first overflow pass, or the first pass when the shared-memory pass is off), tier 1 (large workspaces, free running)
 static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n) {
   int bps = ctx->blocks_per_sm[tier];
   int grid = ctx->num_sms * bps;
   int wpb = WPB;
-  { const char* e = getenv("DCU_WPB"); if (e && atoi(e) == 12 && tier == 0) wpb = 12; }
+  { const char* e = getenv("DCU_WPB"); if (e && tier == 0 && (atoi(e) == 12 || atoi(e) == 32)) { wpb = atoi(e); if (wpb == 32) { bps = 1; grid = ctx->num_sms; } } }
   size_t need_blocks = ((size_t)n + wpb - 1) / wpb;
   if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
   CK(ctx->dslab[tier].ensure((size_t)grid * wpb * ctx->lay[tier].bytes, true));
@@ -661,14 +664,17 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
   a.vs_words = (uint32_t)(vs_bytes / 8);
   a.sync_group = tier ? 1 : ctx->sync_group;       // the large-workspace pass only sees heavy-tailed windows: free running
   while (a.sync_group > 1 && wpb % a.sync_group) --a.sync_group;                       // groups must tile the block
+  int pct_used = 0;
   {   // leave as much of the 228 KB as possible to L1: the kernel lives on cached scratch data (measured +5 %, profiles/r01_summary.md)
     int pct = (int)((bps * (vs_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
     const char* e = getenv("DCU_CARVEOUT");
     if (e) pct = atoi(e);
     CK(cudaFuncSetAttribute(dcu_window_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
     CK(cudaFuncSetAttribute(dcu_window_kernel<12>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+    pct_used = pct > 100 ? 100 : pct;
   }
-  if (wpb == 12) dcu_window_kernel<12><<<grid, 12 * 32, vs_bytes, ctx->stream>>>(a);
+  if (wpb == 32) { CK(cudaFuncSetAttribute(dcu_window_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct_used)); dcu_window_kernel<32, 1><<<grid, 32 * 32, vs_bytes, ctx->stream>>>(a); }
+  else if (wpb == 12) dcu_window_kernel<12><<<grid, 12 * 32, vs_bytes, ctx->stream>>>(a);
   else dcu_window_kernel<16><<<grid, WPB * 32, vs_bytes, ctx->stream>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -692,7 +698,7 @@ static int launch_smem(dcu_ctx* ctx, uint32_t n) {
   if (vs_bytes > 40 * 1024) vs_bytes = 0;
   a.vs_words = (uint32_t)(vs_bytes / 8);
   vs_bytes = (vs_bytes + 127) & ~(size_t)127;
-  { int g = ctx->sync_group_env ? ctx->sync_group_env : wps; while (g > 1 && wps % g) --g; a.sync_group = g; }      // groups must tile the block
+  { int g = ctx->sync_group_env ? ctx->sync_group_env : 4; while (g > 1 && wps % g) --g; a.sync_group = g; }      // groups must tile the block (measured: 4 > 6 > 12 > 2 > 1)
   { const char* e = getenv("DCU_STAGE"); a.stage = e ? atoi(e) : 1; }
   const size_t dyn = vs_bytes + (size_t)wps * ctx->layS.sbytes;
   CK(cudaFuncSetAttribute(dcus_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

@@ -162,3 +162,21 @@ def test_pile_shaped_batch_of_1e5_windows_matches_oracle_and_truth():
     # raw reads: 15 % error events per base; corrected: a few 1e-4 (measured 3.9e-4 on this generator at 40x)
     assert acc["reads"] == ds.nreads and acc["corrected_bases"] > 0.95 * 1e6 and acc["raw_erate"] > 0.14
     assert acc["erate"] < 1e-3, acc
+
+
+def test_shared_memory_build_matches_oracle(monkeypatch):
+    """DCU_SMEM=1: the first pass runs the shared-memory build of the kernel (graph fields in the warp's shared-memory arena, slices of the next
+    window staged by bulk copies, two-bitmap pre-filter); windows beyond its small capacities go on to the HBM passes.  Same results as the oracle,
+    on clean deep piles (nearly everything stays in the first pass) and on repeat-rich ones (many hand-overs); without staging too."""
+    for seed, depth, rf, stage in ((201, 40, 0.0, "1"), (202, 30, 0.5, "1"), (203, 12, 0.3, "0")):
+        p = default_params()
+        packed, win, sl, _ = synth_batch(1200, depth, seed=seed, repeat_frac=rf, depth_jitter=3)
+        ro = run_oracle(p, packed, win, sl, 8)
+        monkeypatch.setenv("DCU_SMEM", "1"); monkeypatch.setenv("DCU_STAGE", stage)
+        e = _engine(p)
+        e.set_reads(packed)
+        rg = e.run(win, sl)
+        st = e.stats()
+        e.close()
+        assert st["smem_warps"] >= 2 and st["lost_windows"] == 0
+        assert not compare_results(ro, rg), (seed, st)
