@@ -636,7 +636,7 @@ static void fill_args(dcu_ctx* ctx, KArgs& a, int cnt_at, int list, const uint32
   a.todo = todo; a.n = n;
   a.ticket = ctx->dcnt.p + cnt_at; a.ovf_cnt = ctx->dcnt.p + cnt_at + 1; a.ovf_list = ctx->dovf[list].p;
   a.packed_bytes = ctx->packed_padded; a.stage = 0; a.launch_seq = ++ctx->launch_seq;
-  { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 47; }
+  { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 255; }
 }
 // HBM passes: tier 0 (first overflow pass, or the first pass when the shared-memory pass is off), tier 1 (large workspaces, free running)
 static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n) {

@@ -490,39 +490,6 @@ template <class F, class G> DCU_FN void for_each_kmer(const Ctx& c, int lane, F 
     if (i1 == numk) g(j, v);
   }
 }
-// The same with the table probes of four consecutive k-mers in flight at a time: pre(v) issues the load of a k-mer's home slot and
-// returns what it held, f(j, i, len, v, key) gets it.  A key may be stale by the time f runs (an earlier k-mer of the same group may
-// have claimed the slot): f must treat an empty key as "try to claim", which the compare-and-swap then decides.
-template <class P, class F, class G> DCU_FN void for_each_kmer4(const Ctx& c, int lane, P pre, F f, G g) {
-  const int K = c.k;
-  const int parts = c.MAo > 48 ? 1 : (c.MAo > 20 ? 2 : 4);
-  const int ntask = c.MAo * parts;
-  DCU_NOUNROLL
-  for (int t = lane; t < ntask; t += DCU_NL) {
-    const int j = t / parts, part = t - j * parts;
-    const int len = seqlen(c, j), numk = len - K + 1;
-    if (numk <= 0) continue;
-    const int per = (numk + parts - 1) / parts;
-    const int i0 = part * per, i1 = i0 + per < numk ? i0 + per : numk;
-    if (i0 >= i1) continue;
-    const uint32_t* u = slice_words(c, j);
-    uint32_t v = 0, wd = u[i0 >> 4] >> (2 * (i0 & 15));
-    int b = i0;                                        // next base to take
-    DCU_NOUNROLL
-    for (; b < i0 + K - 1; ++b) { v = (v << 2) | (wd & 3u); wd >>= 2; if (((b + 1) & 15) == 0) wd = u[(b + 1) >> 4]; }
-    auto roll = [&]() { v = ((v << 2) & c.kmask) | (wd & 3u); wd >>= 2; ++b; if ((b & 15) == 0 && b < len) wd = u[b >> 4]; return v; };
-    int i = i0;
-    DCU_NOUNROLL
-    for (; i + 4 <= i1; i += 4) {
-      const uint32_t v0 = roll(), v1 = roll(), v2 = roll(), v3 = roll();
-      const uint32_t k0 = pre(v0), k1 = pre(v1), k2 = pre(v2), k3 = pre(v3);
-      f(j, i, len, v0, k0); f(j, i + 1, len, v1, k1); f(j, i + 2, len, v2, k2); f(j, i + 3, len, v3, k3);
-    }
-    DCU_NOUNROLL
-    for (; i < i1; ++i) { const uint32_t vv = roll(); f(j, i, len, vv, pre(vv)); }
-    if (i1 == numk) g(j, v);
-  }
-}
 DCU_BIG void kmer_offsets(Ctx& c, int lane) {          // number of k-mer instances of the window
   uint32_t nk = 0;
   DCU_NOUNROLL
@@ -563,11 +530,12 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
   bool full = false;
   const bool live = c.hcap != 0x7fffffff;              // the table may fill up: the claimed-slot counter has to be current
   uint32_t claimed = 0;
-  for_each_kmer4(c, lane, [&](uint32_t v) { return a_load(&w.hkey()[hslot(c, v)]); }, [&](int, int, int, uint32_t v, uint32_t key) {
+  // (four probes in flight per lane were tried here -- call 5/6 of round 2: 15 % slower, the 64-register build spills in the loop)
+  for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
     if (full) return;
     if (pre) { const uint32_t b = prebit(v); if (!((w.hbB()[b >> 5] >> (b & 31)) & 1u)) return; }      // (bitmaps are final: wsync above)
     if (live && a_load(&w.hstate()[0]) > (uint32_t)c.hcap) { full = true; return; }      // racy read of a monotone counter: the overshoot is bounded by the lanes' in-flight inserts
-    hash_insert_fast(c, v, key, claimed, live);
+    hash_insert_fast(c, v, a_load(&w.hkey()[hslot(c, v)]), claimed, live);
   }, [&](int j, uint32_t v) { w.lastk()[j] = v; });                                // final k-mer of the sequence (the `last` array, :2108)
   wsync();
   claimed = red_sum_u32(claimed);
@@ -650,8 +618,8 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   DCU_PEAK(3, c.ni);
   if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
   // instances are filed under their nodes: the k-mers are rolled once more and looked up (no per-instance slot array)
-  for_each_kmer4(c, lane, [&](uint32_t v) { return w.hkey()[hslot(c, v)]; }, [&](int, int i, int len, uint32_t v, uint32_t key) {
-    const int n = lookup_fast(c, v, key);
+  for_each_kmer(c, lane, [&](int, int i, int len, uint32_t v) {
+    const int n = lookup_fast(c, v, w.hkey()[hslot(c, v)]);
     if (n != NID_NONE) { const uint32_t t = add16(w.fillcnt(), (uint32_t)n, 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = (uint8_t)i; w.irpos()[t] = (uint8_t)(len - i - c.k); }
   }, [](int, uint32_t) {});
   DCU_NOUNROLL

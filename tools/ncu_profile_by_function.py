@@ -7,7 +7,8 @@ nwin = float(sys.argv[3]) if len(sys.argv) > 3 else 0
 rows = list(csv.reader(open(src)))
 kern = "dcus_window_kernel" if "dcus_window_kernel" in rows[0][1] else "dcu_window_kernel"
 ns = "dcus" if "dcus" in kern else "dcu"
-elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
+# lib: the library that was profiled, or a text file with its `cuobjdump -elf | grep '$_ZN'` lines saved next to the capture (the symbol ranges must be those of the profiled code)
+elf = open(lib).read() if lib.endswith(".txt") else subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
 funcs = []
 for line in elf.splitlines():
     m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+0\s+0x[0-9a-f]+\s+\$.*\d+%s(?:I\w+?E)?E.*\$_ZN\d+%s\d+([A-Za-z_0-9]+?)E" % (kern, ns), line)
