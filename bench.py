@@ -315,17 +315,24 @@ def main():
         pile_wall = time.perf_counter() - t0
         pile_same = not full_compare((res_ref, cons_ref, ops_ref), out).any()
     # ---- e2e: the whole read-level path on the GPU: overlaps in, corrected bases out (dcu_pile + launch + dcu_vote); D2H = corrected bases only
-    full_wall, full_same, full_d2h, truth = None, None, 0, None
+    full_wall, full_same, full_d2h, truth, e2e_parts = None, None, 0, None, None
     if gpu_pile:
         eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng.launch(); seg, chars = eng.vote()      # warm-up
         barrier()
         t0 = time.perf_counter()
+        tp = tl = tv = 0.0
         for _ in range(args.steps):
+            ta = time.perf_counter()
             eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign)
+            tb = time.perf_counter()
             eng.launch()
+            tc = time.perf_counter()
             seg, chars = eng.vote()
+            td = time.perf_counter()
+            tp += tb - ta; tl += tc - tb; tv += td - tc
         barrier()
         full_wall = time.perf_counter() - t0
+        e2e_parts = {"dcu_pile_ms": 1e3 * tp / args.steps, "dcu_launch_ms": 1e3 * tl / args.steps, "dcu_vote_and_get_corrected_ms": 1e3 * tv / args.steps}
         gfasta = format_segments(seg, chars)[0]
         full_same = bool(gfasta == fasta)
         full_d2h = int(chars.nbytes + seg.nbytes + 16 * nwin)       # + the window descriptors dcu_vote reads back to lay out the reads
@@ -374,7 +381,7 @@ def main():
                         "parallelism": "-J r,%d by A-read, no data-path collective" % world, "setup": info},
                 e2e=(None if not full_wall else {"value": att_t * args.steps / e2e_wall, "unit": "windows/s", "h2d_bytes_per_step": int(h2d_ovl), "d2h_bytes_per_step": int(d2h_full),
                                                  "what": "dcu_pile + dcu_launch + dcu_vote + dcu_get_corrected: overlaps and trace points in (pinned host memory), corrected bases out",
-                                                 "corrected_mbp_per_s": corr_t * args.steps / e2e_wall / 1e6, "fasta_identical_to_host_vote": bool(flags[2].item())}),
+                                                 "corrected_mbp_per_s": corr_t * args.steps / e2e_wall / 1e6, "fasta_identical_to_host_vote": bool(flags[2].item()), "rank0_ms_per_step": e2e_parts}),
                 e2e_descriptors={"value": att_t * args.steps / desc_wall_max, "unit": "windows/s", "what": "dcu_run: window / slice descriptors in, result records + consensus + placement out",
                                  "h2d_bytes_per_step": int(h2d_desc), "d2h_bytes_per_step": int(d2h_desc), "results_identical": bool(flags[0].item())},
                 e2e_from_overlaps=(None if not pile_wall else {"value": att_t * args.steps / pile_wall_max, "unit": "windows/s", "what": "dcu_pile (trace reconstruction + slices on the GPU) + launch + download of the result records",

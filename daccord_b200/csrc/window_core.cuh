@@ -141,10 +141,16 @@ struct WS {
 #define X(name, type, n, S) DCU_MEM type* name() const { return (type*)(((S) ? sm : base) + DCU_LAYOUT.off[F_##name]); }
 #else
   uint32_t sm;                             // byte offset of the warp's arena in dcu_smem
-#define X(name, type, n, S) DCU_MEM type* name() const { return (S) ? (type*)(dcu_smem + sm + DCU_LAYOUT.off[F_##name]) : (type*)(base + DCU_LAYOUT.off[F_##name]); }
+#define X(name, type, n, S) DCU_MEM type* name() const { if (S) return (type*)(dcu_smem + sm + DCU_LAYOUT.off[F_##name]); type* p_ = (type*)(base + DCU_LAYOUT.off[F_##name]); __builtin_assume(__isGlobal(p_)); return p_; }
 #endif
 #else
+#ifdef DCU_EMU
 #define X(name, type, n, S) DCU_MEM type* name() const { return (type*)(base + DCU_LAYOUT.off[F_##name]); }
+#else
+// the slab is global memory: telling the compiler so turns generic LD / ST into LDG / STG and, more important, lets it keep values that
+// live in local memory (the Ctx, spills) in registers across workspace stores, which it otherwise has to assume might alias them
+#define X(name, type, n, S) DCU_MEM type* name() const { type* p_ = (type*)(base + DCU_LAYOUT.off[F_##name]); __builtin_assume(__isGlobal(p_)); return p_; }
+#endif
 #endif
   DCU_WS_FIELDS(X)
 #undef X
