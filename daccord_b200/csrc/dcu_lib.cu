@@ -14,7 +14,10 @@
 #include "window_core.cuh"            // namespace dcu : every workspace field in the warp's HBM slab (overflow passes, deep piles)
 #define DCU_NS dcus
 #define DCU_TIER_SMEM 1
-#include "window_core.cuh"            // namespace dcus: hot fields in the warp's shared-memory arena (first pass)
+#include "window_core.cuh"            // namespace dcus: hot fields in the warp's shared-memory arena (optional first pass)
+#define DCU_NS dcuh
+#define DCU_TIER_SMEM 2
+#include "window_core.cuh"            // namespace dcuh: only the k-mer table in shared memory, at full occupancy (first pass of deep, clean piles)
 #include "host_tables.hpp"
 #include "host_caps.hpp"
 #include "pile_host.hpp"
@@ -112,6 +115,45 @@ template <int W, int B = BPS> __global__ void __launch_bounds__(W * 32, B) dcu_w
     const bool idle = st.ph == dcu::PH_END;
     bool alldone;
     DCU_STAGE_LOOP(dcu, (void)0)
+  }
+}
+
+// ---- hybrid build: as dcu_window_kernel, plus a 5 KB arena per warp behind the VS table that holds the window's k-mer table
+__global__ void __launch_bounds__(WPB * 32, BPS) dcuh_window_kernel(const __grid_constant__ KArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t vs_bytes = (a.vs_words * 8u + 127u) & ~127u;
+  if (a.vs_words) { unsigned long long* s_vs = (unsigned long long*)dcuh::dcu_smem; for (uint32_t i = threadIdx.x; i < a.vs_words; i += blockDim.x) s_vs[i] = dcuh::c_T.VSq[i]; __syncthreads(); }
+  dcuh::Ctx c;
+  c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcuh::c_layout.bytes;
+  c.ws.sm = vs_bytes + (uint32_t)warp * dcuh::c_layout.sbytes;
+  c.vsq = a.vs_words ? (const unsigned long long*)dcuh::dcu_smem : dcuh::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0; c.epoch = (unsigned long long)a.launch_seq << 32;
+  c.packed = a.packed; c.sl = a.sl;
+  __shared__ int s_done[2][WPB];
+  const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
+  auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
+  const int smask = a.sync_mask;
+  dcuh::WinState st; st.ph = dcuh::PH_END;
+  uint32_t wi = 0; bool nomore = false; int par = 0;
+  auto publish = [&]() {
+    if (lane == 0) {
+      a.res[wi] = st.res;
+      if (st.res.status == dcuh::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
+    }
+  };
+  for (;; par ^= 1) {
+    while (!nomore && st.ph == dcuh::PH_END) {         // finish / fetch
+      unsigned int t = 0;
+      if (lane == 0) t = atomicAdd(a.ticket, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= a.n) { nomore = true; break; }
+      wi = a.todo ? a.todo[t] : t;
+      const dcu::Window wd = a.win[wi];
+      dcuh::st_begin(c, st, wd, lane, nullptr);
+      if (st.ph == dcuh::PH_END) publish();
+    }
+    const bool idle = st.ph == dcuh::PH_END;
+    bool alldone;
+    DCU_STAGE_LOOP(dcuh, (void)0)
   }
 }
 
@@ -366,6 +408,7 @@ struct dcu_ctx {
   DevBuf<uint8_t> dslab[3];
   dcu::Caps caps[2]; dcu::Layout lay[2]; int grid[2] = {0, 0};
   dcu::Caps capsS{}; dcus::Layout layS{}; int warpsS = 0;   // shared-memory pass: capacities, layout, warps per block
+  dcu::Caps capsH{}; dcuh::Layout layH{}; int use_hybrid = 1, hybrid_ok = 0; DevBuf<uint8_t> dslabH; DevBuf<uint32_t> dovfH;   // hybrid pass (k-mer table in shared memory)
   uint64_t nwin = 0, nsl = 0; int maxS = 0, maxB = 0;
   // piling scratch
   DevBuf<dpile::Ovl> dpo; DevBuf<dpile::ReadInfo> dpr; DevBuf<uint32_t> dprid, dptile, dpbm, dprlen; DevBuf<uint64_t> dpboff; DevBuf<uint16_t> dptrace;
@@ -430,6 +473,7 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   // parity-tested but measured slower on B200 (12-16 resident warps per SM against 32: profiles/r02_summary.md); DCU_SMEM=1 selects it.
   { const char* e2 = getenv("DCU_SMEM"); ctx->use_smem = (e2 && atoi(e2)) ? 1 : 0; if (getenv("DCU_NO_SMEM") && atoi(getenv("DCU_NO_SMEM"))) ctx->use_smem = 0; }
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  { const char* e3 = getenv("DCU_HYBRID"); ctx->use_hybrid = e3 ? atoi(e3) : 1; }
   const char* e = getenv("DCU_BLOCKS_PER_SM");
   if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);
   e = getenv("DCU_SYNC_GROUP");
@@ -446,7 +490,7 @@ void dcu_destroy(dcu_ctx* ctx) {
   ctx->dpo.release(); ctx->dpr.release(); ctx->dprid.release(); ctx->dptile.release(); ctx->dpbm.release(); ctx->dprlen.release();
   ctx->dpboff.release(); ctx->dptrace.release(); ctx->dpmin.release(); ctx->dpdiv.release(); ctx->dpact.release(); ctx->dpcnt.release(); ctx->dpblkw.release(); ctx->dpblks.release();
   ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dovf[2].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release(); ctx->dslab[2].release();
-  ctx->dvent.release(); ctx->dvflag.release(); ctx->dvblk.release(); ctx->dvchars.release(); ctx->dvreads.release(); ctx->dvbound.release();
+  ctx->dslabH.release(); ctx->dovfH.release(); ctx->dvent.release(); ctx->dvflag.release(); ctx->dvblk.release(); ctx->dvchars.release(); ctx->dvreads.release(); ctx->dvbound.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -508,6 +552,17 @@ static int finish_batch(dcu_ctx* ctx, int maxS, int maxB, uint64_t totS, uint64_
     if (wps > SWPB) wps = SWPB;
     { const char* e = getenv("DCU_S_WARPS"); if (e && atoi(e) > 0 && atoi(e) < wps) wps = atoi(e); }
     ctx->warpsS = wps;
+  }
+  {   // hybrid pass: worth it where the filter frequency 2 graph usually succeeds (deep, clean piles) and the 15-bit counts cannot overflow
+    const double mean = nwin ? (double)totS / (double)nwin : 0.0;
+    ctx->capsH = dcu_host::make_caps_hybrid((int)ctx->prm.w, maxS, maxB); dcuh::make_layout(ctx->capsH, ctx->layH);
+    size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
+    if (vs_bytes > 40 * 1024) vs_bytes = 0;
+    vs_bytes = (vs_bytes + 127) & ~(size_t)127;
+    const size_t per_block = vs_bytes + (size_t)WPB * ctx->layH.sbytes + 1536;
+    const double mind = getenv("DCU_HYBRID_MIN_DEPTH") ? atof(getenv("DCU_HYBRID_MIN_DEPTH")) : 25.0;
+    ctx->hybrid_ok = ctx->use_hybrid && !ctx->use_smem && ctx->prm.max_ff >= 2 && mean >= mind && maxB < 32768 && BPS * per_block <= (size_t)ctx->smem_optin + 1024 && per_block <= (size_t)ctx->smem_optin;
+    CK(ctx->dovfH.ensure(nwin + 1));
   }
   ctx->nwin = nwin; ctx->nsl = nsl; ctx->results_valid = false;
   return DCU_OK;
@@ -708,6 +763,35 @@ static int launch_smem(dcu_ctx* ctx, uint32_t n) {
   return DCU_OK;
 }
 
+// hybrid pass: grid and block shape of the HBM first pass, dynamic shared memory = VS table + 16 k-mer table arenas
+static int launch_hybrid(dcu_ctx* ctx, uint32_t n) {
+  int grid = ctx->num_sms * BPS;
+  size_t need_blocks = ((size_t)n + WPB - 1) / WPB;
+  if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
+  CK(ctx->dslabH.ensure((size_t)grid * WPB * ctx->layH.bytes, true));
+  CK(cudaMemcpyToSymbolAsync(dcuh::c_layout, &ctx->layH, sizeof(dcuh::Layout), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(dcuh::c_cap, &ctx->capsH, sizeof(dcu::Caps), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyToSymbolAsync(dcuh::c_T, &ctx->T, sizeof(dcu::Tables), 0, cudaMemcpyHostToDevice, ctx->stream));
+  { dcu::Params P = ctx->P; P.defer_ff = 0; ctx->Pl[0] = P; CK(cudaMemcpyToSymbolAsync(dcuh::c_P, &ctx->Pl[0], sizeof(dcu::Params), 0, cudaMemcpyHostToDevice, ctx->stream)); }
+  KArgs a;
+  fill_args(ctx, a, 12, 0, nullptr, n);
+  a.ovf_list = ctx->dovfH.p;
+  a.slabs = ctx->dslabH.p;
+  size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
+  if (vs_bytes > 40 * 1024) vs_bytes = 0;
+  a.vs_words = (uint32_t)(vs_bytes / 8);
+  vs_bytes = (vs_bytes + 127) & ~(size_t)127;
+  a.sync_group = ctx->sync_group;
+  while (a.sync_group > 1 && WPB % a.sync_group) --a.sync_group;
+  const size_t dyn = vs_bytes + (size_t)WPB * ctx->layH.sbytes;
+  CK(cudaFuncSetAttribute(dcuh_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  CK(cudaFuncSetAttribute(dcuh_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  dcuh_window_kernel<<<grid, WPB * 32, dyn, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return DCU_OK;
+}
+
 int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
   if (!ctx) return DCU_ERR_PARAM;
   CK(cudaSetDevice(ctx->device));
@@ -716,7 +800,7 @@ int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
   if (!ctx->nwin) return DCU_OK;
   std::lock_guard<std::mutex> pass_lock(g_window_pass_lock[ctx->device & 63]);
   CK(cudaMemsetAsync(ctx->dcnt.p, 0, 4 * sizeof(unsigned int), ctx->stream));
-  CK(cudaMemsetAsync(ctx->dcnt.p + 8, 0, 4 * sizeof(unsigned int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->dcnt.p + 8, 0, 8 * sizeof(unsigned int), ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   unsigned int cnt[2];
   const uint32_t* todo = nullptr; uint32_t n = (uint32_t)ctx->nwin;
@@ -726,6 +810,12 @@ int dcu_launch(dcu_ctx* ctx, float* kernel_ms) {
     CK(cudaMemcpyAsync(cnt, ctx->dcnt.p + 8, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->second = cnt[1]; todo = ctx->dovf[2].p; n = cnt[1];
+  } else if (ctx->hybrid_ok) {                       // pass 1: k-mer table in shared memory, 32 warps per SM
+    int rc = launch_hybrid(ctx, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(cnt, ctx->dcnt.p + 12, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->second = cnt[1]; todo = ctx->dovfH.p; n = cnt[1];
   }
   if (n) {                                           // HBM workspaces, first-pass capacities
     int rc = launch_tier(ctx, 0, todo, n);
@@ -850,8 +940,9 @@ int dcu_last_stats2(dcu_ctx* ctx, uint64_t* second_pass_windows, uint64_t* lost_
   if (!ctx) return DCU_ERR_PARAM;
   if (second_pass_windows) *second_pass_windows = ctx->second;
   if (lost_windows) *lost_windows = ctx->lost;
-  if (smem_warps) *smem_warps = (ctx->use_smem && ctx->warpsS >= 2) ? (uint32_t)ctx->warpsS : 0u;
-  if (smem_bytes_per_warp) *smem_bytes_per_warp = ctx->layS.sbytes;
+  const bool smem = ctx->use_smem && ctx->warpsS >= 2;
+  if (smem_warps) *smem_warps = smem ? (uint32_t)ctx->warpsS : (ctx->hybrid_ok ? (uint32_t)(WPB * BPS) : 0u);
+  if (smem_bytes_per_warp) *smem_bytes_per_warp = smem ? ctx->layS.sbytes : (ctx->hybrid_ok ? ctx->layH.sbytes : 0u);
   return DCU_OK;
 }
 

@@ -62,4 +62,17 @@ inline dcu::Caps make_caps_smem(int w, int maxS, int maxB) {
   c.RLP = 1 << ceil_pow2_log(c.RL);
   return c;
 }
+// capacities of the hybrid build (dcuh): tier-0 capacities in the HBM slab, but the k-mer table in shared memory -- 512 slots behind the
+// two-bitmap pre-filter (it then holds the k-mers seen twice: ~250 of a 40x window), 5 KB per warp, so that all 32 warps of an SM keep
+// theirs.  A window whose table fills up, or that needs the filter frequency 1 graph, is handed to the plain HBM pass.
+inline dcu::Caps make_caps_hybrid(int w, int maxS, int maxB) {
+  dcu::Caps c = make_caps(0, w, maxS, maxB);
+  c.EX = 64;
+  c.LOGH = env_or("DCU_H_LOGH", 9); c.H = 1 << c.LOGH;
+  c.LOGNB = env_or("DCU_H_LOGNB", 13); c.NBITS = 1 << c.LOGNB;
+  if (c.NN > c.NI + c.EX) c.NN = c.NI + c.EX;
+  if (c.NN > 32000) c.NN = 32000;                  // node ids share 16-bit slot values with the counts
+  if (c.SL < c.NN) c.SL = c.NN;
+  return c;
+}
 }  // namespace dcu_host

@@ -27,6 +27,8 @@
 // This file has no include guard: it is compiled once per build of the kernel, inside the namespace DCU_NS.
 //   DCU_NS = dcu,  DCU_TIER_SMEM = 0 : every workspace field lives in the warp's slab in HBM (large / deep windows, overflow passes);
 //   DCU_NS = dcus, DCU_TIER_SMEM = 1 : the fields marked S below live in the warp's shared-memory arena, the rest in a (small) slab.
+//   DCU_NS = dcuh, DCU_TIER_SMEM = 2 : only the k-mer table (S = 1: keys, 16-bit values, pre-filter bitmaps, counters) lives in shared memory -- 5 KB
+//                                      per warp, which all 32 resident warps of an SM can have -- everything else in the HBM slab with tier-0 capacities.
 #include "window_types.cuh"
 #ifndef DCU_NS
 #define DCU_NS dcu
@@ -42,7 +44,11 @@ using dcub::ballot;                      // (hides the toolkit's global ::ballot
 // value of a hash slot and offsets into the instance lists: 16 bit in the shared-memory build (its capacities are small)
 #if DCU_TIER_SMEM
 typedef uint16_t hval_t;                 // bit 15 set: node id in the low 15 bits (the count is then n_freq[id]); else the k-mer's count
+#if DCU_TIER_SMEM == 1
 typedef uint16_t ioff_t;
+#else
+typedef uint32_t ioff_t;                 // hybrid build: instance lists with tier-0 capacities
+#endif
 #else
 typedef uint32_t hval_t;                 // count | node id << 16 (0xFFFF: not a node)
 typedef uint32_t ioff_t;
@@ -58,20 +64,22 @@ struct RSlot { double w, wf; };
 struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
 
 // X(name, type, elements, S)    S = 1: hot and small (tools/field_traffic.py: 4 % of the bytes, 2/3 of the accesses)
+// S = 1 (the k-mer table): in the arena of the shared-memory build and of the hybrid build; S = 2: in the arena of the shared-memory build only
+#define DCU_IN_SMEM(S) ((S) == 1 || ((S) == 2 && DCU_TIER_SMEM == 1))
 #define DCU_WS_FIELDS(X)                                                                                              \
-  X(bw, uint32_t, c.BW, 1) X(sw, uint16_t, c.S + 1, 1) X(soff, uint16_t, c.S + 1, 1) X(lenhist, uint16_t, 256, 0)      \
+  X(bw, uint32_t, c.BW, 2) X(sw, uint16_t, c.S + 1, 2) X(soff, uint16_t, c.S + 1, 2) X(lenhist, uint16_t, 256, 0)      \
   X(hkey, uint32_t, c.H, 1) X(hval, hval_t, c.H, 1) X(hbA, uint32_t, c.NBITS / 32 + 4, 1) X(hbB, uint32_t, c.NBITS / 32 + 4, 1) \
   X(hstate, uint32_t, 4, 1)                                                                                           \
-  X(koff, uint16_t, c.S + 1, 1) X(lastk, uint32_t, c.S, 1)                              \
+  X(koff, uint16_t, c.S + 1, 2) X(lastk, uint32_t, c.S, 2)                              \
   X(ts_k, uint32_t, c.S, 0) X(ts_c, uint16_t, c.S, 0) X(ts_n, uint16_t, c.S, 0)                                        \
-  X(n_kmer, uint32_t, c.NN, 0) X(n_freq, uint16_t, c.NN, 1) X(n_ioff, ioff_t, c.NN, 1)                                 \
+  X(n_kmer, uint32_t, c.NN, 0) X(n_freq, uint16_t, c.NN, 2) X(n_ioff, ioff_t, c.NN, 2)                                 \
   X(n_nsucc, uint8_t, c.NN, 0) X(n_nact, uint8_t, c.NN, 0) X(n_npred, uint8_t, c.NN, 0)                                \
   X(n_sfreq, uint16_t, 4 * c.NN, 0) X(n_snid, uint16_t, 4 * c.NN, 0)                                                  \
-  X(ipos, uint8_t, c.NI + c.EX, 1) X(irpos, uint8_t, c.NI + c.EX, 1)                                                  \
+  X(ipos, uint8_t, c.NI + c.EX, 2) X(irpos, uint8_t, c.NI + c.EX, 2)                                                  \
   X(ex_kmer, uint32_t, c.EX, 0) X(ex_pos, uint8_t, c.EX, 0) X(ex_rpos, uint8_t, c.EX, 0)                               \
   X(ll_kmer, uint32_t, c.S, 0) X(ll_cnt, uint16_t, c.S, 0) X(fl_kmer, uint32_t, c.S, 0) X(fl_cnt, uint16_t, c.S, 0)    \
   X(fl_nid, uint16_t, c.S, 0)                                                                                         \
-  X(slinks, uint16_t, c.SL, 1) X(slsym, uint8_t, c.SL, 1) X(rs_off, uint16_t, c.ST, 0) X(rs_len, uint16_t, c.ST, 0)    \
+  X(slinks, uint16_t, c.SL, 2) X(slsym, uint8_t, c.SL, 2) X(rs_off, uint16_t, c.ST, 0) X(rs_len, uint16_t, c.ST, 0)    \
   X(rs_fO, uint32_t, c.ST, 0) X(rs_cO, uint32_t, c.ST, 0) X(spc, uint32_t, 4, 0)                                       \
   X(ds_off, uint16_t, c.ST, 0) X(ds_len, uint16_t, c.ST, 0) X(ds_fO, uint32_t, c.ST, 0) X(ds_cO, uint32_t, c.ST, 0)    \
   X(dt_off, uint16_t, c.ST, 0) X(dt_len, uint16_t, c.ST, 0) X(du_off, uint16_t, c.ST, 0) X(du_len, uint16_t, c.ST, 0)  \
@@ -99,7 +107,7 @@ struct Layout { uint32_t off[128]; uint32_t bytes; uint32_t sbytes; };
 static inline void make_layout(const Caps& c, Layout& L) {
   uint32_t o = 0, so = 0; int i = 0;
 #if DCU_TIER_SMEM
-#define X(name, type, n, S) { uint32_t& q = (S) ? so : o; const uint32_t al = (S) ? 15u : 31u; q = (q + al) & ~al; L.off[i++] = q; q += (uint32_t)(sizeof(type) * (size_t)(n)); }
+#define X(name, type, n, S) { uint32_t& q = DCU_IN_SMEM(S) ? so : o; const uint32_t al = DCU_IN_SMEM(S) ? 15u : 31u; q = (q + al) & ~al; L.off[i++] = q; q += (uint32_t)(sizeof(type) * (size_t)(n)); }
 #else
 #define X(name, type, n, S) { o = (o + 31u) & ~31u; L.off[i++] = o; o += (uint32_t)(sizeof(type) * (size_t)(n)); }      // 32 bytes: a slot record never straddles a sector
 #endif
@@ -138,10 +146,10 @@ struct WS {
 #if DCU_TIER_SMEM
 #ifdef DCU_EMU
   uint8_t* sm;                             // emulation: the arena is a host buffer
-#define X(name, type, n, S) DCU_MEM type* name() const { return (type*)(((S) ? sm : base) + DCU_LAYOUT.off[F_##name]); }
+#define X(name, type, n, S) DCU_MEM type* name() const { return (type*)((DCU_IN_SMEM(S) ? sm : base) + DCU_LAYOUT.off[F_##name]); }
 #else
   uint32_t sm;                             // byte offset of the warp's arena in dcu_smem
-#define X(name, type, n, S) DCU_MEM type* name() const { if (S) return (type*)(dcu_smem + sm + DCU_LAYOUT.off[F_##name]); type* p_ = (type*)(base + DCU_LAYOUT.off[F_##name]); __builtin_assume(__isGlobal(p_)); return p_; }
+#define X(name, type, n, S) DCU_MEM type* name() const { if (DCU_IN_SMEM(S)) return (type*)(dcu_smem + sm + DCU_LAYOUT.off[F_##name]); type* p_ = (type*)(base + DCU_LAYOUT.off[F_##name]); __builtin_assume(__isGlobal(p_)); return p_; }
 #endif
 #else
 #ifdef DCU_EMU
@@ -514,7 +522,7 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
   // table size of this window and k: the smallest power of two above (k-mer instances + gap filler extras), so that a free slot always
   // remains whatever the k-mers are; where the capacity (LOGH) cuts it short the table only takes hcap distinct k-mers (the margin
   // covers the inserts in flight when the limit is noticed) and a window beyond that is handed to the next pass
-  { int lg = 5; const int need = c.ni + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; c.hcap = (1 << lg) >= need ? 0x7fffffff : (1 << lg) - 288; }
+  { int lg = 5; const int need = c.ni + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; c.hcap = (1 << lg) >= need ? 0x7fffffff : (1 << lg) - (DCU_CAP.EX + 32); }
   {
     const int H = 1 << c.logh;
     DCU_NOUNROLL
@@ -1541,7 +1549,7 @@ DCU_BIG void search_pair(Ctx& c, int Fnode, int lmin, int lmax, int narp, int& n
 // trav_start (unitigs, first / last thresholds), trav_pair (one admissible (first,last) pair per call),
 // trav_finish (candidate heap -> scored, error-sorted list)
 #ifdef DCU_EMU_STATS
-static long g_stats[16];
+static long g_stats[16]; static int g_reach;
 #endif
 struct TravState { int fi, li, ncdh, firstthres, lastthres; uint32_t freeslots; bool started; int F, L, narp; };
 
@@ -1580,6 +1588,12 @@ DCU_BIG void trav_pair_graph(Ctx& c, TravState& t, int lane) {
   t.li += 1;
 #ifdef DCU_EMU_STATS
   g_stats[0]++;
+  {   // experiment: is the last k-mer reachable from the first one over active edges at all (any number of steps)?
+    static std::vector<int> lvl; lvl.assign(c.nn, -1); std::vector<int> q; q.push_back(t.F); lvl[t.F] = 0;
+    for (size_t h = 0; h < q.size(); ++h) { int n = q[h]; for (int e = 0; e < w.n_nact()[n]; ++e) { int m = w.n_snid()[4 * n + e]; if (lvl[m] < 0) { lvl[m] = lvl[n] + 1; q.push_back(m); } } }
+    g_reach = lvl[t.L];
+    g_stats[9] += (g_reach < 0);
+  }
 #endif
   derive_stretches(c, t.F, t.L, lane);
   DCU_PEAK(5, c.nds); DCU_PEAK(12, c.nrs); DCU_PEAK(13, c.slO);
@@ -1609,16 +1623,25 @@ DCU_BIG void trav_pair_rpaths(Ctx& c, TravState& t, int lmax, int lane) {
   t.narp = narp;
   if (c.overflow) return;
 #ifdef DCU_EMU_STATS
-  g_stats[1] += narp; g_stats[2] += c.nds; g_stats[3] += c.nn; g_stats[4] += c.nrl; { long sl = 0; for (int s = 0; s < c.nds; ++s) sl += c.ws.ds_len()[s]; g_stats[5] += sl; }
+  g_stats[7] += (narp == 0); g_stats[1] += narp; g_stats[2] += c.nds; g_stats[3] += c.nn; g_stats[4] += c.nrl; { long sl = 0; for (int s = 0; s < c.nds; ++s) sl += c.ws.ds_len()[s]; g_stats[5] += sl; }
 #endif
   sort_reverse_paths(c, narp, lane);
 }
 DCU_BIG void trav_pair_search(Ctx& c, TravState& t, int lmin, int lmax, int lane) {
   int ncdh = t.ncdh; uint32_t fs = t.freeslots;
+#ifdef DCU_EMU_STATS
+  const int ncdh_before = t.ncdh; const uint32_t fs_before = t.freeslots;
+#endif
   if (lane == 0) search_pair(c, t.F, lmin, lmax, t.narp, ncdh, fs);
   t.ncdh = bcast(ncdh, 0); t.freeslots = bcast(fs, 0);
   c.overflow = bcast(c.overflow, 0);
   wsync();
+#ifdef DCU_EMU_STATS
+  g_stats[8] += (t.ncdh == ncdh_before && t.freeslots == fs_before);      // pairs that left the candidate heap untouched
+  g_stats[10] += (t.ncdh == ncdh_before && t.freeslots == fs_before) && g_reach < 0;
+  g_stats[11] += (t.ncdh == ncdh_before && t.freeslots == fs_before) && (g_reach < 0 || g_reach + c.k > lmax);
+  g_stats[12] += !(t.ncdh == ncdh_before && t.freeslots == fs_before) && (g_reach < 0 || g_reach + c.k > lmax);
+#endif
 }
 // CDH -> CH -> ACC (descending weight, heap tie order), candidate errors, stable sort by error (:5101-5156)
 DCU_BIG int trav_finish(Ctx& c, TravState& t, int lane) {
@@ -1922,3 +1945,4 @@ DCU_FN void process_window(Ctx& c, const Window& win, Result& res, uint8_t* cons
 #undef DCU_P
 #undef DCU_NS
 #undef DCU_TIER_SMEM
+#undef DCU_IN_SMEM

@@ -6,6 +6,7 @@
 #include <stddef.h>
 #if defined(DCU_EMU) && defined(DCU_EMU_STATS)
 #include <chrono>
+#include <vector>
 // footprint study (tests/emu with -DDCU_EMU_STATS): per-window peaks of the workspace counters, read by tools/footprint.py
 static long g_peak[16];
 #define DCU_PEAK(i, v) do { if ((long)(v) > g_peak[i]) g_peak[i] = (long)(v); } while (0)

@@ -122,8 +122,9 @@ int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* rea
 int dcu_get_corrected(dcu_ctx* ctx, dcu_segment* seg, char* chars);
 /* statistics of the last launch: kernels launched, windows that needed the large-workspace pass */
 int dcu_last_stats(dcu_ctx* ctx, uint64_t* launches, uint64_t* hard_windows);
-/* more statistics of the last launch: windows the shared-memory pass handed to the HBM passes, windows beyond every capacity
- * (status DCU_WIN_OVERFLOW), warps per SM and shared-memory bytes per warp of the shared-memory pass (0 warps = pass not used) */
+/* more statistics of the last launch: windows the first pass handed to the plain HBM passes, windows beyond every capacity
+ * (status DCU_WIN_OVERFLOW), warps per SM and shared-memory bytes per warp of a first pass that keeps data in shared memory (the hybrid
+ * pass: k-mer table only, 32 warps; DCU_SMEM=1: the graph, 12-16 warps; 0 warps = plain HBM first pass) */
 int dcu_last_stats2(dcu_ctx* ctx, uint64_t* second_pass_windows, uint64_t* lost_windows, uint32_t* smem_warps, uint32_t* smem_bytes_per_warp);
 /* dump the host-built tables (for tests): returns number of doubles written / needed */
 int64_t dcu_get_tables(dcu_ctx* ctx, int which, double* out, int64_t cap);

@@ -62,6 +62,7 @@ template <class B> static int run_batch(const dcu_params* prm, const uint8_t* pa
   }
 #ifdef DCU_EMU_STATS
   fprintf(stderr, "windows %lu traverse calls %ld pairs %ld narp/pair %.1f nds/pair %.1f nn %.1f nrl %.1f links/pair %.1f\n", (unsigned long)nwin, dcu::g_stats[6], dcu::g_stats[0], (double)dcu::g_stats[1] / dcu::g_stats[0], (double)dcu::g_stats[2] / dcu::g_stats[0], (double)dcu::g_stats[3] / dcu::g_stats[0], (double)dcu::g_stats[4] / dcu::g_stats[0], (double)dcu::g_stats[5] / dcu::g_stats[0]);
+  fprintf(stderr, "pairs without an accepted reverse path %ld, pairs that left the candidate heap untouched %ld; last k-mer unreachable from the first %ld (dead and unreachable %ld, dead and unreachable or beyond lmax %ld, alive though unreachable / too far %ld)\n", dcu::g_stats[7], dcu::g_stats[8], dcu::g_stats[9], dcu::g_stats[10], dcu::g_stats[11], dcu::g_stats[12]);
   for (int i = 0; i < 16; ++i) dcu::g_stats[i] = 0;
 #endif
   if (noverflow) *noverflow = nov;
@@ -70,7 +71,8 @@ template <class B> static int run_batch(const dcu_params* prm, const uint8_t* pa
 // tier 0 / 1: HBM build with the capacities of the library's first / second overflow pass; tier 2: shared-memory build
 extern "C" int emu_run_batch(const dcu_params* prm, const uint8_t* packed, const dcu_window* win, uint64_t nwin, const dcu_slice* sl,
                              dcu_result* res, uint8_t* cons, uint8_t* ops, int tier, uint64_t* noverflow) {
-  return tier == 2 ? run_batch<emu::BuildS>(prm, packed, win, nwin, sl, res, cons, ops, tier, noverflow)
+  return tier == 3 ? run_batch<emu::BuildH>(prm, packed, win, nwin, sl, res, cons, ops, tier, noverflow)
+       : tier == 2 ? run_batch<emu::BuildS>(prm, packed, win, nwin, sl, res, cons, ops, tier, noverflow)
                    : run_batch<emu::BuildG>(prm, packed, win, nwin, sl, res, cons, ops, tier, noverflow);
 }
 // product table builder exposed for the table-parity test

@@ -77,7 +77,7 @@ def test_kernel_emulation_matches_oracle(name, gen, kw):
     p = default_params(**kw)
     packed, win, sl, _ = synth_batch(gen["n"], gen["depth"], seed=gen["seed"], repeat_frac=gen["rf"], depth_jitter=min(gen["depth"], 3), w=p.w)
     ro = run_oracle(p, packed, win, sl, 4)
-    for tier in (1, 0, 2):                   # 2 = the shared-memory build (small capacities: what overflows goes to the HBM passes)
+    for tier in (1, 0, 2, 3):                # 2 = the shared-memory build, 3 = the hybrid build (small capacities: what overflows goes to the HBM passes)
         re_ = run_emu(p, packed, win, sl, tier)
         bad = [i for i in compare_results(ro, re_) if re_[0][i]["status"] != 250]   # 250 = tier overflow, re-run in the next pass by the product
         assert not bad, (name, tier, bad[:5])
