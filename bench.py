@@ -412,6 +412,7 @@ def main():
             cli = {"value": att / cli_wall if r.returncode == 0 else None, "unit": "windows/s", "wall_s": cli_wall, "rc": r.returncode,
                    "what": "`daccord %s b.las b.db` as one process: DB + LAS load, CUDA context, tables, 3 batches in flight, FastA on stdout" % " ".join(opts),
                    "fasta_identical_to_library_path": bool(r.stdout == gfasta), "fraction_of_e2e": (att / cli_wall) / (att * args.steps / e2e_wall) if r.returncode == 0 else None}
+            cli["laps"] = [l[4:] for l in r.stderr.decode(errors="replace").split("\n") if l.startswith("[T] ")]
             if r.returncode != 0:
                 cli["stderr_tail"] = r.stderr.decode(errors="replace")[-400:]
             if args.cli_oracle_reads > 0 and r.returncode == 0:

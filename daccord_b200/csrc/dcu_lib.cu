@@ -408,7 +408,7 @@ struct dcu_ctx {
   DevBuf<uint8_t> dslab[3];
   dcu::Caps caps[2]; dcu::Layout lay[2]; int grid[2] = {0, 0};
   dcu::Caps capsS{}; dcus::Layout layS{}; int warpsS = 0;   // shared-memory pass: capacities, layout, warps per block
-  dcu::Caps capsH{}; dcuh::Layout layH{}; int use_hybrid = 1, hybrid_ok = 0; DevBuf<uint8_t> dslabH; DevBuf<uint32_t> dovfH;   // hybrid pass (k-mer table in shared memory)
+  dcu::Caps capsH{}; dcuh::Layout layH{}; int use_hybrid = 0, hybrid_ok = 0; DevBuf<uint8_t> dslabH; DevBuf<uint32_t> dovfH;   // hybrid pass (k-mer table in shared memory)
   uint64_t nwin = 0, nsl = 0; int maxS = 0, maxB = 0;
   // piling scratch
   DevBuf<dpile::Ovl> dpo; DevBuf<dpile::ReadInfo> dpr; DevBuf<uint32_t> dprid, dptile, dpbm, dprlen; DevBuf<uint64_t> dpboff; DevBuf<uint16_t> dptrace;
@@ -473,7 +473,9 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   // parity-tested but measured slower on B200 (12-16 resident warps per SM against 32: profiles/r02_summary.md); DCU_SMEM=1 selects it.
   { const char* e2 = getenv("DCU_SMEM"); ctx->use_smem = (e2 && atoi(e2)) ? 1 : 0; if (getenv("DCU_NO_SMEM") && atoi(getenv("DCU_NO_SMEM"))) ctx->use_smem = 0; }
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
-  { const char* e3 = getenv("DCU_HYBRID"); ctx->use_hybrid = e3 ? atoi(e3) : 1; }
+  // (measured: 1.55 against 2.33 M windows/s for the plain HBM first pass -- the 168 KB of table arenas take the L1 the scratch data of the
+  //  other stages lives on: L1 hit rate 54 % against 68 %.  Kept as DCU_HYBRID=1 for the record, profiles/r02_summary.md)
+  { const char* e3 = getenv("DCU_HYBRID"); ctx->use_hybrid = e3 ? atoi(e3) : 0; }
   const char* e = getenv("DCU_BLOCKS_PER_SM");
   if (e && atoi(e) > 0) ctx->blocks_per_sm[0] = atoi(e);
   e = getenv("DCU_SYNC_GROUP");

@@ -87,6 +87,7 @@ int main(int argc, char** argv) {
 #endif
   const int device = (int)getu("device", 0); const uint64_t batchreads = getu("batchreads", 256);
   auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) { fprintf(stderr, "[T] %.3fs %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(), what); };
   try {
     PackedDB db; LasData las;
     fprintf(stderr, "[V] loading %s ...", dbfn.c_str()); read_dazzdb(dbfn, db); fprintf(stderr, "done.\n");
@@ -109,6 +110,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "[V] minaread=%ld toparead=%ld\n", (long)minaread, (long)toparead);
     fprintf(stderr, "[V] loading %s ...", lasfn.c_str()); read_las_range(lasfn, lidx, minaread, toparead, las, nthreads); las.build_index(db.rlen.size()); validate_las(las, db.rlen);
     fprintf(stderr, "done (%zu of %ld overlaps).\n", las.ovl.size(), (long)lidx.novl);
+    lap("inputs loaded");
     fprintf(stderr, "[V] minfilterfreq=%d maxfilterfreq=%d\n", prm.min_ff, prm.max_ff);
     // error profile: <las>.eprof or -E, in the reference's binary layout (eprof.hpp); estimated from the first <= 1024 A-reads when the
     // file does not exist, or is older than the .las and --keepeprof is off (reference src/daccord.cpp:1652-1880; keepeprof defaults to 1, :1303)
@@ -146,6 +148,7 @@ int main(int argc, char** argv) {
       rc = i == 0 ? dcu_set_reads(ctxs[0], db.bytes.data(), db.bytes.size()) : dcu_share_reads(ctxs[i], ctxs[0]);
       if (rc) { fprintf(stderr, "[E] dcu_set_reads: %s %s\n", dcu_strerror(rc), dcu_last_error(ctxs[i])); return EXIT_FAILURE; }
     }
+    lap("contexts ready");
     PileParams PP; PP.w = prm.w; PP.a = advance; PP.maxalign = maxalign_eff; PP.maxinput = maxinput;
     VoteParams VP; VP.producefull = producefull; VP.minlen = minlen;
     uint64_t wellcounter = 0, totwin = 0, totok = 0, totlost = 0;
@@ -260,6 +263,7 @@ int main(int argc, char** argv) {
       for (auto& t : th) t.join();
     }
     fflush(stdout);
+    lap("batches done");
     for (auto it = ctxs.rbegin(); it != ctxs.rend(); ++it) dcu_destroy(*it);      // the owner of the read database (ctxs[0]) last
     if (failed.load()) { fprintf(stderr, "[E] %s\n", failmsg.c_str()); return EXIT_FAILURE; }
     if (totlost) fprintf(stderr, "[W] %lu windows exceeded the capacities of this build and have no consensus\n", (unsigned long)totlost);

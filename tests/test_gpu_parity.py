@@ -180,3 +180,20 @@ def test_shared_memory_build_matches_oracle(monkeypatch):
         e.close()
         assert st["smem_warps"] >= 2 and st["lost_windows"] == 0
         assert not compare_results(ro, rg), (seed, st)
+
+
+def test_hybrid_build_matches_oracle(monkeypatch):
+    """DCU_HYBRID=1: first pass with the window's k-mer table (pre-filtered, 512 slots) in shared memory at 32 warps per SM, everything else in the HBM
+    slab; windows whose table fills up or that need the filter frequency 1 graph go on to the plain HBM passes.  Same results as the oracle."""
+    for seed, depth, rf in ((211, 40, 0.0), (212, 30, 0.4)):
+        p = default_params()
+        packed, win, sl, _ = synth_batch(1000, depth, seed=seed, repeat_frac=rf, depth_jitter=3)
+        ro = run_oracle(p, packed, win, sl, 8)
+        monkeypatch.setenv("DCU_HYBRID", "1")
+        e = _engine(p)
+        e.set_reads(packed)
+        rg = e.run(win, sl)
+        st = e.stats()
+        e.close()
+        assert st["smem_warps"] == 32 and st["lost_windows"] == 0
+        assert not compare_results(ro, rg), (seed, st)
