@@ -186,6 +186,10 @@ def main():
     args.warmup = max(args.warmup, 0)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        # torchrun pins every rank to one OpenMP thread; the host sides of the ABI (validation, piling of the setup, host vote check) are OpenMP code:
+        # give every rank its share of the host cores instead (set before the libraries that read it are loaded)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, effective_cpus() // world))
     workload = "%g Mb synthetic %gx pile %s (%d kb reads, 15%% error%s, LAS-equivalent overlaps with tspace=100 trace points), -w%d -a%d -k%d%s%s" % (
         args.mb, args.coverage, "per GPU" if args.scaling == "weak" else "in total, -J sharded", args.read_len // 1000,
         (", %.0f%% of the genome in tandem repeats" % (100 * args.repeat_frac)) if args.repeat_frac else "", args.w, args.a, args.k,
