@@ -12,8 +12,8 @@ inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
   c.S = maxS < 4 ? 4 : maxS;
   c.B = maxB < 64 ? 64 : maxB;
   c.NI = c.B;
-  c.EX = tier == 0 ? 256 : 4096;
-  c.LOGH = ceil_pow2_log((c.NI + c.EX) * 3 / 2);
+  c.EX = tier == 0 ? 1024 : 4096;                  // gap filler extras (the rare windows with more than 256 used to cost a whole extra launch)
+  c.LOGH = ceil_pow2_log((c.NI + (tier == 0 ? 256 : c.EX)) * 3 / 2);
   c.H = 1 << c.LOGH;
   c.BL = w + 8;
   c.HEAVY = 0;
@@ -22,7 +22,7 @@ inline dcu::Caps make_caps(int tier, int w, int maxS, int maxB) {
     // The slab of a warp then spans ~1/4 of the address range (fewer 2 MB pages live per SM), at the price of more windows for the second pass.
     c.NN = 1024; c.ST = 512; c.SL = 2048; c.SF = 6144; c.RL = 512; c.RP = 512; c.FP = 512; c.SI = 512; c.KW = 2; c.HEAVY = 0;
   } else if (tier == 0) {
-    c.NN = 4096; c.ST = 1024; c.SL = 8192; c.SF = 16384; c.RL = 2048; c.RP = 2048; c.FP = 2048; c.SI = 2048; c.KW = 2; c.HEAVY = 0;       // HEAVY > 0 hands graphs with more nodes to the free-running pass (measured: no gain, profiles/r01_summary.md)
+    c.NN = 4096; c.ST = 2048; c.SL = 16384; c.SF = 32768; c.RL = 4096; c.RP = 4096; c.FP = 4096; c.SI = 4096; c.KW = 2; c.HEAVY = 0;       // HEAVY > 0 hands graphs with more nodes to the free-running pass (measured: no gain, profiles/r01_summary.md)
   } else {
     c.NN = c.NI + c.EX; if (c.NN > 65000) c.NN = 65000;
     c.ST = 8192; c.SL = 65000; c.SF = 262144; c.RL = 32768; c.RP = 32768; c.FP = 32768; c.SI = 32768; c.KW = 2;

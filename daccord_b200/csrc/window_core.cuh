@@ -522,7 +522,9 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
   // table size of this window and k: the smallest power of two above (k-mer instances + gap filler extras), so that a free slot always
   // remains whatever the k-mers are; where the capacity (LOGH) cuts it short the table only takes hcap distinct k-mers (the margin
   // covers the inserts in flight when the limit is noticed) and a window beyond that is handed to the next pass
-  { int lg = 5; const int need = c.ni + DCU_CAP.EX + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; c.hcap = (1 << lg) >= need ? 0x7fffffff : (1 << lg) - (DCU_CAP.EX + 32); }
+  // (the gap filler's extras are reserved for up to 256; a window with more of them usually still finds room -- distinct k-mers are far fewer than
+  // instances -- and otherwise ends with capacity code 23 for the next pass)
+  { const int exh = DCU_CAP.EX < 256 ? DCU_CAP.EX : 256; int lg = 5; const int need = c.ni + exh + 1; while ((1 << lg) < need && lg < DCU_CAP.LOGH) ++lg; c.logh = lg; c.hcap = (1 << lg) >= need ? 0x7fffffff : (1 << lg) - (exh + 32); }
   {
     const int H = 1 << c.logh;
     DCU_NOUNROLL
