@@ -12,6 +12,7 @@
 #include <fstream>
 #include <iostream>
 #include <chrono>
+#include <unistd.h>
 #include <thread>
 #include <mutex>
 #include <condition_variable>
@@ -38,7 +39,7 @@ static const char* HELP =
     "\t-e: maximum window error (default unlimited)\n\t-l: minimum length of output (default 0)\n"
     "\t--minfilterfreq: minimum k-mer filter frequency (default 0)\n\t--maxfilterfreq: maximum k-mer filter frequency (default 2)\n"
     "\t-D: maximum number of alignments considered per read (default 5000)\n\t-k: kmer size lo[,hi] (default 8)\n"
-    "\t--device: CUDA device ordinal (default 0)\n\t--batchreads: A-reads per GPU batch (default 256)\n\t--inflight: batches in flight on the GPU (default 3)\n";
+    "\t--device: CUDA device ordinal (default 0)\n\t--batchreads: A-reads per GPU batch (default 1024)\n\t--inflight: batches in flight on the GPU (default 3)\n";
 
 struct Args { std::map<std::string, std::string> opt; std::vector<std::string> pos; };
 static bool parse_args(int argc, char** argv, Args& A) {
@@ -85,7 +86,7 @@ int main(int argc, char** argv) {
 #else
   nthreads = 1;
 #endif
-  const int device = (int)getu("device", 0); const uint64_t batchreads = getu("batchreads", 256);
+  const int device = (int)getu("device", 0); const uint64_t batchreads = getu("batchreads", 1024);
   auto t_start = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) { fprintf(stderr, "[T] %.3fs %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(), what); };
   try {
@@ -142,11 +143,19 @@ int main(int argc, char** argv) {
     if ((int64_t)inflight > nbatches) inflight = (int)std::max<int64_t>(1, nbatches);
     const int wthreads = std::max(1, nthreads / inflight);
     std::vector<dcu_ctx*> ctxs((size_t)inflight, nullptr);
-    for (int i = 0; i < inflight; ++i) {
-      int rc = dcu_create(&prm, device, &ctxs[i]);
-      if (rc) { fprintf(stderr, "[E] dcu_create: %s %s\n", dcu_strerror(rc), ctxs[i] ? dcu_last_error(ctxs[i]) : ""); return EXIT_FAILURE; }
-      rc = i == 0 ? dcu_set_reads(ctxs[0], db.bytes.data(), db.bytes.size()) : dcu_share_reads(ctxs[i], ctxs[0]);
-      if (rc) { fprintf(stderr, "[E] dcu_set_reads: %s %s\n", dcu_strerror(rc), dcu_last_error(ctxs[i])); return EXIT_FAILURE; }
+    {   // one context per in-flight batch, created side by side (each builds its tables and allocates its buffers); the first one uploads the read
+        // database, the others share it
+      std::vector<int> rcs((size_t)inflight, 0);
+      std::vector<std::thread> th;
+      for (int i = 0; i < inflight; ++i) th.emplace_back([&, i]() {
+        rcs[i] = dcu_create(&prm, device, &ctxs[i]);
+        if (!rcs[i] && i == 0) rcs[i] = dcu_set_reads(ctxs[0], db.bytes.data(), db.bytes.size());
+      });
+      for (auto& t : th) t.join();
+      for (int i = 0; i < inflight; ++i) {
+        if (!rcs[i] && i > 0) rcs[i] = dcu_share_reads(ctxs[i], ctxs[0]);
+        if (rcs[i]) { fprintf(stderr, "[E] dcu_create / dcu_set_reads: %s %s\n", dcu_strerror(rcs[i]), ctxs[i] ? dcu_last_error(ctxs[i]) : ""); return EXIT_FAILURE; }
+      }
     }
     lap("contexts ready");
     PileParams PP; PP.w = prm.w; PP.a = advance; PP.maxalign = maxalign_eff; PP.maxinput = maxinput;
@@ -264,9 +273,15 @@ int main(int argc, char** argv) {
     }
     fflush(stdout);
     lap("batches done");
-    for (auto it = ctxs.rbegin(); it != ctxs.rend(); ++it) dcu_destroy(*it);      // the owner of the read database (ctxs[0]) last
     if (failed.load()) { fprintf(stderr, "[E] %s\n", failmsg.c_str()); return EXIT_FAILURE; }
     if (totlost) fprintf(stderr, "[W] %lu windows exceeded the capacities of this build and have no consensus\n", (unsigned long)totlost);
+    if (getenv("DACCORD_CLEAN_EXIT")) for (auto it = ctxs.rbegin(); it != ctxs.rend(); ++it) dcu_destroy(*it);      // the owner of the read database (ctxs[0]) last
+    else {   // the output is complete: ending the process releases the device memory faster than freeing gigabytes of workspaces buffer by buffer
+      double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+      fprintf(stderr, "[V] processed in time %.3fs, %lu windows attempted, %lu consensus\n", secs, (unsigned long)totwin, (unsigned long)totok);
+      fflush(stderr);
+      _exit(EXIT_SUCCESS);
+    }
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     fprintf(stderr, "[V] processed in time %.3fs, %lu windows attempted, %lu consensus\n", secs, (unsigned long)totwin, (unsigned long)totok);
   } catch (std::exception& e) { std::cerr << e.what() << std::endl; return EXIT_FAILURE; }

@@ -417,12 +417,20 @@ DCU_BIG int estimate_length(Ctx& c, int lane) {
 // k-mers are distinct, so the rank of an entry is the number of larger entries: lanes over entries
 DCU_BIG void rank_sort_desc(Ctx& c, uint32_t* km, uint16_t* cn, uint16_t* nd, int n, int lane) {
   const WS w = c.ws;
+  // (count, kmer) as one 64-bit key (counts are >= 1, so 0 is below every entry); the other entries come by shuffle, 32 at a time
   DCU_NOUNROLL
-  for (int e = lane; e < n; e += DCU_NL) {
-    uint32_t k = km[e]; uint16_t cc = cn[e]; int r = 0;
+  for (int e0 = 0; e0 < n; e0 += DCU_NL) {
+    const int e = e0 + lane;
+    const unsigned long long mine = e < n ? (((unsigned long long)cn[e] << 32) | (unsigned long long)km[e]) : 0ull;
+    int r = 0;
     DCU_NOUNROLL
-    for (int i = 0; i < n; ++i) r += (cn[i] > cc) || (cn[i] == cc && km[i] > k);
-    w.ts_k()[r] = k; w.ts_c()[r] = cc; if (nd) w.ts_n()[r] = nd[e];
+    for (int i0 = 0; i0 < n; i0 += DCU_NL) {
+      const unsigned long long theirs = i0 + lane < n ? (((unsigned long long)cn[i0 + lane] << 32) | (unsigned long long)km[i0 + lane]) : 0ull;
+      const int cnt = n - i0 < DCU_NL ? n - i0 : DCU_NL;
+      DCU_NOUNROLL
+      for (int t = 0; t < cnt; ++t) r += bcast(theirs, t) > mine ? 1 : 0;
+    }
+    if (e < n) { w.ts_k()[r] = (uint32_t)mine; w.ts_c()[r] = (uint16_t)(mine >> 32); if (nd) w.ts_n()[r] = nd[e]; }
   }
   wsync();
   DCU_NOUNROLL
@@ -504,6 +512,43 @@ template <class F, class G> DCU_FN void for_each_kmer(const Ctx& c, int lane, F 
     if (i1 == numk) g(j, v);
   }
 }
+// The same with the table probe of the next k-mer in flight while the current one is handled: pre(v) issues the load of a k-mer's home slot
+// and returns what it held, f(j, i, len, v, key) gets it one step later.  A key may be stale by then (the previous k-mer of the lane, or
+// another lane, may have claimed the slot): f must treat an empty key as "try to claim", which the compare-and-swap then decides.
+// (Four probes in flight were tried -- calls 5/6 of round 2: 15 % slower, the 64-register build spills in the loop.)
+template <class P, class F, class G> DCU_FN void for_each_kmer_pf(const Ctx& c, int lane, P pre, F f, G g) {
+  const int K = c.k;
+  const int parts = c.MAo > 48 ? 1 : (c.MAo > 20 ? 2 : 4);
+  const int ntask = c.MAo * parts;
+  DCU_NOUNROLL
+  for (int t = lane; t < ntask; t += DCU_NL) {
+    const int j = t / parts, part = t - j * parts;
+    const int len = seqlen(c, j), numk = len - K + 1;
+    if (numk <= 0) continue;
+    const int per = (numk + parts - 1) / parts;
+    const int i0 = part * per, i1 = i0 + per < numk ? i0 + per : numk;
+    if (i0 >= i1) continue;
+    const uint32_t* u = slice_words(c, j);
+    uint32_t v = 0, wd = u[i0 >> 4] >> (2 * (i0 & 15));
+    int b = i0;                                        // next base to take
+    DCU_NOUNROLL
+    for (; b < i0 + K - 1; ++b) { v = (v << 2) | (wd & 3u); wd >>= 2; if (((b + 1) & 15) == 0) wd = u[(b + 1) >> 4]; }
+    v = ((v << 2) & c.kmask) | (wd & 3u); wd >>= 2; ++b;
+    if ((b & 15) == 0 && b < len) wd = u[b >> 4];
+    uint32_t key = pre(v);
+    DCU_NOUNROLL
+    for (int i = i0; i < i1; ++i) {
+      const uint32_t vc = v, kc = key;
+      if (i + 1 < i1) {
+        v = ((v << 2) & c.kmask) | (wd & 3u); wd >>= 2; ++b;
+        if ((b & 15) == 0 && b < len) wd = u[b >> 4];
+        key = pre(v);
+      }
+      f(j, i, len, vc, kc);
+    }
+    if (i1 == numk) g(j, v);
+  }
+}
 DCU_BIG void kmer_offsets(Ctx& c, int lane) {          // number of k-mer instances of the window
   uint32_t nk = 0;
   DCU_NOUNROLL
@@ -546,12 +591,11 @@ DCU_BIG void build_hash(Ctx& c, int lane, bool pre) {
   bool full = false;
   const bool live = c.hcap != 0x7fffffff;              // the table may fill up: the claimed-slot counter has to be current
   uint32_t claimed = 0;
-  // (four probes in flight per lane were tried here -- call 5/6 of round 2: 15 % slower, the 64-register build spills in the loop)
-  for_each_kmer(c, lane, [&](int, int, int, uint32_t v) {
+  for_each_kmer_pf(c, lane, [&](uint32_t v) { return a_load(&w.hkey()[hslot(c, v)]); }, [&](int, int, int, uint32_t v, uint32_t key) {
     if (full) return;
     if (pre) { const uint32_t b = prebit(v); if (!((w.hbB()[b >> 5] >> (b & 31)) & 1u)) return; }      // (bitmaps are final: wsync above)
     if (live && a_load(&w.hstate()[0]) > (uint32_t)c.hcap) { full = true; return; }      // racy read of a monotone counter: the overshoot is bounded by the lanes' in-flight inserts
-    hash_insert_fast(c, v, a_load(&w.hkey()[hslot(c, v)]), claimed, live);
+    hash_insert_fast(c, v, key, claimed, live);
   }, [&](int j, uint32_t v) { w.lastk()[j] = v; });                                // final k-mer of the sequence (the `last` array, :2108)
   wsync();
   claimed = red_sum_u32(claimed);
@@ -597,11 +641,13 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   wsync();
 #endif
   int nn = 0;
+  uint32_t nkey = w.hkey()[lane]; hval_t nval = w.hval()[lane];       // slots of the next round of the scan are requested one round ahead
   DCU_NOUNROLL
   for (int base = 0; base < H; base += DCU_NL) {
     const int h = base + lane;                         // H is a multiple of 32
-    const uint32_t key = w.hkey()[h];
-    const int cnt = (int)(w.hval()[h] & 0xFFFFu);
+    const uint32_t key = nkey;
+    const int cnt = (int)(nval & 0xFFFFu);
+    if (base + DCU_NL < H) { nkey = w.hkey()[h + DCU_NL]; nval = w.hval()[h + DCU_NL]; }
     const bool occ = key != W_EMPTY, keep = occ && cnt >= f;
     const uint32_t b = ballot(keep);
     const int idx = nn + popc(b & lanemask_lt(lane));
@@ -634,8 +680,8 @@ DCU_BIG void build_nodes(Ctx& c, int f, int lane) {
   DCU_PEAK(3, c.ni);
   if (c.ni > DCU_CAP.NI + DCU_CAP.EX) { c.overflow = 4; return; }
   // instances are filed under their nodes: the k-mers are rolled once more and looked up (no per-instance slot array)
-  for_each_kmer(c, lane, [&](int, int i, int len, uint32_t v) {
-    const int n = lookup_fast(c, v, w.hkey()[hslot(c, v)]);
+  for_each_kmer_pf(c, lane, [&](uint32_t v) { return w.hkey()[hslot(c, v)]; }, [&](int, int i, int len, uint32_t v, uint32_t key) {
+    const int n = lookup_fast(c, v, key);
     if (n != NID_NONE) { const uint32_t t = add16(w.fillcnt(), (uint32_t)n, 1u) + (uint32_t)w.n_ioff()[n]; w.ipos()[t] = (uint8_t)i; w.irpos()[t] = (uint8_t)(len - i - c.k); }
   }, [](int, uint32_t) {});
   DCU_NOUNROLL
