@@ -45,8 +45,6 @@ struct KArgs {
   unsigned int* ovf_cnt; uint32_t* ovf_list;   // windows that overflowed this pass
   unsigned long long packed_bytes;     // readable bytes of the packed database (staging never reads beyond)
   int stage;                           // shared-memory pass: stage the slices of the next window with cp.async.bulk
-  // heavy workers (HBM first pass): the first heavy_blocks blocks run free and take the windows the lock-step blocks hand on (pair budget)
-  unsigned int* heavy_cnt; unsigned int* heavy_head; unsigned int* done_warps; uint32_t* heavy_list; int heavy_blocks;
   unsigned int launch_seq;             // number of this launch in the context's life (upper half of the forward slot tags: records of earlier launches in the slab are stale)
 };
 
@@ -90,15 +88,9 @@ template <int W, int B = BPS> __global__ void __launch_bounds__(W * 32, B) dcu_w
   dcu::Ctx c;
   c.ws.base = a.slabs + ((size_t)blockIdx.x * W + warp) * (size_t)dcu::c_layout.bytes;
   c.vsq = a.vs_words ? s_vs : dcu::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0; c.epoch = (unsigned long long)a.launch_seq << 32;
-  // Heavy workers: a window that walks through dozens of (first,last) pairs would hold its warp for as many rounds of its block's lock step
-  // (a 170-pair window: 70 ms -- the tail of a launch).  The lock-step blocks hand such a window on after `maxpairs` pairs (while few have been:
-  // in shallow piles, where they are the rule, the budget is used up at once and everybody stays); the first heavy_blocks blocks of the grid run
-  // free and redo those windows from scratch, concurrently with the rest of the launch.
-  const bool worker = (int)blockIdx.x < a.heavy_blocks;
-  c.defer_cnt = (a.heavy_blocks && !worker) ? a.heavy_cnt : nullptr; c.defer_limit = a.n / 256u;
   c.packed = a.packed; c.sl = a.sl;
   __shared__ int s_done[2][W];                         // double buffered: with a single barrier per round a fast warp must not overwrite what a slow one still reads
-  const int G = worker ? 1 : a.sync_group, grp = warp / G, gfirst = grp * G;
+  const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
   auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
   const int smask = a.sync_mask;                       // which of the inner stage boundaries are barriers (bit 0: hash|nodes, 5: nodes|edges, 1: edges|trav, 4: trav|pos, 2: pos|rpath, 6: rpath|search, 7: search|score, 3: score|final)
   dcu::WinState st; st.ph = dcu::PH_END;
@@ -106,36 +98,16 @@ template <int W, int B = BPS> __global__ void __launch_bounds__(W * 32, B) dcu_w
   auto publish = [&]() {
     if (lane == 0) {
       a.res[wi] = st.res;
-      if (st.res.status == dcu::ST_OVERFLOW) {
-        if (st.res.err == 24) { unsigned int o = atomicAdd(a.heavy_cnt, 1u); __threadfence(); *(volatile uint32_t*)&a.heavy_list[o] = wi; }      // to the heavy workers of this launch
-        else { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
-      }
+      if (st.res.status == dcu::ST_OVERFLOW) { unsigned int o = atomicAdd(a.ovf_cnt, 1u); a.ovf_list[o] = wi; }
     }
   };
-  const unsigned int main_warps = (gridDim.x - (unsigned int)a.heavy_blocks) * W;
   for (;; par ^= 1) {
     while (!nomore && st.ph == dcu::PH_END) {          // finish / fetch
       unsigned int t = 0;
-      if (!worker) {
-        if (lane == 0) t = atomicAdd(a.ticket, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= a.n) { nomore = true; if (lane == 0 && a.heavy_blocks) { __threadfence(); atomicAdd(a.done_warps, 1u); } break; }
-        wi = a.todo ? a.todo[t] : t;
-      } else {
-        // reserve the next entry of the hand-over list and wait for it -- or for the end of the lock-step blocks with the entry beyond the list
-        if (lane == 0) {
-          const unsigned int h = atomicAdd(a.heavy_head, 1u);
-          for (;;) {
-            t = *(volatile uint32_t*)&a.heavy_list[h];
-            if (t != 0xFFFFFFFFu) break;
-            if (*(volatile unsigned int*)a.done_warps == main_warps) { __threadfence(); if (h >= *(volatile unsigned int*)a.heavy_cnt) break; }
-            __nanosleep(2000);
-          }
-        }
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t == 0xFFFFFFFFu) { nomore = true; break; }
-        wi = t;
-      }
+      if (lane == 0) t = atomicAdd(a.ticket, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= a.n) { nomore = true; break; }
+      wi = a.todo ? a.todo[t] : t;
       const dcu::Window wd = a.win[wi];
       dcu::st_begin(c, st, wd, lane, nullptr);
       if (st.ph == dcu::PH_END) publish();             // skipped or overflowed right away
@@ -155,7 +127,6 @@ __global__ void __launch_bounds__(WPB * 32, BPS) dcuh_window_kernel(const __grid
   c.ws.base = a.slabs + ((size_t)blockIdx.x * WPB + warp) * (size_t)dcuh::c_layout.bytes;
   c.ws.sm = vs_bytes + (uint32_t)warp * dcuh::c_layout.sbytes;
   c.vsq = a.vs_words ? (const unsigned long long*)dcuh::dcu_smem : dcuh::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0; c.epoch = (unsigned long long)a.launch_seq << 32;
-  c.defer_cnt = nullptr; c.defer_limit = 0;
   c.packed = a.packed; c.sl = a.sl;
   __shared__ int s_done[2][WPB];
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
@@ -208,7 +179,6 @@ __global__ void __launch_bounds__(SWPB * 32, 1) dcus_window_kernel(const __grid_
   c.ws.base = a.slabs + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)dcus::c_layout.bytes;
   c.ws.sm = vs_bytes + (uint32_t)warp * dcus::c_layout.sbytes;
   c.vsq = a.vs_words ? (const unsigned long long*)dcus::dcu_smem : dcus::c_T.VSq; c.vs_sm = a.vs_words ? 1 : 0; c.epoch = (unsigned long long)a.launch_seq << 32;
-  c.defer_cnt = nullptr; c.defer_limit = 0;
   c.packed = a.packed; c.sl = a.sl;
   const int G = a.sync_group, grp = warp / G, gfirst = grp * G;
   auto gsync = [&]() { if (G > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory"); };
@@ -496,7 +466,7 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   ctx->T.DPn = ctx->dDPn.p; ctx->T.DPsq = ctx->dDPsq.p; ctx->T.VSq = ctx->dVSq.p; ctx->T.klim = ctx->dklim.p;
   ctx->T.suplo = ctx->dsuplo.p; ctx->T.suphi = ctx->dsuphi.p; ctx->T.NP = H.NP; ctx->T.MS = H.MS; ctx->T.KLIMN = H.KLIMN;
   ctx->P.w = (int)p->w; ctx->P.k_lo = (int)p->k_lo; ctx->P.k_hi = (int)p->k_hi; ctx->P.minff = p->min_ff; ctx->P.maxff = p->max_ff;
-  ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err; ctx->P.defer_ff = 0; ctx->P.maxpairs = 0;
+  ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err; ctx->P.defer_ff = 0;
   { const char* e = getenv("DCU_POSCACHE"); ctx->P.poscache = e ? atoi(e) : 1; }
   CK(ctx->dcnt.ensure(16));
   // First pass: the HBM build by default.  The shared-memory build (graph in shared memory, slices staged by bulk copies) is complete and
@@ -723,14 +693,13 @@ static void fill_args(dcu_ctx* ctx, KArgs& a, int cnt_at, int list, const uint32
   a.todo = todo; a.n = n;
   a.ticket = ctx->dcnt.p + cnt_at; a.ovf_cnt = ctx->dcnt.p + cnt_at + 1; a.ovf_list = ctx->dovf[list].p;
   a.packed_bytes = ctx->packed_padded; a.stage = 0; a.launch_seq = ++ctx->launch_seq;
-  a.heavy_cnt = a.heavy_head = a.done_warps = nullptr; a.heavy_list = nullptr; a.heavy_blocks = 0;
   { const char* e = getenv("DCU_SYNC_MASK"); a.sync_mask = e ? atoi(e) : 255; }
 }
 // HBM passes: tier 0 (first overflow pass, or the first pass when the shared-memory pass is off), tier 1 (large workspaces, free running)
 static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n) {
   int bps = ctx->blocks_per_sm[tier];
   int grid = ctx->num_sms * bps;
-  int wpb = WPB, heavy_blocks = 0;
+  int wpb = WPB;
   { const char* e = getenv("DCU_WPB"); if (e && tier == 0 && (atoi(e) == 12 || atoi(e) == 32)) { wpb = atoi(e); if (wpb == 32) { bps = 1; grid = ctx->num_sms; } } }
   size_t need_blocks = ((size_t)n + wpb - 1) / wpb;
   if ((size_t)grid > need_blocks) grid = (int)std::max<size_t>(1, need_blocks);
@@ -743,18 +712,10 @@ static int launch_tier(dcu_ctx* ctx, int tier, const uint32_t* todo, uint32_t n)
     dcu::Params& P = ctx->Pl[tier];
     P = ctx->P;
     P.defer_ff = (tier == 0 && ctx->sync_group > 1 && getenv("DCU_DEFER_FF")) ? 1 : 0;
-    { const char* e = getenv("DCU_HEAVY_BLOCKS"); heavy_blocks = (tier == 0 && todo == nullptr && ctx->sync_group > 1 && grid >= 64 && wpb == WPB) ? (e ? atoi(e) : 8) : 0; if (heavy_blocks < 0 || heavy_blocks > grid / 4) heavy_blocks = 0; }
-    { const char* e = getenv("DCU_MAXPAIRS"); P.maxpairs = heavy_blocks ? (e ? atoi(e) : 32) : 0; }
     CK(cudaMemcpyToSymbolAsync(dcu::c_P, &P, sizeof(dcu::Params), 0, cudaMemcpyHostToDevice, ctx->stream));
   }
   fill_args(ctx, a, 2 * tier, tier, todo, n);
   a.slabs = ctx->dslab[tier].p;
-  if (heavy_blocks) {                                // hand-over list of this launch: dovf[2] (free: the shared-memory pass is not running), counters dcnt[8..10]
-    const size_t cap = (size_t)n / 256 + 16384;
-    CK(ctx->dovf[2].ensure(cap + 1));
-    CK(cudaMemsetAsync(ctx->dovf[2].p, 0xFF, std::min(cap, ctx->dovf[2].cap) * sizeof(uint32_t), ctx->stream));
-    a.heavy_cnt = ctx->dcnt.p + 8; a.heavy_head = ctx->dcnt.p + 9; a.done_warps = ctx->dcnt.p + 10; a.heavy_list = ctx->dovf[2].p; a.heavy_blocks = heavy_blocks;
-  }
   size_t vs_bytes = ctx->HT.VSq.size() * sizeof(unsigned long long);
   if (vs_bytes > 40 * 1024 || getenv("DCU_VS_GLOBAL")) vs_bytes = 0;            // one copy per block (2 blocks / SM); larger tables are read from L2
   a.vs_words = (uint32_t)(vs_bytes / 8);

@@ -180,7 +180,6 @@ struct Ctx {
   int nrs, slO, nds, nrl, kwtot;
   int overflow;
   unsigned long long epoch, epoch_trav, epoch_pair;   // tags of the forward slot records: a counter ((launch << 32) | events of this warp) stepped at every traverse and pair
-  const unsigned int* defer_cnt; unsigned int defer_limit;   // windows already handed on in this launch / how many may be (kernel wrapper; null in the emulations)
   uint32_t fbase0;                         // forward slots below this offset hold the traverse's cached raw unitigs (tag epoch_trav), the others this pair's pieces (epoch_pair)
 };
 
@@ -1817,7 +1816,7 @@ enum { PH_BEGIN = 0, PH_HASH, PH_NODES, PH_EDGES, PH_TRAV, PH_POS, PH_RPATH, PH_
 struct WinState {
   int ph;
   Result res;
-  int lmin, lmax, k, ff, mintry, npairs;
+  int lmin, lmax, k, ff, mintry;
   bool pathfailed, have;
   unsigned long long minrate;
   int bestlen, bestk, bestff, bestn;
@@ -1846,7 +1845,7 @@ DCU_BIG void st_begin(Ctx& c, WinState& s, const Window& win, int lane, const ui
   s.lmin = elength - 4; s.lmax = elength + 4;
   s.pathfailed = true; s.have = false; s.minrate = DCU_P.eminrate;
   s.bestlen = 0; s.bestk = 0; s.bestff = -1; s.bestn = 0;
-  s.k = DCU_P.k_lo; s.ph = PH_HASH; s.npairs = 0;
+  s.k = DCU_P.k_lo; s.ph = PH_HASH;
 }
 DCU_BIG void st_hash(Ctx& c, WinState& s, int lane) {
   const int k = s.k;
@@ -1940,13 +1939,6 @@ DCU_BIG void st_search(Ctx& c, WinState& s, int lane) {
   TravState& t = s.tv;
   trav_pair_search(c, t, s.lmin, s.lmax, lane);
   if (c.overflow) { st_overflow(c, s); return; }
-  // A window that walks through dozens of pairs holds its warp for as many rounds of the block's lock step (a 170-pair window: 70 ms, the
-  // tail of a launch).  While such windows are rare it is handed to the next pass, which runs free; when they are the rule (shallow piles)
-  // the budget of the launch is used up at once and everybody stays.
-  if (DCU_P.maxpairs && ++s.npairs >= DCU_P.maxpairs && c.defer_cnt) {
-    const unsigned int handed = bcast(lane == 0 ? a_load(c.defer_cnt) : 0u, 0);      // one reading for the whole warp
-    if (handed < c.defer_limit && trav_seek(c, t)) { s.res.status = ST_OVERFLOW; s.res.err = 24; s.ph = PH_END; return; }
-  }
   s.ph = trav_seek(c, t) ? PH_TRAV : PH_SCORE;            // more pairs: next round
 }
 DCU_BIG void st_score(Ctx& c, WinState& s, int lane) { st_trav_done(c, s, lane); }

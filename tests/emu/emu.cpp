@@ -31,7 +31,7 @@ template <class B> static int run_batch(const dcu_params* prm, const uint8_t* pa
   emu::tables_for(HT, T); emu::params_for(prm, tier, P);
   B::globals(L, caps, T, P);
   typename B::Ctx c;
-  B::bind(c, slab.data(), arena.data()); c.vsq = T.VSq; c.vs_sm = 0; c.epoch = 0; c.defer_cnt = nullptr; c.defer_limit = 0;      // (the slab starts zeroed: no forward slot record carries a tag yet)
+  B::bind(c, slab.data(), arena.data()); c.vsq = T.VSq; c.vs_sm = 0; c.epoch = 0;      // (the slab starts zeroed: no forward slot record carries a tag yet)
   c.packed = packed; c.sl = (const dcu::Slice*)sl;
   uint64_t nov = 0;
   for (uint64_t i = 0; i < nwin; ++i) {

@@ -197,22 +197,3 @@ def test_hybrid_build_matches_oracle(monkeypatch):
         e.close()
         assert st["smem_warps"] == 32 and st["lost_windows"] == 0
         assert not compare_results(ro, rg), (seed, st)
-
-
-def test_heavy_worker_blocks_change_nothing(monkeypatch):
-    """windows that walk through many (first,last) pairs are handed by the lock-step blocks to the free-running worker blocks of the same launch
-    (pair budget DCU_MAXPAIRS, at most n/256 windows per launch): with a budget of one pair on a repeat-rich shallow pile the hand-over list
-    fills up at once; same results as the oracle, as without workers."""
-    p = default_params()
-    packed, win, sl, _ = synth_batch(6000, 12, seed=221, repeat_frac=0.5, depth_jitter=3)
-    ro = run_oracle(p, packed, win, sl, 8)
-    for env in (dict(DCU_MAXPAIRS="1", DCU_HEAVY_BLOCKS="8"), dict(DCU_MAXPAIRS="3", DCU_HEAVY_BLOCKS="2"), dict(DCU_HEAVY_BLOCKS="0")):
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        e = _engine(p)
-        e.set_reads(packed)
-        rg = e.run(win, sl)
-        st = e.stats()
-        e.close()
-        assert st["lost_windows"] == 0
-        assert not compare_results(ro, rg), (env, st)
