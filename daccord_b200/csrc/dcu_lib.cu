@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <new>
 #include <mutex>
+#include <chrono>
 #include "window_core.cuh"            // namespace dcu : every workspace field in the warp's HBM slab (overflow passes, deep piles)
 #define DCU_NS dcus
 #define DCU_TIER_SMEM 1
@@ -373,6 +374,14 @@ __global__ void __launch_bounds__(VOTE_TPB) vote_k1(dvote::Ctx c, const dvote::R
 // concurrently, which is what lets a caller keep several batches in flight (daccord_main.cpp).
 std::mutex g_window_pass_lock[64];
 
+// DCU_TIMING=1: host-side lap times of dcu_pile / dcu_vote on stderr (measurement aid)
+struct Laps {
+  bool on; const char* what; std::chrono::steady_clock::time_point t0, t; std::string s;
+  explicit Laps(const char* w) : on(getenv("DCU_TIMING") != nullptr), what(w), t0(std::chrono::steady_clock::now()), t(t0) {}
+  void lap(const char* name) { if (!on) return; auto n = std::chrono::steady_clock::now(); char b[64]; snprintf(b, sizeof b, " %s %.1f", name, std::chrono::duration<double, std::milli>(n - t).count()); s += b; t = n; }
+  ~Laps() { if (on) fprintf(stderr, "[timing] %s: total %.1f ms:%s\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), s.c_str()); }
+};
+
 template <class T> struct DevBuf {
   T* p = nullptr; size_t cap = 0;
   cudaError_t ensure(size_t n, bool zero = false) {
@@ -416,6 +425,7 @@ struct dcu_ctx {
   // vote scratch and results
   DevBuf<uint16_t> dvent; DevBuf<uint8_t> dvflag; DevBuf<uint64_t> dvblk; DevBuf<char> dvchars; DevBuf<dvote::Read> dvreads; DevBuf<dvote::Bound> dvbound;
   std::vector<dcu_segment> segs; uint64_t nchars = 0; bool results_valid = false;
+  dcu_window* hwin = nullptr; uint64_t hwin_cap = 0;      // pinned host copy of the window descriptors (dcu_vote lays out the reads from it)
   unsigned int launch_seq = 0;
   uint64_t launches = 0, hard = 0, second = 0, lost = 0;     // second: windows the shared-memory pass handed on; hard: windows of the large-workspace pass; lost: beyond every capacity
   std::string err;
@@ -493,6 +503,7 @@ void dcu_destroy(dcu_ctx* ctx) {
   ctx->dpboff.release(); ctx->dptrace.release(); ctx->dpmin.release(); ctx->dpdiv.release(); ctx->dpact.release(); ctx->dpcnt.release(); ctx->dpblkw.release(); ctx->dpblks.release();
   ctx->dovf[0].release(); ctx->dovf[1].release(); ctx->dovf[2].release(); ctx->dcnt.release(); ctx->dslab[0].release(); ctx->dslab[1].release(); ctx->dslab[2].release();
   ctx->dslabH.release(); ctx->dovfH.release(); ctx->dvent.release(); ctx->dvflag.release(); ctx->dvblk.release(); ctx->dvchars.release(); ctx->dvreads.release(); ctx->dvbound.release();
+  if (ctx->hwin) cudaFreeHost(ctx->hwin);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -609,8 +620,10 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
   if (!ctx || (!ovl && novl) || (!trace && ntrace) || !read_boff || !read_len) return DCU_ERR_PARAM;
   if (!ctx->dpacked) { ctx->err = "dcu_set_reads not called"; return DCU_ERR_STATE; }
   CK(cudaSetDevice(ctx->device));
+  Laps laps("dcu_pile");
   dpile::Prep P;
   if (!dpile::prepare(ovl, novl, ntrace, tspace, ctx->prm.w, advance, nreads, read_len, P)) { ctx->err = P.err; return DCU_ERR_UNSUPPORTED; }
+  laps.lap("prepare");
   int bad = 0;                                   // every B block must lie inside its read and fit the tile aligner
 #pragma omp parallel for schedule(static) reduction(max : bad)
   for (int64_t i = 0; i < (int64_t)novl; ++i) {
@@ -620,6 +633,7 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
     if ((read_boff[ovl[i].bread] + (read_len[ovl[i].bread] + 3) / 4) > ctx->packed_bytes) e = std::max(e, 1);
     bad = std::max(bad, e);
   }
+  laps.lap("validate");
   if (bad == 3) { ctx->err = "trace block longer than 256"; return DCU_ERR_UNSUPPORTED; }
   if (bad == 2) { ctx->err = "trace points run past the B read"; return DCU_ERR_PARAM; }
   if (bad == 1) { ctx->err = "read outside the packed database"; return DCU_ERR_PARAM; }
@@ -629,6 +643,7 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
   CK(ctx->dprlen.ensure(nreads + 1)); CK(ctx->dpboff.ensure(nreads + 1)); CK(ctx->dptrace.ensure(ntrace + 1));
   CK(ctx->dpmin.ensure(nr + 1)); CK(ctx->dpdiv.ensure(nr + 1)); CK(ctx->dpact.ensure(novl + 1)); CK(ctx->dcnt.ensure(16));
   cudaStream_t st = ctx->stream;
+  laps.lap("ensure");
   if (novl) CK(cudaMemcpyAsync(ctx->dpo.p, P.ovl.data(), novl * sizeof(dpile::Ovl), cudaMemcpyHostToDevice, st));
   if (ntrace) CK(cudaMemcpyAsync(ctx->dptrace.p, trace, ntrace * 2, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->dpboff.p, read_boff, nreads * 8, cudaMemcpyHostToDevice, st));
@@ -658,7 +673,9 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(&tw, ctx->dpblkw.p + nblk, 8, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(&ts, ctx->dpblks.p + nblk, 8, cudaMemcpyDeviceToHost, st));
+      laps.lap("enqueue");
       CK(cudaStreamSynchronize(st));
+      laps.lap("sync1");
     }
     if (tw >= 0xFFFFFFF0ull || ts >= 0xFFFFFFF0ull) { ctx->err = "batch too large"; return DCU_ERR_UNSUPPORTED; }
     CK(ctx->dwin.ensure(tw + 1)); CK(ctx->dsl.ensure(ts + 1));
@@ -672,6 +689,7 @@ int dcu_pile(dcu_ctx* ctx, const dcu_overlap* ovl, uint64_t novl, const uint16_t
     CK(cudaMemcpyAsync(mx, dmx, sizeof(mx), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    laps.lap("pass2+sync");
     if (herr) { ctx->err = "piling failed on the device (slice longer than 65535 bases)"; return DCU_ERR_UNSUPPORTED; }
   }
   if (nwin_out) *nwin_out = tw;
@@ -872,11 +890,20 @@ int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* rea
   if (ctx->prm.w > 127) { ctx->err = "vote tables hold w <= 127"; return DCU_ERR_UNSUPPORTED; }
   cudaStream_t st = ctx->stream;
   const uint64_t nwin = ctx->nwin;
-  std::vector<dcu_window> hwin(nwin);
-  CK(cudaMemcpyAsync(hwin.data(), ctx->dwin.p, nwin * sizeof(dcu_window), cudaMemcpyDeviceToHost, st));
+  Laps laps("dcu_vote");
+  if (nwin > ctx->hwin_cap) {                        // pinned staging of the window descriptors (a pageable target costs 30 ms per 84 MB instead of 4)
+    if (ctx->hwin) cudaFreeHost(ctx->hwin);
+    ctx->hwin = nullptr; ctx->hwin_cap = 0;
+    CK(cudaMallocHost((void**)&ctx->hwin, (nwin + nwin / 4 + 16) * sizeof(dcu_window)));
+    ctx->hwin_cap = nwin + nwin / 4 + 16;
+  }
+  dcu_window* const hwin_p = ctx->hwin;
+  CK(cudaMemcpyAsync(hwin_p, ctx->dwin.p, nwin * sizeof(dcu_window), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  laps.lap("windows_d2h");
   dvote::Layout L;
-  if (!dvote::layout_reads(hwin.data(), nwin, ctx->prm.w, producefull != 0, read_boff, read_len, nreads, L)) { ctx->err = L.err; return DCU_ERR_PARAM; }
+  if (!dvote::layout_reads(hwin_p, nwin, ctx->prm.w, producefull != 0, read_boff, read_len, nreads, L)) { ctx->err = L.err; return DCU_ERR_PARAM; }
+  laps.lap("layout");
   if (producefull) for (auto& R : L.reads) if (R.boff + (R.rlen + 3) / 4 > ctx->packed_bytes) { ctx->err = "read outside the packed database"; return DCU_ERR_PARAM; }
   const uint32_t nr = (uint32_t)L.reads.size();
   const uint64_t npos = L.npos, nblk = (npos + VOTE_TPB - 1) / VOTE_TPB;
@@ -897,6 +924,7 @@ int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* rea
   CK(cudaMemcpyAsync(&total, ctx->dvblk.p + nblk, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  laps.lap("count_pass");
   if (herr) { ctx->err = "a placement trace does not cover its window"; return DCU_ERR_STATE; }
   CK(ctx->dvchars.ensure(total + 1));
   vote_k1<<<(unsigned)nblk, VOTE_TPB, 0, st>>>(vc, ctx->dvreads.p, nr, npos, ctx->dvflag.p, ctx->dvblk.p, ctx->dvchars.p, ctx->dvbound.p, dnb, (unsigned int)bound_cap);
@@ -908,8 +936,10 @@ int dcu_vote(dcu_ctx* ctx, int producefull, uint64_t minlen, const uint64_t* rea
   std::vector<dvote::Bound> hb(nb);
   if (nb) CK(cudaMemcpyAsync(hb.data(), ctx->dvbound.p, nb * sizeof(dvote::Bound), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  laps.lap("fill_pass");
   std::string perr;
   if (!dvote::pair_bounds(hb, L, producefull != 0, minlen, ctx->segs, perr)) { ctx->err = perr; return DCU_ERR_STATE; }
+  laps.lap("pair_bounds");
   ctx->nchars = total; ctx->launches += 4;
   if (nseg) *nseg = ctx->segs.size();
   if (nchars) *nchars = total;
