@@ -322,6 +322,7 @@ def main():
     full_wall, full_same, full_d2h, truth, e2e_parts = None, None, 0, None, None
     if gpu_pile:
         eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng.launch(); seg, chars = eng.vote()      # warm-up
+        chars_p = torch.empty(int(len(chars) * 1.02) + 4096, dtype=torch.uint8).pin_memory().numpy()     # pinned target of the corrected bases, like the other host buffers of the step
         barrier()
         t0 = time.perf_counter()
         tp = tl = tv = 0.0
@@ -331,7 +332,7 @@ def main():
             tb = time.perf_counter()
             eng.launch()
             tc = time.perf_counter()
-            seg, chars = eng.vote()
+            seg, chars = eng.vote(chars_out=chars_p)
             td = time.perf_counter()
             tp += tb - ta; tl += tc - tb; tv += td - tc
         barrier()

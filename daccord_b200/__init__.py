@@ -130,13 +130,14 @@ class Engine:
         self._ck(self.lib.dcu_run(self.ctx, _p(win), C.c_uint64(len(win)), _p(sl), C.c_uint64(len(sl)), _p(res), _p(cons), _p(ops)))
         return res, cons, ops
 
-    def vote(self, producefull=False, minlen=0, read_boff=None, read_len=None):
-        """pile vote of the resident results on the GPU; returns (segments, chars) -- see dcu_vote in include/daccord_b200.h"""
+    def vote(self, producefull=False, minlen=0, read_boff=None, read_len=None, chars_out=None):
+        """pile vote of the resident results on the GPU; returns (segments, chars) -- see dcu_vote in include/daccord_b200.h.
+        chars_out: optional uint8 buffer (e.g. pinned host memory) the corrected bases are copied into when it is large enough"""
         ns, nc = C.c_uint64(0), C.c_uint64(0)
         nreads = 0 if read_len is None else len(read_len)
         self._ck(self.lib.dcu_vote(self.ctx, C.c_int(1 if producefull else 0), C.c_uint64(minlen), _p(read_boff), _p(read_len), C.c_uint64(nreads), C.byref(ns), C.byref(nc)))
         seg = np.zeros(ns.value, SEGMENT_DT)
-        chars = np.zeros(nc.value, np.uint8)
+        chars = chars_out[:nc.value] if (chars_out is not None and len(chars_out) >= nc.value) else np.zeros(nc.value, np.uint8)
         self._ck(self.lib.dcu_get_corrected(self.ctx, _p(seg), _p(chars)))
         return seg, chars
 

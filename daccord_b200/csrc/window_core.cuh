@@ -841,10 +841,11 @@ DCU_BIG void gap_fill(Ctx& c, int lane) {
   }
   wsync();
   int nex = (int)bcast(*nexp, 0);
+  const int used = (int)bcast(w.hstate()[0], 0);     // one reading for the whole warp: the inserts below count up hstate[0] while slower lanes would still be comparing
   wsync();
   DCU_PEAK(4, nex);
   if (nex > DCU_CAP.EX) { c.overflow = 6; c.nex = 0; return; }
-  if ((int)w.hstate()[0] + nex >= (1 << c.logh) - 1) { c.overflow = 23; c.nex = 0; return; }      // the extras must leave a free slot in the table
+  if (used + nex >= (1 << c.logh) - 1) { c.overflow = 23; c.nex = 0; return; }      // the extras must leave a free slot in the table
   c.nex = nex;
   DCU_NOUNROLL
   for (int e = lane; e < nex; e += DCU_NL) hash_insert(c, w.ex_kmer()[e]);

@@ -63,6 +63,7 @@ ucontext_t g_sched;
 unsigned long long g_x[2][NL];        // double buffered exchange words: a lane can be at most one collective ahead of the slowest
 unsigned g_gen = 0; int g_arrived = 0;
 unsigned long long g_ncoll = 0;
+void* g_last_site[NL];                // call site of every lane's last collective (printed when the lanes deadlock)
 
 // what one lane runs
 struct LaneJob { dcu::Ctx c; dcus::Ctx cs; dcu::Window W; dcu::Result r; uint8_t* cons; uint8_t* ops; };
@@ -87,7 +88,7 @@ int emu_skip_sync_line = -1;
 __attribute__((noinline)) const unsigned long long* emu_xchg(unsigned long long v) {
   const int lane = g_cur; const unsigned g = g_gen;
   if (g_prof && lane == 0) ++(*g_prof)[__builtin_return_address(0)];      // DCU_EMU_PROFILE: collectives per call site
-  g_x[g & 1][lane] = v;
+  g_x[g & 1][lane] = v; g_last_site[lane] = __builtin_return_address(0);
   if (++g_arrived == NL) { g_arrived = 0; ++g_gen; ++g_ncoll; }
   else while (g_gen == g) TO_SCHED(lane);
   return g_x[g & 1];
@@ -169,7 +170,11 @@ extern "C" int emu_lanes_run_batch(const dcu_params* prm, const uint8_t* packed,
       j.cons = cons + i * DCU_CONS_STRIDE; j.ops = ops + i * DCU_OPS_STRIDE;
     }
     int rc = run_warp(schedule);
-    if (rc) { fprintf(stderr, "emu_lanes: window %lu: %s\n", (unsigned long)i, rc == 1 ? "deadlock: lanes diverged around a warp collective" : "lanes disagree on the result record"); return 100 + rc; }
+    if (rc) {
+      fprintf(stderr, "emu_lanes: window %lu: %s\n", (unsigned long)i, rc == 1 ? "deadlock: lanes diverged around a warp collective" : "lanes disagree on the result record");
+      if (rc == 1 && getenv("DCU_EMU_DEBUG")) { Dl_info di; dladdr((void*)&emu_lanes_run_batch, &di); for (int l = 0; l < NL; ++l) fprintf(stderr, "  lane %d finished %d last collective at +0x%lx\n", l, (int)g_fib[l].finished, (unsigned long)((char*)g_last_site[l] - (char*)di.dli_fbase)); }
+      return 100 + rc;
+    }
     memcpy(&res[i], &g_job[0].r, sizeof(dcu::Result));
     if (g_job[0].r.status == dcu::ST_OVERFLOW) ++nov;
   }

@@ -245,3 +245,16 @@ def test_product_has_no_oracle_or_cpu_path():
             if f.endswith((".cu", ".cuh", ".hpp", ".cpp", ".py", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r'#include\s*[<"][^>"]*oracle|liboracle|oracle_run|import\s+oracle|from\s+oracle', txt), f
+
+
+def test_gap_fill_table_check_is_uniform_across_lanes():
+    """found by tools/fuzz_parity.py (seed 5031): gap_fill compared hstate[0] + extras with the table size lane by lane while lanes that had
+    passed the check were already inserting extras (which counts hstate[0] up) -- slower lanes could take the overflow branch alone.  w = 59,
+    depth 60, k 7..8, filter frequencies down to 0: window 7 deadlocked the 32-lane emulation under every schedule."""
+    p = default_params(w=59, k_lo=7, k_hi=8, min_cov=3, max_ff=2, min_ff=0, p_i=0.12523667712661934, p_d=0.06831091479633782, est_cor=0.0, max_err=556)
+    e = 0.22770304932112606
+    packed, win, sl, _ = synth_batch(66, 60, seed=5031, w=59, p_ins=e * 0.55, p_del=e * 0.3, p_sub=e * 0.15, repeat_frac=0.6, depth_jitter=1)
+    ro = run_oracle(p, packed, win, sl, 4)
+    for sched in (0, 2):
+        rl = run_emu_lanes(p, packed, win, sl, 1, sched, 5031)
+        assert not compare_results(ro, rl)
