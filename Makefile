@@ -2,7 +2,8 @@
 # `daccord` command line, the host tools library and -- test infrastructure only -- the CPU oracle.
 # daccord_b200/build.py runs the same commands from Python (what __graft_entry__.build() calls).
 NVCC     ?= nvcc
-CXX      ?= /usr/bin/g++
+# (make predefines CXX = g++; in this image that is a wrapper without libgomp.spec, so the system compiler is named -- override with make CXX=...)
+CXX      := /usr/bin/g++
 B        := daccord_b200/_build
 CSRC     := daccord_b200/csrc
 NVFLAGS  := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-O3,-ffp-contract=off,-fopenmp -shared

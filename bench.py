@@ -344,9 +344,42 @@ def main():
         if keep_truth and rank == 0:
             # anchor outside the oracle: the corrected reads of the GPU path against the simulated genome (first reads of the shard)
             truth = ds.truth_eval(gfasta, max_read=info["shard"][0] + args.truth_reads)
+    # ---- the same with two batches in flight (one Engine each, as the command line keeps three): the window passes of the two contexts
+    # alternate on the GPU, piling and vote of one batch overlap the window kernel of the other; every step still copies its inputs in and
+    # its corrected bases out
+    pipe_wall = None
+    if gpu_pile and args.steps >= 2 and getattr(args, "pipelined", 1):
+        eng2 = d.Engine(params, local)
+        eng2.share_reads(eng)
+        chars_p2 = torch.empty(len(chars_p), dtype=torch.uint8).pin_memory().numpy()
+        eng2.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng2.launch(); eng2.vote(chars_out=chars_p2)      # warm-up of the second context
+        todo = list(range(args.steps)); lock = threading.Lock(); errs = []
+
+        def work(e, buf):
+            try:
+                while True:
+                    with lock:
+                        if not todo:
+                            return
+                        todo.pop()
+                    e.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign)
+                    e.launch()
+                    e.vote(chars_out=buf)
+            except Exception as ex:      # noqa: BLE001
+                errs.append(repr(ex))
+        barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(eng, chars_p)), threading.Thread(target=work, args=(eng2, chars_p2))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        barrier()
+        pipe_wall = None if errs else time.perf_counter() - t0
+        eng2.close()
     e2e_wall = full_wall if full_wall else desc_wall
 
-    vals = torch.tensor([tsec, e2e_wall, wall, pile_wall or 0.0, desc_wall], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([tsec, e2e_wall, wall, pile_wall or 0.0, desc_wall, pipe_wall or 0.0], dtype=torch.float64, device="cuda")
     cnts = torch.tensor([att, nwin, okw, corrected, launches, hard, alg_bytes, win.nbytes + sl.nbytes, res_p.numel() + cons_p.numel() + ops_p.numel(), second, lost,
                          ovl.nbytes + trace.nbytes + boff.nbytes + rlen.nbytes, full_d2h], dtype=torch.float64, device="cuda")
     per_rank = torch.zeros(world, dtype=torch.float64, device="cuda"); per_rank[rank] = tsec
@@ -355,7 +388,7 @@ def main():
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX); dist.all_reduce(cnts, op=dist.ReduceOp.SUM); dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
         dist.all_reduce(per_rank_att, op=dist.ReduceOp.SUM); dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    tsec_max, e2e_wall, wall, pile_wall_max, desc_wall_max = [float(x) for x in vals.tolist()]
+    tsec_max, e2e_wall, wall, pile_wall_max, desc_wall_max, pipe_wall_max = [float(x) for x in vals.tolist()]
     att_t, nwin_t, ok_t, corr_t, launches_t, hard_t, alg_t, h2d_desc, d2h_desc, second_t, lost_t, h2d_ovl, d2h_full = [float(x) for x in cnts.tolist()]
     if rank != 0:
         if dist is not None:
@@ -387,6 +420,8 @@ def main():
                 e2e=(None if not full_wall else {"value": att_t * args.steps / e2e_wall, "unit": "windows/s", "h2d_bytes_per_step": int(h2d_ovl), "d2h_bytes_per_step": int(d2h_full),
                                                  "what": "dcu_pile + dcu_launch + dcu_vote + dcu_get_corrected: overlaps and trace points in (pinned host memory), corrected bases out",
                                                  "corrected_mbp_per_s": corr_t * args.steps / e2e_wall / 1e6, "fasta_identical_to_host_vote": bool(flags[2].item()), "rank0_ms_per_step": e2e_parts}),
+                e2e_two_in_flight=(None if not pipe_wall_max else {"value": att_t * args.steps / pipe_wall_max, "unit": "windows/s",
+                                                                  "what": "the e2e path with two batches in flight per GPU (two contexts, one host thread each): every step still copies its overlaps in and its corrected bases out"}),
                 e2e_descriptors={"value": att_t * args.steps / desc_wall_max, "unit": "windows/s", "what": "dcu_run: window / slice descriptors in, result records + consensus + placement out",
                                  "h2d_bytes_per_step": int(h2d_desc), "d2h_bytes_per_step": int(d2h_desc), "results_identical": bool(flags[0].item())},
                 e2e_from_overlaps=(None if not pile_wall else {"value": att_t * args.steps / pile_wall_max, "unit": "windows/s", "what": "dcu_pile (trace reconstruction + slices on the GPU) + launch + download of the result records",

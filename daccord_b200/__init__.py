@@ -95,6 +95,10 @@ class Engine:
     def set_reads_device(self, dptr, nbytes):
         self._ck(self.lib.dcu_set_reads_device(self.ctx, C.c_void_p(dptr), C.c_uint64(nbytes)))
 
+    def share_reads(self, owner):
+        """use the read database of another Engine on the same device (several batches in flight: one Engine per batch)"""
+        self._ck(self.lib.dcu_share_reads(self.ctx, owner.ctx))
+
     def upload(self, win, sl):
         assert win.dtype == WINDOW_DT and sl.dtype == SLICE_DT
         self.nwin = len(win)

@@ -5,6 +5,7 @@ set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2z_pytest_gpu.log 2>&1; echo "pytest=$?"; tail -3 gpurun_out/r2z_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2z_smoke.log 2>&1; echo "smoke=$?"; tail -2 gpurun_out/r2z_smoke.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/r2z_memcheck.log 2>&1; echo "memcheck=$?"; grep -E "ERROR SUMMARY|pile" gpurun_out/r2z_memcheck.log | tail -2
 cuobjdump -elf daccord_b200/_build/libdaccord_b200.so | grep '\$_ZN' > gpurun_out/r2z_symbols.txt
 timeout 1500 python bench.py --steps 10 --warmup 5 2>gpurun_out/r2z_bench.err > gpurun_out/r2z_bench.json; echo "bench=$?"
 timeout 600 python bench.py --impl reference --steps 10 --warmup 5 2>gpurun_out/r2z_ref.err > gpurun_out/r2z_ref.json; echo "reference=$?"
