@@ -234,6 +234,8 @@ char* dh_format_segments(const dcu_segment* seg, uint64_t nseg, const char* char
   *outlen = out.size();
   return buf;
 }
+// banded edit distance of truth.hpp (tests: equal to the full DP when the band holds the optimal path, never below it)
+uint64_t dh_banded_distance(const char* a, uint64_t la, const char* b, uint64_t lb, int64_t W) { return banded_distance(std::string(a, la), std::string(b, lb), W); }
 // the four counts of an error profile file (binary as the reference writes it, or this repository's earlier text form)
 int dh_read_eprof(const char* fn, uint64_t* out4) { return read_eprof(fn, out4) ? 0 : 1; }
 void dh_free(void* p) { free(p); }
