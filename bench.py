@@ -305,7 +305,7 @@ def main():
     ovl, trace, boff, rlen = ds.overlaps(info["shard"][0], info["shard"][1], maxinput=args.maxinput)
     ovl_p = torch.from_numpy(ovl.view(np.uint8).copy()).pin_memory(); trace_p = torch.from_numpy(trace.view(np.uint8).copy()).pin_memory()
     ovl = ovl_p.numpy().view(ovl.dtype); trace = trace_p.numpy().view(np.uint16)
-    gpu_pile = args.w % args.a == 0
+    gpu_pile = ds.tspace <= 128
     pile_wall, pile_same = None, None
     if gpu_pile:
         eng.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng.launch(); eng.download(out)      # warm-up

@@ -162,10 +162,10 @@ int main(int argc, char** argv) {
     VoteParams VP; VP.producefull = producefull; VP.minlen = minlen;
     uint64_t wellcounter = 0, totwin = 0, totok = 0, totlost = 0;
     std::mutex mu; std::condition_variable cv; int64_t turn = 0; std::atomic<int64_t> next{0}; std::atomic<bool> failed{false}; std::string failmsg;
-    const bool gpu_pile = (prm.w % advance == 0) && las.tspace <= 128 && !getenv("DACCORD_HOST_PILE");
+    const bool gpu_pile = las.tspace <= 128 && !getenv("DACCORD_HOST_PILE");
     const bool gpu_vote = !getenv("DACCORD_HOST_VOTE");
     if (!gpu_pile && !getenv("DACCORD_HOST_PILE"))
-      fprintf(stderr, "[W] trace reconstruction and slice extraction run on the host for this input (the GPU piler needs w %% a == 0 and tspace <= 128; here w=%u a=%u tspace=%d)\n", prm.w, advance, las.tspace);
+      fprintf(stderr, "[W] trace reconstruction and slice extraction run on the host for this input (the GPU piler aligns trace tiles of at most 128 A bases; here tspace=%d)\n", las.tspace);
     auto fail = [&](const std::string& m) { std::lock_guard<std::mutex> g(mu); if (!failed.exchange(true)) failmsg = m; cv.notify_all(); };
     auto worker = [&](int wid) {
       dcu_ctx* ctx = ctxs[wid];

@@ -9,7 +9,7 @@
 //                      after every A position that a window boundary can fall on
 //   pile_order       : per A-read, its overlaps in pile order (escore<<32)|z
 //   pile_window      : per window, the pile (a pure function of the read's overlaps, see below) and its slices
-// Requirements of this path (checked by the host, which otherwise uses the host piler): w % a == 0, A tile <= 128.
+// Requirement of this path (checked by the host, which otherwise uses the host piler): A tile <= 128 (tspace <= 128).
 // The same source is compiled for the host (tests/emu, -DDCU_EMU) to check it against the host piler without a GPU.
 #pragma once
 #include <stdint.h>
@@ -36,7 +36,7 @@ struct Ovl {                     // one selected overlap (host order: by A-read,
   uint32_t ridx, pad;            // index of the A-read in the batch
 };
 struct ReadInfo { uint64_t ovl_begin, ovl_end; uint64_t win_off, sl_off; uint32_t maxaepos; uint32_t nwin, nsl; };   // win_off / nwin: index of the read's first candidate window / their number
-struct Params { int32_t tspace; uint32_t w, a; uint64_t maxalign; };
+struct Params { int32_t tspace; uint32_t w, a; uint64_t maxalign; };      // (window boundaries fall on p % a == 0 and, when w % a != 0, on p % a == w % a)
 
 PILE_FN uint8_t base_at(const uint8_t* packed, uint64_t boff, uint32_t len, uint32_t pos, bool comp) {
   uint32_t g = comp ? len - 1 - pos : pos;
@@ -44,12 +44,25 @@ PILE_FN uint8_t base_at(const uint8_t* packed, uint64_t boff, uint32_t len, uint
   return comp ? (uint8_t)(3 - b) : b;
 }
 
-// number of boundary entries of an overlap: A positions p in [abpos, aepos] with p % a == 0, plus two specials
-PILE_HD uint32_t bm_entries(int32_t abpos, int32_t aepos, uint32_t a) {
-  int64_t first = ((int64_t)abpos + a - 1) / a, last = (int64_t)aepos / a;
-  return (uint32_t)(last >= first ? last - first + 1 : 0) + 2;
+// Boundary entries of an overlap: the B offset is recorded at every A position p in [abpos, aepos] a window boundary can fall on -- window
+// starts are multiples of a, window ends are starts + w, i.e. p % a == 0 and (when w % a != 0) p % a == w % a -- plus two specials (l - w and
+// l of the read's final window).  Layout: [class 0 | class 1 | special0, special1].
+PILE_HD uint32_t bm_class_count(int32_t abpos, int32_t aepos, uint32_t a, uint32_t r) {      // positions p in [abpos, aepos] with p % a == r
+  const int64_t first = (int64_t)abpos + (int64_t)((r + a - (uint32_t)abpos % a) % a);
+  return first <= (int64_t)aepos ? (uint32_t)(((int64_t)aepos - first) / a + 1) : 0u;
 }
-PILE_FN uint32_t bm_index(int32_t abpos, uint32_t a, uint32_t p) { return (uint32_t)(p / a - ((uint32_t)abpos + a - 1) / a); }
+PILE_HD uint32_t bm_entries(int32_t abpos, int32_t aepos, uint32_t a, uint32_t w) {
+  const uint32_t r1 = w % a;
+  return bm_class_count(abpos, aepos, a, 0) + (r1 ? bm_class_count(abpos, aepos, a, r1) : 0u) + 2;
+}
+// index of boundary position p (p % a == 0 or p % a == w % a, abpos <= p <= aepos)
+PILE_FN uint32_t bm_index(int32_t abpos, int32_t aepos, uint32_t a, uint32_t w, uint32_t p) {
+  const uint32_t r1 = w % a, r = p % a;
+  const uint32_t first = (uint32_t)abpos + (r + a - (uint32_t)abpos % a) % a;
+  const uint32_t k = (p - first) / a;
+  return (r == 0 || r1 == 0) ? k : bm_class_count(abpos, aepos, a, 0) + k;
+}
+PILE_FN bool bm_is_boundary(uint32_t p, uint32_t a, uint32_t w) { const uint32_t r = p % a; return r == 0 || r == w % a; }
 
 PILE_FN void pile_tile_starts(const Ovl& o, const uint16_t* trace, uint32_t* tile_b) {
   uint32_t b = 0;
@@ -81,10 +94,10 @@ PILE_FN void pile_align_tile(const Ovl& o, int tile, const Params& P, const uint
   const uint64_t aoff = read_boff[o.aread], boff = read_boff[o.bread];
   const uint32_t alen = read_len[o.aread], blen = read_len[o.bread];
   const uint32_t base = tile_b[o.tile_off + tile];
-  const uint32_t nmul = bm_entries(o.abpos, o.aepos, P.a) - 2;
+  const uint32_t nmul = bm_entries(o.abpos, o.aepos, P.a, P.w) - 2;
   uint32_t* out = bm + o.bm_off;
   if (tile == 0) {
-    if ((uint32_t)x0 % P.a == 0) out[bm_index(o.abpos, P.a, (uint32_t)x0)] = 0;
+    if (bm_is_boundary((uint32_t)x0, P.a, P.w)) out[bm_index(o.abpos, o.aepos, P.a, P.w, (uint32_t)x0)] = 0;
     if (special0 == (uint32_t)x0) out[nmul] = 0;
     if (special1 == (uint32_t)x0) out[nmul + 1] = 0;
   }
@@ -115,7 +128,7 @@ PILE_FN void pile_align_tile(const Ovl& o, int tile, const Params& P, const uint
     if (step == 2) { --j; continue; }
     // the i-th A symbol of the tile is consumed by this step, which ends in column j
     const uint32_t p = (uint32_t)(x + i), v = base + (uint32_t)j;
-    if (p % P.a == 0) out[bm_index(o.abpos, P.a, p)] = v;
+    if (bm_is_boundary(p, P.a, P.w)) out[bm_index(o.abpos, o.aepos, P.a, P.w, p)] = v;
     if (p == special0) out[nmul] = v;
     if (p == special1) out[nmul + 1] = v;
     --i; if (step == 0) --j;
@@ -124,8 +137,8 @@ PILE_FN void pile_align_tile(const Ovl& o, int tile, const Params& P, const uint
 
 // B offset (relative to bbpos) once exactly p - abpos A symbols are consumed; p must be a recorded boundary
 PILE_FN uint32_t bm_lookup(const Ovl& o, const Params& P, const uint32_t* bm, uint32_t p, uint32_t special0, uint32_t special1) {
-  const uint32_t nmul = bm_entries(o.abpos, o.aepos, P.a) - 2;
-  if (p % P.a == 0) return bm[o.bm_off + bm_index(o.abpos, P.a, p)];
+  const uint32_t nmul = bm_entries(o.abpos, o.aepos, P.a, P.w) - 2;
+  if (bm_is_boundary(p, P.a, P.w)) return bm[o.bm_off + bm_index(o.abpos, o.aepos, P.a, P.w, p)];
   return bm[o.bm_off + nmul + (p == special0 ? 0 : 1)];
   (void)special1;
 }

@@ -19,7 +19,7 @@ struct Prep {
 
 inline bool prepare(const dcu_overlap* in, uint64_t novl, uint64_t ntrace, int32_t tspace, uint32_t w, uint32_t a, uint64_t nreads, const uint32_t* read_len, Prep& P) {
   if (tspace <= 0 || tspace > 128) { P.err = "tspace outside (0,128]"; return false; }
-  if (a == 0 || w % a != 0) { P.err = "GPU piling needs w % a == 0"; return false; }
+  if (a == 0) { P.err = "advance size 0"; return false; }
   P.ovl.resize(novl); P.reads.clear(); P.read_id.clear(); P.minerate.clear(); P.ediv.clear();
   uint64_t toff = 0, boff = 0;
   for (uint64_t i = 0; i < novl; ++i) {
@@ -31,7 +31,7 @@ inline bool prepare(const dcu_overlap* in, uint64_t novl, uint64_t ntrace, int32
     if (i && (in[i - 1].aread > s.aread || (in[i - 1].aread == s.aread && in[i - 1].abpos > s.abpos))) { P.err = "overlaps must be grouped by aread and ordered by abpos"; return false; }
     o.abpos = s.abpos; o.aepos = s.aepos; o.bbpos = s.bbpos; o.bread = s.bread; o.flags = s.flags; o.aread = s.aread; o.diffs = s.diffs;
     o.ntiles = (int32_t)nt; o.trace_off = s.trace_off; o.tile_off = toff; o.bm_off = boff;
-    toff += (uint64_t)nt; boff += bm_entries(s.abpos, s.aepos, a);
+    toff += (uint64_t)nt; boff += bm_entries(s.abpos, s.aepos, a, w);
     if (P.reads.empty() || P.read_id.back() != (uint32_t)s.aread) {
       ReadInfo R; R.ovl_begin = i; R.ovl_end = i; R.win_off = R.sl_off = 0; R.maxaepos = 0; R.nwin = R.nsl = 0;
       P.reads.push_back(R); P.read_id.push_back((uint32_t)s.aread);

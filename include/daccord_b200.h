@@ -92,7 +92,7 @@ int dcu_upload(dcu_ctx* ctx, const dcu_window* win, uint64_t nwin, const dcu_sli
 int dcu_launch(dcu_ctx* ctx, float* kernel_ms);   /* runs the resident batch; kernel_ms may be NULL */
 int dcu_download(dcu_ctx* ctx, dcu_result* res, uint8_t* cons, uint8_t* ops);
 /* ---- caller stage on the GPU: trace reconstruction + window / slice extraction --------------------
- * Replaces, for w % a == 0 and tspace <= 128, the host work of reference src/HandleContext.hpp:1740-2049
+ * Replaces, for tspace <= 128 (any -w / -a), the host work of reference src/HandleContext.hpp:1740-2049
  * (OverlapDataInterface::computeTrace per activated overlap, advanceA / getStringLengthUsed per window, the active set
  * ordered by (escore<<32)|z).  Input: the overlaps the caller selected for its A-reads (reference
  * src/daccord.cpp:2112-2288: top -D by score, ordered by abpos), grouped by A-read in ascending order, with their

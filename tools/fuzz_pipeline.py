@@ -37,7 +37,7 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         while time.time() - t0 < budget:
             rng = np.random.default_rng(seed)
-            w, a = [(40, 10), (40, 10), (40, 5), (40, 20), (32, 8), (48, 12), (56, 14), (24, 24), (16, 4)][int(rng.integers(0, 9))]
+            w, a = [(40, 10), (40, 10), (40, 5), (40, 20), (32, 8), (48, 12), (56, 14), (24, 24), (16, 4), (40, 7), (40, 15), (33, 10), (59, 13)][int(rng.integers(0, 13))]
             glen = int(rng.integers(1500, 9000)); rl = int(rng.integers(400, 2600)); cov = float(rng.integers(4, 28))
             e = float(rng.uniform(0.04, 0.2))
             ds = Dataset.simulate(glen, read_len=rl, coverage=cov, seed=seed, repeat_frac=float(rng.choice([0.0, 0.0, 0.3])), min_ovl=int(rng.integers(150, 600)),
