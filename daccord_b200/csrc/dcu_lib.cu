@@ -478,7 +478,6 @@ int dcu_create(const dcu_params* p, int device, dcu_ctx** out) {
   ctx->P.w = (int)p->w; ctx->P.k_lo = (int)p->k_lo; ctx->P.k_hi = (int)p->k_hi; ctx->P.minff = p->min_ff; ctx->P.maxff = p->max_ff;
   ctx->P.mincov = (int)p->min_cov; ctx->P.check = p->est_cor != 0.0; ctx->P.eminrate = p->max_err; ctx->P.defer_ff = 0;
   { const char* e = getenv("DCU_POSCACHE"); ctx->P.poscache = e ? atoi(e) : 1; }
-  { const char* e = getenv("DCU_SPFLAT"); ctx->P.spflat = e ? atoi(e) : 1; }
   CK(ctx->dcnt.ensure(16));
   // First pass: the HBM build by default.  The shared-memory build (graph in shared memory, slices staged by bulk copies) is complete and
   // parity-tested but measured slower on B200 (12-16 resident warps per SM against 32: profiles/r02_summary.md); DCU_SMEM=1 selects it.

@@ -1082,54 +1082,7 @@ template <bool SM> DCU_FN void sp_view_t(const Ctx& c, int off, int L, int nr, i
     if (q < nr) { RSlot r; r.w = ar ? sumr : -1.0; r.wf = wfr; w.scs()[cO + q] = r; }
   }
 }
-// The same for views with at most 32 anchor positions (nearly all), in two phases so that all lanes work: (A) the weights of (link, position)
-// pairs, one pair per lane -- a view of 3 links x 20 positions fills two warp passes instead of three at 60 % -- staged in a scratch array
-// (the sort keys of derive_stretches, idle here); (B) lane q adds up its column in link order.  Same weights, same order of the sums.
-#if DCU_NL == 32
-template <bool SM> DCU_FN void sp_view_flat(const Ctx& c, int off, int L, int nr, int br, uint32_t cO, int lane) {
-  const WS w = c.ws;
-  const int NP = DCU_T.NP, MS = DCU_T.MS;
-  double* stg = (double*)w.skey();
-  const int lc = DCU_CAP.STP / nr;                     // links per chunk (nr <= 32 <= STP)
-  const uint32_t inv = (uint32_t)((0x100000000ull + (unsigned long long)nr - 1ull) / (unsigned long long)nr);      // it / nr == (it * inv) >> 32 for it, nr < 2^16
-  bool ar = lane < nr;
-  double sumr = 0.0, wfr = 0.0;
-  DCU_NOUNROLL
-  for (int j0 = 0; j0 < L; j0 += lc) {
-    const int jn = L - j0 < lc ? L - j0 : lc, T = jn * nr;
-    DCU_NOUNROLL
-    for (int it = lane; it < T; it += DCU_NL) {
-      const int t = (int)(((unsigned long long)(uint32_t)it * inv) >> 32), q = it - t * nr, jj = j0 + t;
-      const int n = w.slinks()[off + L - 1 - jj];
-      const int p = br + q + jj;
-      double wt = 0.0;
-      if (p < NP) wt = (double)inst_colsum<SM>(c, w.irpos() + w.n_ioff()[n], (int)w.n_freq()[n], p, NP, MS) * 2.3283064365386963e-10;
-      stg[it] = wt;
-    }
-    wsync();
-    DCU_NOUNROLL
-    for (int t = 0; t < jn; ++t) {
-      if (ar) {
-        const double wt = stg[t * nr + lane];
-        if (wt >= 1e-3) { sumr += wt; if (j0 + t == 0) wfr = wt; } else ar = false;
-      }
-    }
-    wsync();                                           // the staging array is rewritten by the next chunk
-    if (!ballot(ar)) break;                            // nothing feasible left
-  }
-  if (lane < nr) { RSlot r; r.w = ar ? sumr : -1.0; r.wf = wfr; w.scs()[cO + lane] = r; }
-}
-#endif
 DCU_NOINL void sp_view(const Ctx& c, int off, int L, int nr, int br, uint32_t cO, int lane) {
-#if DCU_NL == 32
-  if (DCU_P.spflat && nr >= 1 && nr <= DCU_NL) {
-#ifndef DCU_EMU
-    if (c.vs_sm) { sp_view_flat<true>(c, off, L, nr, br, cO, lane); return; }
-#endif
-    sp_view_flat<false>(c, off, L, nr, br, cO, lane);
-    return;
-  }
-#endif
 #ifndef DCU_EMU
   if (c.vs_sm) { sp_view_t<true>(c, off, L, nr, br, cO, lane); return; }
 #endif

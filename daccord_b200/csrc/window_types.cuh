@@ -145,7 +145,6 @@ struct Params {
   int w, k_lo, k_hi, minff, maxff, mincov, check;   // check = (est_cor != 0)  (DebruijnGraph.hpp:1832-1837)
   unsigned long long eminrate;
   int defer_ff;                                      // experimental (DCU_DEFER_FF, first pass only): hand windows whose first filter frequency fails to the second pass
-  int spflat;                                        // reverse slots of a view by (link, position) pairs in two phases (DCU_SPFLAT=0: one link at a time, lanes over positions; results identical)
   int poscache;                                      // keep the position weights of unsplit unitigs across the (first,last) pairs of a traverse (DCU_POSCACHE=0 turns it off; results identical)
 };
 // capacities of one warp's workspace (two tiers: small for the common case, large for the rest)

@@ -42,8 +42,7 @@ inline void params_for(const dcu_params* prm, int tier, dcu::Params& P) {
   P.w = (int)prm->w; P.k_lo = (int)prm->k_lo; P.k_hi = (int)prm->k_hi; P.minff = prm->min_ff; P.maxff = prm->max_ff;
   P.mincov = (int)prm->min_cov; P.check = prm->est_cor != 0.0; P.eminrate = prm->max_err;
   P.defer_ff = (tier == 0 && getenv("DCU_DEFER_FF")) ? 1 : 0;
-  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }
-  { const char* e = getenv("DCU_SPFLAT"); P.spflat = e ? atoi(e) : 1; }        // same experimental switch as the library's first pass
+  { const char* e = getenv("DCU_POSCACHE"); P.poscache = e ? atoi(e) : 1; }        // same experimental switch as the library's first pass
 }
 inline void tables_for(const dcu_host::HostTables& HT, dcu::Tables& T) {
   T.DPn = HT.DPn.data(); T.DPsq = HT.DPsq.data(); T.VSq = HT.VSq.data(); T.suplo = HT.suplo.data(); T.suphi = HT.suphi.data();
