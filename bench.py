@@ -349,34 +349,38 @@ def main():
     # its corrected bases out
     pipe_wall = None
     if gpu_pile and args.steps >= 2 and getattr(args, "pipelined", 1):
-        eng2 = d.Engine(params, local)
-        eng2.share_reads(eng)
-        chars_p2 = torch.empty(len(chars_p), dtype=torch.uint8).pin_memory().numpy()
-        eng2.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng2.launch(); eng2.vote(chars_out=chars_p2)      # warm-up of the second context
-        todo = list(range(args.steps)); lock = threading.Lock(); errs = []
+        try:
+            eng2 = d.Engine(params, local)
+            eng2.share_reads(eng)
+            chars_p2 = torch.empty(len(chars_p), dtype=torch.uint8).pin_memory().numpy()
+            eng2.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign); eng2.launch(); eng2.vote(chars_out=chars_p2)      # warm-up of the second context
+            todo = list(range(args.steps)); lock = threading.Lock(); errs = []
 
-        def work(e, buf):
-            try:
-                while True:
-                    with lock:
-                        if not todo:
-                            return
-                        todo.pop()
-                    e.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign)
-                    e.launch()
-                    e.vote(chars_out=buf)
-            except Exception as ex:      # noqa: BLE001
-                errs.append(repr(ex))
-        barrier()
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=work, args=(eng, chars_p)), threading.Thread(target=work, args=(eng2, chars_p2))]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        barrier()
-        pipe_wall = None if errs else time.perf_counter() - t0
-        eng2.close()
+            def work(e, buf):
+                try:
+                    while True:
+                        with lock:
+                            if not todo:
+                                return
+                            todo.pop()
+                        e.pile(ovl, trace, ds.tspace, boff, rlen, advance=args.a, maxalign=maxalign)
+                        e.launch()
+                        e.vote(chars_out=buf)
+                except Exception as ex:      # noqa: BLE001
+                    errs.append(repr(ex))
+            torch.cuda.synchronize()               # (no collective inside this guarded leg: a rank that skips it must not leave the others waiting)
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=work, args=(eng, chars_p)), threading.Thread(target=work, args=(eng2, chars_p2))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            pipe_wall = None if errs else time.perf_counter() - t0
+            eng2.close()
+        except Exception as ex:      # noqa: BLE001 -- an extra leg must never cost the line
+            pipe_wall = None
+            print("two-in-flight leg skipped: %r" % (ex,), file=sys.stderr)
     e2e_wall = full_wall if full_wall else desc_wall
 
     vals = torch.tensor([tsec, e2e_wall, wall, pile_wall or 0.0, desc_wall, pipe_wall or 0.0], dtype=torch.float64, device="cuda")
